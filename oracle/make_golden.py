@@ -1,0 +1,220 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference on CPU.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU
+box):      python -m oracle.make_golden
+The reference modules are imported from /root/reference (never copied); the MV-selection
+block, which is inline script code (reference main.py:209-292), is executed by slicing the
+reference file's own text at run time.  Documented deviations applied here: stable argsort
+for the rank fusion (ii) and dropout = 0 (iii).  Inputs are synthetic (pfotgnrec_b200.synth).
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _import_reference():
+    sys.dont_write_bytecode = True
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from model.tgn import TGN                       # noqa: E402
+    from utils.utils import get_neighbor_finder, RandEdgeSampler   # noqa: E402
+    return TGN, get_neighbor_finder, RandEdgeSampler
+
+
+def _data(stream, sl=slice(None)):
+    return types.SimpleNamespace(sources=stream.sources[sl], destinations=stream.destinations[sl],
+                                 edge_idxs=stream.edge_idxs[sl], timestamps=stream.timestamps[sl])
+
+
+def golden_neighbors(get_neighbor_finder):
+    from pfotgnrec_b200.synth import make_stream
+    out = {}
+    for name, mode in (("small", "small"), ("nbg", "nbg")):
+        st = make_stream(n_users=50, n_items=10, n_events=600, n_days=20, seed=3, ts_mode=mode,
+                         with_prices=False)
+        nf = get_neighbor_finder(_data(st), uniform=False, max_node_idx=st.n_nodes - 1)
+        rng = np.random.default_rng(5)
+        Q = 300
+        nodes = rng.integers(0, st.n_nodes, size=Q)
+        # half of the cut times coincide with event times (ties), the rest fall in between
+        ts = st.timestamps[rng.integers(0, st.n_events, size=Q)].copy()
+        ts[::2] += rng.integers(-2, 3, size=ts[::2].shape[0])
+        ts[:5] = [0, st.timestamps[0], st.timestamps[-1] + 1, -5, st.timestamps[-1]]
+        for n in (10, 3, 1):
+            nb, ei, et = nf.get_temporal_neighbor(nodes, ts, n_neighbors=n)
+            out[f"{name}_n{n}_nbr"], out[f"{name}_n{n}_eidx"], out[f"{name}_n{n}_etime"] = nb, ei, et
+        out[f"{name}_nodes"], out[f"{name}_ts"] = nodes, ts
+        for k in ("sources", "destinations", "edge_idxs", "timestamps"):
+            out[f"{name}_{k}"] = getattr(st, k)
+        out[f"{name}_n_nodes"] = st.n_nodes
+    np.savez_compressed(os.path.join(OUT, "neighbors.npz"), **out)
+    print("neighbors.npz", len(out))
+
+
+def _run_model(TGN, get_neighbor_finder, tag, *, d, n_layers, n_neighbors, use_memory, updater,
+               embedding, dyrep, dst_emb, ts_mode, with_ppos, B=24, n_batches=4, n_neg=3, seed=11):
+    from pfotgnrec_b200.synth import make_stream
+    st = make_stream(n_users=40, n_items=12, n_events=B * n_batches + 40, n_days=10, seed=seed,
+                     ts_mode=ts_mode, with_prices=False)
+    rng = np.random.default_rng(seed + 1)
+    torch.manual_seed(seed)
+    node_feat = rng.random((st.n_nodes, d))
+    nf = get_neighbor_finder(_data(st), uniform=False, max_node_idx=st.n_nodes - 1)
+    shift = (3.0, 7.0, 2.0, 5.0)
+    tgn = TGN(neighbor_finder=nf, node_features=node_feat, edge_features=st.edge_features.copy(),
+              device=torch.device("cpu"), n_layers=n_layers, n_heads=2, dropout=0.0,
+              use_memory=use_memory, message_dimension=100, memory_dimension=d,
+              memory_update_at_start=True, embedding_module_type=embedding,
+              message_function="identity", aggregator_type="last", memory_updater_type=updater,
+              n_neighbors=n_neighbors, mean_time_shift_src=shift[0], std_time_shift_src=shift[1],
+              mean_time_shift_dst=shift[2], std_time_shift_dst=shift[3],
+              use_destination_embedding_in_message=dst_emb, use_source_embedding_in_message=False,
+              dyrep=dyrep)
+    tgn.train()
+    out = {"cfg_" + k: v for k, v in dict(d=d, n_layers=n_layers, n_neighbors=n_neighbors,
+                                          use_memory=int(use_memory), B=B, n_batches=n_batches,
+                                          n_neg=n_neg, dyrep=int(dyrep), dst_emb=int(dst_emb),
+                                          with_ppos=int(with_ppos)).items()}
+    out["cfg_updater"], out["cfg_embedding"] = updater, embedding
+    out["cfg_shift"] = np.array(shift)
+    skip = ("memory.memory", "memory.last_update", "memory_updater.memory.", "embedding_module.memory.")
+    for k, v in tgn.state_dict().items():
+        if not any(k.startswith(s) or k == s for s in skip):
+            out["w_" + k] = v.detach().numpy().copy()
+    out["node_feat"] = node_feat
+    for k in ("sources", "destinations", "edge_idxs", "timestamps", "edge_features"):
+        out["st_" + k] = getattr(st, k)
+    out["st_n_nodes"] = st.n_nodes
+    params = [p for p in tgn.parameters() if p.requires_grad]
+    names = [k for k, p in tgn.named_parameters() if p.requires_grad]
+    for bi in range(n_batches):
+        sl = slice(bi * B, (bi + 1) * B)
+        src, dst = st.sources[sl], st.destinations[sl]
+        ts, ei = st.timestamps[sl], st.edge_idxs[sl]
+        neg = rng.integers(st.n_users + 1, st.n_nodes, size=B * n_neg)
+        for p in params:
+            p.grad = None
+        if with_ppos:
+            ppos = rng.integers(st.n_users + 1, st.n_nodes, size=B)
+            e_s, e_d, e_p, e_n = tgn.compute_temporal_embeddings_p(src, dst, ppos, neg, ts, ei, n_neighbors)
+            out[f"b{bi}_ppos"] = ppos
+            out[f"b{bi}_emb_ppos"] = e_p.detach().numpy().copy()
+        else:
+            e_s, e_d, e_n = tgn.compute_temporal_embeddings(src, dst, neg, ts, ei, n_neighbors)
+            e_p = e_d
+        # BPR exactly as reference main.py:321-337
+        bs = e_s.shape[0]
+        s_ = e_s.view(bs, 1, -1)
+        pos_scores = torch.sum(s_ * e_p.view(bs, 1, -1), dim=2)
+        neg_scores = torch.matmul(s_, e_n.view(bs, n_neg, -1).transpose(1, 2)).squeeze()
+        loss = -torch.mean(torch.log(torch.sigmoid(torch.mean(pos_scores - neg_scores, dim=1))))
+        if dyrep:
+            loss.requires_grad_()
+        loss.backward()
+        if use_memory:
+            tgn.memory.detach_memory()
+        out[f"b{bi}_neg"] = neg
+        out[f"b{bi}_emb_src"] = e_s.detach().numpy().copy()
+        out[f"b{bi}_emb_dst"] = e_d.detach().numpy().copy()
+        out[f"b{bi}_emb_neg"] = e_n.detach().numpy().copy()
+        out[f"b{bi}_loss"] = float(loss.item())
+        for k, p in zip(names, params):
+            out[f"b{bi}_g_{k}"] = (p.grad.detach().numpy().copy() if p.grad is not None
+                                   else np.zeros(tuple(p.shape), dtype=np.float32))
+        if use_memory:
+            out[f"b{bi}_memory"] = tgn.memory.memory.detach().numpy().copy()
+            out[f"b{bi}_last_update"] = tgn.memory.last_update.detach().numpy().copy()
+            N = st.n_nodes
+            raw = 3 * d + st.edge_features.shape[1]
+            pv = np.zeros(N, dtype=bool)
+            pm = np.zeros((N, raw), dtype=np.float32)
+            pt = np.zeros(N, dtype=np.float32)
+            for node, lst in tgn.memory.messages.items():
+                if len(lst) > 0:
+                    pv[node] = True
+                    pm[node] = lst[-1][0].detach().numpy()
+                    pt[node] = float(lst[-1][1])
+            out[f"b{bi}_pend_valid"], out[f"b{bi}_pend_msg"], out[f"b{bi}_pend_ts"] = pv, pm, pt
+    np.savez_compressed(os.path.join(OUT, f"tgn_{tag}.npz"), **out)
+    print(f"tgn_{tag}.npz", len(out))
+
+
+def golden_mv_select(RandEdgeSampler):
+    """Run the reference's inline MV block (main.py:209-292) on a synthetic batch."""
+    import scipy.stats as stats
+    from pfotgnrec_b200.synth import make_stream
+    st = make_stream(n_users=80, n_items=60, n_events=400, n_days=12, seed=21, ts_mode="nbg")
+    lines = open(os.path.join(REF, "main.py")).read().split("\n")
+    block = "\n".join(lines[204:292])        # main.py:205-292: p_pos_batch=[] ... p_neg_batch.append
+    block = "\n".join(l[8:] if l.startswith("        ") else l for l in block.split("\n"))
+    code_of = dict(enumerate(st.codes))
+    idx_of = {c: k for k, c in code_of.items()}
+    time_feature = {dk: {c: st.prices_future[di, k] for k, c in enumerate(st.codes)}
+                    for di, dk in enumerate(st.day_keys)}
+    rng = np.random.default_rng(22)
+    out = {}
+    for ci, (lam, gamma, K) in enumerate(((0.5, 2.0, 20), (0.1, 2.0, 20), (0.9, 3.0, 7))):
+        B = 64
+        sl = slice(ci * B, (ci + 1) * B)
+        cand = np.concatenate([(st.destinations[sl] - st.n_users - 1)[:, None],
+                               rng.integers(0, st.n_items, size=(B, K))], axis=1)
+        if ci == 0:
+            cand[:8, 3] = cand[:8, 0]        # the positive can be drawn as a negative (exact ties)
+        portfolios = [[st.codes[k] for k in st.portfolio(e)] or [""] for e in range(sl.start, sl.stop)]
+        for stable in (True, False):
+            ns = {"np": np if not stable else _StableNumpy(), "stats": stats,
+                  "args": types.SimpleNamespace(gamma=gamma, lambda_mv=lam, p_pos_num=1, p_neg_num=3),
+                  "time_feature": time_feature,
+                  "portfolios_batch": np.array(portfolios, dtype=object),
+                  "sources_batch": st.sources[sl], "timestamps_batch": st.timestamps[sl],
+                  "destinations_batch": np.vectorize(code_of.get)(cand[:, 0]),
+                  "negatives_batch": np.vectorize(code_of.get)(cand[:, 1:])}
+            exec(block, ns)
+            pp = np.array([idx_of[c] for y in ns["p_pos_batch"] for c in y])
+            pn = np.array([idx_of[c] for y in ns["p_neg_batch"] for c in y])
+            tag = "stable" if stable else "unstable"
+            out[f"c{ci}_ppos_{tag}"], out[f"c{ci}_pneg_{tag}"] = pp, pn
+        out[f"c{ci}_cand"], out[f"c{ci}_lam"], out[f"c{ci}_gamma"] = cand, lam, gamma
+        out[f"c{ci}_event0"] = sl.start
+    for k in ("day_idx", "port_ptr", "port_items", "prices_future"):
+        out["st_" + k] = getattr(st, k)
+    np.savez_compressed(os.path.join(OUT, "mv_select.npz"), **out)
+    print("mv_select.npz", len(out))
+
+
+class _StableNumpy:
+    """numpy with argsort(kind='stable') -- documented deviation (ii)."""
+
+    def __getattr__(self, name):
+        if name == "argsort":
+            return lambda a, *args, **kw: np.argsort(a, *args, kind="stable", **kw)
+        return getattr(np, name)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    TGN, get_neighbor_finder, RandEdgeSampler = _import_reference()
+    golden_neighbors(get_neighbor_finder)
+    common = dict(n_layers=1, n_neighbors=10, use_memory=True, updater="gru",
+                  embedding="graph_attention", dyrep=False, dst_emb=False)
+    _run_model(TGN, get_neighbor_finder, "ours", d=64, ts_mode="small", with_ppos=True, **common)
+    _run_model(TGN, get_neighbor_finder, "ours_nbg", d=32, ts_mode="nbg", with_ppos=True,
+               n_batches=2, **common)
+    _run_model(TGN, get_neighbor_finder, "tgn", d=32, ts_mode="small", with_ppos=False, **common)
+    _run_model(TGN, get_neighbor_finder, "jodie", d=32, ts_mode="small", with_ppos=False,
+               **{**common, "updater": "rnn", "embedding": "time"})
+    _run_model(TGN, get_neighbor_finder, "dyrep", d=32, ts_mode="small", with_ppos=False,
+               **{**common, "updater": "rnn", "dyrep": True, "dst_emb": True})
+    _run_model(TGN, get_neighbor_finder, "tgat2", d=32, ts_mode="small", with_ppos=False,
+               **{**common, "use_memory": False, "n_layers": 2, "n_neighbors": 5})
+    golden_mv_select(RandEdgeSampler)
+
+
+if __name__ == "__main__":
+    main()

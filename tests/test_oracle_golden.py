@@ -1,0 +1,72 @@
+"""The oracle against vectors produced by the unmodified reference (CPU, no GPU needed)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden, oracle_from_golden, rel_err, batch_inputs
+from oracle.graph import AdjacencyOracle
+from oracle.tgn import bpr_loss
+from oracle import sampling
+
+TOL = 1e-5   # fp32 contract of BASELINE.json north_star
+
+
+@pytest.mark.parametrize("name", ["small", "nbg"])
+@pytest.mark.parametrize("n", [10, 3, 1])
+def test_neighbors_bit_exact(name, n):
+    z = load_golden("neighbors.npz")
+    adj = AdjacencyOracle(z[f"{name}_sources"], z[f"{name}_destinations"], z[f"{name}_edge_idxs"],
+                          z[f"{name}_timestamps"], n_nodes=int(z[f"{name}_n_nodes"]))
+    nb, ei, et = adj.get_temporal_neighbor(z[f"{name}_nodes"], z[f"{name}_ts"], n)
+    assert np.array_equal(nb, z[f"{name}_n{n}_nbr"])
+    assert np.array_equal(ei, z[f"{name}_n{n}_eidx"])
+    assert np.array_equal(et, z[f"{name}_n{n}_etime"])
+    assert nb.dtype == np.int32 and ei.dtype == np.int32 and et.dtype == np.float32
+
+
+@pytest.mark.parametrize("tag", ["ours", "ours_nbg", "tgn", "jodie", "dyrep", "tgat2"])
+def test_model_path_matches_reference(tag):
+    z = load_golden(f"tgn_{tag}.npz")
+    o, p = oracle_from_golden(z)
+    n = int(z["cfg_n_neighbors"])
+    for bi in range(int(z["cfg_n_batches"])):
+        src, dst, extra, ts, ei = batch_inputs(z, bi)
+        for v in p.values():
+            v.grad = None
+        outs = o.compute_temporal_embeddings(src, dst, extra, ts, ei, n)
+        names = ["src", "dst"] + (["ppos"] if len(extra) == 2 else []) + ["neg"]
+        for nm, e in zip(names, outs):
+            assert rel_err(e.detach().numpy(), z[f"b{bi}_emb_{nm}"]) < TOL, (tag, bi, nm)
+        e_pos = outs[2] if len(extra) == 2 else outs[1]
+        loss = bpr_loss(outs[0], e_pos, outs[-1])
+        assert abs(loss.item() - float(z[f"b{bi}_loss"])) < TOL * max(1.0, abs(float(z[f"b{bi}_loss"])))
+        if loss.requires_grad:
+            loss.backward()
+        for k, v in p.items():
+            g = v.grad.numpy() if v.grad is not None else np.zeros(tuple(v.shape), np.float32)
+            key = f"b{bi}_g_{k}"
+            if key in z:
+                ref = z[key]
+                assert np.abs(g - ref).max() <= 2e-5 * max(np.abs(ref).max(), 1e-3) + 1e-7, (tag, bi, k)
+        if bool(z["cfg_use_memory"]):
+            assert rel_err(o.memory.numpy(), z[f"b{bi}_memory"]) < TOL
+            assert np.array_equal(o.last_update.numpy(), z[f"b{bi}_last_update"])
+            assert np.array_equal(o.pend_valid.numpy(), z[f"b{bi}_pend_valid"])
+            v = z[f"b{bi}_pend_valid"]
+            assert np.array_equal(o.pend_ts.numpy()[v], z[f"b{bi}_pend_ts"][v])
+            assert rel_err(o.pend_msg.numpy()[v], z[f"b{bi}_pend_msg"][v]) < TOL
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2])
+def test_mv_select_ids_bit_exact(ci):
+    from pfotgnrec_b200.synth import log_returns
+    z = load_golden("mv_select.npz")
+    cand = z[f"c{ci}_cand"]
+    B = cand.shape[0]
+    e0 = int(z[f"c{ci}_event0"])
+    ptr = z["st_port_ptr"][e0:e0 + B + 1]
+    pp, pn = sampling.mv_select(log_returns(z["st_prices_future"]), z["st_day_idx"][e0:e0 + B], cand,
+                                ptr - ptr[0], z["st_port_items"][ptr[0]:ptr[-1]],
+                                float(z[f"c{ci}_gamma"]), float(z[f"c{ci}_lam"]))
+    assert np.array_equal(pp, z[f"c{ci}_ppos_stable"])
+    assert np.array_equal(pn, z[f"c{ci}_pneg_stable"])
