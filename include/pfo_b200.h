@@ -1,0 +1,165 @@
+/* pfo_b200.h -- C ABI of the B200-native PfoTGNRec hot path (libpfo_b200.so).
+ *
+ * Drop-in boundary: the reference has no FFI of its own -- its
+ * boundary is the Python import surface of model/tgn.py, modules/*.py and utils/utils.py.
+ * The host side (pfotgnrec_b200/overlay/*) mirrors those classes and binds the entry points
+ * below through ctypes.  Every function:
+ *   - takes plain device pointers and sizes (no torch types); the caller owns every buffer;
+ *   - is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - returns 0 on success, else the cudaError_t of the failed launch / bad argument;
+ *   - keeps no global state and makes no hidden allocation.
+ * "file:line" cites the reference code each entry point replaces (paths relative to the
+ * reference repository root).
+ */
+#ifndef PFO_B200_H
+#define PFO_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFO_ABI_VERSION 1
+int pfo_abi_version(void);
+
+/* ---- K1: temporal neighbour sampling --- utils/utils.py:150-161 (find_before) and
+ * :163-220 (get_temporal_neighbor); the Python loop over queries with np.searchsorted.
+ * CSR adjacency sorted by (node, timestamp, stream order): rowptr[N+1], adj_nbr/adj_eidx/adj_ts[2E].
+ * Outputs are [Q, n] row-major, right-aligned / left zero-padded; out_dt = fp32(t - fp32(edge time))
+ * (modules/embedding_module.py:133-135).  uniform != 0 selects the uniform-with-replacement mode
+ * (:193-204) driven by the shared Philox stream (counter = (query, call_id, slot, 3)). */
+int pfo_neighbor_sample(const int64_t* rowptr, const int32_t* adj_nbr, const int32_t* adj_eidx,
+                        const double* adj_ts, const int32_t* q_nodes, const double* q_ts,
+                        int64_t n_queries, int n_neighbors, int uniform, uint64_t seed, uint32_t call_id,
+                        int32_t* out_nbr, int32_t* out_eidx, float* out_etime, float* out_dt, void* stream);
+
+/* ---- touched-node compaction (replaces the O(n_nodes) clone + Python loop of
+ * modules/memory_updater.py:46-51 and modules/message_aggregator.py:40-50: only nodes read
+ * in this batch are updated).  mark: set bit `id` for every id >= 0 (ids == 0 are skipped when
+ * skip_zero != 0: node 0 is padding).  compact: ascending unique ids, slot_of_node[id] = rank,
+ * *n_unique = count; the bitmap is left zeroed. */
+int pfo_mark_nodes(const int32_t* ids, int64_t count, int skip_zero, uint32_t* bitmap, void* stream);
+int64_t pfo_compact_workspace_ints(int64_t n_nodes);
+int pfo_compact_nodes(uint32_t* bitmap, int64_t n_nodes, int32_t* workspace, int32_t* uniq_ids,
+                      int32_t* slot_of_node, int32_t* n_unique, void* stream);
+int pfo_map_slots(const int32_t* ids, int64_t count, int skip_zero, const int32_t* slot_of_node,
+                  int32_t* out, void* stream);
+
+/* ---- dense contractions, exact fp32 --- torch.nn.GRUCell / RNNCell (modules/memory_updater.py:31,47,
+ * 60,68), nn.MultiheadAttention projections (model/temporal_attention.py:26-32,70), MergeLayer
+ * (utils/utils.py:4-17).  C[m,:N] = epi(alpha * (A[row(m),:K] . W^T + bias * brs[m])), row(m) = a_idx ?
+ * a_idx[m] : m (negative -> zero row); W(n,k) = w_transposed ? W[k*ldw+n] : W[n*ldw+k]; act 1 = relu;
+ * rows with row_zero[m] != 0 are written as zero; outputs where relu_gate <= 0 are zeroed;
+ * accumulate adds into C.  m_dev (optional) holds the live row count on the device. */
+int pfo_linear_f32(const float* A, int64_t lda, const int32_t* a_idx, const float* W, int64_t ldw,
+                   int w_transposed, const float* bias, const float* bias_row_scale, int64_t ld_brs,
+                   float* C, int64_t ldc, int64_t M, const int32_t* m_dev, int N, int K,
+                   float alpha, int act, const int32_t* row_zero, const float* relu_gate, int64_t ld_gate,
+                   int accumulate, void* stream);
+/* dW[n,k] = sum_m G[m,n] * A[row(m),k]; db[n] = sum_m G[m,n] (db may be null); two-stage,
+ * deterministic reduction through `workspace` (pfo_wgrad_workspace_floats floats). */
+int64_t pfo_wgrad_workspace_floats(int64_t M, int N, int K, int with_bias);
+int pfo_wgrad_f32(const float* G, int64_t ldg, const float* A, int64_t lda, const int32_t* a_idx,
+                  int64_t M, const int32_t* m_dev, int N, int K, float* dW, int64_t lddw, float* db,
+                  int accumulate, float* workspace, void* stream);
+/* same contract as pfo_linear_f32 with bf16 operands / fp32 accumulation on tcgen05 tensor cores
+ * (TMEM accumulators); selected by the host when gemm_mode == "bf16" (2e-2 contract). */
+int pfo_linear_bf16(const float* A, int64_t lda, const int32_t* a_idx, const float* W, int64_t ldw,
+                    int w_transposed, const float* bias, const float* bias_row_scale, int64_t ld_brs,
+                    float* C, int64_t ldc, int64_t M, const int32_t* m_dev, int N, int K,
+                    float alpha, int act, const int32_t* row_zero, const float* relu_gate, int64_t ld_gate,
+                    int accumulate, void* stream);
+
+/* ---- memory updater gates on the unique touched nodes --- modules/memory_updater.py:35-53
+ * (get_updated_memory) restricted to nodes that are read.  cell: 0 GRU, 1 RNN, 2 no memory.
+ * gather_state snapshots the rows of the unique nodes (HG memory, XG pending message, valid_u,
+ * lu_u = last_update') before persist / store overwrite them.  GI/GH are the input / hidden
+ * pre-activations ([U,3d] or [U,d]).  Hnew = updated memory rows, H0 = Hnew + node_feat rows
+ * (modules/embedding_module.py:93-98). */
+int pfo_gather_state(const int32_t* uniq, const int32_t* n_uniq, int64_t u_max, int d, int raw,
+                     const float* memory, const float* pend_msg, int64_t rawp, const uint8_t* pend_valid,
+                     const float* pend_ts, const float* last_update,
+                     float* HG, float* XG, uint8_t* valid_u, float* lu_u, void* stream);
+int pfo_cell_forward(const int32_t* uniq, const int32_t* n_uniq, int64_t u_max, int d, int cell,
+                     const float* GI, const float* GH, int64_t ldg, const float* HG,
+                     const uint8_t* valid_u, const float* node_feat, float* Hnew, float* H0, void* stream);
+int pfo_cell_backward(const int32_t* uniq, const int32_t* n_uniq, int64_t u_max, int d, int cell,
+                      const float* GI, const float* GH, int64_t ldg, const float* HG,
+                      const uint8_t* valid_u, const float* dH, float* dGI, float* dGH, void* stream);
+
+/* ---- persist + message store --- model/tgn.py:185-206 (update_memory for positives, clear,
+ * get_raw_messages x2, store_raw_messages), model/tgn.py:357-378, modules/memory.py:35-37,
+ * modules/message_aggregator.py:38-55 (`last`).  last_pos[N] is int32 scratch that must hold -1. */
+int pfo_persist_rank(const int32_t* src, const int32_t* dst, int B, int d, const int32_t* slot_of_node,
+                     const float* Hnew, const uint8_t* pend_valid, const float* pend_ts,
+                     float* memory, float* last_update, int32_t* last_pos, void* stream);
+int pfo_store_messages(const int32_t* src, const int32_t* dst, const int32_t* eidx, const double* ts,
+                       int B, int d, int F, const float* memory, const float* last_update,
+                       const float* edge_feat, const float* tw, const float* tb,
+                       const float* other_emb_for_src, const float* other_emb_for_dst,
+                       float* pend_msg, int64_t rawp, float* pend_ts, uint8_t* pend_valid,
+                       int32_t* last_pos, void* stream);
+
+/* ---- jodie time-projection embedding --- modules/embedding_module.py:57-61, model/tgn.py:260-266 */
+int pfo_time_embedding_fwd(const int32_t* q_nodes, const double* q_ts, int64_t Q, int64_t n_src, int d,
+                           const int32_t* slot_of_node, const float* Hnew, const float* lu_u,
+                           float mean_src, float std_src, float mean_dst, float std_dst,
+                           const float* W, const float* b, float* td_out, float* emb, void* stream);
+int pfo_time_embedding_bwd(const int32_t* q_nodes, int64_t Q, int d, const int32_t* slot_of_node,
+                           const float* Hnew, const float* td, const float* W, const float* b,
+                           const float* dEmb, float* dHnew, float* dWdb, float* workspace,
+                           int64_t workspace_floats, void* stream);
+
+/* small row utilities (gather with idx < 0 -> zero row; scatter-add = its gradient) */
+int pfo_reduce_partials(const float* partial, int rows, int cols, float* out, int accumulate, void* stream);
+int pfo_scatter_add_rows(const float* src, int64_t lds, const int32_t* idx, int64_t M, int d,
+                         float* dst, int64_t ldd, void* stream);
+int pfo_gather_rows(const float* src, int64_t lds, const int32_t* idx, int64_t M, int d,
+                    float* dst, int64_t ldd, void* stream);
+
+/* ---- K4 neighbour level: fused gather + TimeEncode + masked softmax over sampled neighbours ---
+ * model/temporal_attention.py:34-90, model/time_encoding.py:17-25, modules/embedding_module.py:141-154.
+ * Weight-absorbed multi-head attention (see csrc/attention_kernels.cu).  QK/XB/dQK/dXB are
+ * [Q, H, ekp] with segment [h (d) | e (F) | te (d) | psum | pad]; T is the feature table the
+ * neighbour rows are gathered from (idx < 0 = padded neighbour); P [Q,H,n] = softmax weights. */
+int pfo_attn_nbr_fwd(const float* QK, const float* T, int64_t ldt, const int32_t* idx, const int32_t* eidx,
+                     const float* dt, const float* efeat, const float* tw, const float* tb,
+                     int64_t Q, int n, int d, int F, int H, int ekp, float p_drop, uint64_t seed, uint32_t step,
+                     float* XB, float* P, int32_t* invalid, void* stream);
+int64_t pfo_attn_nbr_bwd_workspace_floats(int d);
+int pfo_attn_nbr_bwd(const float* QK, const float* dXB, const float* P, const int32_t* invalid,
+                     const float* T, int64_t ldt, const int32_t* idx, const int32_t* eidx, const float* dt,
+                     const float* efeat, const float* tw, const float* tb,
+                     int64_t Q, int n, int d, int F, int H, int ekp, float p_drop, uint64_t seed, uint32_t step,
+                     float* dQK, float* dT, int64_t lddt, float* dtw_dtb, int accumulate,
+                     float* workspace, void* stream);
+
+/* ---- K6: BPR loss forward + backward --- main.py:321-337 / :364-381.  du/dp/dn may be null
+ * (forward only).  workspace: 1024 floats. */
+int pfo_bpr(const float* eu, const float* ep, const float* en, int B, int k, int d,
+            float* du, float* dp, float* dn, float* loss, float grad_scale, float* workspace, void* stream);
+
+/* ---- evaluation scoring + ranking --- evaluation.py:107-115,134-138 (stable argsort, reversed).
+ * scores [B, 1+n_cand]; pos_rank[b] = position of the true item; top_idx [B, topk] candidate
+ * positions (0 = the true item). */
+int pfo_eval_score(const float* es, const float* ed, const float* ec, int B, int n_cand, int d, int topk,
+                   float* scores, int32_t* pos_rank, int32_t* top_idx, void* stream);
+
+/* ---- K5: candidate sampling + mean-variance efficient selection --- utils/utils.py:65-114
+ * (RandEdgeSampler) and main.py:197-304 (inline block).  Stocks are 0-based indices; logret is
+ * float64 [n_days, n_stocks, n_returns].  sample != 0 draws cand[:,1:] from the Philox stream
+ * (cand[:,0] = pos_stock); sample == 0 takes cand as input.  p_neg is [n_neg-th lowest .. lowest]. */
+int pfo_mv_select(const int64_t* event_ids, const int32_t* day_idx, const int32_t* pos_stock,
+                  const int64_t* port_ptr, const int32_t* port_items,
+                  const int32_t* items_sorted, int n_items_universe,
+                  const double* logret, int n_stocks, int n_returns,
+                  int B, int K, double gamma, double lam, int n_pos, int n_neg, uint64_t seed, int sample,
+                  int32_t* cand, double* y_out, int32_t* p_pos, int32_t* p_neg, void* stream);
+int pfo_sample_candidates(const int64_t* event_ids, const int64_t* port_ptr, const int32_t* port_items,
+                          const int32_t* items_sorted, int n_items_universe, int B, int size,
+                          uint64_t seed, int32_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFO_B200_H */

@@ -21,9 +21,9 @@ def sample_candidates(event_ids, items_sorted, port_ptr, port_items, size, seed)
     Returns int64[B, size] item ids.
 
     Without replacement when enough items are available (utils.py:107-111): every
-    available item at position p of `items_sorted` gets the 64-bit key
-    philox(g_lo, g_hi, p, PURPOSE_NEG)[0:2]; the sample is the `size` smallest keys in
-    ascending (key, p) order.  With replacement otherwise (:99-105): draw j is
+    available item at position p of `items_sorted` gets the key
+    (philox(g_lo, g_hi, p, PURPOSE_NEG)[0], p); the sample is the `size` smallest keys in
+    ascending order (the 32-bit draw first, the position breaks ties).  With replacement otherwise (:99-105): draw j is
     available[mulhi32(philox(g_lo, g_hi, j, PURPOSE_NEG_REPL)[0], n_available)].
     """
     event_ids = np.asarray(event_ids, dtype=np.int64)
@@ -43,9 +43,8 @@ def sample_candidates(event_ids, items_sorted, port_ptr, port_items, size, seed)
             x0 = philox4x32_10(g & 0xFFFFFFFF, (g >> 32) & 0xFFFFFFFF, j, PURPOSE_NEG_REPL, k0, k1)[0]
             out[b] = items_sorted[pos[mulhi32(x0, n_av)]]
         else:
-            x = philox4x32_10(g & 0xFFFFFFFF, (g >> 32) & 0xFFFFFFFF, pos, PURPOSE_NEG, k0, k1)
-            key = (x[0].astype(np.uint64) << np.uint64(32)) | x[1].astype(np.uint64)
-            o = np.lexsort((pos, key))[:size]
+            x0 = philox4x32_10(g & 0xFFFFFFFF, (g >> 32) & 0xFFFFFFFF, pos, PURPOSE_NEG, k0, k1)[0]
+            o = np.lexsort((pos, x0))[:size]
             out[b] = items_sorted[pos[o]]
     return out
 

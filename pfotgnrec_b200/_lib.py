@@ -1,0 +1,107 @@
+"""ctypes binding of libpfo_b200.so (the C ABI declared in include/pfo_b200.h).
+
+There is no CPU fallback: if the library is missing or a launch fails this module raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_int, c_int32, c_int64, c_uint32, c_uint64, c_float, c_double, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpfo_b200.so")
+
+P = c_void_p
+_SIGS = {
+    "pfo_abi_version": (c_int, []),
+    "pfo_neighbor_sample": (c_int, [P, P, P, P, P, P, c_int64, c_int, c_int, c_uint64, c_uint32, P, P, P, P, P]),
+    "pfo_mark_nodes": (c_int, [P, c_int64, c_int, P, P]),
+    "pfo_compact_workspace_ints": (c_int64, [c_int64]),
+    "pfo_compact_nodes": (c_int, [P, c_int64, P, P, P, P, P]),
+    "pfo_map_slots": (c_int, [P, c_int64, c_int, P, P, P]),
+    "pfo_linear_f32": (c_int, [P, c_int64, P, P, c_int64, c_int, P, P, c_int64, P, c_int64, c_int64, P, c_int, c_int,
+                               c_float, c_int, P, P, c_int64, c_int, P]),
+    "pfo_linear_bf16": (c_int, [P, c_int64, P, P, c_int64, c_int, P, P, c_int64, P, c_int64, c_int64, P, c_int, c_int,
+                                c_float, c_int, P, P, c_int64, c_int, P]),
+    "pfo_wgrad_workspace_floats": (c_int64, [c_int64, c_int, c_int, c_int]),
+    "pfo_wgrad_f32": (c_int, [P, c_int64, P, c_int64, P, c_int64, P, c_int, c_int, P, c_int64, P, c_int, P, P]),
+    "pfo_gather_state": (c_int, [P, P, c_int64, c_int, c_int, P, P, c_int64, P, P, P, P, P, P, P, P]),
+    "pfo_cell_forward": (c_int, [P, P, c_int64, c_int, c_int, P, P, c_int64, P, P, P, P, P, P]),
+    "pfo_cell_backward": (c_int, [P, P, c_int64, c_int, c_int, P, P, c_int64, P, P, P, P, P, P]),
+    "pfo_persist_rank": (c_int, [P, P, c_int, c_int, P, P, P, P, P, P, P, P]),
+    "pfo_store_messages": (c_int, [P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_int64, P, P, P, P]),
+    "pfo_time_embedding_fwd": (c_int, [P, P, c_int64, c_int64, c_int, P, P, P, c_float, c_float, c_float,
+                                       c_float, P, P, P, P, P]),
+    "pfo_time_embedding_bwd": (c_int, [P, c_int64, c_int, P, P, P, P, P, P, P, P, P, c_int64, P]),
+    "pfo_reduce_partials": (c_int, [P, c_int, c_int, P, c_int, P]),
+    "pfo_scatter_add_rows": (c_int, [P, c_int64, P, c_int64, c_int, P, c_int64, P]),
+    "pfo_gather_rows": (c_int, [P, c_int64, P, c_int64, c_int, P, c_int64, P]),
+    "pfo_attn_nbr_fwd": (c_int, [P, P, c_int64, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int,
+                                 c_float, c_uint64, c_uint32, P, P, P, P]),
+    "pfo_attn_nbr_bwd_workspace_floats": (c_int64, [c_int]),
+    "pfo_attn_nbr_bwd": (c_int, [P, P, P, P, P, c_int64, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int,
+                                 c_float, c_uint64, c_uint32, P, P, c_int64, P, c_int, P, P]),
+    "pfo_bpr": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P, P, c_float, P, P]),
+    "pfo_eval_score": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, P, P, P]),
+    "pfo_mv_select": (c_int, [P, P, P, P, P, P, c_int, P, c_int, c_int, c_int, c_int, c_double, c_double, c_int,
+                              c_int, c_uint64, c_int, P, P, P, P, P]),
+    "pfo_sample_candidates": (c_int, [P, P, P, P, c_int, c_int, c_int, c_uint64, P, P]),
+}
+
+EXPORTS = tuple(_SIGS)
+_lib = None
+LAUNCHES = 0            # kernels launched through this binding (bench.py reports it)
+_LAUNCHES_PER_CALL = {"pfo_compact_nodes": 3, "pfo_wgrad_f32": 2, "pfo_time_embedding_bwd": 2,
+                      "pfo_attn_nbr_bwd": 2, "pfo_bpr": 2, "pfo_abi_version": 0,
+                      "pfo_compact_workspace_ints": 0, "pfo_wgrad_workspace_floats": 0,
+                      "pfo_attn_nbr_bwd_workspace_floats": 0}
+
+
+class PfoError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built: no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PfoError(f"{LIB_PATH} is missing: run `python -m pfotgnrec_b200.build` "
+                       "(or __graft_entry__.build()); there is no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)      # AttributeError if the header and the library disagree
+        fn.restype, fn.argtypes = res, args
+    if lib.pfo_abi_version() != 1:
+        raise PfoError("libpfo_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    """Invoke an entry point on the current torch stream and raise on a non-zero return."""
+    global LAUNCHES
+    lib = load()
+    rc = getattr(lib, name)(*args, stream())
+    LAUNCHES += _LAUNCHES_PER_CALL.get(name, 1)
+    if rc != 0:
+        raise PfoError(f"{name} failed with cudaError {rc}")
+
+
+def query(name, *args):
+    """Host-only helper entry points (workspace sizes)."""
+    return getattr(load(), name)(*args)

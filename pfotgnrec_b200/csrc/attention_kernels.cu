@@ -1,0 +1,465 @@
+// K4 (neighbour level): fused gather + time encoding + masked softmax over the sampled
+// temporal neighbours, in the weight-absorbed form of multi-head attention.
+//
+// Reference: model/temporal_attention.py:34-90 feeding torch.nn.MultiheadAttention with
+// key = value = [h_nbr | e | cos(dt*w+b)] (:52).  Because K and V are linear in the
+// neighbour row x_j, the per-neighbour projections are never materialised:
+//     score_hj = q_h . (Wk_h x_j + bk_h) = (Wk_h^T q_h) . x_j + const_h   (const cancels in softmax)
+//     out_h    = sum_j p_hj (Wv_h x_j + bv_h) = Wv_h (sum_j p_hj x_j) + bv_h * sum_j p_hj
+// so this kernel consumes qk_h = Wk_h^T q_h per query and produces xbar_h = sum_j p_hj x_j
+// (plus psum_h); the Q-level projections around it are tall-skinny GEMMs (linear_*.cu).
+// This cuts the neighbour-level FLOPs by ~8x and leaves a gather-bound kernel:
+// one warp per query, lanes own contiguous feature columns, online softmax in registers.
+//
+// Row layout of QK / XB / dQK / dXB: [Q, H, EKP], segment = [h (d) | e (F) | te (d) | psum | pad].
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace {
+
+constexpr int kMaxHeads = 4;
+
+struct NbrArgs {
+    const float* QK; const float* T; int64_t ldt;
+    const int32_t* idx; const int32_t* eidx; const float* dt;
+    const float* efeat; const float* tw; const float* tb;
+    int64_t Q; int n; int d; int F; int H; int ekp;
+    float p_drop; uint32_t k0, k1, step;
+    float* XB; float* P; int32_t* invalid;
+    // backward only
+    const float* dXB; float* dQK; float* dT; int64_t lddt; float* partial;
+};
+
+__device__ __forceinline__ float keep_scale(const NbrArgs& p, int64_t q, int h, int j) {
+    if (p.p_drop <= 0.0f) return 1.0f;
+    const uint32_t r = philox4x32_10((uint32_t)q, (uint32_t)(h * p.n + j), p.step, PFO_PURPOSE_DROPOUT, p.k0, p.k1).x;
+    const float u = (float)(r >> 8) * (1.0f / 16777216.0f);
+    return u < p.p_drop ? 0.0f : 1.0f / (1.0f - p.p_drop);
+}
+
+template <int DPL>
+__global__ void __launch_bounds__(256)
+attn_nbr_fwd_kernel(const NbrArgs p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int d = p.d, F = p.F, H = p.H, n = p.n;
+    const int c0 = lane * DPL;
+    float tw[DPL], tb[DPL];
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) { tw[i] = p.tw[c0 + i]; tb[i] = p.tb[c0 + i]; }
+    for (int64_t q = warp; q < p.Q; q += nwarps) {
+        float qa[kMaxHeads][DPL], qg[kMaxHeads][DPL], qe[kMaxHeads];
+        float ah[kMaxHeads][DPL], at[kMaxHeads][DPL], ae[kMaxHeads], ap[kMaxHeads];
+        float mx[kMaxHeads], l[kMaxHeads], sj[kMaxHeads];
+#pragma unroll
+        for (int h = 0; h < kMaxHeads; ++h) {
+            if (h < H) {
+                const float* qk = p.QK + (q * H + h) * p.ekp;
+#pragma unroll
+                for (int i = 0; i < DPL; ++i) { qa[h][i] = qk[c0 + i]; qg[h][i] = qk[d + F + c0 + i]; ah[h][i] = 0.f; at[h][i] = 0.f; }
+                qe[h] = lane < F ? qk[d + lane] : 0.0f;
+                ae[h] = 0.f; ap[h] = 0.f; mx[h] = -INFINITY; l[h] = 0.f; sj[h] = 0.f;
+            }
+        }
+        bool any = false;
+        for (int j = 0; j < n; ++j) {
+            const int id = p.idx[q * n + j];
+            if (id < 0) continue;                       // padded neighbour: masked (embedding_module.py:154)
+            any = true;
+            const float dtj = p.dt[q * n + j];
+            float xh[DPL], xt[DPL];
+            const float* row = p.T + (int64_t)id * p.ldt + c0;
+#pragma unroll
+            for (int i = 0; i < DPL; ++i) {
+                xh[i] = row[i];
+                xt[i] = cosf(fmaf(dtj, tw[i], tb[i]));  // full-range cosf, never __cosf (SURVEY hard part 1)
+            }
+            const float xe = lane < F ? p.efeat[(int64_t)p.eidx[q * n + j] * F + lane] : 0.0f;
+#pragma unroll
+            for (int h = 0; h < kMaxHeads; ++h) {
+                if (h < H) {
+                    float part = qe[h] * xe;
+#pragma unroll
+                    for (int i = 0; i < DPL; ++i) part = fmaf(qa[h][i], xh[i], fmaf(qg[h][i], xt[i], part));
+                    const float s = warp_sum(part);
+                    if (lane == j) sj[h] = s;
+                    const float m_new = fmaxf(mx[h], s);
+                    const float sc = expf(mx[h] - m_new);
+                    const float e = expf(s - m_new);
+                    const float w = e * keep_scale(p, q, h, j);
+                    l[h] = l[h] * sc + e;
+                    ap[h] = ap[h] * sc + w;
+                    ae[h] = ae[h] * sc + w * xe;
+#pragma unroll
+                    for (int i = 0; i < DPL; ++i) {
+                        ah[h][i] = ah[h][i] * sc + w * xh[i];
+                        at[h][i] = at[h][i] * sc + w * xt[i];
+                    }
+                    mx[h] = m_new;
+                }
+            }
+        }
+        if (lane == 0) p.invalid[q] = any ? 0 : 1;     // rows with no neighbours: output zeroed (temporal_attention.py:84)
+#pragma unroll
+        for (int h = 0; h < kMaxHeads; ++h) {
+            if (h < H) {
+                float* xb = p.XB + (q * H + h) * p.ekp;
+                const float inv = any ? 1.0f / l[h] : 0.0f;
+#pragma unroll
+                for (int i = 0; i < DPL; ++i) { xb[c0 + i] = ah[h][i] * inv; xb[d + F + c0 + i] = at[h][i] * inv; }
+                if (lane < F) xb[d + lane] = ae[h] * inv;
+                if (lane == 0) xb[2 * d + F] = ap[h] * inv;
+                if (lane < n) {
+                    const bool live = p.idx[q * n + lane] >= 0;
+                    p.P[(q * H + h) * n + lane] = live ? expf(sj[h] - mx[h]) * inv : 0.0f;
+                }
+            }
+        }
+    }
+}
+
+template <int DPL>
+__global__ void __launch_bounds__(128)
+attn_nbr_bwd_kernel(const NbrArgs p) {
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int64_t warp = (int64_t)blockIdx.x * wpb + wib;
+    const int64_t nwarps = (int64_t)gridDim.x * wpb;
+    const int d = p.d, F = p.F, H = p.H, n = p.n;
+    const int sw = 3 * d + 32;                          // stash row: [h | cos | sin | e(32)]
+    float* stash = smem + (size_t)wib * n * sw;
+    float* red = smem + (size_t)wpb * n * sw;           // [wpb][2][d] for the block reduction
+    const int c0 = lane * DPL;
+    float tw[DPL], tb[DPL], dwl[DPL], dbl[DPL];
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) { tw[i] = p.tw[c0 + i]; tb[i] = p.tb[c0 + i]; dwl[i] = 0.f; dbl[i] = 0.f; }
+    for (int64_t q = warp; q < p.Q; q += nwarps) {
+        const bool dead = p.invalid[q] != 0;
+        float qa[kMaxHeads][DPL], qg[kMaxHeads][DPL], qe[kMaxHeads];
+        float ga[kMaxHeads][DPL], gg[kMaxHeads][DPL], ge[kMaxHeads], gp[kMaxHeads];
+        float da[kMaxHeads][DPL], dg[kMaxHeads][DPL], de[kMaxHeads];
+        float pj[kMaxHeads], dpj[kMaxHeads];
+#pragma unroll
+        for (int h = 0; h < kMaxHeads; ++h) {
+            if (h < H) {
+                const float* qk = p.QK + (q * H + h) * p.ekp;
+                const float* gx = p.dXB + (q * H + h) * p.ekp;
+#pragma unroll
+                for (int i = 0; i < DPL; ++i) {
+                    qa[h][i] = qk[c0 + i]; qg[h][i] = qk[d + F + c0 + i];
+                    ga[h][i] = gx[c0 + i]; gg[h][i] = gx[d + F + c0 + i];
+                    da[h][i] = 0.f; dg[h][i] = 0.f;
+                }
+                qe[h] = lane < F ? qk[d + lane] : 0.0f;
+                ge[h] = lane < F ? gx[d + lane] : 0.0f;
+                gp[h] = gx[2 * d + F];
+                de[h] = 0.f;
+                pj[h] = (lane < n) ? p.P[(q * H + h) * n + lane] : 0.0f;
+                dpj[h] = 0.f;
+            }
+        }
+        if (!dead) {
+            // pass A: rebuild x_j, stash it, dp_hj = dXB_h . [x_j | 1]
+            for (int j = 0; j < n; ++j) {
+                const int id = p.idx[q * n + j];
+                if (id < 0) continue;
+                const float dtj = p.dt[q * n + j];
+                float* st = stash + j * sw;
+                const float* row = p.T + (int64_t)id * p.ldt + c0;
+                float xh[DPL], xt[DPL];
+#pragma unroll
+                for (int i = 0; i < DPL; ++i) {
+                    float sn, cs;
+                    sincosf(fmaf(dtj, tw[i], tb[i]), &sn, &cs);
+                    xh[i] = row[i]; xt[i] = cs;
+                    st[c0 + i] = xh[i]; st[d + c0 + i] = cs; st[2 * d + c0 + i] = sn;
+                }
+                const float xe = lane < F ? p.efeat[(int64_t)p.eidx[q * n + j] * F + lane] : 0.0f;
+                st[3 * d + lane] = xe;
+#pragma unroll
+                for (int h = 0; h < kMaxHeads; ++h) {
+                    if (h < H) {
+                        float part = ge[h] * xe;
+#pragma unroll
+                        for (int i = 0; i < DPL; ++i) part = fmaf(ga[h][i], xh[i], fmaf(gg[h][i], xt[i], part));
+                        const float dp = (warp_sum(part) + gp[h]) * keep_scale(p, q, h, j);
+                        if (lane == j) dpj[h] = dp;
+                    }
+                }
+            }
+            __syncwarp();
+            // softmax backward: ds_hj = p_hj (dp_hj - sum_j' p_hj' dp_hj')
+            float dsj[kMaxHeads];
+#pragma unroll
+            for (int h = 0; h < kMaxHeads; ++h)
+                if (h < H) { const float dot = warp_sum(pj[h] * dpj[h]); dsj[h] = pj[h] * (dpj[h] - dot); }
+            // pass B: dqk_h += ds_hj x_j ; dx_j = sum_h (p'_hj dXB_h + ds_hj qk_h)
+            for (int j = 0; j < n; ++j) {
+                const int id = p.idx[q * n + j];
+                if (id < 0) continue;
+                const float dtj = p.dt[q * n + j];
+                const float* st = stash + j * sw;
+                float xh[DPL], cs[DPL], sn[DPL], gxh[DPL], gxt[DPL];
+#pragma unroll
+                for (int i = 0; i < DPL; ++i) {
+                    xh[i] = st[c0 + i]; cs[i] = st[d + c0 + i]; sn[i] = st[2 * d + c0 + i];
+                    gxh[i] = 0.f; gxt[i] = 0.f;
+                }
+                const float xe = st[3 * d + lane];
+#pragma unroll
+                for (int h = 0; h < kMaxHeads; ++h) {
+                    if (h < H) {
+                        const float ds = __shfl_sync(0xffffffffu, dsj[h], j);
+                        const float pw = __shfl_sync(0xffffffffu, pj[h], j) * keep_scale(p, q, h, j);
+                        de[h] = fmaf(ds, xe, de[h]);
+#pragma unroll
+                        for (int i = 0; i < DPL; ++i) {
+                            da[h][i] = fmaf(ds, xh[i], da[h][i]);
+                            dg[h][i] = fmaf(ds, cs[i], dg[h][i]);
+                            gxh[i] += pw * ga[h][i] + ds * qa[h][i];
+                            gxt[i] += pw * gg[h][i] + ds * qg[h][i];
+                        }
+                    }
+                }
+                float* drow = p.dT + (int64_t)id * p.lddt + c0;
+                if (DPL == 4) red_add_f32x4(drow, gxh[0], gxh[1], gxh[2], gxh[3]);
+                else {
+#pragma unroll
+                    for (int i = 0; i < DPL; ++i) atomicAdd(drow + i, gxh[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < DPL; ++i) {          // d cos(dt*w+b) = -sin(.) * (dt dw + db)
+                    const float t = -sn[i] * gxt[i];
+                    dwl[i] = fmaf(t, dtj, dwl[i]);
+                    dbl[i] += t;
+                }
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int h = 0; h < kMaxHeads; ++h) {
+            if (h < H) {
+                float* o = p.dQK + (q * H + h) * p.ekp;
+#pragma unroll
+                for (int i = 0; i < DPL; ++i) { o[c0 + i] = da[h][i]; o[d + F + c0 + i] = dg[h][i]; }
+                if (lane < F) o[d + lane] = de[h];
+                if (lane < p.ekp - (2 * d + F)) o[2 * d + F + lane] = 0.0f;
+            }
+        }
+    }
+    // block reduction of the time-encoder gradients -> partial[block][2][d]
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) { red[(wib * 2 + 0) * d + c0 + i] = dwl[i]; red[(wib * 2 + 1) * d + c0 + i] = dbl[i]; }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) {
+        float s = 0.f;
+        for (int w = 0; w < wpb; ++w) s += red[(w * 2) * d + c];   // red is [wpb][2*d]
+        p.partial[(int64_t)blockIdx.x * 2 * d + c] = s;
+    }
+}
+
+// ---- BPR loss forward + backward (reference main.py:321-337) --------------------------
+// one warp per interaction; loss_partial[block] and gradients w.r.t. the three embedding groups
+__global__ void __launch_bounds__(256)
+bpr_kernel(const float* __restrict__ eu, const float* __restrict__ ep, const float* __restrict__ en,
+           int B, int k, int d, float* __restrict__ du, float* __restrict__ dp, float* __restrict__ dn,
+           float* __restrict__ loss_partial, float grad_scale) {
+    __shared__ float wl[8];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float lsum = 0.f;
+    for (int64_t b = warp; b < B; b += nwarps) {
+        const float* u = eu + b * d;
+        const float* pp = ep + b * d;
+        float pos = 0.f;
+        for (int c = lane; c < d; c += 32) pos = fmaf(u[c], pp[c], pos);
+        pos = warp_sum(pos);
+        float diff = 0.f;
+        for (int j = 0; j < k; ++j) {
+            const float* nn = en + (b * k + j) * d;
+            float s = 0.f;
+            for (int c = lane; c < d; c += 32) s = fmaf(u[c], nn[c], s);
+            diff += pos - warp_sum(s);
+        }
+        const float x = diff / (float)k;
+        const float sg = sigmoidf_(x);
+        lsum += -logf(sg);
+        if (du) {
+            const float gx = -(1.0f - sg) * grad_scale / (float)B;     // d(-log sigmoid(x))/dx / B
+            for (int c = lane; c < d; c += 32) {
+                float nsum = 0.f;
+                for (int j = 0; j < k; ++j) {
+                    nsum += en[(b * k + j) * d + c];
+                    dn[(b * k + j) * d + c] = -gx / (float)k * u[c];
+                }
+                du[b * d + c] = gx * (pp[c] - nsum / (float)k);
+                dp[b * d + c] = gx * u[c];
+            }
+        }
+    }
+    if (lane == 0) wl[wib] = lsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += wl[w];
+        loss_partial[blockIdx.x] = s / (float)B;
+    }
+}
+
+// ---- evaluation scoring + ranking (reference evaluation.py:107-115,134-138) -----------
+// one CTA per interaction: scores[0] = <src,dst>, scores[1+c] = <src,cand_c>; the rank of the
+// positive under argsort(scores)[::-1] with a stable sort, and the top-k candidate positions.
+__global__ void __launch_bounds__(256)
+eval_score_kernel(const float* __restrict__ es, const float* __restrict__ ed, const float* __restrict__ ec,
+                  int n_cand, int d, int topk, float* __restrict__ scores, int32_t* __restrict__ pos_rank,
+                  int32_t* __restrict__ top_idx) {
+    extern __shared__ float sh[];            // [1 + n_cand] scores, then reduction scratch
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const float* u = es + (int64_t)b * d;
+    const int total = 1 + n_cand;
+    for (int c = wib; c < total; c += wpb) {
+        const float* v = c == 0 ? ed + (int64_t)b * d : ec + ((int64_t)b * n_cand + (c - 1)) * d;
+        float s = 0.f;
+        for (int k = lane; k < d; k += 32) s += u[k] * v[k];    // torch.sum(a * b): mul then add
+        s = warp_sum(s);
+        if (lane == 0) { sh[c] = s; scores[(int64_t)b * total + c] = s; }
+    }
+    __syncthreads();
+    // reversed stable ascending order: among equal scores the larger index comes first
+    __shared__ int cnt;
+    __shared__ float best_v[8];
+    __shared__ int best_i[8];
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    const float s0 = sh[0];
+    int local = 0;
+    for (int c = 1 + threadIdx.x; c < total; c += blockDim.x) local += (sh[c] >= s0) ? 1 : 0;
+    local = warp_sum_i(local);
+    if (lane == 0) atomicAdd(&cnt, local);
+    __syncthreads();
+    if (threadIdx.x == 0) pos_rank[b] = cnt;
+    float prev_v = INFINITY;
+    int prev_i = 0x7fffffff;
+    for (int r = 0; r < topk; ++r) {
+        float bv = -INFINITY; int bi = -1;
+        for (int c = threadIdx.x; c < total; c += blockDim.x) {
+            const float v = sh[c];
+            const bool after_prev = v < prev_v || (v == prev_v && c < prev_i);
+            if (after_prev && (v > bv || (v == bv && c > bi))) { bv = v; bi = c; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi > bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { best_v[wib] = bv; best_i[wib] = bi; }
+        __syncthreads();
+        bv = best_v[0]; bi = best_i[0];
+        for (int w = 1; w < wpb; ++w)
+            if (best_v[w] > bv || (best_v[w] == bv && best_i[w] > bi)) { bv = best_v[w]; bi = best_i[w]; }
+        if (threadIdx.x == 0) top_idx[(int64_t)b * topk + r] = bi;
+        prev_v = bv; prev_i = bi;
+        __syncthreads();
+    }
+}
+
+template <int DPL>
+int launch_fwd(const NbrArgs& a, cudaStream_t s) {
+    attn_nbr_fwd_kernel<DPL><<<pfo_grid(a.Q * 32, 256, 4), 256, 0, s>>>(a);
+    PFO_LAUNCH_CHECK();
+}
+
+template <int DPL>
+int launch_bwd(const NbrArgs& a, int grid, size_t smem, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(attn_nbr_bwd_kernel<DPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    attn_nbr_bwd_kernel<DPL><<<grid, 128, smem, s>>>(a);
+    PFO_LAUNCH_CHECK();
+}
+
+}  // namespace
+
+PFO_API int pfo_attn_nbr_fwd(const float* QK, const float* T, int64_t ldt, const int32_t* idx, const int32_t* eidx,
+                             const float* dt, const float* efeat, const float* tw, const float* tb,
+                             int64_t Q, int n, int d, int F, int H, int ekp,
+                             float p_drop, uint64_t seed, uint32_t step,
+                             float* XB, float* P, int32_t* invalid, void* stream) {
+    if (Q <= 0) return 0;
+    if (d % 32 != 0 || d > 128 || F > 32 || H > kMaxHeads || n > 32 || n < 1) return (int)cudaErrorInvalidValue;
+    NbrArgs a{};
+    a.QK = QK; a.T = T; a.ldt = ldt; a.idx = idx; a.eidx = eidx; a.dt = dt; a.efeat = efeat; a.tw = tw; a.tb = tb;
+    a.Q = Q; a.n = n; a.d = d; a.F = F; a.H = H; a.ekp = ekp; a.p_drop = p_drop;
+    a.k0 = (uint32_t)(seed & 0xffffffffu); a.k1 = (uint32_t)(seed >> 32); a.step = step;
+    a.XB = XB; a.P = P; a.invalid = invalid;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (d / 32) {
+        case 1: return launch_fwd<1>(a, s);
+        case 2: return launch_fwd<2>(a, s);
+        case 3: return launch_fwd<3>(a, s);
+        default: return launch_fwd<4>(a, s);
+    }
+}
+
+PFO_API int64_t pfo_attn_nbr_bwd_workspace_floats(int d) { return (int64_t)2 * 148 * 4 * 2 * d; }
+
+PFO_API int pfo_attn_nbr_bwd(const float* QK, const float* dXB, const float* P, const int32_t* invalid,
+                             const float* T, int64_t ldt, const int32_t* idx, const int32_t* eidx, const float* dt,
+                             const float* efeat, const float* tw, const float* tb,
+                             int64_t Q, int n, int d, int F, int H, int ekp,
+                             float p_drop, uint64_t seed, uint32_t step,
+                             float* dQK, float* dT, int64_t lddt, float* dtw_dtb, int accumulate,
+                             float* workspace, void* stream) {
+    if (Q <= 0) return 0;
+    if (d % 32 != 0 || d > 128 || F > 32 || H > kMaxHeads || n > 32 || n < 1) return (int)cudaErrorInvalidValue;
+    NbrArgs a{};
+    a.QK = QK; a.T = T; a.ldt = ldt; a.idx = idx; a.eidx = eidx; a.dt = dt; a.efeat = efeat; a.tw = tw; a.tb = tb;
+    a.Q = Q; a.n = n; a.d = d; a.F = F; a.H = H; a.ekp = ekp; a.p_drop = p_drop;
+    a.k0 = (uint32_t)(seed & 0xffffffffu); a.k1 = (uint32_t)(seed >> 32); a.step = step;
+    a.P = const_cast<float*>(P); a.invalid = const_cast<int32_t*>(invalid);
+    a.dXB = dXB; a.dQK = dQK; a.dT = dT; a.lddt = lddt; a.partial = workspace;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int wpb = 4;
+    const size_t smem = ((size_t)wpb * n * (3 * d + 32) + (size_t)wpb * 2 * d) * sizeof(float);
+    int grid = pfo_grid(Q * 32, 128, 4);
+    const int max_grid = 2 * 148 * 4;
+    if (grid > max_grid) grid = max_grid;
+    int rc;
+    switch (d / 32) {
+        case 1: rc = launch_bwd<1>(a, grid, smem, s); break;
+        case 2: rc = launch_bwd<2>(a, grid, smem, s); break;
+        case 3: rc = launch_bwd<3>(a, grid, smem, s); break;
+        default: rc = launch_bwd<4>(a, grid, smem, s); break;
+    }
+    if (rc) return rc;
+    return pfo_reduce_partials(workspace, grid, 2 * d, dtw_dtb, accumulate, stream);
+}
+
+PFO_API int pfo_bpr(const float* eu, const float* ep, const float* en, int B, int k, int d,
+                    float* du, float* dp, float* dn, float* loss, float grad_scale, float* workspace, void* stream) {
+    if (B <= 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    int grid = pfo_grid((int64_t)B * 32, 256, 2);
+    if (grid > 1024) grid = 1024;
+    bpr_kernel<<<grid, 256, 0, s>>>(eu, ep, en, B, k, d, du, dp, dn, workspace, grad_scale);
+    // loss = sum over blocks of per-block means/B contributions: reduce rows=grid, cols=1
+    return pfo_reduce_partials(workspace, grid, 1, loss, 0, stream);
+}
+
+PFO_API int pfo_eval_score(const float* es, const float* ed, const float* ec, int B, int n_cand, int d, int topk,
+                           float* scores, int32_t* pos_rank, int32_t* top_idx, void* stream) {
+    if (B <= 0) return 0;
+    const size_t smem = (size_t)(1 + n_cand) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(eval_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    eval_score_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(es, ed, ec, n_cand, d, topk, scores, pos_rank, top_idx);
+    PFO_LAUNCH_CHECK();
+}

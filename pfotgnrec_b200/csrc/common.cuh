@@ -1,0 +1,53 @@
+// Shared device helpers for the pfotgnrec_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/pfo_b200.h"
+
+#define PFO_API extern "C" __attribute__((visibility("default")))
+
+// Every entry point returns 0 on success or the cudaError_t of the failed launch.
+#define PFO_LAUNCH_CHECK() do { cudaError_t e__ = cudaGetLastError(); return (int)e__; } while (0)
+
+static inline int pfo_num_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+// grid for a grid-stride kernel: enough CTAs to cover `work` items, capped at a whole number of waves
+static inline int pfo_grid(int64_t work, int block, int ctas_per_sm) {
+    int64_t need = (work + block - 1) / block;
+    int64_t cap = (int64_t)pfo_num_sms() * ctas_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// 16-byte vector reduction into global memory (sm_90+): one L2 op instead of four
+__device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }

@@ -1,0 +1,278 @@
+// K1: temporal neighbour sampling over a time-sorted CSR adjacency, and the
+// touched-node compaction that turns per-batch node ids into a dense "unique node" table.
+//
+// Replaces reference utils/utils.py:150-220 (NeighborFinder.find_before /
+// get_temporal_neighbor) -- a Python loop over queries with np.searchsorted.
+// HBM-bound integer work: one lane owns one query for the binary search (32 searches
+// in flight per warp), then the warp emits its 32*n output slots cooperatively so that
+// the stores to the [Q, n] outputs are fully coalesced.
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace {
+
+__device__ __forceinline__ int64_t lower_bound_ts(const double* __restrict__ ts, int64_t lo, int64_t hi, double t) {
+    // first index in [lo, hi) whose timestamp is >= t  (np.searchsorted side='left', utils.py:158)
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (__ldg(ts + mid) < t) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256)
+neighbor_recent_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ adj_nbr,
+                       const int32_t* __restrict__ adj_eidx, const double* __restrict__ adj_ts,
+                       const int32_t* __restrict__ q_nodes, const double* __restrict__ q_ts,
+                       int64_t Q, int n,
+                       int32_t* __restrict__ out_nbr, int32_t* __restrict__ out_eidx,
+                       float* __restrict__ out_etime, float* __restrict__ out_dt) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t base = warp * 32; base < Q; base += nwarps * 32) {
+        const int64_t q = base + lane;
+        long long end = 0;
+        int cnt = 0;
+        double t = 0.0;
+        if (q < Q) {
+            const int node = q_nodes[q];
+            t = q_ts[q];
+            const int64_t lo = rowptr[node], hi = rowptr[node + 1];
+            end = lower_bound_ts(adj_ts, lo, hi, t);
+            const int64_t c = end - lo;
+            cnt = c > n ? n : (int)c;          // only the most recent n are ever taken (utils.py:207-209)
+        }
+        const int nq = (Q - base) < 32 ? (int)(Q - base) : 32;
+        const int total = nq * n;
+        for (int e0 = 0; e0 < total; e0 += 32) {
+            const int e = e0 + lane;
+            const bool live = e < total;
+            const int ql = live ? e / n : 0;
+            const long long end_q = __shfl_sync(0xffffffffu, end, ql);
+            const int cnt_q = __shfl_sync(0xffffffffu, cnt, ql);
+            const double t_q = __shfl_sync(0xffffffffu, t, ql);
+            if (live) {
+                const int j = e - ql * n;
+                const int jj = j - (n - cnt_q);      // right-aligned, left zero-padded (utils.py:216-218)
+                int nb = 0, ei = 0;
+                float tt = 0.0f;
+                if (jj >= 0) {
+                    const int64_t idx = end_q - cnt_q + jj;
+                    nb = __ldg(adj_nbr + idx);
+                    ei = __ldg(adj_eidx + idx);
+                    tt = (float)__ldg(adj_ts + idx);   // fp32 edge time (utils.py:179-180)
+                }
+                const int64_t o = base * n + e;
+                out_nbr[o] = nb;
+                out_eidx[o] = ei;
+                out_etime[o] = tt;
+                // fp64 subtraction of the fp32-rounded edge time, then fp32 (embedding_module.py:133-135)
+                out_dt[o] = (float)(t_q - (double)tt);
+            }
+        }
+    }
+}
+
+#define PFO_MAX_UNIFORM_NBR 64
+
+__global__ void __launch_bounds__(128)
+neighbor_uniform_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ adj_nbr,
+                        const int32_t* __restrict__ adj_eidx, const double* __restrict__ adj_ts,
+                        const int32_t* __restrict__ q_nodes, const double* __restrict__ q_ts,
+                        int64_t Q, int n, uint32_t k0, uint32_t k1, uint32_t call_id,
+                        int32_t* __restrict__ out_nbr, int32_t* __restrict__ out_eidx,
+                        float* __restrict__ out_etime, float* __restrict__ out_dt) {
+    // uniform-with-replacement mode (utils.py:193-204); slot j of query q draws
+    // pos = mulhi32(philox(q, call_id, j, PURPOSE_NBR).x, i) and the picks are ordered by
+    // (fp32 time, position): see oracle/graph.py for the contract.
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < Q; q += (int64_t)gridDim.x * blockDim.x) {
+        const int node = q_nodes[q];
+        const double t = q_ts[q];
+        const int64_t lo = rowptr[node], hi = rowptr[node + 1];
+        const uint32_t cnt = (uint32_t)(lower_bound_ts(adj_ts, lo, hi, t) - lo);
+        uint32_t pos[PFO_MAX_UNIFORM_NBR];
+        float tt[PFO_MAX_UNIFORM_NBR];
+        const int64_t o = q * n;
+        if (cnt == 0) {
+            for (int j = 0; j < n; ++j) {
+                out_nbr[o + j] = 0; out_eidx[o + j] = 0; out_etime[o + j] = 0.0f; out_dt[o + j] = (float)t;
+            }
+            continue;
+        }
+        for (int j = 0; j < n; ++j) {
+            const uint32_t p = mulhi32(philox4x32_10((uint32_t)q, call_id, (uint32_t)j, PFO_PURPOSE_NBR, k0, k1).x, cnt);
+            const float tj = (float)__ldg(adj_ts + lo + p);
+            int k = j;                                   // insertion sort by (time, position)
+            while (k > 0 && (tt[k - 1] > tj || (tt[k - 1] == tj && pos[k - 1] > p))) {
+                tt[k] = tt[k - 1]; pos[k] = pos[k - 1]; --k;
+            }
+            tt[k] = tj; pos[k] = p;
+        }
+        for (int j = 0; j < n; ++j) {
+            out_nbr[o + j] = __ldg(adj_nbr + lo + pos[j]);
+            out_eidx[o + j] = __ldg(adj_eidx + lo + pos[j]);
+            out_etime[o + j] = tt[j];
+            out_dt[o + j] = (float)(t - (double)tt[j]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- touched-node compaction
+__global__ void mark_nodes_kernel(const int32_t* __restrict__ ids, int64_t count, int skip_zero,
+                                  uint32_t* __restrict__ bitmap) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        const int v = ids[i];
+        if (v > 0 || (v == 0 && !skip_zero)) atomicOr(bitmap + (v >> 5), 1u << (v & 31));
+    }
+}
+
+constexpr int kCompactBlock = 256;
+constexpr int kWordsPerThread = 4;
+constexpr int kWordsPerBlock = kCompactBlock * kWordsPerThread;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
+    // 256 threads; returns the exclusive prefix of v, *total = block sum
+    __shared__ int warp_tot[kCompactBlock / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) warp_tot[w] = inc;
+    __syncthreads();
+    int off = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < kCompactBlock / 32; ++i) {
+        int x = warp_tot[i];
+        if (i < w) off += x;
+        tot += x;
+    }
+    __syncthreads();
+    *total = tot;
+    return off + inc - v;
+}
+
+__global__ void __launch_bounds__(kCompactBlock)
+compact_count_kernel(const uint32_t* __restrict__ bitmap, int64_t n_words, int32_t* __restrict__ block_sums) {
+    const int64_t w0 = (int64_t)blockIdx.x * kWordsPerBlock + (int64_t)threadIdx.x * kWordsPerThread;
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < kWordsPerThread; ++k)
+        if (w0 + k < n_words) c += __popc(bitmap[w0 + k]);
+    int tot;
+    block_exclusive_scan(c, &tot);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(kCompactBlock)
+compact_scan_kernel(int32_t* __restrict__ block_sums, int n_blocks, int32_t* __restrict__ n_unique) {
+    // single CTA: exclusive scan of the per-block counts, in place
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_blocks; base += kCompactBlock) {
+        const int i = base + threadIdx.x;
+        const int v = i < n_blocks ? block_sums[i] : 0;
+        int tot;
+        const int ex = block_exclusive_scan(v, &tot);
+        const int c = carry;
+        if (i < n_blocks) block_sums[i] = c + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_unique = carry;
+}
+
+__global__ void __launch_bounds__(kCompactBlock)
+compact_emit_kernel(uint32_t* __restrict__ bitmap, int64_t n_words, const int32_t* __restrict__ block_offs,
+                    int32_t* __restrict__ uniq_ids, int32_t* __restrict__ slot_of_node) {
+    const int64_t w0 = (int64_t)blockIdx.x * kWordsPerBlock + (int64_t)threadIdx.x * kWordsPerThread;
+    uint32_t words[kWordsPerThread];
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < kWordsPerThread; ++k) {
+        words[k] = (w0 + k < n_words) ? bitmap[w0 + k] : 0u;
+        c += __popc(words[k]);
+    }
+    int tot;
+    int pos = block_offs[blockIdx.x] + block_exclusive_scan(c, &tot);
+#pragma unroll
+    for (int k = 0; k < kWordsPerThread; ++k) {
+        uint32_t w = words[k];
+        if (w) bitmap[w0 + k] = 0u;            // leave the bitmap clean for the next batch
+        while (w) {
+            const int b = __ffs(w) - 1;
+            w &= w - 1;
+            const int node = (int)((w0 + k) * 32 + b);
+            uniq_ids[pos] = node;              // ascending node id -> deterministic order
+            slot_of_node[node] = pos;
+            ++pos;
+        }
+    }
+}
+
+__global__ void map_slots_kernel(const int32_t* __restrict__ ids, int64_t count, int skip_zero,
+                                 const int32_t* __restrict__ slot_of_node, int32_t* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        const int v = ids[i];
+        out[i] = (v > 0 || (v == 0 && !skip_zero)) ? slot_of_node[v] : -1;
+    }
+}
+
+}  // namespace
+
+PFO_API int pfo_neighbor_sample(const int64_t* rowptr, const int32_t* adj_nbr, const int32_t* adj_eidx,
+                                const double* adj_ts, const int32_t* q_nodes, const double* q_ts,
+                                int64_t n_queries, int n_neighbors, int uniform, uint64_t seed, uint32_t call_id,
+                                int32_t* out_nbr, int32_t* out_eidx, float* out_etime, float* out_dt,
+                                void* stream) {
+    if (n_queries <= 0) return 0;
+    if (n_neighbors <= 0) return (int)cudaErrorInvalidValue;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (uniform) {
+        if (n_neighbors > PFO_MAX_UNIFORM_NBR) return (int)cudaErrorInvalidValue;
+        neighbor_uniform_kernel<<<pfo_grid(n_queries, 128, 8), 128, 0, s>>>(
+            rowptr, adj_nbr, adj_eidx, adj_ts, q_nodes, q_ts, n_queries, n_neighbors,
+            (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), call_id, out_nbr, out_eidx, out_etime, out_dt);
+    } else {
+        neighbor_recent_kernel<<<pfo_grid(n_queries, 256, 8), 256, 0, s>>>(
+            rowptr, adj_nbr, adj_eidx, adj_ts, q_nodes, q_ts, n_queries, n_neighbors,
+            out_nbr, out_eidx, out_etime, out_dt);
+    }
+    PFO_LAUNCH_CHECK();
+}
+
+PFO_API int pfo_abi_version(void) { return PFO_ABI_VERSION; }
+
+PFO_API int pfo_mark_nodes(const int32_t* ids, int64_t count, int skip_zero, uint32_t* bitmap, void* stream) {
+    if (count <= 0) return 0;
+    mark_nodes_kernel<<<pfo_grid(count, 256, 8), 256, 0, (cudaStream_t)stream>>>(ids, count, skip_zero, bitmap);
+    PFO_LAUNCH_CHECK();
+}
+
+PFO_API int64_t pfo_compact_workspace_ints(int64_t n_nodes) {
+    const int64_t n_words = (n_nodes + 31) / 32;
+    return (n_words + kWordsPerBlock - 1) / kWordsPerBlock + 1;
+}
+
+PFO_API int pfo_compact_nodes(uint32_t* bitmap, int64_t n_nodes, int32_t* workspace, int32_t* uniq_ids,
+                              int32_t* slot_of_node, int32_t* n_unique, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t n_words = (n_nodes + 31) / 32;
+    const int n_blocks = (int)((n_words + kWordsPerBlock - 1) / kWordsPerBlock);
+    compact_count_kernel<<<n_blocks, kCompactBlock, 0, s>>>(bitmap, n_words, workspace);
+    compact_scan_kernel<<<1, kCompactBlock, 0, s>>>(workspace, n_blocks, n_unique);
+    compact_emit_kernel<<<n_blocks, kCompactBlock, 0, s>>>(bitmap, n_words, workspace, uniq_ids, slot_of_node);
+    PFO_LAUNCH_CHECK();
+}
+
+PFO_API int pfo_map_slots(const int32_t* ids, int64_t count, int skip_zero, const int32_t* slot_of_node,
+                          int32_t* out, void* stream) {
+    if (count <= 0) return 0;
+    map_slots_kernel<<<pfo_grid(count, 256, 8), 256, 0, (cudaStream_t)stream>>>(ids, count, skip_zero, slot_of_node, out);
+    PFO_LAUNCH_CHECK();
+}

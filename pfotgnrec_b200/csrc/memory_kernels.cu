@@ -1,0 +1,373 @@
+// K2/K3 glue: the dense pending-message table, the lazy memory updater gates, persist,
+// and message construction with last-wins scatter.
+//
+// Replaces the reference's dict-of-lists message store and its per-node Python loops:
+//   modules/memory.py:35-37,73-75 (store / clear), modules/message_aggregator.py:38-55
+//   (`last` aggregator), modules/memory_updater.py:18-53 (GRU/RNN update, functional and
+//   in place) and model/tgn.py:357-378 (get_raw_messages).
+// State layout in HBM (all fp32 unless noted), N = n_nodes:
+//   memory[N, d], last_update[N], pend_msg[N, RAWP], pend_ts[N], pend_valid[N] (u8),
+//   last_pos[N] (i32 scratch, -1 when idle).
+// RAW = 2d + F + d floats per message, rows padded to RAWP (multiple of 4).
+#include "common.cuh"
+
+namespace {
+
+// ---- gates: cell outputs for the unique touched nodes -------------------------------
+// cell: 0 = GRU (GI/GH hold [r | z | n] pre-activations, 3d wide), 1 = RNN (d wide),
+//       2 = no memory (H0 = node features only).
+__global__ void __launch_bounds__(256)
+cell_forward_kernel(const int32_t* __restrict__ uniq, const int32_t* __restrict__ n_uniq, int64_t u_max, int d,
+                    int cell, const float* __restrict__ GI, const float* __restrict__ GH, int64_t ldg,
+                    const float* __restrict__ HG, const uint8_t* __restrict__ valid_u,
+                    const float* __restrict__ node_feat, float* __restrict__ Hnew, float* __restrict__ H0) {
+    int64_t U = *n_uniq; if (U > u_max) U = u_max;
+    const int64_t total = U * d;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t u = i / d;
+        const int c = (int)(i - u * d);
+        const int node = uniq[u];
+        const float nf = node_feat[(int64_t)node * d + c];
+        if (cell == 2) { H0[i] = nf; continue; }
+        const float h = HG[i];
+        float hn = h;
+        if (valid_u[u]) {
+            const float* gi = GI + u * ldg;
+            const float* gh = GH + u * ldg;
+            if (cell == 0) {
+                // torch GRUCell: r,z = sigmoid(i + h); n = tanh(i_n + r * h_n); h' = n + z * (h - n)
+                const float r = sigmoidf_(gi[c] + gh[c]);
+                const float z = sigmoidf_(gi[d + c] + gh[d + c]);
+                const float n = tanhf(gi[2 * d + c] + r * gh[2 * d + c]);
+                hn = n + z * (h - n);
+            } else {
+                hn = tanhf(gi[c] + gh[c]);
+            }
+        }
+        Hnew[i] = hn;
+        H0[i] = hn + nf;          // h0 = memory' + node features (embedding_module.py:93-98)
+    }
+}
+
+// backward of the cell w.r.t. its pre-activations (memory and messages are detached inputs)
+__global__ void __launch_bounds__(256)
+cell_backward_kernel(const int32_t* __restrict__ uniq, const int32_t* __restrict__ n_uniq, int64_t u_max, int d,
+                     int cell, const float* __restrict__ GI, const float* __restrict__ GH, int64_t ldg,
+                     const float* __restrict__ HG, const uint8_t* __restrict__ valid_u,
+                     const float* __restrict__ dH, float* __restrict__ dGI, float* __restrict__ dGH) {
+    int64_t U = *n_uniq; if (U > u_max) U = u_max;
+    const int64_t total = U * d;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t u = i / d;
+        const int c = (int)(i - u * d);
+        float* dgi = dGI + u * ldg;
+        float* dgh = dGH + u * ldg;
+        const bool live = valid_u[u] != 0;
+        const float g = dH[i];
+        if (cell == 0) {
+            float dr = 0.f, dz = 0.f, dn = 0.f, dhn = 0.f;
+            if (live) {
+                const float* gi = GI + u * ldg;
+                const float* gh = GH + u * ldg;
+                const float h = HG[i];
+                const float r = sigmoidf_(gi[c] + gh[c]);
+                const float z = sigmoidf_(gi[d + c] + gh[d + c]);
+                const float hn_ = gh[2 * d + c];
+                const float n = tanhf(gi[2 * d + c] + r * hn_);
+                const float dn_ = g * (1.0f - z);
+                dn = dn_ * (1.0f - n * n);            // d pre-activation of n
+                dz = g * (h - n) * z * (1.0f - z);
+                dr = dn * hn_ * r * (1.0f - r);
+                dhn = dn * r;
+            }
+            dgi[c] = dr; dgi[d + c] = dz; dgi[2 * d + c] = dn;
+            dgh[c] = dr; dgh[d + c] = dz; dgh[2 * d + c] = dhn;
+        } else {
+            float dp = 0.f;
+            if (live) {
+                const float y = tanhf(GI[u * ldg + c] + GH[u * ldg + c]);
+                dp = g * (1.0f - y * y);
+            }
+            dgi[c] = dp; dgh[c] = dp;
+        }
+    }
+}
+
+// snapshot of the state rows of the unique touched nodes, taken before persist / store overwrite them:
+// HG = memory rows, XG = pending raw messages, valid_u, lu_u = last_update' (message time if pending)
+__global__ void __launch_bounds__(256)
+gather_state_kernel(const int32_t* __restrict__ uniq, const int32_t* __restrict__ n_uniq, int64_t u_max, int d, int raw,
+                    const float* __restrict__ memory, const float* __restrict__ pend_msg, int64_t rawp,
+                    const uint8_t* __restrict__ pend_valid, const float* __restrict__ pend_ts,
+                    const float* __restrict__ last_update,
+                    float* __restrict__ HG, float* __restrict__ XG, uint8_t* __restrict__ valid_u, float* __restrict__ lu_u) {
+    int64_t U = *n_uniq; if (U > u_max) U = u_max;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t u = warp; u < U; u += nwarps) {
+        const int node = uniq[u];
+        const bool v = pend_valid[node] != 0;
+        const float* m = memory + (int64_t)node * d;
+        for (int c = lane; c < d; c += 32) HG[u * d + c] = m[c];
+        if (XG) {
+            const float* x = pend_msg + (int64_t)node * rawp;
+            for (int c = lane; c < raw; c += 32) XG[u * raw + c] = v ? x[c] : 0.0f;
+        }
+        if (lane == 0) {
+            valid_u[u] = v ? 1 : 0;
+            lu_u[u] = v ? pend_ts[node] : last_update[node];
+        }
+    }
+}
+
+// ---- persist + last-occurrence ranking ----------------------------------------------
+// One warp per (side, event).  Positives with a pending message get memory <- cell output
+// and last_update <- message time (tgn.py:185, memory_updater.py:18-33).  Every positive
+// receives a new message in this batch, so pend_valid is simply re-set by the store kernel.
+__global__ void __launch_bounds__(256)
+persist_rank_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ dst, int B, int d,
+                    const int32_t* __restrict__ slot_of_node, const float* __restrict__ Hnew,
+                    const uint8_t* __restrict__ pend_valid, const float* __restrict__ pend_ts,
+                    float* __restrict__ memory, float* __restrict__ last_update, int32_t* __restrict__ last_pos) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t idx = warp; idx < 2 * (int64_t)B; idx += nwarps) {
+        const int i = (int)(idx % B);
+        const int node = idx < B ? src[i] : dst[i];
+        if (lane == 0) atomicMax(last_pos + node, (int)idx);   // dst-view messages are appended last (tgn.py:205-206)
+        if (pend_valid[node]) {
+            const float* h = Hnew + (int64_t)slot_of_node[node] * d;
+            float* m = memory + (int64_t)node * d;
+            for (int c = lane; c < d; c += 32) m[c] = h[c];
+            if (lane == 0) last_update[node] = pend_ts[node];
+        }
+    }
+}
+
+// One warp per (side, event); only the last occurrence of a node writes (last-wins,
+// message_aggregator.py:49-50).  msg = [mem[self] | mem[other] | edge_feat | cos(dt*w+b)],
+// dt = fp32(t) - last_update[self] in fp32 (tgn.py:359-371).
+__global__ void __launch_bounds__(256)
+store_messages_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                      const int32_t* __restrict__ eidx, const double* __restrict__ ts, int B, int d, int F,
+                      const float* __restrict__ memory, const float* __restrict__ last_update,
+                      const float* __restrict__ edge_feat, const float* __restrict__ tw, const float* __restrict__ tb,
+                      const float* __restrict__ other_emb_for_src, const float* __restrict__ other_emb_for_dst,
+                      float* __restrict__ pend_msg, int64_t rawp, float* __restrict__ pend_ts,
+                      uint8_t* __restrict__ pend_valid, int32_t* __restrict__ last_pos) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t idx = warp; idx < 2 * (int64_t)B; idx += nwarps) {
+        const int i = (int)(idx % B);
+        const bool is_src = idx < B;
+        const int node = is_src ? src[i] : dst[i];
+        const int other = is_src ? dst[i] : src[i];
+        if (last_pos[node] != (int)idx) continue;
+        __syncwarp();
+        const float t32 = (float)ts[i];
+        const float delta = t32 - last_update[node];
+        float* out = pend_msg + (int64_t)node * rawp;
+        const float* ms = memory + (int64_t)node * d;
+        const float* oe = is_src ? other_emb_for_src : other_emb_for_dst;   // dyrep: embedding of the other endpoint
+        const float* mo = oe ? oe + (int64_t)i * d : memory + (int64_t)other * d;
+        const float* ef = edge_feat + (int64_t)eidx[i] * F;
+        for (int c = lane; c < d; c += 32) {
+            out[c] = ms[c];
+            out[d + c] = mo[c];
+            out[2 * d + F + c] = cosf(fmaf(delta, tw[c], tb[c]));   // fmaf == nn.Linear(1, d) (SURVEY hard part 1)
+        }
+        for (int c = lane; c < F; c += 32) out[2 * d + c] = ef[c];
+        __syncwarp();
+        if (lane == 0) {
+            pend_ts[node] = t32;
+            pend_valid[node] = 1;
+            last_pos[node] = -1;
+        }
+    }
+}
+
+// ---- jodie time-projection embedding (embedding_module.py:57-61, tgn.py:260-266) ------
+// emb = mem'[q] * (1 + W * td + b), td = (float(int64(t) - int64(last_update'[q])) - mean) / std
+__global__ void __launch_bounds__(256)
+time_embedding_fwd_kernel(const int32_t* __restrict__ q_nodes, const double* __restrict__ q_ts, int64_t Q,
+                          int64_t n_src, int d, const int32_t* __restrict__ slot_of_node,
+                          const float* __restrict__ Hnew, const float* __restrict__ lu_u,
+                          float mean_src, float std_src, float mean_dst, float std_dst,
+                          const float* __restrict__ W, const float* __restrict__ b,
+                          float* __restrict__ td_out, float* __restrict__ emb) {
+    const int64_t total = Q * d;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = i / d;
+        const int c = (int)(i - q * d);
+        const int node = q_nodes[q];
+        const float lu = lu_u[slot_of_node[node]];
+        const long long diff = (long long)q_ts[q] - (long long)lu;
+        const bool s = q < n_src;
+        const float td = ((float)diff - (s ? mean_src : mean_dst)) / (s ? std_src : std_dst);
+        if (c == 0) td_out[q] = td;
+        emb[i] = Hnew[(int64_t)slot_of_node[node] * d + c] * (1.0f + fmaf(td, W[c], b[c]));
+    }
+}
+
+// block per d-column-slab is overkill; one warp per query row, lane-strided columns, then
+// per-block partial sums for dW/db written to `partial[grid, 2, d]` (deterministic reduce).
+__global__ void __launch_bounds__(256)
+time_embedding_bwd_kernel(const int32_t* __restrict__ q_nodes, int64_t Q, int d,
+                          const int32_t* __restrict__ slot_of_node, const float* __restrict__ Hnew,
+                          const float* __restrict__ td, const float* __restrict__ W, const float* __restrict__ b,
+                          const float* __restrict__ dEmb, float* __restrict__ dHnew, float* __restrict__ partial) {
+    extern __shared__ float sm[];          // [2][d]
+    for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) sm[c] = 0.0f;
+    __syncthreads();
+    const int64_t total = Q * d;
+    // consecutive threads walk consecutive columns so that the smem atomics spread over banks
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = i / d;
+        const int c = (int)(i - q * d);
+        const int node = q_nodes[q];
+        const int64_t hrow = (int64_t)slot_of_node[node] * d + c;
+        const float g = dEmb[i], h = Hnew[hrow], t = td[q];
+        atomicAdd(&sm[c], g * h * t);
+        atomicAdd(&sm[d + c], g * h);
+        atomicAdd(dHnew + hrow, g * (1.0f + fmaf(t, W[c], b[c])));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) partial[(int64_t)blockIdx.x * 2 * d + c] = sm[c];
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int rows, int cols,
+                                       float* __restrict__ out, int accumulate) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x) {
+        float s = 0.0f;
+        for (int r = 0; r < rows; ++r) s += partial[(int64_t)r * cols + c];
+        out[c] = accumulate ? out[c] + s : s;
+    }
+}
+
+// scatter-add rows: dst[idx[m], :] += src[m, :]  (gradient of a row gather)
+__global__ void __launch_bounds__(256)
+scatter_add_rows_kernel(const float* __restrict__ src, int64_t lds, const int32_t* __restrict__ idx, int64_t M, int d,
+                        float* __restrict__ dst, int64_t ldd) {
+    const int64_t total = M * d;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / d;
+        const int c = (int)(i - m * d);
+        const int r = idx[m];
+        if (r >= 0) atomicAdd(dst + (int64_t)r * ldd + c, src[m * lds + c]);
+    }
+}
+
+// gather rows: dst[m, :] = idx[m] >= 0 ? src[idx[m], :] : 0
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ src, int64_t lds, const int32_t* __restrict__ idx, int64_t M, int d,
+                   float* __restrict__ dst, int64_t ldd) {
+    const int64_t total = M * d;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / d;
+        const int c = (int)(i - m * d);
+        const int r = idx[m];
+        dst[m * ldd + c] = r >= 0 ? src[(int64_t)r * lds + c] : 0.0f;
+    }
+}
+
+}  // namespace
+
+PFO_API int pfo_cell_forward(const int32_t* uniq, const int32_t* n_uniq, int64_t u_max, int d, int cell,
+                             const float* GI, const float* GH, int64_t ldg, const float* HG,
+                             const uint8_t* valid_u, const float* node_feat, float* Hnew, float* H0,
+                             void* stream) {
+    if (u_max <= 0) return 0;
+    cell_forward_kernel<<<pfo_grid(u_max * d, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        uniq, n_uniq, u_max, d, cell, GI, GH, ldg, HG, valid_u, node_feat, Hnew, H0);
+    PFO_LAUNCH_CHECK();
+}
+
+PFO_API int pfo_cell_backward(const int32_t* uniq, const int32_t* n_uniq, int64_t u_max, int d, int cell,
+                              const float* GI, const float* GH, int64_t ldg, const float* HG,
+                              const uint8_t* valid_u, const float* dH, float* dGI, float* dGH, void* stream) {
+    if (u_max <= 0) return 0;
+    cell_backward_kernel<<<pfo_grid(u_max * d, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        uniq, n_uniq, u_max, d, cell, GI, GH, ldg, HG, valid_u, dH, dGI, dGH);
+    PFO_LAUNCH_CHECK();
+}
+
+PFO_API int pfo_gather_state(const int32_t* uniq, const int32_t* n_uniq, int64_t u_max, int d, int raw,
+                             const float* memory, const float* pend_msg, int64_t rawp, const uint8_t* pend_valid,
+                             const float* pend_ts, const float* last_update,
+                             float* HG, float* XG, uint8_t* valid_u, float* lu_u, void* stream) {
+    if (u_max <= 0) return 0;
+    gather_state_kernel<<<pfo_grid(u_max * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        uniq, n_uniq, u_max, d, raw, memory, pend_msg, rawp, pend_valid, pend_ts, last_update, HG, XG, valid_u, lu_u);
+    PFO_LAUNCH_CHECK();
+}
+
+PFO_API int pfo_persist_rank(const int32_t* src, const int32_t* dst, int B, int d, const int32_t* slot_of_node,
+                             const float* Hnew, const uint8_t* pend_valid, const float* pend_ts,
+                             float* memory, float* last_update, int32_t* last_pos, void* stream) {
+    if (B <= 0) return 0;
+    persist_rank_kernel<<<pfo_grid(2 * (int64_t)B * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        src, dst, B, d, slot_of_node, Hnew, pend_valid, pend_ts, memory, last_update, last_pos);
+    PFO_LAUNCH_CHECK();
+}
+
+PFO_API int pfo_store_messages(const int32_t* src, const int32_t* dst, const int32_t* eidx, const double* ts,
+                               int B, int d, int F, const float* memory, const float* last_update,
+                               const float* edge_feat, const float* tw, const float* tb,
+                               const float* other_emb_for_src, const float* other_emb_for_dst,
+                               float* pend_msg, int64_t rawp, float* pend_ts, uint8_t* pend_valid,
+                               int32_t* last_pos, void* stream) {
+    if (B <= 0) return 0;
+    store_messages_kernel<<<pfo_grid(2 * (int64_t)B * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        src, dst, eidx, ts, B, d, F, memory, last_update, edge_feat, tw, tb, other_emb_for_src,
+        other_emb_for_dst, pend_msg, rawp, pend_ts, pend_valid, last_pos);
+    PFO_LAUNCH_CHECK();
+}
+
+PFO_API int pfo_time_embedding_fwd(const int32_t* q_nodes, const double* q_ts, int64_t Q, int64_t n_src, int d,
+                                   const int32_t* slot_of_node, const float* Hnew, const float* lu_u,
+                                   float mean_src, float std_src, float mean_dst, float std_dst,
+                                   const float* W, const float* b, float* td_out, float* emb, void* stream) {
+    if (Q <= 0) return 0;
+    time_embedding_fwd_kernel<<<pfo_grid(Q * d, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        q_nodes, q_ts, Q, n_src, d, slot_of_node, Hnew, lu_u,
+        mean_src, std_src, mean_dst, std_dst, W, b, td_out, emb);
+    PFO_LAUNCH_CHECK();
+}
+
+PFO_API int pfo_time_embedding_bwd(const int32_t* q_nodes, int64_t Q, int d, const int32_t* slot_of_node,
+                                   const float* Hnew, const float* td, const float* W, const float* b,
+                                   const float* dEmb, float* dHnew, float* dWdb,
+                                   float* workspace, int64_t workspace_floats, void* stream) {
+    if (Q <= 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    int grid = pfo_grid(Q * d, 256, 2);
+    if ((int64_t)grid * 2 * d > workspace_floats) grid = (int)(workspace_floats / (2 * d));
+    if (grid < 1) return (int)cudaErrorInvalidValue;
+    time_embedding_bwd_kernel<<<grid, 256, 2 * d * sizeof(float), s>>>(q_nodes, Q, d, slot_of_node, Hnew, td, W, b,
+                                                                      dEmb, dHnew, workspace);
+    // partial rows are [dW(d) | db(d)]; dWdb receives the same layout
+    reduce_partials_kernel<<<1, 256, 0, s>>>(workspace, grid, 2 * d, dWdb, 0);
+    PFO_LAUNCH_CHECK();
+}
+
+PFO_API int pfo_reduce_partials(const float* partial, int rows, int cols, float* out, int accumulate, void* stream) {
+    reduce_partials_kernel<<<(cols + 255) / 256, 256, 0, (cudaStream_t)stream>>>(partial, rows, cols, out, accumulate);
+    PFO_LAUNCH_CHECK();
+}
+
+PFO_API int pfo_scatter_add_rows(const float* src, int64_t lds, const int32_t* idx, int64_t M, int d,
+                                 float* dst, int64_t ldd, void* stream) {
+    if (M <= 0) return 0;
+    scatter_add_rows_kernel<<<pfo_grid(M * d, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, lds, idx, M, d, dst, ldd);
+    PFO_LAUNCH_CHECK();
+}
+
+PFO_API int pfo_gather_rows(const float* src, int64_t lds, const int32_t* idx, int64_t M, int d,
+                            float* dst, int64_t ldd, void* stream) {
+    if (M <= 0) return 0;
+    gather_rows_kernel<<<pfo_grid(M * d, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, lds, idx, M, d, dst, ldd);
+    PFO_LAUNCH_CHECK();
+}

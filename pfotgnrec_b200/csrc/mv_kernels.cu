@@ -1,0 +1,279 @@
+// K5: candidate sampling + mean-variance efficient selection.  Compiled with -fmad=false so
+// that the fp64 arithmetic rounds exactly like the numpy oracle (mul and add never fuse).
+//
+// Replaces reference utils/utils.py:65-114 (RandEdgeSampler: np.unique + setdiff1d +
+// np.random.choice per interaction) and the inline per-interaction / per-candidate Python
+// loops of main.py:197-304 (np.cov x21, rankdata x2, argsort x2 per interaction).
+// One warp per interaction: Philox keys over the item universe with a threshold select for
+// the K candidates, lanes 0..K then own one candidate each for y_mv and the rank fusion.
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace {
+
+constexpr int kCap = 256;          // threshold-select buffer per warp
+constexpr int kWarps = 4;
+
+__device__ __forceinline__ int find_pos(const int32_t* __restrict__ items, int M, int v) {
+    int lo = 0, hi = M;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (items[mid] < v) lo = mid + 1; else hi = mid; }
+    return (lo < M && items[lo] == v) ? lo : -1;
+}
+
+__device__ __forceinline__ bool is_held(const int32_t* __restrict__ held, int nP, int v) {
+    for (int k = 0; k < nP; ++k) if (held[k] == v) return true;
+    return false;
+}
+
+// number of distinct held items that belong to the universe (np.setdiff1d semantics)
+__device__ int count_held_in_universe(const int32_t* held, int nP, const int32_t* items, int M, int lane) {
+    int c = 0;
+    for (int k = lane; k < nP; k += 32) {
+        const int v = held[k];
+        bool first = true;
+        for (int k2 = 0; k2 < k; ++k2) if (held[k2] == v) { first = false; break; }
+        if (first && find_pos(items, M, v) >= 0) ++c;
+    }
+    return warp_sum_i(c);
+}
+
+// r-th available universe position when drawing with replacement (utils.py:99-105)
+__device__ int nth_available(const int32_t* items, int M, const int32_t* held, int nP, int r) {
+    // walk the universe positions of the held items in ascending order
+    int pos = r, last = -1;
+    for (;;) {
+        int best = 0x7fffffff;
+        for (int k = 0; k < nP; ++k) {
+            const int hp = find_pos(items, M, held[k]);
+            if (hp > last && hp < best) best = hp;
+        }
+        if (best == 0x7fffffff || best > pos) break;
+        ++pos; last = best;
+    }
+    return pos;
+}
+
+struct MvArgs {
+    const int64_t* event_ids; const int32_t* day_idx; const int32_t* pos_stock;
+    const int64_t* port_ptr; const int32_t* port_items;
+    const int32_t* items; int M;
+    const double* logret; int n_stocks; int T;
+    int B; int K; double gamma; double lam; int n_pos; int n_neg; uint32_t k0, k1; int sample;
+    int32_t* cand; double* y_out; int32_t* p_pos; int32_t* p_neg;
+};
+
+__global__ void __launch_bounds__(kWarps * 32)
+mv_select_kernel(const MvArgs p) {
+    __shared__ unsigned long long keys[kWarps][kCap];
+    __shared__ int counts[kWarps];
+    __shared__ double Ssum[kWarps][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t warp = (int64_t)blockIdx.x * kWarps + wib;
+    const int64_t nwarps = (int64_t)gridDim.x * kWarps;
+    const int K = p.K, C = K + 1, M = p.M, T = p.T;
+    for (int64_t b = warp; b < p.B; b += nwarps) {
+        const int64_t g = p.event_ids[b];
+        const uint32_t g_lo = (uint32_t)(g & 0xffffffffll), g_hi = (uint32_t)((g >> 32) & 0xffffffffll);
+        const int64_t pb = p.port_ptr[b];
+        const int nP = (int)(p.port_ptr[b + 1] - pb);
+        const int32_t* held = p.port_items + pb;
+        const int n_av = M - count_held_in_universe(held, nP, p.items, M, lane);
+        int my_cand = 0;
+        if (lane == 0) my_cand = p.pos_stock[b];
+        if (!p.sample) {
+            if (lane < C) my_cand = p.cand[b * C + lane];
+        } else if (n_av < K) {
+            if (lane >= 1 && lane <= K) {
+                const int j = lane - 1;
+                const uint32_t x0 = philox4x32_10(g_lo, g_hi, (uint32_t)j, PFO_PURPOSE_NEG_REPL, p.k0, p.k1).x;
+                my_cand = p.items[nth_available(p.items, M, held, nP, (int)mulhi32(x0, (uint32_t)n_av))];
+            }
+        } else {
+            // threshold select: expected count ~ K + 4 sqrt(K) + 8 keys below the cut
+            double frac = ((double)K + 4.0 * sqrt((double)K) + 8.0) / (double)n_av;
+            unsigned long long cut = frac >= 1.0 ? 0x100000000ull : (unsigned long long)(frac * 4294967296.0);
+            for (;;) {
+                if (lane == 0) counts[wib] = 0;
+                __syncwarp();
+                for (int base = 0; base < M; base += 32) {
+                    const int pos = base + lane;
+                    bool take = false;
+                    uint32_t x0 = 0;
+                    if (pos < M && !is_held(held, nP, p.items[pos])) {
+                        x0 = philox4x32_10(g_lo, g_hi, (uint32_t)pos, PFO_PURPOSE_NEG, p.k0, p.k1).x;
+                        take = (unsigned long long)x0 < cut;
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, take);
+                    if (m) {
+                        int start = 0;
+                        if (lane == 0) { start = counts[wib]; counts[wib] = start + __popc(m); }
+                        start = __shfl_sync(0xffffffffu, start, 0);
+                        if (take) {
+                            const int slot = start + __popc(m & ((1u << lane) - 1u));
+                            if (slot < kCap) keys[wib][slot] = ((unsigned long long)x0 << 32) | (unsigned)pos;
+                        }
+                    }
+                }
+                __syncwarp();
+                const int cnt = counts[wib];
+                if (cnt > kCap) { cut >>= 1; continue; }
+                if (cnt >= K || cut >= 0x100000000ull) break;
+                cut <<= 1;
+                if (cut > 0x100000000ull) cut = 0x100000000ull;
+            }
+            const int cnt = counts[wib];
+            // rank by counting: the K smallest keys, ascending (keys are unique: position is the low word)
+            for (int i = lane; i < cnt; i += 32) {
+                const unsigned long long ki = keys[wib][i];
+                int rank = 0;
+                for (int t = 0; t < cnt; ++t) rank += keys[wib][t] < ki ? 1 : 0;
+                if (rank < K) p.cand[b * C + 1 + rank] = p.items[(int)(ki & 0xffffffffull)];
+            }
+            __syncwarp();
+            __threadfence_block();
+            if (lane >= 1 && lane <= K) my_cand = p.cand[b * C + lane];
+        }
+        if (lane < C) p.cand[b * C + lane] = my_cand;
+
+        // ---- y_mv (main.py:243-271), closed form, left-to-right fp64 sums ----
+        const double* lr = p.logret + (int64_t)p.day_idx[b] * p.n_stocks * T;
+        if (lane < T) {
+            double s = 0.0;
+            for (int k = 0; k < nP; ++k) s = s + lr[(int64_t)held[k] * T + lane];
+            Ssum[wib][lane] = s;
+        }
+        __syncwarp();
+        double y = 0.0;
+        if (lane < C) {
+            const double* r = lr + (int64_t)my_cand * T;
+            double acc = 0.0;
+            for (int t = 0; t < T; ++t) acc = acc + r[t];
+            const double mu = acc / (double)T;
+            double v = 0.0;
+            for (int t = 0; t < T; ++t) { const double dc = r[t] - mu; v = v + dc * dc; }
+            const double var = v / (double)(T - 1);
+            if (nP == 0) {
+                y = (mu / p.gamma) / var;
+            } else {
+                double ms = 0.0;
+                for (int t = 0; t < T; ++t) ms = ms + Ssum[wib][t];
+                ms = ms / (double)T;
+                double cv = 0.0;
+                for (int t = 0; t < T; ++t) { const double dc = r[t] - mu; cv = cv + dc * (Ssum[wib][t] - ms); }
+                const double cov = cv / (double)(T - 1);
+                y = (mu / p.gamma - 0.5 * (cov / (double)nP)) / var;
+            }
+            if (p.y_out) p.y_out[b * C + lane] = y;
+        }
+        // ---- rank fusion (main.py:282-292): rankdata(average) + stable argsort ----
+        int less = 0, eq = 0;
+        for (int c = 0; c < C; ++c) {
+            const double yc = __shfl_sync(0xffffffffu, y, c);
+            less += yc < y ? 1 : 0;
+            eq += yc == y ? 1 : 0;
+        }
+        const double invest = (double)less + (double)(eq + 1) / 2.0;
+        const double pref = (double)(C - lane);
+        const double a1 = invest * p.lam;
+        const double a2 = pref * (1.0 - p.lam);
+        const double nr = a1 + a2;
+        int position = 0;
+        for (int c = 0; c < C; ++c) {
+            const double nc = __shfl_sync(0xffffffffu, nr, c);
+            position += (nc < nr || (nc == nr && c < lane)) ? 1 : 0;
+        }
+        if (lane < C) {
+            const int desc = K - position;            // index in argsort(new_rank)[::-1]
+            if (desc < p.n_pos) p.p_pos[b * p.n_pos + desc] = my_cand;
+            if (desc >= C - p.n_neg) p.p_neg[b * p.n_neg + (desc - (C - p.n_neg))] = my_cand;
+        }
+        __syncwarp();
+    }
+}
+
+// ---- general candidate sampler (evaluation: size = N_ITEMS) --------------------------
+// one CTA per interaction; without replacement = full bitonic sort of (draw, position) keys.
+__global__ void __launch_bounds__(256)
+sample_candidates_kernel(const int64_t* __restrict__ event_ids, const int64_t* __restrict__ port_ptr,
+                         const int32_t* __restrict__ port_items, const int32_t* __restrict__ items, int M,
+                         int size, uint32_t k0, uint32_t k1, int pow2, int32_t* __restrict__ out) {
+    extern __shared__ unsigned long long sk[];      // [pow2]
+    __shared__ int n_held_s;
+    const int b = blockIdx.x;
+    const int64_t g = event_ids[b];
+    const uint32_t g_lo = (uint32_t)(g & 0xffffffffll), g_hi = (uint32_t)((g >> 32) & 0xffffffffll);
+    const int64_t pb = port_ptr[b];
+    const int nP = (int)(port_ptr[b + 1] - pb);
+    const int32_t* held = port_items + pb;
+    if (threadIdx.x < 32) {
+        const int c = count_held_in_universe(held, nP, items, M, threadIdx.x);
+        if (threadIdx.x == 0) n_held_s = c;
+    }
+    __syncthreads();
+    const int n_av = M - n_held_s;
+    if (n_av < size) {
+        for (int j = threadIdx.x; j < size; j += blockDim.x) {
+            const uint32_t x0 = philox4x32_10(g_lo, g_hi, (uint32_t)j, PFO_PURPOSE_NEG_REPL, k0, k1).x;
+            out[(int64_t)b * size + j] = items[nth_available(items, M, held, nP, (int)mulhi32(x0, (uint32_t)n_av))];
+        }
+        return;
+    }
+    for (int pos = threadIdx.x; pos < pow2; pos += blockDim.x) {
+        unsigned long long k = ~0ull;
+        if (pos < M && !is_held(held, nP, items[pos]))
+            k = ((unsigned long long)philox4x32_10(g_lo, g_hi, (uint32_t)pos, PFO_PURPOSE_NEG, k0, k1).x << 32) | (unsigned)pos;
+        sk[pos] = k;
+    }
+    __syncthreads();
+    for (int kk = 2; kk <= pow2; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < pow2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = sk[i], c = sk[ixj];
+                    const bool up = (i & kk) == 0;
+                    if ((a > c) == up) { sk[i] = c; sk[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int j = threadIdx.x; j < size; j += blockDim.x)
+        out[(int64_t)b * size + j] = items[(int)(sk[j] & 0xffffffffull)];
+}
+
+}  // namespace
+
+PFO_API int pfo_mv_select(const int64_t* event_ids, const int32_t* day_idx, const int32_t* pos_stock,
+                          const int64_t* port_ptr, const int32_t* port_items,
+                          const int32_t* items_sorted, int n_items_universe,
+                          const double* logret, int n_stocks, int n_returns,
+                          int B, int K, double gamma, double lam, int n_pos, int n_neg, uint64_t seed, int sample,
+                          int32_t* cand, double* y_out, int32_t* p_pos, int32_t* p_neg, void* stream) {
+    if (B <= 0) return 0;
+    if (K < 1 || K > 31 || n_returns > 32 || n_returns < 2 || n_pos + n_neg > K + 1) return (int)cudaErrorInvalidValue;
+    MvArgs a{event_ids, day_idx, pos_stock, port_ptr, port_items, items_sorted, n_items_universe,
+             logret, n_stocks, n_returns, B, K, gamma, lam, n_pos, n_neg,
+             (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), sample, cand, y_out, p_pos, p_neg};
+    mv_select_kernel<<<pfo_grid((int64_t)B * 32, kWarps * 32, 8), kWarps * 32, 0, (cudaStream_t)stream>>>(a);
+    PFO_LAUNCH_CHECK();
+}
+
+PFO_API int pfo_sample_candidates(const int64_t* event_ids, const int64_t* port_ptr, const int32_t* port_items,
+                                  const int32_t* items_sorted, int n_items_universe, int B, int size,
+                                  uint64_t seed, int32_t* out, void* stream) {
+    if (B <= 0 || size <= 0) return 0;
+    int pow2 = 1;
+    while (pow2 < n_items_universe) pow2 <<= 1;
+    if (pow2 > 16384) return (int)cudaErrorInvalidValue;
+    const size_t smem = (size_t)pow2 * sizeof(unsigned long long);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(sample_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        attr_set = true;
+    }
+    sample_candidates_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(
+        event_ids, port_ptr, port_items, items_sorted, n_items_universe, size,
+        (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), pow2, out);
+    PFO_LAUNCH_CHECK();
+}

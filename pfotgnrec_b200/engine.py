@@ -1,0 +1,533 @@
+"""Step engine: dense TGN state on the device + the kernel sequence of one batch.
+
+Host-side orchestration of the path reference model/tgn.py:102-327 walks
+(get_updated_memory -> compute_embedding -> update_memory -> get_raw_messages -> store), on
+the restatements of SURVEY.md section 7: dense pending-message table, lazy memory update on
+the unique touched nodes only, one cell evaluation for both the functional and the persisted
+view, CSR adjacency.  All arithmetic runs in libpfo_b200.so; torch is used for buffers,
+streams and the autograd plumbing (`TGNStepFunction`).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ptr
+
+CELL_GRU, CELL_RNN, CELL_NONE = 0, 1, 2
+
+
+@dataclass
+class ModelConfig:
+    d: int                      # node-feature / memory / time-encoding dimension
+    n_edge_feat: int
+    n_layers: int = 1
+    n_heads: int = 2
+    use_memory: bool = True
+    updater: str = "gru"        # "gru" | "rnn"
+    embedding: str = "graph_attention"   # "graph_attention" | "time" | "identity"
+    dyrep: bool = False
+    dst_emb_in_msg: bool = False
+    shift: tuple = (0.0, 1.0, 0.0, 1.0)  # mean/std time shift src, dst
+    dropout: float = 0.0
+    gemm_mode: str = "fp32"     # "fp32" (FFMA, 1e-5 contract) | "bf16" (tcgen05, 2e-2 contract)
+
+    @property
+    def E(self):                # attention embed dim = d + time dim
+        return 2 * self.d
+
+    @property
+    def Ek(self):               # key / value input dim
+        return 2 * self.d + self.n_edge_feat
+
+    @property
+    def ekp(self):
+        return (self.Ek + 1 + 3) // 4 * 4
+
+    @property
+    def raw(self):              # raw message width
+        return 3 * self.d + self.n_edge_feat
+
+    @property
+    def rawp(self):
+        return (self.raw + 3) // 4 * 4
+
+    @property
+    def cell(self):
+        if not self.use_memory:
+            return CELL_NONE
+        return CELL_GRU if self.updater == "gru" else CELL_RNN
+
+    @property
+    def gates(self):
+        return 3 if self.updater == "gru" else 1
+
+
+class TGNState:
+    """memory / last_update / pending messages of every node, resident in HBM.
+
+    Dense restatement of reference modules/memory.py:8-75 (`Memory.memory`, `.last_update`,
+    `.messages`)."""
+
+    def __init__(self, n_nodes: int, cfg: ModelConfig, device):
+        self.n_nodes, self.cfg, self.device = n_nodes, cfg, torch.device(device)
+        N, d = n_nodes, cfg.d
+        dev = self.device
+        self.memory = torch.zeros(N, d, device=dev)
+        self.last_update = torch.zeros(N, device=dev)
+        self.pend_msg = torch.zeros(N, cfg.rawp, device=dev)
+        self.pend_ts = torch.zeros(N, device=dev)
+        self.pend_valid = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self.last_pos = torch.full((N,), -1, dtype=torch.int32, device=dev)
+        self.bitmap = torch.zeros((N + 31) // 32, dtype=torch.int32, device=dev)
+        self.slot_of_node = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.compact_ws = torch.zeros(int(_lib.query("pfo_compact_workspace_ints", N)) if dev.type == "cuda" else 1,
+                                      dtype=torch.int32, device=dev)
+        self.n_unique = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def reset(self):
+        """reference modules/memory.py:23-33 (__init_memory__)."""
+        self.memory.zero_()
+        self.last_update.zero_()
+        self.pend_valid.zero_()
+        self.pend_ts.zero_()
+        self.pend_msg.zero_()
+
+    def backup(self):
+        return tuple(t.clone() for t in (self.memory, self.last_update, self.pend_msg, self.pend_ts, self.pend_valid))
+
+    def restore(self, b):
+        for dst, src in zip((self.memory, self.last_update, self.pend_msg, self.pend_ts, self.pend_valid), b):
+            dst.copy_(src)
+
+
+def _linear(cfg, A, lda, a_idx, W, ldw, wt, bias, C, ldc, M, N, K, *, m_dev=None, alpha=1.0, act=0,
+            row_zero=None, relu_gate=None, ld_gate=0, accumulate=0, brs=None, ld_brs=0):
+    name = "pfo_linear_f32" if cfg.gemm_mode == "fp32" else "pfo_linear_bf16"
+    _lib.call(name, A, lda, a_idx, W, ldw, int(wt), bias, brs, ld_brs, C, ldc, M, m_dev, N, K,
+              float(alpha), int(act), row_zero, relu_gate, ld_gate, int(accumulate))
+
+
+class _Workspace:
+    """Scratch for the two-stage deterministic reductions."""
+
+    def __init__(self, device):
+        self.device = device
+        self.buf = None
+
+    def get(self, n_floats):
+        if self.buf is None or self.buf.numel() < n_floats:
+            self.buf = torch.empty(max(int(n_floats), 1 << 20), device=self.device)
+        return self.buf
+
+
+def _wgrad(ws, G, ldg, A, lda, a_idx, M, N, K, dW, lddw, db, *, m_dev=None, accumulate=0):
+    need = _lib.query("pfo_wgrad_workspace_floats", M, N, K, 1 if db is not None else 0)
+    buf = ws.get(need)
+    _lib.call("pfo_wgrad_f32", G, ldg, A, lda, a_idx, M, m_dev, N, K, dW, lddw, db, int(accumulate), ptr(buf))
+
+
+F4 = 4  # sizeof(float)
+
+
+class _LayerTape:
+    """Everything one attention-layer invocation saves for its backward."""
+    __slots__ = ("layer", "M", "n", "Tq", "qidx", "T", "idx", "eidx", "dt", "CAT", "QP", "QK", "XB", "P",
+                 "invalid", "ATT", "H1", "OUT", "child_q", "child_n", "dTq", "dT", "step")
+
+
+class TGNEngine:
+    """One model instance bound to a state, node/edge feature tables and a neighbour finder."""
+
+    def __init__(self, cfg: ModelConfig, state: Optional[TGNState], node_feat: torch.Tensor,
+                 edge_feat: torch.Tensor, neighbor_finder):
+        assert cfg.d % 32 == 0 and cfg.d <= 128, "kernels are specialised for d in {32,64,96,128}"
+        assert cfg.E % cfg.n_heads == 0
+        self.cfg, self.state = cfg, state
+        self.node_feat = node_feat.contiguous()
+        self.edge_feat = edge_feat.contiguous()
+        self.nf = neighbor_finder
+        self.device = node_feat.device
+        self.n_nodes = node_feat.shape[0]
+        self.ws = _Workspace(self.device)
+        self.step_id = 0
+        self.seed = 0
+        if state is None:        # memory-less models still need the compaction scratch
+            self.state = TGNState(self.n_nodes, ModelConfig(d=cfg.d, n_edge_feat=cfg.n_edge_feat), self.device)
+
+    # ------------------------------------------------------------------ parameter packing
+    def param_names(self):
+        c = self.cfg
+        names = ["time_encoder.w.weight", "time_encoder.w.bias"]
+        if c.use_memory:
+            pre = "memory_updater.memory_updater."
+            names += [pre + "weight_ih", pre + "weight_hh", pre + "bias_ih", pre + "bias_hh"]
+        if c.embedding == "graph_attention":
+            for l in range(c.n_layers):
+                a = f"embedding_module.attention_models.{l}."
+                names += [a + "multi_head_target.q_proj_weight", a + "multi_head_target.k_proj_weight",
+                          a + "multi_head_target.v_proj_weight", a + "multi_head_target.in_proj_bias",
+                          a + "multi_head_target.out_proj.weight", a + "multi_head_target.out_proj.bias",
+                          a + "merger.fc1.weight", a + "merger.fc1.bias", a + "merger.fc2.weight",
+                          a + "merger.fc2.bias"]
+        elif c.embedding == "time":
+            names += ["embedding_module.embedding_layer.weight", "embedding_module.embedding_layer.bias"]
+        return names
+
+    def _pack(self, params):
+        """Derived, kernel-friendly tensors built with torch autograd ops on the reference-named
+        parameters (tiny; gradients flow back through them to the parameters)."""
+        c = self.cfg
+        d, E, Ek, H = c.d, c.E, c.Ek, c.n_heads
+        hd = E // H
+        tw = params["time_encoder.w.weight"].reshape(d)
+        tb = params["time_encoder.w.bias"]
+        flat = [tw.contiguous(), tb.contiguous()]
+        if c.use_memory:
+            pre = "memory_updater.memory_updater."
+            flat += [params[pre + "weight_ih"].contiguous(), params[pre + "weight_hh"].contiguous(),
+                     params[pre + "bias_ih"].contiguous(), params[pre + "bias_hh"].contiguous()]
+        if c.embedding == "graph_attention":
+            te0 = torch.cos(tb)                                  # TimeEncode(0) (embedding_module.py:92)
+            for l in range(c.n_layers):
+                a = f"embedding_module.attention_models.{l}."
+                Wq = params[a + "multi_head_target.q_proj_weight"]
+                Wk = params[a + "multi_head_target.k_proj_weight"]
+                Wv = params[a + "multi_head_target.v_proj_weight"]
+                b_in = params[a + "multi_head_target.in_proj_bias"]
+                cq = Wq[:, d:] @ te0 + b_in[:E]                  # query bias incl. the constant time part
+                WvA = torch.cat([Wv.view(H, hd, Ek), b_in[2 * E:].view(H, hd, 1),
+                                 Wv.new_zeros(H, hd, c.ekp - Ek - 1)], dim=2)
+                flat += [Wq.contiguous(), cq.contiguous(), Wk.contiguous(), WvA.contiguous(),
+                         params[a + "multi_head_target.out_proj.weight"].contiguous(),
+                         params[a + "multi_head_target.out_proj.bias"].contiguous(),
+                         params[a + "merger.fc1.weight"].contiguous(), params[a + "merger.fc1.bias"].contiguous(),
+                         params[a + "merger.fc2.weight"].contiguous(), params[a + "merger.fc2.bias"].contiguous()]
+        elif c.embedding == "time":
+            flat += [params["embedding_module.embedding_layer.weight"].reshape(d).contiguous(),
+                     params["embedding_module.embedding_layer.bias"].contiguous()]
+        return flat
+
+    # ------------------------------------------------------------------ public step
+    def compute_temporal_embeddings(self, params, src, dst, extra_groups, ts, eidx, n_neighbors,
+                                    train=True, update_state=True):
+        """src/dst int32[B], extra_groups list of int32[k*B] (interaction-major), ts float64[B],
+        eidx int32[B] -- all device tensors.  Returns [emb_src, emb_dst, *emb_extra] ([.,d] fp32,
+        differentiable w.r.t. `params` when grad mode is on) and advances memory / messages."""
+        groups = [src, dst] + list(extra_groups)
+        B = src.shape[0]
+        q_nodes = torch.cat(groups)
+        q_ts = torch.cat([ts if g.shape[0] == B else ts.repeat_interleave(g.shape[0] // B) for g in groups])
+        flat = self._pack(params)
+        batch = dict(src=src, dst=dst, ts=ts, eidx=eidx, q_nodes=q_nodes, q_ts=q_ts, n=int(n_neighbors),
+                     B=B, train=bool(train), update_state=bool(update_state))
+        emb = TGNStepFunction.apply(self, batch, *flat)
+        return list(torch.split(emb, [g.shape[0] for g in groups]))
+
+    # ------------------------------------------------------------------ forward internals
+    def _sample_tree(self, nodes, ts, layer, n):
+        """Neighbour sampling in the call order of the reference recursion
+        (modules/embedding_module.py:115-145): inner queries, own call, inner neighbours."""
+        if layer == 0:
+            return None
+        M = nodes.shape[0]
+        child_q = self._sample_tree(nodes, ts, layer - 1, n)
+        nbr, eidx, _etime, dt = self.nf.sample(nodes, ts, n)
+        n_eff = nbr.shape[1]
+        child_n = self._sample_tree(nbr.reshape(-1), ts.repeat_interleave(n_eff), layer - 1, n) if layer > 1 else None
+        return dict(layer=layer, M=M, nodes=nodes, nbr=nbr, eidx=eidx, dt=dt, child_q=child_q, child_n=child_n)
+
+    def _collect_level0(self, tree, out):
+        if tree["layer"] == 1:
+            out.append(tree["nodes"])
+            out.append(tree["nbr"].reshape(-1))
+        else:
+            self._collect_level0(tree["child_q"], out)
+            self._collect_level0(tree["child_n"], out)
+
+    def _unique_nodes(self, id_lists):
+        st = self.state
+        total = 0
+        for ids in id_lists:
+            _lib.call("pfo_mark_nodes", ptr(ids), ids.numel(), 1, ptr(st.bitmap))
+            total += ids.numel()
+        u_max = min(total, self.n_nodes)
+        uniq = torch.zeros(u_max, dtype=torch.int32, device=self.device)
+        _lib.call("pfo_compact_nodes", ptr(st.bitmap), self.n_nodes, ptr(st.compact_ws), ptr(uniq),
+                  ptr(st.slot_of_node), ptr(st.n_unique))
+        return uniq, u_max
+
+    def _slots(self, ids):
+        out = torch.empty(ids.shape, dtype=torch.int32, device=self.device)
+        _lib.call("pfo_map_slots", ptr(ids), ids.numel(), 1, ptr(self.state.slot_of_node), ptr(out))
+        return out
+
+    def _attention_forward(self, tree, W, H0, save):
+        """Returns (OUT [M,d], tape)."""
+        c = self.cfg
+        d, E, Ek, H, ekp, F = c.d, c.E, c.Ek, c.n_heads, c.ekp, c.n_edge_feat
+        hd = E // H
+        dev = self.device
+        layer, M = tree["layer"], tree["M"]
+        n = tree["nbr"].shape[1]
+        Wq, cq, Wk, WvA, Wo, bo, W1, b1, W2, b2 = W[layer - 1]
+        tp = _LayerTape()
+        tp.layer, tp.M, tp.n = layer, M, n
+        tp.child_q = tp.child_n = None
+        if layer == 1:
+            tp.Tq, tp.qidx = H0, self._slots(tree["nodes"])
+            tp.T, tp.idx = H0, self._slots(tree["nbr"].reshape(-1)).view(M, n)
+        else:
+            out_q, tp.child_q = self._attention_forward(tree["child_q"], W, H0, save)
+            out_n, tp.child_n = self._attention_forward(tree["child_n"], W, H0, save)
+            ar = torch.arange(M * n, dtype=torch.int32, device=dev).view(M, n)
+            tp.Tq, tp.qidx = out_q, torch.arange(M, dtype=torch.int32, device=dev)
+            tp.T, tp.idx = out_n, torch.where(tree["nbr"] == 0, torch.full_like(ar, -1), ar)
+        tp.eidx, tp.dt = tree["eidx"], tree["dt"]
+        ldc = E + d
+        tp.CAT = torch.empty(M, ldc, device=dev)
+        _lib.call("pfo_gather_rows", ptr(tp.Tq), d, ptr(tp.qidx), M, d, tp.CAT.data_ptr() + E * F4, ldc)
+        scale = 1.0 / math.sqrt(hd)
+        tp.QP = torch.empty(M, E, device=dev)
+        _linear(c, tp.CAT.data_ptr() + E * F4, ldc, None, ptr(Wq), E, 0, ptr(cq), ptr(tp.QP), E, M, E, d, alpha=scale)
+        tp.QK = torch.empty(M, H, ekp, device=dev)
+        for h in range(H):          # qk_h = Wk_h^T q_h  (weight absorption, see attention_kernels.cu)
+            _linear(c, tp.QP.data_ptr() + h * hd * F4, E, None, Wk.data_ptr() + h * hd * Ek * F4, Ek, 1, None,
+                    tp.QK.data_ptr() + h * ekp * F4, H * ekp, M, Ek, hd)
+        tp.XB = torch.empty(M, H, ekp, device=dev)
+        tp.P = torch.empty(M, H, n, device=dev)
+        tp.invalid = torch.empty(M, dtype=torch.int32, device=dev)
+        tp.step = self.step_id * 16 + layer
+        p_drop = c.dropout if save["train"] else 0.0
+        _lib.call("pfo_attn_nbr_fwd", ptr(tp.QK), ptr(tp.T), d, ptr(tp.idx), ptr(tp.eidx), ptr(tp.dt),
+                  ptr(self.edge_feat), ptr(save["tw"]), ptr(save["tb"]), M, n, d, F, H, ekp,
+                  float(p_drop), self.seed, tp.step, ptr(tp.XB), ptr(tp.P), ptr(tp.invalid))
+        tp.ATT = torch.empty(M, E, device=dev)
+        for h in range(H):          # attn_h = Wv_h xbar_h + bv_h * psum_h
+            _linear(c, tp.XB.data_ptr() + h * ekp * F4, H * ekp, None, WvA.data_ptr() + h * hd * ekp * F4, ekp, 0,
+                    None, tp.ATT.data_ptr() + h * hd * F4, E, M, hd, Ek + 1)
+        _linear(c, ptr(tp.ATT), E, None, ptr(Wo), E, 0, ptr(bo), ptr(tp.CAT), ldc, M, E, E, row_zero=ptr(tp.invalid))
+        tp.H1 = torch.empty(M, d, device=dev)
+        _linear(c, ptr(tp.CAT), ldc, None, ptr(W1), ldc, 0, ptr(b1), ptr(tp.H1), d, M, d, ldc, act=1)
+        tp.OUT = torch.empty(M, d, device=dev)
+        _linear(c, ptr(tp.H1), d, None, ptr(W2), d, 0, ptr(b2), ptr(tp.OUT), d, M, d, d)
+        return tp.OUT, tp
+
+    def _attention_backward(self, tp, dOUT, W, dW, save):
+        """Accumulates parameter grads into dW[layer-1] and feature grads into tp.dTq / tp.dT."""
+        c = self.cfg
+        d, E, Ek, H, ekp, F = c.d, c.E, c.Ek, c.n_heads, c.ekp, c.n_edge_feat
+        hd = E // H
+        dev = self.device
+        M, n = tp.M, tp.n
+        ldc = E + d
+        Wq, cq, Wk, WvA, Wo, bo, W1, b1, W2, b2 = W[tp.layer - 1]
+        gWq, gcq, gWk, gWvA, gWo, gbo, gW1, gb1, gW2, gb2 = dW[tp.layer - 1]
+        scale = 1.0 / math.sqrt(hd)
+        ws = self.ws
+        f32 = ModelConfig(d=d, n_edge_feat=F)           # gradients always take the exact fp32 path
+        # merge MLP
+        dH1 = torch.empty(M, d, device=dev)
+        _linear(f32, ptr(dOUT), d, None, ptr(W2), d, 1, None, ptr(dH1), d, M, d, d, relu_gate=ptr(tp.H1), ld_gate=d)
+        _wgrad(ws, ptr(dOUT), d, ptr(tp.H1), d, None, M, d, d, ptr(gW2), d, ptr(gb2), accumulate=1)
+        dCAT = torch.empty(M, ldc, device=dev)
+        _linear(f32, ptr(dH1), d, None, ptr(W1), ldc, 1, None, ptr(dCAT), ldc, M, ldc, d)
+        _wgrad(ws, ptr(dH1), d, ptr(tp.CAT), ldc, None, M, d, ldc, ptr(gW1), ldc, ptr(gb1), accumulate=1)
+        # rows without neighbours had their attention output zeroed (temporal_attention.py:84)
+        dCAT[:, :E].masked_fill_((tp.invalid != 0).unsqueeze(1), 0.0)
+        _wgrad(ws, ptr(dCAT), ldc, ptr(tp.ATT), E, None, M, E, E, ptr(gWo), E, ptr(gbo), accumulate=1)
+        dATT = torch.empty(M, E, device=dev)
+        _linear(f32, ptr(dCAT), ldc, None, ptr(Wo), E, 1, None, ptr(dATT), E, M, E, E)
+        dXB = torch.empty(M, H, ekp, device=dev)
+        for h in range(H):
+            _linear(f32, dATT.data_ptr() + h * hd * F4, E, None, WvA.data_ptr() + h * hd * ekp * F4, ekp, 1, None,
+                    dXB.data_ptr() + h * ekp * F4, H * ekp, M, Ek + 1, hd)
+            _wgrad(ws, dATT.data_ptr() + h * hd * F4, E, tp.XB.data_ptr() + h * ekp * F4, H * ekp, None, M, hd, Ek + 1,
+                   gWvA.data_ptr() + h * hd * ekp * F4, ekp, None, accumulate=1)
+        dQK = torch.empty(M, H, ekp, device=dev)
+        nws = ws.get(_lib.query("pfo_attn_nbr_bwd_workspace_floats", d))
+        p_drop = c.dropout if save["train"] else 0.0
+        _lib.call("pfo_attn_nbr_bwd", ptr(tp.QK), ptr(dXB), ptr(tp.P), ptr(tp.invalid), ptr(tp.T), d, ptr(tp.idx),
+                  ptr(tp.eidx), ptr(tp.dt), ptr(self.edge_feat), ptr(save["tw"]), ptr(save["tb"]),
+                  M, n, d, F, H, ekp, float(p_drop), self.seed, tp.step, ptr(dQK), ptr(tp.dT), d,
+                  ptr(save["g_twtb"]), 1, ptr(nws))
+        dQP = torch.empty(M, E, device=dev)
+        for h in range(H):
+            _linear(f32, dQK.data_ptr() + h * ekp * F4, H * ekp, None, Wk.data_ptr() + h * hd * Ek * F4, Ek, 0, None,
+                    dQP.data_ptr() + h * hd * F4, E, M, hd, Ek)
+            _wgrad(ws, tp.QP.data_ptr() + h * hd * F4, E, dQK.data_ptr() + h * ekp * F4, H * ekp, None, M, hd, Ek,
+                   gWk.data_ptr() + h * hd * Ek * F4, Ek, None, accumulate=1)
+        # q = scale * (Wq[:, :d] h_q + cq)
+        tmpW = torch.zeros(E, d, device=dev)
+        tmpb = torch.zeros(E, device=dev)
+        _wgrad(ws, ptr(dQP), E, tp.CAT.data_ptr() + E * F4, ldc, None, M, E, d, ptr(tmpW), d, ptr(tmpb))
+        gWq[:, :d].add_(tmpW, alpha=scale)
+        gcq.add_(tmpb, alpha=scale)
+        _linear(f32, ptr(dQP), E, None, ptr(Wq), E, 1, None, dCAT.data_ptr() + E * F4, ldc, M, d, E,
+                alpha=scale, accumulate=1)
+        _lib.call("pfo_scatter_add_rows", dCAT.data_ptr() + E * F4, ldc, ptr(tp.qidx), M, d, ptr(tp.dTq), d)
+
+
+class TGNStepFunction(torch.autograd.Function):
+    """One batch of the TGN path as a single autograd node over the packed parameters."""
+
+    @staticmethod
+    def forward(ctx, eng: TGNEngine, batch, *flat):
+        c, st, dev = eng.cfg, eng.state, eng.device
+        d, F = c.d, c.n_edge_feat
+        need_grad = torch.is_grad_enabled() and any(t.requires_grad for t in flat)
+        it = iter(flat)
+        tw, tb = next(it), next(it)
+        cellW = [next(it) for _ in range(4)] if c.use_memory else None
+        layerW, embW = [], None
+        if c.embedding == "graph_attention":
+            layerW = [[next(it) for _ in range(10)] for _ in range(c.n_layers)]
+        elif c.embedding == "time":
+            embW = [next(it), next(it)]
+        q_nodes, q_ts, n, B = batch["q_nodes"], batch["q_ts"], batch["n"], batch["B"]
+        Q = q_nodes.shape[0]
+        save = dict(train=batch["train"], tw=tw, tb=tb)
+        eng.step_id += 1
+
+        # 1. neighbour sampling tree + unique touched nodes
+        tree = None
+        id_lists = [q_nodes]
+        if c.embedding == "graph_attention":
+            tree = eng._sample_tree(q_nodes, q_ts, c.n_layers, n)
+            id_lists = []
+            eng._collect_level0(tree, id_lists)
+        uniq, u_max = eng._unique_nodes(id_lists)
+        n_uniq = st.n_unique
+
+        # 2. lazy memory update on the unique nodes (memory_updater.py:35-53, restricted)
+        G = c.gates * d
+        H0 = torch.empty(u_max, d, device=dev)
+        Hnew = HG = XG = valid_u = lu_u = GI = GH = None
+        if c.use_memory:
+            HG = torch.empty(u_max, d, device=dev)
+            XG = torch.empty(u_max, c.raw, device=dev)
+            valid_u = torch.empty(u_max, dtype=torch.uint8, device=dev)
+            lu_u = torch.empty(u_max, device=dev)
+            _lib.call("pfo_gather_state", ptr(uniq), ptr(n_uniq), u_max, d, c.raw, ptr(st.memory), ptr(st.pend_msg),
+                      c.rawp, ptr(st.pend_valid), ptr(st.pend_ts), ptr(st.last_update),
+                      ptr(HG), ptr(XG), ptr(valid_u), ptr(lu_u))
+            W_ih, W_hh, b_ih, b_hh = cellW
+            GI = torch.empty(u_max, G, device=dev)
+            GH = torch.empty(u_max, G, device=dev)
+            _linear(c, ptr(XG), c.raw, None, ptr(W_ih), c.raw, 0, ptr(b_ih), ptr(GI), G, u_max, G, c.raw, m_dev=ptr(n_uniq))
+            _linear(c, ptr(HG), d, None, ptr(W_hh), d, 0, ptr(b_hh), ptr(GH), G, u_max, G, d, m_dev=ptr(n_uniq))
+            Hnew = torch.empty(u_max, d, device=dev)
+        _lib.call("pfo_cell_forward", ptr(uniq), ptr(n_uniq), u_max, d, c.cell, ptr(GI), ptr(GH), G, ptr(HG),
+                  ptr(valid_u), ptr(eng.node_feat), ptr(Hnew), ptr(H0))
+
+        # 3. embeddings
+        tape = None
+        td = None
+        qslots = eng._slots(q_nodes)
+        if c.embedding == "graph_attention":
+            emb, tape = eng._attention_forward(tree, layerW, H0, save)
+        elif c.embedding == "time":
+            n_src = batch["src"].shape[0]
+            emb = torch.empty(Q, d, device=dev)
+            td = torch.empty(Q, device=dev)
+            ms, ss, md, sd = c.shift
+            _lib.call("pfo_time_embedding_fwd", ptr(q_nodes), ptr(q_ts), Q, n_src, d, ptr(st.slot_of_node), ptr(Hnew),
+                      ptr(lu_u), float(ms), float(ss), float(md), float(sd), ptr(embW[0]), ptr(embW[1]),
+                      ptr(td), ptr(emb))
+        else:                       # identity: memory'[nodes] (embedding_module.py:32-35)
+            emb = torch.empty(Q, d, device=dev)
+            _lib.call("pfo_gather_rows", ptr(Hnew), d, ptr(qslots), Q, d, ptr(emb), d)
+
+        # 4. persist positives, then build + store the new raw messages (tgn.py:185-206)
+        if c.use_memory and batch["update_state"]:
+            src, dst = batch["src"], batch["dst"]
+            _lib.call("pfo_persist_rank", ptr(src), ptr(dst), B, d, ptr(st.slot_of_node), ptr(Hnew),
+                      ptr(st.pend_valid), ptr(st.pend_ts), ptr(st.memory), ptr(st.last_update), ptr(st.last_pos))
+            o_src = o_dst = None
+            if c.dst_emb_in_msg:    # dyrep: the other endpoint's embedding rides in the message (tgn.py:364-365)
+                o_src, o_dst = emb[B:2 * B], emb[:B]
+            _lib.call("pfo_store_messages", ptr(src), ptr(dst), ptr(batch["eidx"]), ptr(batch["ts"]), B, d, F,
+                      ptr(st.memory), ptr(st.last_update), ptr(eng.edge_feat), ptr(tw), ptr(tb),
+                      ptr(o_src), ptr(o_dst), ptr(st.pend_msg), c.rawp, ptr(st.pend_ts), ptr(st.pend_valid),
+                      ptr(st.last_pos))
+        out = emb
+        if c.use_memory and c.dyrep:    # dyrep returns the updated memory rows (tgn.py:211-215, :322-325)
+            out = torch.empty(Q, d, device=dev)
+            _lib.call("pfo_gather_rows", ptr(Hnew), d, ptr(qslots), Q, d, ptr(out), d)
+        if need_grad:
+            ctx.eng, ctx.save = eng, save
+            ctx.pack = dict(flat=flat, cellW=cellW, layerW=layerW, embW=embW, tape=tape, uniq=uniq, u_max=u_max,
+                            n_uniq=n_uniq.clone(), HG=HG, XG=XG, valid_u=valid_u, GI=GI, GH=GH, Hnew=Hnew,
+                            qslots=qslots, q_nodes=q_nodes, td=td, Q=Q,
+                            slot_snapshot=None)
+            if c.embedding == "time":   # slots are reused by later batches: snapshot what backward needs
+                ctx.pack["slot_snapshot"] = qslots
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        eng, save, pk = ctx.eng, ctx.save, ctx.pack
+        c, dev = eng.cfg, eng.device
+        d = c.d
+        dOut = dOut.contiguous()
+        flat = pk["flat"]
+        grads = [torch.zeros_like(t) for t in flat]
+        it = iter(grads)
+        g_tw, g_tb = next(it), next(it)
+        g_cell = [next(it) for _ in range(4)] if c.use_memory else None
+        g_layers, g_emb = [], None
+        if c.embedding == "graph_attention":
+            g_layers = [[next(it) for _ in range(10)] for _ in range(c.n_layers)]
+        elif c.embedding == "time":
+            g_emb = [next(it), next(it)]
+        u_max, n_uniq = pk["u_max"], pk["n_uniq"]
+        dH0 = torch.zeros(u_max, d, device=dev)          # grad of the unique-node feature table
+        attention_grad = c.embedding == "graph_attention" and not (c.use_memory and c.dyrep)
+        if c.use_memory and c.dyrep:
+            _lib.call("pfo_scatter_add_rows", ptr(dOut), d, ptr(pk["qslots"]), pk["Q"], d, ptr(dH0), d)
+        elif c.embedding == "identity":
+            _lib.call("pfo_scatter_add_rows", ptr(dOut), d, ptr(pk["qslots"]), pk["Q"], d, ptr(dH0), d)
+        elif c.embedding == "time":
+            need = 2 * 148 * 2 * d
+            buf = eng.ws.get(need)
+            gwb = torch.zeros(2 * d, device=dev)
+            # slot_of_node may have been rewritten by a later batch: go through the saved slots
+            ar = torch.arange(pk["Q"], dtype=torch.int32, device=dev)
+            _lib.call("pfo_time_embedding_bwd", ptr(ar), pk["Q"], d, ptr(pk["qslots"]), ptr(pk["Hnew"]), ptr(pk["td"]),
+                      ptr(pk["embW"][0]), ptr(pk["embW"][1]), ptr(dOut), ptr(dH0), ptr(gwb), ptr(buf), need)
+            g_emb[0].copy_(gwb[:d])
+            g_emb[1].copy_(gwb[d:])
+        if attention_grad:
+            save["g_twtb"] = torch.zeros(2 * d, device=dev)
+            # walk the tape from the outermost layer down; level-0 feature grads land in dH0
+            stack = [(pk["tape"], dOut)]
+            while stack:
+                tp, g = stack.pop()
+                if tp.layer == 1:
+                    tp.dTq = tp.dT = dH0
+                else:
+                    tp.dTq = torch.zeros_like(tp.child_q.OUT)
+                    tp.dT = torch.zeros_like(tp.child_n.OUT)
+                eng._attention_backward(tp, g, pk["layerW"], g_layers, save)
+                if tp.layer > 1:
+                    stack.append((tp.child_q, tp.dTq))
+                    stack.append((tp.child_n, tp.dT))
+            g_tw.add_(save["g_twtb"][:d])
+            g_tb.add_(save["g_twtb"][d:])
+        if c.use_memory:
+            G = c.gates * d
+            dGI = torch.empty(u_max, G, device=dev)
+            dGH = torch.empty(u_max, G, device=dev)
+            _lib.call("pfo_cell_backward", ptr(pk["uniq"]), ptr(n_uniq), u_max, d, c.cell, ptr(pk["GI"]), ptr(pk["GH"]),
+                      G, ptr(pk["HG"]), ptr(pk["valid_u"]), ptr(dH0), ptr(dGI), ptr(dGH))
+            gW_ih, gW_hh, gb_ih, gb_hh = g_cell
+            _wgrad(eng.ws, ptr(dGI), G, ptr(pk["XG"]), c.raw, None, u_max, G, c.raw, ptr(gW_ih), c.raw, ptr(gb_ih),
+                   m_dev=ptr(n_uniq))
+            _wgrad(eng.ws, ptr(dGH), G, ptr(pk["HG"]), d, None, u_max, G, d, ptr(gW_hh), d, ptr(gb_hh),
+                   m_dev=ptr(n_uniq))
+        return (None, None) + tuple(grads)

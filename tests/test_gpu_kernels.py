@@ -1,0 +1,268 @@
+"""Kernel-level parity on the GPU, through the C ABI (ctypes), against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _stream(U=300, I=40, E=6000, mode="small", seed=1):
+    from pfotgnrec_b200.synth import make_stream
+    return make_stream(n_users=U, n_items=I, n_events=E, n_days=30, seed=seed, ts_mode=mode)
+
+
+# ------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize("name", ["small", "nbg"])
+@pytest.mark.parametrize("n", [10, 3, 1])
+def test_neighbors_golden_bit_exact(name, n):
+    from pfotgnrec_b200.graph import TemporalCSR, NeighborFinder
+    z = load_golden("neighbors.npz")
+    csr = TemporalCSR(z[f"{name}_sources"], z[f"{name}_destinations"], z[f"{name}_edge_idxs"],
+                      z[f"{name}_timestamps"], n_nodes=int(z[f"{name}_n_nodes"]), device=DEV)
+    nf = NeighborFinder(csr)
+    nb, ei, et = nf.get_temporal_neighbor(z[f"{name}_nodes"], z[f"{name}_ts"], n)
+    assert np.array_equal(nb, z[f"{name}_n{n}_nbr"])
+    assert np.array_equal(ei, z[f"{name}_n{n}_eidx"])
+    assert np.array_equal(et, z[f"{name}_n{n}_etime"])
+    assert nb.dtype == np.int32 and et.dtype == np.float32
+
+
+@pytest.mark.parametrize("uniform", [False, True])
+@pytest.mark.parametrize("mode", ["small", "nbg"])
+def test_neighbors_vs_oracle(uniform, mode):
+    from oracle.graph import AdjacencyOracle
+    from pfotgnrec_b200.graph import TemporalCSR, NeighborFinder
+    st = _stream(mode=mode)
+    adj = AdjacencyOracle(st.sources, st.destinations, st.edge_idxs, st.timestamps, n_nodes=st.n_nodes, uniform=uniform)
+    csr = TemporalCSR(st.sources, st.destinations, st.edge_idxs, st.timestamps, n_nodes=st.n_nodes, device=DEV)
+    # the device-built CSR equals the oracle's stable (node, ts, stream-order) sort
+    assert np.array_equal(csr.rowptr.cpu().numpy(), adj.rowptr)
+    assert np.array_equal(csr.nbr.cpu().numpy(), adj.nbr)
+    assert np.array_equal(csr.eidx.cpu().numpy(), adj.eidx)
+    assert np.array_equal(csr.ts.cpu().numpy(), adj.ts)
+    rng = np.random.default_rng(0)
+    Q = 1000 + 7        # ragged: not a multiple of 32
+    nodes = rng.integers(0, st.n_nodes, size=Q)
+    ts = st.timestamps[rng.integers(0, st.n_events, size=Q)] + rng.integers(-1, 2, size=Q)
+    nf = NeighborFinder(csr, uniform=uniform, seed=77)
+    for call in range(2):
+        for n in (10, 20):
+            nf.call_id = call
+            a = nf.get_temporal_neighbor(nodes, ts, n)
+            b = adj.get_temporal_neighbor(nodes, ts, n, call_id=call, seed=77)
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y)
+
+
+def test_neighbors_empty_and_delta():
+    from pfotgnrec_b200.graph import TemporalCSR, NeighborFinder
+    st = _stream(mode="nbg")
+    csr = TemporalCSR(st.sources, st.destinations, st.edge_idxs, st.timestamps, n_nodes=st.n_nodes, device=DEV)
+    nf = NeighborFinder(csr)
+    qn = torch.as_tensor(st.sources[:500].astype(np.int32), device=DEV)
+    qt = torch.as_tensor(st.timestamps[:500], device=DEV)
+    nbr, eidx, et, dt = nf.sample(qn, qt, 10)
+    ref = (st.timestamps[:500, None] - et.cpu().numpy().astype(np.float64)).astype(np.float32)
+    assert np.array_equal(dt.cpu().numpy(), ref)          # fp64 subtract, then fp32 (embedding_module.py:133-135)
+    e = nf.get_temporal_neighbor(np.zeros(0, np.int64), np.zeros(0), 10)
+    assert e[0].shape == (0, 10)
+    z = nf.get_temporal_neighbor(np.array([1, 2]), np.array([5.0, 6.0]), 0)
+    assert z[0].shape == (2, 1) and not z[0].any()
+
+
+# ------------------------------------------------------------------------------ compaction
+def test_unique_node_compaction():
+    from pfotgnrec_b200 import _lib
+    from pfotgnrec_b200._lib import ptr
+    for N in (1000, 100003):
+        rng = np.random.default_rng(N)
+        ids = rng.integers(0, N, size=5000).astype(np.int32)
+        ids[:10] = 0
+        t = torch.as_tensor(ids, device=DEV)
+        bitmap = torch.zeros((N + 31) // 32, dtype=torch.int32, device=DEV)
+        ws = torch.zeros(_lib.query("pfo_compact_workspace_ints", N), dtype=torch.int32, device=DEV)
+        uniq = torch.zeros(5000, dtype=torch.int32, device=DEV)
+        slot = torch.zeros(N, dtype=torch.int32, device=DEV)
+        cnt = torch.zeros(1, dtype=torch.int32, device=DEV)
+        _lib.call("pfo_mark_nodes", ptr(t), t.numel(), 1, ptr(bitmap))
+        _lib.call("pfo_compact_nodes", ptr(bitmap), N, ptr(ws), ptr(uniq), ptr(slot), ptr(cnt))
+        ref = np.unique(ids[ids > 0])
+        assert int(cnt.item()) == ref.shape[0]
+        assert np.array_equal(uniq.cpu().numpy()[:ref.shape[0]], ref)
+        assert not bitmap.any()
+        out = torch.empty_like(t)
+        _lib.call("pfo_map_slots", ptr(t), t.numel(), 1, ptr(slot), ptr(out))
+        o = out.cpu().numpy()
+        assert (o[ids == 0] == -1).all()
+        assert np.array_equal(ref[o[ids > 0]], ids[ids > 0])
+
+
+# ------------------------------------------------------------------------------ dense contractions
+@pytest.mark.parametrize("M,N,K", [(1000, 192, 193), (257, 64, 64), (4096, 129, 64), (33, 130, 32), (5000, 64, 192)])
+@pytest.mark.parametrize("wt", [0, 1])
+def test_linear_f32(M, N, K, wt):
+    from pfotgnrec_b200 import _lib
+    from pfotgnrec_b200._lib import ptr
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = torch.randn(M + 50, K + 3, generator=g)
+    W = torch.randn(N, K, generator=g)
+    b = torch.randn(N, generator=g)
+    idx = torch.randint(-1, M + 50, (M,), generator=g, dtype=torch.int32)
+    rz = (torch.rand(M, generator=g) < 0.1).to(torch.int32)
+    ref_rows = torch.where(idx.unsqueeze(1) >= 0, A[idx.clamp(min=0).long(), :K], torch.zeros(1))
+    ref = (ref_rows.double() @ W.double().t() + b.double()) * 0.5
+    ref = torch.relu(ref)
+    ref[rz != 0] = 0
+    Ad, Wd, bd, idxd, rzd = (t.to(DEV) for t in (A, W.t().contiguous() if wt else W, b, idx, rz))
+    C = torch.full((M, N + 2), 7.0, device=DEV)
+    _lib.call("pfo_linear_f32", ptr(Ad), K + 3, ptr(idxd), ptr(Wd), N if wt else K, wt, ptr(bd), None, 0,
+              ptr(C), N + 2, M, None, N, K, 0.5, 1, ptr(rzd), None, 0, 0)
+    assert rel_err(C[:, :N].cpu().numpy(), ref.numpy()) < 1e-5
+    assert (C[:, N:] == 7.0).all()
+    # accumulate + device-side row count
+    md = torch.tensor([M - 5], dtype=torch.int32, device=DEV)
+    C2 = torch.ones(M, N, device=DEV)
+    _lib.call("pfo_linear_f32", ptr(Ad), K + 3, None, ptr(Wd), N if wt else K, wt, None, None, 0,
+              ptr(C2), N, M, ptr(md), N, K, 1.0, 0, None, None, 0, 1)
+    ref2 = A[:M, :K].double() @ W.double().t() + 1.0
+    assert rel_err(C2[:M - 5].cpu().numpy(), ref2[:M - 5].numpy()) < 1e-5
+    assert (C2[M - 5:] == 1.0).all()
+
+
+@pytest.mark.parametrize("M,N,K", [(3000, 192, 193), (100, 64, 130), (70000, 64, 64), (1, 128, 129)])
+def test_wgrad_f32(M, N, K):
+    from pfotgnrec_b200 import _lib
+    from pfotgnrec_b200._lib import ptr
+    g = torch.Generator(device="cpu").manual_seed(M)
+    G = torch.randn(M, N, generator=g)
+    A = torch.randn(M, K, generator=g)
+    ref = G.double().t() @ A.double()
+    refb = G.double().sum(0)
+    Gd, Ad = G.to(DEV), A.to(DEV)
+    dW = torch.zeros(N, K, device=DEV)
+    db = torch.zeros(N, device=DEV)
+    ws = torch.empty(_lib.query("pfo_wgrad_workspace_floats", M, N, K, 1), device=DEV)
+    _lib.call("pfo_wgrad_f32", ptr(Gd), N, ptr(Ad), K, None, M, None, N, K, ptr(dW), K, ptr(db), 0, ptr(ws))
+    assert rel_err(dW.cpu().numpy(), ref.numpy()) < 2e-5
+    assert rel_err(db.cpu().numpy(), refb.numpy()) < 2e-5
+    dW2 = dW.clone()
+    _lib.call("pfo_wgrad_f32", ptr(Gd), N, ptr(Ad), K, None, M, None, N, K, ptr(dW2), K, None, 1, ptr(ws))
+    assert rel_err(dW2.cpu().numpy(), 2 * ref.numpy()) < 2e-5
+    # determinism: bit-identical on a re-run
+    dW3 = torch.zeros(N, K, device=DEV)
+    _lib.call("pfo_wgrad_f32", ptr(Gd), N, ptr(Ad), K, None, M, None, N, K, ptr(dW3), K, None, 0, ptr(ws))
+    assert torch.equal(dW3, dW)
+
+
+# ------------------------------------------------------------------------------ K5
+def _mv_inputs(st, sl):
+    ptr_ = st.port_ptr[sl.start:sl.stop + 1]
+    return ptr_ - ptr_[0], st.port_items[ptr_[0]:ptr_[-1]]
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2])
+def test_mv_select_golden_ids_bit_exact(ci):
+    from pfotgnrec_b200.sampler import MVSelector
+    from pfotgnrec_b200.synth import log_returns
+    z = load_golden("mv_select.npz")
+    cand = z[f"c{ci}_cand"]
+    B, C = cand.shape
+    e0 = int(z[f"c{ci}_event0"])
+    ptr_ = z["st_port_ptr"][e0:e0 + B + 1]
+    sel = MVSelector(log_returns(z["st_prices_future"]), np.arange(60), n_users=0, gamma=float(z[f"c{ci}_gamma"]),
+                     lam=float(z[f"c{ci}_lam"]), n_candidates=C - 1)
+    pp, pn = sel.select(np.arange(B), z["st_day_idx"][e0:e0 + B], cand[:, 0] + 1, ptr_ - ptr_[0],
+                        z["st_port_items"][ptr_[0]:ptr_[-1]], cand=cand)
+    assert np.array_equal(pp.cpu().numpy() - 1, z[f"c{ci}_ppos_stable"])
+    assert np.array_equal(pn.cpu().numpy() - 1, z[f"c{ci}_pneg_stable"])
+
+
+def test_mv_select_sampled_vs_oracle():
+    from oracle import sampling
+    from pfotgnrec_b200.sampler import MVSelector
+    from pfotgnrec_b200.synth import log_returns
+    st = _stream(U=500, I=300, E=4000, mode="nbg", seed=5)
+    lr = log_returns(st.prices_future)
+    universe = np.unique(st.destinations[:3000] - st.n_users - 1)
+    sl = slice(1000, 1000 + 777)
+    pptr, pitems = _mv_inputs(st, sl)
+    ev = st.edge_idxs[sl]
+    for K, lam in ((20, 0.5), (31, 0.3), (5, 0.9)):
+        sel = MVSelector(lr, universe, n_users=st.n_users, gamma=2.0, lam=lam, n_candidates=K, seed=123)
+        pp, pn, cand, y = sel.select(ev, st.day_idx[sl], st.destinations[sl], pptr, pitems, return_scores=True)
+        ref_neg = sampling.sample_candidates(ev, universe, pptr, pitems, K, seed=123)
+        ref_cand = np.concatenate([(st.destinations[sl] - st.n_users - 1)[:, None], ref_neg], axis=1)
+        assert np.array_equal(cand.cpu().numpy(), ref_cand)          # Philox candidates: bit-exact
+        ry = sampling.mv_scores(lr, st.day_idx[sl], ref_cand, pptr, pitems, 2.0)
+        assert np.array_equal(y.cpu().numpy(), ry)                   # fp64 y_mv: bit-exact (same op order, no fma)
+        rp, rn = sampling.mv_select(lr, st.day_idx[sl], ref_cand, pptr, pitems, 2.0, lam)
+        assert np.array_equal(pp.cpu().numpy() - st.n_users - 1, rp)
+        assert np.array_equal(pn.cpu().numpy() - st.n_users - 1, rn)
+
+
+@pytest.mark.parametrize("size", [3, 20, 40, 45])
+def test_candidate_sampler_vs_oracle(size):
+    from oracle import sampling
+    from pfotgnrec_b200.sampler import CandidateSampler
+    st = _stream(U=200, I=40, E=2000, mode="small", seed=9)     # 40 items: size 40/45 hits the replacement path
+    universe = np.unique(st.destinations)
+    sl = slice(100, 400)
+    pptr, pitems = _mv_inputs(st, sl)
+    held_items = pitems.astype(np.int64) + st.n_users + 1
+    cs = CandidateSampler(universe)
+    out = cs.sample(st.edge_idxs[sl], pptr, held_items, size, seed=2024).cpu().numpy()
+    ref = sampling.sample_candidates(st.edge_idxs[sl], universe, pptr, held_items, size, seed=2024)
+    assert np.array_equal(out, ref)
+    for b in range(out.shape[0]):
+        held = set(held_items[pptr[b]:pptr[b + 1]].tolist())
+        assert not (set(out[b].tolist()) & held)
+
+
+# ------------------------------------------------------------------------------ K6 / eval
+def test_bpr_forward_backward():
+    from oracle.tgn import bpr_loss
+    from pfotgnrec_b200 import _lib
+    from pfotgnrec_b200._lib import ptr
+    torch.manual_seed(0)
+    B, k, d = 517, 3, 64
+    eu, ep, en = torch.randn(B, d), torch.randn(B, d), torch.randn(B * k, d)
+    for t in (eu, ep, en):
+        t.mul_(0.3).requires_grad_(True)
+    loss = bpr_loss(eu, ep, en)
+    loss.backward()
+    du, dp, dn = (torch.empty_like(t, device=DEV) for t in (eu, ep, en))
+    out = torch.zeros(1, device=DEV)
+    ws = torch.empty(1024, device=DEV)
+    _lib.call("pfo_bpr", ptr(eu.detach().to(DEV)), ptr(ep.detach().to(DEV)), ptr(en.detach().to(DEV)), B, k, d,
+              ptr(du), ptr(dp), ptr(dn), ptr(out), 1.0, ptr(ws))
+    assert abs(out.item() - loss.item()) < 1e-5 * abs(loss.item())
+    assert rel_err(du.cpu().numpy(), eu.grad.numpy()) < 1e-5
+    assert rel_err(dp.cpu().numpy(), ep.grad.numpy()) < 1e-5
+    assert rel_err(dn.cpu().numpy(), en.grad.numpy()) < 1e-5
+
+
+def test_eval_score_and_ranking():
+    from oracle.tgn import eval_scores, eval_ranking
+    from pfotgnrec_b200 import _lib
+    from pfotgnrec_b200._lib import ptr
+    torch.manual_seed(1)
+    B, n_cand, d = 37, 203, 64
+    es, ed, ec = torch.randn(B, d), torch.randn(B, d), torch.randn(B * n_cand, d)
+    ec.view(B, n_cand, d)[:, 5] = ec.view(B, n_cand, d)[:, 9]        # exact ties among candidates
+    ec.view(B, n_cand, d)[::2, 3] = ed[::2]                           # ties with the positive
+    ref = eval_scores(es, ed, ec)
+    rank = eval_ranking(ref.numpy())
+    scores = torch.empty(B, 1 + n_cand, device=DEV)
+    pos_rank = torch.empty(B, dtype=torch.int32, device=DEV)
+    top = torch.empty(B, 5, dtype=torch.int32, device=DEV)
+    _lib.call("pfo_eval_score", ptr(es.to(DEV)), ptr(ed.to(DEV)), ptr(ec.to(DEV)), B, n_cand, d, 5,
+              ptr(scores), ptr(pos_rank), ptr(top))
+    s = scores.cpu().numpy()
+    assert rel_err(s, ref.numpy()) < 1e-5
+    # ranking semantics checked on the kernel's own scores (bit-exact integer work)
+    rk = eval_ranking(s)
+    assert np.array_equal(top.cpu().numpy(), rk[:, :5])
+    assert np.array_equal(pos_rank.cpu().numpy(), np.argmax(rk == 0, axis=1))

@@ -1,0 +1,157 @@
+"""Model-level parity on the GPU: the drop-in TGN (overlay) against the reference's golden
+vectors and against the CPU oracle, reading like the reference's own call sequence."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden, oracle_from_golden, rel_err, batch_inputs
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OVERLAY = os.path.join(ROOT, "pfotgnrec_b200", "overlay")
+TOL = 1e-5          # fp32 contract of BASELINE.json north_star (max-norm relative error)
+GTOL = 5e-5         # parameter gradients: sums over thousands of rows in a different order
+
+
+@pytest.fixture(scope="module")
+def overlay():
+    sys.path.insert(0, OVERLAY)
+    for m in [k for k in sys.modules if k.split(".")[0] in ("model", "modules", "utils")]:
+        del sys.modules[m]
+    import model.tgn as tgn_mod
+    import utils.utils as utils_mod
+    yield tgn_mod, utils_mod
+    sys.path.remove(OVERLAY)
+
+
+def build_tgn(tgn_mod, utils_mod, z):
+    import types
+    data = types.SimpleNamespace(sources=z["st_sources"], destinations=z["st_destinations"],
+                                 edge_idxs=z["st_edge_idxs"], timestamps=z["st_timestamps"])
+    nf = utils_mod.get_neighbor_finder(data, uniform=False, max_node_idx=int(z["st_n_nodes"]) - 1)
+    torch.manual_seed(11)
+    tgn = tgn_mod.TGN(neighbor_finder=nf, node_features=z["node_feat"], edge_features=z["st_edge_features"].copy(),
+                      device=torch.device("cuda"), n_layers=int(z["cfg_n_layers"]), n_heads=2, dropout=0.0,
+                      use_memory=bool(z["cfg_use_memory"]), message_dimension=100, memory_dimension=int(z["cfg_d"]),
+                      memory_update_at_start=True, embedding_module_type=str(z["cfg_embedding"]),
+                      message_function="identity", aggregator_type="last",
+                      memory_updater_type=str(z["cfg_updater"]), n_neighbors=int(z["cfg_n_neighbors"]),
+                      mean_time_shift_src=z["cfg_shift"][0], std_time_shift_src=z["cfg_shift"][1],
+                      mean_time_shift_dst=z["cfg_shift"][2], std_time_shift_dst=z["cfg_shift"][3],
+                      use_destination_embedding_in_message=bool(z["cfg_dst_emb"]),
+                      use_source_embedding_in_message=False, dyrep=bool(z["cfg_dyrep"]))
+    tgn = tgn.to(torch.device("cuda"))
+    sd = tgn.state_dict()
+    for k in z:
+        if k.startswith("w_"):
+            assert np.array_equal(sd[k[2:]].cpu().numpy(), z[k]), k     # same seed -> same initial weights
+    return tgn
+
+
+@pytest.mark.parametrize("tag", ["ours", "ours_nbg", "tgn", "jodie", "dyrep", "tgat2"])
+def test_drop_in_tgn_matches_reference_golden(overlay, tag):
+    tgn_mod, utils_mod = overlay
+    z = load_golden(f"tgn_{tag}.npz")
+    tgn = build_tgn(tgn_mod, utils_mod, z).train()
+    n = int(z["cfg_n_neighbors"])
+    n_neg = int(z["cfg_n_neg"])
+    names = [k for k, p in tgn.named_parameters() if p.requires_grad]
+    report = []
+    for bi in range(int(z["cfg_n_batches"])):
+        src, dst, extra, ts, ei = batch_inputs(z, bi)
+        tgn.zero_grad(set_to_none=True)
+        if len(extra) == 2:
+            e_s, e_d, e_p, e_n = tgn.compute_temporal_embeddings_p(src, dst, extra[0], extra[1], ts, ei, n)
+            outs = {"src": e_s, "dst": e_d, "ppos": e_p, "neg": e_n}
+        else:
+            e_s, e_d, e_n = tgn.compute_temporal_embeddings(src, dst, extra[0], ts, ei, n)
+            e_p = e_d
+            outs = {"src": e_s, "dst": e_d, "neg": e_n}
+        for nm, e in outs.items():
+            err = rel_err(e.detach().cpu().numpy(), z[f"b{bi}_emb_{nm}"])
+            report.append((bi, nm, err))
+            assert err < TOL, (tag, bi, nm, err)
+        # BPR exactly as the reference script computes it (main.py:321-337), on the returned tensors
+        bs = e_s.shape[0]
+        s_ = e_s.view(bs, 1, -1)
+        pos = torch.sum(s_ * e_p.view(bs, 1, -1), dim=2)
+        neg = torch.matmul(s_, e_n.view(bs, n_neg, -1).transpose(1, 2)).squeeze()
+        loss = -torch.mean(torch.log(torch.sigmoid(torch.mean(pos - neg, dim=1))))
+        ref_loss = float(z[f"b{bi}_loss"])
+        assert abs(loss.item() - ref_loss) < TOL * max(1.0, abs(ref_loss)), (tag, bi, loss.item(), ref_loss)
+        if bool(z["cfg_dyrep"]):
+            loss.requires_grad_()
+        loss.backward()
+        if tgn.use_memory:
+            tgn.memory.detach_memory()
+        params = dict(tgn.named_parameters())
+        for k in names:
+            ref = z[f"b{bi}_g_{k}"]
+            g = params[k].grad
+            g = np.zeros_like(ref) if g is None else g.cpu().numpy()
+            scale = max(np.abs(ref).max(), 1e-3)
+            assert np.abs(g - ref).max() <= GTOL * scale + 1e-7, (tag, bi, k, np.abs(g - ref).max(), scale)
+        if tgn.use_memory:
+            assert rel_err(tgn.memory.memory.cpu().numpy(), z[f"b{bi}_memory"]) < TOL
+            assert np.array_equal(tgn.memory.last_update.cpu().numpy(), z[f"b{bi}_last_update"])
+            st = tgn.memory.state
+            v = z[f"b{bi}_pend_valid"]
+            assert np.array_equal(st.pend_valid.cpu().numpy().astype(bool), v)           # last-message selection: bit-exact
+            assert np.array_equal(st.pend_ts.cpu().numpy()[v], z[f"b{bi}_pend_ts"][v])
+            raw = z[f"b{bi}_pend_msg"].shape[1]
+            assert rel_err(st.pend_msg.cpu().numpy()[v][:, :raw], z[f"b{bi}_pend_msg"][v]) < TOL
+
+
+def test_larger_stream_vs_oracle(overlay):
+    """PfoTGNRec config (d=64, n=10, heads 2) on a bigger synthetic stream, weights injected into the
+    CPU oracle; several batches so that memory, last-wins messages and lazy updates interact."""
+    tgn_mod, utils_mod = overlay
+    import types
+    from oracle.graph import AdjacencyOracle
+    from oracle.tgn import TGNOracle, bpr_loss
+    from pfotgnrec_b200.synth import make_stream
+    st = make_stream(n_users=400, n_items=50, n_events=3000, n_days=30, seed=4, ts_mode="small", with_prices=False)
+    rng = np.random.default_rng(0)
+    d, B, n = 64, 200, 10
+    node_feat = rng.random((st.n_nodes, d))
+    data = types.SimpleNamespace(sources=st.sources, destinations=st.destinations, edge_idxs=st.edge_idxs,
+                                 timestamps=st.timestamps)
+    nf = utils_mod.get_neighbor_finder(data, uniform=False, max_node_idx=st.n_nodes - 1)
+    torch.manual_seed(3)
+    tgn = tgn_mod.TGN(neighbor_finder=nf, node_features=node_feat, edge_features=st.edge_features.copy(),
+                      device=torch.device("cuda"), n_layers=1, n_heads=2, dropout=0.0, use_memory=True,
+                      message_dimension=100, memory_dimension=d, embedding_module_type="graph_attention",
+                      message_function="identity", aggregator_type="last", memory_updater_type="gru",
+                      n_neighbors=n).to("cuda").train()
+    p = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in tgn.named_parameters()}
+    adj = AdjacencyOracle(st.sources, st.destinations, st.edge_idxs, st.timestamps, n_nodes=st.n_nodes)
+    orc = TGNOracle(p, adj, node_feat, st.edge_features, n_layers=1, n_heads=2)
+    for bi in range(8):
+        sl = slice(bi * B, (bi + 1) * B)
+        ppos = rng.integers(st.n_users + 1, st.n_nodes, size=B)
+        pneg = rng.integers(st.n_users + 1, st.n_nodes, size=3 * B)
+        args = (st.sources[sl], st.destinations[sl])
+        tgn.zero_grad(set_to_none=True)
+        for v in p.values():
+            v.grad = None
+        e = tgn.compute_temporal_embeddings_p(*args, ppos, pneg, st.timestamps[sl], st.edge_idxs[sl], n)
+        o = orc.compute_temporal_embeddings(*args, [ppos, pneg], st.timestamps[sl], st.edge_idxs[sl], n)
+        for a, b in zip(e, o):
+            assert rel_err(a.detach().cpu().numpy(), b.detach().numpy()) < TOL, bi
+        la = bpr_loss(e[0], e[2], e[3])
+        lb = bpr_loss(o[0], o[2], o[3])
+        assert abs(la.item() - lb.item()) < TOL
+        la.backward()
+        lb.backward()
+        for k, v in tgn.named_parameters():
+            if p[k].grad is None:
+                continue
+            ref = p[k].grad.numpy()
+            got = v.grad.cpu().numpy() if v.grad is not None else np.zeros_like(ref)
+            scale = max(np.abs(ref).max(), 1e-3)
+            assert np.abs(got - ref).max() <= GTOL * scale + 1e-7, (bi, k)
+        assert rel_err(tgn.memory.memory.cpu().numpy(), orc.memory.numpy()) < TOL
+        assert np.array_equal(tgn.memory.state.pend_valid.cpu().numpy().astype(bool), orc.pend_valid.numpy())

@@ -1,0 +1,88 @@
+"""Host-side checks of the drop-in overlay that need no GPU: import surface, state_dict keys,
+initial-weight parity with the reference (same seed, same construction order), C-ABI symbols."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OVERLAY = os.path.join(ROOT, "pfotgnrec_b200", "overlay")
+
+
+@pytest.fixture(scope="module")
+def overlay():
+    sys.path.insert(0, OVERLAY)
+    for m in [k for k in sys.modules if k.split(".")[0] in ("model", "modules", "utils")]:
+        del sys.modules[m]
+    import model.tgn as tgn_mod
+    import utils.utils as utils_mod
+    yield tgn_mod, utils_mod
+    sys.path.remove(OVERLAY)
+
+
+def _build(tgn_mod, z, device="cpu"):
+    torch.manual_seed(11)
+    return tgn_mod.TGN(neighbor_finder=None, node_features=z["node_feat"], edge_features=z["st_edge_features"].copy(),
+                       device=torch.device(device), n_layers=int(z["cfg_n_layers"]), n_heads=2, dropout=0.0,
+                       use_memory=bool(z["cfg_use_memory"]), message_dimension=100, memory_dimension=int(z["cfg_d"]),
+                       memory_update_at_start=True, embedding_module_type=str(z["cfg_embedding"]),
+                       message_function="identity", aggregator_type="last",
+                       memory_updater_type=str(z["cfg_updater"]), n_neighbors=int(z["cfg_n_neighbors"]),
+                       mean_time_shift_src=z["cfg_shift"][0], std_time_shift_src=z["cfg_shift"][1],
+                       mean_time_shift_dst=z["cfg_shift"][2], std_time_shift_dst=z["cfg_shift"][3],
+                       use_destination_embedding_in_message=bool(z["cfg_dst_emb"]),
+                       use_source_embedding_in_message=False, dyrep=bool(z["cfg_dyrep"]))
+
+
+@pytest.mark.parametrize("tag", ["ours", "jodie", "dyrep", "tgat2"])
+def test_initial_weights_and_keys_match_reference(overlay, tag):
+    tgn_mod, _ = overlay
+    z = load_golden(f"tgn_{tag}.npz")
+    tgn = _build(tgn_mod, z)
+    sd = tgn.state_dict()
+    ref_keys = {k[2:] for k in z if k.startswith("w_")}
+    mine = {k for k in sd if not re.match(r"(memory\.|memory_updater\.memory\.|embedding_module\.memory\.)", k)}
+    assert mine == ref_keys
+    for k in ref_keys:
+        assert np.array_equal(sd[k].numpy(), z["w_" + k]), k
+    if bool(z["cfg_use_memory"]):
+        for alias in ("memory.memory", "memory_updater.memory.memory", "embedding_module.memory.last_update"):
+            assert alias in sd
+
+
+def test_import_surface(overlay):
+    tgn_mod, utils_mod = overlay
+    for name in ("EarlyStopMonitor", "RandEdgeSampler", "get_neighbor_finder", "MergeLayer", "MLP", "NeighborFinder"):
+        assert hasattr(utils_mod, name)
+    for name in ("compute_temporal_embeddings_p", "compute_temporal_embeddings", "set_neighbor_finder"):
+        assert hasattr(tgn_mod.TGN, name)
+    import modules.memory as mm
+    for name in ("__init_memory__", "detach_memory", "backup_memory", "restore_memory", "get_memory",
+                 "set_memory", "get_last_update", "store_raw_messages", "clear_messages"):
+        assert hasattr(mm.Memory, name)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from pfotgnrec_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "pfo_b200.h")).read()
+    declared = set(re.findall(r"\b(pfo_[a-z0-9_]+)\s*\(", header))
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    assert lib.pfo_abi_version() == 1
+
+
+def test_product_path_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "pfotgnrec_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(dirpath, f)
