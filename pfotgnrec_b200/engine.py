@@ -380,7 +380,7 @@ class TGNStepFunction(torch.autograd.Function):
     def forward(ctx, eng: TGNEngine, batch, *flat):
         c, st, dev = eng.cfg, eng.state, eng.device
         d, F = c.d, c.n_edge_feat
-        need_grad = torch.is_grad_enabled() and any(t.requires_grad for t in flat)
+        need_grad = any(ctx.needs_input_grad)
         it = iter(flat)
         tw, tb = next(it), next(it)
         cellW = [next(it) for _ in range(4)] if c.use_memory else None

@@ -236,7 +236,8 @@ def test_bpr_forward_backward():
     du, dp, dn = (torch.empty_like(t, device=DEV) for t in (eu, ep, en))
     out = torch.zeros(1, device=DEV)
     ws = torch.empty(1024, device=DEV)
-    _lib.call("pfo_bpr", ptr(eu.detach().to(DEV)), ptr(ep.detach().to(DEV)), ptr(en.detach().to(DEV)), B, k, d,
+    eu_d, ep_d, en_d = eu.detach().to(DEV), ep.detach().to(DEV), en.detach().to(DEV)   # keep alive across the launch
+    _lib.call("pfo_bpr", ptr(eu_d), ptr(ep_d), ptr(en_d), B, k, d,
               ptr(du), ptr(dp), ptr(dn), ptr(out), 1.0, ptr(ws))
     assert abs(out.item() - loss.item()) < 1e-5 * abs(loss.item())
     assert rel_err(du.cpu().numpy(), eu.grad.numpy()) < 1e-5
@@ -258,7 +259,8 @@ def test_eval_score_and_ranking():
     scores = torch.empty(B, 1 + n_cand, device=DEV)
     pos_rank = torch.empty(B, dtype=torch.int32, device=DEV)
     top = torch.empty(B, 5, dtype=torch.int32, device=DEV)
-    _lib.call("pfo_eval_score", ptr(es.to(DEV)), ptr(ed.to(DEV)), ptr(ec.to(DEV)), B, n_cand, d, 5,
+    es_d, ed_d, ec_d = es.to(DEV), ed.to(DEV), ec.to(DEV)
+    _lib.call("pfo_eval_score", ptr(es_d), ptr(ed_d), ptr(ec_d), B, n_cand, d, 5,
               ptr(scores), ptr(pos_rank), ptr(top))
     s = scores.cpu().numpy()
     assert rel_err(s, ref.numpy()) < 1e-5
