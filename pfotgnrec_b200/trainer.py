@@ -1,0 +1,252 @@
+"""Training / evaluation driver over a synthetic stream: the loop of reference main.py:160-394
+(train) and evaluation.py:63-138 (scoring + ranking), with the MV-selection block and the BPR
+loss -- inline script code in the reference -- behind entry points (`MVSelector.select`,
+`bpr_loss`).  Everything per batch runs on the device; the host only launches.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ptr
+from .engine import ModelConfig
+from .graph import TemporalCSR, NeighborFinder
+from .sampler import CandidateSampler, MVSelector
+from .synth import Stream, log_returns
+
+_OVERLAY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "overlay")
+
+
+def load_overlay():
+    """Import the drop-in packages (model.tgn, utils.utils, ...) from pfotgnrec_b200/overlay."""
+    if _OVERLAY not in sys.path:
+        sys.path.insert(0, _OVERLAY)
+    return importlib.import_module("model.tgn"), importlib.import_module("utils.utils")
+
+
+class _BPR(torch.autograd.Function):
+    """-mean log sigmoid(mean_k(<u,p> - <u,n_k>)) with its gradient from one fused kernel (K6)."""
+
+    @staticmethod
+    def forward(ctx, eu, ep, en, ws):
+        B, d = eu.shape
+        k = en.shape[0] // B
+        eu, ep, en = eu.contiguous(), ep.contiguous(), en.contiguous()
+        loss = torch.empty(1, device=eu.device)
+        need = any(ctx.needs_input_grad[:3])
+        du = torch.empty_like(eu) if need else None
+        dp = torch.empty_like(ep) if need else None
+        dn = torch.empty_like(en) if need else None
+        _lib.call("pfo_bpr", ptr(eu), ptr(ep), ptr(en), B, k, d, ptr(du), ptr(dp), ptr(dn), ptr(loss), 1.0, ptr(ws))
+        ctx.grads = (du, dp, dn)
+        return loss.squeeze(0)
+
+    @staticmethod
+    def backward(ctx, g):
+        du, dp, dn = ctx.grads
+        return du * g, dp * g, dn * g, None
+
+
+def bpr_loss(e_u, e_pos, e_neg, workspace=None):
+    """BPR loss of reference main.py:321-337 (e_neg is [B*k, d], interaction-major)."""
+    if workspace is None:
+        workspace = torch.empty(1024, device=e_u.device)
+    return _BPR.apply(e_u, e_pos, e_neg, workspace)
+
+
+@dataclass
+class TrainConfig:
+    model: str = "ours"          # ours | tgn | jodie | dyrep | tgat   (reference main.py:63-74)
+    bs: int = 512
+    n_neighbors: int = 10
+    n_layers: int = 1
+    d: int = 64
+    n_heads: int = 2
+    dropout: float = 0.0
+    lr: float = 1e-4
+    num_negatives: int = 20      # candidates per interaction for MV selection
+    p_pos_num: int = 1
+    p_neg_num: int = 3
+    gamma: float = 2.0
+    lambda_mv: float = 0.5
+    seed: int = 0
+    gemm_mode: str = "fp32"
+
+
+class StreamOnDevice:
+    """The interaction stream resident in HBM (columns of reference utils/data.py `Data`)."""
+
+    def __init__(self, st: Stream, device):
+        dev = torch.device(device)
+        self.n_events = st.n_events
+        self.src = torch.as_tensor(st.sources.astype(np.int32), device=dev)
+        self.dst = torch.as_tensor(st.destinations.astype(np.int32), device=dev)
+        self.ts = torch.as_tensor(st.timestamps, device=dev)
+        self.eidx = torch.as_tensor(st.edge_idxs.astype(np.int32), device=dev)
+        self.ev = torch.as_tensor(st.edge_idxs.astype(np.int64), device=dev)
+        self.day = torch.as_tensor(st.day_idx.astype(np.int32), device=dev)
+        self.port_ptr = torch.as_tensor(st.port_ptr.astype(np.int64), device=dev)
+        pi = st.port_items if st.port_items.size else np.zeros(1, np.int32)
+        self.port_items = torch.as_tensor(pi.astype(np.int32), device=dev)
+        self.port_items_as_item_ids = self.port_items + (st.n_users + 1)
+
+
+class PfoTrainer:
+    """Builds the model on a synthetic stream and steps it (train or evaluate)."""
+
+    def __init__(self, st: Stream, tc: TrainConfig, device="cuda", train_frac_mask=None):
+        self.st, self.tc, self.device = st, tc, torch.device(device)
+        tgn_mod, _ = load_overlay()
+        train_mask, val_mask, test_mask = st.split()
+        if train_frac_mask is not None:
+            train_mask = train_frac_mask
+        self.masks = (train_mask, val_mask, test_mask)
+        self.n_train = int(train_mask.sum())
+        tr = np.nonzero(train_mask)[0]
+        self.csr_train = TemporalCSR(st.sources[tr], st.destinations[tr], st.edge_idxs[tr], st.timestamps[tr],
+                                     n_nodes=st.n_nodes, device=device)
+        self.csr_full = TemporalCSR(st.sources, st.destinations, st.edge_idxs, st.timestamps,
+                                    n_nodes=st.n_nodes, device=device)
+        uniform = tc.model == "tgat"
+        self.nf_train = NeighborFinder(self.csr_train, uniform=uniform, seed=tc.seed)
+        self.nf_full = NeighborFinder(self.csr_full, uniform=uniform, seed=tc.seed)
+        rs = np.random.RandomState(0)                     # main.py:9,87: node features ~ U(0,1)
+        node_feat = rs.rand(st.n_nodes, tc.d)
+        kw = dict(memory_updater_type="gru", embedding_module_type="graph_attention", use_memory=True,
+                  dyrep=False, use_destination_embedding_in_message=False)
+        if tc.model == "jodie":
+            kw.update(memory_updater_type="rnn", embedding_module_type="time")
+        elif tc.model == "dyrep":
+            kw.update(memory_updater_type="rnn", dyrep=True, use_destination_embedding_in_message=True)
+        elif tc.model == "tgat":
+            kw.update(use_memory=False)
+        ms, ss, md, sd = self._time_statistics()
+        torch.manual_seed(tc.seed)
+        self.tgn = tgn_mod.TGN(neighbor_finder=self.nf_train, node_features=node_feat,
+                               edge_features=st.edge_features.copy(), device=self.device, n_layers=tc.n_layers,
+                               n_heads=tc.n_heads, dropout=tc.dropout, message_dimension=100,
+                               memory_dimension=tc.d, memory_update_at_start=True, message_function="identity",
+                               aggregator_type="last", n_neighbors=tc.n_neighbors,
+                               mean_time_shift_src=ms, std_time_shift_src=ss, mean_time_shift_dst=md,
+                               std_time_shift_dst=sd, use_source_embedding_in_message=False,
+                               gemm_mode=tc.gemm_mode, **kw).to(self.device)
+        self.opt = torch.optim.Adam(self.tgn.parameters(), lr=tc.lr, fused=True)
+        self.dev_stream = StreamOnDevice(st, device)
+        universe_items = np.unique(st.destinations[tr])
+        self.universe_items = universe_items
+        self.mv = None
+        if tc.model == "ours":
+            self.mv = MVSelector(log_returns(st.prices_future), universe_items - st.n_users - 1, st.n_users,
+                                 gamma=tc.gamma, lam=tc.lambda_mv, n_candidates=tc.num_negatives,
+                                 n_pos=tc.p_pos_num, n_neg=tc.p_neg_num, seed=tc.seed, device=device)
+        self.neg_sampler = CandidateSampler(universe_items, device=device)
+        self.eval_sampler = CandidateSampler(np.unique(st.destinations), device=device)
+        self.bpr_ws = torch.empty(1024, device=self.device)
+
+    def _time_statistics(self):
+        """reference utils/data.py:75-99 (compute_time_statistics), vectorised."""
+        st = self.st
+        out = []
+        for ids in (st.sources, st.destinations):
+            order = np.lexsort((np.arange(st.n_events), ids))
+            t = st.timestamps[order]
+            first = np.r_[True, ids[order][1:] != ids[order][:-1]]
+            diff = np.where(first, t, t - np.r_[0.0, t[:-1]])
+            out += [float(np.mean(diff)), float(np.std(diff))]
+        return out
+
+    # ------------------------------------------------------------------ one training step
+    def _batch(self, s, e):
+        D = self.dev_stream
+        return dict(src=D.src[s:e], dst=D.dst[s:e], ts=D.ts[s:e], eidx=D.eidx[s:e], ev=D.ev[s:e], day=D.day[s:e],
+                    port_ptr=D.port_ptr[s:e + 1])
+
+    def make_host_batches(self, start, count, bs):
+        """Pinned host copies of `count` consecutive batches, as a caller holding numpy data passes them."""
+        st, out = self.st, []
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        for i in range(count):
+            s, e = start + i * bs, start + (i + 1) * bs
+            pp = st.port_ptr[s:e + 1]
+            hb = dict(src=pin(st.sources[s:e].astype(np.int32)), dst=pin(st.destinations[s:e].astype(np.int32)),
+                      ts=pin(st.timestamps[s:e]), eidx=pin(st.edge_idxs[s:e].astype(np.int32)),
+                      ev=pin(st.edge_idxs[s:e].astype(np.int64)), day=pin(st.day_idx[s:e].astype(np.int32)),
+                      port_ptr=pin((pp - pp[0]).astype(np.int64)),
+                      port_items=pin(np.r_[st.port_items[pp[0]:pp[-1]], 0].astype(np.int32)))
+            hb["nbytes"] = sum(v.numel() * v.element_size() for v in hb.values())
+            out.append(hb)
+        return out
+
+    def train_step_host(self, hb):
+        """One step from HOST buffers: host->device copies of the batch, then `train_step`."""
+        b = {k: v.to(self.device, non_blocking=True) for k, v in hb.items() if k != "nbytes"}
+        return self.train_step(0, 0, batch=b)
+
+    def train_step(self, s, e, batch=None):
+        """Events [s, e) of the stream: MV selection (or uniform negatives) -> embeddings -> BPR ->
+        backward -> Adam (reference main.py:179-394).  Returns the loss tensor (no host sync)."""
+        tc, D = self.tc, self.dev_stream
+        b = batch if batch is not None else self._batch(s, e)
+        tgn = self.tgn.train()
+        eng = tgn._get_engine()
+        eng.nf = self.nf_train
+        self.opt.zero_grad(set_to_none=True)
+        params = tgn._params()
+        B = b["src"].shape[0]
+        port_items = b.get("port_items", D.port_items)
+        if tc.model == "ours":
+            p_pos, p_neg = self.mv.select(b["ev"], b["day"], b["dst"], b["port_ptr"], port_items)
+            e_s, _, e_p, e_n = eng.compute_temporal_embeddings(params, b["src"], b["dst"], [p_pos, p_neg], b["ts"],
+                                                               b["eidx"], tc.n_neighbors, train=True)
+        else:
+            held = port_items + (self.st.n_users + 1) if "port_items" in b else D.port_items_as_item_ids
+            neg = self.neg_sampler.sample(b["ev"], b["port_ptr"], held, tc.p_neg_num, seed=tc.seed).reshape(-1)
+            e_s, e_p, e_n = eng.compute_temporal_embeddings(params, b["src"], b["dst"], [neg], b["ts"], b["eidx"],
+                                                            tc.n_neighbors, train=True)
+        loss = bpr_loss(e_s, e_p, e_n, self.bpr_ws)
+        loss.backward()
+        self.opt.step()
+        return loss.detach()
+
+    # ------------------------------------------------------------------ one evaluation step
+    @torch.no_grad()
+    def eval_step(self, s, e, n_items=None, batch=None):
+        """Interactions [s, e): N_ITEMS candidates per interaction (seed 2024), embeddings, scores, rank of
+        the true item and top-5 (reference evaluation.py:84-115,134-138).  Advances memory like the
+        reference does.  Returns (pos_rank int32[B], top5 int32[B,5], candidates int32[B,N])."""
+        D = self.dev_stream
+        b = batch if batch is not None else self._batch(s, e)
+        tgn = self.tgn.eval()
+        eng = tgn._get_engine()
+        eng.nf = self.nf_full
+        N = int(n_items) if n_items is not None else int(self.eval_sampler.items.shape[0])
+        B = b["src"].shape[0]
+        # evaluation recreates RandomState(2024) per batch: the stream is keyed by position in the batch
+        ev = torch.arange(B, dtype=torch.int64, device=self.device)
+        cand = self.eval_sampler.sample(ev, b["port_ptr"], D.port_items_as_item_ids, N, seed=2024)
+        e_s, e_d, e_c = eng.compute_temporal_embeddings(tgn._params(), b["src"], b["dst"], [cand.reshape(-1)], b["ts"],
+                                                        b["eidx"], self.tc.n_neighbors, train=False)
+        d = e_s.shape[1]
+        scores = torch.empty(B, 1 + N, device=self.device)
+        pos_rank = torch.empty(B, dtype=torch.int32, device=self.device)
+        top = torch.empty(B, 5, dtype=torch.int32, device=self.device)
+        e_s, e_d, e_c = e_s.contiguous(), e_d.contiguous(), e_c.contiguous()
+        _lib.call("pfo_eval_score", ptr(e_s), ptr(e_d), ptr(e_c), B, N, d, 5, ptr(scores), ptr(pos_rank), ptr(top))
+        return pos_rank, top, cand, scores
+
+    @staticmethod
+    def recall_ndcg(pos_rank, ks=(1, 3, 5)):
+        """Recall@k / NDCG@k with a single relevant item (reference evaluation.py:11-21,141-144)."""
+        r = pos_rank.to(torch.float32)
+        out = {}
+        for k in ks:
+            hit = (r < k).to(torch.float32)
+            out[f"recall_{k}"] = hit.mean()
+            out[f"ndcg_{k}"] = (hit / torch.log2(r + 2.0)).mean()
+        return out
