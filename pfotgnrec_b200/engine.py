@@ -138,7 +138,7 @@ F4 = 4  # sizeof(float)
 class _LayerTape:
     """Everything one attention-layer invocation saves for its backward."""
     __slots__ = ("layer", "M", "n", "Tq", "qidx", "T", "idx", "eidx", "dt", "CAT", "QP", "QK", "XB", "P",
-                 "invalid", "ATT", "H1", "OUT", "child_q", "child_n", "dTq", "dT", "step")
+                 "invalid", "ATT", "H1", "out_rows", "child_q", "child_n", "dTq", "dT", "step")
 
 
 class TGNEngine:
@@ -314,9 +314,12 @@ class TGNEngine:
         _linear(c, ptr(tp.ATT), E, None, ptr(Wo), E, 0, ptr(bo), ptr(tp.CAT), ldc, M, E, E, row_zero=ptr(tp.invalid))
         tp.H1 = torch.empty(M, d, device=dev)
         _linear(c, ptr(tp.CAT), ldc, None, ptr(W1), ldc, 0, ptr(b1), ptr(tp.H1), d, M, d, ldc, act=1)
-        tp.OUT = torch.empty(M, d, device=dev)
-        _linear(c, ptr(tp.H1), d, None, ptr(W2), d, 0, ptr(b2), ptr(tp.OUT), d, M, d, d)
-        return tp.OUT, tp
+        # the output is NOT kept on the tape: it is the autograd output, and holding it from the
+        # backward context would form a reference cycle that only the cyclic GC can free
+        out = torch.empty(M, d, device=dev)
+        tp.out_rows = M
+        _linear(c, ptr(tp.H1), d, None, ptr(W2), d, 0, ptr(b2), ptr(out), d, M, d, d)
+        return out, tp
 
     def _attention_backward(self, tp, dOUT, W, dW, save):
         """Accumulates parameter grads into dW[layer-1] and feature grads into tp.dTq / tp.dT."""
@@ -511,8 +514,8 @@ class TGNStepFunction(torch.autograd.Function):
                 if tp.layer == 1:
                     tp.dTq = tp.dT = dH0
                 else:
-                    tp.dTq = torch.zeros_like(tp.child_q.OUT)
-                    tp.dT = torch.zeros_like(tp.child_n.OUT)
+                    tp.dTq = torch.zeros(tp.child_q.out_rows, d, device=dev)
+                    tp.dT = torch.zeros(tp.child_n.out_rows, d, device=dev)
                 eng._attention_backward(tp, g, pk["layerW"], g_layers, save)
                 if tp.layer > 1:
                     stack.append((tp.child_q, tp.dTq))
