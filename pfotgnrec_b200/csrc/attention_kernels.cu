@@ -14,6 +14,7 @@
 // Row layout of QK / XB / dQK / dXB: [Q, H, EKP], segment = [h (d) | e (F) | te (d) | psum | pad].
 #include "common.cuh"
 #include "philox.cuh"
+#include "pfo_math.cuh"
 
 namespace {
 
@@ -73,7 +74,7 @@ attn_nbr_fwd_kernel(const NbrArgs p) {
 #pragma unroll
             for (int i = 0; i < DPL; ++i) {
                 xh[i] = row[i];
-                xt[i] = cosf(fmaf(dtj, tw[i], tb[i]));  // full-range cosf, never __cosf (SURVEY hard part 1)
+                xt[i] = pfo_cosf(fmaf(dtj, tw[i], tb[i]));  // full-range, never __cosf (SURVEY hard part 1)
             }
             const float xe = lane < F ? p.efeat[(int64_t)p.eidx[q * n + j] * F + lane] : 0.0f;
 #pragma unroll
@@ -171,7 +172,7 @@ attn_nbr_bwd_kernel(const NbrArgs p) {
 #pragma unroll
                 for (int i = 0; i < DPL; ++i) {
                     float sn, cs;
-                    sincosf(fmaf(dtj, tw[i], tb[i]), &sn, &cs);
+                    pfo_sincosf(fmaf(dtj, tw[i], tb[i]), &sn, &cs);
                     xh[i] = row[i]; xt[i] = cs;
                     st[c0 + i] = xh[i]; st[d + c0 + i] = cs; st[2 * d + c0 + i] = sn;
                 }

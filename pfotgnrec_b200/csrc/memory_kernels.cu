@@ -10,6 +10,7 @@
 //   last_pos[N] (i32 scratch, -1 when idle).
 // RAW = 2d + F + d floats per message, rows padded to RAWP (multiple of 4).
 #include "common.cuh"
+#include "pfo_math.cuh"
 
 namespace {
 
@@ -177,7 +178,7 @@ store_messages_kernel(const int32_t* __restrict__ src, const int32_t* __restrict
         for (int c = lane; c < d; c += 32) {
             out[c] = ms[c];
             out[d + c] = mo[c];
-            out[2 * d + F + c] = cosf(fmaf(delta, tw[c], tb[c]));   // fmaf == nn.Linear(1, d) (SURVEY hard part 1)
+            out[2 * d + F + c] = pfo_cosf(fmaf(delta, tw[c], tb[c]));   // fmaf == nn.Linear(1, d) (SURVEY hard part 1)
         }
         for (int c = lane; c < F; c += 32) out[2 * d + c] = ef[c];
         __syncwarp();

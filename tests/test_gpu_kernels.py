@@ -268,3 +268,34 @@ def test_eval_score_and_ranking():
     rk = eval_ranking(s)
     assert np.array_equal(top.cpu().numpy(), rk[:, :5])
     assert np.array_equal(pos_rank.cpu().numpy(), np.argmax(rk == 0, axis=1))
+
+
+# ------------------------------------------------------------------------------ bf16 tcgen05 path
+@pytest.mark.parametrize("M,N,K", [(1000, 192, 193), (257, 64, 64), (4096, 129, 64), (33, 130, 32), (5000, 64, 192),
+                                   (300, 128, 128), (70000, 192, 64)])
+@pytest.mark.parametrize("wt", [0, 1])
+def test_linear_bf16_tcgen05(M, N, K, wt):
+    from pfotgnrec_b200 import _lib
+    from pfotgnrec_b200._lib import ptr
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    lda = K + 3 if K % 2 else K          # exercise both the scalar and the float4 staging path
+    A = torch.randn(M + 50, lda, generator=g)
+    W = torch.randn(N, K, generator=g)
+    b = torch.randn(N, generator=g)
+    idx = torch.randint(-1, M + 50, (M,), generator=g, dtype=torch.int32)
+    rz = (torch.rand(M, generator=g) < 0.1).to(torch.int32)
+    rows = torch.where(idx.unsqueeze(1) >= 0, A[idx.clamp(min=0).long(), :K], torch.zeros(1))
+    # operands rounded to bf16, exact products, fp32-ish accumulation: a sharp check of the layouts
+    ref = (rows.bfloat16().double() @ W.bfloat16().double().t() + b.double()) * 0.5
+    ref = torch.relu(ref)
+    ref[rz != 0] = 0
+    full = torch.relu((rows.double() @ W.double().t() + b.double()) * 0.5)
+    full[rz != 0] = 0
+    Ad, Wd, bd, idxd, rzd = (t.to(DEV) for t in (A, W.t().contiguous() if wt else W, b, idx, rz))
+    C = torch.full((M, N + 2), 7.0, device=DEV)
+    _lib.call("pfo_linear_bf16", ptr(Ad), lda, ptr(idxd), ptr(Wd), N if wt else K, wt, ptr(bd), None, 0,
+              ptr(C), N + 2, M, None, N, K, 0.5, 1, ptr(rzd), None, 0, 0)
+    got = C[:, :N].cpu().numpy()
+    assert rel_err(got, ref.numpy()) < 1e-5
+    assert rel_err(got, full.numpy()) < 2e-2           # the bf16 contract of BASELINE.json
+    assert (C[:, N:] == 7.0).all()
