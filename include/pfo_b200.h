@@ -100,6 +100,18 @@ int pfo_store_messages(const int32_t* src, const int32_t* dst, const int32_t* ei
                        float* pend_msg, int64_t rawp, float* pend_ts, uint8_t* pend_valid,
                        int32_t* last_pos, void* stream);
 
+/* node-sharded variants (pfotgnrec_b200/dist.py): build the message rows where the events live (from the
+ * unique-node rows fetched from the owners), apply persist + last-wins where the nodes live.  key = global
+ * position (side * B_global + event index): the largest key per node wins, independent of the shard count. */
+int pfo_build_messages(const int32_t* src_slot, const int32_t* dst_slot, const int32_t* eidx, const double* ts,
+                       int B, int d, int F, const float* Hnew, const float* lu_u, const float* edge_feat,
+                       const float* tw, const float* tb, const float* other_emb_for_src,
+                       const float* other_emb_for_dst, float* rows, int64_t ldr, float* t32_out, void* stream);
+int pfo_apply_messages(const int32_t* node, const int32_t* key, int64_t R, int d, int raw,
+                       const int32_t* slot_of_node, const float* Hnew, const float* rows, int64_t ldr,
+                       const float* t32, float* memory, float* last_update, float* pend_msg, int64_t rawp,
+                       float* pend_ts, uint8_t* pend_valid, int32_t* last_pos, void* stream);
+
 /* ---- jodie time-projection embedding --- modules/embedding_module.py:57-61, model/tgn.py:260-266 */
 int pfo_time_embedding_fwd(const int32_t* q_nodes, const double* q_ts, int64_t Q, int64_t n_src, int d,
                            const int32_t* slot_of_node, const float* Hnew, const float* lu_u,

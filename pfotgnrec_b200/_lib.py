@@ -32,6 +32,8 @@ _SIGS = {
     "pfo_cell_backward": (c_int, [P, P, c_int64, c_int, c_int, P, P, c_int64, P, P, P, P, P, P]),
     "pfo_persist_rank": (c_int, [P, P, c_int, c_int, P, P, P, P, P, P, P, P]),
     "pfo_store_messages": (c_int, [P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_int64, P, P, P, P]),
+    "pfo_build_messages": (c_int, [P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_int64, P, P]),
+    "pfo_apply_messages": (c_int, [P, P, c_int64, c_int, c_int, P, P, P, c_int64, P, P, P, P, c_int64, P, P, P, P]),
     "pfo_time_embedding_fwd": (c_int, [P, P, c_int64, c_int64, c_int, P, P, P, c_float, c_float, c_float,
                                        c_float, P, P, P, P, P]),
     "pfo_time_embedding_bwd": (c_int, [P, c_int64, c_int, P, P, P, P, P, P, P, P, P, c_int64, P]),
@@ -54,7 +56,7 @@ EXPORTS = tuple(_SIGS)
 _lib = None
 LAUNCHES = 0            # kernels launched through this binding (bench.py reports it)
 _LAUNCHES_PER_CALL = {"pfo_compact_nodes": 3, "pfo_wgrad_f32": 2, "pfo_time_embedding_bwd": 2,
-                      "pfo_attn_nbr_bwd": 2, "pfo_bpr": 2, "pfo_abi_version": 0,
+                      "pfo_attn_nbr_bwd": 2, "pfo_bpr": 2, "pfo_apply_messages": 2, "pfo_abi_version": 0,
                       "pfo_compact_workspace_ints": 0, "pfo_wgrad_workspace_floats": 0,
                       "pfo_attn_nbr_bwd_workspace_floats": 0}
 

@@ -274,6 +274,84 @@ gather_rows_kernel(const float* __restrict__ src, int64_t lds, const int32_t* __
     }
 }
 
+// ---- node-sharded variants (pfotgnrec_b200/dist.py): messages are BUILT where the events live,
+// from the feature rows fetched from the owners, and APPLIED where the nodes live.
+// build: one warp per (side, event): row = [mem'[self] | mem'[other] | edge_feat | cos((fp32(t) - lu'[self]) w + b)]
+// with mem' / lu' = post-persist memory / last_update = the rows of the unique-node table.
+__global__ void __launch_bounds__(256)
+build_messages_kernel(const int32_t* __restrict__ src_slot, const int32_t* __restrict__ dst_slot,
+                      const int32_t* __restrict__ eidx, const double* __restrict__ ts, int B, int d, int F,
+                      const float* __restrict__ Hnew, const float* __restrict__ lu_u,
+                      const float* __restrict__ edge_feat, const float* __restrict__ tw, const float* __restrict__ tb,
+                      const float* __restrict__ other_emb_for_src, const float* __restrict__ other_emb_for_dst,
+                      float* __restrict__ rows, int64_t ldr, float* __restrict__ t32_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t idx = warp; idx < 2 * (int64_t)B; idx += nwarps) {
+        const int i = (int)(idx % B);
+        const bool is_src = idx < B;
+        const int self = is_src ? src_slot[i] : dst_slot[i];
+        const int other = is_src ? dst_slot[i] : src_slot[i];
+        const float t32 = (float)ts[i];
+        const float delta = t32 - lu_u[self];
+        float* out = rows + idx * ldr;
+        const float* ms = Hnew + (int64_t)self * d;
+        const float* oe = is_src ? other_emb_for_src : other_emb_for_dst;
+        const float* mo = oe ? oe + (int64_t)i * d : Hnew + (int64_t)other * d;
+        const float* ef = edge_feat + (int64_t)eidx[i] * F;
+        for (int c = lane; c < d; c += 32) {
+            out[c] = ms[c];
+            out[d + c] = mo[c];
+            out[2 * d + F + c] = pfo_cosf(fmaf(delta, tw[c], tb[c]));
+        }
+        for (int c = lane; c < F; c += 32) out[2 * d + c] = ef[c];
+        if (lane == 0) t32_out[idx] = t32;
+    }
+}
+
+// apply (owner side), pass 1: last-wins key + persist of the positives that had a pending message
+__global__ void __launch_bounds__(256)
+apply_rank_kernel(const int32_t* __restrict__ node, const int32_t* __restrict__ key, int64_t R, int d,
+                  const int32_t* __restrict__ slot_of_node, const float* __restrict__ Hnew,
+                  const uint8_t* __restrict__ pend_valid, const float* __restrict__ pend_ts,
+                  float* __restrict__ memory, float* __restrict__ last_update, int32_t* __restrict__ last_pos) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < R; r += nwarps) {
+        const int v = node[r];
+        if (lane == 0) atomicMax(last_pos + v, key[r]);
+        if (pend_valid[v]) {
+            const float* h = Hnew + (int64_t)slot_of_node[v] * d;
+            float* m = memory + (int64_t)v * d;
+            for (int c = lane; c < d; c += 32) m[c] = h[c];
+            if (lane == 0) last_update[v] = pend_ts[v];
+        }
+    }
+}
+
+// pass 2: the row with the largest global position per node becomes the pending message
+__global__ void __launch_bounds__(256)
+apply_store_kernel(const int32_t* __restrict__ node, const int32_t* __restrict__ key, int64_t R, int raw,
+                   const float* __restrict__ rows, int64_t ldr, const float* __restrict__ t32,
+                   float* __restrict__ pend_msg, int64_t rawp, float* __restrict__ pend_ts,
+                   uint8_t* __restrict__ pend_valid, int32_t* __restrict__ last_pos) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < R; r += nwarps) {
+        const int v = node[r];
+        if (last_pos[v] != key[r]) continue;
+        __syncwarp();
+        const float* in = rows + r * ldr;
+        float* out = pend_msg + (int64_t)v * rawp;
+        for (int c = lane; c < raw; c += 32) out[c] = in[c];
+        __syncwarp();
+        if (lane == 0) { pend_ts[v] = t32[r]; pend_valid[v] = 1; last_pos[v] = -1; }
+    }
+}
+
 }  // namespace
 
 PFO_API int pfo_cell_forward(const int32_t* uniq, const int32_t* n_uniq, int64_t u_max, int d, int cell,
@@ -370,5 +448,30 @@ PFO_API int pfo_gather_rows(const float* src, int64_t lds, const int32_t* idx, i
                             float* dst, int64_t ldd, void* stream) {
     if (M <= 0) return 0;
     gather_rows_kernel<<<pfo_grid(M * d, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, lds, idx, M, d, dst, ldd);
+    PFO_LAUNCH_CHECK();
+}
+
+PFO_API int pfo_build_messages(const int32_t* src_slot, const int32_t* dst_slot, const int32_t* eidx, const double* ts,
+                               int B, int d, int F, const float* Hnew, const float* lu_u, const float* edge_feat,
+                               const float* tw, const float* tb, const float* other_emb_for_src,
+                               const float* other_emb_for_dst, float* rows, int64_t ldr, float* t32_out, void* stream) {
+    if (B <= 0) return 0;
+    build_messages_kernel<<<pfo_grid(2 * (int64_t)B * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        src_slot, dst_slot, eidx, ts, B, d, F, Hnew, lu_u, edge_feat, tw, tb, other_emb_for_src, other_emb_for_dst,
+        rows, ldr, t32_out);
+    PFO_LAUNCH_CHECK();
+}
+
+PFO_API int pfo_apply_messages(const int32_t* node, const int32_t* key, int64_t R, int d, int raw,
+                               const int32_t* slot_of_node, const float* Hnew, const float* rows, int64_t ldr,
+                               const float* t32, float* memory, float* last_update, float* pend_msg, int64_t rawp,
+                               float* pend_ts, uint8_t* pend_valid, int32_t* last_pos, void* stream) {
+    if (R <= 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int grid = pfo_grid(R * 32, 256, 8);
+    apply_rank_kernel<<<grid, 256, 0, s>>>(node, key, R, d, slot_of_node, Hnew, pend_valid, pend_ts, memory,
+                                           last_update, last_pos);
+    apply_store_kernel<<<grid, 256, 0, s>>>(node, key, R, raw, rows, ldr, t32, pend_msg, rawp, pend_ts, pend_valid,
+                                            last_pos);
     PFO_LAUNCH_CHECK();
 }

@@ -262,9 +262,72 @@ class TGNEngine:
                   ptr(st.slot_of_node), ptr(st.n_unique))
         return uniq, u_max
 
+    # ------------------------------------------------------------------ overridable stages
+    # (pfotgnrec_b200/dist.py replaces these three with their node-sharded, all-to-all versions)
+    def node_table(self, id_lists, cellW):
+        """Unique touched nodes of the batch and their feature rows: Hnew = lazily updated memory
+        (GRU/RNN applied to the pending message), H0 = Hnew + node features, lu_u = last_update'."""
+        c, st, dev = self.cfg, self.state, self.device
+        d = c.d
+        uniq, u_max = self._unique_nodes(id_lists)
+        n_uniq = st.n_unique.clone()
+        self.slot_map = st.slot_of_node
+        G = c.gates * d
+        H0 = torch.empty(u_max, d, device=dev)
+        Hnew = HG = XG = valid_u = lu_u = GI = GH = None
+        if c.use_memory:
+            HG = torch.empty(u_max, d, device=dev)
+            XG = torch.empty(u_max, c.raw, device=dev)
+            valid_u = torch.empty(u_max, dtype=torch.uint8, device=dev)
+            lu_u = torch.empty(u_max, device=dev)
+            _lib.call("pfo_gather_state", ptr(uniq), ptr(n_uniq), u_max, d, c.raw, ptr(st.memory), ptr(st.pend_msg),
+                      c.rawp, ptr(st.pend_valid), ptr(st.pend_ts), ptr(st.last_update),
+                      ptr(HG), ptr(XG), ptr(valid_u), ptr(lu_u))
+            W_ih, W_hh, b_ih, b_hh = cellW
+            GI = torch.empty(u_max, G, device=dev)
+            GH = torch.empty(u_max, G, device=dev)
+            _linear(c, ptr(XG), c.raw, None, ptr(W_ih), c.raw, 0, ptr(b_ih), ptr(GI), G, u_max, G, c.raw, m_dev=ptr(n_uniq))
+            _linear(c, ptr(HG), d, None, ptr(W_hh), d, 0, ptr(b_hh), ptr(GH), G, u_max, G, d, m_dev=ptr(n_uniq))
+            Hnew = torch.empty(u_max, d, device=dev)
+        _lib.call("pfo_cell_forward", ptr(uniq), ptr(n_uniq), u_max, d, c.cell, ptr(GI), ptr(GH), G, ptr(HG),
+                  ptr(valid_u), ptr(self.node_feat), ptr(Hnew), ptr(H0))
+        return dict(uniq=uniq, u_max=u_max, n_uniq=n_uniq, H0=H0, Hnew=Hnew, lu_u=lu_u, HG=HG, XG=XG,
+                    valid_u=valid_u, GI=GI, GH=GH)
+
+    def node_table_backward(self, tab, dH0, g_cell):
+        """dH0 (= dHnew) -> gradients of the cell weights (memory and messages are detached inputs)."""
+        c, dev = self.cfg, self.device
+        d, u_max, n_uniq = c.d, tab["u_max"], tab["n_uniq"]
+        G = c.gates * d
+        dGI = torch.empty(u_max, G, device=dev)
+        dGH = torch.empty(u_max, G, device=dev)
+        _lib.call("pfo_cell_backward", ptr(tab["uniq"]), ptr(n_uniq), u_max, d, c.cell, ptr(tab["GI"]), ptr(tab["GH"]),
+                  G, ptr(tab["HG"]), ptr(tab["valid_u"]), ptr(dH0), ptr(dGI), ptr(dGH))
+        gW_ih, gW_hh, gb_ih, gb_hh = g_cell
+        _wgrad(self.ws, ptr(dGI), G, ptr(tab["XG"]), c.raw, None, u_max, G, c.raw, ptr(gW_ih), c.raw, ptr(gb_ih),
+               m_dev=ptr(n_uniq))
+        _wgrad(self.ws, ptr(dGH), G, ptr(tab["HG"]), d, None, u_max, G, d, ptr(gW_hh), d, ptr(gb_hh),
+               m_dev=ptr(n_uniq))
+
+    def persist_and_store(self, tab, batch, emb, tw, tb):
+        """Persist the positives' memory from the lazy result, then build and store the new raw
+        messages with last-wins (tgn.py:185-206)."""
+        c, st = self.cfg, self.state
+        d, F, B = c.d, c.n_edge_feat, batch["B"]
+        src, dst = batch["src"], batch["dst"]
+        _lib.call("pfo_persist_rank", ptr(src), ptr(dst), B, d, ptr(st.slot_of_node), ptr(tab["Hnew"]),
+                  ptr(st.pend_valid), ptr(st.pend_ts), ptr(st.memory), ptr(st.last_update), ptr(st.last_pos))
+        o_src = o_dst = None
+        if c.dst_emb_in_msg:    # dyrep: the other endpoint's embedding rides in the message (tgn.py:364-365)
+            o_src, o_dst = emb[B:2 * B], emb[:B]
+        _lib.call("pfo_store_messages", ptr(src), ptr(dst), ptr(batch["eidx"]), ptr(batch["ts"]), B, d, F,
+                  ptr(st.memory), ptr(st.last_update), ptr(self.edge_feat), ptr(tw), ptr(tb),
+                  ptr(o_src), ptr(o_dst), ptr(st.pend_msg), c.rawp, ptr(st.pend_ts), ptr(st.pend_valid),
+                  ptr(st.last_pos))
+
     def _slots(self, ids):
         out = torch.empty(ids.shape, dtype=torch.int32, device=self.device)
-        _lib.call("pfo_map_slots", ptr(ids), ids.numel(), 1, ptr(self.state.slot_of_node), ptr(out))
+        _lib.call("pfo_map_slots", ptr(ids), ids.numel(), 1, ptr(self.slot_map), ptr(out))
         return out
 
     def _attention_forward(self, tree, W, H0, save):
@@ -333,7 +396,7 @@ class TGNEngine:
         gWq, gcq, gWk, gWvA, gWo, gbo, gW1, gb1, gW2, gb2 = dW[tp.layer - 1]
         scale = 1.0 / math.sqrt(hd)
         ws = self.ws
-        f32 = ModelConfig(d=d, n_edge_feat=F)           # gradients always take the exact fp32 path
+        f32 = c                                         # dgrad follows the GEMM mode; wgrad always accumulates in fp32
         # merge MLP
         dH1 = torch.empty(M, d, device=dev)
         _linear(f32, ptr(dOUT), d, None, ptr(W2), d, 1, None, ptr(dH1), d, M, d, d, relu_gate=ptr(tp.H1), ld_gate=d)
@@ -404,29 +467,11 @@ class TGNStepFunction(torch.autograd.Function):
             tree = eng._sample_tree(q_nodes, q_ts, c.n_layers, n)
             id_lists = []
             eng._collect_level0(tree, id_lists)
-        uniq, u_max = eng._unique_nodes(id_lists)
-        n_uniq = st.n_unique
 
         # 2. lazy memory update on the unique nodes (memory_updater.py:35-53, restricted)
-        G = c.gates * d
-        H0 = torch.empty(u_max, d, device=dev)
-        Hnew = HG = XG = valid_u = lu_u = GI = GH = None
-        if c.use_memory:
-            HG = torch.empty(u_max, d, device=dev)
-            XG = torch.empty(u_max, c.raw, device=dev)
-            valid_u = torch.empty(u_max, dtype=torch.uint8, device=dev)
-            lu_u = torch.empty(u_max, device=dev)
-            _lib.call("pfo_gather_state", ptr(uniq), ptr(n_uniq), u_max, d, c.raw, ptr(st.memory), ptr(st.pend_msg),
-                      c.rawp, ptr(st.pend_valid), ptr(st.pend_ts), ptr(st.last_update),
-                      ptr(HG), ptr(XG), ptr(valid_u), ptr(lu_u))
-            W_ih, W_hh, b_ih, b_hh = cellW
-            GI = torch.empty(u_max, G, device=dev)
-            GH = torch.empty(u_max, G, device=dev)
-            _linear(c, ptr(XG), c.raw, None, ptr(W_ih), c.raw, 0, ptr(b_ih), ptr(GI), G, u_max, G, c.raw, m_dev=ptr(n_uniq))
-            _linear(c, ptr(HG), d, None, ptr(W_hh), d, 0, ptr(b_hh), ptr(GH), G, u_max, G, d, m_dev=ptr(n_uniq))
-            Hnew = torch.empty(u_max, d, device=dev)
-        _lib.call("pfo_cell_forward", ptr(uniq), ptr(n_uniq), u_max, d, c.cell, ptr(GI), ptr(GH), G, ptr(HG),
-                  ptr(valid_u), ptr(eng.node_feat), ptr(Hnew), ptr(H0))
+        tab = eng.node_table(id_lists, cellW)
+        uniq, u_max, n_uniq = tab["uniq"], tab["u_max"], tab["n_uniq"]
+        H0, Hnew, lu_u = tab["H0"], tab["Hnew"], tab["lu_u"]
 
         # 3. embeddings
         tape = None
@@ -439,7 +484,7 @@ class TGNStepFunction(torch.autograd.Function):
             emb = torch.empty(Q, d, device=dev)
             td = torch.empty(Q, device=dev)
             ms, ss, md, sd = c.shift
-            _lib.call("pfo_time_embedding_fwd", ptr(q_nodes), ptr(q_ts), Q, n_src, d, ptr(st.slot_of_node), ptr(Hnew),
+            _lib.call("pfo_time_embedding_fwd", ptr(q_nodes), ptr(q_ts), Q, n_src, d, ptr(eng.slot_map), ptr(Hnew),
                       ptr(lu_u), float(ms), float(ss), float(md), float(sd), ptr(embW[0]), ptr(embW[1]),
                       ptr(td), ptr(emb))
         else:                       # identity: memory'[nodes] (embedding_module.py:32-35)
@@ -448,28 +493,15 @@ class TGNStepFunction(torch.autograd.Function):
 
         # 4. persist positives, then build + store the new raw messages (tgn.py:185-206)
         if c.use_memory and batch["update_state"]:
-            src, dst = batch["src"], batch["dst"]
-            _lib.call("pfo_persist_rank", ptr(src), ptr(dst), B, d, ptr(st.slot_of_node), ptr(Hnew),
-                      ptr(st.pend_valid), ptr(st.pend_ts), ptr(st.memory), ptr(st.last_update), ptr(st.last_pos))
-            o_src = o_dst = None
-            if c.dst_emb_in_msg:    # dyrep: the other endpoint's embedding rides in the message (tgn.py:364-365)
-                o_src, o_dst = emb[B:2 * B], emb[:B]
-            _lib.call("pfo_store_messages", ptr(src), ptr(dst), ptr(batch["eidx"]), ptr(batch["ts"]), B, d, F,
-                      ptr(st.memory), ptr(st.last_update), ptr(eng.edge_feat), ptr(tw), ptr(tb),
-                      ptr(o_src), ptr(o_dst), ptr(st.pend_msg), c.rawp, ptr(st.pend_ts), ptr(st.pend_valid),
-                      ptr(st.last_pos))
+            eng.persist_and_store(tab, batch, emb, tw, tb)
         out = emb
         if c.use_memory and c.dyrep:    # dyrep returns the updated memory rows (tgn.py:211-215, :322-325)
             out = torch.empty(Q, d, device=dev)
             _lib.call("pfo_gather_rows", ptr(Hnew), d, ptr(qslots), Q, d, ptr(out), d)
         if need_grad:
             ctx.eng, ctx.save = eng, save
-            ctx.pack = dict(flat=flat, cellW=cellW, layerW=layerW, embW=embW, tape=tape, uniq=uniq, u_max=u_max,
-                            n_uniq=n_uniq.clone(), HG=HG, XG=XG, valid_u=valid_u, GI=GI, GH=GH, Hnew=Hnew,
-                            qslots=qslots, q_nodes=q_nodes, td=td, Q=Q,
-                            slot_snapshot=None)
-            if c.embedding == "time":   # slots are reused by later batches: snapshot what backward needs
-                ctx.pack["slot_snapshot"] = qslots
+            ctx.pack = dict(flat=flat, cellW=cellW, layerW=layerW, embW=embW, tape=tape, tab=tab, u_max=u_max,
+                            Hnew=Hnew, qslots=qslots, td=td, Q=Q)
         return out
 
     @staticmethod
@@ -488,7 +520,7 @@ class TGNStepFunction(torch.autograd.Function):
             g_layers = [[next(it) for _ in range(10)] for _ in range(c.n_layers)]
         elif c.embedding == "time":
             g_emb = [next(it), next(it)]
-        u_max, n_uniq = pk["u_max"], pk["n_uniq"]
+        u_max = pk["u_max"]
         dH0 = torch.zeros(u_max, d, device=dev)          # grad of the unique-node feature table
         attention_grad = c.embedding == "graph_attention" and not (c.use_memory and c.dyrep)
         if c.use_memory and c.dyrep:
@@ -523,14 +555,5 @@ class TGNStepFunction(torch.autograd.Function):
             g_tw.add_(save["g_twtb"][:d])
             g_tb.add_(save["g_twtb"][d:])
         if c.use_memory:
-            G = c.gates * d
-            dGI = torch.empty(u_max, G, device=dev)
-            dGH = torch.empty(u_max, G, device=dev)
-            _lib.call("pfo_cell_backward", ptr(pk["uniq"]), ptr(n_uniq), u_max, d, c.cell, ptr(pk["GI"]), ptr(pk["GH"]),
-                      G, ptr(pk["HG"]), ptr(pk["valid_u"]), ptr(dH0), ptr(dGI), ptr(dGH))
-            gW_ih, gW_hh, gb_ih, gb_hh = g_cell
-            _wgrad(eng.ws, ptr(dGI), G, ptr(pk["XG"]), c.raw, None, u_max, G, c.raw, ptr(gW_ih), c.raw, ptr(gb_ih),
-                   m_dev=ptr(n_uniq))
-            _wgrad(eng.ws, ptr(dGH), G, ptr(pk["HG"]), d, None, u_max, G, d, ptr(gW_hh), d, ptr(gb_hh),
-                   m_dev=ptr(n_uniq))
+            eng.node_table_backward(pk["tab"], dH0, g_cell)
         return (None, None) + tuple(grads)

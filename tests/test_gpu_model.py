@@ -27,7 +27,7 @@ def overlay():
     sys.path.remove(OVERLAY)
 
 
-def build_tgn(tgn_mod, utils_mod, z):
+def build_tgn(tgn_mod, utils_mod, z, gemm_mode="fp32"):
     import types
     data = types.SimpleNamespace(sources=z["st_sources"], destinations=z["st_destinations"],
                                  edge_idxs=z["st_edge_idxs"], timestamps=z["st_timestamps"])
@@ -42,7 +42,7 @@ def build_tgn(tgn_mod, utils_mod, z):
                       mean_time_shift_src=z["cfg_shift"][0], std_time_shift_src=z["cfg_shift"][1],
                       mean_time_shift_dst=z["cfg_shift"][2], std_time_shift_dst=z["cfg_shift"][3],
                       use_destination_embedding_in_message=bool(z["cfg_dst_emb"]),
-                      use_source_embedding_in_message=False, dyrep=bool(z["cfg_dyrep"]))
+                      use_source_embedding_in_message=False, dyrep=bool(z["cfg_dyrep"]), gemm_mode=gemm_mode)
     tgn = tgn.to(torch.device("cuda"))
     sd = tgn.state_dict()
     for k in z:
@@ -155,3 +155,30 @@ def test_larger_stream_vs_oracle(overlay):
             assert np.abs(got - ref).max() <= GTOL * scale + 1e-7, (bi, k)
         assert rel_err(tgn.memory.memory.cpu().numpy(), orc.memory.numpy()) < TOL
         assert np.array_equal(tgn.memory.state.pend_valid.cpu().numpy().astype(bool), orc.pend_valid.numpy())
+
+
+@pytest.mark.parametrize("tag", ["ours", "jodie"])
+def test_bf16_gemm_mode_within_2e_2(overlay, tag):
+    """gemm_mode='bf16' (tcgen05 tensor cores): 2e-2 contract of the north_star on embeddings, loss, memory."""
+    tgn_mod, utils_mod = overlay
+    z = load_golden(f"tgn_{tag}.npz")
+    tgn = build_tgn(tgn_mod, utils_mod, z, gemm_mode="bf16").train()
+    n, n_neg = int(z["cfg_n_neighbors"]), int(z["cfg_n_neg"])
+    from pfotgnrec_b200.trainer import bpr_loss
+    for bi in range(int(z["cfg_n_batches"])):
+        src, dst, extra, ts, ei = batch_inputs(z, bi)
+        tgn.zero_grad(set_to_none=True)
+        if len(extra) == 2:
+            e_s, e_d, e_p, e_n = tgn.compute_temporal_embeddings_p(src, dst, extra[0], extra[1], ts, ei, n)
+        else:
+            e_s, e_d, e_n = tgn.compute_temporal_embeddings(src, dst, extra[0], ts, ei, n)
+            e_p = e_d
+        for nm, e in (("src", e_s), ("dst", e_d), ("neg", e_n)):
+            assert rel_err(e.detach().cpu().numpy(), z[f"b{bi}_emb_{nm}"]) < 2e-2, (tag, bi, nm)
+        loss = bpr_loss(e_s, e_p, e_n)
+        ref_loss = float(z[f"b{bi}_loss"])
+        assert abs(loss.item() - ref_loss) < 2e-2 * max(1.0, abs(ref_loss))
+        loss.backward()
+        assert all(torch.isfinite(p.grad).all() for p in tgn.parameters() if p.grad is not None)
+        assert rel_err(tgn.memory.memory.cpu().numpy(), z[f"b{bi}_memory"]) < 2e-2
+        assert np.array_equal(tgn.memory.state.pend_valid.cpu().numpy().astype(bool), z[f"b{bi}_pend_valid"])
