@@ -62,6 +62,21 @@ int64_t pfo_wgrad_workspace_floats(int64_t M, int N, int K, int with_bias);
 int pfo_wgrad_f32(const float* G, int64_t ldg, const float* A, int64_t lda, const int32_t* a_idx,
                   int64_t M, const int32_t* m_dev, int N, int K, float* dW, int64_t lddw, float* db,
                   int accumulate, float* workspace, void* stream);
+/* ---- the same two contractions on the tcgen05 tensor cores, fed by TMA straight from the fp32 tensors
+ * (kind::tf32, accumulators in TMEM).  passes = 3: error-compensated 3xTF32 (a = rna_tf32(a) + residual,
+ * three MMAs per K step) -- the default "fp32" mode, 1e-5 contract; passes = 1: plain TF32, the fast mode
+ * (2e-2 contract).  Operand layouts TMA cannot describe (a_idx gathers, rows not 16-byte aligned, K beyond
+ * one accumulator) are routed to the FFMA kernels above inside the call.  pfo_wgrad_tf32 needs
+ * pfo_wgrad_tf32_workspace_floats floats of workspace. */
+int pfo_linear_tf32(const float* A, int64_t lda, const int32_t* a_idx, const float* W, int64_t ldw,
+                    int w_transposed, const float* bias, const float* bias_row_scale, int64_t ld_brs,
+                    float* C, int64_t ldc, int64_t M, const int32_t* m_dev, int N, int K,
+                    float alpha, int act, const int32_t* row_zero, const float* relu_gate, int64_t ld_gate,
+                    int accumulate, int passes, void* stream);
+int64_t pfo_wgrad_tf32_workspace_floats(int64_t M, int N, int K, int with_bias);
+int pfo_wgrad_tf32(const float* G, int64_t ldg, const float* A, int64_t lda, const int32_t* a_idx,
+                   int64_t M, const int32_t* m_dev, int N, int K, float* dW, int64_t lddw, float* db,
+                   int accumulate, float* workspace, int passes, void* stream);
 /* same contract as pfo_linear_f32 with bf16 operands / fp32 accumulation on tcgen05 tensor cores
  * (TMEM accumulators); selected by the host when gemm_mode == "bf16" (2e-2 contract). */
 int pfo_linear_bf16(const float* A, int64_t lda, const int32_t* a_idx, const float* W, int64_t ldw,

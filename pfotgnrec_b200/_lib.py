@@ -25,6 +25,10 @@ _SIGS = {
                                c_float, c_int, P, P, c_int64, c_int, P]),
     "pfo_linear_bf16": (c_int, [P, c_int64, P, P, c_int64, c_int, P, P, c_int64, P, c_int64, c_int64, P, c_int, c_int,
                                 c_float, c_int, P, P, c_int64, c_int, P]),
+    "pfo_linear_tf32": (c_int, [P, c_int64, P, P, c_int64, c_int, P, P, c_int64, P, c_int64, c_int64, P, c_int, c_int,
+                                c_float, c_int, P, P, c_int64, c_int, c_int, P]),
+    "pfo_wgrad_tf32_workspace_floats": (c_int64, [c_int64, c_int, c_int, c_int]),
+    "pfo_wgrad_tf32": (c_int, [P, c_int64, P, c_int64, P, c_int64, P, c_int, c_int, P, c_int64, P, c_int, P, c_int, P]),
     "pfo_wgrad_workspace_floats": (c_int64, [c_int64, c_int, c_int, c_int]),
     "pfo_wgrad_f32": (c_int, [P, c_int64, P, c_int64, P, c_int64, P, c_int, c_int, P, c_int64, P, c_int, P, P]),
     "pfo_gather_state": (c_int, [P, P, c_int64, c_int, c_int, P, P, c_int64, P, P, P, P, P, P, P, P]),
@@ -55,7 +59,8 @@ _SIGS = {
 EXPORTS = tuple(_SIGS)
 _lib = None
 LAUNCHES = 0            # kernels launched through this binding (bench.py reports it)
-_LAUNCHES_PER_CALL = {"pfo_compact_nodes": 3, "pfo_wgrad_f32": 2, "pfo_time_embedding_bwd": 2,
+_LAUNCHES_PER_CALL = {"pfo_compact_nodes": 3, "pfo_wgrad_f32": 2, "pfo_wgrad_tf32": 2,
+                      "pfo_wgrad_tf32_workspace_floats": 0, "pfo_time_embedding_bwd": 2,
                       "pfo_attn_nbr_bwd": 2, "pfo_bpr": 2, "pfo_apply_messages": 2, "pfo_abi_version": 0,
                       "pfo_compact_workspace_ints": 0, "pfo_wgrad_workspace_floats": 0,
                       "pfo_attn_nbr_bwd_workspace_floats": 0}

@@ -13,6 +13,8 @@ SOURCES = {
     "graph_kernels.cu": [],
     "linear_simt.cu": [],
     "linear_tc.cu": [],
+    "linear_tma.cu": [],
+    "wgrad_tma.cu": [],
     "memory_kernels.cu": [],
     "attention_kernels.cu": [],
     "mv_kernels.cu": ["-fmad=false"],

@@ -255,12 +255,13 @@ int launch_linear(const LinearArgs& a, cudaStream_t s) {
 
 }  // namespace
 
-PFO_API int pfo_linear_f32(const float* A, int64_t lda, const int32_t* a_idx,
-                           const float* W, int64_t ldw, int w_transposed,
-                           const float* bias, const float* bias_row_scale, int64_t ld_brs,
-                           float* C, int64_t ldc, int64_t M, const int32_t* m_dev, int N, int K,
-                           float alpha, int act, const int32_t* row_zero,
-                           const float* relu_gate, int64_t ld_gate, int accumulate, void* stream) {
+// also the landing path of pfo_linear_tf32 for operand layouts TMA cannot describe (linear_tma.cu)
+int pfo_linear_f32_impl(const float* A, int64_t lda, const int32_t* a_idx,
+                        const float* W, int64_t ldw, int w_transposed,
+                        const float* bias, const float* bias_row_scale, int64_t ld_brs,
+                        float* C, int64_t ldc, int64_t M, const int32_t* m_dev, int N, int K,
+                        float alpha, int act, const int32_t* row_zero,
+                        const float* relu_gate, int64_t ld_gate, int accumulate, void* stream) {
     if (M <= 0 || N <= 0) return 0;
     LinearArgs a{A, lda, a_idx, W, ldw, w_transposed, bias, bias_row_scale, ld_brs, C, ldc, M, m_dev, N, K,
                  alpha, act, row_zero, relu_gate, ld_gate, accumulate};
@@ -268,6 +269,16 @@ PFO_API int pfo_linear_f32(const float* A, int64_t lda, const int32_t* a_idx,
     if (N <= 64) return launch_linear<4>(a, s);
     if (N <= 128) return launch_linear<8>(a, s);
     return launch_linear<12>(a, s);      // BN = 192; wider N loops over grid.y
+}
+
+PFO_API int pfo_linear_f32(const float* A, int64_t lda, const int32_t* a_idx,
+                           const float* W, int64_t ldw, int w_transposed,
+                           const float* bias, const float* bias_row_scale, int64_t ld_brs,
+                           float* C, int64_t ldc, int64_t M, const int32_t* m_dev, int N, int K,
+                           float alpha, int act, const int32_t* row_zero,
+                           const float* relu_gate, int64_t ld_gate, int accumulate, void* stream) {
+    return pfo_linear_f32_impl(A, lda, a_idx, W, ldw, w_transposed, bias, bias_row_scale, ld_brs, C, ldc, M, m_dev,
+                               N, K, alpha, act, row_zero, relu_gate, ld_gate, accumulate, stream);
 }
 
 PFO_API int64_t pfo_wgrad_workspace_floats(int64_t M, int N, int K, int with_bias) {
@@ -280,9 +291,10 @@ PFO_API int64_t pfo_wgrad_workspace_floats(int64_t M, int N, int K, int with_bia
     return S * N * Kaug;
 }
 
-PFO_API int pfo_wgrad_f32(const float* G, int64_t ldg, const float* A, int64_t lda, const int32_t* a_idx,
-                          int64_t M, const int32_t* m_dev, int N, int K,
-                          float* dW, int64_t lddw, float* db, int accumulate, float* workspace, void* stream) {
+// also the landing path of pfo_wgrad_tf32 for operand layouts TMA cannot describe (wgrad_tma.cu)
+int pfo_wgrad_f32_impl(const float* G, int64_t ldg, const float* A, int64_t lda, const int32_t* a_idx,
+                       int64_t M, const int32_t* m_dev, int N, int K,
+                       float* dW, int64_t lddw, float* db, int accumulate, float* workspace, void* stream) {
     if (N <= 0 || K <= 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     const int Kaug = K + (db ? 1 : 0);
@@ -296,4 +308,10 @@ PFO_API int pfo_wgrad_f32(const float* G, int64_t ldg, const float* A, int64_t l
     const int total = N * Kaug;
     wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(workspace, (int)S, N, K, Kaug, dW, lddw, db, accumulate);
     PFO_LAUNCH_CHECK();
+}
+
+PFO_API int pfo_wgrad_f32(const float* G, int64_t ldg, const float* A, int64_t lda, const int32_t* a_idx,
+                          int64_t M, const int32_t* m_dev, int N, int K,
+                          float* dW, int64_t lddw, float* db, int accumulate, float* workspace, void* stream) {
+    return pfo_wgrad_f32_impl(G, ldg, A, lda, a_idx, M, m_dev, N, K, dW, lddw, db, accumulate, workspace, stream);
 }

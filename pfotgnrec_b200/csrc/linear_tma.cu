@@ -1,0 +1,470 @@
+// TMA-fed tcgen05 / TMEM path of the tall-skinny contractions (forward and dgrad).
+//
+// Same contract as pfo_linear_f32 (linear_simt.cu):
+//     C[m, :N] = epi(alpha * (A[m, :K] . W^T + bias * brs[m]))
+// for the GRU/RNN cell (reference modules/memory_updater.py:31,47), the attention projections
+// (model/temporal_attention.py:70) and the merge MLP (utils/utils.py:14-17): M = unique nodes or
+// queries (10^4..10^7 rows), N, K <= 320.  The activations live in HBM as fp32, so the tensor
+// cores run kind::tf32 straight on what TMA delivers -- no conversion pass:
+//
+//   warp 0     TMA producer: one 128-row x 32-column fp32 box (16 KiB, SWIZZLE_128B) per K chunk
+//              into a ring of shared-memory stages (mbarrier full/empty handshake)
+//   warp 1     MMA issuer: one elected lane issues tcgen05.mma (M=128, N=NT, K=8 per instruction),
+//              accumulating in TMEM; tcgen05.commit releases the stage / publishes the accumulator
+//   warps 2-5  epilogue: tcgen05.ld of their 32 TMEM lanes, transposed through shared memory so
+//              that bias / relu / gate / row-mask / accumulate and the stores are coalesced
+//   warps 6-9  (3-pass mode only) operand splitters, see below
+//
+// passes = 1: plain TF32 (10-bit mantissa), the "fast" mode (2e-2 contract, in practice ~1e-3).
+// passes = 3: error-compensated 3xTF32 for the 1e-5 contract: a = a_hi + a_lo with a_hi =
+//   rna_tf32(a); D = A_hi.W_hi + A_lo.W_hi + A_hi.W_lo; the dropped terms are ~2^-22 relative.
+//   The splitter warps rewrite each landed stage in place (hi) and into a twin stage (lo).
+// The weight slice W[n0:n0+NT, :K] is staged once per CTA (canonical no-swizzle K-major core
+// matrices, split hi/lo in 3-pass mode) and stays resident while the CTA walks its row tiles;
+// two TMEM accumulators let the epilogue of tile i overlap the MMAs of tile i+1.
+#include "common.cuh"
+#include <cuda.h>
+
+int pfo_linear_f32_impl(const float* A, int64_t lda, const int32_t* a_idx, const float* W, int64_t ldw,
+                        int w_transposed, const float* bias, const float* bias_row_scale, int64_t ld_brs,
+                        float* C, int64_t ldc, int64_t M, const int32_t* m_dev, int N, int K,
+                        float alpha, int act, const int32_t* row_zero, const float* relu_gate, int64_t ld_gate,
+                        int accumulate, void* stream);
+
+namespace {
+
+constexpr int TM = 128;                      // rows per tile = UMMA_M (cta_group::1)
+constexpr int CK = 32;                       // fp32 columns per K chunk = one 128-byte swizzle row
+constexpr int CHUNK_BYTES = TM * CK * 4;     // 16 KiB
+constexpr int MAX_STAGES = 8;
+constexpr int EPI_LD = 36;                   // padded row of the per-warp transposition buffer
+constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
+constexpr int SMEM_LIMIT = 232448;           // 227 KiB opt-in maximum per CTA
+
+struct TmaLinArgs {
+    const float* W; int64_t ldw; int w_transposed;
+    const float* bias; const float* bias_row_scale; int64_t ld_brs;
+    float* C; int64_t ldc;
+    int64_t M; const int32_t* m_dev; int N; int K;
+    float alpha; int act; const int32_t* row_zero; const float* relu_gate; int64_t ld_gate; int accumulate;
+    int NT;            // output columns per CTA (multiple of 16, <= 256)
+    int KP8;           // K rounded up to the MMA K step (8)
+    int n_chunks;      // ceil(K / 32)
+    int stages;
+    int tmem_cols;     // allocated TMEM columns (power of two >= 2 * NT)
+    int vec_ok;        // C / relu_gate rows are 16-byte aligned
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        :: "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+        :: "r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+// K-major operand in the 128-byte-swizzled layout TMA writes (8-row x 128 B atoms, SBO = 1024 B)
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// K-major operand in the canonical no-swizzle layout: 8-row x 16-byte core matrices,
+// LBO = distance between core matrices along K, SBO = along M/N
+__device__ __forceinline__ uint64_t desc_nosw(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ float rna_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
+template <int PASSES>
+__global__ void __launch_bounds__(PASSES == 3 ? 320 : 192, 1)
+linear_tma_kernel(const __grid_constant__ CUtensorMap tmA, const TmaLinArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NT = p.NT, KP8 = p.KP8, stages = p.stages, n_chunks = p.n_chunks;
+    const int n0 = blockIdx.y * NT;
+
+    // ---- carve shared memory (stages need 1024-byte alignment for the 128-byte swizzle)
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
+    uint8_t* base = smem_raw + pad;
+    uint8_t* sA = base;                                            // [stages][16 KiB]  A (hi)
+    uint8_t* sAlo = sA + (size_t)stages * CHUNK_BYTES;             // [stages][16 KiB]  A lo (3-pass)
+    uint8_t* sW = sAlo + (PASSES == 3 ? (size_t)stages * CHUNK_BYTES : 0);
+    const uint32_t w_bytes = (uint32_t)NT * KP8 * 4;               // [KP8/4][NT/8][8 rows][16 B]
+    uint8_t* sWlo = sW + w_bytes;
+    float* sEpi = reinterpret_cast<float*>(sWlo + (PASSES == 3 ? w_bytes : 0));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sEpi) + EPI_BYTES);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto ready_bar = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (2 * MAX_STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (3 * MAX_STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * MAX_STAGES + 2 + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4);
+
+    int64_t M = p.M;
+    if (p.m_dev) { int64_t md = *p.m_dev; M = md < M ? md : M; }
+    const int64_t n_tiles = (M + TM - 1) / TM;
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(ready_bar(s), 4);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // ---- stage the weight slice once: rna(w) (and the residual) into core-matrix order
+    {
+        const int kcs = KP8 >> 2;                                  // 16-byte units along K
+        const int units = NT * kcs;
+        for (int i = tid; i < units; i += blockDim.x) {
+            int n, kc;
+            if (p.w_transposed) { n = i % NT; kc = i / NT; } else { kc = i % kcs; n = i / kcs; }
+            float hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = kc * 4 + j, ng = n0 + n;
+                float w = 0.0f;
+                if (ng < p.N && k < p.K)
+                    w = p.w_transposed ? __ldg(p.W + (int64_t)k * p.ldw + ng) : __ldg(p.W + (int64_t)ng * p.ldw + k);
+                hi[j] = rna_tf32(w);
+                lo[j] = w - hi[j];
+            }
+            const size_t off = (size_t)kc * (NT * 16) + (size_t)(n >> 3) * 128 + (size_t)(n & 7) * 16;
+            *reinterpret_cast<float4*>(sW + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            if (PASSES == 3) *reinterpret_cast<float4*>(sWlo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t acc_stride = (uint32_t)p.tmem_cols >> 1;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int c = 0; c < n_chunks; ++c) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    mbar_arrive_expect_tx(full_bar(stage), CHUNK_BYTES);
+                    tma_load_2d(smem_u32(sA + (size_t)stage * CHUNK_BYTES), &tmA, c * CK, (int)(tile * TM), full_bar(stage));
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // D = f32, A = B = tf32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            const uint32_t a_base = smem_u32(sA), alo_base = smem_u32(sAlo);
+            const uint32_t w_base = smem_u32(sW), wlo_base = smem_u32(sWlo);
+            const uint32_t w_lbo = (uint32_t)NT * 16u;
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_stride;
+                for (int c = 0; c < n_chunks; ++c) {
+                    mbar_wait(PASSES == 3 ? ready_bar(stage) : full_bar(stage), phase);
+                    tc_fence_after();
+                    int ksteps = (KP8 - c * CK) >> 3;
+                    if (ksteps > 4) ksteps = 4;
+                    for (int s = 0; s < ksteps; ++s) {
+                        const uint32_t koff = (uint32_t)(c * 4 + s) * 2u * w_lbo;
+                        const uint64_t da = desc_sw128(a_base + (uint32_t)stage * CHUNK_BYTES + (uint32_t)s * 32u);
+                        const uint64_t dw = desc_nosw(w_base + koff, w_lbo, 128u);
+                        if (PASSES == 3) {
+                            const uint64_t dalo = desc_sw128(alo_base + (uint32_t)stage * CHUNK_BYTES + (uint32_t)s * 32u);
+                            const uint64_t dwlo = desc_nosw(wlo_base + koff, w_lbo, 128u);
+                            tc_mma_tf32(d_tmem, dalo, dw, idesc, (c | s) ? 1u : 0u);   // small terms first
+                            tc_mma_tf32(d_tmem, da, dwlo, idesc, 1u);
+                            tc_mma_tf32(d_tmem, da, dw, idesc, 1u);
+                        } else {
+                            tc_mma_tf32(d_tmem, da, dw, idesc, (c | s) ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(empty_bar(stage));                   // stage free once these MMAs retire
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
+                }
+                tc_commit(tfull_bar(acc));                         // accumulator complete
+                acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+        __syncwarp();
+    } else if (warp < 6) {
+        // ===== epilogue: warp owns TMEM lanes [32q, 32q+32) = rows of the tile
+        const int q = warp & 3;
+        float* buf = sEpi + (size_t)(warp - 2) * 32 * EPI_LD;
+        const int r_sub = lane >> 3, c4 = (lane & 7) * 4;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            for (int c0 = 0; c0 < NT; c0 += 32) {
+                const int ncols = (NT - c0) < 32 ? (NT - c0) : 32;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_stride + (uint32_t)c0;
+                uint32_t r[32];
+                tmem_ld16(taddr, r);
+                if (ncols > 16) tmem_ld16(taddr + 16u, r + 16);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (j * 4 < ncols)
+                        *reinterpret_cast<float4*>(buf + lane * EPI_LD + j * 4) =
+                            make_float4(__uint_as_float(r[j * 4]), __uint_as_float(r[j * 4 + 1]),
+                                        __uint_as_float(r[j * 4 + 2]), __uint_as_float(r[j * 4 + 3]));
+                }
+                __syncwarp();
+                // transposed read: 8 lanes cover 32 consecutive columns of one row, 4 rows per pass
+                if (c4 < ncols) {
+                    const int nb = n0 + c0 + c4;
+                    float bv[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (p.bias) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) if (nb + e < p.N) bv[e] = __ldg(p.bias + nb + e);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = i * 4 + r_sub;
+                        const int64_t m = tile * TM + q * 32 + row;
+                        if (m >= M) continue;
+                        const float4 a4 = *reinterpret_cast<const float4*>(buf + row * EPI_LD + c4);
+                        float v[4] = {a4.x, a4.y, a4.z, a4.w};
+                        const bool zero_row = p.row_zero && p.row_zero[m] != 0;
+                        const float brs = p.bias_row_scale ? p.bias_row_scale[m * p.ld_brs] : 1.0f;
+                        float* dst = p.C + m * p.ldc + nb;
+                        const bool full4 = p.vec_ok && (nb + 3 < p.N);
+                        float g[4] = {1.f, 1.f, 1.f, 1.f}, old[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (p.relu_gate) {
+                            const float* gp = p.relu_gate + m * p.ld_gate + nb;
+                            if (full4) { const float4 t = *reinterpret_cast<const float4*>(gp); g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w; }
+                            else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) if (nb + e < p.N) g[e] = gp[e];
+                            }
+                        }
+                        if (p.accumulate) {
+                            if (full4) { const float4 t = *reinterpret_cast<const float4*>(dst); old[0] = t.x; old[1] = t.y; old[2] = t.z; old[3] = t.w; }
+                            else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) if (nb + e < p.N) old[e] = dst[e];
+                            }
+                        }
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float x = v[e];
+                            if (p.bias) x += bv[e] * brs;
+                            x *= p.alpha;
+                            if (p.act == 1) x = fmaxf(x, 0.0f);
+                            if (p.relu_gate && g[e] <= 0.0f) x = 0.0f;
+                            if (zero_row) x = 0.0f;
+                            v[e] = x + old[e];
+                        }
+                        if (full4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                        else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) if (nb + e < p.N) dst[e] = v[e];
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));           // TMEM accumulator drained
+            acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+        }
+    } else if (PASSES == 3) {
+        // ===== operand splitters: hi = rna_tf32(a) in place, lo = a - hi into the twin stage
+        const int t = tid - 192;
+        int stage = 0; uint32_t phase = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int c = 0; c < n_chunks; ++c) {
+                mbar_wait(full_bar(stage), phase);
+                float4* hi = reinterpret_cast<float4*>(sA + (size_t)stage * CHUNK_BYTES);
+                float4* lo = reinterpret_cast<float4*>(sAlo + (size_t)stage * CHUNK_BYTES);
+#pragma unroll
+                for (int j = 0; j < CHUNK_BYTES / 16 / 128; ++j) {
+                    const int idx = t + 128 * j;
+                    const float4 v = hi[idx];
+                    float4 h, l;
+                    h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+                    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+                    hi[idx] = h;
+                    lo[idx] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ready_bar(stage));
+                if (++stage == stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    }
+    // ---- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                     :: "r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+template <int PASSES>
+int launch_tma(const CUtensorMap& map, const TmaLinArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(linear_tma_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    linear_tma_kernel<PASSES><<<grid, PASSES == 3 ? 320 : 192, smem, s>>>(map, a);
+    PFO_LAUNCH_CHECK();
+}
+
+}  // namespace
+
+// Builds the 2-D tensor map of a row-major fp32 matrix [rows, cols] (row stride ld floats) with
+// 32-column x box_rows boxes and the 128-byte swizzle (atom32: 32-byte swizzle atoms, the form the tensor
+// core needs for MN-major tf32 operands).  Shared with wgrad_tma.cu.
+int pfo_make_tensor_map_f32(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                            int atom32) {
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return (int)cudaErrorNotSupported;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4u};
+    cuuint32_t box[2] = {(cuuint32_t)CK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+PFO_API int pfo_linear_tf32(const float* A, int64_t lda, const int32_t* a_idx, const float* W, int64_t ldw,
+                            int w_transposed, const float* bias, const float* bias_row_scale, int64_t ld_brs,
+                            float* C, int64_t ldc, int64_t M, const int32_t* m_dev, int N, int K,
+                            float alpha, int act, const int32_t* row_zero, const float* relu_gate, int64_t ld_gate,
+                            int accumulate, int passes, void* stream) {
+    if (M <= 0 || N <= 0) return 0;
+    if (passes != 1 && passes != 3) return (int)cudaErrorInvalidValue;
+    // layouts TMA cannot describe (gathered rows, rows that are not 16-byte aligned) take the FFMA kernel
+    const bool tma_ok = a_idx == nullptr && K >= 1 && (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
+                        get_encode_tiled() != nullptr;
+    if (!tma_ok)
+        return pfo_linear_f32_impl(A, lda, a_idx, W, ldw, w_transposed, bias, bias_row_scale, ld_brs, C, ldc, M, m_dev,
+                                   N, K, alpha, act, row_zero, relu_gate, ld_gate, accumulate, stream);
+    TmaLinArgs a{};
+    a.W = W; a.ldw = ldw; a.w_transposed = w_transposed; a.bias = bias; a.bias_row_scale = bias_row_scale;
+    a.ld_brs = ld_brs; a.C = C; a.ldc = ldc; a.M = M; a.m_dev = m_dev; a.N = N; a.K = K; a.alpha = alpha; a.act = act;
+    a.row_zero = row_zero; a.relu_gate = relu_gate; a.ld_gate = ld_gate; a.accumulate = accumulate;
+    a.KP8 = (K + 7) / 8 * 8;
+    a.n_chunks = (K + CK - 1) / CK;
+    a.vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
+               (!relu_gate || ((ld_gate % 4 == 0) && ((reinterpret_cast<uintptr_t>(relu_gate) & 15) == 0)));
+    const int mult = passes == 3 ? 2 : 1;
+    const int stage_bytes = CHUNK_BYTES * mult;
+    const int fixed = EPI_BYTES + 8 * (3 * MAX_STAGES + 4) + 16 + 1024;   // epilogue buffers, barriers, alignment slack
+    const int budget = SMEM_LIMIT - fixed;
+    int n_ntiles = (N + 255) / 256;
+    int NT;
+    for (;;) {
+        NT = ((N + n_ntiles - 1) / n_ntiles + 15) / 16 * 16;
+        if ((int64_t)NT * a.KP8 * 4 * mult + 2 * stage_bytes <= budget) break;
+        if (NT <= 16) return (int)cudaErrorInvalidValue;
+        ++n_ntiles;
+    }
+    a.NT = NT;
+    const int w_bytes = NT * a.KP8 * 4 * mult;
+    int stages = (budget - w_bytes) / stage_bytes;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    a.stages = stages;
+    int cols = 32;
+    while (cols < 2 * NT) cols <<= 1;
+    a.tmem_cols = cols;
+    CUtensorMap map;
+    int rc = pfo_make_tensor_map_f32(&map, A, M, K, lda, TM, 0);
+    if (rc) return rc;
+    const size_t smem = (size_t)stages * stage_bytes + w_bytes + fixed;
+    const int64_t m_tiles = (M + TM - 1) / TM;
+    int gx = pfo_num_sms() / n_ntiles;
+    if (gx < 1) gx = 1;
+    if (gx > m_tiles) gx = (int)m_tiles;
+    dim3 grid((unsigned)gx, (unsigned)n_ntiles);
+    cudaStream_t s = (cudaStream_t)stream;
+    return passes == 3 ? launch_tma<3>(map, a, grid, smem, s) : launch_tma<1>(map, a, grid, smem, s);
+}

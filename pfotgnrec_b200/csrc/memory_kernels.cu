@@ -95,7 +95,7 @@ cell_backward_kernel(const int32_t* __restrict__ uniq, const int32_t* __restrict
 }
 
 // snapshot of the state rows of the unique touched nodes, taken before persist / store overwrite them:
-// HG = memory rows, XG = pending raw messages, valid_u, lu_u = last_update' (message time if pending)
+// HG = memory rows, XG = pending raw messages (row stride rawp), valid_u, lu_u = last_update' (message time if pending)
 __global__ void __launch_bounds__(256)
 gather_state_kernel(const int32_t* __restrict__ uniq, const int32_t* __restrict__ n_uniq, int64_t u_max, int d, int raw,
                     const float* __restrict__ memory, const float* __restrict__ pend_msg, int64_t rawp,
@@ -113,7 +113,8 @@ gather_state_kernel(const int32_t* __restrict__ uniq, const int32_t* __restrict_
         for (int c = lane; c < d; c += 32) HG[u * d + c] = m[c];
         if (XG) {
             const float* x = pend_msg + (int64_t)node * rawp;
-            for (int c = lane; c < raw; c += 32) XG[u * raw + c] = v ? x[c] : 0.0f;
+            // XG rows keep the 16-byte-aligned stride of the table (rawp) so that TMA can stream them
+            for (int c = lane; c < rawp; c += 32) XG[u * rawp + c] = (v && c < raw) ? x[c] : 0.0f;
         }
         if (lane == 0) {
             valid_u[u] = v ? 1 : 0;

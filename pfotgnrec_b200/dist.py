@@ -177,7 +177,7 @@ class ShardedEngine(TGNEngine):
         n_own = st.n_unique.clone()
         Gd = c.gates * d
         HG = torch.empty(u_own, d, device=dev)
-        XG = torch.empty(u_own, c.raw, device=dev)
+        XG = torch.empty(u_own, c.rawp, device=dev)
         valid_u = torch.empty(u_own, dtype=torch.uint8, device=dev)
         lu_own = torch.zeros(u_own, device=dev)
         _lib.call("pfo_gather_state", ptr(uo), ptr(n_own), u_own, d, c.raw, ptr(st.memory), ptr(st.pend_msg),
@@ -186,7 +186,7 @@ class ShardedEngine(TGNEngine):
         W_ih, W_hh, b_ih, b_hh = cellW
         GI = torch.empty(u_own, Gd, device=dev)
         GH = torch.empty(u_own, Gd, device=dev)
-        _linear(c, ptr(XG), c.raw, None, ptr(W_ih), c.raw, 0, ptr(b_ih), ptr(GI), Gd, u_own, Gd, c.raw, m_dev=ptr(n_own))
+        _linear(c, ptr(XG), c.rawp, None, ptr(W_ih), c.raw, 0, ptr(b_ih), ptr(GI), Gd, u_own, Gd, c.raw, m_dev=ptr(n_own))
         _linear(c, ptr(HG), d, None, ptr(W_hh), d, 0, ptr(b_hh), ptr(GH), Gd, u_own, Gd, d, m_dev=ptr(n_own))
         Hnew_own = torch.zeros(u_own, d, device=dev)
         scratch = torch.empty(u_own, d, device=dev)         # H0 is formed on the requester

@@ -35,7 +35,7 @@ class ModelConfig:
     dst_emb_in_msg: bool = False
     shift: tuple = (0.0, 1.0, 0.0, 1.0)  # mean/std time shift src, dst
     dropout: float = 0.0
-    gemm_mode: str = "fp32"     # "fp32" (FFMA, 1e-5 contract) | "bf16" (tcgen05, 2e-2 contract)
+    gemm_mode: str = "fp32"     # "fp32" (3xTF32 tcgen05, 1e-5) | "tf32" (tcgen05, 2e-2) | "bf16" | "simt" (FFMA)
 
     @property
     def E(self):                # attention embed dim = d + time dim
@@ -106,9 +106,19 @@ class TGNState:
             dst.copy_(src)
 
 
+_LINEAR_PASSES = {"fp32": 3, "tf32": 1}
+
+
 def _linear(cfg, A, lda, a_idx, W, ldw, wt, bias, C, ldc, M, N, K, *, m_dev=None, alpha=1.0, act=0,
             row_zero=None, relu_gate=None, ld_gate=0, accumulate=0, brs=None, ld_brs=0):
-    name = "pfo_linear_f32" if cfg.gemm_mode == "fp32" else "pfo_linear_bf16"
+    """C = epi(alpha * (A W^T + bias)).  gemm_mode: "fp32" = 3xTF32 on tcgen05 (1e-5 contract),
+    "tf32" = single-pass TF32 on tcgen05, "bf16" = bf16 tcgen05, "simt" = FFMA."""
+    mode = cfg.gemm_mode
+    if mode in _LINEAR_PASSES:
+        _lib.call("pfo_linear_tf32", A, lda, a_idx, W, ldw, int(wt), bias, brs, ld_brs, C, ldc, M, m_dev, N, K,
+                  float(alpha), int(act), row_zero, relu_gate, ld_gate, int(accumulate), _LINEAR_PASSES[mode])
+        return
+    name = "pfo_linear_f32" if mode == "simt" else "pfo_linear_bf16"
     _lib.call(name, A, lda, a_idx, W, ldw, int(wt), bias, brs, ld_brs, C, ldc, M, m_dev, N, K,
               float(alpha), int(act), row_zero, relu_gate, ld_gate, int(accumulate))
 
@@ -126,9 +136,15 @@ class _Workspace:
         return self.buf
 
 
-def _wgrad(ws, G, ldg, A, lda, a_idx, M, N, K, dW, lddw, db, *, m_dev=None, accumulate=0):
-    need = _lib.query("pfo_wgrad_workspace_floats", M, N, K, 1 if db is not None else 0)
-    buf = ws.get(need)
+def _wgrad(cfg, ws, G, ldg, A, lda, a_idx, M, N, K, dW, lddw, db, *, m_dev=None, accumulate=0):
+    """dW = G^T A (+ db): tcgen05 in the "fp32" (3xTF32) / "tf32" modes, FFMA otherwise."""
+    wb = 1 if db is not None else 0
+    if cfg.gemm_mode in _LINEAR_PASSES:
+        buf = ws.get(_lib.query("pfo_wgrad_tf32_workspace_floats", M, N, K, wb))
+        _lib.call("pfo_wgrad_tf32", G, ldg, A, lda, a_idx, M, m_dev, N, K, dW, lddw, db, int(accumulate), ptr(buf),
+                  _LINEAR_PASSES[cfg.gemm_mode])
+        return
+    buf = ws.get(_lib.query("pfo_wgrad_workspace_floats", M, N, K, wb))
     _lib.call("pfo_wgrad_f32", G, ldg, A, lda, a_idx, M, m_dev, N, K, dW, lddw, db, int(accumulate), ptr(buf))
 
 
@@ -277,7 +293,7 @@ class TGNEngine:
         Hnew = HG = XG = valid_u = lu_u = GI = GH = None
         if c.use_memory:
             HG = torch.empty(u_max, d, device=dev)
-            XG = torch.empty(u_max, c.raw, device=dev)
+            XG = torch.empty(u_max, c.rawp, device=dev)
             valid_u = torch.empty(u_max, dtype=torch.uint8, device=dev)
             lu_u = torch.empty(u_max, device=dev)
             _lib.call("pfo_gather_state", ptr(uniq), ptr(n_uniq), u_max, d, c.raw, ptr(st.memory), ptr(st.pend_msg),
@@ -286,7 +302,7 @@ class TGNEngine:
             W_ih, W_hh, b_ih, b_hh = cellW
             GI = torch.empty(u_max, G, device=dev)
             GH = torch.empty(u_max, G, device=dev)
-            _linear(c, ptr(XG), c.raw, None, ptr(W_ih), c.raw, 0, ptr(b_ih), ptr(GI), G, u_max, G, c.raw, m_dev=ptr(n_uniq))
+            _linear(c, ptr(XG), c.rawp, None, ptr(W_ih), c.raw, 0, ptr(b_ih), ptr(GI), G, u_max, G, c.raw, m_dev=ptr(n_uniq))
             _linear(c, ptr(HG), d, None, ptr(W_hh), d, 0, ptr(b_hh), ptr(GH), G, u_max, G, d, m_dev=ptr(n_uniq))
             Hnew = torch.empty(u_max, d, device=dev)
         _lib.call("pfo_cell_forward", ptr(uniq), ptr(n_uniq), u_max, d, c.cell, ptr(GI), ptr(GH), G, ptr(HG),
@@ -304,9 +320,9 @@ class TGNEngine:
         _lib.call("pfo_cell_backward", ptr(tab["uniq"]), ptr(n_uniq), u_max, d, c.cell, ptr(tab["GI"]), ptr(tab["GH"]),
                   G, ptr(tab["HG"]), ptr(tab["valid_u"]), ptr(dH0), ptr(dGI), ptr(dGH))
         gW_ih, gW_hh, gb_ih, gb_hh = g_cell
-        _wgrad(self.ws, ptr(dGI), G, ptr(tab["XG"]), c.raw, None, u_max, G, c.raw, ptr(gW_ih), c.raw, ptr(gb_ih),
+        _wgrad(c, self.ws, ptr(dGI), G, ptr(tab["XG"]), c.rawp, None, u_max, G, c.raw, ptr(gW_ih), c.raw, ptr(gb_ih),
                m_dev=ptr(n_uniq))
-        _wgrad(self.ws, ptr(dGH), G, ptr(tab["HG"]), d, None, u_max, G, d, ptr(gW_hh), d, ptr(gb_hh),
+        _wgrad(c, self.ws, ptr(dGH), G, ptr(tab["HG"]), d, None, u_max, G, d, ptr(gW_hh), d, ptr(gb_hh),
                m_dev=ptr(n_uniq))
 
     def persist_and_store(self, tab, batch, emb, tw, tb):
@@ -400,20 +416,20 @@ class TGNEngine:
         # merge MLP
         dH1 = torch.empty(M, d, device=dev)
         _linear(f32, ptr(dOUT), d, None, ptr(W2), d, 1, None, ptr(dH1), d, M, d, d, relu_gate=ptr(tp.H1), ld_gate=d)
-        _wgrad(ws, ptr(dOUT), d, ptr(tp.H1), d, None, M, d, d, ptr(gW2), d, ptr(gb2), accumulate=1)
+        _wgrad(c, ws, ptr(dOUT), d, ptr(tp.H1), d, None, M, d, d, ptr(gW2), d, ptr(gb2), accumulate=1)
         dCAT = torch.empty(M, ldc, device=dev)
         _linear(f32, ptr(dH1), d, None, ptr(W1), ldc, 1, None, ptr(dCAT), ldc, M, ldc, d)
-        _wgrad(ws, ptr(dH1), d, ptr(tp.CAT), ldc, None, M, d, ldc, ptr(gW1), ldc, ptr(gb1), accumulate=1)
+        _wgrad(c, ws, ptr(dH1), d, ptr(tp.CAT), ldc, None, M, d, ldc, ptr(gW1), ldc, ptr(gb1), accumulate=1)
         # rows without neighbours had their attention output zeroed (temporal_attention.py:84)
         dCAT[:, :E].masked_fill_((tp.invalid != 0).unsqueeze(1), 0.0)
-        _wgrad(ws, ptr(dCAT), ldc, ptr(tp.ATT), E, None, M, E, E, ptr(gWo), E, ptr(gbo), accumulate=1)
+        _wgrad(c, ws, ptr(dCAT), ldc, ptr(tp.ATT), E, None, M, E, E, ptr(gWo), E, ptr(gbo), accumulate=1)
         dATT = torch.empty(M, E, device=dev)
         _linear(f32, ptr(dCAT), ldc, None, ptr(Wo), E, 1, None, ptr(dATT), E, M, E, E)
         dXB = torch.empty(M, H, ekp, device=dev)
         for h in range(H):
             _linear(f32, dATT.data_ptr() + h * hd * F4, E, None, WvA.data_ptr() + h * hd * ekp * F4, ekp, 1, None,
                     dXB.data_ptr() + h * ekp * F4, H * ekp, M, Ek + 1, hd)
-            _wgrad(ws, dATT.data_ptr() + h * hd * F4, E, tp.XB.data_ptr() + h * ekp * F4, H * ekp, None, M, hd, Ek + 1,
+            _wgrad(c, ws, dATT.data_ptr() + h * hd * F4, E, tp.XB.data_ptr() + h * ekp * F4, H * ekp, None, M, hd, Ek + 1,
                    gWvA.data_ptr() + h * hd * ekp * F4, ekp, None, accumulate=1)
         dQK = torch.empty(M, H, ekp, device=dev)
         nws = ws.get(_lib.query("pfo_attn_nbr_bwd_workspace_floats", d))
@@ -426,12 +442,12 @@ class TGNEngine:
         for h in range(H):
             _linear(f32, dQK.data_ptr() + h * ekp * F4, H * ekp, None, Wk.data_ptr() + h * hd * Ek * F4, Ek, 0, None,
                     dQP.data_ptr() + h * hd * F4, E, M, hd, Ek)
-            _wgrad(ws, tp.QP.data_ptr() + h * hd * F4, E, dQK.data_ptr() + h * ekp * F4, H * ekp, None, M, hd, Ek,
+            _wgrad(c, ws, tp.QP.data_ptr() + h * hd * F4, E, dQK.data_ptr() + h * ekp * F4, H * ekp, None, M, hd, Ek,
                    gWk.data_ptr() + h * hd * Ek * F4, Ek, None, accumulate=1)
         # q = scale * (Wq[:, :d] h_q + cq)
         tmpW = torch.zeros(E, d, device=dev)
         tmpb = torch.zeros(E, device=dev)
-        _wgrad(ws, ptr(dQP), E, tp.CAT.data_ptr() + E * F4, ldc, None, M, E, d, ptr(tmpW), d, ptr(tmpb))
+        _wgrad(c, ws, ptr(dQP), E, tp.CAT.data_ptr() + E * F4, ldc, None, M, E, d, ptr(tmpW), d, ptr(tmpb))
         gWq[:, :d].add_(tmpW, alpha=scale)
         gcq.add_(tmpb, alpha=scale)
         _linear(f32, ptr(dQP), E, None, ptr(Wq), E, 1, None, dCAT.data_ptr() + E * F4, ldc, M, d, E,

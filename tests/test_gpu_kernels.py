@@ -299,3 +299,79 @@ def test_linear_bf16_tcgen05(M, N, K, wt):
     assert rel_err(got, ref.numpy()) < 1e-5
     assert rel_err(got, full.numpy()) < 2e-2           # the bf16 contract of BASELINE.json
     assert (C[:, N:] == 7.0).all()
+
+
+# ------------------------------------------------------------------------------ TMA + tcgen05 (tf32 / 3xtf32) path
+def _tf32_trunc(x):
+    return (x.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 192, 193), (257, 64, 64), (4096, 129, 64), (33, 130, 32), (5000, 64, 192),
+                                   (300, 128, 128), (70000, 192, 64), (1, 16, 1), (129, 256, 320), (40000, 64, 130)])
+@pytest.mark.parametrize("wt", [0, 1])
+@pytest.mark.parametrize("passes", [3, 1])
+def test_linear_tf32_tma(M, N, K, wt, passes):
+    from pfotgnrec_b200 import _lib
+    from pfotgnrec_b200._lib import ptr
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    lda = (K + 3) // 4 * 4 + 4                      # strided rows, 16-byte aligned: the TMA path
+    A = torch.randn(M + 50, lda, generator=g)
+    W = torch.randn(N, K, generator=g)
+    b = torch.randn(N, generator=g)
+    rz = (torch.rand(M, generator=g) < 0.1).to(torch.int32)
+    brs = torch.rand(M, generator=g)
+    full = (A[:M, :K].double() @ W.double().t() + b.double() * brs.double().unsqueeze(1)) * 0.5
+    full = torch.relu(full)
+    full[rz != 0] = 0
+    Ad, Wd, bd, rzd, brsd = (t.to(DEV) for t in (A, W.t().contiguous() if wt else W, b, rz, brs))
+    C = torch.full((M, N + 4), 7.0, device=DEV)
+    _lib.call("pfo_linear_tf32", ptr(Ad), lda, None, ptr(Wd), N if wt else K, wt, ptr(bd), ptr(brsd), 1,
+              ptr(C), N + 4, M, None, N, K, 0.5, 1, ptr(rzd), None, 0, 0, passes)
+    got = C[:, :N].cpu().numpy()
+    assert rel_err(got, full.numpy()) < (1e-5 if passes == 3 else 2e-3)
+    assert (C[:, N:] == 7.0).all()
+    # accumulate + relu gate + device-side row count, unaligned output stride (scalar store path)
+    live = max(M - 5, 1)
+    md = torch.tensor([live], dtype=torch.int32, device=DEV)
+    gate = torch.randn(M, N + 1, generator=g)
+    C2 = torch.ones(M, N + 1, device=DEV)
+    _lib.call("pfo_linear_tf32", ptr(Ad), lda, None, ptr(Wd), N if wt else K, wt, None, None, 0,
+              ptr(C2), N + 1, M, ptr(md), N, K, 1.0, 0, None, ptr(gate.to(DEV)), N + 1, 1, passes)
+    ref2 = A[:M, :K].double() @ W.double().t()
+    ref2[gate[:, :N] <= 0] = 0
+    ref2 = ref2 + 1.0
+    assert rel_err(C2[:live, :N].cpu().numpy(), ref2[:live].numpy()) < (1e-5 if passes == 3 else 2e-3)
+    assert (C2[live:] == 1.0).all() and (C2[:, N] == 1.0).all()
+
+
+@pytest.mark.parametrize("M,N,K", [(3000, 192, 193), (100, 64, 130), (70000, 64, 64), (1, 128, 129), (5000, 128, 128),
+                                   (777, 64, 192), (49152, 128, 64), (31, 192, 64)])
+@pytest.mark.parametrize("passes", [3, 1])
+def test_wgrad_tf32_tma(M, N, K, passes):
+    from pfotgnrec_b200 import _lib
+    from pfotgnrec_b200._lib import ptr
+    g = torch.Generator(device="cpu").manual_seed(M)
+    ldg, lda = N + 4, (K + 3) // 4 * 4
+    G = torch.randn(M + 40, ldg, generator=g)
+    A = torch.randn(M + 40, lda, generator=g)
+    G[M:] = float("nan")                             # rows past M must never be read into the sums
+    A[M:] = float("nan")
+    ref = G[:M, :N].double().t() @ A[:M, :K].double()
+    refb = G[:M, :N].double().sum(0)
+    tol = 2e-5 if passes == 3 else 5e-3
+    Gd, Ad = G.to(DEV), A.to(DEV)
+    dW = torch.zeros(N, K, device=DEV)
+    db = torch.zeros(N, device=DEV)
+    ws = torch.empty(_lib.query("pfo_wgrad_tf32_workspace_floats", M + 40, N, K, 1), device=DEV)
+    _lib.call("pfo_wgrad_tf32", ptr(Gd), ldg, ptr(Ad), lda, None, M, None, N, K, ptr(dW), K, ptr(db), 0, ptr(ws), passes)
+    assert rel_err(dW.cpu().numpy(), ref.numpy()) < tol
+    assert rel_err(db.cpu().numpy(), refb.numpy()) < tol
+    # accumulate, no bias, live row count on the device (capacity M + 40, rows past M hold NaN)
+    md = torch.tensor([M], dtype=torch.int32, device=DEV)
+    dW2 = dW.clone()
+    _lib.call("pfo_wgrad_tf32", ptr(Gd), ldg, ptr(Ad), lda, None, M + 40, ptr(md), N, K, ptr(dW2), K, None, 1, ptr(ws), passes)
+    assert rel_err(dW2.cpu().numpy(), 2 * ref.numpy()) < tol
+    # determinism: bit-identical on a re-run
+    dW3 = torch.zeros(N, K, device=DEV)
+    _lib.call("pfo_wgrad_tf32", ptr(Gd), ldg, ptr(Ad), lda, None, M, None, N, K, ptr(dW3), K, None, 0, ptr(ws), passes)
+    assert torch.equal(dW3, dW)

@@ -52,10 +52,13 @@ def build_tgn(tgn_mod, utils_mod, z, gemm_mode="fp32"):
 
 
 @pytest.mark.parametrize("tag", ["ours", "ours_nbg", "tgn", "jodie", "dyrep", "tgat2"])
-def test_drop_in_tgn_matches_reference_golden(overlay, tag):
+@pytest.mark.parametrize("mode", ["fp32", "simt"])
+def test_drop_in_tgn_matches_reference_golden(overlay, tag, mode):
+    """1e-5 contract in both exact GEMM modes: "fp32" = 3xTF32 on the tcgen05 tensor cores (default),
+    "simt" = FFMA."""
     tgn_mod, utils_mod = overlay
     z = load_golden(f"tgn_{tag}.npz")
-    tgn = build_tgn(tgn_mod, utils_mod, z).train()
+    tgn = build_tgn(tgn_mod, utils_mod, z, gemm_mode=mode).train()
     n = int(z["cfg_n_neighbors"])
     n_neg = int(z["cfg_n_neg"])
     names = [k for k, p in tgn.named_parameters() if p.requires_grad]
@@ -158,11 +161,13 @@ def test_larger_stream_vs_oracle(overlay):
 
 
 @pytest.mark.parametrize("tag", ["ours", "jodie"])
-def test_bf16_gemm_mode_within_2e_2(overlay, tag):
-    """gemm_mode='bf16' (tcgen05 tensor cores): 2e-2 contract of the north_star on embeddings, loss, memory."""
+@pytest.mark.parametrize("mode", ["bf16", "tf32"])
+def test_fast_gemm_modes_within_2e_2(overlay, tag, mode):
+    """gemm_mode='tf32' (single-pass TF32, TMA-fed tcgen05) and 'bf16' (tcgen05): the 2e-2 contract of the
+    north_star on embeddings, loss, memory."""
     tgn_mod, utils_mod = overlay
     z = load_golden(f"tgn_{tag}.npz")
-    tgn = build_tgn(tgn_mod, utils_mod, z, gemm_mode="bf16").train()
+    tgn = build_tgn(tgn_mod, utils_mod, z, gemm_mode=mode).train()
     n, n_neg = int(z["cfg_n_neighbors"]), int(z["cfg_n_neg"])
     from pfotgnrec_b200.trainer import bpr_loss
     for bi in range(int(z["cfg_n_batches"])):
