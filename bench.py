@@ -26,8 +26,8 @@ sys.path.insert(0, ROOT)
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ours", choices=["ours", "tgn", "jodie", "dyrep", "tgat"])
     ap.add_argument("--bs", type=int, default=8192)
@@ -35,7 +35,10 @@ def parse():
     ap.add_argument("--items", type=int, default=1000)
     ap.add_argument("--events", type=int, default=5000000)
     ap.add_argument("--days", type=int, default=200)
-    ap.add_argument("--gemm", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--gemm", default="fp32", choices=["fp32", "tf32", "bf16", "simt"],
+                    help="fp32 = 3xTF32 on tcgen05 (1e-5 contract, default); tf32 / bf16 = 2e-2 contract; simt = FFMA")
+    ap.add_argument("--dropout", type=float, default=0.1, help="attention dropout (reference main.py:29 default)")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of one CUDA graph")
     ap.add_argument("--eval-steps", type=int, default=4)
     ap.add_argument("--eval-bs", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -55,45 +58,57 @@ def make_data(a):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in a polling thread (2 ms period --
+    the timed region is tens of milliseconds, too short for `nvidia-smi -lms`), nvidia-smi as the fallback."""
+    BAD = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.sm, self.mask, self.max_mhz = index, [], 0, None
+        self._stop, self.th, self.h, self.nv = threading.Event(), None, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.th = threading.Thread(target=self._poll, daemon=True)
             self.th.start()
-        except OSError:
-            self.proc = None
+        except Exception:
+            self.nv = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def _poll(self):
+        nv, h = self.nv, self.h
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.nv is None:
+            return self._smi_once()
+        self._stop.set()
+        self.th.join(timeout=1.0)
+        reasons = sorted(k for k, bit in self.BAD.items() if self.mask & bit)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(self.sm), "source": "nvml, 2 ms polling during the timed region"}
+
+    def _smi_once(self):
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20).stdout
+            f = [float(x) for x in out.strip().split(",")]
+            return {"sm_mhz": f[0], "sm_max_mhz": f[1], "reasons": [], "samples": 1, "source": "nvidia-smi (after)"}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
 
 
 def run_reference(a):
@@ -131,14 +146,14 @@ def run_reference(a):
                       "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def algorithmic_work(name, args, n_uniq):
-    """(unit, amount) of algorithmic work of one C-ABI call (DESIGN.md section 'Kernels')."""
-    if name in ("pfo_linear_f32", "pfo_linear_bf16"):
+def algorithmic_work(name, args, n_uniq, extra):
+    """(unit, amount) of ALGORITHMIC work of one C-ABI call (DESIGN.md section 4 / SURVEY.md section 8d)."""
+    if name in ("pfo_linear_f32", "pfo_linear_bf16", "pfo_linear_tf32"):
         M, m_dev, N, K = args[11], args[12], args[13], args[14]
         if m_dev:
             M = min(M, n_uniq)
         return "flop", 2.0 * M * N * K
-    if name == "pfo_wgrad_f32":
+    if name in ("pfo_wgrad_f32", "pfo_wgrad_tf32"):
         M, m_dev, N, K = args[5], args[6], args[7], args[8]
         if m_dev:
             M = min(M, n_uniq)
@@ -151,12 +166,23 @@ def algorithmic_work(name, args, n_uniq):
         return "byte", Q * (3 * H * ekp * 4 + n * (2 * 4 * d + 4 * F + 12) + H * n * 4)
     if name == "pfo_neighbor_sample":
         Q, n = args[6], args[7]
-        return "byte", Q * (16 + 8 * 10 + 28 * n)
+        return "byte", Q * (16 + 8 * extra["log2deg"] + 28 * n)
+    if name == "pfo_mv_select":
+        n_ret, B, K = args[9], args[10], args[11]
+        return "byte", B * ((K + 1 + extra["mean_portfolio"]) * n_ret * 8 + 4 * extra["mean_portfolio"] + 16)
+    if name == "pfo_bpr":
+        B, k, d = args[3], args[4], args[5]
+        return "byte", B * (2 + k) * 4 * d * 2
+    if name == "pfo_store_messages":
+        B, d, F = args[4], args[5], args[6]
+        return "byte", 2 * B * ((2 * 4 * d + 4 * F + 12) + (4 * (3 * d + F) + 5))
     return None, 0.0
 
 
-def profile_kernels(step_fn, n_steps, n_uniq_fn):
-    """Per-entry-point device time with CUDA events on the launching stream (a separate pass)."""
+def profile_kernels(step_fn, n_steps, n_uniq_fn, extra):
+    """Per-entry-point device time with CUDA events on the launching stream, in a separate eager pass (the timed
+    region replays a CUDA graph, which has no per-kernel hooks).  A device-side sleep is queued ahead of every
+    profiled step so the host runs ahead of the GPU and the events bracket kernels, not launch gaps."""
     from pfotgnrec_b200 import _lib
     records = []
     orig = _lib.call
@@ -171,20 +197,42 @@ def profile_kernels(step_fn, n_steps, n_uniq_fn):
     _lib.call = timed_call
     try:
         for i in range(n_steps):
+            torch.cuda._sleep(40_000_000)            # ~20 ms at 1.9 GHz
             step_fn(i)
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
     finally:
         _lib.call = orig
     n_uniq = n_uniq_fn()
     agg = {}
     for name, args, e0, e1 in records:
-        unit, amt = algorithmic_work(name, args, n_uniq)
+        unit, amt = algorithmic_work(name, args, n_uniq, extra)
         a = agg.setdefault(name, {"ms": 0.0, "calls": 0, "flop": 0.0, "byte": 0.0})
         a["ms"] += e0.elapsed_time(e1)
         a["calls"] += 1
         if unit:
             a[unit] += amt
     return agg
+
+
+def roofline_of(name, v, peaks, gemm, ncu):
+    """roofline object of one entry point from its aggregated (ms, algorithmic work)."""
+    if v["ms"] <= 0:
+        return None
+    traffic = (ncu.get(name) or {}).get("dram_bytes_per_launch")
+    if v["flop"] > 0:
+        ach = v["flop"] / (v["ms"] * 1e-3) / 1e12
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        note = {"fp32": "3xTF32 on tcgen05 (3 MMAs per algorithmic MAC)", "tf32": "TF32 on tcgen05",
+                "bf16": "bf16 on tcgen05", "simt": "fp32 FFMA"}[gemm]
+        return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": traffic, "launches": v["calls"],
+                "note": note + "; peak = measured sustained dense bf16 (MEASURED_PEAKS.json)"}
+    if v["byte"] > 0:
+        ach = v["byte"] / (v["ms"] * 1e-3) / 1e9
+        peak = peaks.get("hbm_gbs", 6650.0)
+        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic, "launches": v["calls"], "note": "peak = measured copy bandwidth (MEASURED_PEAKS.json)"}
+    return None
 
 
 def main():
@@ -205,7 +253,7 @@ def main():
     from pfotgnrec_b200.trainer import PfoTrainer, TrainConfig
     _lib.load()
     st = make_data(a)
-    tc = TrainConfig(model=a.workload, bs=a.bs, gemm_mode=a.gemm)
+    tc = TrainConfig(model=a.workload, bs=a.bs, gemm_mode=a.gemm, dropout=a.dropout, cuda_graph=not a.no_graph)
     if world > 1:
         from pfotgnrec_b200.dist import ShardedTrainer
         tr = ShardedTrainer(st, tc, dev, rank, world)
@@ -272,6 +320,7 @@ def main():
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for hb in host[1:]:
+            flush.fill_(1)                           # same L2 flush as the device-timed loop (inside e2e's clock)
             l = tr.train_step_host(hb)
             _ = float(l.item())                      # device -> host read of the step's result
         torch.cuda.synchronize()
@@ -279,27 +328,35 @@ def main():
         e2e = {"value": a.steps * bs / dt, "unit": "events/s", "h2d_bytes_per_step": int(host[1]["nbytes"]),
                "d2h_bytes_per_step": 4}
 
-    # ---- per-kernel pass for the roofline of the dominant kernel
-    roofline, kernels = None, None
+    # ---- per-kernel pass (eager launches, CUDA events per C-ABI call) for the rooflines
+    roofline, kernels, rooflines = None, None, None
     if not a.no_profile and world == 1:
-        agg = profile_kernels(step, 3, lambda: int(tr.tgn.memory.state.n_unique.item()) if tr.tgn.use_memory else 0)
+        ncu = {}
+        try:
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        except (OSError, ValueError):
+            pass
+        deg = np.diff(tr.csr_train.rowptr.cpu().numpy())
+        hot = np.concatenate([st.sources[s0:s0 + 4 * bs], st.destinations[s0:s0 + 4 * bs]])
+        extra = {"log2deg": float(np.mean(np.ceil(np.log2(deg[hot] + 1.0)))),
+                 "mean_portfolio": float(np.mean(np.diff(st.port_ptr[s0:s0 + 4 * bs + 1])))}
+        graph_mode, tr.tc.cuda_graph = tr.tc.cuda_graph, False
+        try:
+            agg = profile_kernels(step, 3, lambda: int(tr.tgn.memory.state.n_unique.item()) if tr.tgn.use_memory else 0,
+                                  extra)
+        finally:
+            tr.tc.cuda_graph = graph_mode
         tot = sum(v["ms"] for v in agg.values())
         kernels = {k: {"ms_per_step": v["ms"] / 3, "share": v["ms"] / tot, "calls_per_step": v["calls"] / 3}
                    for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
-        top = max(agg.items(), key=lambda kv: kv[1]["ms"])
-        name, v = top
-        if v["flop"] > 0:
-            ach = v["flop"] / (v["ms"] * 1e-3) / 1e12
-            peak = peaks.get("bf16_tflops_sustained", 1400.0)
-            roofline = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                        "frac": ach / peak, "traffic": None,
-                        "note": "fp32 FFMA path measured against the bf16 tensor peak (measured, sustained)"
-                        if a.gemm == "fp32" else "bf16 tcgen05 path, of measured sustained peak"}
-        elif v["byte"] > 0:
-            ach = v["byte"] / (v["ms"] * 1e-3) / 1e9
-            peak = peaks.get("hbm_gbs", 6650.0)
-            roofline = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                        "frac": ach / peak, "traffic": None, "note": "of measured copy bandwidth"}
+        rooflines = {}
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+            r = roofline_of(k, v, peaks, a.gemm, ncu)
+            if r is not None:
+                r["share_of_step"] = v["ms"] / tot
+                rooflines[k] = r
+        top = max(agg.items(), key=lambda kv: kv[1]["ms"])[0]
+        roofline = rooflines.get(top)
 
     # ---- eval users/sec (the second half of the metric): full ranking over all stocks
     eval_users = None
@@ -342,7 +399,10 @@ def main():
                           "global_batch": events_per_step, "parallelism": f"node-sharded x{world}" if world > 1 else "1 GPU",
                           "timing": "sum of per-step CUDA-event durations, max over ranks"},
                "clocks": clk, "e2e": e2e, "gpu_launches": launches, "wall_s": wall,
-               "roofline": roofline, "cpu_baseline": cpu, "eval_users_per_sec": eval_users, "kernels": kernels}
+               "roofline": roofline, "cpu_baseline": cpu, "eval_users_per_sec": eval_users, "kernels": kernels,
+               "rooflines": rooflines}
+        out["config"].update({"dropout": a.dropout, "gemm_mode": a.gemm, "cuda_graph": bool(tc.cuda_graph and world == 1),
+                              "eval": f"full ranking over all {a.items} stocks, {a.eval_bs} users per batch"})
         print(json.dumps(out))
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -44,6 +44,19 @@ def init_params(d, F, model="ours", n_layers=1, seed=0):
     return p
 
 
+def time_statistics(sources, destinations, timestamps):
+    """mean / std of the per-node inter-event times, sources and destinations separately, the first event of a
+    node measured from 0 (reference utils/data.py:75-99; main.py passes them to the TGN constructor)."""
+    out = []
+    for ids in (sources, destinations):
+        last, diffs = {}, np.empty(len(ids), dtype=np.float64)
+        for k, (v, t) in enumerate(zip(ids.tolist(), timestamps.tolist())):
+            diffs[k] = t - last.get(v, 0)
+            last[v] = t
+        out += [float(np.mean(diffs)), float(np.std(diffs))]
+    return tuple(out)
+
+
 class OracleTrainer:
     def __init__(self, st, model="ours", bs=512, d=64, n_neighbors=10, n_layers=1, lr=1e-4, num_negatives=20,
                  p_neg_num=3, gamma=2.0, lam=0.5, seed=0, params=None, train_mask=None):
@@ -67,7 +80,10 @@ class OracleTrainer:
             kw = dict(memory_updater="rnn", dyrep=True, use_destination_embedding_in_message=True)
         elif model == "tgat":
             kw = dict(use_memory=False)
-        self.tgn = TGNOracle(self.p, self.adj_train, node_feat, st.edge_features, n_layers=n_layers, n_heads=2, **kw)
+        ms, ss, md, sd = time_statistics(st.sources, st.destinations, st.timestamps)
+        self.tgn = TGNOracle(self.p, self.adj_train, node_feat, st.edge_features, n_layers=n_layers, n_heads=2,
+                             mean_time_shift_src=ms, std_time_shift_src=ss, mean_time_shift_dst=md,
+                             std_time_shift_dst=sd, **kw)
         self.tgn.nbr_seed = seed
         self.opt = torch.optim.Adam([v for v in self.p.values()], lr=lr)
         self.universe_items = np.unique(st.destinations[tr])

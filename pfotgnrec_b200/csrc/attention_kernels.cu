@@ -25,15 +25,17 @@ struct NbrArgs {
     const int32_t* idx; const int32_t* eidx; const float* dt;
     const float* efeat; const float* tw; const float* tb;
     int64_t Q; int n; int d; int F; int H; int ekp;
-    float p_drop; uint32_t k0, k1, step;
+    float p_drop; uint32_t k0, k1, step; const uint32_t* step_dev;
     float* XB; float* P; int32_t* invalid;
     // backward only
     const float* dXB; float* dQK; float* dT; int64_t lddt; float* partial;
 };
 
-__device__ __forceinline__ float keep_scale(const NbrArgs& p, int64_t q, int h, int j) {
+// the dropout stream is keyed by (query, head * n + slot, step): `step` = p.step + *p.step_dev, the device
+// part being a per-batch counter the host bumps on the stream (so a captured CUDA graph replays fresh masks)
+__device__ __forceinline__ float keep_scale(const NbrArgs& p, uint32_t step, int64_t q, int h, int j) {
     if (p.p_drop <= 0.0f) return 1.0f;
-    const uint32_t r = philox4x32_10((uint32_t)q, (uint32_t)(h * p.n + j), p.step, PFO_PURPOSE_DROPOUT, p.k0, p.k1).x;
+    const uint32_t r = philox4x32_10((uint32_t)q, (uint32_t)(h * p.n + j), step, PFO_PURPOSE_DROPOUT, p.k0, p.k1).x;
     const float u = (float)(r >> 8) * (1.0f / 16777216.0f);
     return u < p.p_drop ? 0.0f : 1.0f / (1.0f - p.p_drop);
 }
@@ -46,6 +48,7 @@ attn_nbr_fwd_kernel(const NbrArgs p) {
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int d = p.d, F = p.F, H = p.H, n = p.n;
     const int c0 = lane * DPL;
+    const uint32_t step = p.step + (p.step_dev ? *p.step_dev : 0u);
     float tw[DPL], tb[DPL];
 #pragma unroll
     for (int i = 0; i < DPL; ++i) { tw[i] = p.tw[c0 + i]; tb[i] = p.tb[c0 + i]; }
@@ -88,7 +91,7 @@ attn_nbr_fwd_kernel(const NbrArgs p) {
                     const float m_new = fmaxf(mx[h], s);
                     const float sc = expf(mx[h] - m_new);
                     const float e = expf(s - m_new);
-                    const float w = e * keep_scale(p, q, h, j);
+                    const float w = e * keep_scale(p, step, q, h, j);
                     l[h] = l[h] * sc + e;
                     ap[h] = ap[h] * sc + w;
                     ae[h] = ae[h] * sc + w * xe;
@@ -132,6 +135,7 @@ attn_nbr_bwd_kernel(const NbrArgs p) {
     float* stash = smem + (size_t)wib * n * sw;
     float* red = smem + (size_t)wpb * n * sw;           // [wpb][2][d] for the block reduction
     const int c0 = lane * DPL;
+    const uint32_t step = p.step + (p.step_dev ? *p.step_dev : 0u);
     float tw[DPL], tb[DPL], dwl[DPL], dbl[DPL];
 #pragma unroll
     for (int i = 0; i < DPL; ++i) { tw[i] = p.tw[c0 + i]; tb[i] = p.tb[c0 + i]; dwl[i] = 0.f; dbl[i] = 0.f; }
@@ -184,7 +188,7 @@ attn_nbr_bwd_kernel(const NbrArgs p) {
                         float part = ge[h] * xe;
 #pragma unroll
                         for (int i = 0; i < DPL; ++i) part = fmaf(ga[h][i], xh[i], fmaf(gg[h][i], xt[i], part));
-                        const float dp = (warp_sum(part) + gp[h]) * keep_scale(p, q, h, j);
+                        const float dp = (warp_sum(part) + gp[h]) * keep_scale(p, step, q, h, j);
                         if (lane == j) dpj[h] = dp;
                     }
                 }
@@ -212,7 +216,7 @@ attn_nbr_bwd_kernel(const NbrArgs p) {
                 for (int h = 0; h < kMaxHeads; ++h) {
                     if (h < H) {
                         const float ds = __shfl_sync(0xffffffffu, dsj[h], j);
-                        const float pw = __shfl_sync(0xffffffffu, pj[h], j) * keep_scale(p, q, h, j);
+                        const float pw = __shfl_sync(0xffffffffu, pj[h], j) * keep_scale(p, step, q, h, j);
                         de[h] = fmaf(ds, xe, de[h]);
 #pragma unroll
                         for (int i = 0; i < DPL; ++i) {
@@ -389,14 +393,14 @@ int launch_bwd(const NbrArgs& a, int grid, size_t smem, cudaStream_t s) {
 PFO_API int pfo_attn_nbr_fwd(const float* QK, const float* T, int64_t ldt, const int32_t* idx, const int32_t* eidx,
                              const float* dt, const float* efeat, const float* tw, const float* tb,
                              int64_t Q, int n, int d, int F, int H, int ekp,
-                             float p_drop, uint64_t seed, uint32_t step,
+                             float p_drop, uint64_t seed, uint32_t step, const uint32_t* step_dev,
                              float* XB, float* P, int32_t* invalid, void* stream) {
     if (Q <= 0) return 0;
     if (d % 32 != 0 || d > 128 || F > 32 || H > kMaxHeads || n > 32 || n < 1) return (int)cudaErrorInvalidValue;
     NbrArgs a{};
     a.QK = QK; a.T = T; a.ldt = ldt; a.idx = idx; a.eidx = eidx; a.dt = dt; a.efeat = efeat; a.tw = tw; a.tb = tb;
     a.Q = Q; a.n = n; a.d = d; a.F = F; a.H = H; a.ekp = ekp; a.p_drop = p_drop;
-    a.k0 = (uint32_t)(seed & 0xffffffffu); a.k1 = (uint32_t)(seed >> 32); a.step = step;
+    a.k0 = (uint32_t)(seed & 0xffffffffu); a.k1 = (uint32_t)(seed >> 32); a.step = step; a.step_dev = step_dev;
     a.XB = XB; a.P = P; a.invalid = invalid;
     cudaStream_t s = (cudaStream_t)stream;
     switch (d / 32) {
@@ -413,7 +417,7 @@ PFO_API int pfo_attn_nbr_bwd(const float* QK, const float* dXB, const float* P, 
                              const float* T, int64_t ldt, const int32_t* idx, const int32_t* eidx, const float* dt,
                              const float* efeat, const float* tw, const float* tb,
                              int64_t Q, int n, int d, int F, int H, int ekp,
-                             float p_drop, uint64_t seed, uint32_t step,
+                             float p_drop, uint64_t seed, uint32_t step, const uint32_t* step_dev,
                              float* dQK, float* dT, int64_t lddt, float* dtw_dtb, int accumulate,
                              float* workspace, void* stream) {
     if (Q <= 0) return 0;
@@ -421,7 +425,7 @@ PFO_API int pfo_attn_nbr_bwd(const float* QK, const float* dXB, const float* P, 
     NbrArgs a{};
     a.QK = QK; a.T = T; a.ldt = ldt; a.idx = idx; a.eidx = eidx; a.dt = dt; a.efeat = efeat; a.tw = tw; a.tb = tb;
     a.Q = Q; a.n = n; a.d = d; a.F = F; a.H = H; a.ekp = ekp; a.p_drop = p_drop;
-    a.k0 = (uint32_t)(seed & 0xffffffffu); a.k1 = (uint32_t)(seed >> 32); a.step = step;
+    a.k0 = (uint32_t)(seed & 0xffffffffu); a.k1 = (uint32_t)(seed >> 32); a.step = step; a.step_dev = step_dev;
     a.P = const_cast<float*>(P); a.invalid = const_cast<int32_t*>(invalid);
     a.dXB = dXB; a.dQK = dQK; a.dT = dT; a.lddt = lddt; a.partial = workspace;
     cudaStream_t s = (cudaStream_t)stream;

@@ -173,6 +173,9 @@ class TGNEngine:
         self.ws = _Workspace(self.device)
         self.step_id = 0
         self.seed = 0
+        # device-resident batch counter keying the dropout stream (bumped on the stream each batch, so a
+        # captured CUDA graph of the step draws fresh masks on every replay)
+        self.step_ctr = torch.zeros(1, dtype=torch.int32, device=self.device)
         if state is None:        # memory-less models still need the compaction scratch
             self.state = TGNState(self.n_nodes, ModelConfig(d=cfg.d, n_edge_feat=cfg.n_edge_feat), self.device)
 
@@ -381,11 +384,11 @@ class TGNEngine:
         tp.XB = torch.empty(M, H, ekp, device=dev)
         tp.P = torch.empty(M, H, n, device=dev)
         tp.invalid = torch.empty(M, dtype=torch.int32, device=dev)
-        tp.step = self.step_id * 16 + layer
+        tp.step = layer
         p_drop = c.dropout if save["train"] else 0.0
         _lib.call("pfo_attn_nbr_fwd", ptr(tp.QK), ptr(tp.T), d, ptr(tp.idx), ptr(tp.eidx), ptr(tp.dt),
                   ptr(self.edge_feat), ptr(save["tw"]), ptr(save["tb"]), M, n, d, F, H, ekp,
-                  float(p_drop), self.seed, tp.step, ptr(tp.XB), ptr(tp.P), ptr(tp.invalid))
+                  float(p_drop), self.seed, tp.step, ptr(self.step_ctr), ptr(tp.XB), ptr(tp.P), ptr(tp.invalid))
         tp.ATT = torch.empty(M, E, device=dev)
         for h in range(H):          # attn_h = Wv_h xbar_h + bv_h * psum_h
             _linear(c, tp.XB.data_ptr() + h * ekp * F4, H * ekp, None, WvA.data_ptr() + h * hd * ekp * F4, ekp, 0,
@@ -436,7 +439,7 @@ class TGNEngine:
         p_drop = c.dropout if save["train"] else 0.0
         _lib.call("pfo_attn_nbr_bwd", ptr(tp.QK), ptr(dXB), ptr(tp.P), ptr(tp.invalid), ptr(tp.T), d, ptr(tp.idx),
                   ptr(tp.eidx), ptr(tp.dt), ptr(self.edge_feat), ptr(save["tw"]), ptr(save["tb"]),
-                  M, n, d, F, H, ekp, float(p_drop), self.seed, tp.step, ptr(dQK), ptr(tp.dT), d,
+                  M, n, d, F, H, ekp, float(p_drop), self.seed, tp.step, ptr(self.step_ctr), ptr(dQK), ptr(tp.dT), d,
                   ptr(save["g_twtb"]), 1, ptr(nws))
         dQP = torch.empty(M, E, device=dev)
         for h in range(H):
@@ -475,6 +478,8 @@ class TGNStepFunction(torch.autograd.Function):
         Q = q_nodes.shape[0]
         save = dict(train=batch["train"], tw=tw, tb=tb)
         eng.step_id += 1
+        if c.dropout > 0.0 and batch["train"]:
+            eng.step_ctr.add_(16)
 
         # 1. neighbour sampling tree + unique touched nodes
         tree = None

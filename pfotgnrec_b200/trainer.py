@@ -77,6 +77,7 @@ class TrainConfig:
     lambda_mv: float = 0.5
     seed: int = 0
     gemm_mode: str = "fp32"
+    cuda_graph: bool = True      # replay the whole step (sampling .. Adam) as one CUDA graph per batch size
 
 
 class StreamOnDevice:
@@ -95,6 +96,29 @@ class StreamOnDevice:
         pi = st.port_items if st.port_items.size else np.zeros(1, np.int32)
         self.port_items = torch.as_tensor(pi.astype(np.int32), device=dev)
         self.port_items_as_item_ids = self.port_items + (st.n_users + 1)
+
+
+def time_statistics(sources, destinations, timestamps):
+    """reference utils/data.py:75-99 (compute_time_statistics) without the Python loop over events: per-node
+    inter-event times through one stable sort by node id.  The mean / std run over the diffs in stream order,
+    like the reference's lists, so the fp64 sums round identically."""
+    out = []
+    n = len(sources)
+    for ids in (np.asarray(sources), np.asarray(destinations)):
+        order = np.lexsort((np.arange(n), ids))
+        t = np.asarray(timestamps, dtype=np.float64)[order]
+        first = np.r_[True, ids[order][1:] != ids[order][:-1]]
+        diff = np.empty(n, dtype=np.float64)
+        diff[order] = np.where(first, t, t - np.r_[0.0, t[:-1]])
+        out += [float(np.mean(diff)), float(np.std(diff))]
+    return out
+
+
+class _StepGraph:
+    """Static input buffers, the captured graph and its output for one batch size."""
+
+    def __init__(self, static):
+        self.static, self.graph, self.loss, self.eager_steps, self.launches = static, None, None, 0, 0
 
 
 class PfoTrainer:
@@ -136,7 +160,8 @@ class PfoTrainer:
                                mean_time_shift_src=ms, std_time_shift_src=ss, mean_time_shift_dst=md,
                                std_time_shift_dst=sd, use_source_embedding_in_message=False,
                                gemm_mode=tc.gemm_mode, **kw).to(self.device)
-        self.opt = torch.optim.Adam(self.tgn.parameters(), lr=tc.lr, fused=True)
+        self.opt = torch.optim.Adam(self.tgn.parameters(), lr=tc.lr, fused=True, capturable=True)
+        self._graphs = {}            # batch size -> _StepGraph
         self.dev_stream = StreamOnDevice(st, device)
         universe_items = np.unique(st.destinations[tr])
         self.universe_items = universe_items
@@ -150,16 +175,7 @@ class PfoTrainer:
         self.bpr_ws = torch.empty(1024, device=self.device)
 
     def _time_statistics(self):
-        """reference utils/data.py:75-99 (compute_time_statistics), vectorised."""
-        st = self.st
-        out = []
-        for ids in (st.sources, st.destinations):
-            order = np.lexsort((np.arange(st.n_events), ids))
-            t = st.timestamps[order]
-            first = np.r_[True, ids[order][1:] != ids[order][:-1]]
-            diff = np.where(first, t, t - np.r_[0.0, t[:-1]])
-            out += [float(np.mean(diff)), float(np.std(diff))]
-        return out
+        return time_statistics(self.st.sources, self.st.destinations, self.st.timestamps)
 
     # ------------------------------------------------------------------ one training step
     def _batch(self, s, e):
@@ -185,14 +201,78 @@ class PfoTrainer:
 
     def train_step_host(self, hb):
         """One step from HOST buffers: host->device copies of the batch, then `train_step`."""
+        B = hb["src"].shape[0]
+        if self._graph_ok(B):
+            sg = self._step_graph(B)
+            for k, v in hb.items():
+                if k == "nbytes":
+                    continue
+                dst = sg.static[k]
+                (dst[:v.shape[0]] if k == "port_items" else dst).copy_(v, non_blocking=True)
+            return self._run_graphed(sg)
         b = {k: v.to(self.device, non_blocking=True) for k, v in hb.items() if k != "nbytes"}
         return self.train_step(0, 0, batch=b)
 
+    # ---- CUDA-graph replay.  Every shape of the step is a function of the batch size alone (the unique-node
+    # count lives on the device, kernels read it there), so one graph per batch size covers the stream.
+    def _graph_ok(self, B):
+        return bool(self.tc.cuda_graph) and self.device.type == "cuda" and self.tc.model != "tgat"
+
+    def _step_graph(self, B):
+        sg = self._graphs.get(B)
+        if sg is None:
+            st, dev = self.st, self.device
+            cap = int(np.max(np.diff(st.port_ptr))) * B + 1 if st.port_ptr.size > 1 else 1
+            i32, i64 = torch.int32, torch.int64
+            static = dict(src=torch.zeros(B, dtype=i32, device=dev), dst=torch.zeros(B, dtype=i32, device=dev),
+                          ts=torch.zeros(B, dtype=torch.float64, device=dev), eidx=torch.zeros(B, dtype=i32, device=dev),
+                          ev=torch.zeros(B, dtype=i64, device=dev), day=torch.zeros(B, dtype=i32, device=dev),
+                          port_ptr=torch.zeros(B + 1, dtype=i64, device=dev),
+                          port_items=torch.zeros(cap, dtype=i32, device=dev))
+            sg = self._graphs[B] = _StepGraph(static)
+        return sg
+
+    def _fill_static(self, sg, s, e):
+        D, st = self.dev_stream, self.st
+        x = sg.static
+        x["src"].copy_(D.src[s:e]); x["dst"].copy_(D.dst[s:e]); x["ts"].copy_(D.ts[s:e])
+        x["eidx"].copy_(D.eidx[s:e]); x["ev"].copy_(D.ev[s:e]); x["day"].copy_(D.day[s:e])
+        p0, p1 = int(st.port_ptr[s]), int(st.port_ptr[e])          # host copy of the CSR: no device sync
+        torch.sub(D.port_ptr[s:e + 1], p0, out=x["port_ptr"])
+        if p1 > p0:
+            x["port_items"][:p1 - p0].copy_(D.port_items[p0:p1])
+
+    def _run_graphed(self, sg):
+        """The first steps at a batch size run eagerly on the static buffers (they are real training steps and
+        warm every lazy allocation); the next one is captured (capture launches nothing) and replayed."""
+        if sg.graph is None:
+            if sg.eager_steps < 2:
+                sg.eager_steps += 1
+                return self._step_body(sg.static)
+            torch.cuda.synchronize(self.device)
+            self.opt.zero_grad(set_to_none=True)
+            g = torch.cuda.CUDAGraph()
+            launches0 = _lib.LAUNCHES
+            with torch.cuda.graph(g):
+                sg.loss = self._step_body(sg.static)
+            sg.launches = _lib.LAUNCHES - launches0
+            sg.graph = g
+        sg.graph.replay()
+        _lib.LAUNCHES += sg.launches
+        return sg.loss
+
     def train_step(self, s, e, batch=None):
         """Events [s, e) of the stream: MV selection (or uniform negatives) -> embeddings -> BPR ->
-        backward -> Adam (reference main.py:179-394).  Returns the loss tensor (no host sync)."""
+        backward -> Adam (reference main.py:179-394).  Returns the loss tensor (no host sync; in CUDA-graph
+        mode it is the graph's output buffer, overwritten by the next step)."""
+        if batch is None and self._graph_ok(e - s) and e - s > 0 and e <= self.st.n_events:
+            sg = self._step_graph(e - s)
+            self._fill_static(sg, s, e)
+            return self._run_graphed(sg)
+        return self._step_body(batch if batch is not None else self._batch(s, e))
+
+    def _step_body(self, b):
         tc, D = self.tc, self.dev_stream
-        b = batch if batch is not None else self._batch(s, e)
         tgn = self.tgn.train()
         eng = tgn._get_engine()
         eng.nf = self.nf_train

@@ -1,0 +1,116 @@
+"""GPU tests of the training / evaluation driver (pfotgnrec_b200/trainer.py): the step loop of reference
+main.py:179-394 against the CPU oracle loop, and the CUDA-graph replay against kernel-by-kernel launches."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from helpers import rel_err
+
+
+def _stream(seed=1):
+    from pfotgnrec_b200.synth import make_stream
+    return make_stream(n_users=300, n_items=60, n_events=3000, n_days=20, seed=seed, ts_mode="small")
+
+
+@pytest.mark.parametrize("model", ["ours", "tgn", "jodie"])
+def test_trainer_steps_match_oracle_loop(model):
+    """Per-step parity of loss / memory / pending flags with weights injected from the CUDA model (Adam turns
+    1e-10 gradient noise into 1e-4 updates, so the weights are re-synchronised every step)."""
+    from pfotgnrec_b200.trainer import PfoTrainer, TrainConfig
+    from oracle.train_loop import OracleTrainer
+    st = _stream()
+    tc = TrainConfig(model=model, bs=128, lr=1e-4, cuda_graph=False)
+    tr = PfoTrainer(st, tc, device="cuda:0")
+    p = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in tr.tgn.named_parameters()}
+    orc = OracleTrainer(st, model, bs=128, params=p, seed=tc.seed)
+    for i in range(4):
+        s, e = 1000 + i * 128, 1000 + (i + 1) * 128
+        for k, v in tr.tgn.named_parameters():
+            p[k].data.copy_(v.detach().cpu())
+        la = float(tr.train_step(s, e).item())
+        lb = orc.train_step(s, e)
+        assert abs(la - lb) < 1e-4 * max(1.0, abs(lb)), (i, la, lb)
+    assert rel_err(tr.tgn.memory.memory.detach().cpu().numpy(), orc.tgn.memory.numpy()) < 1e-4
+    assert np.array_equal(tr.tgn.memory.state.pend_valid.cpu().numpy().astype(bool), orc.tgn.pend_valid.numpy())
+
+
+@pytest.mark.parametrize("model", ["ours", "jodie"])
+def test_cuda_graph_replay_matches_eager(model):
+    """One CUDA graph per batch size (captured on the third step) == kernel-by-kernel launches: same losses,
+    same memory, bit-identical pending-message flags and timestamps, same weights after Adam."""
+    from pfotgnrec_b200.trainer import PfoTrainer, TrainConfig
+    st = _stream(seed=2)
+    out = []
+    for graph in (False, True):
+        tr = PfoTrainer(st, TrainConfig(model=model, bs=128, lr=1e-3, cuda_graph=graph), device="cuda:0")
+        losses = []
+        for i in range(8):
+            s = 600 + i * 128
+            losses.append(float(tr.train_step(s, s + 128).item()))
+        if graph:
+            assert tr._graphs[128].graph is not None and tr._graphs[128].launches > 10
+        sd = tr.tgn.memory.state
+        out.append((losses, sd.memory.cpu().numpy(), sd.pend_valid.cpu().numpy(), sd.pend_ts.cpu().numpy(),
+                    {k: v.detach().cpu().numpy() for k, v in tr.tgn.named_parameters()}))
+    (la, ma, va, ta, pa), (lb, mb, vb, tb, pb) = out
+    assert np.allclose(la, lb, rtol=1e-5, atol=1e-6), (la, lb)
+    assert rel_err(mb, ma) < 1e-5
+    assert np.array_equal(va, vb) and np.array_equal(ta, tb)
+    for k in pa:
+        assert rel_err(pb[k], pa[k]) < 1e-4, k
+
+
+def test_cuda_graph_from_host_batches():
+    """train_step_host (pinned host buffers -> static device buffers -> graph replay) == train_step on the
+    device-resident stream."""
+    from pfotgnrec_b200.trainer import PfoTrainer, TrainConfig
+    st = _stream(seed=3)
+    res = []
+    for host in (False, True):
+        tr = PfoTrainer(st, TrainConfig(model="ours", bs=64, cuda_graph=True), device="cuda:0")
+        hbs = tr.make_host_batches(500, 6, 64)
+        ls = []
+        for i in range(6):
+            l = tr.train_step_host(hbs[i]) if host else tr.train_step(500 + i * 64, 500 + (i + 1) * 64)
+            ls.append(float(l.item()))
+        res.append((ls, tr.tgn.memory.state.memory.cpu().numpy()))
+    assert np.allclose(res[0][0], res[1][0], rtol=1e-5, atol=1e-6)
+    assert rel_err(res[1][1], res[0][1]) < 1e-5
+
+
+def test_dropout_stream_is_keyed_by_the_device_step_counter():
+    """Attention dropout draws from Philox keyed by (query, head * n + slot, step + *step_dev): the host part
+    and the device part of the step are interchangeable, and a bumped counter gives a fresh mask."""
+    from pfotgnrec_b200 import _lib
+    from pfotgnrec_b200._lib import ptr
+    g = torch.Generator(device="cuda").manual_seed(0)
+    Q, n, d, F, H = 257, 10, 64, 1, 2
+    ekp = (2 * d + F + 1 + 3) // 4 * 4
+    T = torch.randn(500, d, device="cuda", generator=g)
+    QK = torch.randn(Q, H, ekp, device="cuda", generator=g) * 0.2
+    idx = torch.randint(-1, 500, (Q, n), device="cuda", generator=g, dtype=torch.int32)
+    eidx = torch.randint(0, 50, (Q, n), device="cuda", generator=g, dtype=torch.int32)
+    dt = torch.rand(Q, n, device="cuda", generator=g) * 100
+    ef = torch.randn(50, F, device="cuda", generator=g)
+    tw, tb = torch.rand(d, device="cuda", generator=g), torch.rand(d, device="cuda", generator=g)
+
+    def run(p_drop, step, ctr):
+        XB = torch.empty(Q, H, ekp, device="cuda")
+        P = torch.empty(Q, H, n, device="cuda")
+        inv = torch.empty(Q, dtype=torch.int32, device="cuda")
+        c = torch.tensor([ctr], dtype=torch.int32, device="cuda")
+        _lib.call("pfo_attn_nbr_fwd", ptr(QK), ptr(T), d, ptr(idx), ptr(eidx), ptr(dt), ptr(ef), ptr(tw), ptr(tb),
+                  Q, n, d, F, H, ekp, float(p_drop), 7, step, ptr(c), ptr(XB), ptr(P), ptr(inv))
+        torch.cuda.synchronize()
+        return XB.cpu().numpy()
+
+    base = run(0.0, 0, 0)
+    a = run(0.5, 3, 16)
+    assert np.array_equal(a, run(0.5, 19, 0))            # host and device parts of the step add up
+    assert not np.array_equal(a, run(0.5, 3, 32))        # next batch: fresh mask
+    assert not np.array_equal(a, base)
+    psum = a[:, :, 2 * d + F]                            # kept softmax mass, scaled by 1/(1-p): mean ~ 1
+    live = (idx.cpu().numpy() >= 0).any(axis=1)
+    assert abs(psum[live].mean() - 1.0) < 0.1

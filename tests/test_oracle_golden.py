@@ -70,3 +70,15 @@ def test_mv_select_ids_bit_exact(ci):
                                 float(z[f"c{ci}_gamma"]), float(z[f"c{ci}_lam"]))
     assert np.array_equal(pp, z[f"c{ci}_ppos_stable"])
     assert np.array_equal(pn, z[f"c{ci}_pneg_stable"])
+
+
+def test_time_statistics_host_vs_oracle():
+    """pfotgnrec_b200.trainer.time_statistics (one sort) == the oracle's restatement of the reference loop
+    (utils/data.py:75-99), bit for bit, on a small and an NBG-format stream."""
+    from pfotgnrec_b200.synth import make_stream
+    from pfotgnrec_b200.trainer import time_statistics as host_stats
+    from oracle.train_loop import time_statistics as oracle_stats
+    for mode in ("small", "nbg"):
+        st = make_stream(n_users=200, n_items=40, n_events=2500, n_days=15, seed=5, ts_mode=mode, with_prices=False)
+        assert tuple(host_stats(st.sources, st.destinations, st.timestamps)) == \
+            oracle_stats(st.sources, st.destinations, st.timestamps)
