@@ -162,7 +162,7 @@ def algorithmic_work(name, args, n_uniq, extra):
         Q, n, d, F, H, ekp = args[9:15]
         return "byte", Q * (2 * H * ekp * 4 + n * (4 * d + 4 * F + 12) + H * n * 4)
     if name == "pfo_attn_nbr_bwd":
-        Q, n, d, F, H, ekp = args[12:18]
+        Q, n, d, F, H, ekp = args[13:19]
         return "byte", Q * (3 * H * ekp * 4 + n * (2 * 4 * d + 4 * F + 12) + H * n * 4)
     if name == "pfo_neighbor_sample":
         Q, n = args[6], args[7]

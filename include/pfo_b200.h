@@ -147,16 +147,18 @@ int pfo_gather_rows(const float* src, int64_t lds, const int32_t* idx, int64_t M
 /* ---- K4 neighbour level: fused gather + TimeEncode + masked softmax over sampled neighbours ---
  * model/temporal_attention.py:34-90, model/time_encoding.py:17-25, modules/embedding_module.py:141-154.
  * Weight-absorbed multi-head attention (see csrc/attention_kernels.cu).  QK/XB/dQK/dXB are
- * [Q, H, ekp] with segment [h (d) | e (F) | te (d) | psum | pad]; T is the feature table the
+ * [Q, H, ekp] with segment [h (d) | e (F) | te (d) | psum | valid | one | 0..] (ekp >= 2d+F+3; `valid` = the
+ * query has a neighbour, `one` = 1: constant columns that let the host fold biases into the consuming GEMM);
+ * XB / dXB rows are ldxb / lddxb floats apart.  T is the feature table the
  * neighbour rows are gathered from (idx < 0 = padded neighbour); P [Q,H,n] = softmax weights.
  * Dropout on the attention weights (p_drop > 0) draws from the shared Philox stream keyed by
  * (query, head * n + slot, step + *step_dev); step_dev (optional) is a device-resident batch counter. */
 int pfo_attn_nbr_fwd(const float* QK, const float* T, int64_t ldt, const int32_t* idx, const int32_t* eidx,
                      const float* dt, const float* efeat, const float* tw, const float* tb,
                      int64_t Q, int n, int d, int F, int H, int ekp, float p_drop, uint64_t seed, uint32_t step,
-                     const uint32_t* step_dev, float* XB, float* P, int32_t* invalid, void* stream);
+                     const uint32_t* step_dev, float* XB, int64_t ldxb, float* P, int32_t* invalid, void* stream);
 int64_t pfo_attn_nbr_bwd_workspace_floats(int d);
-int pfo_attn_nbr_bwd(const float* QK, const float* dXB, const float* P, const int32_t* invalid,
+int pfo_attn_nbr_bwd(const float* QK, const float* dXB, int64_t lddxb, const float* P, const int32_t* invalid,
                      const float* T, int64_t ldt, const int32_t* idx, const int32_t* eidx, const float* dt,
                      const float* efeat, const float* tw, const float* tb,
                      int64_t Q, int n, int d, int F, int H, int ekp, float p_drop, uint64_t seed, uint32_t step,

@@ -45,9 +45,9 @@ _SIGS = {
     "pfo_scatter_add_rows": (c_int, [P, c_int64, P, c_int64, c_int, P, c_int64, P]),
     "pfo_gather_rows": (c_int, [P, c_int64, P, c_int64, c_int, P, c_int64, P]),
     "pfo_attn_nbr_fwd": (c_int, [P, P, c_int64, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int,
-                                 c_float, c_uint64, c_uint32, P, P, P, P, P]),
+                                 c_float, c_uint64, c_uint32, P, P, c_int64, P, P, P]),
     "pfo_attn_nbr_bwd_workspace_floats": (c_int64, [c_int]),
-    "pfo_attn_nbr_bwd": (c_int, [P, P, P, P, P, c_int64, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int,
+    "pfo_attn_nbr_bwd": (c_int, [P, P, c_int64, P, P, P, c_int64, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int,
                                  c_float, c_uint64, c_uint32, P, P, P, c_int64, P, c_int, P, P]),
     "pfo_bpr": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P, P, c_float, P, P]),
     "pfo_eval_score": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, P, P, P]),

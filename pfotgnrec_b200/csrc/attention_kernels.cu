@@ -11,14 +11,19 @@
 // This cuts the neighbour-level FLOPs by ~8x and leaves a gather-bound kernel:
 // one warp per query, lanes own contiguous feature columns, online softmax in registers.
 //
-// Row layout of QK / XB / dQK / dXB: [Q, H, EKP], segment = [h (d) | e (F) | te (d) | psum | pad].
+// Row layout of QK / XB / dQK / dXB: [Q, H, EKP], segment = [h (d) | e (F) | te (d) | psum | valid | one | 0..],
+// EKP >= 2d + F + 3.  `valid` (1 when the query has at least one neighbour, else 0) and `one` (always 1) are
+// constant columns the forward kernel emits so that the host can fold the out-projection bias (applied to
+// valid rows only, temporal_attention.py:84) and the merge-layer bias into the weight of the GEMM that consumes
+// XB.  XB / dXB rows may be strided (ldxb / lddxb floats between queries) so that XB lands directly inside
+// the operand row [XB | h_query] of that GEMM.
 #include "common.cuh"
 #include "philox.cuh"
 #include "pfo_math.cuh"
 
 namespace {
 
-constexpr int kMaxHeads = 4;
+constexpr int kMaxHeads = 4;      // instantiated head counts: 1, 2, 4
 
 struct NbrArgs {
     const float* QK; const float* T; int64_t ldt;
@@ -26,9 +31,9 @@ struct NbrArgs {
     const float* efeat; const float* tw; const float* tb;
     int64_t Q; int n; int d; int F; int H; int ekp;
     float p_drop; uint32_t k0, k1, step; const uint32_t* step_dev;
-    float* XB; float* P; int32_t* invalid;
+    float* XB; int64_t ldxb; float* P; int32_t* invalid;
     // backward only
-    const float* dXB; float* dQK; float* dT; int64_t lddt; float* partial;
+    const float* dXB; int64_t lddxb; float* dQK; float* dT; int64_t lddt; float* partial;
 };
 
 // the dropout stream is keyed by (query, head * n + slot, step): `step` = p.step + *p.step_dev, the device
@@ -40,98 +45,145 @@ __device__ __forceinline__ float keep_scale(const NbrArgs& p, uint32_t step, int
     return u < p.p_drop ? 0.0f : 1.0f / (1.0f - p.p_drop);
 }
 
+// DPL consecutive floats of a row owned by one lane (rows are 16-byte aligned, checked by the entry points)
 template <int DPL>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void ld_cols(const float* __restrict__ p, float (&v)[DPL]) {
+    if constexpr (DPL == 2) { const float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y; }
+    else if constexpr (DPL == 4) { const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else {
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) v[i] = p[i];
+    }
+}
+template <int DPL>
+__device__ __forceinline__ void st_cols(float* __restrict__ p, const float (&v)[DPL]) {
+    if constexpr (DPL == 2) *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    else if constexpr (DPL == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    else {
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) p[i] = v[i];
+    }
+}
+
+constexpr int kUnroll = 4;      // neighbour rows in flight per warp (independent gathers issued back to back)
+
+// One warp per query; lane l owns feature columns [l*DPL, (l+1)*DPL) of the h and te segments and -- for the
+// per-slot scalars (neighbour id, dt, edge id, dropout factor, score, softmax weight) -- neighbour slot l.
+// The slot scalars are fetched with one coalesced load each and broadcast by shuffle; neighbour rows are
+// gathered kUnroll at a time before the arithmetic that consumes them, so the L2 latency of the gathers
+// overlaps instead of serialising behind the online softmax.
+template <int DPL, int NH>
+__global__ void __launch_bounds__(128)
 attn_nbr_fwd_kernel(const NbrArgs p) {
+    constexpr int d = 32 * DPL;
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int d = p.d, F = p.F, H = p.H, n = p.n;
+    const int F = p.F, n = p.n, ekp = p.ekp;
     const int c0 = lane * DPL;
     const uint32_t step = p.step + (p.step_dev ? *p.step_dev : 0u);
     float tw[DPL], tb[DPL];
 #pragma unroll
     for (int i = 0; i < DPL; ++i) { tw[i] = p.tw[c0 + i]; tb[i] = p.tb[c0 + i]; }
     for (int64_t q = warp; q < p.Q; q += nwarps) {
-        float qa[kMaxHeads][DPL], qg[kMaxHeads][DPL], qe[kMaxHeads];
-        float ah[kMaxHeads][DPL], at[kMaxHeads][DPL], ae[kMaxHeads], ap[kMaxHeads];
-        float mx[kMaxHeads], l[kMaxHeads], sj[kMaxHeads];
-#pragma unroll
-        for (int h = 0; h < kMaxHeads; ++h) {
-            if (h < H) {
-                const float* qk = p.QK + (q * H + h) * p.ekp;
-#pragma unroll
-                for (int i = 0; i < DPL; ++i) { qa[h][i] = qk[c0 + i]; qg[h][i] = qk[d + F + c0 + i]; ah[h][i] = 0.f; at[h][i] = 0.f; }
-                qe[h] = lane < F ? qk[d + lane] : 0.0f;
-                ae[h] = 0.f; ap[h] = 0.f; mx[h] = -INFINITY; l[h] = 0.f; sj[h] = 0.f;
-            }
+        int id_l = -1, ei_l = 0;
+        float dt_l = 0.0f;
+        if (lane < n) {
+            id_l = __ldg(p.idx + q * n + lane);
+            dt_l = __ldg(p.dt + q * n + lane);
+            ei_l = __ldg(p.eidx + q * n + lane);
         }
-        bool any = false;
-        for (int j = 0; j < n; ++j) {
-            const int id = p.idx[q * n + j];
-            if (id < 0) continue;                       // padded neighbour: masked (embedding_module.py:154)
-            any = true;
-            const float dtj = p.dt[q * n + j];
-            float xh[DPL], xt[DPL];
-            const float* row = p.T + (int64_t)id * p.ldt + c0;
+        float qa[NH][DPL], qg[NH][DPL], qe[NH], keep[NH];
+        float ah[NH][DPL], at[NH][DPL], ae[NH], ap[NH], mx[NH], l[NH], sj[NH];
 #pragma unroll
-            for (int i = 0; i < DPL; ++i) {
-                xh[i] = row[i];
-                xt[i] = pfo_cosf(fmaf(dtj, tw[i], tb[i]));  // full-range, never __cosf (SURVEY hard part 1)
+        for (int h = 0; h < NH; ++h) {
+            const float* qk = p.QK + (q * NH + h) * ekp;
+            ld_cols<DPL>(qk + c0, qa[h]);
+#pragma unroll
+            for (int i = 0; i < DPL; ++i) { qg[h][i] = qk[d + F + c0 + i]; ah[h][i] = 0.f; at[h][i] = 0.f; }
+            qe[h] = lane < F ? qk[d + lane] : 0.0f;
+            keep[h] = (id_l >= 0) ? keep_scale(p, step, q, h, lane) : 1.0f;    // dropout factor of slot `lane`
+            ae[h] = 0.f; ap[h] = 0.f; mx[h] = -INFINITY; l[h] = 0.f; sj[h] = 0.f;
+        }
+        const bool any = __ballot_sync(0xffffffffu, id_l >= 0) != 0u;   // padded neighbours are masked (embedding_module.py:154)
+        for (int j0 = 0; j0 < n; j0 += kUnroll) {
+            int id[kUnroll];
+            float dtj[kUnroll], xe[kUnroll], xh[kUnroll][DPL];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int j = j0 + u;
+                id[u] = __shfl_sync(0xffffffffu, id_l, j & 31);
+                dtj[u] = __shfl_sync(0xffffffffu, dt_l, j & 31);
+                const int ei = __shfl_sync(0xffffffffu, ei_l, j & 31);
+                if (j >= n) id[u] = -1;
+                xe[u] = 0.0f;
+#pragma unroll
+                for (int i = 0; i < DPL; ++i) xh[u][i] = 0.0f;
+                if (id[u] >= 0) {
+                    ld_cols<DPL>(p.T + (int64_t)id[u] * p.ldt + c0, xh[u]);
+                    if (lane < F) xe[u] = __ldg(p.efeat + (int64_t)ei * F + lane);
+                }
             }
-            const float xe = lane < F ? p.efeat[(int64_t)p.eidx[q * n + j] * F + lane] : 0.0f;
 #pragma unroll
-            for (int h = 0; h < kMaxHeads; ++h) {
-                if (h < H) {
-                    float part = qe[h] * xe;
+            for (int u = 0; u < kUnroll; ++u) {
+                if (id[u] < 0) continue;
+                const int j = j0 + u;
+                float xt[DPL];
 #pragma unroll
-                    for (int i = 0; i < DPL; ++i) part = fmaf(qa[h][i], xh[i], fmaf(qg[h][i], xt[i], part));
+                for (int i = 0; i < DPL; ++i)
+                    xt[i] = pfo_cosf(fmaf(dtj[u], tw[i], tb[i]));   // full-range, never __cosf (SURVEY hard part 1)
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                    float part = qe[h] * xe[u];
+#pragma unroll
+                    for (int i = 0; i < DPL; ++i) part = fmaf(qa[h][i], xh[u][i], fmaf(qg[h][i], xt[i], part));
                     const float s = warp_sum(part);
                     if (lane == j) sj[h] = s;
-                    const float m_new = fmaxf(mx[h], s);
-                    const float sc = expf(mx[h] - m_new);
-                    const float e = expf(s - m_new);
-                    const float w = e * keep_scale(p, step, q, h, j);
+                    // online softmax; one of exp(mx - m_new), exp(s - m_new) is exp(0)
+                    const bool up = s > mx[h];
+                    const float t = expf(up ? mx[h] - s : s - mx[h]);
+                    const float sc = up ? t : 1.0f, e = up ? 1.0f : t;
+                    const float w = e * __shfl_sync(0xffffffffu, keep[h], j);
                     l[h] = l[h] * sc + e;
                     ap[h] = ap[h] * sc + w;
-                    ae[h] = ae[h] * sc + w * xe;
+                    ae[h] = ae[h] * sc + w * xe[u];
 #pragma unroll
                     for (int i = 0; i < DPL; ++i) {
-                        ah[h][i] = ah[h][i] * sc + w * xh[i];
+                        ah[h][i] = ah[h][i] * sc + w * xh[u][i];
                         at[h][i] = at[h][i] * sc + w * xt[i];
                     }
-                    mx[h] = m_new;
+                    if (up) mx[h] = s;
                 }
             }
         }
         if (lane == 0) p.invalid[q] = any ? 0 : 1;     // rows with no neighbours: output zeroed (temporal_attention.py:84)
 #pragma unroll
-        for (int h = 0; h < kMaxHeads; ++h) {
-            if (h < H) {
-                float* xb = p.XB + (q * H + h) * p.ekp;
-                const float inv = any ? 1.0f / l[h] : 0.0f;
+        for (int h = 0; h < NH; ++h) {
+            float* xb = p.XB + q * p.ldxb + (int64_t)h * ekp;
+            const float inv = any ? 1.0f / l[h] : 0.0f;
+            float oh[DPL];
 #pragma unroll
-                for (int i = 0; i < DPL; ++i) { xb[c0 + i] = ah[h][i] * inv; xb[d + F + c0 + i] = at[h][i] * inv; }
-                if (lane < F) xb[d + lane] = ae[h] * inv;
-                if (lane == 0) xb[2 * d + F] = ap[h] * inv;
-                if (lane < n) {
-                    const bool live = p.idx[q * n + lane] >= 0;
-                    p.P[(q * H + h) * n + lane] = live ? expf(sj[h] - mx[h]) * inv : 0.0f;
-                }
-            }
+            for (int i = 0; i < DPL; ++i) { oh[i] = ah[h][i] * inv; xb[d + F + c0 + i] = at[h][i] * inv; }
+            st_cols<DPL>(xb + c0, oh);
+            if (lane < F) xb[d + lane] = ae[h] * inv;
+            if (lane == 0) xb[2 * d + F] = ap[h] * inv;
+            if (lane < ekp - (2 * d + F + 1))            // constant tail: [valid, one, 0...]
+                xb[2 * d + F + 1 + lane] = lane == 0 ? (any ? 1.0f : 0.0f) : (lane == 1 ? 1.0f : 0.0f);
+            if (lane < n) p.P[(q * NH + h) * n + lane] = id_l >= 0 ? expf(sj[h] - mx[h]) * inv : 0.0f;
         }
     }
 }
 
-template <int DPL>
+template <int DPL, int NH>
 __global__ void __launch_bounds__(128)
 attn_nbr_bwd_kernel(const NbrArgs p) {
     extern __shared__ float smem[];
+    constexpr int d = 32 * DPL;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int64_t warp = (int64_t)blockIdx.x * wpb + wib;
     const int64_t nwarps = (int64_t)gridDim.x * wpb;
-    const int d = p.d, F = p.F, H = p.H, n = p.n;
-    const int sw = 3 * d + 32;                          // stash row: [h | cos | sin | e(32)]
+    const int F = p.F, n = p.n, ekp = p.ekp;
+    constexpr int sw = 3 * d + 32;                      // stash row: [h | cos | sin | e(32)]
     float* stash = smem + (size_t)wib * n * sw;
     float* red = smem + (size_t)wpb * n * sw;           // [wpb][2][d] for the block reduction
     const int c0 = lane * DPL;
@@ -141,94 +193,117 @@ attn_nbr_bwd_kernel(const NbrArgs p) {
     for (int i = 0; i < DPL; ++i) { tw[i] = p.tw[c0 + i]; tb[i] = p.tb[c0 + i]; dwl[i] = 0.f; dbl[i] = 0.f; }
     for (int64_t q = warp; q < p.Q; q += nwarps) {
         const bool dead = p.invalid[q] != 0;
-        float qa[kMaxHeads][DPL], qg[kMaxHeads][DPL], qe[kMaxHeads];
-        float ga[kMaxHeads][DPL], gg[kMaxHeads][DPL], ge[kMaxHeads], gp[kMaxHeads];
-        float da[kMaxHeads][DPL], dg[kMaxHeads][DPL], de[kMaxHeads];
-        float pj[kMaxHeads], dpj[kMaxHeads];
+        int id_l = -1, ei_l = 0;
+        float dt_l = 0.0f;
+        if (lane < n && !dead) {
+            id_l = __ldg(p.idx + q * n + lane);
+            dt_l = __ldg(p.dt + q * n + lane);
+            ei_l = __ldg(p.eidx + q * n + lane);
+        }
+        float qa[NH][DPL], qg[NH][DPL];
+        float ga[NH][DPL], gg[NH][DPL], ge[NH], gp[NH];
+        float da[NH][DPL], dg[NH][DPL], de[NH];
+        float pj[NH], pk[NH], dpj[NH];
 #pragma unroll
-        for (int h = 0; h < kMaxHeads; ++h) {
-            if (h < H) {
-                const float* qk = p.QK + (q * H + h) * p.ekp;
-                const float* gx = p.dXB + (q * H + h) * p.ekp;
+        for (int h = 0; h < NH; ++h) {
+            const float* qk = p.QK + (q * NH + h) * ekp;
+            const float* gx = p.dXB + q * p.lddxb + (int64_t)h * ekp;
+            ld_cols<DPL>(qk + c0, qa[h]);
+            ld_cols<DPL>(gx + c0, ga[h]);
 #pragma unroll
-                for (int i = 0; i < DPL; ++i) {
-                    qa[h][i] = qk[c0 + i]; qg[h][i] = qk[d + F + c0 + i];
-                    ga[h][i] = gx[c0 + i]; gg[h][i] = gx[d + F + c0 + i];
-                    da[h][i] = 0.f; dg[h][i] = 0.f;
-                }
-                qe[h] = lane < F ? qk[d + lane] : 0.0f;
-                ge[h] = lane < F ? gx[d + lane] : 0.0f;
-                gp[h] = gx[2 * d + F];
-                de[h] = 0.f;
-                pj[h] = (lane < n) ? p.P[(q * H + h) * n + lane] : 0.0f;
-                dpj[h] = 0.f;
+            for (int i = 0; i < DPL; ++i) {
+                qg[h][i] = qk[d + F + c0 + i];
+                gg[h][i] = gx[d + F + c0 + i];
+                da[h][i] = 0.f; dg[h][i] = 0.f;
             }
+            ge[h] = lane < F ? gx[d + lane] : 0.0f;
+            gp[h] = gx[2 * d + F];
+            de[h] = 0.f;
+            pj[h] = (lane < n) ? p.P[(q * NH + h) * n + lane] : 0.0f;
+            const float keep = (id_l >= 0) ? keep_scale(p, step, q, h, lane) : 1.0f;
+            pk[h] = pj[h] * keep;                       // softmax weight after dropout (what multiplied x_j forward)
+            dpj[h] = keep;                              // holds the factor until pass A overwrites it with dp_hj
         }
         if (!dead) {
-            // pass A: rebuild x_j, stash it, dp_hj = dXB_h . [x_j | 1]
-            for (int j = 0; j < n; ++j) {
-                const int id = p.idx[q * n + j];
-                if (id < 0) continue;
-                const float dtj = p.dt[q * n + j];
-                float* st = stash + j * sw;
-                const float* row = p.T + (int64_t)id * p.ldt + c0;
-                float xh[DPL], xt[DPL];
+            // pass A: rebuild x_j (kUnroll gathers in flight), stash it, dp_hj = keep_hj * (dXB_h . [x_j | 1])
+            for (int j0 = 0; j0 < n; j0 += kUnroll) {
+                int id[kUnroll];
+                float dtj[kUnroll], xe[kUnroll], xh[kUnroll][DPL];
 #pragma unroll
-                for (int i = 0; i < DPL; ++i) {
-                    float sn, cs;
-                    pfo_sincosf(fmaf(dtj, tw[i], tb[i]), &sn, &cs);
-                    xh[i] = row[i]; xt[i] = cs;
-                    st[c0 + i] = xh[i]; st[d + c0 + i] = cs; st[2 * d + c0 + i] = sn;
+                for (int u = 0; u < kUnroll; ++u) {
+                    const int j = j0 + u;
+                    id[u] = __shfl_sync(0xffffffffu, id_l, j & 31);
+                    dtj[u] = __shfl_sync(0xffffffffu, dt_l, j & 31);
+                    const int ei = __shfl_sync(0xffffffffu, ei_l, j & 31);
+                    if (j >= n) id[u] = -1;
+                    xe[u] = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < DPL; ++i) xh[u][i] = 0.0f;
+                    if (id[u] >= 0) {
+                        ld_cols<DPL>(p.T + (int64_t)id[u] * p.ldt + c0, xh[u]);
+                        if (lane < F) xe[u] = __ldg(p.efeat + (int64_t)ei * F + lane);
+                    }
                 }
-                const float xe = lane < F ? p.efeat[(int64_t)p.eidx[q * n + j] * F + lane] : 0.0f;
-                st[3 * d + lane] = xe;
 #pragma unroll
-                for (int h = 0; h < kMaxHeads; ++h) {
-                    if (h < H) {
-                        float part = ge[h] * xe;
+                for (int u = 0; u < kUnroll; ++u) {
+                    if (id[u] < 0) continue;
+                    const int j = j0 + u;
+                    float* st = stash + j * sw;
+                    float xt[DPL], sn[DPL];
 #pragma unroll
-                        for (int i = 0; i < DPL; ++i) part = fmaf(ga[h][i], xh[i], fmaf(gg[h][i], xt[i], part));
-                        const float dp = (warp_sum(part) + gp[h]) * keep_scale(p, step, q, h, j);
-                        if (lane == j) dpj[h] = dp;
+                    for (int i = 0; i < DPL; ++i) pfo_sincosf(fmaf(dtj[u], tw[i], tb[i]), &sn[i], &xt[i]);
+                    st_cols<DPL>(st + c0, xh[u]);
+                    st_cols<DPL>(st + d + c0, xt);
+                    st_cols<DPL>(st + 2 * d + c0, sn);
+                    st[3 * d + lane] = xe[u];
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) {
+                        float part = ge[h] * xe[u];
+#pragma unroll
+                        for (int i = 0; i < DPL; ++i) part = fmaf(ga[h][i], xh[u][i], fmaf(gg[h][i], xt[i], part));
+                        const float dp = warp_sum(part) + gp[h];
+                        if (lane == j) dpj[h] *= dp;
                     }
                 }
             }
             __syncwarp();
             // softmax backward: ds_hj = p_hj (dp_hj - sum_j' p_hj' dp_hj')
-            float dsj[kMaxHeads];
+            float dsj[NH];
 #pragma unroll
-            for (int h = 0; h < kMaxHeads; ++h)
-                if (h < H) { const float dot = warp_sum(pj[h] * dpj[h]); dsj[h] = pj[h] * (dpj[h] - dot); }
+            for (int h = 0; h < NH; ++h) {
+                const float dpv = (id_l >= 0) ? dpj[h] : 0.0f;
+                const float dot = warp_sum(pj[h] * dpv);
+                dsj[h] = pj[h] * (dpv - dot);
+            }
             // pass B: dqk_h += ds_hj x_j ; dx_j = sum_h (p'_hj dXB_h + ds_hj qk_h)
             for (int j = 0; j < n; ++j) {
-                const int id = p.idx[q * n + j];
+                const int id = __shfl_sync(0xffffffffu, id_l, j);
                 if (id < 0) continue;
-                const float dtj = p.dt[q * n + j];
+                const float dtj = __shfl_sync(0xffffffffu, dt_l, j);
                 const float* st = stash + j * sw;
                 float xh[DPL], cs[DPL], sn[DPL], gxh[DPL], gxt[DPL];
+                ld_cols<DPL>(st + c0, xh);
+                ld_cols<DPL>(st + d + c0, cs);
+                ld_cols<DPL>(st + 2 * d + c0, sn);
 #pragma unroll
-                for (int i = 0; i < DPL; ++i) {
-                    xh[i] = st[c0 + i]; cs[i] = st[d + c0 + i]; sn[i] = st[2 * d + c0 + i];
-                    gxh[i] = 0.f; gxt[i] = 0.f;
-                }
+                for (int i = 0; i < DPL; ++i) { gxh[i] = 0.f; gxt[i] = 0.f; }
                 const float xe = st[3 * d + lane];
 #pragma unroll
-                for (int h = 0; h < kMaxHeads; ++h) {
-                    if (h < H) {
-                        const float ds = __shfl_sync(0xffffffffu, dsj[h], j);
-                        const float pw = __shfl_sync(0xffffffffu, pj[h], j) * keep_scale(p, step, q, h, j);
-                        de[h] = fmaf(ds, xe, de[h]);
+                for (int h = 0; h < NH; ++h) {
+                    const float ds = __shfl_sync(0xffffffffu, dsj[h], j);
+                    const float pw = __shfl_sync(0xffffffffu, pk[h], j);
+                    de[h] = fmaf(ds, xe, de[h]);
 #pragma unroll
-                        for (int i = 0; i < DPL; ++i) {
-                            da[h][i] = fmaf(ds, xh[i], da[h][i]);
-                            dg[h][i] = fmaf(ds, cs[i], dg[h][i]);
-                            gxh[i] += pw * ga[h][i] + ds * qa[h][i];
-                            gxt[i] += pw * gg[h][i] + ds * qg[h][i];
-                        }
+                    for (int i = 0; i < DPL; ++i) {
+                        da[h][i] = fmaf(ds, xh[i], da[h][i]);
+                        dg[h][i] = fmaf(ds, cs[i], dg[h][i]);
+                        gxh[i] += pw * ga[h][i] + ds * qa[h][i];
+                        gxt[i] += pw * gg[h][i] + ds * qg[h][i];
                     }
                 }
                 float* drow = p.dT + (int64_t)id * p.lddt + c0;
-                if (DPL == 4) red_add_f32x4(drow, gxh[0], gxh[1], gxh[2], gxh[3]);
+                if constexpr (DPL == 4) red_add_f32x4(drow, gxh[0], gxh[1], gxh[2], gxh[3]);
+                else if constexpr (DPL == 2) red_add_f32x2(drow, gxh[0], gxh[1]);
                 else {
 #pragma unroll
                     for (int i = 0; i < DPL; ++i) atomicAdd(drow + i, gxh[i]);
@@ -243,14 +318,13 @@ attn_nbr_bwd_kernel(const NbrArgs p) {
             __syncwarp();
         }
 #pragma unroll
-        for (int h = 0; h < kMaxHeads; ++h) {
-            if (h < H) {
-                float* o = p.dQK + (q * H + h) * p.ekp;
+        for (int h = 0; h < NH; ++h) {
+            float* o = p.dQK + (q * NH + h) * ekp;
+            st_cols<DPL>(o + c0, da[h]);
 #pragma unroll
-                for (int i = 0; i < DPL; ++i) { o[c0 + i] = da[h][i]; o[d + F + c0 + i] = dg[h][i]; }
-                if (lane < F) o[d + lane] = de[h];
-                if (lane < p.ekp - (2 * d + F)) o[2 * d + F + lane] = 0.0f;
-            }
+            for (int i = 0; i < DPL; ++i) o[d + F + c0 + i] = dg[h][i];
+            if (lane < F) o[d + lane] = de[h];
+            if (lane < ekp - (2 * d + F)) o[2 * d + F + lane] = 0.0f;
         }
     }
     // block reduction of the time-encoder gradients -> partial[block][2][d]
@@ -371,22 +445,44 @@ eval_score_kernel(const float* __restrict__ es, const float* __restrict__ ed, co
     }
 }
 
-template <int DPL>
+template <int DPL, int NH>
 int launch_fwd(const NbrArgs& a, cudaStream_t s) {
-    attn_nbr_fwd_kernel<DPL><<<pfo_grid(a.Q * 32, 256, 4), 256, 0, s>>>(a);
+    attn_nbr_fwd_kernel<DPL, NH><<<pfo_grid(a.Q * 32, 128, 10), 128, 0, s>>>(a);
     PFO_LAUNCH_CHECK();
 }
 
-template <int DPL>
+template <int DPL, int NH>
 int launch_bwd(const NbrArgs& a, int grid, size_t smem, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(attn_nbr_bwd_kernel<DPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(attn_nbr_bwd_kernel<DPL, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    attn_nbr_bwd_kernel<DPL><<<grid, 128, smem, s>>>(a);
+    attn_nbr_bwd_kernel<DPL, NH><<<grid, 128, smem, s>>>(a);
     PFO_LAUNCH_CHECK();
 }
+
+// (d / 32, heads) -> kernel instance; both are compile-time so the per-head state lives in registers
+template <int DPL>
+int dispatch_fwd(const NbrArgs& a, cudaStream_t s) {
+    switch (a.H) {
+        case 1: return launch_fwd<DPL, 1>(a, s);
+        case 2: return launch_fwd<DPL, 2>(a, s);
+        case 4: return launch_fwd<DPL, 4>(a, s);
+        default: return (int)cudaErrorInvalidValue;
+    }
+}
+template <int DPL>
+int dispatch_bwd(const NbrArgs& a, int grid, size_t smem, cudaStream_t s) {
+    switch (a.H) {
+        case 1: return launch_bwd<DPL, 1>(a, grid, smem, s);
+        case 2: return launch_bwd<DPL, 2>(a, grid, smem, s);
+        case 4: return launch_bwd<DPL, 4>(a, grid, smem, s);
+        default: return (int)cudaErrorInvalidValue;
+    }
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
 
@@ -394,26 +490,30 @@ PFO_API int pfo_attn_nbr_fwd(const float* QK, const float* T, int64_t ldt, const
                              const float* dt, const float* efeat, const float* tw, const float* tb,
                              int64_t Q, int n, int d, int F, int H, int ekp,
                              float p_drop, uint64_t seed, uint32_t step, const uint32_t* step_dev,
-                             float* XB, float* P, int32_t* invalid, void* stream) {
+                             float* XB, int64_t ldxb, float* P, int32_t* invalid, void* stream) {
     if (Q <= 0) return 0;
-    if (d % 32 != 0 || d > 128 || F > 32 || H > kMaxHeads || n > 32 || n < 1) return (int)cudaErrorInvalidValue;
+    if (d % 32 != 0 || d > 128 || F > 32 || H > kMaxHeads || n > 32 || n < 1 || ekp < 2 * d + F + 3 ||
+        ldxb < (int64_t)H * ekp)
+        return (int)cudaErrorInvalidValue;
     NbrArgs a{};
     a.QK = QK; a.T = T; a.ldt = ldt; a.idx = idx; a.eidx = eidx; a.dt = dt; a.efeat = efeat; a.tw = tw; a.tb = tb;
     a.Q = Q; a.n = n; a.d = d; a.F = F; a.H = H; a.ekp = ekp; a.p_drop = p_drop;
     a.k0 = (uint32_t)(seed & 0xffffffffu); a.k1 = (uint32_t)(seed >> 32); a.step = step; a.step_dev = step_dev;
-    a.XB = XB; a.P = P; a.invalid = invalid;
+    a.XB = XB; a.ldxb = ldxb; a.P = P; a.invalid = invalid;
     cudaStream_t s = (cudaStream_t)stream;
+    if (ldt % 4 != 0 || ldxb % 4 != 0 || ekp % 4 != 0 || !aligned16(T) || !aligned16(QK) || !aligned16(XB))
+        return (int)cudaErrorInvalidValue;             // rows are read / written with 8- and 16-byte accesses
     switch (d / 32) {
-        case 1: return launch_fwd<1>(a, s);
-        case 2: return launch_fwd<2>(a, s);
-        case 3: return launch_fwd<3>(a, s);
-        default: return launch_fwd<4>(a, s);
+        case 1: return dispatch_fwd<1>(a, s);
+        case 2: return dispatch_fwd<2>(a, s);
+        case 3: return dispatch_fwd<3>(a, s);
+        default: return dispatch_fwd<4>(a, s);
     }
 }
 
 PFO_API int64_t pfo_attn_nbr_bwd_workspace_floats(int d) { return (int64_t)2 * 148 * 4 * 2 * d; }
 
-PFO_API int pfo_attn_nbr_bwd(const float* QK, const float* dXB, const float* P, const int32_t* invalid,
+PFO_API int pfo_attn_nbr_bwd(const float* QK, const float* dXB, int64_t lddxb, const float* P, const int32_t* invalid,
                              const float* T, int64_t ldt, const int32_t* idx, const int32_t* eidx, const float* dt,
                              const float* efeat, const float* tw, const float* tb,
                              int64_t Q, int n, int d, int F, int H, int ekp,
@@ -427,19 +527,22 @@ PFO_API int pfo_attn_nbr_bwd(const float* QK, const float* dXB, const float* P, 
     a.Q = Q; a.n = n; a.d = d; a.F = F; a.H = H; a.ekp = ekp; a.p_drop = p_drop;
     a.k0 = (uint32_t)(seed & 0xffffffffu); a.k1 = (uint32_t)(seed >> 32); a.step = step; a.step_dev = step_dev;
     a.P = const_cast<float*>(P); a.invalid = const_cast<int32_t*>(invalid);
-    a.dXB = dXB; a.dQK = dQK; a.dT = dT; a.lddt = lddt; a.partial = workspace;
+    a.dXB = dXB; a.lddxb = lddxb; a.dQK = dQK; a.dT = dT; a.lddt = lddt; a.partial = workspace;
     cudaStream_t s = (cudaStream_t)stream;
     const int wpb = 4;
     const size_t smem = ((size_t)wpb * n * (3 * d + 32) + (size_t)wpb * 2 * d) * sizeof(float);
     int grid = pfo_grid(Q * 32, 128, 4);
     const int max_grid = 2 * 148 * 4;
     if (grid > max_grid) grid = max_grid;
+    if (ldt % 4 != 0 || lddxb % 4 != 0 || lddt % 4 != 0 || ekp % 4 != 0 || !aligned16(T) || !aligned16(QK) ||
+        !aligned16(dXB) || !aligned16(dQK) || !aligned16(dT))
+        return (int)cudaErrorInvalidValue;
     int rc;
     switch (d / 32) {
-        case 1: rc = launch_bwd<1>(a, grid, smem, s); break;
-        case 2: rc = launch_bwd<2>(a, grid, smem, s); break;
-        case 3: rc = launch_bwd<3>(a, grid, smem, s); break;
-        default: rc = launch_bwd<4>(a, grid, smem, s); break;
+        case 1: rc = dispatch_bwd<1>(a, grid, smem, s); break;
+        case 2: rc = dispatch_bwd<2>(a, grid, smem, s); break;
+        case 3: rc = dispatch_bwd<3>(a, grid, smem, s); break;
+        default: rc = dispatch_bwd<4>(a, grid, smem, s); break;
     }
     if (rc) return rc;
     return pfo_reduce_partials(workspace, grid, 2 * d, dtw_dtb, accumulate, stream);

@@ -201,7 +201,20 @@ PFO_API int pfo_linear_bf16(const float* A, int64_t lda, const int32_t* a_idx, c
                             float alpha, int act, const int32_t* row_zero, const float* relu_gate, int64_t ld_gate,
                             int accumulate, void* stream) {
     if (M <= 0 || N <= 0) return 0;
-    if (N > 256 || K > 512) return (int)cudaErrorInvalidValue;
+    if (K > 512) return (int)cudaErrorInvalidValue;
+    if (N > 256) {          // one accumulator holds 256 columns: wider outputs go panel by panel
+        const int panels = (N + 255) / 256;
+        const int np = ((N + panels - 1) / panels + 15) / 16 * 16;
+        for (int n0 = 0; n0 < N; n0 += np) {
+            const int nn = N - n0 < np ? N - n0 : np;
+            int rc = pfo_linear_bf16(A, lda, a_idx, w_transposed ? W + n0 : W + (int64_t)n0 * ldw, ldw, w_transposed,
+                                     bias ? bias + n0 : nullptr, bias_row_scale, ld_brs, C + n0, ldc, M, m_dev, nn, K,
+                                     alpha, act, row_zero, relu_gate ? relu_gate + n0 : nullptr, ld_gate, accumulate,
+                                     stream);
+            if (rc) return rc;
+        }
+        return 0;
+    }
     TcArgs a{A, lda, a_idx, W, ldw, w_transposed, bias, bias_row_scale, ld_brs, C, ldc, M, m_dev, N, K,
              alpha, act, row_zero, relu_gate, ld_gate, accumulate, 0, 0, 0};
     a.NP = (N + 15) / 16 * 16;

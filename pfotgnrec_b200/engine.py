@@ -46,8 +46,12 @@ class ModelConfig:
         return 2 * self.d + self.n_edge_feat
 
     @property
-    def ekp(self):
-        return (self.Ek + 1 + 3) // 4 * 4
+    def ekp(self):              # per-head row of QK / XB: [h | e | te | psum | valid | one | 0..], 16-byte multiple
+        return (self.Ek + 3 + 3) // 4 * 4
+
+    @property
+    def ldcat(self):            # operand row of the merge GEMM: [XB (H * ekp) | h_query (d)]
+        return self.n_heads * self.ekp + self.d
 
     @property
     def raw(self):              # raw message width
@@ -153,8 +157,8 @@ F4 = 4  # sizeof(float)
 
 class _LayerTape:
     """Everything one attention-layer invocation saves for its backward."""
-    __slots__ = ("layer", "M", "n", "Tq", "qidx", "T", "idx", "eidx", "dt", "CAT", "QP", "QK", "XB", "P",
-                 "invalid", "ATT", "H1", "out_rows", "child_q", "child_n", "dTq", "dT", "step")
+    __slots__ = ("layer", "M", "n", "Tq", "qidx", "T", "idx", "eidx", "dt", "CAT", "QK", "P",
+                 "invalid", "H1", "out_rows", "child_q", "child_n", "dTq", "dT", "step")
 
 
 class TGNEngine:
@@ -212,25 +216,59 @@ class TGNEngine:
             flat += [params[pre + "weight_ih"].contiguous(), params[pre + "weight_hh"].contiguous(),
                      params[pre + "bias_ih"].contiguous(), params[pre + "bias_hh"].contiguous()]
         if c.embedding == "graph_attention":
-            te0 = torch.cos(tb)                                  # TimeEncode(0) (embedding_module.py:92)
-            for l in range(c.n_layers):
-                a = f"embedding_module.attention_models.{l}."
-                Wq = params[a + "multi_head_target.q_proj_weight"]
-                Wk = params[a + "multi_head_target.k_proj_weight"]
-                Wv = params[a + "multi_head_target.v_proj_weight"]
-                b_in = params[a + "multi_head_target.in_proj_bias"]
-                cq = Wq[:, d:] @ te0 + b_in[:E]                  # query bias incl. the constant time part
-                WvA = torch.cat([Wv.view(H, hd, Ek), b_in[2 * E:].view(H, hd, 1),
-                                 Wv.new_zeros(H, hd, c.ekp - Ek - 1)], dim=2)
-                flat += [Wq.contiguous(), cq.contiguous(), Wk.contiguous(), WvA.contiguous(),
-                         params[a + "multi_head_target.out_proj.weight"].contiguous(),
-                         params[a + "multi_head_target.out_proj.bias"].contiguous(),
-                         params[a + "merger.fc1.weight"].contiguous(), params[a + "merger.fc1.bias"].contiguous(),
-                         params[a + "merger.fc2.weight"].contiguous(), params[a + "merger.fc2.bias"].contiguous()]
+            flat += self._fold_attention(params, tb)
         elif c.embedding == "time":
             flat += [params["embedding_module.embedding_layer.weight"].reshape(d).contiguous(),
                      params["embedding_module.embedding_layer.bias"].contiguous()]
         return flat
+
+    def _fold_attention(self, params, tb):
+        """Per layer, the five GEMM operands the kernels consume, folded from the reference's ten tensors with
+        differentiable fp64 torch ops on the (tiny) weights -- autograd carries the gradients back:
+
+          Wqk  [H*ekp, d], cqk [H*ekp]   qk_h = (scale Wk_h^T Wq_h[:, :d]) h_q + scale Wk_h^T (Wq_h[:, d:] te(0) + bq_h)
+          Wc1T [H*ekp + d, d]            fc1([out_proj(attn) | h_q]) as ONE contraction over [XB | h_q]:
+                                         rows of head h = (W1a Wo_h [Wv_h | bv_h])^T, then the `valid` row = W1a bo
+                                         (out-proj bias, valid rows only) and the `one` row = b1; last d rows = W1b^T
+          W2, b2                         fc2
+        K/V projections, the query projection, the out-projection and fc1 never materialise per query
+        (model/temporal_attention.py:52-90, utils/utils.py:14-17)."""
+        c = self.cfg
+        d, E, Ek, H, ekp = c.d, c.E, c.Ek, c.n_heads, c.ekp
+        hd = E // H
+        scale = 1.0 / math.sqrt(hd)
+        D = torch.float64
+        te0 = torch.cos(tb).to(D)                                # TimeEncode(0) (embedding_module.py:92)
+        out = []
+        for l in range(c.n_layers):
+            a = f"embedding_module.attention_models.{l}."
+            Wq = params[a + "multi_head_target.q_proj_weight"].to(D)
+            Wk = params[a + "multi_head_target.k_proj_weight"].to(D).view(H, hd, Ek)
+            Wv = params[a + "multi_head_target.v_proj_weight"].to(D).view(H, hd, Ek)
+            b_in = params[a + "multi_head_target.in_proj_bias"].to(D)
+            Wo = params[a + "multi_head_target.out_proj.weight"].to(D)
+            bo = params[a + "multi_head_target.out_proj.bias"].to(D)
+            W1 = params[a + "merger.fc1.weight"].to(D)
+            b1 = params[a + "merger.fc1.bias"].to(D)
+            cq = Wq[:, d:] @ te0 + b_in[:E]
+            WkT = Wk.transpose(1, 2)                             # [H, Ek, hd]
+            A = scale * (WkT @ Wq[:, :d].view(H, hd, d))         # [H, Ek, d]
+            cA = scale * (WkT @ cq.view(H, hd, 1)).squeeze(2)    # [H, Ek]
+            Wqk = torch.nn.functional.pad(A, (0, 0, 0, ekp - Ek)).reshape(H * ekp, d)
+            cqk = torch.nn.functional.pad(cA, (0, ekp - Ek)).reshape(H * ekp)
+            WvA = torch.cat([Wv, b_in[2 * E:].view(H, hd, 1)], dim=2)          # [H, hd, Ek+1]
+            WoH = Wo.view(E, H, hd).permute(1, 0, 2)             # [H, E, hd]
+            W1a, W1b = W1[:, :E], W1[:, E:]
+            Bh = W1a @ (WoH @ WvA)                               # [H, d, Ek+1]
+            tail0 = torch.cat([(W1a @ bo).unsqueeze(0), b1.unsqueeze(0), Bh.new_zeros(ekp - Ek - 3, d)], dim=0)
+            tailz = Bh.new_zeros(ekp - Ek - 1, d)
+            rows = []
+            for h in range(H):
+                rows += [Bh[h].t(), tail0 if h == 0 else tailz]
+            Wc1T = torch.cat(rows + [W1b.t()], dim=0)            # [H*ekp + d, d]
+            out += [Wqk.float().contiguous(), cqk.float().contiguous(), Wc1T.float().contiguous(),
+                    params[a + "merger.fc2.weight"].contiguous(), params[a + "merger.fc2.bias"].contiguous()]
+        return out
 
     # ------------------------------------------------------------------ public step
     def compute_temporal_embeddings(self, params, src, dst, extra_groups, ts, eidx, n_neighbors,
@@ -357,7 +395,7 @@ class TGNEngine:
         dev = self.device
         layer, M = tree["layer"], tree["M"]
         n = tree["nbr"].shape[1]
-        Wq, cq, Wk, WvA, Wo, bo, W1, b1, W2, b2 = W[layer - 1]
+        Wqk, cqk, Wc1T, W2, b2 = W[layer - 1]
         tp = _LayerTape()
         tp.layer, tp.M, tp.n = layer, M, n
         tp.child_q = tp.child_n = None
@@ -371,31 +409,21 @@ class TGNEngine:
             tp.Tq, tp.qidx = out_q, torch.arange(M, dtype=torch.int32, device=dev)
             tp.T, tp.idx = out_n, torch.where(tree["nbr"] == 0, torch.full_like(ar, -1), ar)
         tp.eidx, tp.dt = tree["eidx"], tree["dt"]
-        ldc = E + d
+        ldc, hq = c.ldcat, H * ekp                  # CAT row = [XB (H*ekp) | h_query (d)]
         tp.CAT = torch.empty(M, ldc, device=dev)
-        _lib.call("pfo_gather_rows", ptr(tp.Tq), d, ptr(tp.qidx), M, d, tp.CAT.data_ptr() + E * F4, ldc)
-        scale = 1.0 / math.sqrt(hd)
-        tp.QP = torch.empty(M, E, device=dev)
-        _linear(c, tp.CAT.data_ptr() + E * F4, ldc, None, ptr(Wq), E, 0, ptr(cq), ptr(tp.QP), E, M, E, d, alpha=scale)
-        tp.QK = torch.empty(M, H, ekp, device=dev)
-        for h in range(H):          # qk_h = Wk_h^T q_h  (weight absorption, see attention_kernels.cu)
-            _linear(c, tp.QP.data_ptr() + h * hd * F4, E, None, Wk.data_ptr() + h * hd * Ek * F4, Ek, 1, None,
-                    tp.QK.data_ptr() + h * ekp * F4, H * ekp, M, Ek, hd)
-        tp.XB = torch.empty(M, H, ekp, device=dev)
+        hq_ptr = tp.CAT.data_ptr() + hq * F4
+        _lib.call("pfo_gather_rows", ptr(tp.Tq), d, ptr(tp.qidx), M, d, hq_ptr, ldc)
+        tp.QK = torch.empty(M, H, ekp, device=dev)  # qk_h = Wk_h^T q_h for both heads: one contraction over h_query
+        _linear(c, hq_ptr, ldc, None, ptr(Wqk), d, 0, ptr(cqk), ptr(tp.QK), hq, M, hq, d)
         tp.P = torch.empty(M, H, n, device=dev)
         tp.invalid = torch.empty(M, dtype=torch.int32, device=dev)
         tp.step = layer
         p_drop = c.dropout if save["train"] else 0.0
         _lib.call("pfo_attn_nbr_fwd", ptr(tp.QK), ptr(tp.T), d, ptr(tp.idx), ptr(tp.eidx), ptr(tp.dt),
                   ptr(self.edge_feat), ptr(save["tw"]), ptr(save["tb"]), M, n, d, F, H, ekp,
-                  float(p_drop), self.seed, tp.step, ptr(self.step_ctr), ptr(tp.XB), ptr(tp.P), ptr(tp.invalid))
-        tp.ATT = torch.empty(M, E, device=dev)
-        for h in range(H):          # attn_h = Wv_h xbar_h + bv_h * psum_h
-            _linear(c, tp.XB.data_ptr() + h * ekp * F4, H * ekp, None, WvA.data_ptr() + h * hd * ekp * F4, ekp, 0,
-                    None, tp.ATT.data_ptr() + h * hd * F4, E, M, hd, Ek + 1)
-        _linear(c, ptr(tp.ATT), E, None, ptr(Wo), E, 0, ptr(bo), ptr(tp.CAT), ldc, M, E, E, row_zero=ptr(tp.invalid))
-        tp.H1 = torch.empty(M, d, device=dev)
-        _linear(c, ptr(tp.CAT), ldc, None, ptr(W1), ldc, 0, ptr(b1), ptr(tp.H1), d, M, d, ldc, act=1)
+                  float(p_drop), self.seed, tp.step, ptr(self.step_ctr), ptr(tp.CAT), ldc, ptr(tp.P), ptr(tp.invalid))
+        tp.H1 = torch.empty(M, d, device=dev)       # relu(fc1([out_proj(attn) | h_query])), biases folded into Wc1T
+        _linear(c, ptr(tp.CAT), ldc, None, ptr(Wc1T), d, 1, None, ptr(tp.H1), d, M, d, ldc, act=1)
         # the output is NOT kept on the tape: it is the autograd output, and holding it from the
         # backward context would form a reference cycle that only the cyclic GC can free
         out = torch.empty(M, d, device=dev)
@@ -404,58 +432,35 @@ class TGNEngine:
         return out, tp
 
     def _attention_backward(self, tp, dOUT, W, dW, save):
-        """Accumulates parameter grads into dW[layer-1] and feature grads into tp.dTq / tp.dT."""
+        """Accumulates the folded-operand grads into dW[layer-1] and feature grads into tp.dTq / tp.dT."""
         c = self.cfg
-        d, E, Ek, H, ekp, F = c.d, c.E, c.Ek, c.n_heads, c.ekp, c.n_edge_feat
-        hd = E // H
+        d, H, ekp, F = c.d, c.n_heads, c.ekp, c.n_edge_feat
         dev = self.device
         M, n = tp.M, tp.n
-        ldc = E + d
-        Wq, cq, Wk, WvA, Wo, bo, W1, b1, W2, b2 = W[tp.layer - 1]
-        gWq, gcq, gWk, gWvA, gWo, gbo, gW1, gb1, gW2, gb2 = dW[tp.layer - 1]
-        scale = 1.0 / math.sqrt(hd)
+        ldc, hq = c.ldcat, H * ekp
+        Wqk, cqk, Wc1T, W2, b2 = W[tp.layer - 1]
+        gWqk, gcqk, gWc1T, gW2, gb2 = dW[tp.layer - 1]
         ws = self.ws
-        f32 = c                                         # dgrad follows the GEMM mode; wgrad always accumulates in fp32
-        # merge MLP
+        hq_ptr = tp.CAT.data_ptr() + hq * F4
+        # merge MLP: fc2, then fc1 straight down to [dXB | dh_query]
         dH1 = torch.empty(M, d, device=dev)
-        _linear(f32, ptr(dOUT), d, None, ptr(W2), d, 1, None, ptr(dH1), d, M, d, d, relu_gate=ptr(tp.H1), ld_gate=d)
+        _linear(c, ptr(dOUT), d, None, ptr(W2), d, 1, None, ptr(dH1), d, M, d, d, relu_gate=ptr(tp.H1), ld_gate=d)
         _wgrad(c, ws, ptr(dOUT), d, ptr(tp.H1), d, None, M, d, d, ptr(gW2), d, ptr(gb2), accumulate=1)
         dCAT = torch.empty(M, ldc, device=dev)
-        _linear(f32, ptr(dH1), d, None, ptr(W1), ldc, 1, None, ptr(dCAT), ldc, M, ldc, d)
-        _wgrad(c, ws, ptr(dH1), d, ptr(tp.CAT), ldc, None, M, d, ldc, ptr(gW1), ldc, ptr(gb1), accumulate=1)
-        # rows without neighbours had their attention output zeroed (temporal_attention.py:84)
-        dCAT[:, :E].masked_fill_((tp.invalid != 0).unsqueeze(1), 0.0)
-        _wgrad(c, ws, ptr(dCAT), ldc, ptr(tp.ATT), E, None, M, E, E, ptr(gWo), E, ptr(gbo), accumulate=1)
-        dATT = torch.empty(M, E, device=dev)
-        _linear(f32, ptr(dCAT), ldc, None, ptr(Wo), E, 1, None, ptr(dATT), E, M, E, E)
-        dXB = torch.empty(M, H, ekp, device=dev)
-        for h in range(H):
-            _linear(f32, dATT.data_ptr() + h * hd * F4, E, None, WvA.data_ptr() + h * hd * ekp * F4, ekp, 1, None,
-                    dXB.data_ptr() + h * ekp * F4, H * ekp, M, Ek + 1, hd)
-            _wgrad(c, ws, dATT.data_ptr() + h * hd * F4, E, tp.XB.data_ptr() + h * ekp * F4, H * ekp, None, M, hd, Ek + 1,
-                   gWvA.data_ptr() + h * hd * ekp * F4, ekp, None, accumulate=1)
+        _linear(c, ptr(dH1), d, None, ptr(Wc1T), d, 0, None, ptr(dCAT), ldc, M, ldc, d)
+        # gWc1T[k, :] = sum_m CAT[m, k] dH1[m, :]  (rows without neighbours carry XB = 0, valid = 0)
+        _wgrad(c, ws, ptr(tp.CAT), ldc, ptr(dH1), d, None, M, ldc, d, ptr(gWc1T), d, None, accumulate=1)
         dQK = torch.empty(M, H, ekp, device=dev)
         nws = ws.get(_lib.query("pfo_attn_nbr_bwd_workspace_floats", d))
         p_drop = c.dropout if save["train"] else 0.0
-        _lib.call("pfo_attn_nbr_bwd", ptr(tp.QK), ptr(dXB), ptr(tp.P), ptr(tp.invalid), ptr(tp.T), d, ptr(tp.idx),
+        _lib.call("pfo_attn_nbr_bwd", ptr(tp.QK), ptr(dCAT), ldc, ptr(tp.P), ptr(tp.invalid), ptr(tp.T), d, ptr(tp.idx),
                   ptr(tp.eidx), ptr(tp.dt), ptr(self.edge_feat), ptr(save["tw"]), ptr(save["tb"]),
                   M, n, d, F, H, ekp, float(p_drop), self.seed, tp.step, ptr(self.step_ctr), ptr(dQK), ptr(tp.dT), d,
                   ptr(save["g_twtb"]), 1, ptr(nws))
-        dQP = torch.empty(M, E, device=dev)
-        for h in range(H):
-            _linear(f32, dQK.data_ptr() + h * ekp * F4, H * ekp, None, Wk.data_ptr() + h * hd * Ek * F4, Ek, 0, None,
-                    dQP.data_ptr() + h * hd * F4, E, M, hd, Ek)
-            _wgrad(c, ws, tp.QP.data_ptr() + h * hd * F4, E, dQK.data_ptr() + h * ekp * F4, H * ekp, None, M, hd, Ek,
-                   gWk.data_ptr() + h * hd * Ek * F4, Ek, None, accumulate=1)
-        # q = scale * (Wq[:, :d] h_q + cq)
-        tmpW = torch.zeros(E, d, device=dev)
-        tmpb = torch.zeros(E, device=dev)
-        _wgrad(c, ws, ptr(dQP), E, tp.CAT.data_ptr() + E * F4, ldc, None, M, E, d, ptr(tmpW), d, ptr(tmpb))
-        gWq[:, :d].add_(tmpW, alpha=scale)
-        gcq.add_(tmpb, alpha=scale)
-        _linear(f32, ptr(dQP), E, None, ptr(Wq), E, 1, None, dCAT.data_ptr() + E * F4, ldc, M, d, E,
-                alpha=scale, accumulate=1)
-        _lib.call("pfo_scatter_add_rows", dCAT.data_ptr() + E * F4, ldc, ptr(tp.qidx), M, d, ptr(tp.dTq), d)
+        dhq_ptr = dCAT.data_ptr() + hq * F4
+        _linear(c, ptr(dQK), hq, None, ptr(Wqk), d, 1, None, dhq_ptr, ldc, M, d, hq, accumulate=1)
+        _wgrad(c, ws, ptr(dQK), hq, hq_ptr, ldc, None, M, hq, d, ptr(gWqk), d, ptr(gcqk), accumulate=1)
+        _lib.call("pfo_scatter_add_rows", dhq_ptr, ldc, ptr(tp.qidx), M, d, ptr(tp.dTq), d)
 
 
 class TGNStepFunction(torch.autograd.Function):
@@ -471,7 +476,7 @@ class TGNStepFunction(torch.autograd.Function):
         cellW = [next(it) for _ in range(4)] if c.use_memory else None
         layerW, embW = [], None
         if c.embedding == "graph_attention":
-            layerW = [[next(it) for _ in range(10)] for _ in range(c.n_layers)]
+            layerW = [[next(it) for _ in range(5)] for _ in range(c.n_layers)]
         elif c.embedding == "time":
             embW = [next(it), next(it)]
         q_nodes, q_ts, n, B = batch["q_nodes"], batch["q_ts"], batch["n"], batch["B"]
@@ -538,7 +543,7 @@ class TGNStepFunction(torch.autograd.Function):
         g_cell = [next(it) for _ in range(4)] if c.use_memory else None
         g_layers, g_emb = [], None
         if c.embedding == "graph_attention":
-            g_layers = [[next(it) for _ in range(10)] for _ in range(c.n_layers)]
+            g_layers = [[next(it) for _ in range(5)] for _ in range(c.n_layers)]
         elif c.embedding == "time":
             g_emb = [next(it), next(it)]
         u_max = pk["u_max"]

@@ -87,7 +87,7 @@ def test_dropout_stream_is_keyed_by_the_device_step_counter():
     from pfotgnrec_b200._lib import ptr
     g = torch.Generator(device="cuda").manual_seed(0)
     Q, n, d, F, H = 257, 10, 64, 1, 2
-    ekp = (2 * d + F + 1 + 3) // 4 * 4
+    ekp = (2 * d + F + 3 + 3) // 4 * 4
     T = torch.randn(500, d, device="cuda", generator=g)
     QK = torch.randn(Q, H, ekp, device="cuda", generator=g) * 0.2
     idx = torch.randint(-1, 500, (Q, n), device="cuda", generator=g, dtype=torch.int32)
@@ -102,7 +102,7 @@ def test_dropout_stream_is_keyed_by_the_device_step_counter():
         inv = torch.empty(Q, dtype=torch.int32, device="cuda")
         c = torch.tensor([ctr], dtype=torch.int32, device="cuda")
         _lib.call("pfo_attn_nbr_fwd", ptr(QK), ptr(T), d, ptr(idx), ptr(eidx), ptr(dt), ptr(ef), ptr(tw), ptr(tb),
-                  Q, n, d, F, H, ekp, float(p_drop), 7, step, ptr(c), ptr(XB), ptr(P), ptr(inv))
+                  Q, n, d, F, H, ekp, float(p_drop), 7, step, ptr(c), ptr(XB), H * ekp, ptr(P), ptr(inv))
         torch.cuda.synchronize()
         return XB.cpu().numpy()
 
