@@ -11,9 +11,10 @@
 //              into a ring of shared-memory stages (mbarrier full/empty handshake)
 //   warp 1     MMA issuer: one elected lane issues tcgen05.mma (M=128, N=NT, K=8 per instruction),
 //              accumulating in TMEM; tcgen05.commit releases the stage / publishes the accumulator
-//   warps 2-5  epilogue: tcgen05.ld of their 32 TMEM lanes, transposed through shared memory so
-//              that bias / relu / gate / row-mask / accumulate and the stores are coalesced
-//   warps 6-9  (3-pass mode only) operand splitters, see below
+//   warps 2-9  epilogue: tcgen05.ld of their 32 TMEM lanes (lane = output row), bias / scale / relu / row-mask in
+//              registers, a swizzled staging tile per 16-column slab, then coalesced 16-byte stores (relu gate
+//              and accumulate applied there); two warps per lane quarter so the schedulers can hide latency
+//   warps 10-17 (3-pass mode only) operand splitters, see below
 //
 // passes = 1: plain TF32 (10-bit mantissa), the "fast" mode (2e-2 contract, in practice ~1e-3).
 // passes = 3: error-compensated 3xTF32 for the 1e-5 contract: a = a_hi + a_lo with a_hi =
@@ -37,8 +38,7 @@ constexpr int TM = 128;                      // rows per tile = UMMA_M (cta_grou
 constexpr int CK = 32;                       // fp32 columns per K chunk = one 128-byte swizzle row
 constexpr int CHUNK_BYTES = TM * CK * 4;     // 16 KiB
 constexpr int MAX_STAGES = 8;
-constexpr int EPI_LD = 36;                   // padded row of the per-warp transposition buffer
-constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
+constexpr int EPI_BYTES = 8 * 32 * 64;        // per epilogue warp: one 32-row x 64-byte swizzled staging tile
 constexpr int SMEM_LIMIT = 232448;           // 227 KiB opt-in maximum per CTA
 
 struct TmaLinArgs {
@@ -53,9 +53,11 @@ struct TmaLinArgs {
     int stages;
     int tmem_cols;     // allocated TMEM columns (power of two >= 2 * NT)
     int vec_ok;        // C / relu_gate rows are 16-byte aligned
+    long long* trace;  // diagnostic timeline of CTA (0,0) (tools/linear_trace.py); null in normal use
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+#define PFO_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[(slot)] = clock64(); } while (0)
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
@@ -116,25 +118,37 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         : "r"(taddr));
 }
 
+constexpr int EPI_WARPS = 8;                         // two per TMEM lane quarter
+constexpr int SPLIT_WARPS = 8;                       // operand splitters of the 3-pass mode
+constexpr int THREADS_1 = 32 * (2 + EPI_WARPS), THREADS_3 = THREADS_1 + 32 * SPLIT_WARPS;
+
+// A-operand producer state: walks (tile, chunk) in order; shared by the pre-issue before the weight staging
+// and the steady-state loop after it
+struct Producer {
+    int stage; uint32_t phase; int64_t tile; int c;
+};
+
 template <int PASSES>
-__global__ void __launch_bounds__(PASSES == 3 ? 320 : 192, 1)
+__global__ void __launch_bounds__(PASSES == 3 ? THREADS_3 : THREADS_1, 1)
 linear_tma_kernel(const __grid_constant__ CUtensorMap tmA, const TmaLinArgs p) {
     extern __shared__ uint8_t smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NT = p.NT, KP8 = p.KP8, stages = p.stages, n_chunks = p.n_chunks;
     const int n0 = blockIdx.y * NT;
+    if (tid == 0) PFO_TRACE(0);
 
-    // ---- carve shared memory (stages need 1024-byte alignment for the 128-byte swizzle)
+    // ---- carve shared memory (stages and the store staging need 1024-byte alignment for the 128-byte swizzle)
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
     uint8_t* base = smem_raw + pad;
     uint8_t* sA = base;                                            // [stages][16 KiB]  A (hi)
     uint8_t* sAlo = sA + (size_t)stages * CHUNK_BYTES;             // [stages][16 KiB]  A lo (3-pass)
-    uint8_t* sW = sAlo + (PASSES == 3 ? (size_t)stages * CHUNK_BYTES : 0);
+    uint8_t* sOut = sAlo + (PASSES == 3 ? (size_t)stages * CHUNK_BYTES : 0);   // [EPI_WARPS][32 rows x 64 B]
+    uint8_t* sW = sOut + EPI_BYTES;
     const uint32_t w_bytes = (uint32_t)NT * KP8 * 4;               // [KP8/4][NT/8][8 rows][16 B]
     uint8_t* sWlo = sW + w_bytes;
-    float* sEpi = reinterpret_cast<float*>(sWlo + (PASSES == 3 ? w_bytes : 0));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sEpi) + EPI_BYTES);
+    float* sBias = reinterpret_cast<float*>(sWlo + (PASSES == 3 ? w_bytes : 0));   // [NT]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + NT);
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto ready_bar = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
@@ -150,10 +164,10 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tmA, const TmaLinArgs p) {
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(ready_bar(s), 4);
+            mbar_init(ready_bar(s), SPLIT_WARPS);
             mbar_init(empty_bar(s), 1);
         }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -161,27 +175,68 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tmA, const TmaLinArgs p) {
                      :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // ---- stage the weight slice once: rna(w) (and the residual) into core-matrix order
+    __syncthreads();                                               // barriers initialised
+
+    // ---- the activation stream does not depend on the weights: fill the ring before staging them
+    Producer pr{0, 0u, (int64_t)blockIdx.x, 0};
+    auto produce = [&](int max_chunks) {
+        int issued = 0;
+        while (pr.tile < n_tiles && issued < max_chunks) {
+            mbar_wait(empty_bar(pr.stage), pr.phase ^ 1u);
+            mbar_arrive_expect_tx(full_bar(pr.stage), CHUNK_BYTES);
+            tma_load_2d(smem_u32(sA + (size_t)pr.stage * CHUNK_BYTES), &tmA, pr.c * CK, (int)(pr.tile * TM), full_bar(pr.stage));
+            ++issued;
+            if (++pr.stage == stages) { pr.stage = 0; pr.phase ^= 1u; }
+            if (++pr.c == n_chunks) { pr.c = 0; pr.tile += gridDim.x; }
+        }
+    };
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        PFO_TRACE(8);
+        produce(stages);
+    }
+    // ---- stage the weight slice once: rna(w) (and the residual) into core-matrix order; consecutive threads
+    // take consecutive output columns n, so the 16-byte shared-memory writes of a warp are contiguous
     {
         const int kcs = KP8 >> 2;                                  // 16-byte units along K
+        const bool vec = !p.w_transposed && (p.ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.W) & 15) == 0);
         const int units = NT * kcs;
-        for (int i = tid; i < units; i += blockDim.x) {
-            int n, kc;
-            if (p.w_transposed) { n = i % NT; kc = i / NT; } else { kc = i % kcs; n = i / kcs; }
-            float hi[4], lo[4];
+        constexpr int U = 4;                                       // units in flight per thread
+        for (int i0 = tid; i0 < units; i0 += U * blockDim.x) {
+            float w[U][4];
+            int nn[U], kk[U];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int k = kc * 4 + j, ng = n0 + n;
-                float w = 0.0f;
-                if (ng < p.N && k < p.K)
-                    w = p.w_transposed ? __ldg(p.W + (int64_t)k * p.ldw + ng) : __ldg(p.W + (int64_t)ng * p.ldw + k);
-                hi[j] = rna_tf32(w);
-                lo[j] = w - hi[j];
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * blockDim.x;
+                nn[u] = i % NT; kk[u] = i / NT;
+                const int ng = n0 + nn[u], kc = kk[u];
+                w[u][0] = w[u][1] = w[u][2] = w[u][3] = 0.f;
+                if (i < units && ng < p.N) {
+                    if (vec && kc * 4 + 3 < p.K) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(p.W + (int64_t)ng * p.ldw + kc * 4));
+                        w[u][0] = t.x; w[u][1] = t.y; w[u][2] = t.z; w[u][3] = t.w;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int k = kc * 4 + j;
+                            if (k < p.K)
+                                w[u][j] = p.w_transposed ? __ldg(p.W + (int64_t)k * p.ldw + ng) : __ldg(p.W + (int64_t)ng * p.ldw + k);
+                        }
+                    }
+                }
             }
-            const size_t off = (size_t)kc * (NT * 16) + (size_t)(n >> 3) * 128 + (size_t)(n & 7) * 16;
-            *reinterpret_cast<float4*>(sW + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            if (PASSES == 3) *reinterpret_cast<float4*>(sWlo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (i0 + u * (int)blockDim.x >= units) break;
+                float hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { hi[j] = rna_tf32(w[u][j]); lo[j] = w[u][j] - hi[j]; }
+                const size_t off = (size_t)kk[u] * (NT * 16) + (size_t)(nn[u] >> 3) * 128 + (size_t)(nn[u] & 7) * 16;
+                *reinterpret_cast<float4*>(sW + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                if (PASSES == 3) *reinterpret_cast<float4*>(sWlo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
         }
+        for (int n = tid; n < NT; n += blockDim.x) sBias[n] = (p.bias && n0 + n < p.N) ? __ldg(p.bias + n0 + n) : 0.0f;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core proxy
     tc_fence_before();
@@ -189,21 +244,12 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tmA, const TmaLinArgs p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t acc_stride = (uint32_t)p.tmem_cols >> 1;
+    if (tid == 0) PFO_TRACE(1);
+    int tr_tile = 0;
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
-            int stage = 0; uint32_t phase = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int c = 0; c < n_chunks; ++c) {
-                    mbar_wait(empty_bar(stage), phase ^ 1u);
-                    mbar_arrive_expect_tx(full_bar(stage), CHUNK_BYTES);
-                    tma_load_2d(smem_u32(sA + (size_t)stage * CHUNK_BYTES), &tmA, c * CK, (int)(tile * TM), full_bar(stage));
-                    if (++stage == stages) { stage = 0; phase ^= 1u; }
-                }
-            }
-        }
+        // ===== TMA producer (steady state) =====
+        if (lane == 0) produce(0x7fffffff);
         __syncwarp();
     } else if (warp == 1) {
         // ===== MMA issuer =====
@@ -222,6 +268,7 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tmA, const TmaLinArgs p) {
                 for (int c = 0; c < n_chunks; ++c) {
                     mbar_wait(PASSES == 3 ? ready_bar(stage) : full_bar(stage), phase);
                     tc_fence_after();
+                    if (c == 0 && tr_tile < 8) PFO_TRACE(8 + 8 * tr_tile + 2);
                     int ksteps = (KP8 - c * CK) >> 3;
                     if (ksteps > 4) ksteps = 4;
                     for (int s = 0; s < ksteps; ++s) {
@@ -242,105 +289,108 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tmA, const TmaLinArgs p) {
                     if (++stage == stages) { stage = 0; phase ^= 1u; }
                 }
                 tc_commit(tfull_bar(acc));                         // accumulator complete
+                if (tr_tile < 8) PFO_TRACE(8 + 8 * tr_tile + 3);
+                ++tr_tile;
                 acc ^= 1; if (acc == 0) acc_phase ^= 1u;
             }
         }
         __syncwarp();
-    } else if (warp < 6) {
-        // ===== epilogue: warp owns TMEM lanes [32q, 32q+32) = rows of the tile
-        const int q = warp & 3;
-        float* buf = sEpi + (size_t)(warp - 2) * 32 * EPI_LD;
-        const int r_sub = lane >> 3, c4 = (lane & 7) * 4;
+    } else if (warp < 2 + EPI_WARPS) {
+        // ===== epilogue: EPI_WARPS warps; warp owns TMEM lanes [32q, 32q+32) = 32 rows of the tile and every
+        // other 16-column slab.  A slab goes registers (lane = row: bias, scale, relu, row mask) -> 64-byte-swizzled
+        // staging tile -> coalesced 16-byte global stores (4 lanes per row; relu gate and accumulate applied
+        // there, where their loads coalesce too).  Two things this shape fixes, both measured (ncu + clock64
+        // trace): the first version was instruction-fetch bound (unrolled 45 KB of SASS), the second ran one
+        // epilogue warp per scheduler and could not hide its own dependent-issue latency.
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        uint8_t* stg = sOut + (size_t)(warp - 2) * 2048;
+        const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+        const int r_sub = lane >> 2, ch = lane & 3;
         int acc = 0; uint32_t acc_phase = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            for (int c0 = 0; c0 < NT; c0 += 32) {
-                const int ncols = (NT - c0) < 32 ? (NT - c0) : 32;
+            if (warp == 2 && lane == 0 && tr_tile < 8) PFO_TRACE(8 + 8 * tr_tile + 4);
+            const int64_t m0 = tile * TM + q * 32;
+            const int64_t mc = m0 + lane < M ? m0 + lane : M - 1;  // clamp the side loads of rows past M
+            const bool zero_row = p.row_zero && p.row_zero[mc] != 0;
+            const float brs = p.bias_row_scale ? p.bias_row_scale[mc * p.ld_brs] : 1.0f;
+            for (int c0 = half * 16; c0 < NT; c0 += 32) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_stride + (uint32_t)c0;
-                uint32_t r[32];
+                uint32_t r[16];
                 tmem_ld16(taddr, r);
-                if (ncols > 16) tmem_ld16(taddr + 16u, r + 16);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                __syncwarp();                                      // the previous slab has been read out of stg
+                uint8_t* dst = stg + (size_t)lane * 64;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (j * 4 < ncols)
-                        *reinterpret_cast<float4*>(buf + lane * EPI_LD + j * 4) =
-                            make_float4(__uint_as_float(r[j * 4]), __uint_as_float(r[j * 4 + 1]),
-                                        __uint_as_float(r[j * 4 + 2]), __uint_as_float(r[j * 4 + 3]));
+                for (int j = 0; j < 4; ++j) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(sBias + c0 + j * 4);
+                    float4 v;
+                    v.x = fmaf(b4.x, brs, __uint_as_float(r[j * 4])) * p.alpha;
+                    v.y = fmaf(b4.y, brs, __uint_as_float(r[j * 4 + 1])) * p.alpha;
+                    v.z = fmaf(b4.z, brs, __uint_as_float(r[j * 4 + 2])) * p.alpha;
+                    v.w = fmaf(b4.w, brs, __uint_as_float(r[j * 4 + 3])) * p.alpha;
+                    if (p.act == 1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    if (zero_row) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4*>(dst + (((uint32_t)j ^ sw) << 4)) = v;
                 }
                 __syncwarp();
-                // transposed read: 8 lanes cover 32 consecutive columns of one row, 4 rows per pass
-                if (c4 < ncols) {
-                    const int nb = n0 + c0 + c4;
-                    float bv[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (p.bias) {
+                const int nb = n0 + c0 + ch * 4;
+                if (nb < p.N) {
+                    const bool full4 = p.vec_ok && nb + 3 < p.N;
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) if (nb + e < p.N) bv[e] = __ldg(p.bias + nb + e);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int row = i * 4 + r_sub;
-                        const int64_t m = tile * TM + q * 32 + row;
-                        if (m >= M) continue;
-                        const float4 a4 = *reinterpret_cast<const float4*>(buf + row * EPI_LD + c4);
-                        float v[4] = {a4.x, a4.y, a4.z, a4.w};
-                        const bool zero_row = p.row_zero && p.row_zero[m] != 0;
-                        const float brs = p.bias_row_scale ? p.bias_row_scale[m * p.ld_brs] : 1.0f;
-                        float* dst = p.C + m * p.ldc + nb;
-                        const bool full4 = p.vec_ok && (nb + 3 < p.N);
-                        float g[4] = {1.f, 1.f, 1.f, 1.f}, old[4] = {0.f, 0.f, 0.f, 0.f};
-                        if (p.relu_gate) {
-                            const float* gp = p.relu_gate + m * p.ld_gate + nb;
-                            if (full4) { const float4 t = *reinterpret_cast<const float4*>(gp); g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w; }
-                            else {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) if (nb + e < p.N) g[e] = gp[e];
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = i * 8 + r_sub;
+                        const int64_t m = m0 + row;
+                        if (m >= M) break;
+                        const float4 t = *reinterpret_cast<const float4*>(stg + row * 64 + (((uint32_t)ch ^ (uint32_t)((row >> 1) & 3)) << 4));
+                        float v[4] = {t.x, t.y, t.z, t.w};
+                        float* cp = p.C + m * p.ldc + nb;
+                        if (full4) {
+                            if (p.relu_gate) {
+                                const float4 g = *reinterpret_cast<const float4*>(p.relu_gate + m * p.ld_gate + nb);
+                                if (g.x <= 0.f) v[0] = 0.f;
+                                if (g.y <= 0.f) v[1] = 0.f;
+                                if (g.z <= 0.f) v[2] = 0.f;
+                                if (g.w <= 0.f) v[3] = 0.f;
                             }
-                        }
-                        if (p.accumulate) {
-                            if (full4) { const float4 t = *reinterpret_cast<const float4*>(dst); old[0] = t.x; old[1] = t.y; old[2] = t.z; old[3] = t.w; }
-                            else {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) if (nb + e < p.N) old[e] = dst[e];
+                            if (p.accumulate) {
+                                const float4 o = *reinterpret_cast<const float4*>(cp);
+                                v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
                             }
-                        }
+                            *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+                        } else {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float x = v[e];
-                            if (p.bias) x += bv[e] * brs;
-                            x *= p.alpha;
-                            if (p.act == 1) x = fmaxf(x, 0.0f);
-                            if (p.relu_gate && g[e] <= 0.0f) x = 0.0f;
-                            if (zero_row) x = 0.0f;
-                            v[e] = x + old[e];
-                        }
-                        if (full4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                        else {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) if (nb + e < p.N) dst[e] = v[e];
+                            for (int e = 0; e < 4; ++e) {
+                                if (nb + e >= p.N) break;
+                                float x = v[e];
+                                if (p.relu_gate && p.relu_gate[m * p.ld_gate + nb + e] <= 0.f) x = 0.f;
+                                cp[e] = p.accumulate ? cp[e] + x : x;
+                            }
                         }
                     }
                 }
-                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));           // TMEM accumulator drained
+            if (warp == 2 && lane == 0 && tr_tile < 8) PFO_TRACE(8 + 8 * tr_tile + 5);
+            ++tr_tile;
             acc ^= 1; if (acc == 0) acc_phase ^= 1u;
         }
     } else if (PASSES == 3) {
         // ===== operand splitters: hi = rna_tf32(a) in place, lo = a - hi into the twin stage
-        const int t = tid - 192;
+        const int t = tid - THREADS_1;
         int stage = 0; uint32_t phase = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int c = 0; c < n_chunks; ++c) {
                 mbar_wait(full_bar(stage), phase);
+                if (c == 0 && t == 0 && tr_tile < 8) PFO_TRACE(8 + 8 * tr_tile + 1);
                 float4* hi = reinterpret_cast<float4*>(sA + (size_t)stage * CHUNK_BYTES);
                 float4* lo = reinterpret_cast<float4*>(sAlo + (size_t)stage * CHUNK_BYTES);
 #pragma unroll
-                for (int j = 0; j < CHUNK_BYTES / 16 / 128; ++j) {
-                    const int idx = t + 128 * j;
+                for (int j = 0; j < CHUNK_BYTES / 16 / (32 * SPLIT_WARPS); ++j) {
+                    const int idx = t + 32 * SPLIT_WARPS * j;
                     const float4 v = hi[idx];
                     float4 h, l;
                     h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
@@ -353,11 +403,13 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tmA, const TmaLinArgs p) {
                 if (lane == 0) mbar_arrive(ready_bar(stage));
                 if (++stage == stages) { stage = 0; phase ^= 1u; }
             }
+            ++tr_tile;
         }
     }
     // ---- teardown
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) PFO_TRACE(2);
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
@@ -391,11 +443,17 @@ int launch_tma(const CUtensorMap& map, const TmaLinArgs& a, dim3 grid, size_t sm
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    linear_tma_kernel<PASSES><<<grid, PASSES == 3 ? 320 : 192, smem, s>>>(map, a);
+    linear_tma_kernel<PASSES><<<grid, PASSES == 3 ? THREADS_3 : THREADS_1, smem, s>>>(map, a);
     PFO_LAUNCH_CHECK();
 }
 
+long long* g_linear_trace = nullptr;
+
 }  // namespace
+
+// Diagnostic hook (not part of the product ABI, not declared in include/pfo_b200.h): when set to a device buffer
+// of >= 80 int64, CTA (0,0) of every pfo_linear_tf32 launch records clock64() at its pipeline milestones.
+PFO_API void pfo_debug_set_linear_trace(void* device_buffer) { g_linear_trace = static_cast<long long*>(device_buffer); }
 
 // Builds the 2-D tensor map of a row-major fp32 matrix [rows, cols] (row stride ld floats) with
 // 32-column x box_rows boxes and the 128-byte swizzle (atom32: 32-byte swizzle atoms, the form the tensor
@@ -432,24 +490,26 @@ PFO_API int pfo_linear_tf32(const float* A, int64_t lda, const int32_t* a_idx, c
     a.W = W; a.ldw = ldw; a.w_transposed = w_transposed; a.bias = bias; a.bias_row_scale = bias_row_scale;
     a.ld_brs = ld_brs; a.C = C; a.ldc = ldc; a.M = M; a.m_dev = m_dev; a.N = N; a.K = K; a.alpha = alpha; a.act = act;
     a.row_zero = row_zero; a.relu_gate = relu_gate; a.ld_gate = ld_gate; a.accumulate = accumulate;
+    a.trace = g_linear_trace;
     a.KP8 = (K + 7) / 8 * 8;
     a.n_chunks = (K + CK - 1) / CK;
     a.vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
                (!relu_gate || ((ld_gate % 4 == 0) && ((reinterpret_cast<uintptr_t>(relu_gate) & 15) == 0)));
     const int mult = passes == 3 ? 2 : 1;
     const int stage_bytes = CHUNK_BYTES * mult;
-    const int fixed = EPI_BYTES + 8 * (3 * MAX_STAGES + 4) + 16 + 1024;   // epilogue buffers, barriers, alignment slack
+    // output staging, barriers + TMEM slot, alignment slack; the bias slice (4 * NT bytes) is counted with the weights
+    const int fixed = EPI_BYTES + 8 * (3 * MAX_STAGES + 4) + 16 + 1024;
     const int budget = SMEM_LIMIT - fixed;
     int n_ntiles = (N + 255) / 256;
-    int NT;
+    int NT;                                      // output columns per CTA: whole 32-column store slabs
     for (;;) {
-        NT = ((N + n_ntiles - 1) / n_ntiles + 15) / 16 * 16;
-        if ((int64_t)NT * a.KP8 * 4 * mult + 2 * stage_bytes <= budget) break;
-        if (NT <= 16) return (int)cudaErrorInvalidValue;
+        NT = ((N + n_ntiles - 1) / n_ntiles + 31) / 32 * 32;
+        if ((int64_t)NT * (a.KP8 * 4 * mult + 4) + 2 * stage_bytes <= budget) break;
+        if (NT <= 32) return (int)cudaErrorInvalidValue;
         ++n_ntiles;
     }
     a.NT = NT;
-    const int w_bytes = NT * a.KP8 * 4 * mult;
+    const int w_bytes = NT * (a.KP8 * 4 * mult + 4);
     int stages = (budget - w_bytes) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     a.stages = stages;

@@ -240,12 +240,40 @@ time_embedding_bwd_kernel(const int32_t* __restrict__ q_nodes, int64_t Q, int d,
     for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) partial[(int64_t)blockIdx.x * 2 * d + c] = sm[c];
 }
 
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int rows, int cols,
-                                       float* __restrict__ out, int accumulate) {
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x) {
+// out[c] (+)= sum_r partial[r, c] in a fixed order (deterministic): a CTA owns 32 columns, its 8 warps stride the
+// rows (coalesced 128-byte reads), then the 8 per-warp sums are added in warp order.  Narrow inputs (cols < 32,
+// e.g. the BPR loss partials) put the rows across the lanes instead.
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ partial, int rows, int cols, float* __restrict__ out, int accumulate) {
+    __shared__ float sm[8][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (cols >= 32) {
+        const int c = blockIdx.x * 32 + lane;
         float s = 0.0f;
-        for (int r = 0; r < rows; ++r) s += partial[(int64_t)r * cols + c];
-        out[c] = accumulate ? out[c] + s : s;
+        if (c < cols)
+            for (int r = w; r < rows; r += 8) s += partial[(int64_t)r * cols + c];
+        sm[w][lane] = s;
+        __syncthreads();
+        if (w == 0 && c < cols) {
+            float t = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t += sm[k][lane];
+            out[c] = accumulate ? out[c] + t : t;
+        }
+    } else {
+        const int c = blockIdx.x;                      // one CTA per column
+        float s = 0.0f;
+        for (int r = threadIdx.x; r < rows; r += 256) s += partial[(int64_t)r * cols + c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) sm[w][0] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t += sm[k][0];
+            out[c] = accumulate ? out[c] + t : t;
+        }
     }
 }
 
@@ -429,12 +457,13 @@ PFO_API int pfo_time_embedding_bwd(const int32_t* q_nodes, int64_t Q, int d, con
     time_embedding_bwd_kernel<<<grid, 256, 2 * d * sizeof(float), s>>>(q_nodes, Q, d, slot_of_node, Hnew, td, W, b,
                                                                       dEmb, dHnew, workspace);
     // partial rows are [dW(d) | db(d)]; dWdb receives the same layout
-    reduce_partials_kernel<<<1, 256, 0, s>>>(workspace, grid, 2 * d, dWdb, 0);
+    reduce_partials_kernel<<<(2 * d + 31) / 32, 256, 0, s>>>(workspace, grid, 2 * d, dWdb, 0);
     PFO_LAUNCH_CHECK();
 }
 
 PFO_API int pfo_reduce_partials(const float* partial, int rows, int cols, float* out, int accumulate, void* stream) {
-    reduce_partials_kernel<<<(cols + 255) / 256, 256, 0, (cudaStream_t)stream>>>(partial, rows, cols, out, accumulate);
+    if (cols <= 0) return 0;
+    reduce_partials_kernel<<<cols >= 32 ? (cols + 31) / 32 : cols, 256, 0, (cudaStream_t)stream>>>(partial, rows, cols, out, accumulate);
     PFO_LAUNCH_CHECK();
 }
 
