@@ -165,6 +165,26 @@ int pfo_attn_nbr_bwd(const float* QK, const float* dXB, int64_t lddxb, const flo
                      const uint32_t* step_dev, float* dQK, float* dT, int64_t lddt, float* dtw_dtb, int accumulate,
                      float* workspace, void* stream);
 
+/* ---- parameter-side folding of the attention layer --- model/temporal_attention.py:26-90 (q/k/v/out projections of
+ * nn.MultiheadAttention, TimeEncode(0) of the query) and utils/utils.py:4-17 (MergeLayer fc1).  Forward builds the
+ * GEMM operands the per-query kernels consume: Wqk [H*ekp, d], cqk [H*ekp] (qk_h = Wqk_h h_q + cqk_h) and
+ * Wc1T [H*ekp + d, d] (fc1([out_proj(attn) | h_q]) as one contraction over [XB | h_q], biases in the `valid` and
+ * `one` rows).  Backward carries d/dWqk, d/dcqk, d/dWc1T back to the reference's tensors (all outputs fully
+ * written; q_proj / k_proj / v_proj weights are [2d, 2d] / [2d, 2d+F] / [2d, 2d+F], in_proj_bias [6d], out_proj
+ * [2d, 2d] + [2d], fc1 [d, 3d] + [d], tb = TimeEncode bias [d]).  fp64 arithmetic; `workspace` holds
+ * pfo_fold_attention_workspace_doubles doubles and must be kept from the forward to the backward call. */
+int64_t pfo_fold_attention_workspace_doubles(int d, int F, int H);
+int pfo_fold_attention_fwd(const float* Wq, const float* Wk, const float* Wv, const float* b_in, const float* Wo,
+                           const float* bo, const float* W1, const float* b1, const float* tb,
+                           int d, int F, int H, int ekp, double* workspace,
+                           float* Wqk, float* cqk, float* Wc1T, void* stream);
+int pfo_fold_attention_bwd(const float* Wq, const float* Wk, const float* Wv, const float* b_in, const float* Wo,
+                           const float* bo, const float* W1, const float* b1, const float* tb,
+                           int d, int F, int H, int ekp, double* workspace,
+                           const float* gWqk, const float* gcqk, const float* gWc1T,
+                           float* gWq, float* gWk, float* gWv, float* gb_in, float* gWo, float* gbo,
+                           float* gW1, float* gb1, float* gtb, void* stream);
+
 /* ---- K6: BPR loss forward + backward --- main.py:321-337 / :364-381.  du/dp/dn may be null
  * (forward only).  workspace: 1024 floats. */
 int pfo_bpr(const float* eu, const float* ep, const float* en, int B, int k, int d,

@@ -7,9 +7,9 @@
 //   Wc1T [H*ekp + d, d]          : rows of head h = (W1a Wo_h [Wv_h | bv_h])^T, row `valid` = W1a bo and row
 //                                  `one` = b1 in head 0, zero padding rows, then W1b^T
 // Everything here is O(weights) -- a few MFLOP per step -- so the arithmetic is done in fp64 (the folded operands
-// are then at least as accurate as the reference's chained fp32 products) with one thread per output element and
-// the thread index laid along the operand that makes the inner-loop loads coalesce.  Two launches forward, two
-// backward, instead of ~95 tiny framework kernels per step.
+// are then at least as accurate as the reference's chained fp32 products)
+// as a handful of 32x32-tiled fp64 GEMM jobs per launch (one CTA per tile, the leftover matvecs / copies in the last
+// CTA).  Two launches forward, two backward, instead of ~95 tiny framework kernels per step.
 #include "common.cuh"
 
 namespace {
@@ -36,167 +36,276 @@ __device__ __forceinline__ double wva(const FoldArgs& p, int h, int i, int r) {
     return r < p.Ek ? (double)p.Wv[(size_t)row * p.Ek + r] : (double)p.b_in[2 * p.E + row];
 }
 
-// ---- forward stage 1: te0, cq | T_h = Wo_h [Wv_h | bv_h] | Wqk = s Wk_h^T Wq_h[:, :d] (padding rows zero)
+// ---- one 32x32 output tile of C[m, n] = sum_k A(m, k) B(k, n) in fp64: 256 threads, 2x2 outputs each, K in chunks
+// of 32 through shared memory.  A_MC / B_NC say which index of the operand is contiguous in memory so that the
+// tile loads coalesce (A_MC: m contiguous, else k; B_NC: n contiguous, else k).
+constexpr int TS = 32;
+
+template <bool A_MC, bool B_NC, class FA, class FB, class FC>
+__device__ __forceinline__ void gemm_tile(double (*As)[TS + 1], double (*Bs)[TS + 1], int M, int N, int K, int tm, int tn,
+                                          FA fa, FB fb, FC fc) {
+    const int t = threadIdx.x;
+    const int ty = t >> 4, tx = t & 15;
+    const int m0 = tm * TS, n0 = tn * TS;
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    for (int k0 = 0; k0 < K; k0 += TS) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int idx = t + 256 * j;
+            const int fast = idx & 31, slow = idx >> 5;
+            {
+                const int m = A_MC ? fast : slow, k = A_MC ? slow : fast;
+                As[m][k] = (m0 + m < M && k0 + k < K) ? fa(m0 + m, k0 + k) : 0.0;
+            }
+            {
+                const int n = B_NC ? fast : slow, k = B_NC ? slow : fast;
+                Bs[k][n] = (n0 + n < N && k0 + k < K) ? fb(k0 + k, n0 + n) : 0.0;
+            }
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < TS; ++k) {
+            const double a0 = As[ty * 2][k], a1 = As[ty * 2 + 1][k];
+            const double b0 = Bs[k][tx * 2], b1 = Bs[k][tx * 2 + 1];
+            acc[0][0] = fma(a0, b0, acc[0][0]); acc[0][1] = fma(a0, b1, acc[0][1]);
+            acc[1][0] = fma(a1, b0, acc[1][0]); acc[1][1] = fma(a1, b1, acc[1][1]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int m = m0 + ty * 2 + i, n = n0 + tx * 2 + j;
+            if (m < M && n < N) fc(m, n, acc[i][j]);
+        }
+}
+
+__host__ __device__ __forceinline__ int tiles(int x) { return (x + TS - 1) / TS; }
+
+// a CTA takes the job `job` of a group of `batch` GEMMs with tiles(M) x tiles(N) tiles each; returns false (and
+// rebases job) when the job belongs to a later group
+#define FOLD_GROUP(batch, M, N)                                                        \
+    const int tmn_ = tiles(M) * tiles(N);                                              \
+    if (job >= (batch) * tmn_) { job -= (batch) * tmn_; } else
+
+// ---- forward stage 1: T_h = Wo_h [Wv_h | bv_h] | Wqk_h = s Wk_h^T Wq_h[:, :d] | te0, cq, padding rows of Wqk
 __global__ void __launch_bounds__(256) fold_fwd1_kernel(const FoldArgs p) {
     const int d = p.d, E = p.E, Ek = p.Ek, H = p.H, hd = p.hd, ekp = p.ekp, R = Ek + 1;
-    const int n_cq = E, n_T = H * E * R, n_A = H * ekp * d;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_cq + n_T + n_A; i += gridDim.x * blockDim.x) {
-        if (i < n_cq) {
-            const int e = i;
-            double s = (double)p.b_in[e];
-            for (int k = 0; k < d; ++k) s += (double)p.Wq[(size_t)e * E + d + k] * cos((double)p.tb[k]);
-            ws_cq(p)[e] = s;
-            if (e < d) ws_te0(p)[e] = cos((double)p.tb[e]);
-        } else if (i < n_cq + n_T) {
-            const int j = i - n_cq;
-            const int r = j % R, e = (j / R) % E, h = j / (R * E);
-            double s = 0.0;
-            for (int t = 0; t < hd; ++t) s += (double)p.Wo[(size_t)e * E + h * hd + t] * wva(p, h, t, r);
-            ws_T(p)[j] = s;
-        } else {
-            const int j = i - n_cq - n_T;
-            const int c = j % d, r = (j / d) % ekp, h = j / (d * ekp);
-            double s = 0.0;
-            if (r < Ek)
-                for (int t = 0; t < hd; ++t)
-                    s += (double)p.Wk[(size_t)(h * hd + t) * Ek + r] * (double)p.Wq[(size_t)(h * hd + t) * E + c];
-            p.Wqk[j] = (float)(p.scale * s);
-        }
+    __shared__ double As[TS][TS + 1], Bs[TS][TS + 1];   // A tile [m][k], B tile [k][n]
+    int job = blockIdx.x;
+    { FOLD_GROUP(H, E, R) {
+        const int h = job / tmn_, t = job % tmn_;
+        double* T = ws_T(p) + (size_t)h * E * R;
+        gemm_tile<false, true>(As, Bs, E, R, hd, t / tiles(R), t % tiles(R),
+            [&](int m, int k) { return (double)p.Wo[(size_t)m * E + h * hd + k]; },
+            [&](int k, int n) { return wva(p, h, k, n); },
+            [&](int m, int n, double v) { T[(size_t)m * R + n] = v; });
+        return; } }
+    { FOLD_GROUP(H, Ek, d) {
+        const int h = job / tmn_, t = job % tmn_;
+        gemm_tile<true, true>(As, Bs, Ek, d, hd, t / tiles(d), t % tiles(d),
+            [&](int m, int k) { return (double)p.Wk[(size_t)(h * hd + k) * Ek + m]; },
+            [&](int k, int n) { return (double)p.Wq[(size_t)(h * hd + k) * E + n]; },
+            [&](int m, int n, double v) { p.Wqk[(size_t)(h * ekp + m) * d + n] = (float)(p.scale * v); });
+        return; } }
+    // last CTA: te0, cq (warp per output, lanes along k) and the zero padding rows of Wqk
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double* te0 = &As[0][0];                                       // d <= 128 doubles; the GEMM tiles are idle here
+    for (int k = threadIdx.x; k < d; k += 256) { te0[k] = cos((double)p.tb[k]); ws_te0(p)[k] = te0[k]; }
+    __syncthreads();
+    for (int e = w; e < E; e += 8) {
+        double s = 0.0;
+        for (int k = lane; k < d; k += 32) s += (double)p.Wq[(size_t)e * E + d + k] * te0[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) ws_cq(p)[e] = s + (double)p.b_in[e];
+    }
+    const int pad = ekp - Ek;
+    for (int i = threadIdx.x; i < H * pad * d; i += 256) {
+        const int c = i % d, r = Ek + (i / d) % pad, h = i / (d * pad);
+        p.Wqk[(size_t)(h * ekp + r) * d + c] = 0.0f;
     }
 }
+static int fold_fwd1_jobs(int d, int F, int H) { const int E = 2 * d, Ek = E + F; return H * tiles(E) * tiles(Ek + 1) + H * tiles(Ek) * tiles(d) + 1; }
 
-// ---- forward stage 2: cqk = s Wk_h^T cq_h | Wc1T
+// ---- forward stage 2: Wc1T head rows = (W1a T_h)^T | cqk, `valid` / `one` / padding rows, W1b^T rows
 __global__ void __launch_bounds__(256) fold_fwd2_kernel(const FoldArgs p) {
     const int d = p.d, E = p.E, Ek = p.Ek, H = p.H, hd = p.hd, ekp = p.ekp, R = Ek + 1;
-    const int n_c = H * ekp, n_W = (H * ekp + d) * d;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_c + n_W; i += gridDim.x * blockDim.x) {
-        if (i < n_c) {
-            const int r = i % ekp, h = i / ekp;
-            double s = 0.0;
-            if (r < Ek)
-                for (int t = 0; t < hd; ++t) s += (double)p.Wk[(size_t)(h * hd + t) * Ek + r] * ws_cq(p)[h * hd + t];
-            p.cqk[i] = (float)(p.scale * s);
-        } else {
-            // thread index along the folded row index (rr) so that T_h[e, r] loads coalesce; column c is the slow index
-            const int j = i - n_c;
-            const int rows = H * ekp + d;
-            const int rr = j % rows, c = j / rows;
-            double s = 0.0;
-            if (rr >= H * ekp) {
-                s = (double)p.W1[(size_t)c * (E + d) + E + (rr - H * ekp)];               // W1b^T
-            } else {
-                const int h = rr / ekp, r = rr % ekp;
-                if (r < R) {
-                    const double* T = ws_T(p) + (size_t)h * E * R;
-                    for (int e = 0; e < E; ++e) s += (double)p.W1[(size_t)c * (E + d) + e] * T[(size_t)e * R + r];
-                } else if (h == 0 && r == R) {                                           // `valid` row: W1a bo
-                    for (int e = 0; e < E; ++e) s += (double)p.W1[(size_t)c * (E + d) + e] * (double)p.bo[e];
-                } else if (h == 0 && r == R + 1) {                                       // `one` row: b1
-                    s = (double)p.b1[c];
-                }
-            }
-            p.Wc1T[(size_t)rr * d + c] = (float)s;
+    __shared__ double As[TS][TS + 1], Bs[TS][TS + 1];   // A tile [m][k], B tile [k][n]
+    int job = blockIdx.x;
+    { FOLD_GROUP(H, d, R) {
+        const int h = job / tmn_, t = job % tmn_;
+        const double* T = ws_T(p) + (size_t)h * E * R;
+        gemm_tile<false, true>(As, Bs, d, R, E, t / tiles(R), t % tiles(R),
+            [&](int m, int k) { return (double)p.W1[(size_t)m * (E + d) + k]; },
+            [&](int k, int n) { return T[(size_t)k * R + n]; },
+            [&](int m, int n, double v) { p.Wc1T[(size_t)(h * ekp + n) * d + m] = (float)v; });
+        return; } }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    // cqk[h, r] = s sum_t Wk[h*hd+t, r] cq[h*hd+t]: thread per r (coalesced along r), 8 partial sums over t
+    double (*part)[TS + 1] = As;                                   // the GEMM tiles are idle in the last CTA
+    for (int base = 0; base < H * ekp; base += TS) {
+        const int i = base + lane;
+        const int h = i / ekp, r = i % ekp;
+        double s = 0.0;
+        if (i < H * ekp && r < Ek)
+            for (int t = w; t < hd; t += 8) s += (double)p.Wk[(size_t)(h * hd + t) * Ek + r] * ws_cq(p)[h * hd + t];
+        part[w][lane] = s;
+        __syncthreads();
+        if (w == 0 && i < H * ekp) {
+            double tsum = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) tsum += part[k][lane];
+            p.cqk[i] = (float)(p.scale * tsum);
         }
+        __syncthreads();
+    }
+    // `valid` row of head 0 = W1a bo (warp per output column c, lanes along e)
+    for (int c = w; c < d; c += 8) {
+        double s = 0.0;
+        for (int e = lane; e < E; e += 32) s += (double)p.W1[(size_t)c * (E + d) + e] * (double)p.bo[e];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) p.Wc1T[(size_t)R * d + c] = (float)s;
+    }
+    // `one` row of head 0 = b1; remaining tail rows zero; W1b^T
+    const int tail = ekp - R;
+    for (int i = threadIdx.x; i < H * tail * d; i += 256) {
+        const int c = i % d, r = R + (i / d) % tail, h = i / (d * tail);
+        if (h == 0 && r == R) continue;
+        p.Wc1T[(size_t)(h * ekp + r) * d + c] = (h == 0 && r == R + 1) ? p.b1[c] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < d * d; i += 256) {
+        const int c = i % d, k = i / d;
+        p.Wc1T[(size_t)(H * ekp + k) * d + c] = p.W1[(size_t)c * (E + d) + E + k];
     }
 }
+static int fold_fwd2_jobs(int d, int F, int H) { const int Ek = 2 * d + F; return H * tiles(d) * tiles(Ek + 1) + 1; }
 
 // ---- backward stage 1 (needs T and cq of the forward):
-//   gW1 (a and b parts), gb1 | gT_h = W1a^T gB_h (layout [h][r][e]) | gbo | gWq[:, :d] | gcq | gWk
+//   gW1a | gT_h = (W1a^T gB_h)^T (layout [h][r][e]) | gWq[:, :d] | gWk | gbo, gcq, gW1b, gb1
 __global__ void __launch_bounds__(256) fold_bwd1_kernel(const FoldArgs p) {
     const int d = p.d, E = p.E, Ek = p.Ek, H = p.H, hd = p.hd, ekp = p.ekp, R = Ek + 1;
-    const int n_W1 = d * (E + d), n_b1 = d, n_gT = H * R * E, n_bo = E, n_Wq = E * d, n_cq = E, n_Wk = E * Ek;
-    const int o1 = n_W1, o2 = o1 + n_b1, o3 = o2 + n_gT, o4 = o3 + n_bo, o5 = o4 + n_Wq, o6 = o5 + n_cq, o7 = o6 + n_Wk;
     const float* gc1 = p.gWc1T + (size_t)R * d;                   // head 0, `valid` row
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < o7; i += gridDim.x * blockDim.x) {
-        if (i < o1) {                                              // gW1[c, x]; thread index along c
-            const int c = i % d, x = i / d;
-            double s = 0.0;
-            if (x >= E) {
-                s = (double)p.gWc1T[(size_t)(H * ekp + (x - E)) * d + c];
-            } else {
-                for (int h = 0; h < H; ++h) {
-                    const double* T = ws_T(p) + ((size_t)h * E + x) * R;
-                    const float* g = p.gWc1T + (size_t)h * ekp * d + c;
-                    for (int r = 0; r < R; ++r) s += (double)g[(size_t)r * d] * T[r];
-                }
-                s += (double)gc1[c] * (double)p.bo[x];
-            }
-            p.gW1[(size_t)c * (E + d) + x] = (float)s;
-        } else if (i < o2) {
-            const int c = i - o1;
-            p.gb1[c] = p.gWc1T[(size_t)(R + 1) * d + c];           // head 0, `one` row
-        } else if (i < o3) {                                       // gT[h][r][e]; thread index along e
-            const int j = i - o2;
-            const int e = j % E, r = (j / E) % R, h = j / (E * R);
-            const float* g = p.gWc1T + (size_t)(h * ekp + r) * d;
-            double s = 0.0;
-            for (int c = 0; c < d; ++c) s += (double)p.W1[(size_t)c * (E + d) + e] * (double)g[c];
-            ws_gT(p)[j] = s;
-        } else if (i < o4) {
-            const int e = i - o3;
-            double s = 0.0;
-            for (int c = 0; c < d; ++c) s += (double)p.W1[(size_t)c * (E + d) + e] * (double)gc1[c];
-            p.gbo[e] = (float)s;
-        } else if (i < o5) {                                       // gWq[row, c < d]; thread index along c
-            const int j = i - o4;
-            const int c = j % d, row = j / d, h = row / hd;
-            const float* g = p.gWqk + (size_t)h * ekp * d + c;
-            double s = 0.0;
-            for (int r = 0; r < Ek; ++r) s += (double)p.Wk[(size_t)row * Ek + r] * (double)g[(size_t)r * d];
-            p.gWq[(size_t)row * E + c] = (float)(p.scale * s);
-        } else if (i < o6) {
-            const int row = i - o5, h = row / hd;
-            double s = 0.0;
-            for (int r = 0; r < Ek; ++r) s += (double)p.Wk[(size_t)row * Ek + r] * (double)p.gcqk[h * ekp + r];
-            ws_gcq(p)[row] = p.scale * s;
-        } else {                                                   // gWk[row, r]
-            const int j = i - o6;
-            const int r = j % Ek, row = j / Ek, h = row / hd;
-            const float* g = p.gWqk + (size_t)(h * ekp + r) * d;
-            const float* wq = p.Wq + (size_t)row * E;
-            double s = 0.0;
-            for (int c = 0; c < d; ++c) s += (double)g[c] * (double)wq[c];
-            s += (double)p.gcqk[h * ekp + r] * ws_cq(p)[row];
-            p.gWk[j] = (float)(p.scale * s);
+    __shared__ double As[TS][TS + 1], Bs[TS][TS + 1];   // A tile [m][k], B tile [k][n]
+    int job = blockIdx.x;
+    { FOLD_GROUP(1, d, E) {                                        // gW1a[c, e], K = (h, r) pairs + the rank-1 term gc1 bo^T
+        const int t = job;
+        gemm_tile<true, false>(As, Bs, d, E, H * R + 1, t / tiles(E), t % tiles(E),
+            [&](int m, int k) { return k < H * R ? (double)p.gWc1T[(size_t)((k / R) * ekp + (k % R)) * d + m] : (double)gc1[m]; },
+            [&](int k, int n) { return k < H * R ? ws_T(p)[((size_t)(k / R) * E + n) * R + (k % R)] : (double)p.bo[n]; },
+            [&](int m, int n, double v) { p.gW1[(size_t)m * (E + d) + n] = (float)v; });
+        return; } }
+    { FOLD_GROUP(H, R, E) {                                        // gT[h][r][e]
+        const int h = job / tmn_, t = job % tmn_;
+        double* gT = ws_gT(p) + (size_t)h * R * E;
+        gemm_tile<false, true>(As, Bs, R, E, d, t / tiles(E), t % tiles(E),
+            [&](int m, int k) { return (double)p.gWc1T[(size_t)(h * ekp + m) * d + k]; },
+            [&](int k, int n) { return (double)p.W1[(size_t)k * (E + d) + n]; },
+            [&](int m, int n, double v) { gT[(size_t)m * E + n] = v; });
+        return; } }
+    { FOLD_GROUP(H, hd, d) {                                       // gWq[h*hd + m, c]
+        const int h = job / tmn_, t = job % tmn_;
+        gemm_tile<false, true>(As, Bs, hd, d, Ek, t / tiles(d), t % tiles(d),
+            [&](int m, int k) { return (double)p.Wk[(size_t)(h * hd + m) * Ek + k]; },
+            [&](int k, int n) { return (double)p.gWqk[(size_t)(h * ekp + k) * d + n]; },
+            [&](int m, int n, double v) { p.gWq[(size_t)(h * hd + m) * E + n] = (float)(p.scale * v); });
+        return; } }
+    { FOLD_GROUP(H, hd, Ek) {                                      // gWk[h*hd + m, r], K = c plus the rank-1 term cq gcqk^T
+        const int h = job / tmn_, t = job % tmn_;
+        gemm_tile<false, false>(As, Bs, hd, Ek, d + 1, t / tiles(Ek), t % tiles(Ek),
+            [&](int m, int k) { return k < d ? (double)p.Wq[(size_t)(h * hd + m) * E + k] : ws_cq(p)[h * hd + m]; },
+            [&](int k, int n) { return k < d ? (double)p.gWqk[(size_t)(h * ekp + n) * d + k] : (double)p.gcqk[h * ekp + n]; },
+            [&](int m, int n, double v) { p.gWk[(size_t)(h * hd + m) * Ek + n] = (float)(p.scale * v); });
+        return; } }
+    // last CTA: matvecs and copies
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double (*part)[TS + 1] = As;                                   // the GEMM tiles are idle in the last CTA
+    for (int base = 0; base < E; base += TS) {                     // gbo[e] = sum_c W1[c, e] gc1[c]: thread per e
+        const int e = base + lane;
+        double s = 0.0;
+        if (e < E) for (int c = w; c < d; c += 8) s += (double)p.W1[(size_t)c * (E + d) + e] * (double)gc1[c];
+        part[w][lane] = s;
+        __syncthreads();
+        if (w == 0 && e < E) {
+            double tsum = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) tsum += part[k][lane];
+            p.gbo[e] = (float)tsum;
         }
+        __syncthreads();
     }
+    for (int row = w; row < E; row += 8) {                         // gcq[row] = s sum_r Wk[row, r] gcqk[h, r]: warp per row
+        const int h = row / hd;
+        double s = 0.0;
+        for (int r = lane; r < Ek; r += 32) s += (double)p.Wk[(size_t)row * Ek + r] * (double)p.gcqk[h * ekp + r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) ws_gcq(p)[row] = p.scale * s;
+    }
+    for (int i = threadIdx.x; i < d * d; i += 256) {               // gW1b[c, k] = gWc1T[H*ekp + k, c]
+        const int c = i % d, k = i / d;
+        p.gW1[(size_t)c * (E + d) + E + k] = p.gWc1T[(size_t)(H * ekp + k) * d + c];
+    }
+    for (int c = threadIdx.x; c < d; c += 256) p.gb1[c] = p.gWc1T[(size_t)(R + 1) * d + c];   // head 0, `one` row
+}
+static int fold_bwd1_jobs(int d, int F, int H) {
+    const int E = 2 * d, Ek = E + F, R = Ek + 1, hd = E / H;
+    return tiles(d) * tiles(E) + H * tiles(R) * tiles(E) + H * tiles(hd) * tiles(d) + H * tiles(hd) * tiles(Ek) + 1;
 }
 
-// ---- backward stage 2 (needs gT and gcq): gWo | gWv, gb_in | gWq[:, d:] | gtb
+// ---- backward stage 2 (needs gT and gcq): gWo | gWv, gbv | gb_in (q, k parts), gWq[:, d:], gtb
 __global__ void __launch_bounds__(256) fold_bwd2_kernel(const FoldArgs p) {
     const int d = p.d, E = p.E, Ek = p.Ek, H = p.H, hd = p.hd, R = Ek + 1;
-    const int n_Wo = E * E, n_Wv = E * R, n_bq = 2 * E, n_Wqt = E * d, n_tb = d;
-    const int o1 = n_Wo, o2 = o1 + n_Wv, o3 = o2 + n_bq, o4 = o3 + n_Wqt, o5 = o4 + n_tb;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < o5; i += gridDim.x * blockDim.x) {
-        if (i < o1) {                                              // gWo[e, col]; thread index along e
-            const int e = i % E, col = i / E, h = col / hd, t = col % hd;
-            const double* gT = ws_gT(p) + (size_t)h * R * E + e;
-            double s = 0.0;
-            for (int r = 0; r < R; ++r) s += gT[(size_t)r * E] * wva(p, h, t, r);
-            p.gWo[(size_t)e * E + col] = (float)s;
-        } else if (i < o2) {                                       // g[Wv | bv][row, r]; thread index along row's t
-            const int j = i - o1;
-            const int t = j % hd, r = (j / hd) % R, h = j / (hd * R);
-            const double* gT = ws_gT(p) + ((size_t)h * R + r) * E;
-            double s = 0.0;
-            for (int e = 0; e < E; ++e) s += (double)p.Wo[(size_t)e * E + h * hd + t] * gT[e];
-            const int row = h * hd + t;
-            if (r < Ek) p.gWv[(size_t)row * Ek + r] = (float)s;
-            else p.gb_in[2 * E + row] = (float)s;
-        } else if (i < o3) {                                       // gb_in: query part = gcq, key part = 0 (cancels in softmax)
-            const int e = i - o2;
-            p.gb_in[e] = e < E ? (float)ws_gcq(p)[e] : 0.0f;
-        } else if (i < o4) {                                       // gWq[e, d + k] = gcq[e] te0[k]
-            const int j = i - o3;
-            const int k = j % d, e = j / d;
-            p.gWq[(size_t)e * E + d + k] = (float)(ws_gcq(p)[e] * ws_te0(p)[k]);
-        } else {                                                   // gtb[k] = -sin(tb[k]) sum_e Wq[e, d+k] gcq[e]
-            const int k = i - o4;
-            double s = 0.0;
-            for (int e = 0; e < E; ++e) s += (double)p.Wq[(size_t)e * E + d + k] * ws_gcq(p)[e];
-            p.gtb[k] = (float)(-sin((double)p.tb[k]) * s);
-        }
+    __shared__ double As[TS][TS + 1], Bs[TS][TS + 1];   // A tile [m][k], B tile [k][n]
+    int job = blockIdx.x;
+    { FOLD_GROUP(H, E, hd) {                                       // gWo[e, h*hd + t]
+        const int h = job / tmn_, t = job % tmn_;
+        const double* gT = ws_gT(p) + (size_t)h * R * E;
+        gemm_tile<true, false>(As, Bs, E, hd, R, t / tiles(hd), t % tiles(hd),
+            [&](int m, int k) { return gT[(size_t)k * E + m]; },
+            [&](int k, int n) { return wva(p, h, n, k); },
+            [&](int m, int n, double v) { p.gWo[(size_t)m * E + h * hd + n] = (float)v; });
+        return; } }
+    { FOLD_GROUP(H, hd, R) {                                       // g[Wv | bv][h*hd + t, r]
+        const int h = job / tmn_, t = job % tmn_;
+        const double* gT = ws_gT(p) + (size_t)h * R * E;
+        gemm_tile<true, false>(As, Bs, hd, R, E, t / tiles(R), t % tiles(R),
+            [&](int m, int k) { return (double)p.Wo[(size_t)k * E + h * hd + m]; },
+            [&](int k, int n) { return gT[(size_t)n * E + k]; },
+            [&](int m, int n, double v) {
+                const int row = h * hd + m;
+                if (n < Ek) p.gWv[(size_t)row * Ek + n] = (float)v; else p.gb_in[2 * E + row] = (float)v;
+            });
+        return; } }
+    // last CTA
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int e = threadIdx.x; e < 2 * E; e += 256)                 // query part = gcq, key part = 0 (cancels in the softmax)
+        p.gb_in[e] = e < E ? (float)ws_gcq(p)[e] : 0.0f;
+    for (int i = threadIdx.x; i < E * d; i += 256) {               // gWq[e, d + k] = gcq[e] te0[k]
+        const int k = i % d, e = i / d;
+        p.gWq[(size_t)e * E + d + k] = (float)(ws_gcq(p)[e] * ws_te0(p)[k]);
     }
+    double (*part)[TS + 1] = As;                                   // the GEMM tiles are idle in the last CTA
+    for (int base = 0; base < d; base += TS) {                     // gtb[k] = -sin(tb[k]) sum_e Wq[e, d+k] gcq[e]: thread per k
+        const int k = base + lane;
+        double s = 0.0;
+        if (k < d) for (int e = w; e < E; e += 8) s += (double)p.Wq[(size_t)e * E + d + k] * ws_gcq(p)[e];
+        part[w][lane] = s;
+        __syncthreads();
+        if (w == 0 && k < d) {
+            double tsum = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tsum += part[j][lane];
+            p.gtb[k] = (float)(-sin((double)p.tb[k]) * tsum);
+        }
+        __syncthreads();
+    }
+}
+static int fold_bwd2_jobs(int d, int F, int H) {
+    const int E = 2 * d, Ek = E + F, R = Ek + 1, hd = E / H;
+    return H * tiles(E) * tiles(hd) + H * tiles(hd) * tiles(R) + 1;
 }
 
 int fill(FoldArgs& a, const float* Wq, const float* Wk, const float* Wv, const float* b_in, const float* Wo,
@@ -208,8 +317,6 @@ int fill(FoldArgs& a, const float* Wq, const float* Wk, const float* Wv, const f
     a.ws = ws;
     return 0;
 }
-
-int blocks_for(int64_t n) { int64_t b = (n + 255) / 256; return (int)(b < 1 ? 1 : (b > 4096 ? 4096 : b)); }
 
 }  // namespace
 
@@ -226,10 +333,8 @@ PFO_API int pfo_fold_attention_fwd(const float* Wq, const float* Wk, const float
     if (fill(a, Wq, Wk, Wv, b_in, Wo, bo, W1, b1, tb, d, F, H, ekp, workspace)) return (int)cudaErrorInvalidValue;
     a.Wqk = Wqk; a.cqk = cqk; a.Wc1T = Wc1T;
     cudaStream_t s = (cudaStream_t)stream;
-    const int64_t n1 = a.E + (int64_t)H * a.E * (a.Ek + 1) + (int64_t)H * ekp * d;
-    fold_fwd1_kernel<<<blocks_for(n1), 256, 0, s>>>(a);
-    const int64_t n2 = (int64_t)H * ekp + (int64_t)(H * ekp + d) * d;
-    fold_fwd2_kernel<<<blocks_for(n2), 256, 0, s>>>(a);
+    fold_fwd1_kernel<<<fold_fwd1_jobs(d, F, H), 256, 0, s>>>(a);
+    fold_fwd2_kernel<<<fold_fwd2_jobs(d, F, H), 256, 0, s>>>(a);
     PFO_LAUNCH_CHECK();
 }
 
@@ -244,10 +349,7 @@ PFO_API int pfo_fold_attention_bwd(const float* Wq, const float* Wk, const float
     a.gWqk = gWqk; a.gcqk = gcqk; a.gWc1T = gWc1T;
     a.gWq = gWq; a.gWk = gWk; a.gWv = gWv; a.gb_in = gb_in; a.gWo = gWo; a.gbo = gbo; a.gW1 = gW1; a.gb1 = gb1; a.gtb = gtb;
     cudaStream_t s = (cudaStream_t)stream;
-    const int64_t E = a.E, R = a.Ek + 1;
-    const int64_t n1 = (int64_t)d * (E + d) + d + H * R * E + E + E * d + E + E * a.Ek;
-    fold_bwd1_kernel<<<blocks_for(n1), 256, 0, s>>>(a);
-    const int64_t n2 = E * E + E * R + 2 * E + E * d + d;
-    fold_bwd2_kernel<<<blocks_for(n2), 256, 0, s>>>(a);
+    fold_bwd1_kernel<<<fold_bwd1_jobs(d, F, H), 256, 0, s>>>(a);
+    fold_bwd2_kernel<<<fold_bwd2_jobs(d, F, H), 256, 0, s>>>(a);
     PFO_LAUNCH_CHECK();
 }

@@ -72,6 +72,33 @@ class ModelConfig:
         return 3 if self.updater == "gru" else 1
 
 
+class _FoldAttention(torch.autograd.Function):
+    """(Wq, Wk, Wv, b_in, Wo, bo, W1, b1, tb) -> (Wqk, cqk, Wc1T) and its adjoint, two kernel launches each way."""
+
+    @staticmethod
+    def forward(ctx, cfg, Wq, Wk, Wv, b_in, Wo, bo, W1, b1, tb):
+        d, F, H, ekp = cfg.d, cfg.n_edge_feat, cfg.n_heads, cfg.ekp
+        dev = Wq.device
+        w = [t.detach().contiguous() for t in (Wq, Wk, Wv, b_in, Wo, bo, W1, b1, tb)]
+        ws = torch.empty(int(_lib.query("pfo_fold_attention_workspace_doubles", d, F, H)), dtype=torch.float64, device=dev)
+        Wqk = torch.empty(H * ekp, d, device=dev)
+        cqk = torch.empty(H * ekp, device=dev)
+        Wc1T = torch.empty(H * ekp + d, d, device=dev)
+        _lib.call("pfo_fold_attention_fwd", *[ptr(t) for t in w], d, F, H, ekp, ptr(ws), ptr(Wqk), ptr(cqk), ptr(Wc1T))
+        ctx.cfg, ctx.w, ctx.ws = cfg, w, ws
+        return Wqk, cqk, Wc1T
+
+    @staticmethod
+    def backward(ctx, gWqk, gcqk, gWc1T):
+        cfg, w, ws = ctx.cfg, ctx.w, ctx.ws
+        d, F, H, ekp = cfg.d, cfg.n_edge_feat, cfg.n_heads, cfg.ekp
+        g_in = [gWqk.contiguous(), gcqk.contiguous(), gWc1T.contiguous()]
+        g_out = [torch.empty_like(t) for t in w]
+        _lib.call("pfo_fold_attention_bwd", *[ptr(t) for t in w], d, F, H, ekp, ptr(ws), *[ptr(t) for t in g_in],
+                  *[ptr(t) for t in g_out])
+        return (None,) + tuple(g_out)
+
+
 class TGNState:
     """memory / last_update / pending messages of every node, resident in HBM.
 
@@ -180,6 +207,7 @@ class TGNEngine:
         # device-resident batch counter keying the dropout stream (bumped on the stream each batch, so a
         # captured CUDA graph of the step draws fresh masks on every replay)
         self.step_ctr = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.side = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
         if state is None:        # memory-less models still need the compaction scratch
             self.state = TGNState(self.n_nodes, ModelConfig(d=cfg.d, n_edge_feat=cfg.n_edge_feat), self.device)
 
@@ -216,15 +244,28 @@ class TGNEngine:
             flat += [params[pre + "weight_ih"].contiguous(), params[pre + "weight_hh"].contiguous(),
                      params[pre + "bias_ih"].contiguous(), params[pre + "bias_hh"].contiguous()]
         if c.embedding == "graph_attention":
-            flat += self._fold_attention(params, tb)
+            flat += self._layer_params(params)
         elif c.embedding == "time":
             flat += [params["embedding_module.embedding_layer.weight"].reshape(d).contiguous(),
                      params["embedding_module.embedding_layer.bias"].contiguous()]
         return flat
 
-    def _fold_attention(self, params, tb):
-        """Per layer, the five GEMM operands the kernels consume, folded from the reference's ten tensors with
-        differentiable fp64 torch ops on the (tiny) weights -- autograd carries the gradients back:
+    def _layer_params(self, params):
+        """The reference's ten tensors per attention layer, in the order the fold kernels take them
+        (model/temporal_attention.py:26-32 nn.MultiheadAttention + MergeLayer utils/utils.py:7-8)."""
+        out = []
+        for l in range(self.cfg.n_layers):
+            a = f"embedding_module.attention_models.{l}."
+            m = a + "multi_head_target."
+            out += [params[k].contiguous() for k in (
+                m + "q_proj_weight", m + "k_proj_weight", m + "v_proj_weight", m + "in_proj_bias",
+                m + "out_proj.weight", m + "out_proj.bias", a + "merger.fc1.weight", a + "merger.fc1.bias",
+                a + "merger.fc2.weight", a + "merger.fc2.bias")]
+        return out
+
+    def fold_layers(self, raw, tb):
+        """Per layer, the five GEMM operands the kernels consume, folded from the reference's ten tensors
+        (pfo_fold_attention_fwd, csrc/fold_kernels.cu; fp64 arithmetic on the weights):
 
           Wqk  [H*ekp, d], cqk [H*ekp]   qk_h = (scale Wk_h^T Wq_h[:, :d]) h_q + scale Wk_h^T (Wq_h[:, d:] te(0) + bq_h)
           Wc1T [H*ekp + d, d]            fc1([out_proj(attn) | h_q]) as ONE contraction over [XB | h_q]:
@@ -232,43 +273,40 @@ class TGNEngine:
                                          (out-proj bias, valid rows only) and the `one` row = b1; last d rows = W1b^T
           W2, b2                         fc2
         K/V projections, the query projection, the out-projection and fc1 never materialise per query
-        (model/temporal_attention.py:52-90, utils/utils.py:14-17)."""
-        c = self.cfg
-        d, E, Ek, H, ekp = c.d, c.E, c.Ek, c.n_heads, c.ekp
-        hd = E // H
-        scale = 1.0 / math.sqrt(hd)
-        D = torch.float64
-        te0 = torch.cos(tb).to(D)                                # TimeEncode(0) (embedding_module.py:92)
-        out = []
+        (model/temporal_attention.py:52-90, utils/utils.py:14-17).  The fold only touches weights, so it runs on
+        a side stream (a parallel branch of the captured graph) while the batch is sampled; `join_fold` is the
+        join point.  Returns (folded operands per layer, fp64 workspaces kept for the adjoint)."""
+        c, dev = self.cfg, self.device
+        d, F, H, ekp = c.d, c.n_edge_feat, c.n_heads, c.ekp
+        n_ws = int(_lib.query("pfo_fold_attention_workspace_doubles", d, F, H))
+        folded, wss = [], []
         for l in range(c.n_layers):
-            a = f"embedding_module.attention_models.{l}."
-            Wq = params[a + "multi_head_target.q_proj_weight"].to(D)
-            Wk = params[a + "multi_head_target.k_proj_weight"].to(D).view(H, hd, Ek)
-            Wv = params[a + "multi_head_target.v_proj_weight"].to(D).view(H, hd, Ek)
-            b_in = params[a + "multi_head_target.in_proj_bias"].to(D)
-            Wo = params[a + "multi_head_target.out_proj.weight"].to(D)
-            bo = params[a + "multi_head_target.out_proj.bias"].to(D)
-            W1 = params[a + "merger.fc1.weight"].to(D)
-            b1 = params[a + "merger.fc1.bias"].to(D)
-            cq = Wq[:, d:] @ te0 + b_in[:E]
-            WkT = Wk.transpose(1, 2)                             # [H, Ek, hd]
-            A = scale * (WkT @ Wq[:, :d].view(H, hd, d))         # [H, Ek, d]
-            cA = scale * (WkT @ cq.view(H, hd, 1)).squeeze(2)    # [H, Ek]
-            Wqk = torch.nn.functional.pad(A, (0, 0, 0, ekp - Ek)).reshape(H * ekp, d)
-            cqk = torch.nn.functional.pad(cA, (0, ekp - Ek)).reshape(H * ekp)
-            WvA = torch.cat([Wv, b_in[2 * E:].view(H, hd, 1)], dim=2)          # [H, hd, Ek+1]
-            WoH = Wo.view(E, H, hd).permute(1, 0, 2)             # [H, E, hd]
-            W1a, W1b = W1[:, :E], W1[:, E:]
-            Bh = W1a @ (WoH @ WvA)                               # [H, d, Ek+1]
-            tail0 = torch.cat([(W1a @ bo).unsqueeze(0), b1.unsqueeze(0), Bh.new_zeros(ekp - Ek - 3, d)], dim=0)
-            tailz = Bh.new_zeros(ekp - Ek - 1, d)
-            rows = []
-            for h in range(H):
-                rows += [Bh[h].t(), tail0 if h == 0 else tailz]
-            Wc1T = torch.cat(rows + [W1b.t()], dim=0)            # [H*ekp + d, d]
-            out += [Wqk.float().contiguous(), cqk.float().contiguous(), Wc1T.float().contiguous(),
-                    params[a + "merger.fc2.weight"].contiguous(), params[a + "merger.fc2.bias"].contiguous()]
-        return out
+            w = raw[l]
+            wss.append(torch.empty(n_ws, dtype=torch.float64, device=dev))
+            folded.append([torch.empty(H * ekp, d, device=dev), torch.empty(H * ekp, device=dev),
+                           torch.empty(H * ekp + d, d, device=dev), w[8], w[9]])
+        cur = torch.cuda.current_stream(dev)
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            for l in range(c.n_layers):
+                w, f = raw[l], folded[l]
+                _lib.call("pfo_fold_attention_fwd", *[ptr(t) for t in w[:8]], ptr(tb), d, F, H, ekp, ptr(wss[l]),
+                          ptr(f[0]), ptr(f[1]), ptr(f[2]))
+        return folded, wss
+
+    def join_side(self):
+        torch.cuda.current_stream(self.device).wait_stream(self.side)
+
+    def unfold_layer_grads(self, raw, tb, wss, g_folded, g_raw, g_tb_fold):
+        """Adjoint of `fold_layers` on the side stream: d/d(Wqk, cqk, Wc1T) -> d/d(the ten reference tensors)."""
+        c, dev = self.cfg, self.device
+        d, F, H, ekp = c.d, c.n_edge_feat, c.n_heads, c.ekp
+        self.side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self.side):
+            for l in range(c.n_layers):
+                w, gf, gr = raw[l], g_folded[l], g_raw[l]
+                _lib.call("pfo_fold_attention_bwd", *[ptr(t) for t in w[:8]], ptr(tb), d, F, H, ekp, ptr(wss[l]),
+                          ptr(gf[0]), ptr(gf[1]), ptr(gf[2]), *[ptr(t) for t in gr[:8]], ptr(g_tb_fold[l]))
 
     # ------------------------------------------------------------------ public step
     def compute_temporal_embeddings(self, params, src, dst, extra_groups, ts, eidx, n_neighbors,
@@ -439,7 +477,7 @@ class TGNEngine:
         M, n = tp.M, tp.n
         ldc, hq = c.ldcat, H * ekp
         Wqk, cqk, Wc1T, W2, b2 = W[tp.layer - 1]
-        gWqk, gcqk, gWc1T, gW2, gb2 = dW[tp.layer - 1]
+        gWqk, gcqk, gWc1T, gW2, gb2 = dW[tp.layer - 1][:5]
         ws = self.ws
         hq_ptr = tp.CAT.data_ptr() + hq * F4
         # merge MLP: fc2, then fc1 straight down to [dXB | dh_query]
@@ -474,9 +512,10 @@ class TGNStepFunction(torch.autograd.Function):
         it = iter(flat)
         tw, tb = next(it), next(it)
         cellW = [next(it) for _ in range(4)] if c.use_memory else None
-        layerW, embW = [], None
+        layerW, embW, rawW, fold_ws = [], None, None, None
         if c.embedding == "graph_attention":
-            layerW = [[next(it) for _ in range(5)] for _ in range(c.n_layers)]
+            rawW = [[next(it) for _ in range(10)] for _ in range(c.n_layers)]
+            layerW, fold_ws = eng.fold_layers(rawW, tb)             # side stream; joined before the attention
         elif c.embedding == "time":
             embW = [next(it), next(it)]
         q_nodes, q_ts, n, B = batch["q_nodes"], batch["q_ts"], batch["n"], batch["B"]
@@ -504,6 +543,7 @@ class TGNStepFunction(torch.autograd.Function):
         td = None
         qslots = eng._slots(q_nodes)
         if c.embedding == "graph_attention":
+            eng.join_side()
             emb, tape = eng._attention_forward(tree, layerW, H0, save)
         elif c.embedding == "time":
             n_src = batch["src"].shape[0]
@@ -526,7 +566,8 @@ class TGNStepFunction(torch.autograd.Function):
             _lib.call("pfo_gather_rows", ptr(Hnew), d, ptr(qslots), Q, d, ptr(out), d)
         if need_grad:
             ctx.eng, ctx.save = eng, save
-            ctx.pack = dict(flat=flat, cellW=cellW, layerW=layerW, embW=embW, tape=tape, tab=tab, u_max=u_max,
+            ctx.pack = dict(flat=flat, cellW=cellW, layerW=layerW, rawW=rawW, fold_ws=fold_ws, embW=embW, tape=tape,
+                            tab=tab, u_max=u_max,
                             Hnew=Hnew, qslots=qslots, td=td, Q=Q)
         return out
 
@@ -537,13 +578,21 @@ class TGNStepFunction(torch.autograd.Function):
         d = c.d
         dOut = dOut.contiguous()
         flat = pk["flat"]
-        grads = [torch.zeros_like(t) for t in flat]
+        sizes = [t.numel() for t in flat]              # one zero-fill for all operand gradients
+        gbuf = torch.zeros(sum(sizes), device=dev)
+        grads = [g.view_as(t) for g, t in zip(gbuf.split(sizes), flat)]
         it = iter(grads)
         g_tw, g_tb = next(it), next(it)
         g_cell = [next(it) for _ in range(4)] if c.use_memory else None
-        g_layers, g_emb = [], None
+        g_layers, g_raw, g_emb = [], [], None
         if c.embedding == "graph_attention":
-            g_layers = [[next(it) for _ in range(5)] for _ in range(c.n_layers)]
+            g_raw = [[next(it) for _ in range(10)] for _ in range(c.n_layers)]
+            fsz = [t.numel() for t in pk["layerW"][0][:3]]
+            fbuf = torch.zeros(c.n_layers * (sum(fsz) + d), device=dev)     # folded-operand grads + the fold's d/dtb
+            for l, chunk in enumerate(fbuf.split(sum(fsz) + d)):
+                gq, gc, gw, gt = chunk.split(fsz + [d])
+                g_layers.append([gq.view_as(pk["layerW"][l][0]), gc, gw.view_as(pk["layerW"][l][2]),
+                                 g_raw[l][8], g_raw[l][9], gt])
         elif c.embedding == "time":
             g_emb = [next(it), next(it)]
         u_max = pk["u_max"]
@@ -578,8 +627,14 @@ class TGNStepFunction(torch.autograd.Function):
                 if tp.layer > 1:
                     stack.append((tp.child_q, tp.dTq))
                     stack.append((tp.child_n, tp.dT))
+            # the fold's adjoint runs beside the memory-updater backward (it needs only the finished operand grads)
+            eng.unfold_layer_grads(pk["rawW"], flat[1], pk["fold_ws"], g_layers, g_raw, [g[5] for g in g_layers])
             g_tw.add_(save["g_twtb"][:d])
             g_tb.add_(save["g_twtb"][d:])
         if c.use_memory:
             eng.node_table_backward(pk["tab"], dH0, g_cell)
+        if attention_grad:
+            eng.join_side()
+            for g in g_layers:
+                g_tb.add_(g[5])
         return (None, None) + tuple(grads)

@@ -591,3 +591,55 @@ def test_wgrad_tf32_tma(M, N, K, passes):
     dW3 = torch.zeros(N, K, device=DEV)
     _lib.call("pfo_wgrad_tf32", ptr(Gd), ldg, ptr(Ad), lda, None, M, None, N, K, ptr(dW3), K, None, 0, ptr(ws), passes)
     assert torch.equal(dW3, dW)
+
+
+# ------------------------------------------------------------------------------ attention operand folding
+def _fold_reference(cfg, Wq, Wk, Wv, b_in, Wo, bo, W1, b1, tb):
+    """fp64 torch restatement of the fold (differentiable): what the per-query kernels assume about Wqk / cqk / Wc1T,
+    derived from nn.MultiheadAttention + MergeLayer (model/temporal_attention.py:52-90, utils/utils.py:14-17)."""
+    import math
+    d, E, Ek, H, ekp = cfg.d, cfg.E, cfg.Ek, cfg.n_heads, cfg.ekp
+    hd = E // H
+    scale = 1.0 / math.sqrt(hd)
+    D = torch.float64
+    Wq, Wk, Wv, b_in, Wo, bo, W1, b1, tb = (t.to(D) for t in (Wq, Wk, Wv, b_in, Wo, bo, W1, b1, tb))
+    te0 = torch.cos(tb)
+    cq = Wq[:, d:] @ te0 + b_in[:E]
+    WkT = Wk.view(H, hd, Ek).transpose(1, 2)
+    A = scale * (WkT @ Wq[:, :d].reshape(H, hd, d))
+    cA = scale * (WkT @ cq.view(H, hd, 1)).squeeze(2)
+    Wqk = torch.nn.functional.pad(A, (0, 0, 0, ekp - Ek)).reshape(H * ekp, d)
+    cqk = torch.nn.functional.pad(cA, (0, ekp - Ek)).reshape(H * ekp)
+    WvA = torch.cat([Wv.view(H, hd, Ek), b_in[2 * E:].view(H, hd, 1)], dim=2)
+    WoH = Wo.view(E, H, hd).permute(1, 0, 2)
+    W1a, W1b = W1[:, :E], W1[:, E:]
+    Bh = W1a @ (WoH @ WvA)
+    tail0 = torch.cat([(W1a @ bo).unsqueeze(0), b1.unsqueeze(0), Bh.new_zeros(ekp - Ek - 3, d)], dim=0)
+    tailz = Bh.new_zeros(ekp - Ek - 1, d)
+    rows = []
+    for h in range(H):
+        rows += [Bh[h].t(), tail0 if h == 0 else tailz]
+    return Wqk, cqk, torch.cat(rows + [W1b.t()], dim=0)
+
+
+@pytest.mark.parametrize("d,F,H", [(64, 1, 2), (32, 3, 2), (64, 1, 4), (32, 2, 1)])
+def test_fold_attention_forward_and_adjoint(d, F, H):
+    """pfo_fold_attention_fwd / _bwd against the fp64 torch restatement and its autograd gradients."""
+    from pfotgnrec_b200.engine import ModelConfig, _FoldAttention
+    cfg = ModelConfig(d=d, n_edge_feat=F, n_heads=H)
+    g = torch.Generator(device="cpu").manual_seed(d + F + H)
+    E, Ek = 2 * d, 2 * d + F
+    shapes = [(E, E), (E, Ek), (E, Ek), (3 * E,), (E, E), (E,), (d, E + d), (d,), (d,)]
+    w = [(torch.randn(*s, generator=g) * 0.3).to(DEV).requires_grad_(True) for s in shapes]
+    w64 = [t.detach().double().requires_grad_(True) for t in w]
+    ref = _fold_reference(cfg, *w64)
+    got = _FoldAttention.apply(cfg, *w)
+    for a, b in zip(got, ref):
+        assert a.shape == b.shape
+        assert rel_err(a.detach().cpu().numpy(), b.detach().cpu().numpy()) < 1e-6
+    cot = [torch.randn(t.shape, generator=g).to(DEV) for t in got]
+    torch.autograd.backward(got, cot)
+    torch.autograd.backward(ref, [c.double() for c in cot])
+    names = ["Wq", "Wk", "Wv", "b_in", "Wo", "bo", "W1", "b1", "tb"]
+    for nm, a, b in zip(names, w, w64):
+        assert rel_err(a.grad.cpu().numpy(), b.grad.cpu().numpy()) < 1e-6, nm
