@@ -15,6 +15,8 @@ MASK = np.uint64(0xFFFFFFFF)
 PURPOSE_NEG = 1        # candidate key of (event, item position)
 PURPOSE_NEG_REPL = 2   # j-th draw with replacement of an event
 PURPOSE_NBR = 3        # uniform temporal-neighbour slot j of query q
+PURPOSE_DROPOUT = 4    # attention-dropout factor of (query, head * n + slot, step)
+PURPOSE_NEG_SEQ = 5    # attempt a of slot j of an event's draw without replacement (counter word 2 = j | a << 16)
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):

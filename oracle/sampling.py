@@ -9,7 +9,7 @@
 """
 import numpy as np
 
-from .philox import philox4x32_10, mulhi32, PURPOSE_NEG, PURPOSE_NEG_REPL
+from .philox import philox4x32_10, mulhi32, PURPOSE_NEG, PURPOSE_NEG_REPL, PURPOSE_NEG_SEQ
 
 
 def sample_candidates(event_ids, items_sorted, port_ptr, port_items, size, seed):
@@ -20,10 +20,15 @@ def sample_candidates(event_ids, items_sorted, port_ptr, port_items, size, seed)
     port_ptr/port_items   CSR of the held item ids per interaction (utils.py:76-81)
     Returns int64[B, size] item ids.
 
-    Without replacement when enough items are available (utils.py:107-111): every
-    available item at position p of `items_sorted` gets the key
-    (philox(g_lo, g_hi, p, PURPOSE_NEG)[0], p); the sample is the `size` smallest keys in
-    ascending order (the 32-bit draw first, the position breaks ties).  With replacement otherwise (:99-105): draw j is
+    Without replacement when enough items are available (utils.py:107-111), by one of two exact schemes chosen
+    from the sizes alone:
+      * size <= 32 and 8 * size <= n_available -- sequential rejection: slot j keeps the first draw
+        available[mulhi32(philox(g_lo, g_hi, j | a << 16, PURPOSE_NEG_SEQ)[0], n_available)], a = 0, 1, ..,
+        that no slot < j holds;
+      * otherwise every available item at position p of `items_sorted` gets the key
+        (philox(g_lo, g_hi, p, PURPOSE_NEG)[0], p) and the sample is the `size` smallest keys in ascending order
+        (the 32-bit draw first, the position breaks ties).
+    With replacement when fewer items are available than requested (:99-105): draw j is
     available[mulhi32(philox(g_lo, g_hi, j, PURPOSE_NEG_REPL)[0], n_available)].
     """
     event_ids = np.asarray(event_ids, dtype=np.int64)
@@ -42,6 +47,16 @@ def sample_candidates(event_ids, items_sorted, port_ptr, port_items, size, seed)
             j = np.arange(size, dtype=np.int64)
             x0 = philox4x32_10(g & 0xFFFFFFFF, (g >> 32) & 0xFFFFFFFF, j, PURPOSE_NEG_REPL, k0, k1)[0]
             out[b] = items_sorted[pos[mulhi32(x0, n_av)]]
+        elif size <= 32 and 8 * size <= n_av:
+            glo, ghi = g & 0xFFFFFFFF, (g >> 32) & 0xFFFFFFFF
+            q = mulhi32(philox4x32_10(glo, ghi, np.arange(size, dtype=np.int64), PURPOSE_NEG_SEQ, k0, k1)[0], n_av)
+            if np.unique(q).shape[0] != size:                  # rare: resolve the collisions slot by slot
+                for j in range(1, size):
+                    a = 0
+                    while q[j] in q[:j]:
+                        a += 1
+                        q[j] = mulhi32(philox4x32_10(glo, ghi, j | (a << 16), PURPOSE_NEG_SEQ, k0, k1)[0], n_av)
+            out[b] = items_sorted[pos[q]]
         else:
             x0 = philox4x32_10(g & 0xFFFFFFFF, (g >> 32) & 0xFFFFFFFF, pos, PURPOSE_NEG, k0, k1)[0]
             o = np.lexsort((pos, x0))[:size]

@@ -4,8 +4,10 @@
 // Replaces reference utils/utils.py:65-114 (RandEdgeSampler: np.unique + setdiff1d +
 // np.random.choice per interaction) and the inline per-interaction / per-candidate Python
 // loops of main.py:197-304 (np.cov x21, rankdata x2, argsort x2 per interaction).
-// One warp per interaction: Philox keys over the item universe with a threshold select for
-// the K candidates, lanes 0..K then own one candidate each for y_mv and the rank fusion.
+// One warp per interaction: the K candidates are drawn without replacement by sequential rejection
+// (slot j takes the first draw of its own Philox stream that no earlier slot holds -- ~K Philox calls per
+// interaction; when K is not small against the available items the draw falls back to "K smallest of one
+// Philox key per item"), lanes 0..K then own one candidate each for y_mv and the rank fusion.
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -53,6 +55,57 @@ __device__ int nth_available(const int32_t* items, int M, const int32_t* held, i
     return pos;
 }
 
+// positions (in the sorted universe) of the distinct held items that belong to it, ascending, in hs[0..nH)
+// (np.setdiff1d semantics, utils.py:96); warp-cooperative, nP <= 32.  Returns nH.
+__device__ int held_positions(const int32_t* held, int nP, const int32_t* items, int M, int lane, int* hs) {
+    int hp = -1, v = 0;
+    if (lane < nP) { v = held[lane]; hp = find_pos(items, M, v); }
+    for (int k = 0; k < nP; ++k) {                      // duplicates: keep the first occurrence
+        const int vk = __shfl_sync(0xffffffffu, v, k);
+        if (lane > k && lane < nP && v == vk) hp = -1;
+    }
+    int rank = 0;
+    for (int k = 0; k < nP; ++k) {
+        const int hk = __shfl_sync(0xffffffffu, hp, k);
+        rank += (hk >= 0 && hk < hp) ? 1 : 0;
+    }
+    __syncwarp();
+    if (hp >= 0) hs[rank] = hp;
+    __syncwarp();
+    return __popc(__ballot_sync(0xffffffffu, hp >= 0));
+}
+
+// universe position of the q-th available item given the ascending held positions
+__device__ __forceinline__ int skip_held(const int* hs, int nH, int q) {
+    int pos = q;
+    for (int i = 0; i < nH; ++i) if (hs[i] <= pos) ++pos;
+    return pos;
+}
+
+// `size` (<= 32) distinct indices in [0, n_av), slot j in lane j: slot j keeps the first draw
+// mulhi32(philox(event, j | attempt << 16, NEG_SEQ), n_av), attempt = 0, 1, .., that no slot < j holds
+// (sequential rejection = uniform sampling without replacement; shared with oracle/sampling.py)
+__device__ int draw_distinct(uint32_t g_lo, uint32_t g_hi, uint32_t k0, uint32_t k1, int size, int n_av, int lane) {
+    int q = -1;
+    uint32_t attempt = 0;
+    if (lane < size) q = (int)mulhi32(philox4x32_10(g_lo, g_hi, (uint32_t)lane, PFO_PURPOSE_NEG_SEQ, k0, k1).x, (uint32_t)n_av);
+    for (int j = 1; j < size; ++j) {
+        for (;;) {
+            const int qj = __shfl_sync(0xffffffffu, q, j);
+            if (!__any_sync(0xffffffffu, lane < j && q == qj)) break;
+            if (lane == j) {
+                ++attempt;
+                q = (int)mulhi32(philox4x32_10(g_lo, g_hi, (uint32_t)j | (attempt << 16), PFO_PURPOSE_NEG_SEQ, k0, k1).x,
+                                 (uint32_t)n_av);
+            }
+        }
+    }
+    return q;
+}
+
+// the sampler's rule, a function of the sizes only: sequential rejection when the sample is small against the pool
+__device__ __forceinline__ bool use_rejection(int size, int n_av) { return size <= 32 && 8 * size <= n_av; }
+
 struct MvArgs {
     const int64_t* event_ids; const int32_t* day_idx; const int32_t* pos_stock;
     const int64_t* port_ptr; const int32_t* port_items;
@@ -66,6 +119,7 @@ __global__ void __launch_bounds__(kWarps * 32)
 mv_select_kernel(const MvArgs p) {
     __shared__ unsigned long long keys[kWarps][kCap];
     __shared__ int counts[kWarps];
+    __shared__ int hs[kWarps][32];
     __shared__ double Ssum[kWarps][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t warp = (int64_t)blockIdx.x * kWarps + wib;
@@ -77,7 +131,11 @@ mv_select_kernel(const MvArgs p) {
         const int64_t pb = p.port_ptr[b];
         const int nP = (int)(p.port_ptr[b + 1] - pb);
         const int32_t* held = p.port_items + pb;
-        const int n_av = M - count_held_in_universe(held, nP, p.items, M, lane);
+        const bool small_p = nP <= 32;                  // held positions fit the per-warp table
+        int nH = 0;
+        if (p.sample) nH = small_p ? held_positions(held, nP, p.items, M, lane, hs[wib])
+                                   : count_held_in_universe(held, nP, p.items, M, lane);
+        const int n_av = M - nH;
         int my_cand = 0;
         if (lane == 0) my_cand = p.pos_stock[b];
         if (!p.sample) {
@@ -86,8 +144,13 @@ mv_select_kernel(const MvArgs p) {
             if (lane >= 1 && lane <= K) {
                 const int j = lane - 1;
                 const uint32_t x0 = philox4x32_10(g_lo, g_hi, (uint32_t)j, PFO_PURPOSE_NEG_REPL, p.k0, p.k1).x;
-                my_cand = p.items[nth_available(p.items, M, held, nP, (int)mulhi32(x0, (uint32_t)n_av))];
+                const int q = (int)mulhi32(x0, (uint32_t)n_av);
+                my_cand = p.items[small_p ? skip_held(hs[wib], nH, q) : nth_available(p.items, M, held, nP, q)];
             }
+        } else if (use_rejection(K, n_av)) {
+            const int q = __shfl_up_sync(0xffffffffu, draw_distinct(g_lo, g_hi, p.k0, p.k1, K, n_av, lane), 1);
+            if (lane >= 1 && lane <= K)
+                my_cand = p.items[small_p ? skip_held(hs[wib], nH, q) : nth_available(p.items, M, held, nP, q)];
         } else {
             // threshold select: expected count ~ K + 4 sqrt(K) + 8 keys below the cut
             double frac = ((double)K + 4.0 * sqrt((double)K) + 8.0) / (double)n_av;
@@ -199,22 +262,34 @@ sample_candidates_kernel(const int64_t* __restrict__ event_ids, const int64_t* _
                          int size, uint32_t k0, uint32_t k1, int pow2, int32_t* __restrict__ out) {
     extern __shared__ unsigned long long sk[];      // [pow2]
     __shared__ int n_held_s;
+    __shared__ int hs[32];
     const int b = blockIdx.x;
     const int64_t g = event_ids[b];
     const uint32_t g_lo = (uint32_t)(g & 0xffffffffll), g_hi = (uint32_t)((g >> 32) & 0xffffffffll);
     const int64_t pb = port_ptr[b];
     const int nP = (int)(port_ptr[b + 1] - pb);
     const int32_t* held = port_items + pb;
+    const bool small_p = nP <= 32;
     if (threadIdx.x < 32) {
-        const int c = count_held_in_universe(held, nP, items, M, threadIdx.x);
+        const int c = small_p ? held_positions(held, nP, items, M, threadIdx.x, hs)
+                              : count_held_in_universe(held, nP, items, M, threadIdx.x);
         if (threadIdx.x == 0) n_held_s = c;
     }
     __syncthreads();
-    const int n_av = M - n_held_s;
+    const int nH = n_held_s, n_av = M - nH;
     if (n_av < size) {
         for (int j = threadIdx.x; j < size; j += blockDim.x) {
             const uint32_t x0 = philox4x32_10(g_lo, g_hi, (uint32_t)j, PFO_PURPOSE_NEG_REPL, k0, k1).x;
-            out[(int64_t)b * size + j] = items[nth_available(items, M, held, nP, (int)mulhi32(x0, (uint32_t)n_av))];
+            const int q = (int)mulhi32(x0, (uint32_t)n_av);
+            out[(int64_t)b * size + j] = items[small_p ? skip_held(hs, nH, q) : nth_available(items, M, held, nP, q)];
+        }
+        return;
+    }
+    if (use_rejection(size, n_av)) {
+        if (threadIdx.x < 32) {
+            const int q = draw_distinct(g_lo, g_hi, k0, k1, size, n_av, threadIdx.x);
+            if (threadIdx.x < size)
+                out[(int64_t)b * size + threadIdx.x] = items[small_p ? skip_held(hs, nH, q) : nth_available(items, M, held, nP, q)];
         }
         return;
     }

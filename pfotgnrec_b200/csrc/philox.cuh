@@ -6,6 +6,7 @@
 #define PFO_PURPOSE_NEG_REPL 2u
 #define PFO_PURPOSE_NBR 3u
 #define PFO_PURPOSE_DROPOUT 4u
+#define PFO_PURPOSE_NEG_SEQ 5u
 
 struct Philox4 { uint32_t x, y, z, w; };
 
