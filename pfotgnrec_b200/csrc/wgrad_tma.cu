@@ -13,7 +13,7 @@
 //
 //   warp 0     TMA producer (G boxes + A boxes per stage, mbarrier full/empty ring)
 //   warp 1     MMA issuer (one lane): passes = 1 plain TF32, passes = 3 error-compensated 3xTF32
-//   warps 2-5  stage fix-up: zero the rows past the live row count (m_dev), split hi/lo in
+//   warps 2-9  stage fix-up: zero the rows past the live row count (m_dev), split hi/lo in
 //              3-pass mode; afterwards the same warps drain TMEM (epilogue)
 #include "common.cuh"
 #include <cuda.h>
@@ -34,6 +34,8 @@ constexpr int MAX_STAGES = 8;
 constexpr int EPI_LD = 36;
 constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
 constexpr int SMEM_LIMIT = 232448;
+constexpr int FIX_WARPS = 8;                // stage fix-up warps (two per scheduler: one could not hide its own latency)
+constexpr int WG_THREADS = 64 + 32 * FIX_WARPS;
 
 struct WgTmaArgs {
     float* partial;            // [S, N, Kaug]
@@ -104,7 +106,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 }
 
 template <int PASSES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmA, const WgTmaArgs p) {
     extern __shared__ uint8_t smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -139,7 +141,7 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(ready_bar(s), 4);
+            mbar_init(ready_bar(s), FIX_WARPS);
             mbar_init(empty_bar(s), 1);
         }
         mbar_init(done_bar, 1);
@@ -220,7 +222,7 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
         __syncwarp();
     } else {
         // ===== stage fix-up (mask the tail rows, split hi / lo), then the epilogue
-        const int t = tid - 64;                                    // 0..127
+        const int t = tid - 64;                                    // 0 .. 32 * FIX_WARPS - 1
         const int units = (G_BOXES + nkb) * (BOX_BYTES / 16);     // 16-byte units TMA wrote per stage
         int stage = 0; uint32_t phase = 0;
         for (int it = 0; it < n_iters; ++it) {
@@ -230,7 +232,7 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
             if (PASSES == 3 || live < R) {
                 float4* hi = reinterpret_cast<float4*>(sHi + (size_t)stage * stage_bytes);
                 float4* lo = reinterpret_cast<float4*>(sLo + (size_t)stage * stage_bytes);
-                for (int u = t; u < units; u += 128) {
+                for (int u = t; u < units; u += 32 * FIX_WARPS) {
                     const int row = (u % (BOX_BYTES / 16)) >> 3;
                     float4 v = hi[u];
                     if (row >= live) v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -250,7 +252,8 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
             if (lane == 0) mbar_arrive(ready_bar(stage));
             if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
-        // ---- epilogue: partial[slab][n][k]; warp q owns TMEM lanes [32q, 32q+32) = n rows
+        // ---- epilogue: partial[slab][n][k]; warp q owns TMEM lanes [32q, 32q+32) = n rows (warps 2-5 only)
+        if (warp < 6) {
         const int q = warp & 3;
         float* buf = sEpi + (size_t)(warp - 2) * 32 * EPI_LD;
         const int r_sub = lane >> 3, c4 = (lane & 7) * 4;
@@ -298,6 +301,7 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
             }
             __syncwarp();
         }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -308,18 +312,30 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
     }
 }
 
-__global__ void wgrad_tma_reduce_kernel(const float* __restrict__ partial, int S, int N, int K, int Kaug,
-                                        float* __restrict__ dW, int64_t lddw, float* __restrict__ db, int accumulate) {
+// dW (+)= sum over the slabs, in a fixed order (deterministic).  A CTA owns 32 consecutive outputs; its 8 warps
+// stride the slabs (8 independent chains of coalesced 128-byte reads), then the 8 sums are added in warp order.
+__global__ void __launch_bounds__(256)
+wgrad_tma_reduce_kernel(const float* __restrict__ partial, int S, int N, int K, int Kaug,
+                        float* __restrict__ dW, int64_t lddw, float* __restrict__ db, int accumulate) {
+    __shared__ float sm[8][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int total = N * Kaug;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        float s = 0.0f;
-        for (int y = 0; y < S; ++y) s += partial[(int64_t)y * total + i];   // fixed order: deterministic
+    const int i = blockIdx.x * 32 + lane;
+    float s = 0.0f;
+    if (i < total)
+        for (int y = w; y < S; y += 8) s += partial[(int64_t)y * total + i];
+    sm[w][lane] = s;
+    __syncthreads();
+    if (w == 0 && i < total) {
+        float t = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sm[k][lane];
         const int n = i / Kaug, k = i - n * Kaug;
         if (k < K) {
             float* d = dW + (int64_t)n * lddw + k;
-            *d = accumulate ? *d + s : s;
+            *d = accumulate ? *d + t : t;
         } else if (db) {
-            db[n] = accumulate ? db[n] + s : s;
+            db[n] = accumulate ? db[n] + t : t;
         }
     }
 }
@@ -341,7 +357,7 @@ int launch_wg(const CUtensorMap& mg, const CUtensorMap& ma, const WgTmaArgs& a, 
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    wgrad_tma_kernel<PASSES><<<grid, 192, smem, s>>>(mg, ma, a);
+    wgrad_tma_kernel<PASSES><<<grid, WG_THREADS, smem, s>>>(mg, ma, a);
     return (int)cudaGetLastError();
 }
 
@@ -389,6 +405,6 @@ PFO_API int pfo_wgrad_tf32(const float* G, int64_t ldg, const float* A, int64_t 
     int rc = passes == 3 ? launch_wg<3>(mg, ma, a, grid, smem, s) : launch_wg<1>(mg, ma, a, grid, smem, s);
     if (rc) return rc;
     const int total = N * a.Kaug;
-    wgrad_tma_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(workspace, a.S, N, K, a.Kaug, dW, lddw, db, accumulate);
+    wgrad_tma_reduce_kernel<<<(total + 31) / 32, 256, 0, s>>>(workspace, a.S, N, K, a.Kaug, dW, lddw, db, accumulate);
     PFO_LAUNCH_CHECK();
 }
