@@ -67,19 +67,49 @@ __device__ __forceinline__ void st_cols(float* __restrict__ p, const float (&v)[
 
 constexpr int kUnroll = 4;      // neighbour rows in flight per warp (independent gathers issued back to back)
 
+// Sum NV (power of two <= 32) per-lane values across the warp at once: each step of the butterfly halves the
+// number of values a lane carries (it sends one half, keeps and accumulates the other), then the usual
+// xor-reduction finishes.  NV + log2(32 / NV) - 1 shuffles instead of 5 * NV; the total of value v ends up in
+// lanes [v * 32 / NV, (v + 1) * 32 / NV).
+template <int NV, int O = 16>
+__device__ __forceinline__ float multi_reduce(float (&v)[NV], int lane) {
+    if constexpr (NV == 1) {
+        float r = v[0];
+#pragma unroll
+        for (int o = O; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+        return r;
+    } else {
+        const bool upper = (lane & O) != 0;
+        float h[NV / 2];
+#pragma unroll
+        for (int i = 0; i < NV / 2; ++i) {
+            const float send = upper ? v[i] : v[i + NV / 2];
+            const float keep = upper ? v[i + NV / 2] : v[i];
+            h[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);
+        }
+        return multi_reduce<NV / 2, O / 2>(h, lane);
+    }
+}
+
 // One warp per query; lane l owns feature columns [l*DPL, (l+1)*DPL) of the h and te segments and -- for the
 // per-slot scalars (neighbour id, dt, edge id, dropout factor, score, softmax weight) -- neighbour slot l.
-// The slot scalars are fetched with one coalesced load each and broadcast by shuffle; neighbour rows are
-// gathered kUnroll at a time before the arithmetic that consumes them, so the L2 latency of the gathers
-// overlaps instead of serialising behind the online softmax.
+//   phase A  slot scalars by one coalesced load each; neighbour rows gathered kUnroll at a time (independent L2
+//            requests in flight), x_j = [h_j | e_j | cos(dt_j w + b)] stashed in shared memory, the kUnroll * NH
+//            partial scores reduced across the warp together (multi_reduce), score of slot j kept in lane j
+//   phase B  softmax over the slots, lane-parallel: one exp per lane and head, two warp reductions per head
+//   phase C  xbar_h = sum_j p'_hj x_j from the stash (p' = softmax weight times the dropout factor)
 template <int DPL, int NH>
 __global__ void __launch_bounds__(128)
 attn_nbr_fwd_kernel(const NbrArgs p) {
+    extern __shared__ float smem[];
     constexpr int d = 32 * DPL;
-    const int lane = threadIdx.x & 31;
+    constexpr int SW = 2 * d + 32;                      // stash row: [h | cos | e(32)]
+    constexpr int NV = kUnroll * NH;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int F = p.F, n = p.n, ekp = p.ekp;
+    float* stash = smem + (size_t)wib * n * SW;
     const int c0 = lane * DPL;
     const uint32_t step = p.step + (p.step_dev ? *p.step_dev : 0u);
     float tw[DPL], tb[DPL];
@@ -93,19 +123,20 @@ attn_nbr_fwd_kernel(const NbrArgs p) {
             dt_l = __ldg(p.dt + q * n + lane);
             ei_l = __ldg(p.eidx + q * n + lane);
         }
-        float qa[NH][DPL], qg[NH][DPL], qe[NH], keep[NH];
-        float ah[NH][DPL], at[NH][DPL], ae[NH], ap[NH], mx[NH], l[NH], sj[NH];
+        const bool live_l = id_l >= 0;                  // padded neighbours are masked (embedding_module.py:154)
+        const unsigned live_mask = __ballot_sync(0xffffffffu, live_l);
+        const bool any = live_mask != 0u;
+        float qa[NH][DPL], qg[NH][DPL], qe[NH], sj[NH];
 #pragma unroll
         for (int h = 0; h < NH; ++h) {
             const float* qk = p.QK + (q * NH + h) * ekp;
             ld_cols<DPL>(qk + c0, qa[h]);
 #pragma unroll
-            for (int i = 0; i < DPL; ++i) { qg[h][i] = qk[d + F + c0 + i]; ah[h][i] = 0.f; at[h][i] = 0.f; }
+            for (int i = 0; i < DPL; ++i) qg[h][i] = qk[d + F + c0 + i];
             qe[h] = lane < F ? qk[d + lane] : 0.0f;
-            keep[h] = (id_l >= 0) ? keep_scale(p, step, q, h, lane) : 1.0f;    // dropout factor of slot `lane`
-            ae[h] = 0.f; ap[h] = 0.f; mx[h] = -INFINITY; l[h] = 0.f; sj[h] = 0.f;
+            sj[h] = 0.0f;
         }
-        const bool any = __ballot_sync(0xffffffffu, id_l >= 0) != 0u;   // padded neighbours are masked (embedding_module.py:154)
+        // ---- phase A
         for (int j0 = 0; j0 < n; j0 += kUnroll) {
             int id[kUnroll];
             float dtj[kUnroll], xe[kUnroll], xh[kUnroll][DPL];
@@ -124,52 +155,84 @@ attn_nbr_fwd_kernel(const NbrArgs p) {
                     if (lane < F) xe[u] = __ldg(p.efeat + (int64_t)ei * F + lane);
                 }
             }
+            float part[NV];
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
+#pragma unroll
+                for (int h = 0; h < NH; ++h) part[u * NH + h] = 0.0f;
                 if (id[u] < 0) continue;
-                const int j = j0 + u;
                 float xt[DPL];
 #pragma unroll
                 for (int i = 0; i < DPL; ++i)
                     xt[i] = pfo_cosf(fmaf(dtj[u], tw[i], tb[i]));   // full-range, never __cosf (SURVEY hard part 1)
+                float* st = stash + (j0 + u) * SW;
+                st_cols<DPL>(st + c0, xh[u]);
+                st_cols<DPL>(st + d + c0, xt);
+                st[2 * d + lane] = xe[u];
 #pragma unroll
                 for (int h = 0; h < NH; ++h) {
-                    float part = qe[h] * xe[u];
+                    float acc = qe[h] * xe[u];
 #pragma unroll
-                    for (int i = 0; i < DPL; ++i) part = fmaf(qa[h][i], xh[u][i], fmaf(qg[h][i], xt[i], part));
-                    const float s = warp_sum(part);
-                    if (lane == j) sj[h] = s;
-                    // online softmax; one of exp(mx - m_new), exp(s - m_new) is exp(0)
-                    const bool up = s > mx[h];
-                    const float t = expf(up ? mx[h] - s : s - mx[h]);
-                    const float sc = up ? t : 1.0f, e = up ? 1.0f : t;
-                    const float w = e * __shfl_sync(0xffffffffu, keep[h], j);
-                    l[h] = l[h] * sc + e;
-                    ap[h] = ap[h] * sc + w;
-                    ae[h] = ae[h] * sc + w * xe[u];
-#pragma unroll
-                    for (int i = 0; i < DPL; ++i) {
-                        ah[h][i] = ah[h][i] * sc + w * xh[u][i];
-                        at[h][i] = at[h][i] * sc + w * xt[i];
-                    }
-                    if (up) mx[h] = s;
+                    for (int i = 0; i < DPL; ++i) acc = fmaf(qa[h][i], xh[u][i], fmaf(qg[h][i], xt[i], acc));
+                    part[u * NH + h] = acc;
                 }
             }
+            const float r = multi_reduce<NV>(part, lane);          // total of (u, h) in lanes [(u*NH+h) * 32/NV, ..)
+            const int u_l = (lane - j0) & (kUnroll - 1);
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+                const float s = __shfl_sync(0xffffffffu, r, (u_l * NH + h) * (32 / NV));
+                if (lane >= j0 && lane < j0 + kUnroll) sj[h] = s;
+            }
         }
+        __syncwarp();
+        // ---- phase B: softmax over the slots (lane = slot), then the dropout factor of torch's attention dropout
+        float w[NH], psum[NH];
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            const float m = warp_max(live_l ? sj[h] : -INFINITY);
+            const float e = live_l ? expf(sj[h] - m) : 0.0f;
+            const float l = warp_sum(e);
+            const float pw = any ? e / l : 0.0f;
+            if (lane < n) p.P[(q * NH + h) * n + lane] = pw;
+            w[h] = live_l ? pw * keep_scale(p, step, q, h, lane) : 0.0f;
+            psum[h] = warp_sum(w[h]);
+        }
+        // ---- phase C
+        float ah[NH][DPL], at[NH][DPL], ae[NH];
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            ae[h] = 0.0f;
+#pragma unroll
+            for (int i = 0; i < DPL; ++i) { ah[h][i] = 0.0f; at[h][i] = 0.0f; }
+        }
+        for (unsigned mleft = live_mask; mleft; mleft &= mleft - 1) {
+            const int j = __ffs(mleft) - 1;
+            const float* st = stash + j * SW;
+            float xh[DPL], xt[DPL];
+            ld_cols<DPL>(st + c0, xh);
+            ld_cols<DPL>(st + d + c0, xt);
+            const float xe = st[2 * d + lane];
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+                const float wj = __shfl_sync(0xffffffffu, w[h], j);
+                ae[h] = fmaf(wj, xe, ae[h]);
+#pragma unroll
+                for (int i = 0; i < DPL; ++i) { ah[h][i] = fmaf(wj, xh[i], ah[h][i]); at[h][i] = fmaf(wj, xt[i], at[h][i]); }
+            }
+        }
+        __syncwarp();                                   // the stash is rewritten by the next query
         if (lane == 0) p.invalid[q] = any ? 0 : 1;     // rows with no neighbours: output zeroed (temporal_attention.py:84)
 #pragma unroll
         for (int h = 0; h < NH; ++h) {
             float* xb = p.XB + q * p.ldxb + (int64_t)h * ekp;
-            const float inv = any ? 1.0f / l[h] : 0.0f;
-            float oh[DPL];
+            st_cols<DPL>(xb + c0, ah[h]);
 #pragma unroll
-            for (int i = 0; i < DPL; ++i) { oh[i] = ah[h][i] * inv; xb[d + F + c0 + i] = at[h][i] * inv; }
-            st_cols<DPL>(xb + c0, oh);
-            if (lane < F) xb[d + lane] = ae[h] * inv;
-            if (lane == 0) xb[2 * d + F] = ap[h] * inv;
+            for (int i = 0; i < DPL; ++i) xb[d + F + c0 + i] = at[h][i];
+            if (lane < F) xb[d + lane] = ae[h];
+            if (lane == 0) xb[2 * d + F] = psum[h];
             if (lane < ekp - (2 * d + F + 1))            // constant tail: [valid, one, 0...]
                 xb[2 * d + F + 1 + lane] = lane == 0 ? (any ? 1.0f : 0.0f) : (lane == 1 ? 1.0f : 0.0f);
-            if (lane < n) p.P[(q * NH + h) * n + lane] = id_l >= 0 ? expf(sj[h] - mx[h]) * inv : 0.0f;
         }
     }
 }
@@ -244,8 +307,11 @@ attn_nbr_bwd_kernel(const NbrArgs p) {
                         if (lane < F) xe[u] = __ldg(p.efeat + (int64_t)ei * F + lane);
                     }
                 }
+                float part[kUnroll * NH];
 #pragma unroll
                 for (int u = 0; u < kUnroll; ++u) {
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) part[u * NH + h] = 0.0f;
                     if (id[u] < 0) continue;
                     const int j = j0 + u;
                     float* st = stash + j * sw;
@@ -258,12 +324,18 @@ attn_nbr_bwd_kernel(const NbrArgs p) {
                     st[3 * d + lane] = xe[u];
 #pragma unroll
                     for (int h = 0; h < NH; ++h) {
-                        float part = ge[h] * xe[u];
+                        float acc = ge[h] * xe[u];
 #pragma unroll
-                        for (int i = 0; i < DPL; ++i) part = fmaf(ga[h][i], xh[u][i], fmaf(gg[h][i], xt[i], part));
-                        const float dp = warp_sum(part) + gp[h];
-                        if (lane == j) dpj[h] *= dp;
+                        for (int i = 0; i < DPL; ++i) acc = fmaf(ga[h][i], xh[u][i], fmaf(gg[h][i], xt[i], acc));
+                        part[u * NH + h] = acc;
                     }
+                }
+                const float r = multi_reduce<kUnroll * NH>(part, lane);
+                const int u_l = (lane - j0) & (kUnroll - 1);
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                    const float dp = __shfl_sync(0xffffffffu, r, (u_l * NH + h) * (32 / (kUnroll * NH))) + gp[h];
+                    if (lane >= j0 && lane < j0 + kUnroll) dpj[h] *= dp;
                 }
             }
             __syncwarp();
@@ -447,7 +519,16 @@ eval_score_kernel(const float* __restrict__ es, const float* __restrict__ ed, co
 
 template <int DPL, int NH>
 int launch_fwd(const NbrArgs& a, cudaStream_t s) {
-    attn_nbr_fwd_kernel<DPL, NH><<<pfo_grid(a.Q * 32, 128, 10), 128, 0, s>>>(a);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(attn_nbr_fwd_kernel<DPL, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    const size_t smem = (size_t)4 * a.n * (2 * a.d + 32) * sizeof(float);      // 4 warps x n stash rows
+    int per_sm = (int)((200 * 1024) / (smem + 1024));
+    if (per_sm > 5) per_sm = 5;
+    if (per_sm < 1) per_sm = 1;
+    attn_nbr_fwd_kernel<DPL, NH><<<pfo_grid(a.Q * 32, 128, 2 * per_sm), 128, smem, s>>>(a);
     PFO_LAUNCH_CHECK();
 }
 
@@ -552,7 +633,7 @@ PFO_API int pfo_bpr(const float* eu, const float* ep, const float* en, int B, in
                     float* du, float* dp, float* dn, float* loss, float grad_scale, float* workspace, void* stream) {
     if (B <= 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    int grid = pfo_grid((int64_t)B * 32, 256, 2);
+    int grid = pfo_grid((int64_t)B * 32, 256, 8);   // one warp per interaction when they fit (latency-bound, tiny)
     if (grid > 1024) grid = 1024;
     bpr_kernel<<<grid, 256, 0, s>>>(eu, ep, en, B, k, d, du, dp, dn, workspace, grad_scale);
     // loss = sum over blocks of per-block means/B contributions: reduce rows=grid, cols=1

@@ -121,9 +121,23 @@ neighbor_uniform_kernel(const int64_t* __restrict__ rowptr, const int32_t* __res
 // ---------------------------------------------------------------- touched-node compaction
 __global__ void mark_nodes_kernel(const int32_t* __restrict__ ids, int64_t count, int skip_zero,
                                   uint32_t* __restrict__ bitmap) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
-        const int v = ids[i];
-        if (v > 0 || (v == 0 && !skip_zero)) atomicOr(bitmap + (v >> 5), 1u << (v & 31));
+    // hot nodes (a few hundred stocks) repeat thousands of times per batch and would serialise in L2 as
+    // same-address atomics: lanes that hit the same bitmap word combine their bits first (match_any +
+    // reduce_or) and one of them issues the OR
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t rounds = (count + stride - 1) / stride;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t r = 0; r < rounds; ++r, i += stride) {            // every lane runs every round (full-mask intrinsics)
+        int word = -1;
+        uint32_t bit = 0u;
+        if (i < count) {
+            const int v = ids[i];
+            if (v > 0 || (v == 0 && !skip_zero)) { word = v >> 5; bit = 1u << (v & 31); }
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, word);
+        const uint32_t bits = __reduce_or_sync(peers, bit);
+        if (word >= 0 && lane == __ffs(peers) - 1) atomicOr(bitmap + word, bits);
     }
 }
 
