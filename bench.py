@@ -39,6 +39,9 @@ def parse():
                     help="fp32 = 3xTF32 on tcgen05 (1e-5 contract, default); tf32 / bf16 = 2e-2 contract; simt = FFMA")
     ap.add_argument("--dropout", type=float, default=0.1, help="attention dropout (reference main.py:29 default)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of one CUDA graph")
+    ap.add_argument("--parallelism", default="replicated", choices=["replicated", "sharded"],
+                    help="N > 1: replicated state + data-parallel interactions (default), or node-sharded state with "
+                         "all-to-all routing (pfotgnrec_b200/dist.py)")
     ap.add_argument("--eval-steps", type=int, default=4)
     ap.add_argument("--eval-bs", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -262,15 +265,20 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     from pfotgnrec_b200 import _lib
     from pfotgnrec_b200.trainer import PfoTrainer, TrainConfig
     _lib.load()
     st = make_data(a)
     tc = TrainConfig(model=a.workload, bs=a.bs, gemm_mode=a.gemm, dropout=a.dropout, cuda_graph=not a.no_graph)
-    if world > 1:
+    if world > 1 and a.parallelism == "sharded":
         from pfotgnrec_b200.dist import ShardedTrainer
         tr = ShardedTrainer(st, tc, dev, rank, world)
+    elif world > 1:
+        from pfotgnrec_b200.trainer import ReplicatedTrainer
+        tr = ReplicatedTrainer(st, tc, dev, rank, world)
     else:
         tr = PfoTrainer(st, tc, device=dev)
     bs = a.bs
@@ -325,22 +333,23 @@ def main():
 
     # ---- end-to-end through the public API with HOST buffers (H2D of the batch + D2H of the loss per step)
     e2e = None
-    if world == 1:
-        host = tr.make_host_batches(pos[0], a.steps + 1, bs) if hasattr(tr, "make_host_batches") else None
-    else:
-        host = None
+    host = tr.make_host_batches(pos[0], a.steps + 1, bs) if hasattr(tr, "make_host_batches") else None
     if host is not None:
         tr.train_step_host(host[0])                  # warm the path
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         for hb in host[1:]:
             flush.fill_(1)                           # same L2 flush as the device-timed loop (inside e2e's clock)
             l = tr.train_step_host(hb)
             _ = float(l.item())                      # device -> host read of the step's result
-        torch.cuda.synchronize()
+        barrier()
         dt = time.perf_counter() - t0
-        e2e = {"value": a.steps * bs / dt, "unit": "events/s", "h2d_bytes_per_step": int(host[1]["nbytes"]),
-               "d2h_bytes_per_step": 4}
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": a.steps * events_per_step / dt, "unit": "events/s",
+               "h2d_bytes_per_step": int(host[1]["nbytes"]) * world, "d2h_bytes_per_step": 4 * world}
 
     # ---- per-kernel pass (eager launches, CUDA events per C-ABI call) for the rooflines
     roofline, kernels, rooflines = None, None, None
@@ -410,12 +419,15 @@ def main():
                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if a.gemm == "fp32" else "bf16",
                "data": "synthetic",
                "config": {"workload": workload_name(a), "l2": "flushed between timed steps (256 MiB write)",
-                          "global_batch": events_per_step, "parallelism": f"node-sharded x{world}" if world > 1 else "1 GPU",
+                          "global_batch": events_per_step,
+                          "parallelism": "1 GPU" if world == 1 else (f"node-sharded x{world}" if a.parallelism == "sharded"
+                                                                     else f"replicated state, data-parallel x{world}"),
                           "timing": "sum of per-step CUDA-event durations, max over ranks"},
                "clocks": clk, "e2e": e2e, "gpu_launches": launches, "wall_s": wall,
                "roofline": roofline, "cpu_baseline": cpu, "eval_users_per_sec": eval_users, "kernels": kernels,
                "rooflines": rooflines}
-        out["config"].update({"dropout": a.dropout, "gemm_mode": a.gemm, "cuda_graph": bool(tc.cuda_graph and world == 1),
+        out["config"].update({"dropout": a.dropout, "gemm_mode": a.gemm,
+                              "cuda_graph": bool(tc.cuda_graph and (world == 1 or a.parallelism == "replicated")),
                               "eval": f"full ranking over all {a.items} stocks, {a.eval_bs} users per batch"})
         print(json.dumps(out))
     if world > 1:

@@ -310,10 +310,15 @@ class TGNEngine:
 
     # ------------------------------------------------------------------ public step
     def compute_temporal_embeddings(self, params, src, dst, extra_groups, ts, eidx, n_neighbors,
-                                    train=True, update_state=True):
+                                    train=True, update_state=True, state_batch=None):
         """src/dst int32[B], extra_groups list of int32[k*B] (interaction-major), ts float64[B],
         eidx int32[B] -- all device tensors.  Returns [emb_src, emb_dst, *emb_extra] ([.,d] fp32,
-        differentiable w.r.t. `params` when grad mode is on) and advances memory / messages."""
+        differentiable w.r.t. `params` when grad mode is on) and advances memory / messages.
+
+        state_batch (optional, dict(src, dst, ts, eidx)): the interactions whose memory / messages are advanced, when
+        they are not the ones embedded -- the replicated data-parallel mode embeds this rank's slice of the global
+        batch and advances the (replicated) state with the WHOLE global batch, so every replica stays identical
+        without exchanging rows."""
         groups = [src, dst] + list(extra_groups)
         B = src.shape[0]
         q_nodes = torch.cat(groups)
@@ -321,6 +326,11 @@ class TGNEngine:
         flat = self._pack(params)
         batch = dict(src=src, dst=dst, ts=ts, eidx=eidx, q_nodes=q_nodes, q_ts=q_ts, n=int(n_neighbors),
                      B=B, train=bool(train), update_state=bool(update_state))
+        if state_batch is not None:
+            if self.cfg.dst_emb_in_msg:
+                raise NotImplementedError("messages that carry embeddings (dyrep) need the embedded batch as state batch")
+            batch["state"] = dict(src=state_batch["src"], dst=state_batch["dst"], ts=state_batch["ts"],
+                                  eidx=state_batch["eidx"], B=int(state_batch["src"].shape[0]))
         emb = TGNStepFunction.apply(self, batch, *flat)
         return list(torch.split(emb, [g.shape[0] for g in groups]))
 
@@ -532,6 +542,9 @@ class TGNStepFunction(torch.autograd.Function):
             tree = eng._sample_tree(q_nodes, q_ts, c.n_layers, n)
             id_lists = []
             eng._collect_level0(tree, id_lists)
+        sb = batch.get("state", batch)                  # interactions that advance the state (default: the embedded ones)
+        if sb is not batch and c.use_memory:
+            id_lists = id_lists + [sb["src"], sb["dst"]]    # their updated memory rows must be in the node table
 
         # 2. lazy memory update on the unique nodes (memory_updater.py:35-53, restricted)
         tab = eng.node_table(id_lists, cellW)
@@ -559,7 +572,7 @@ class TGNStepFunction(torch.autograd.Function):
 
         # 4. persist positives, then build + store the new raw messages (tgn.py:185-206)
         if c.use_memory and batch["update_state"]:
-            eng.persist_and_store(tab, batch, emb, tw, tb)
+            eng.persist_and_store(tab, sb, emb, tw, tb)
         out = emb
         if c.use_memory and c.dyrep:    # dyrep returns the updated memory rows (tgn.py:211-215, :322-325)
             out = torch.empty(Q, d, device=dev)

@@ -250,15 +250,17 @@ class PfoTrainer:
                 sg.eager_steps += 1
                 return self._step_body(sg.static)
             torch.cuda.synchronize(self.device)
-            self.opt.zero_grad(set_to_none=True)
+            self._zero_grads()
             g = torch.cuda.CUDAGraph()
             launches0 = _lib.LAUNCHES
             with torch.cuda.graph(g):
-                sg.loss = self._step_body(sg.static)
+                sg.loss = self._fwd_bwd(sg.static) if self._graph_tail_eager else self._step_body(sg.static)
             sg.launches = _lib.LAUNCHES - launches0
             sg.graph = g
         sg.graph.replay()
         _lib.LAUNCHES += sg.launches
+        if self._graph_tail_eager:                   # gradient exchange + optimiser outside the graph
+            self._finish()
         return sg.loss
 
     def train_step(self, s, e, batch=None):
@@ -272,27 +274,46 @@ class PfoTrainer:
         return self._step_body(batch if batch is not None else self._batch(s, e))
 
     def _step_body(self, b):
+        loss = self._fwd_bwd(b)
+        self._finish()
+        return loss
+
+    def _finish(self):
+        self._reduce_grads()
+        self.opt.step()
+
+    def _fwd_bwd(self, b):
         tc, D = self.tc, self.dev_stream
         tgn = self.tgn.train()
         eng = tgn._get_engine()
         eng.nf = self.nf_train
-        self.opt.zero_grad(set_to_none=True)
+        self._zero_grads()
         params = tgn._params()
         B = b["src"].shape[0]
         port_items = b.get("port_items", D.port_items)
+        sb = b.get("state")                          # replicated data-parallel mode: the global batch advances the state
         if tc.model == "ours":
             p_pos, p_neg = self.mv.select(b["ev"], b["day"], b["dst"], b["port_ptr"], port_items)
             e_s, _, e_p, e_n = eng.compute_temporal_embeddings(params, b["src"], b["dst"], [p_pos, p_neg], b["ts"],
-                                                               b["eidx"], tc.n_neighbors, train=True)
+                                                               b["eidx"], tc.n_neighbors, train=True, state_batch=sb)
         else:
             held = port_items + (self.st.n_users + 1) if "port_items" in b else D.port_items_as_item_ids
             neg = self.neg_sampler.sample(b["ev"], b["port_ptr"], held, tc.p_neg_num, seed=tc.seed).reshape(-1)
             e_s, e_p, e_n = eng.compute_temporal_embeddings(params, b["src"], b["dst"], [neg], b["ts"], b["eidx"],
-                                                            tc.n_neighbors, train=True)
+                                                            tc.n_neighbors, train=True, state_batch=sb)
         loss = bpr_loss(e_s, e_p, e_n, self.bpr_ws)
-        loss.backward()
-        self.opt.step()
+        (loss if self._loss_scale == 1.0 else loss * self._loss_scale).backward()
         return loss.detach()
+
+    # hooks of the data-parallel subclass
+    _loss_scale = 1.0
+    _graph_tail_eager = False
+
+    def _zero_grads(self):
+        self.opt.zero_grad(set_to_none=True)
+
+    def _reduce_grads(self):
+        pass
 
     # ------------------------------------------------------------------ one evaluation step
     @torch.no_grad()
@@ -330,3 +351,115 @@ class PfoTrainer:
             out[f"recall_{k}"] = hit.mean()
             out[f"ndcg_{k}"] = (hit / torch.log2(r + 2.0)).mean()
         return out
+
+
+def replica_slice(s, e, rank, world):
+    """This rank's share [ls, le) of the global batch [s, e): equal consecutive slices (the batch size must divide)."""
+    n = e - s
+    if n % world != 0:
+        raise ValueError(f"global batch of {n} interactions does not split evenly over {world} ranks")
+    bs = n // world
+    return s + rank * bs, s + (rank + 1) * bs
+
+
+def allreduce_sum_(flat, group=None):
+    """In-place sum of the flat gradient bucket over the ranks (the loss is pre-scaled by 1 / world)."""
+    import torch.distributed as dist
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return flat
+
+
+class ReplicatedTrainer(PfoTrainer):
+    """Data-parallel training over `world` GPUs with REPLICATED state (one process per GPU).
+
+    Every rank holds the whole node memory, pending-message table and adjacency (config 4 of BASELINE.json --
+    10M users, 1B events -- is ~45 GB of state: it fits each 180 GB B200), embeds ITS slice of the global batch
+    (sampling, attention, BPR, backward are embarrassingly parallel over interactions) and advances the state with
+    the WHOLE global batch, which it already has on the device: the lazily updated memory rows of all positives
+    are part of its node table, so persist + last-wins message store run identically on every replica and the
+    replicas never diverge.  The only exchange per step is one NCCL all-reduce of the 133 k-float gradient bucket,
+    launched right after the step's CUDA graph (sampling .. backward), followed by the fused Adam.  Same semantics as the reference on the global batch (embeddings from
+    the pre-batch state, then one state update), same numbers as the 1-GPU step on that batch up to the order of
+    the gradient sum (tools/check_replicated.py).  The node-sharded alternative (all-to-all routing, for state
+    beyond one GPU) is pfotgnrec_b200/dist.py."""
+
+    def __init__(self, st, tc, device, rank, world, group=None, nccl_in_graph=False):
+        super().__init__(st, tc, device)
+        if tc.model in ("dyrep",):
+            raise NotImplementedError("dyrep messages carry embeddings of the other ranks' interactions")
+        self.rank, self.world, self.group, self.nccl_in_graph = int(rank), int(world), group, bool(nccl_in_graph)
+        self._loss_scale = 1.0 / self.world
+        # nccl_in_graph=False: the graph holds sampling .. backward, the all-reduce and Adam are launched after it
+        self._graph_tail_eager = not self.nccl_in_graph
+        self.tgn._get_engine().seed = tc.seed + 7919 * self.rank        # decorrelate the dropout streams of the replicas
+        self.params = [p for p in self.tgn.parameters() if p.requires_grad]
+        sizes = [p.numel() for p in self.params]
+        self.gflat = torch.zeros(sum(sizes), device=self.device)         # gradient bucket; p.grad are views into it
+        for p, g in zip(self.params, self.gflat.split(sizes)):
+            p.grad = g.view_as(p)
+
+    def _zero_grads(self):
+        self.gflat.zero_()
+
+    def _reduce_grads(self):
+        if self.world > 1:
+            allreduce_sum_(self.gflat, self.group)
+
+    def _step_graph(self, B):
+        sg = super()._step_graph(B)
+        if "state" not in sg.static:
+            dev, Bg = self.device, B * self.world
+            i32 = torch.int32
+            sg.static["state"] = dict(src=torch.zeros(Bg, dtype=i32, device=dev), dst=torch.zeros(Bg, dtype=i32, device=dev),
+                                      ts=torch.zeros(Bg, dtype=torch.float64, device=dev),
+                                      eidx=torch.zeros(Bg, dtype=i32, device=dev))
+        return sg
+
+    def _state_batch(self, s, e):
+        D = self.dev_stream
+        return dict(src=D.src[s:e], dst=D.dst[s:e], ts=D.ts[s:e], eidx=D.eidx[s:e])
+
+    def train_step(self, s, e, batch=None):
+        """Global batch [s, e): this rank embeds its slice, every rank advances the state with all of it."""
+        ls, le = replica_slice(s, e, self.rank, self.world)
+        if self._graph_ok(le - ls) and e <= self.st.n_events:
+            sg = self._step_graph(le - ls)
+            self._fill_static(sg, ls, le)
+            for k, v in self._state_batch(s, e).items():
+                sg.static["state"][k].copy_(v)
+            return self._run_graphed(sg)
+        b = self._batch(ls, le)
+        b["state"] = self._state_batch(s, e)
+        return self._step_body(b)
+
+    def make_host_batches(self, start, count, bs):
+        """Pinned host copies of `count` consecutive GLOBAL batches of bs * world interactions: this rank's slice
+        (all columns) plus the four columns of the whole batch that advance the state."""
+        st, out = self.st, []
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        for i in range(count):
+            s = start + i * bs * self.world
+            e = s + bs * self.world
+            ls, le = replica_slice(s, e, self.rank, self.world)
+            hb = super().make_host_batches(ls, 1, bs)[0]
+            hb["state"] = dict(src=pin(st.sources[s:e].astype(np.int32)), dst=pin(st.destinations[s:e].astype(np.int32)),
+                               ts=pin(st.timestamps[s:e]), eidx=pin(st.edge_idxs[s:e].astype(np.int32)))
+            hb["nbytes"] += sum(v.numel() * v.element_size() for v in hb["state"].values())
+            out.append(hb)
+        return out
+
+    def train_step_host(self, hb):
+        B = hb["src"].shape[0]
+        if self._graph_ok(B):
+            sg = self._step_graph(B)
+            for k, v in hb.items():
+                if k in ("nbytes", "state"):
+                    continue
+                dst = sg.static[k]
+                (dst[:v.shape[0]] if k == "port_items" else dst).copy_(v, non_blocking=True)
+            for k, v in hb["state"].items():
+                sg.static["state"][k].copy_(v, non_blocking=True)
+            return self._run_graphed(sg)
+        b = {k: v.to(self.device, non_blocking=True) for k, v in hb.items() if k not in ("nbytes", "state")}
+        b["state"] = {k: v.to(self.device, non_blocking=True) for k, v in hb["state"].items()}
+        return self._step_body(b)

@@ -74,3 +74,52 @@ def test_local_csr_partition_matches_global():
                 assert np.array_equal(c.nbr.numpy()[rp[l]:rp[l + 1]], adj.nbr[lo:hi])
                 assert np.array_equal(c.eidx.numpy()[rp[l]:rp[l + 1]], adj.eidx[lo:hi])
                 assert np.array_equal(c.ts.numpy()[rp[l]:rp[l + 1]], adj.ts[lo:hi])
+
+
+def _dp_worker(rank, world, port, results):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pfotgnrec_b200.trainer import replica_slice, allreduce_sum_
+    try:
+        # slices tile the global batch in rank order
+        ls, le = replica_slice(1000, 1000 + 64 * world, rank, world)
+        assert (ls, le) == (1000 + 64 * rank, 1000 + 64 * (rank + 1))
+        # the gradient bucket: every rank back-propagates loss_r / world, the sum over ranks is the gradient of the
+        # global-batch mean loss; parameter .grad tensors are views into the bucket
+        torch.manual_seed(0)
+        w = [torch.randn(5, 3, requires_grad=True), torch.randn(7, requires_grad=True)]
+        sizes = [p.numel() for p in w]
+        flat = torch.zeros(sum(sizes))
+        for p, g in zip(w, flat.split(sizes)):
+            p.grad = g.view_as(p)
+        x = torch.arange(4 * world * 3, dtype=torch.float32).view(4 * world, 3) / 10.0
+        xs = x[4 * rank:4 * (rank + 1)]
+        loss = ((xs @ w[0].t()).pow(2).mean() + w[1].sum() * xs.mean())
+        (loss / world).backward()
+        allreduce_sum_(flat)
+        wg = [p.detach().clone().requires_grad_(True) for p in w]
+        full = sum(((x[4 * r:4 * (r + 1)] @ wg[0].t()).pow(2).mean() + wg[1].sum() * x[4 * r:4 * (r + 1)].mean())
+                   for r in range(world)) / world
+        full.backward()
+        for p, q in zip(w, wg):
+            assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-6)
+        results[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_replicated_dp_gradient_bucket_gloo_world2():
+    world = 2
+    mgr = mp.Manager()
+    results = mgr.dict()
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_dp_worker, args=(world, port, results), nprocs=world, join=True)
+    assert dict(results) == {0: "ok", 1: "ok"}
+
+
+def test_replica_slice_rejects_ragged_batches():
+    sys.path.insert(0, ROOT)
+    from pfotgnrec_b200.trainer import replica_slice
+    with pytest.raises(ValueError):
+        replica_slice(0, 130, 0, 4)
