@@ -42,8 +42,8 @@ def parse():
     ap.add_argument("--parallelism", default="replicated", choices=["replicated", "sharded"],
                     help="N > 1: replicated state + data-parallel interactions (default), or node-sharded state with "
                          "all-to-all routing (pfotgnrec_b200/dist.py)")
-    ap.add_argument("--eval-steps", type=int, default=4)
-    ap.add_argument("--eval-bs", type=int, default=128)
+    ap.add_argument("--eval-steps", type=int, default=8)
+    ap.add_argument("--eval-bs", type=int, default=512, help="users per evaluation batch and GPU (reference --bs default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     return ap.parse_args()
@@ -381,20 +381,26 @@ def main():
         top = max(agg.items(), key=lambda kv: kv[1]["ms"])[0]
         roofline = rooflines.get(top)
 
-    # ---- eval users/sec (the second half of the metric): full ranking over all stocks
+    # ---- eval users/sec (the second half of the metric): full ranking over all stocks, users split over the ranks
     eval_users = None
-    if world == 1 and a.eval_steps > 0:
-        ebs = a.eval_bs
+    if a.eval_steps > 0 and hasattr(tr, "eval_step") and (world == 1 or a.parallelism == "replicated"):
+        ebs = a.eval_bs * world                      # global evaluation batch
         p = pos[0]
-        tr.eval_step(p, p + ebs); p += ebs
-        torch.cuda.synchronize()
+        for _ in range(3):                           # two eager steps, then the graph is captured
+            tr.eval_step(p, p + ebs); p += ebs
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(a.eval_steps):
             tr.eval_step(p, p + ebs); p += ebs
         e1.record()
-        torch.cuda.synchronize()
-        eval_users = a.eval_steps * ebs / (e0.elapsed_time(e1) * 1e-3)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        eval_users = a.eval_steps * ebs / (ms * 1e-3)
 
     # ---- CPU baseline (oracle port) on the host cores, bounded sample, rank 0 only
     cpu = None

@@ -119,6 +119,7 @@ class _StepGraph:
 
     def __init__(self, static):
         self.static, self.graph, self.loss, self.eager_steps, self.launches = static, None, None, 0, 0
+        self.evals = {}              # (n_items, with state batch) -> _StepGraph of the evaluation step
 
 
 class PfoTrainer:
@@ -317,22 +318,59 @@ class PfoTrainer:
 
     # ------------------------------------------------------------------ one evaluation step
     @torch.no_grad()
-    def eval_step(self, s, e, n_items=None, batch=None):
+    def eval_step(self, s, e, n_items=None, batch=None, state_batch=None):
         """Interactions [s, e): N_ITEMS candidates per interaction (seed 2024), embeddings, scores, rank of
         the true item and top-5 (reference evaluation.py:84-115,134-138).  Advances memory like the
-        reference does.  Returns (pos_rank int32[B], top5 int32[B,5], candidates int32[B,N])."""
+        reference does.  Returns (pos_rank int32[B], top5 int32[B,5], candidates int32[B,N], scores); in
+        CUDA-graph mode these are the graph's output buffers, overwritten by the next evaluation step."""
+        N = int(n_items) if n_items is not None else int(self.eval_sampler.items.shape[0])
+        if batch is None and self._graph_ok(e - s) and e - s > 0 and e <= self.st.n_events:
+            sg = self._step_graph(e - s)
+            self._fill_static(sg, s, e)
+            if state_batch is not None:
+                self._ensure_state_buffers(sg, state_batch["src"].shape[0])
+                for k, v in state_batch.items():
+                    sg.static["state"][k].copy_(v)
+            eg = sg.evals.setdefault((N, state_batch is not None), _StepGraph(sg.static))
+            if eg.graph is None:
+                if eg.eager_steps < 2:
+                    eg.eager_steps += 1
+                    return self._eval_body(sg.static, N, state_batch is not None)
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                launches0 = _lib.LAUNCHES
+                with torch.cuda.graph(g):
+                    eg.loss = self._eval_body(sg.static, N, state_batch is not None)
+                eg.launches = _lib.LAUNCHES - launches0
+                eg.graph = g
+            eg.graph.replay()
+            _lib.LAUNCHES += eg.launches
+            return eg.loss
+        b = dict(batch) if batch is not None else self._batch(s, e)
+        if state_batch is not None:
+            b["state"] = state_batch
+        return self._eval_body(b, N, state_batch is not None)
+
+    def _ensure_state_buffers(self, sg, Bg):
+        if "state" not in sg.static or sg.static["state"]["src"].shape[0] != Bg:
+            dev, i32 = self.device, torch.int32
+            sg.static["state"] = dict(src=torch.zeros(Bg, dtype=i32, device=dev), dst=torch.zeros(Bg, dtype=i32, device=dev),
+                                      ts=torch.zeros(Bg, dtype=torch.float64, device=dev),
+                                      eidx=torch.zeros(Bg, dtype=i32, device=dev))
+
+    def _eval_body(self, b, N, with_state):
         D = self.dev_stream
-        b = batch if batch is not None else self._batch(s, e)
         tgn = self.tgn.eval()
         eng = tgn._get_engine()
         eng.nf = self.nf_full
-        N = int(n_items) if n_items is not None else int(self.eval_sampler.items.shape[0])
         B = b["src"].shape[0]
         # evaluation recreates RandomState(2024) per batch: the stream is keyed by position in the batch
         ev = torch.arange(B, dtype=torch.int64, device=self.device)
-        cand = self.eval_sampler.sample(ev, b["port_ptr"], D.port_items_as_item_ids, N, seed=2024)
+        held = b["port_items"] + (self.st.n_users + 1) if "port_items" in b else D.port_items_as_item_ids
+        cand = self.eval_sampler.sample(ev, b["port_ptr"], held, N, seed=2024)
         e_s, e_d, e_c = eng.compute_temporal_embeddings(tgn._params(), b["src"], b["dst"], [cand.reshape(-1)], b["ts"],
-                                                        b["eidx"], self.tc.n_neighbors, train=False)
+                                                        b["eidx"], self.tc.n_neighbors, train=False,
+                                                        state_batch=b["state"] if with_state else None)
         d = e_s.shape[1]
         scores = torch.empty(B, 1 + N, device=self.device)
         pos_rank = torch.empty(B, dtype=torch.int32, device=self.device)
@@ -407,13 +445,14 @@ class ReplicatedTrainer(PfoTrainer):
 
     def _step_graph(self, B):
         sg = super()._step_graph(B)
-        if "state" not in sg.static:
-            dev, Bg = self.device, B * self.world
-            i32 = torch.int32
-            sg.static["state"] = dict(src=torch.zeros(Bg, dtype=i32, device=dev), dst=torch.zeros(Bg, dtype=i32, device=dev),
-                                      ts=torch.zeros(Bg, dtype=torch.float64, device=dev),
-                                      eidx=torch.zeros(Bg, dtype=i32, device=dev))
+        self._ensure_state_buffers(sg, B * self.world)
         return sg
+
+    def eval_step(self, s, e, n_items=None, batch=None, state_batch=None):
+        """Global evaluation batch [s, e): this rank scores its slice of the users against all candidates, every
+        rank advances the state with the whole batch (returns this rank's slice of the results)."""
+        ls, le = replica_slice(s, e, self.rank, self.world)
+        return super().eval_step(ls, le, n_items=n_items, state_batch=self._state_batch(s, e))
 
     def _state_batch(self, s, e):
         D = self.dev_stream

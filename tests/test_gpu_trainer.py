@@ -114,3 +114,29 @@ def test_dropout_stream_is_keyed_by_the_device_step_counter():
     psum = a[:, :, 2 * d + F]                            # kept softmax mass, scaled by 1/(1-p): mean ~ 1
     live = (idx.cpu().numpy() >= 0).any(axis=1)
     assert abs(psum[live].mean() - 1.0) < 0.1
+
+
+def test_eval_step_graph_replay_matches_eager_and_oracle():
+    """Evaluation step (candidates, embeddings, scores, ranking): CUDA-graph replay == eager launches, and the
+    first batch == the oracle's evaluation step (ranks bit-exact, scores to 1e-5)."""
+    from pfotgnrec_b200.trainer import PfoTrainer, TrainConfig
+    from oracle.train_loop import OracleTrainer
+    st = _stream(seed=4)
+    res = []
+    for graph in (False, True):
+        tr = PfoTrainer(st, TrainConfig(model="ours", bs=64, cuda_graph=graph), device="cuda:0")
+        outs = []
+        for i in range(5):
+            r = tr.eval_step(2400 + i * 64, 2400 + (i + 1) * 64, n_items=30)
+            outs.append([t.clone().cpu().numpy() for t in r])
+        res.append((outs, tr))
+    for a, b in zip(res[0][0], res[1][0]):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+        assert rel_err(b[3], a[3]) < 1e-6
+    tr = res[0][1]
+    p = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in tr.tgn.named_parameters()}
+    orc = OracleTrainer(st, "ours", bs=64, params=p, seed=0)
+    rk, top5, cand, scores = orc.eval_step(2400, 2464, n_items=30)
+    a = res[0][0][0]
+    assert np.array_equal(a[2], cand - 0) and rel_err(a[3], scores) < 1e-5
+    assert np.array_equal(a[0], rk) and np.array_equal(a[1], top5)
