@@ -196,6 +196,20 @@ int pfo_bpr(const float* eu, const float* ep, const float* en, int B, int k, int
 int pfo_eval_score(const float* es, const float* ed, const float* ec, int B, int n_cand, int d, int topk,
                    float* scores, int32_t* pos_rank, int32_t* top_idx, void* stream);
 
+/* ---- evaluation metric block --- evaluation.py:127-207 (per-interaction loop: Recall/NDCG@{1,3,5}, :11-21, and
+ * return_sharpe_at_k, :23-36, in and out of sample) and :209-258 (means / fraction-positive).  pos_rank / top_idx are
+ * pfo_eval_score's outputs (topk >= 5); pos_item / cand are item ids, stock = id - item_offset; the portfolio CSR
+ * holds 0-based stocks (an empty row = the reference's ['']); logret_* are float64 [n_days, n_stocks, n_returns]
+ * log(p[1:]/p[:-1]) of time_feature_past / time_feature_future (n_returns <= 32).  per_event is float64 [B, 18] =
+ * [recall@1,3,5 | ndcg@1,3,5 | d_return_in@1,3,5 | d_sharpe_in@1,3,5 | d_return_out@1,3,5 | d_sharpe_out@1,3,5],
+ * rounded exactly like the reference's numpy fp64 arithmetic.  acc (optional, float64 [31]) accumulates over
+ * calls: column sums [0..18), positive counts of columns 6..17 [18..30), number of interactions [30]. */
+int pfo_eval_metrics(const int32_t* pos_rank, const int32_t* top_idx, int topk, const int32_t* pos_item,
+                     const int32_t* cand, int n_cand, int item_offset, const int32_t* day_idx,
+                     const int64_t* port_ptr, const int32_t* port_items, const double* logret_past,
+                     const double* logret_future, int n_stocks, int n_returns, int B,
+                     double* per_event, double* acc, void* stream);
+
 /* ---- K5: candidate sampling + mean-variance efficient selection --- utils/utils.py:65-114
  * (RandEdgeSampler) and main.py:197-304 (inline block).  Stocks are 0-based indices; logret is
  * float64 [n_days, n_stocks, n_returns].  sample != 0 draws cand[:,1:] from the Philox stream

@@ -188,6 +188,62 @@ def golden_mv_select(RandEdgeSampler):
     print("mv_select.npz", len(out))
 
 
+def golden_eval_metrics():
+    """Run the reference's UNMODIFIED eval_recommendation (evaluation.py:39-265) on a synthetic stream written
+    in the reference's on-disk format, with a stub model whose embeddings are rows of a fixed random table: pins
+    the metric block (ranking, Recall/NDCG@k, delta-return / delta-Sharpe@k in and out of sample, aggregation)."""
+    import tempfile
+    from pfotgnrec_b200.synth import make_stream, write_reference_format
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import evaluation as ref_eval                   # noqa: E402  (/root/reference/evaluation.py)
+    st = make_stream(n_users=60, n_items=30, n_events=330, n_days=6, seed=31, ts_mode="nbg")
+    work = tempfile.mkdtemp(prefix="pfo_golden_eval_")
+    write_reference_format(st, work, period="30")
+    rng = np.random.default_rng(32)
+    table = torch.tensor(rng.standard_normal((st.n_nodes, 16)).astype(np.float32))
+    negs = []
+
+    class StubTGN:
+        def eval(self):
+            return self
+
+        def compute_temporal_embeddings(self, src, dst, neg, ts, eidx, n_neighbors):
+            negs.append(np.asarray(neg).copy())
+            return table[torch.as_tensor(src)], table[torch.as_tensor(dst)], table[torch.as_tensor(neg)]
+
+    portfolios = np.array([[st.codes[k] for k in st.portfolio(e)] or [""] for e in range(st.n_events)], dtype=object)
+    e0, e1, B = 100, 330, 64                        # 3 full batches + a short last one (skipped, evaluation.py:68-69)
+    data = types.SimpleNamespace(sources=st.sources[e0:e1], destinations=st.destinations[e0:e1],
+                                 timestamps=st.timestamps[e0:e1], edge_idxs=st.edge_idxs[e0:e1],
+                                 portfolios=portfolios[e0:e1])
+    cwd = os.getcwd()
+    os.chdir(work)
+    out = {}
+    try:
+        # the true item is often drawn as a candidate too (equal scores): the ranking depends on how argsort
+        # breaks ties, so both variants are recorded -- numpy's default and the stable sort (deviation ii)
+        for tag, mod in (("unstable", np), ("stable", _StableNumpy())):
+            ref_eval.np = mod
+            n0 = len(negs)
+            res = ref_eval.eval_recommendation(StubTGN(), data, _data(st), B, 10, st.n_users, "30", False, "val")
+            out.update({f"res_{tag}_" + k: float(v) for k, v in res.items()})
+        assert all(np.array_equal(a, b) for a, b in zip(negs[:n0], negs[n0:]))    # RandomState(2024) per batch
+        del negs[n0:]
+    finally:
+        ref_eval.np = np
+        os.chdir(cwd)
+    out["table"] = table.numpy()
+    out["negatives"] = np.stack([n.reshape(B, -1) for n in negs])         # [n_batches, B, N_ITEMS] item ids
+    out["e0"], out["B"], out["n_batches"] = e0, B, len(negs)
+    for k in ("sources", "destinations", "timestamps", "day_idx", "port_ptr", "port_items", "prices_future",
+              "prices_past"):
+        out["st_" + k] = getattr(st, k)
+    out["st_n_users"] = st.n_users
+    np.savez_compressed(os.path.join(OUT, "eval_metrics.npz"), **out)
+    print("eval_metrics.npz", len(out), "batches", len(negs))
+
+
 class _StableNumpy:
     """numpy with argsort(kind='stable') -- documented deviation (ii)."""
 
@@ -214,6 +270,7 @@ def main():
     _run_model(TGN, get_neighbor_finder, "tgat2", d=32, ts_mode="small", with_ppos=False,
                **{**common, "use_memory": False, "n_layers": 2, "n_neighbors": 5})
     golden_mv_select(RandEdgeSampler)
+    golden_eval_metrics()
 
 
 if __name__ == "__main__":

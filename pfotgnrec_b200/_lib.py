@@ -54,6 +54,7 @@ _SIGS = {
     "pfo_fold_attention_bwd": (c_int, [P] * 9 + [c_int, c_int, c_int, c_int, P] + [P] * 3 + [P] * 9 + [P]),
     "pfo_bpr": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P, P, c_float, P, P]),
     "pfo_eval_score": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, P, P, P]),
+    "pfo_eval_metrics": (c_int, [P, P, c_int, P, P, c_int, c_int, P, P, P, P, P, c_int, c_int, c_int, P, P, P]),
     "pfo_mv_select": (c_int, [P, P, P, P, P, P, c_int, P, c_int, c_int, c_int, c_int, c_double, c_double, c_int,
                               c_int, c_uint64, c_int, P, P, P, P, P]),
     "pfo_sample_candidates": (c_int, [P, P, P, P, c_int, c_int, c_int, c_uint64, P, P]),
@@ -65,7 +66,7 @@ LAUNCHES = 0            # kernels launched through this binding (bench.py report
 _LAUNCHES_PER_CALL = {"pfo_compact_nodes": 3, "pfo_fold_attention_fwd": 2, "pfo_fold_attention_bwd": 2,
                       "pfo_fold_attention_workspace_doubles": 0, "pfo_wgrad_f32": 2, "pfo_wgrad_tf32": 2,
                       "pfo_wgrad_tf32_workspace_floats": 0, "pfo_time_embedding_bwd": 2,
-                      "pfo_attn_nbr_bwd": 2, "pfo_bpr": 2, "pfo_apply_messages": 2, "pfo_abi_version": 0,
+                      "pfo_attn_nbr_bwd": 2, "pfo_bpr": 2, "pfo_eval_metrics": 2, "pfo_apply_messages": 2, "pfo_abi_version": 0,
                       "pfo_compact_workspace_ints": 0, "pfo_wgrad_workspace_floats": 0,
                       "pfo_attn_nbr_bwd_workspace_floats": 0}
 

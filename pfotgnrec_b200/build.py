@@ -19,6 +19,7 @@ SOURCES = {
     "attention_kernels.cu": [],
     "fold_kernels.cu": [],
     "mv_kernels.cu": ["-fmad=false"],
+    "eval_kernels.cu": ["-fmad=false"],     # fp64 metric block rounds like numpy
 }
 
 

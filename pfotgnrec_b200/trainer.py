@@ -18,6 +18,7 @@ from ._lib import ptr
 from .engine import ModelConfig
 from .graph import TemporalCSR, NeighborFinder
 from .sampler import CandidateSampler, MVSelector
+from .evalmetrics import EvalMetricBlock
 from .synth import Stream, log_returns
 
 _OVERLAY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "overlay")
@@ -174,6 +175,16 @@ class PfoTrainer:
         self.neg_sampler = CandidateSampler(universe_items, device=device)
         self.eval_sampler = CandidateSampler(np.unique(st.destinations), device=device)
         self.bpr_ws = torch.empty(1024, device=self.device)
+        # evaluation metric block (reference evaluation.py:127-258): in-sample (past) / out-of-sample (future)
+        # daily log-returns and the running sums of the per-interaction metrics live on the device
+        self.metrics = None
+        if st.prices_past.shape[0] == len(st.day_keys) and st.prices_past.shape[1] == st.n_items:
+            self.metrics = EvalMetricBlock(log_returns(st.prices_past), log_returns(st.prices_future),
+                                           st.n_users + 1, device=self.device)
+
+    @property
+    def eval_acc(self):
+        return self.metrics.acc
 
     def _time_statistics(self):
         return time_statistics(self.st.sources, self.st.destinations, self.st.timestamps)
@@ -320,8 +331,9 @@ class PfoTrainer:
     @torch.no_grad()
     def eval_step(self, s, e, n_items=None, batch=None, state_batch=None):
         """Interactions [s, e): N_ITEMS candidates per interaction (seed 2024), embeddings, scores, rank of
-        the true item and top-5 (reference evaluation.py:84-115,134-138).  Advances memory like the
-        reference does.  Returns (pos_rank int32[B], top5 int32[B,5], candidates int32[B,N], scores); in
+        the true item and top-5 (reference evaluation.py:84-115,134-138), then the metric block (:127-207) into
+        `per_event` float64[B,18] and the running sums `self.eval_acc`.  Advances memory like the
+        reference does.  Returns (pos_rank int32[B], top5 int32[B,5], candidates int32[B,N], scores, per_event); in
         CUDA-graph mode these are the graph's output buffers, overwritten by the next evaluation step."""
         N = int(n_items) if n_items is not None else int(self.eval_sampler.items.shape[0])
         if batch is None and self._graph_ok(e - s) and e - s > 0 and e <= self.st.n_events:
@@ -371,13 +383,42 @@ class PfoTrainer:
         e_s, e_d, e_c = eng.compute_temporal_embeddings(tgn._params(), b["src"], b["dst"], [cand.reshape(-1)], b["ts"],
                                                         b["eidx"], self.tc.n_neighbors, train=False,
                                                         state_batch=b["state"] if with_state else None)
+        if self.metrics is not None and N >= 4:
+            pos_rank, top, scores, per_event = self.metrics.step(e_s, e_d, e_c, b["dst"], cand, b["day"], b["port_ptr"],
+                                                                 b.get("port_items", D.port_items))
+            return pos_rank, top, cand, scores, per_event
         d = e_s.shape[1]
         scores = torch.empty(B, 1 + N, device=self.device)
         pos_rank = torch.empty(B, dtype=torch.int32, device=self.device)
         top = torch.empty(B, 5, dtype=torch.int32, device=self.device)
         e_s, e_d, e_c = e_s.contiguous(), e_d.contiguous(), e_c.contiguous()
         _lib.call("pfo_eval_score", ptr(e_s), ptr(e_d), ptr(e_c), B, N, d, 5, ptr(scores), ptr(pos_rank), ptr(top))
-        return pos_rank, top, cand, scores
+        return pos_rank, top, cand, scores, None
+
+    def reset_eval_metrics(self):
+        self.metrics.reset()
+
+    def eval_summary(self, EVAL="val"):
+        """The dictionary reference eval_recommendation returns (evaluation.py:209-258), from the 31 running sums
+        the evaluation steps since `reset_eval_metrics` left on the device (in the replicated multi-GPU mode the
+        sums of the ranks' user slices are all-reduced first)."""
+        return self.metrics.summary(EVAL, reduce=self._all_ranks_sum)
+
+    def _all_ranks_sum(self, t):
+        return t
+
+    def evaluate(self, s, e, bs=None, n_items=None, EVAL="val"):
+        """The loop of reference eval_recommendation (evaluation.py:63-207) over interactions [s, e): batches of
+        `bs`, the last (short or exactly-ending) batch skipped like the reference does (:68-69)."""
+        bs = int(bs or self.tc.bs)
+        self.reset_eval_metrics()
+        n_batches = -(-(e - s) // bs)
+        for i in range(n_batches):
+            a, b_ = s + i * bs, min(e, s + (i + 1) * bs)
+            if b_ == e:
+                continue
+            self.eval_step(a, b_, n_items=n_items)
+        return self.eval_summary(EVAL)
 
     @staticmethod
     def recall_ndcg(pos_rank, ks=(1, 3, 5)):
@@ -438,6 +479,9 @@ class ReplicatedTrainer(PfoTrainer):
 
     def _zero_grads(self):
         self.gflat.zero_()
+
+    def _all_ranks_sum(self, t):
+        return allreduce_sum_(t, self.group) if self.world > 1 else t
 
     def _reduce_grads(self):
         if self.world > 1:

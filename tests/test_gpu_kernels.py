@@ -270,219 +270,91 @@ def test_eval_score_and_ranking():
     assert np.array_equal(pos_rank.cpu().numpy(), np.argmax(rk == 0, axis=1))
 
 
-# ------------------------------------------------------------------------------ bf16 tcgen05 path
-@pytest.mark.parametrize("M,N,K", [(1000, 192, 193), (257, 64, 64), (4096, 129, 64), (33, 130, 32), (5000, 64, 192),
-                                   (300, 128, 128), (70000, 192, 64)])
-@pytest.mark.parametrize("wt", [0, 1])
-def test_linear_bf16_tcgen05(M, N, K, wt):
+def _eval_metrics_on_device(scores_inputs, pos_item, cand_item, item_offset, day_idx, port_ptr, port_items, lr_past,
+                            lr_future, acc=None):
+    """pfo_eval_score -> pfo_eval_metrics on the device; returns (scores, pos_rank, top5, per_event)."""
     from pfotgnrec_b200 import _lib
     from pfotgnrec_b200._lib import ptr
-    g = torch.Generator(device="cpu").manual_seed(M + N + K)
-    lda = K + 3 if K % 2 else K          # exercise both the scalar and the float4 staging path
-    A = torch.randn(M + 50, lda, generator=g)
-    W = torch.randn(N, K, generator=g)
-    b = torch.randn(N, generator=g)
-    idx = torch.randint(-1, M + 50, (M,), generator=g, dtype=torch.int32)
-    rz = (torch.rand(M, generator=g) < 0.1).to(torch.int32)
-    rows = torch.where(idx.unsqueeze(1) >= 0, A[idx.clamp(min=0).long(), :K], torch.zeros(1))
-    # operands rounded to bf16, exact products, fp32-ish accumulation: a sharp check of the layouts
-    ref = (rows.bfloat16().double() @ W.bfloat16().double().t() + b.double()) * 0.5
-    ref = torch.relu(ref)
-    ref[rz != 0] = 0
-    full = torch.relu((rows.double() @ W.double().t() + b.double()) * 0.5)
-    full[rz != 0] = 0
-    Ad, Wd, bd, idxd, rzd = (t.to(DEV) for t in (A, W.t().contiguous() if wt else W, b, idx, rz))
-    C = torch.full((M, N + 2), 7.0, device=DEV)
-    _lib.call("pfo_linear_bf16", ptr(Ad), lda, ptr(idxd), ptr(Wd), N if wt else K, wt, ptr(bd), None, 0,
-              ptr(C), N + 2, M, None, N, K, 0.5, 1, ptr(rzd), None, 0, 0)
-    got = C[:, :N].cpu().numpy()
-    assert rel_err(got, ref.numpy()) < 1e-5
-    assert rel_err(got, full.numpy()) < 2e-2           # the bf16 contract of BASELINE.json
-    assert (C[:, N:] == 7.0).all()
-
-
-# ------------------------------------------------------------------------------ TMA + tcgen05 (tf32 / 3xtf32) path
-def _tf32_trunc(x):
-    return (x.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
-
-
-@pytest.mark.parametrize("M,N,K", [(1000, 192, 193), (257, 64, 64), (4096, 129, 64), (33, 130, 32), (5000, 64, 192),
-                                   (300, 128, 128), (70000, 192, 64), (1, 16, 1), (129, 256, 320), (40000, 64, 130),
-                                   (3000, 264, 64), (3000, 64, 328), (3000, 328, 64), (3000, 64, 264)])
-@pytest.mark.parametrize("wt", [0, 1])
-@pytest.mark.parametrize("passes", [3, 1])
-def test_linear_tf32_tma(M, N, K, wt, passes):
-    from pfotgnrec_b200 import _lib
-    from pfotgnrec_b200._lib import ptr
-    g = torch.Generator(device="cpu").manual_seed(M + N + K)
-    lda = (K + 3) // 4 * 4 + 4                      # strided rows, 16-byte aligned: the TMA path
-    A = torch.randn(M + 50, lda, generator=g)
-    W = torch.randn(N, K, generator=g)
-    b = torch.randn(N, generator=g)
-    rz = (torch.rand(M, generator=g) < 0.1).to(torch.int32)
-    brs = torch.rand(M, generator=g)
-    full = (A[:M, :K].double() @ W.double().t() + b.double() * brs.double().unsqueeze(1)) * 0.5
-    full = torch.relu(full)
-    full[rz != 0] = 0
-    Ad, Wd, bd, rzd, brsd = (t.to(DEV) for t in (A, W.t().contiguous() if wt else W, b, rz, brs))
-    C = torch.full((M, N + 4), 7.0, device=DEV)
-    _lib.call("pfo_linear_tf32", ptr(Ad), lda, None, ptr(Wd), N if wt else K, wt, ptr(bd), ptr(brsd), 1,
-              ptr(C), N + 4, M, None, N, K, 0.5, 1, ptr(rzd), None, 0, 0, passes)
-    got = C[:, :N].cpu().numpy()
-    assert rel_err(got, full.numpy()) < (1e-5 if passes == 3 else 2e-3)
-    assert (C[:, N:] == 7.0).all()
-    # accumulate + relu gate + device-side row count: 16-byte-aligned output rows (vector stores) and an unaligned
-    # output stride (scalar stores); rows past the live count and columns past N stay untouched
-    live = max(M - 5, 1)
-    md = torch.tensor([live], dtype=torch.int32, device=DEV)
-    for pad in (4, 1):
-        gate = torch.randn(M, N + pad, generator=g)
-        C2 = torch.ones(M, N + pad, device=DEV)
-        _lib.call("pfo_linear_tf32", ptr(Ad), lda, None, ptr(Wd), N if wt else K, wt, None, None, 0,
-                  ptr(C2), N + pad, M, ptr(md), N, K, 1.0, 0, None, ptr(gate.to(DEV)), N + pad, 1, passes)
-        ref2 = A[:M, :K].double() @ W.double().t()
-        ref2[gate[:, :N] <= 0] = 0
-        ref2 = ref2 + 1.0
-        assert rel_err(C2[:live, :N].cpu().numpy(), ref2[:live].numpy()) < (1e-5 if passes == 3 else 2e-3)
-        assert (C2[live:] == 1.0).all() and (C2[:, N:] == 1.0).all()
-
-
-@pytest.mark.parametrize("M,N,K", [(3000, 192, 193), (100, 64, 130), (70000, 64, 64), (1, 128, 129)])
-def test_wgrad_f32(M, N, K):
-    from pfotgnrec_b200 import _lib
-    from pfotgnrec_b200._lib import ptr
-    g = torch.Generator(device="cpu").manual_seed(M)
-    G = torch.randn(M, N, generator=g)
-    A = torch.randn(M, K, generator=g)
-    ref = G.double().t() @ A.double()
-    refb = G.double().sum(0)
-    Gd, Ad = G.to(DEV), A.to(DEV)
-    dW = torch.zeros(N, K, device=DEV)
-    db = torch.zeros(N, device=DEV)
-    ws = torch.empty(_lib.query("pfo_wgrad_workspace_floats", M, N, K, 1), device=DEV)
-    _lib.call("pfo_wgrad_f32", ptr(Gd), N, ptr(Ad), K, None, M, None, N, K, ptr(dW), K, ptr(db), 0, ptr(ws))
-    assert rel_err(dW.cpu().numpy(), ref.numpy()) < 2e-5
-    assert rel_err(db.cpu().numpy(), refb.numpy()) < 2e-5
-    dW2 = dW.clone()
-    _lib.call("pfo_wgrad_f32", ptr(Gd), N, ptr(Ad), K, None, M, None, N, K, ptr(dW2), K, None, 1, ptr(ws))
-    assert rel_err(dW2.cpu().numpy(), 2 * ref.numpy()) < 2e-5
-    # determinism: bit-identical on a re-run
-    dW3 = torch.zeros(N, K, device=DEV)
-    _lib.call("pfo_wgrad_f32", ptr(Gd), N, ptr(Ad), K, None, M, None, N, K, ptr(dW3), K, None, 0, ptr(ws))
-    assert torch.equal(dW3, dW)
-
-
-# ------------------------------------------------------------------------------ K5
-def _mv_inputs(st, sl):
-    ptr_ = st.port_ptr[sl.start:sl.stop + 1]
-    return ptr_ - ptr_[0], st.port_items[ptr_[0]:ptr_[-1]]
-
-
-@pytest.mark.parametrize("ci", [0, 1, 2])
-def test_mv_select_golden_ids_bit_exact(ci):
-    from pfotgnrec_b200.sampler import MVSelector
-    from pfotgnrec_b200.synth import log_returns
-    z = load_golden("mv_select.npz")
-    cand = z[f"c{ci}_cand"]
-    B, C = cand.shape
-    e0 = int(z[f"c{ci}_event0"])
-    ptr_ = z["st_port_ptr"][e0:e0 + B + 1]
-    sel = MVSelector(log_returns(z["st_prices_future"]), np.arange(60), n_users=0, gamma=float(z[f"c{ci}_gamma"]),
-                     lam=float(z[f"c{ci}_lam"]), n_candidates=C - 1)
-    pp, pn = sel.select(np.arange(B), z["st_day_idx"][e0:e0 + B], cand[:, 0] + 1, ptr_ - ptr_[0],
-                        z["st_port_items"][ptr_[0]:ptr_[-1]], cand=cand)
-    assert np.array_equal(pp.cpu().numpy() - 1, z[f"c{ci}_ppos_stable"])
-    assert np.array_equal(pn.cpu().numpy() - 1, z[f"c{ci}_pneg_stable"])
-
-
-def test_mv_select_sampled_vs_oracle():
-    from oracle import sampling
-    from pfotgnrec_b200.sampler import MVSelector
-    from pfotgnrec_b200.synth import log_returns
-    st = _stream(U=500, I=300, E=4000, mode="nbg", seed=5)
-    lr = log_returns(st.prices_future)
-    universe = np.unique(st.destinations[:3000] - st.n_users - 1)
-    sl = slice(1000, 1000 + 777)
-    pptr, pitems = _mv_inputs(st, sl)
-    ev = st.edge_idxs[sl]
-    for K, lam in ((20, 0.5), (31, 0.3), (5, 0.9)):
-        sel = MVSelector(lr, universe, n_users=st.n_users, gamma=2.0, lam=lam, n_candidates=K, seed=123)
-        pp, pn, cand, y = sel.select(ev, st.day_idx[sl], st.destinations[sl], pptr, pitems, return_scores=True)
-        ref_neg = sampling.sample_candidates(ev, universe, pptr, pitems, K, seed=123)
-        ref_cand = np.concatenate([(st.destinations[sl] - st.n_users - 1)[:, None], ref_neg], axis=1)
-        assert np.array_equal(cand.cpu().numpy(), ref_cand)          # Philox candidates: bit-exact
-        ry = sampling.mv_scores(lr, st.day_idx[sl], ref_cand, pptr, pitems, 2.0)
-        assert np.array_equal(y.cpu().numpy(), ry)                   # fp64 y_mv: bit-exact (same op order, no fma)
-        rp, rn = sampling.mv_select(lr, st.day_idx[sl], ref_cand, pptr, pitems, 2.0, lam)
-        assert np.array_equal(pp.cpu().numpy() - st.n_users - 1, rp)
-        assert np.array_equal(pn.cpu().numpy() - st.n_users - 1, rn)
-
-
-@pytest.mark.parametrize("size", [3, 20, 40, 45])
-def test_candidate_sampler_vs_oracle(size):
-    from oracle import sampling
-    from pfotgnrec_b200.sampler import CandidateSampler
-    st = _stream(U=200, I=40, E=2000, mode="small", seed=9)     # 40 items: size 40/45 hits the replacement path
-    universe = np.unique(st.destinations)
-    sl = slice(100, 400)
-    pptr, pitems = _mv_inputs(st, sl)
-    held_items = pitems.astype(np.int64) + st.n_users + 1
-    cs = CandidateSampler(universe)
-    out = cs.sample(st.edge_idxs[sl], pptr, held_items, size, seed=2024).cpu().numpy()
-    ref = sampling.sample_candidates(st.edge_idxs[sl], universe, pptr, held_items, size, seed=2024)
-    assert np.array_equal(out, ref)
-    for b in range(out.shape[0]):
-        held = set(held_items[pptr[b]:pptr[b + 1]].tolist())
-        assert not (set(out[b].tolist()) & held)
-
-
-# ------------------------------------------------------------------------------ K6 / eval
-def test_bpr_forward_backward():
-    from oracle.tgn import bpr_loss
-    from pfotgnrec_b200 import _lib
-    from pfotgnrec_b200._lib import ptr
-    torch.manual_seed(0)
-    B, k, d = 517, 3, 64
-    eu, ep, en = torch.randn(B, d), torch.randn(B, d), torch.randn(B * k, d)
-    for t in (eu, ep, en):
-        t.mul_(0.3).requires_grad_(True)
-    loss = bpr_loss(eu, ep, en)
-    loss.backward()
-    du, dp, dn = (torch.empty_like(t, device=DEV) for t in (eu, ep, en))
-    out = torch.zeros(1, device=DEV)
-    ws = torch.empty(1024, device=DEV)
-    eu_d, ep_d, en_d = eu.detach().to(DEV), ep.detach().to(DEV), en.detach().to(DEV)   # keep alive across the launch
-    _lib.call("pfo_bpr", ptr(eu_d), ptr(ep_d), ptr(en_d), B, k, d,
-              ptr(du), ptr(dp), ptr(dn), ptr(out), 1.0, ptr(ws))
-    assert abs(out.item() - loss.item()) < 1e-5 * abs(loss.item())
-    assert rel_err(du.cpu().numpy(), eu.grad.numpy()) < 1e-5
-    assert rel_err(dp.cpu().numpy(), ep.grad.numpy()) < 1e-5
-    assert rel_err(dn.cpu().numpy(), en.grad.numpy()) < 1e-5
-
-
-def test_eval_score_and_ranking():
-    from oracle.tgn import eval_scores, eval_ranking
-    from pfotgnrec_b200 import _lib
-    from pfotgnrec_b200._lib import ptr
-    torch.manual_seed(1)
-    B, n_cand, d = 37, 203, 64
-    es, ed, ec = torch.randn(B, d), torch.randn(B, d), torch.randn(B * n_cand, d)
-    ec.view(B, n_cand, d)[:, 5] = ec.view(B, n_cand, d)[:, 9]        # exact ties among candidates
-    ec.view(B, n_cand, d)[::2, 3] = ed[::2]                           # ties with the positive
-    ref = eval_scores(es, ed, ec)
-    rank = eval_ranking(ref.numpy())
-    scores = torch.empty(B, 1 + n_cand, device=DEV)
+    es, ed, ec = (t.to(DEV).contiguous() for t in scores_inputs)
+    B, d = es.shape
+    N = ec.shape[0] // B
+    scores = torch.empty(B, 1 + N, device=DEV)
     pos_rank = torch.empty(B, dtype=torch.int32, device=DEV)
     top = torch.empty(B, 5, dtype=torch.int32, device=DEV)
-    es_d, ed_d, ec_d = es.to(DEV), ed.to(DEV), ec.to(DEV)
-    _lib.call("pfo_eval_score", ptr(es_d), ptr(ed_d), ptr(ec_d), B, n_cand, d, 5,
-              ptr(scores), ptr(pos_rank), ptr(top))
-    s = scores.cpu().numpy()
-    assert rel_err(s, ref.numpy()) < 1e-5
-    # ranking semantics checked on the kernel's own scores (bit-exact integer work)
-    rk = eval_ranking(s)
-    assert np.array_equal(top.cpu().numpy(), rk[:, :5])
-    assert np.array_equal(pos_rank.cpu().numpy(), np.argmax(rk == 0, axis=1))
+    _lib.call("pfo_eval_score", ptr(es), ptr(ed), ptr(ec), B, N, d, 5, ptr(scores), ptr(pos_rank), ptr(top))
+    i32 = lambda a: torch.as_tensor(np.ascontiguousarray(a).astype(np.int32), device=DEV)
+    pi = i32(port_items if len(port_items) else np.zeros(1))
+    pp = torch.as_tensor(np.ascontiguousarray(port_ptr).astype(np.int64), device=DEV)
+    pos_d, cand_d, day_d = i32(pos_item), i32(cand_item), i32(day_idx)
+    per_event = torch.full((B, 18), float("nan"), dtype=torch.float64, device=DEV)
+    _lib.call("pfo_eval_metrics", ptr(pos_rank), ptr(top), 5, ptr(pos_d), ptr(cand_d), N, int(item_offset), ptr(day_d),
+              ptr(pp), ptr(pi), ptr(lr_past), ptr(lr_future), lr_past.shape[1], lr_past.shape[2], B, ptr(per_event),
+              ptr(acc))
+    return scores.cpu().numpy(), pos_rank.cpu().numpy(), top.cpu().numpy(), per_event.cpu().numpy()
+
+
+def test_eval_metric_block_golden_and_oracle():
+    """pfo_eval_metrics (reference evaluation.py:127-258) on the inputs of the reference run behind
+    tests/golden/eval_metrics.npz: per-interaction metrics BIT-EXACT against the numpy oracle on the kernel's own
+    ranking, the 30 aggregated keys against the dictionary the unmodified reference returned."""
+    from oracle import eval_metrics as em
+    from pfotgnrec_b200.synth import log_returns
+    z = load_golden("eval_metrics.npz")
+    table = torch.tensor(z["table"])
+    e0, B, U = int(z["e0"]), int(z["B"]), int(z["st_n_users"])
+    lrp = torch.as_tensor(log_returns(z["st_prices_past"]), device=DEV).contiguous()
+    lrf = torch.as_tensor(log_returns(z["st_prices_future"]), device=DEV).contiguous()
+    acc = torch.zeros(31, dtype=torch.float64, device=DEV)
+    rows = []
+    for bi in range(int(z["n_batches"])):
+        s, e = e0 + bi * B, e0 + (bi + 1) * B
+        src, dst, neg = z["st_sources"][s:e], z["st_destinations"][s:e], z["negatives"][bi]
+        ptr_ = z["st_port_ptr"][s:e + 1]
+        held = z["st_port_items"][ptr_[0]:ptr_[-1]]
+        emb = (table[torch.as_tensor(src)], table[torch.as_tensor(dst)], table[torch.as_tensor(neg.reshape(-1))])
+        sc, rk, top, pe = _eval_metrics_on_device(emb, dst, neg, U + 1, z["st_day_idx"][s:e], ptr_ - ptr_[0], held,
+                                                  lrp, lrf, acc)
+        ref, ork, otop = em.per_event_metrics(sc, dst - U - 1, neg - U - 1, z["st_day_idx"][s:e], ptr_ - ptr_[0], held,
+                                              z["st_prices_past"], z["st_prices_future"])
+        assert np.array_equal(rk, ork) and np.array_equal(top, otop)
+        assert np.array_equal(pe, ref), np.abs(pe - ref).max()          # fp64, rounded like numpy: bit-exact
+        rows.append(pe)
+    allrows = np.concatenate(rows)
+    a = acc.cpu().numpy()
+    assert a[30] == allrows.shape[0]
+    assert np.allclose(a[:18], allrows.sum(axis=0), rtol=1e-13, atol=1e-15)
+    assert np.array_equal(a[18:30], (allrows[:, 6:] > 0).sum(axis=0))
+    got = em.aggregate(allrows, "val")
+    for k, v in z.items():
+        if k.startswith("res_stable_"):
+            assert abs(got[k[len("res_stable_"):]] - float(v)) <= 1e-12 * max(1.0, abs(float(v))), k
+
+
+def test_eval_metric_block_edge_cases():
+    """Empty portfolios for every interaction, portfolios of 1..5 stocks, the true item ranked first / last,
+    ragged batch (not a multiple of the warps per CTA), T < 8 and T = 32 return columns (numpy's two summation
+    regimes)."""
+    from oracle import eval_metrics as em
+    rng = np.random.default_rng(7)
+    for T1, B, I, maxp in ((30, 77, 25, 5), (6, 33, 12, 0), (33, 130, 40, 3)):
+        D = 4
+        prices = [np.exp(np.cumsum(rng.standard_normal((D, I, T1)) * 0.02, axis=2)) * 50.0 for _ in range(2)]
+        plen = rng.integers(0, maxp + 1, size=B)
+        pp = np.r_[0, np.cumsum(plen)].astype(np.int64)
+        held = np.concatenate([rng.choice(I, size=n, replace=False) for n in plen] + [np.zeros(0, np.int64)]).astype(np.int64)
+        day = rng.integers(0, D, size=B)
+        N, d = 19, 16
+        es, ed, ec = torch.randn(B, d), torch.randn(B, d), torch.randn(B * N, d)
+        ed[:5] = es[:5] * 10.0                     # true item first
+        ed[5:10] = -es[5:10] * 10.0                # true item last
+        pos = rng.integers(0, I, size=B) + 100
+        cand = rng.integers(0, I, size=(B, N)) + 100
+        lrp, lrf = (torch.as_tensor(np.log(p[..., 1:] / p[..., :-1]), device=DEV).contiguous() for p in prices)
+        sc, rk, top, pe = _eval_metrics_on_device((es, ed, ec), pos, cand, 100, day, pp, held, lrp, lrf)
+        ref, ork, otop = em.per_event_metrics(sc, pos - 100, cand - 100, day, pp, held, prices[0], prices[1])
+        assert np.array_equal(rk, ork) and np.array_equal(top, otop)
+        assert (rk[:5] == 0).all() and (rk[5:10] == N).all()
+        assert np.array_equal(pe, ref), (T1, np.abs(pe - ref).max())
 
 
 # ------------------------------------------------------------------------------ bf16 tcgen05 path

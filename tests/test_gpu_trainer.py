@@ -140,3 +140,60 @@ def test_eval_step_graph_replay_matches_eager_and_oracle():
     a = res[0][0][0]
     assert np.array_equal(a[2], cand - 0) and rel_err(a[3], scores) < 1e-5
     assert np.array_equal(a[0], rk) and np.array_equal(a[1], top5)
+    # the metric block of the same step (evaluation.py:127-207) against the numpy oracle, on the kernel's ranking
+    from oracle import eval_metrics as em
+    U = st.n_users
+    pp = st.port_ptr[2400:2465]
+    ref, _, _ = em.per_event_metrics(a[3], st.destinations[2400:2464] - U - 1, a[2] - U - 1, st.day_idx[2400:2464],
+                                     pp - pp[0], st.port_items[pp[0]:pp[-1]], st.prices_past, st.prices_future)
+    assert np.array_equal(a[4], ref)
+    for outs, t in res:                                   # running sums on the device == sum of the per-batch tables
+        allrows = np.concatenate([o[4] for o in outs])
+        acc = t.eval_acc.cpu().numpy()
+        assert acc[30] == allrows.shape[0] and np.allclose(acc[:18], allrows.sum(axis=0), rtol=1e-12, atol=1e-14)
+        summ = t.eval_summary("test")
+        assert abs(summ["test_recall_avg_5"] - allrows[:, 2].mean()) < 1e-12 and len(summ) == 30
+
+
+def test_evaluate_loop_skips_last_batch_like_reference():
+    """PfoTrainer.evaluate == the loop of reference evaluation.py:63-69: full batches only, the last one skipped."""
+    from pfotgnrec_b200.trainer import PfoTrainer, TrainConfig
+    st = _stream(seed=5)
+    tr = PfoTrainer(st, TrainConfig(model="ours", bs=64, cuda_graph=False), device="cuda:0")
+    out = tr.evaluate(2400, 2400 + 64 * 3 + 10, bs=64, n_items=30, EVAL="val")
+    assert float(tr.eval_acc[30].item()) == 64 * 3
+    out2 = tr.evaluate(2700, 2700 + 64 * 2, bs=64, n_items=30, EVAL="val")      # exact multiple: last batch skipped too
+    assert float(tr.eval_acc[30].item()) == 64
+    assert set(out) == set(out2) and all(np.isfinite(v) for v in out.values())
+
+
+def test_overlay_eval_recommendation_matches_trainer_loop(tmp_path, monkeypatch):
+    """The drop-in `evaluation.eval_recommendation` (reference signature, data read from the reference's on-disk
+    files: pickled price dictionaries, stock codes, 'YYYYMMDD' day keys) == PfoTrainer.evaluate on the in-memory
+    stream: same 30 keys, same values."""
+    import types
+    from pfotgnrec_b200.synth import make_stream, write_reference_format
+    from pfotgnrec_b200.trainer import PfoTrainer, TrainConfig
+    st = make_stream(n_users=300, n_items=60, n_events=3000, n_days=20, seed=6, ts_mode="nbg")
+    write_reference_format(st, str(tmp_path), period="30")
+    monkeypatch.chdir(tmp_path)
+    tc = TrainConfig(model="ours", bs=64, cuda_graph=False)
+    a, b = PfoTrainer(st, tc, device="cuda:0"), PfoTrainer(st, tc, device="cuda:0")
+    for t in (a, b):
+        for i in range(3):                       # some history in memory / pending messages first
+            t.train_step(2000 + i * 64, 2000 + (i + 1) * 64)
+    s, e = 2400, 2400 + 64 * 3 + 20
+    want = a.evaluate(s, e, bs=64, EVAL="val")
+    import evaluation as ev_mod                  # pfotgnrec_b200/overlay/evaluation.py (load_overlay put it on sys.path)
+    assert "overlay" in ev_mod.__file__
+    ev_mod._TABLES.clear()
+    portfolios = np.array([[st.codes[k] for k in st.portfolio(i)] or [""] for i in range(st.n_events)], dtype=object)
+    ns = lambda sl: types.SimpleNamespace(sources=st.sources[sl], destinations=st.destinations[sl],
+                                          timestamps=st.timestamps[sl], edge_idxs=st.edge_idxs[sl],
+                                          portfolios=portfolios[sl])
+    b.tgn.set_neighbor_finder(b.nf_full)
+    got = ev_mod.eval_recommendation(b.tgn, ns(slice(s, e)), ns(slice(None)), 64, 10, st.n_users, "30", False, "val")
+    assert set(got) == set(want) and len(got) == 30
+    for k in want:
+        assert abs(got[k] - want[k]) <= 1e-12 * max(1.0, abs(want[k])), (k, got[k], want[k])
+    assert rel_err(b.tgn.memory.memory.detach().cpu().numpy(), a.tgn.memory.memory.detach().cpu().numpy()) < 1e-6

@@ -82,3 +82,33 @@ def test_time_statistics_host_vs_oracle():
         st = make_stream(n_users=200, n_items=40, n_events=2500, n_days=15, seed=5, ts_mode=mode, with_prices=False)
         assert tuple(host_stats(st.sources, st.destinations, st.timestamps)) == \
             oracle_stats(st.sources, st.destinations, st.timestamps)
+
+
+def _eval_golden_batches(z):
+    """(scores, pos_stock, cand_stock, day_idx, port_ptr, port_items) per batch of tests/golden/eval_metrics.npz;
+    scores are formed like reference evaluation.py:107-115 from the stub model's embedding table."""
+    table = torch.tensor(z["table"])
+    e0, B, U = int(z["e0"]), int(z["B"]), int(z["st_n_users"])
+    for bi in range(int(z["n_batches"])):
+        s, e = e0 + bi * B, e0 + (bi + 1) * B
+        src, dst, neg = z["st_sources"][s:e], z["st_destinations"][s:e], z["negatives"][bi]
+        es = table[torch.as_tensor(src)].view(B, 1, -1)
+        pos = torch.sum(es * table[torch.as_tensor(dst)].view(B, 1, -1), dim=2)
+        negs = torch.sum(es * table[torch.as_tensor(neg.reshape(-1))].view(B, neg.shape[1], -1), dim=2)
+        scores = torch.cat([pos, negs], dim=1).numpy()
+        ptr = z["st_port_ptr"][s:e + 1]
+        yield (scores, dst - U - 1, neg - U - 1, z["st_day_idx"][s:e], ptr - ptr[0],
+               z["st_port_items"][ptr[0]:ptr[-1]])
+
+
+def test_eval_metric_block_matches_reference():
+    """oracle/eval_metrics.py vs the dictionary the unmodified reference eval_recommendation returned
+    (evaluation.py:127-258) on the same scores: 30 keys, fp64."""
+    from oracle import eval_metrics as em
+    z = load_golden("eval_metrics.npz")
+    rows = [em.per_event_metrics(*b, z["st_prices_past"], z["st_prices_future"])[0] for b in _eval_golden_batches(z)]
+    got = em.aggregate(np.concatenate(rows), "val")
+    ref = {k[len("res_stable_"):]: float(v) for k, v in z.items() if k.startswith("res_stable_")}
+    assert set(got) == set(ref) and len(ref) == 30
+    for k, v in ref.items():
+        assert abs(got[k] - v) <= 1e-12 * max(1.0, abs(v)), (k, got[k], v)

@@ -18,7 +18,7 @@ OVERLAY = os.path.join(ROOT, "pfotgnrec_b200", "overlay")
 @pytest.fixture(scope="module")
 def overlay():
     sys.path.insert(0, OVERLAY)
-    for m in [k for k in sys.modules if k.split(".")[0] in ("model", "modules", "utils")]:
+    for m in [k for k in sys.modules if k.split(".")[0] in ("model", "modules", "utils", "evaluation")]:
         del sys.modules[m]
     import model.tgn as tgn_mod
     import utils.utils as utils_mod
@@ -62,6 +62,10 @@ def test_import_surface(overlay):
         assert hasattr(utils_mod, name)
     for name in ("compute_temporal_embeddings_p", "compute_temporal_embeddings", "set_neighbor_finder"):
         assert hasattr(tgn_mod.TGN, name)
+    import evaluation as ev_mod            # overlay/evaluation.py shadows the reference's top-level module
+    import inspect
+    assert list(inspect.signature(ev_mod.eval_recommendation).parameters) == [
+        "tgn", "data", "full_data", "batch_size", "n_neighbors", "upper_u", "period", "is_test_run", "EVAL"]
     import modules.memory as mm
     for name in ("__init_memory__", "detach_memory", "backup_memory", "restore_memory", "get_memory",
                  "set_memory", "get_last_update", "store_raw_messages", "clear_messages"):
