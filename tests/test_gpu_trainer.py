@@ -178,12 +178,14 @@ def test_overlay_eval_recommendation_matches_trainer_loop(tmp_path, monkeypatch)
     write_reference_format(st, str(tmp_path), period="30")
     monkeypatch.chdir(tmp_path)
     tc = TrainConfig(model="ours", bs=64, cuda_graph=False)
-    a, b = PfoTrainer(st, tc, device="cuda:0"), PfoTrainer(st, tc, device="cuda:0")
-    for t in (a, b):
-        for i in range(3):                       # some history in memory / pending messages first
-            t.train_step(2000 + i * 64, 2000 + (i + 1) * 64)
+    a = PfoTrainer(st, tc, device="cuda:0")
+    for i in range(3):                           # some history in memory / pending messages first
+        a.train_step(2000 + i * 64, 2000 + (i + 1) * 64)
     s, e = 2400, 2400 + 64 * 3 + 20
+    state0 = a.tgn.memory.state.backup()         # both loops start from the same state and weights
     want = a.evaluate(s, e, bs=64, EVAL="val")
+    mem_want = a.tgn.memory.memory.detach().clone()
+    a.tgn.memory.state.restore(state0)
     import evaluation as ev_mod                  # pfotgnrec_b200/overlay/evaluation.py (load_overlay put it on sys.path)
     assert "overlay" in ev_mod.__file__
     ev_mod._TABLES.clear()
@@ -191,9 +193,9 @@ def test_overlay_eval_recommendation_matches_trainer_loop(tmp_path, monkeypatch)
     ns = lambda sl: types.SimpleNamespace(sources=st.sources[sl], destinations=st.destinations[sl],
                                           timestamps=st.timestamps[sl], edge_idxs=st.edge_idxs[sl],
                                           portfolios=portfolios[sl])
-    b.tgn.set_neighbor_finder(b.nf_full)
-    got = ev_mod.eval_recommendation(b.tgn, ns(slice(s, e)), ns(slice(None)), 64, 10, st.n_users, "30", False, "val")
+    a.tgn.set_neighbor_finder(a.nf_full)
+    got = ev_mod.eval_recommendation(a.tgn, ns(slice(s, e)), ns(slice(None)), 64, 10, st.n_users, "30", False, "val")
     assert set(got) == set(want) and len(got) == 30
     for k in want:
-        assert abs(got[k] - want[k]) <= 1e-12 * max(1.0, abs(want[k])), (k, got[k], want[k])
-    assert rel_err(b.tgn.memory.memory.detach().cpu().numpy(), a.tgn.memory.memory.detach().cpu().numpy()) < 1e-6
+        assert got[k] == want[k], (k, got[k], want[k])
+    assert torch.equal(a.tgn.memory.memory.detach(), mem_want)
