@@ -51,8 +51,11 @@ struct TmaLinArgs {
     int KP8;           // K rounded up to the MMA K step (8)
     int n_chunks;      // ceil(K / 32)
     int stages;
-    int tmem_cols;     // allocated TMEM columns (power of two >= 2 * NT)
+    int tmem_cols;     // allocated TMEM columns (power of two >= 2 * NT [+ 32 * stages in 3-pass mode])
+    int acc_stride;    // TMEM columns between the two accumulators
+    int lo_col;        // 3-pass mode: first TMEM column of the A-lo slots (32 columns per stage)
     int vec_ok;        // C / relu_gate rows are 16-byte aligned
+    int dbg;           // timing experiments only (wrong numerics): 1 = splitters skip their work, 2 = one MMA per K step
     long long* trace;  // diagnostic timeline of CTA (0,0) (tools/linear_trace.py); null in normal use
 };
 
@@ -93,6 +96,20 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t da, uint64
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
         :: "r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
 }
+// A operand from tensor memory (lane = row, one 32-bit column per K element), B from shared memory
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n"
+        :: "r"(d_tmem), "r"(a_tmem), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+        :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+           "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
 // K-major operand in the 128-byte-swizzled layout TMA writes (8-row x 128 B atoms, SBO = 1024 B)
 __device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {
     return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
@@ -118,6 +135,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         : "r"(taddr));
 }
 
+// One lane of a converged warp.  The TMA / MMA issue loops are executed by the WHOLE warp and only the instruction
+// itself is predicated on the elected lane: loop counters and descriptors then stay warp-uniform for the compiler
+// (uniform registers feed UTMALDG / UTCHMMA directly).  Under `if (lane == 0)` every operand lived in a vector
+// register and each tcgen05.mma cost an ELECT + 4x R2UR.BROADCAST waterfall loop (~110 cycles per MMA, measured).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 constexpr int EPI_WARPS = 8;                         // two per TMEM lane quarter
 constexpr int SPLIT_WARPS = 8;                       // operand splitters of the 3-pass mode
 constexpr int THREADS_1 = 32 * (2 + EPI_WARPS), THREADS_3 = THREADS_1 + 32 * SPLIT_WARPS;
@@ -132,20 +159,24 @@ template <int PASSES>
 __global__ void __launch_bounds__(PASSES == 3 ? THREADS_3 : THREADS_1, 1)
 linear_tma_kernel(const __grid_constant__ CUtensorMap tmA, const TmaLinArgs p) {
     extern __shared__ uint8_t smem_raw[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler (role dispatch)
     const int NT = p.NT, KP8 = p.KP8, stages = p.stages, n_chunks = p.n_chunks;
     const int n0 = blockIdx.y * NT;
     if (tid == 0) PFO_TRACE(0);
+    if (p.trace && tid == 0) {                                     // diagnostic: wall-clock window of every CTA
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[128 + 2 * (blockIdx.y * gridDim.x + blockIdx.x)] = (long long)t;
+    }
 
     // ---- carve shared memory (stages and the store staging need 1024-byte alignment for the 128-byte swizzle)
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
     uint8_t* base = smem_raw + pad;
-    uint8_t* sA = base;                                            // [stages][16 KiB]  A (hi)
-    uint8_t* sAlo = sA + (size_t)stages * CHUNK_BYTES;             // [stages][16 KiB]  A lo (3-pass)
-    uint8_t* sOut = sAlo + (PASSES == 3 ? (size_t)stages * CHUNK_BYTES : 0);   // [EPI_WARPS][32 rows x 64 B]
+    uint8_t* sA = base;                                            // [stages][16 KiB]  A (hi in 3-pass mode; lo lives in TMEM)
+    uint8_t* sOut = sA + (size_t)stages * CHUNK_BYTES;             // [EPI_WARPS][32 rows x 64 B]
     uint8_t* sW = sOut + EPI_BYTES;
-    const uint32_t w_bytes = (uint32_t)NT * KP8 * 4;               // [KP8/4][NT/8][8 rows][16 B]
+    const uint32_t w_bytes = (uint32_t)(KP8 >> 2) * ((uint32_t)NT * 16u + 16u);   // [KP8/4][NT/8 core matrices (8 rows x 16 B) + 16 B pad]
     uint8_t* sWlo = sW + w_bytes;
     float* sBias = reinterpret_cast<float*>(sWlo + (PASSES == 3 ? w_bytes : 0));   // [NT]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + NT);
@@ -176,31 +207,42 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tmA, const TmaLinArgs p) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     __syncthreads();                                               // barriers initialised
+    if (tid == 64) PFO_TRACE(3);
 
     // ---- the activation stream does not depend on the weights: fill the ring before staging them
     Producer pr{0, 0u, (int64_t)blockIdx.x, 0};
-    auto produce = [&](int max_chunks) {
+    auto produce = [&](int max_chunks) {                           // executed by the whole warp 0
         int issued = 0;
         while (pr.tile < n_tiles && issued < max_chunks) {
             mbar_wait(empty_bar(pr.stage), pr.phase ^ 1u);
-            mbar_arrive_expect_tx(full_bar(pr.stage), CHUNK_BYTES);
-            tma_load_2d(smem_u32(sA + (size_t)pr.stage * CHUNK_BYTES), &tmA, pr.c * CK, (int)(pr.tile * TM), full_bar(pr.stage));
+            if (elect_one()) {
+                mbar_arrive_expect_tx(full_bar(pr.stage), CHUNK_BYTES);
+                tma_load_2d(smem_u32(sA + (size_t)pr.stage * CHUNK_BYTES), &tmA, pr.c * CK, (int)(pr.tile * TM), full_bar(pr.stage));
+            }
             ++issued;
             if (++pr.stage == stages) { pr.stage = 0; pr.phase ^= 1u; }
             if (++pr.c == n_chunks) { pr.c = 0; pr.tile += gridDim.x; }
         }
+        __syncwarp();
     };
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
-        PFO_TRACE(8);
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+            PFO_TRACE(8);
+        }
+        __syncwarp();
         produce(stages);
     }
-    // ---- stage the weight slice once: rna(w) (and the residual) into core-matrix order; consecutive threads
-    // take consecutive output columns n, so the 16-byte shared-memory writes of a warp are contiguous
+    // ---- stage the weight slice once: rna(w) (and the residual) into core-matrix order (8 rows x 16 bytes).
+    // The warp's lanes run along the CONTIGUOUS axis of W in global memory -- K for row-major weights, N for
+    // transposed ones -- so a load instruction touches 4 lines, not 32 (the uncoalesced version spent 2-6 us of a
+    // 10-40 us launch in LSU replays).  Core matrices of consecutive K units are w_lbo = NT * 16 + 16 bytes apart:
+    // the 16-byte pad walks the banks, so the K-major store pattern is conflict-free too.
     {
         const int kcs = KP8 >> 2;                                  // 16-byte units along K
         const bool vec = !p.w_transposed && (p.ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.W) & 15) == 0);
         const int units = NT * kcs;
+        const uint32_t lbo = (uint32_t)NT * 16u + 16u;
         constexpr int U = 4;                                       // units in flight per thread
         for (int i0 = tid; i0 < units; i0 += U * blockDim.x) {
             float w[U][4];
@@ -208,7 +250,7 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tmA, const TmaLinArgs p) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int i = i0 + u * blockDim.x;
-                nn[u] = i % NT; kk[u] = i / NT;
+                if (p.w_transposed) { nn[u] = i % NT; kk[u] = i / NT; } else { kk[u] = i % kcs; nn[u] = i / kcs; }
                 const int ng = n0 + nn[u], kc = kk[u];
                 w[u][0] = w[u][1] = w[u][2] = w[u][3] = 0.f;
                 if (i < units && ng < p.N) {
@@ -231,11 +273,12 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tmA, const TmaLinArgs p) {
                 float hi[4], lo[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { hi[j] = rna_tf32(w[u][j]); lo[j] = w[u][j] - hi[j]; }
-                const size_t off = (size_t)kk[u] * (NT * 16) + (size_t)(nn[u] >> 3) * 128 + (size_t)(nn[u] & 7) * 16;
+                const size_t off = (size_t)kk[u] * lbo + (size_t)(nn[u] >> 3) * 128 + (size_t)(nn[u] & 7) * 16;
                 *reinterpret_cast<float4*>(sW + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
                 if (PASSES == 3) *reinterpret_cast<float4*>(sWlo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
             }
         }
+        if (tid == 64) PFO_TRACE(4);
         for (int n = tid; n < NT; n += blockDim.x) sBias[n] = (p.bias && n0 + n < p.N) ? __ldg(p.bias + n0 + n) : 0.0f;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core proxy
@@ -243,22 +286,24 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tmA, const TmaLinArgs p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t acc_stride = (uint32_t)p.tmem_cols >> 1;
+    const uint32_t acc_stride = (uint32_t)p.acc_stride;
     if (tid == 0) PFO_TRACE(1);
     int tr_tile = 0;
 
     if (warp == 0) {
         // ===== TMA producer (steady state) =====
-        if (lane == 0) produce(0x7fffffff);
-        __syncwarp();
+        produce(0x7fffffff);
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer (whole warp walks the loops, the elected lane issues) =====
+        {
             // D = f32, A = B = tf32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-            const uint32_t a_base = smem_u32(sA), alo_base = smem_u32(sAlo);
-            const uint32_t w_base = smem_u32(sW), wlo_base = smem_u32(sWlo);
-            const uint32_t w_lbo = (uint32_t)NT * 16u;
+            const uint32_t a_base = smem_u32(sA), alo_tmem = tmem_base + (uint32_t)p.lo_col;
+            const uint32_t w_lbo = (uint32_t)NT * 16u + 16u;
+            const uint64_t da0 = desc_sw128(a_base);               // + byte offset >> 4 in the low word
+            const uint64_t dw0 = desc_nosw(smem_u32(sW), w_lbo, 128u);
+            const uint64_t dwlo0 = desc_nosw(smem_u32(sWlo), w_lbo, 128u);
+            const bool one_mma = PASSES == 3 && (p.dbg & 2);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -268,28 +313,36 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tmA, const TmaLinArgs p) {
                 for (int c = 0; c < n_chunks; ++c) {
                     mbar_wait(PASSES == 3 ? ready_bar(stage) : full_bar(stage), phase);
                     tc_fence_after();
-                    if (c == 0 && tr_tile < 8) PFO_TRACE(8 + 8 * tr_tile + 2);
+                    if (c == 0 && lane == 0 && tr_tile < 8) PFO_TRACE(8 + 8 * tr_tile + 2);
                     int ksteps = (KP8 - c * CK) >> 3;
                     if (ksteps > 4) ksteps = 4;
-                    for (int s = 0; s < ksteps; ++s) {
-                        const uint32_t koff = (uint32_t)(c * 4 + s) * 2u * w_lbo;
-                        const uint64_t da = desc_sw128(a_base + (uint32_t)stage * CHUNK_BYTES + (uint32_t)s * 32u);
-                        const uint64_t dw = desc_nosw(w_base + koff, w_lbo, 128u);
-                        if (PASSES == 3) {
-                            const uint64_t dalo = desc_sw128(alo_base + (uint32_t)stage * CHUNK_BYTES + (uint32_t)s * 32u);
-                            const uint64_t dwlo = desc_nosw(wlo_base + koff, w_lbo, 128u);
-                            tc_mma_tf32(d_tmem, dalo, dw, idesc, (c | s) ? 1u : 0u);   // small terms first
-                            tc_mma_tf32(d_tmem, da, dwlo, idesc, 1u);
-                            tc_mma_tf32(d_tmem, da, dw, idesc, 1u);
-                        } else {
-                            tc_mma_tf32(d_tmem, da, dw, idesc, (c | s) ? 1u : 0u);
+                    const uint32_t a_off = ((uint32_t)stage * CHUNK_BYTES) >> 4;
+                    const uint32_t w_off = ((uint32_t)(c * 4) * 2u * w_lbo) >> 4;
+                    const uint32_t w_step = (2u * w_lbo) >> 4;
+                    if (elect_one()) {
+#pragma unroll 4
+                        for (int s = 0; s < ksteps; ++s) {
+                            const uint64_t da = da0 + (uint64_t)(a_off + (uint32_t)s * 2u);
+                            const uint64_t dw = dw0 + (uint64_t)(w_off + (uint32_t)s * w_step);
+                            const uint32_t first = (c | s) ? 1u : 0u;
+                            if (PASSES == 3 && !one_mma) {
+                                const uint64_t dwlo = dwlo0 + (uint64_t)(w_off + (uint32_t)s * w_step);
+                                // A_lo . W_hi: A from its TMEM slot (lane = row, columns = the chunk's 32 K elements)
+                                tc_mma_tf32_ts(d_tmem, alo_tmem + (uint32_t)stage * 32u + (uint32_t)s * 8u, dw, idesc, first);
+                                tc_mma_tf32(d_tmem, da, dwlo, idesc, 1u);      // small terms first
+                                tc_mma_tf32(d_tmem, da, dw, idesc, 1u);
+                            } else {
+                                tc_mma_tf32(d_tmem, da, dw, idesc, first);
+                            }
                         }
+                        tc_commit(empty_bar(stage));               // stage free once these MMAs retire
                     }
-                    tc_commit(empty_bar(stage));                   // stage free once these MMAs retire
+                    __syncwarp();
                     if (++stage == stages) { stage = 0; phase ^= 1u; }
                 }
-                tc_commit(tfull_bar(acc));                         // accumulator complete
-                if (tr_tile < 8) PFO_TRACE(8 + 8 * tr_tile + 3);
+                if (elect_one()) tc_commit(tfull_bar(acc));        // accumulator complete
+                __syncwarp();
+                if (lane == 0 && tr_tile < 8) PFO_TRACE(8 + 8 * tr_tile + 3);
                 ++tr_tile;
                 acc ^= 1; if (acc == 0) acc_phase ^= 1u;
             }
@@ -379,26 +432,40 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tmA, const TmaLinArgs p) {
             acc ^= 1; if (acc == 0) acc_phase ^= 1u;
         }
     } else if (PASSES == 3) {
-        // ===== operand splitters: hi = rna_tf32(a) in place, lo = a - hi into the twin stage
-        const int t = tid - THREADS_1;
+        // ===== operand splitters: hi = rna_tf32(a) in place, lo = a - hi into the stage's TMEM slot (the A operand of
+        // the A_lo . W_hi MMA comes from tensor memory, so the ring holds twice the stages a shared-memory twin allowed).
+        // Thread = one row of the tile (TMEM lane), warp pair per lane quarter, 16 of the chunk's 32 columns each.
+        const int q = warp & 3, half = (warp - (2 + EPI_WARPS)) >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t row_off = (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
+        const uint32_t lo_taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)p.lo_col + (uint32_t)half * 16u;
         int stage = 0; uint32_t phase = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int c = 0; c < n_chunks; ++c) {
                 mbar_wait(full_bar(stage), phase);
-                if (c == 0 && t == 0 && tr_tile < 8) PFO_TRACE(8 + 8 * tr_tile + 1);
-                float4* hi = reinterpret_cast<float4*>(sA + (size_t)stage * CHUNK_BYTES);
-                float4* lo = reinterpret_cast<float4*>(sAlo + (size_t)stage * CHUNK_BYTES);
-#pragma unroll
-                for (int j = 0; j < CHUNK_BYTES / 16 / (32 * SPLIT_WARPS); ++j) {
-                    const int idx = t + 32 * SPLIT_WARPS * j;
-                    const float4 v = hi[idx];
-                    float4 h, l;
-                    h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
-                    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-                    hi[idx] = h;
-                    lo[idx] = l;
+                if (c == 0 && tid == THREADS_1 && tr_tile < 8) PFO_TRACE(8 + 8 * tr_tile + 1);
+                uint8_t* st = sA + (size_t)stage * CHUNK_BYTES + row_off;
+                uint32_t lo[16];
+                if (p.dbg & 1) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(ready_bar(stage));
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
+                    continue;
                 }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float4* ptr4 = reinterpret_cast<float4*>(st + ((((uint32_t)(half * 4 + j)) ^ sw) << 4));
+                    const float4 v = *ptr4;
+                    float4 h;
+                    h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+                    lo[j * 4 + 0] = __float_as_uint(v.x - h.x); lo[j * 4 + 1] = __float_as_uint(v.y - h.y);
+                    lo[j * 4 + 2] = __float_as_uint(v.z - h.z); lo[j * 4 + 3] = __float_as_uint(v.w - h.w);
+                    *ptr4 = h;
+                }
+                tmem_st16(lo_taddr + (uint32_t)stage * 32u, lo);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(ready_bar(stage));
                 if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -410,6 +477,10 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tmA, const TmaLinArgs p) {
     tc_fence_before();
     __syncthreads();
     if (tid == 0) PFO_TRACE(2);
+    if (p.trace && tid == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[128 + 2 * (blockIdx.y * gridDim.x + blockIdx.x) + 1] = (long long)t;
+    }
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
@@ -448,12 +519,17 @@ int launch_tma(const CUtensorMap& map, const TmaLinArgs& a, dim3 grid, size_t sm
 }
 
 long long* g_linear_trace = nullptr;
+int g_linear_min_stages = 2;
+int g_linear_dbg = 0;
 
 }  // namespace
 
 // Diagnostic hook (not part of the product ABI, not declared in include/pfo_b200.h): when set to a device buffer
 // of >= 80 int64, CTA (0,0) of every pfo_linear_tf32 launch records clock64() at its pipeline milestones.
 PFO_API void pfo_debug_set_linear_trace(void* device_buffer) { g_linear_trace = static_cast<long long*>(device_buffer); }
+
+PFO_API void pfo_debug_set_linear_min_stages(int n) { g_linear_min_stages = n; }
+PFO_API void pfo_debug_set_linear_dbg(int flags) { g_linear_dbg = flags; }
 
 // Builds the 2-D tensor map of a row-major fp32 matrix [rows, cols] (row stride ld floats) with
 // 32-column x box_rows boxes and the 128-byte swizzle (atom32: 32-byte swizzle atoms, the form the tensor
@@ -491,31 +567,43 @@ PFO_API int pfo_linear_tf32(const float* A, int64_t lda, const int32_t* a_idx, c
     a.ld_brs = ld_brs; a.C = C; a.ldc = ldc; a.M = M; a.m_dev = m_dev; a.N = N; a.K = K; a.alpha = alpha; a.act = act;
     a.row_zero = row_zero; a.relu_gate = relu_gate; a.ld_gate = ld_gate; a.accumulate = accumulate;
     a.trace = g_linear_trace;
+    a.dbg = g_linear_dbg;
     a.KP8 = (K + 7) / 8 * 8;
     a.n_chunks = (K + CK - 1) / CK;
     a.vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
                (!relu_gate || ((ld_gate % 4 == 0) && ((reinterpret_cast<uintptr_t>(relu_gate) & 15) == 0)));
-    const int mult = passes == 3 ? 2 : 1;
-    const int stage_bytes = CHUNK_BYTES * mult;
+    const int mult = passes == 3 ? 2 : 1;        // weight copies in shared memory (hi, lo); the A-lo operand lives in TMEM
+    const int stage_bytes = CHUNK_BYTES;
     // output staging, barriers + TMEM slot, alignment slack; the bias slice (4 * NT bytes) is counted with the weights
     const int fixed = EPI_BYTES + 8 * (3 * MAX_STAGES + 4) + 16 + 1024;
     const int budget = SMEM_LIMIT - fixed;
+    // Output columns per CTA (whole 32-column store slabs).  The ring must be deep enough to keep the HBM latency
+    // covered (Little: ~100 KB in flight per SM), so N is cut into more column tiles -- whose CTAs re-read the row
+    // tile from L2 -- until `want` stages fit beside the resident weight slice; 3-pass mode also needs
+    // 2 * NT + 32 * stages <= 512 TMEM columns.
+    const int want = g_linear_min_stages;
     int n_ntiles = (N + 255) / 256;
-    int NT;                                      // output columns per CTA: whole 32-column store slabs
+    int NT, stages;
     for (;;) {
         NT = ((N + n_ntiles - 1) / n_ntiles + 31) / 32 * 32;
-        if ((int64_t)NT * (a.KP8 * 4 * mult + 4) + 2 * stage_bytes <= budget) break;
-        if (NT <= 32) return (int)cudaErrorInvalidValue;
+        const int64_t wb = (int64_t)(a.KP8 / 4) * (NT * 16 + 16) * mult + 4 * NT;
+        stages = wb < budget ? (int)((budget - wb) / stage_bytes) : 0;
+        if (stages > MAX_STAGES) stages = MAX_STAGES;
+        if (passes == 3 && stages > (512 - 2 * NT) / 32) stages = (512 - 2 * NT) / 32;
+        if (stages >= want || NT <= 32) break;
         ++n_ntiles;
     }
+    if (stages < 1) return (int)cudaErrorInvalidValue;
     a.NT = NT;
-    const int w_bytes = NT * (a.KP8 * 4 * mult + 4);
-    int stages = (budget - w_bytes) / stage_bytes;
-    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    n_ntiles = (N + NT - 1) / NT;
+    const int w_bytes = (a.KP8 / 4) * (NT * 16 + 16) * mult + 4 * NT;
     a.stages = stages;
     int cols = 32;
-    while (cols < 2 * NT) cols <<= 1;
+    const int need_cols = passes == 3 ? 2 * NT + 32 * stages : 2 * NT;
+    while (cols < need_cols) cols <<= 1;
     a.tmem_cols = cols;
+    a.acc_stride = passes == 3 ? NT : cols >> 1;
+    a.lo_col = 2 * NT;
     CUtensorMap map;
     int rc = pfo_make_tensor_map_f32(&map, A, M, K, lda, TM, 0);
     if (rc) return rc;
