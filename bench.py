@@ -44,6 +44,10 @@ def parse():
                          "all-to-all routing (pfotgnrec_b200/dist.py)")
     ap.add_argument("--eval-steps", type=int, default=8)
     ap.add_argument("--eval-bs", type=int, default=512, help="users per evaluation batch and GPU (reference --bs default)")
+    ap.add_argument("--large-bs", type=int, default=65536,
+                    help="also time the step at this batch size (BASELINE config 4's) and report its per-kernel rooflines "
+                         "under `large_batch`: at bs 8192 every kernel runs 10-40 us and is bound by launch / pipeline-fill "
+                         "latency, not by HBM; 0 disables")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     return ap.parse_args()
@@ -381,6 +385,44 @@ def main():
         top = max(agg.items(), key=lambda kv: kv[1]["ms"])[0]
         roofline = rooflines.get(top)
 
+    # ---- the same step at the scale configuration's batch size: what the kernels reach once a launch carries enough
+    # rows to leave the latency regime (extra information; `value` above stays the bs-8192 headline)
+    large = None
+    if a.large_bs > 0 and world == 1 and not a.no_profile and a.large_bs != bs and pos[0] + 14 * a.large_bs < st.n_events:
+        BL = a.large_bs
+
+        def lstep(_i=None):
+            s = pos[0]
+            pos[0] += BL
+            return tr.train_step(s, s + BL)
+
+        for _ in range(4):                           # two eager steps, capture, one replay
+            lstep()
+        torch.cuda.synchronize()
+        levs = []
+        for _ in range(5):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); lstep(); e1.record()
+            levs.append((e0, e1))
+        torch.cuda.synchronize()
+        lms = sum(x.elapsed_time(y) for x, y in levs) / len(levs)
+        graph_mode, tr.tc.cuda_graph = tr.tc.cuda_graph, False
+        try:
+            lagg = profile_kernels(lstep, 2, lambda: int(tr.tgn.memory.state.n_unique.item()) if tr.tgn.use_memory else 0, extra)
+        finally:
+            tr.tc.cuda_graph = graph_mode
+        ltot = sum(v["ms"] for v in lagg.values())
+        lroof = {}
+        for k, v in sorted(lagg.items(), key=lambda kv: -kv[1]["ms"]):
+            r = roofline_of(k, v, peaks, a.gemm, {})
+            if r is not None:
+                lroof[k] = {"bound": r["bound"], "achieved": r["achieved"], "peak": r["peak"], "unit": r["unit"],
+                            "frac": r["frac"], "share_of_step": v["ms"] / ltot, "ms_per_step": v["ms"] / 2}
+        large = {"global_batch": BL, "value": BL / (lms * 1e-3), "unit": "events/s", "ms_per_step": lms, "steps": 5,
+                 "rooflines": lroof,
+                 "note": "same model, stream and timing rules at BASELINE config 4's batch size (graph replay, L2 flushed)"}
+
     # ---- eval users/sec (the second half of the metric): full ranking over all stocks, users split over the ranks
     eval_users = None
     if a.eval_steps > 0 and hasattr(tr, "eval_step") and (world == 1 or a.parallelism == "replicated"):
@@ -431,10 +473,11 @@ def main():
                           "timing": "sum of per-step CUDA-event durations, max over ranks"},
                "clocks": clk, "e2e": e2e, "gpu_launches": launches, "wall_s": wall,
                "roofline": roofline, "cpu_baseline": cpu, "eval_users_per_sec": eval_users, "kernels": kernels,
-               "rooflines": rooflines}
+               "rooflines": rooflines, "large_batch": large}
         out["config"].update({"dropout": a.dropout, "gemm_mode": a.gemm,
                               "cuda_graph": bool(tc.cuda_graph and (world == 1 or a.parallelism == "replicated")),
-                              "eval": f"full ranking over all {a.items} stocks, {a.eval_bs} users per batch"})
+                              "eval": f"full ranking over all {a.items} stocks, {a.eval_bs} users per batch, metric block "
+                                      "(Recall/NDCG and delta-return/delta-Sharpe @1,3,5) on the device"})
         print(json.dumps(out))
     if world > 1:
         torch.distributed.destroy_process_group()
