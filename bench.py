@@ -31,6 +31,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ours", choices=["ours", "tgn", "jodie", "dyrep", "tgat"])
     ap.add_argument("--bs", type=int, default=8192)
+    ap.add_argument("--layers", type=int, default=1, help="attention layers (BASELINE config 3, TGAT: 2)")
+    ap.add_argument("--neighbors", type=int, default=10, help="sampled temporal neighbours (BASELINE config 3, TGAT: 20)")
     ap.add_argument("--users", type=int, default=100000)
     ap.add_argument("--items", type=int, default=1000)
     ap.add_argument("--events", type=int, default=5000000)
@@ -55,7 +57,8 @@ def parse():
 
 def workload_name(a):
     return (f"{'PfoTGNRec' if a.workload == 'ours' else a.workload} train step "
-            f"(d=64, 1 layer, 10 neighbours, 2 heads{', MV sampling K=20' if a.workload == 'ours' else ''}), "
+            f"(d=64, {a.layers} layer{'s' if a.layers > 1 else ''}, {a.neighbors} neighbours, 2 heads"
+            f"{', MV sampling K=20' if a.workload == 'ours' else ''}), "
             f"synthetic {a.users}-user x {a.items}-stock x {a.events}-event stream, bs={a.bs}")
 
 
@@ -127,7 +130,7 @@ def run_reference(a):
     from oracle.train_loop import OracleTrainer
     torch.set_num_threads(os.cpu_count())
     st = make_data(a)
-    tr = OracleTrainer(st, a.workload, bs=a.bs)
+    tr = OracleTrainer(st, a.workload, bs=a.bs, n_layers=a.layers, n_neighbors=a.neighbors)
     s0 = int(st.n_events * 0.4)
     # bounded sample: the step is the first `sample_bs` events of each batch, sized from a probe step
     t0 = time.perf_counter()
@@ -183,6 +186,19 @@ def algorithmic_work(name, args, n_uniq, extra):
     if name == "pfo_store_messages":
         B, d, F = args[4], args[5], args[6]
         return "byte", 2 * B * ((2 * 4 * d + 4 * F + 12) + (4 * (3 * d + F) + 5))
+    if name == "pfo_gather_state":                   # rows of the unique nodes: memory + pending message, read and written
+        u_max, d, raw = args[2], args[3], args[4]
+        return "byte", min(u_max, n_uniq) * (2 * 4 * (d + raw) + 4 + 4 + 1 + 12)
+    if name in ("pfo_cell_forward", "pfo_cell_backward"):
+        u_max, d, cell = args[2], args[3], args[4]
+        g = {0: 3, 1: 1}.get(cell, 0) * d
+        return "byte", min(u_max, n_uniq) * 4 * (2 * g + (4 * d if name == "pfo_cell_forward" else d + 2 * g + d))
+    if name == "pfo_time_embedding_fwd":
+        Q, d = args[2], args[4]
+        return "byte", Q * (12 + 4 + 2 * 4 * d + 4)
+    if name == "pfo_time_embedding_bwd":
+        Q, d = args[1], args[2]
+        return "byte", Q * (4 + 4 + 3 * 4 * d)
     return None, 0.0
 
 
@@ -276,7 +292,8 @@ def main():
     from pfotgnrec_b200.trainer import PfoTrainer, TrainConfig
     _lib.load()
     st = make_data(a)
-    tc = TrainConfig(model=a.workload, bs=a.bs, gemm_mode=a.gemm, dropout=a.dropout, cuda_graph=not a.no_graph)
+    tc = TrainConfig(model=a.workload, bs=a.bs, gemm_mode=a.gemm, dropout=a.dropout, cuda_graph=not a.no_graph,
+                     n_layers=a.layers, n_neighbors=a.neighbors)
     if world > 1 and a.parallelism == "sharded":
         from pfotgnrec_b200.dist import ShardedTrainer
         tr = ShardedTrainer(st, tc, dev, rank, world)
@@ -382,8 +399,7 @@ def main():
             if r is not None:
                 r["share_of_step"] = v["ms"] / tot
                 rooflines[k] = r
-        top = max(agg.items(), key=lambda kv: kv[1]["ms"])[0]
-        roofline = rooflines.get(top)
+        roofline = next(iter(rooflines.values()), None)      # the most expensive entry point with a roofline model
 
     # ---- the same step at the scale configuration's batch size: what the kernels reach once a launch carries enough
     # rows to leave the latency regime (extra information; `value` above stays the bs-8192 headline)
@@ -449,7 +465,7 @@ def main():
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         from oracle.train_loop import OracleTrainer
         torch.set_num_threads(os.cpu_count())
-        otr = OracleTrainer(st, a.workload, bs=bs)
+        otr = OracleTrainer(st, a.workload, bs=bs, n_layers=a.layers, n_neighbors=a.neighbors)
         sb = 1024
         otr.train_step(s0, s0 + sb)
         t0 = time.perf_counter()

@@ -104,7 +104,10 @@ int pfo_cell_backward(const int32_t* uniq, const int32_t* n_uniq, int64_t u_max,
 
 /* ---- persist + message store --- model/tgn.py:185-206 (update_memory for positives, clear,
  * get_raw_messages x2, store_raw_messages), model/tgn.py:357-378, modules/memory.py:35-37,
- * modules/message_aggregator.py:38-55 (`last`).  last_pos[N] is int32 scratch that must hold -1. */
+ * modules/message_aggregator.py:38-55 (`last`).  last_pos[N] is int32 scratch that must hold -1.
+ * other_emb_* (optional, [B,d]): embedding of the other endpoint in place of its memory row
+ * (use_destination_embedding_in_message, tgn.py:362-365); self_emb_* (optional): own embedding in place of the own
+ * memory row (use_source_embedding_in_message, tgn.py:360-361). */
 int pfo_persist_rank(const int32_t* src, const int32_t* dst, int B, int d, const int32_t* slot_of_node,
                      const float* Hnew, const uint8_t* pend_valid, const float* pend_ts,
                      float* memory, float* last_update, int32_t* last_pos, void* stream);
@@ -112,8 +115,20 @@ int pfo_store_messages(const int32_t* src, const int32_t* dst, const int32_t* ei
                        int B, int d, int F, const float* memory, const float* last_update,
                        const float* edge_feat, const float* tw, const float* tb,
                        const float* other_emb_for_src, const float* other_emb_for_dst,
+                       const float* self_emb_for_src, const float* self_emb_for_dst,
                        float* pend_msg, int64_t rawp, float* pend_ts, uint8_t* pend_valid,
                        int32_t* last_pos, void* stream);
+/* `mean` aggregator --- modules/message_aggregator.py:62-81: pending message = mean of the raw messages the node's
+ * interactions of this batch appended (in append order), pending time = that of the last one.  sorted_node / order
+ * [2B]: the batch's (node, position = side * B + event) pairs sorted by node with a stable sort. */
+int pfo_store_messages_mean(const int32_t* src, const int32_t* dst, const int32_t* eidx, const double* ts,
+                            int B, int d, int F, const int32_t* sorted_node, const int32_t* order,
+                            const float* memory, const float* last_update,
+                            const float* edge_feat, const float* tw, const float* tb,
+                            const float* other_emb_for_src, const float* other_emb_for_dst,
+                            const float* self_emb_for_src, const float* self_emb_for_dst,
+                            float* pend_msg, int64_t rawp, float* pend_ts, uint8_t* pend_valid,
+                            int32_t* last_pos, void* stream);
 
 /* node-sharded variants (pfotgnrec_b200/dist.py): build the message rows where the events live (from the
  * unique-node rows fetched from the owners), apply persist + last-wins where the nodes live.  key = global

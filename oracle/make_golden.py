@@ -58,7 +58,8 @@ def golden_neighbors(get_neighbor_finder):
 
 
 def _run_model(TGN, get_neighbor_finder, tag, *, d, n_layers, n_neighbors, use_memory, updater,
-               embedding, dyrep, dst_emb, ts_mode, with_ppos, B=24, n_batches=4, n_neg=3, seed=11):
+               embedding, dyrep, dst_emb, ts_mode, with_ppos, B=24, n_batches=4, n_neg=3, seed=11,
+               msg_fn="identity", aggregator="last", src_emb=False):
     from pfotgnrec_b200.synth import make_stream
     st = make_stream(n_users=40, n_items=12, n_events=B * n_batches + 40, n_days=10, seed=seed,
                      ts_mode=ts_mode, with_prices=False)
@@ -71,10 +72,10 @@ def _run_model(TGN, get_neighbor_finder, tag, *, d, n_layers, n_neighbors, use_m
               device=torch.device("cpu"), n_layers=n_layers, n_heads=2, dropout=0.0,
               use_memory=use_memory, message_dimension=100, memory_dimension=d,
               memory_update_at_start=True, embedding_module_type=embedding,
-              message_function="identity", aggregator_type="last", memory_updater_type=updater,
+              message_function=msg_fn, aggregator_type=aggregator, memory_updater_type=updater,
               n_neighbors=n_neighbors, mean_time_shift_src=shift[0], std_time_shift_src=shift[1],
               mean_time_shift_dst=shift[2], std_time_shift_dst=shift[3],
-              use_destination_embedding_in_message=dst_emb, use_source_embedding_in_message=False,
+              use_destination_embedding_in_message=dst_emb, use_source_embedding_in_message=src_emb,
               dyrep=dyrep)
     tgn.train()
     out = {"cfg_" + k: v for k, v in dict(d=d, n_layers=n_layers, n_neighbors=n_neighbors,
@@ -82,6 +83,7 @@ def _run_model(TGN, get_neighbor_finder, tag, *, d, n_layers, n_neighbors, use_m
                                           n_neg=n_neg, dyrep=int(dyrep), dst_emb=int(dst_emb),
                                           with_ppos=int(with_ppos)).items()}
     out["cfg_updater"], out["cfg_embedding"] = updater, embedding
+    out["cfg_msg_fn"], out["cfg_aggregator"], out["cfg_src_emb"] = msg_fn, aggregator, int(src_emb)
     out["cfg_shift"] = np.array(shift)
     skip = ("memory.memory", "memory.last_update", "memory_updater.memory.", "embedding_module.memory.")
     for k, v in tgn.state_dict().items():
@@ -138,7 +140,8 @@ def _run_model(TGN, get_neighbor_finder, tag, *, d, n_layers, n_neighbors, use_m
             for node, lst in tgn.memory.messages.items():
                 if len(lst) > 0:
                     pv[node] = True
-                    pm[node] = lst[-1][0].detach().numpy()
+                    pm[node] = (lst[-1][0] if aggregator == "last" else
+                                torch.mean(torch.stack([m[0] for m in lst]), dim=0)).detach().numpy()
                     pt[node] = float(lst[-1][1])
             out[f"b{bi}_pend_valid"], out[f"b{bi}_pend_msg"], out[f"b{bi}_pend_ts"] = pv, pm, pt
     np.savez_compressed(os.path.join(OUT, f"tgn_{tag}.npz"), **out)
@@ -269,6 +272,12 @@ def main():
                **{**common, "updater": "rnn", "dyrep": True, "dst_emb": True})
     _run_model(TGN, get_neighbor_finder, "tgat2", d=32, ts_mode="small", with_ppos=False,
                **{**common, "use_memory": False, "n_layers": 2, "n_neighbors": 5})
+    # API-surface variants no model of main.py builds: MLP message function + mean aggregator,
+    # and the node's own embedding in its message
+    _run_model(TGN, get_neighbor_finder, "mlp_mean", d=32, ts_mode="small", with_ppos=False, n_batches=3,
+               msg_fn="mlp", aggregator="mean", **common)
+    _run_model(TGN, get_neighbor_finder, "srcemb", d=32, ts_mode="small", with_ppos=False, n_batches=3,
+               src_emb=True, **{**common, "dst_emb": True})
     golden_mv_select(RandEdgeSampler)
     golden_eval_metrics()
 

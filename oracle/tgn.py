@@ -108,7 +108,7 @@ class TGNOracle:
     def __init__(self, params, adj, node_features, edge_features, n_layers=1, n_heads=2,
                  use_memory=True, memory_updater="gru", embedding="graph_attention",
                  dyrep=False, use_destination_embedding_in_message=False,
-                 use_source_embedding_in_message=False,
+                 use_source_embedding_in_message=False, message_function="identity", aggregator="last",
                  mean_time_shift_src=0.0, std_time_shift_src=1.0,
                  mean_time_shift_dst=0.0, std_time_shift_dst=1.0, edge_features_normalized=False):
         self.p = params
@@ -123,6 +123,7 @@ class TGNOracle:
         self.dyrep = dyrep
         self.dst_emb_in_msg = use_destination_embedding_in_message
         self.src_emb_in_msg = use_source_embedding_in_message
+        self.message_function, self.aggregator = message_function, aggregator
         self.shift = (mean_time_shift_src, std_time_shift_src, mean_time_shift_dst, std_time_shift_dst)
         self.raw_dim = 2 * self.d + self.F + self.d
         self.call_id = 0
@@ -153,7 +154,12 @@ class TGNOracle:
         mem = self.memory.clone()
         lu = self.last_update.clone()
         if ids.numel() > 0:
-            mem[ids] = self._cell(self.pend_msg[ids], self.memory[ids])
+            x = self.pend_msg[ids]
+            if self.message_function == "mlp":                    # modules/message_function.py:13-26 (tgn.py:348)
+                pre = "message_function.mlp."
+                x = F.linear(torch.relu(F.linear(x, self.p[pre + "0.weight"], self.p[pre + "0.bias"])),
+                             self.p[pre + "2.weight"], self.p[pre + "2.bias"])
+            mem[ids] = self._cell(x, self.memory[ids])
             lu[ids] = self.pend_ts[ids]
         return mem, lu
 
@@ -255,6 +261,13 @@ class TGNOracle:
         delta = t32 - self.last_update[a_t]
         msg = torch.cat([m_a, m_b, self.edge_feat[eidx_t], self._te(delta.unsqueeze(1)).view(len(a), -1)],
                         dim=1).detach()
+        if self.aggregator == "mean":                             # message_aggregator.py:62-81: a node's list holds
+            for node in np.unique(a):                             # exactly its messages of this batch (cleared at
+                rows = np.nonzero(a == node)[0]                   # tgn.py:191 before they are appended)
+                self.pend_msg[node] = torch.mean(torch.stack([msg[i] for i in rows]), dim=0)
+                self.pend_ts[node] = t32[rows[-1]]
+                self.pend_valid[node] = True
+            return
         for i in range(len(a)):                                   # later occurrences win
             self.pend_msg[a[i]] = msg[i]
             self.pend_ts[a[i]] = t32[i]

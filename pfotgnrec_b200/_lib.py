@@ -35,7 +35,9 @@ _SIGS = {
     "pfo_cell_forward": (c_int, [P, P, c_int64, c_int, c_int, P, P, c_int64, P, P, P, P, P, P]),
     "pfo_cell_backward": (c_int, [P, P, c_int64, c_int, c_int, P, P, c_int64, P, P, P, P, P, P]),
     "pfo_persist_rank": (c_int, [P, P, c_int, c_int, P, P, P, P, P, P, P, P]),
-    "pfo_store_messages": (c_int, [P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_int64, P, P, P, P]),
+    "pfo_store_messages": (c_int, [P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, c_int64, P, P, P, P]),
+    "pfo_store_messages_mean": (c_int, [P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, P, c_int64,
+                                        P, P, P, P]),
     "pfo_build_messages": (c_int, [P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_int64, P, P]),
     "pfo_apply_messages": (c_int, [P, P, c_int64, c_int, c_int, P, P, P, c_int64, P, P, P, P, c_int64, P, P, P, P]),
     "pfo_time_embedding_fwd": (c_int, [P, P, c_int64, c_int64, c_int, P, P, P, c_float, c_float, c_float,

@@ -157,6 +157,7 @@ store_messages_kernel(const int32_t* __restrict__ src, const int32_t* __restrict
                       const float* __restrict__ memory, const float* __restrict__ last_update,
                       const float* __restrict__ edge_feat, const float* __restrict__ tw, const float* __restrict__ tb,
                       const float* __restrict__ other_emb_for_src, const float* __restrict__ other_emb_for_dst,
+                      const float* __restrict__ self_emb_for_src, const float* __restrict__ self_emb_for_dst,
                       float* __restrict__ pend_msg, int64_t rawp, float* __restrict__ pend_ts,
                       uint8_t* __restrict__ pend_valid, int32_t* __restrict__ last_pos) {
     const int lane = threadIdx.x & 31;
@@ -172,7 +173,8 @@ store_messages_kernel(const int32_t* __restrict__ src, const int32_t* __restrict
         const float t32 = (float)ts[i];
         const float delta = t32 - last_update[node];
         float* out = pend_msg + (int64_t)node * rawp;
-        const float* ms = memory + (int64_t)node * d;
+        const float* se = is_src ? self_emb_for_src : self_emb_for_dst;     // use_source_embedding_in_message (tgn.py:360-361)
+        const float* ms = se ? se + (int64_t)i * d : memory + (int64_t)node * d;
         const float* oe = is_src ? other_emb_for_src : other_emb_for_dst;   // dyrep: embedding of the other endpoint
         const float* mo = oe ? oe + (int64_t)i * d : memory + (int64_t)other * d;
         const float* ef = edge_feat + (int64_t)eidx[i] * F;
@@ -381,6 +383,81 @@ apply_store_kernel(const int32_t* __restrict__ node, const int32_t* __restrict__
     }
 }
 
+// `mean` aggregator (reference modules/message_aggregator.py:62-81): the pending message of a node is the MEAN of the
+// raw messages its interactions of this batch appended, the pending time that of the last one.  A node's list only
+// ever holds the messages of the most recent batch it was a positive of (cleared at tgn.py:191, refilled at :205-206),
+// so the dense slot is exact here too.  `sorted_node` / `order` are the (node, position) pairs of the batch sorted by
+// node with a STABLE sort (position = side * B + event, ascending inside a node = append order): the warp at the
+// head of a node's run walks it in order and sums sequentially -- deterministic, no float atomics.
+__global__ void __launch_bounds__(256)
+store_messages_mean_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                           const int32_t* __restrict__ eidx, const double* __restrict__ ts, int B, int d, int F,
+                           const int32_t* __restrict__ sorted_node, const int32_t* __restrict__ order,
+                           const float* __restrict__ memory, const float* __restrict__ last_update,
+                           const float* __restrict__ edge_feat, const float* __restrict__ tw, const float* __restrict__ tb,
+                           const float* __restrict__ other_emb_for_src, const float* __restrict__ other_emb_for_dst,
+                           const float* __restrict__ self_emb_for_src, const float* __restrict__ self_emb_for_dst,
+                           float* __restrict__ pend_msg, int64_t rawp, float* __restrict__ pend_ts,
+                           uint8_t* __restrict__ pend_valid, int32_t* __restrict__ last_pos) {
+    constexpr int MAXC = 4;                                    // d <= 128: columns per lane and segment
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n2 = 2 * (int64_t)B;
+    for (int64_t k = warp; k < n2; k += nwarps) {
+        const int node = sorted_node[k];
+        if (k > 0 && sorted_node[k - 1] == node) continue;     // not the head of its run
+        float a_self[MAXC], a_other[MAXC], a_te[MAXC], a_e = 0.0f;
+#pragma unroll
+        for (int j = 0; j < MAXC; ++j) a_self[j] = a_other[j] = a_te[j] = 0.0f;
+        const float lu = last_update[node];
+        int count = 0;
+        float t_last = 0.0f;
+        for (int64_t kk = k; kk < n2 && sorted_node[kk] == node; ++kk) {
+            const int pos = order[kk];
+            const int i = pos % B;
+            const bool is_src = pos < B;
+            const int other = is_src ? dst[i] : src[i];
+            const float t32 = (float)ts[i];
+            const float delta = t32 - lu;
+            const float* se = is_src ? self_emb_for_src : self_emb_for_dst;
+            const float* ms = se ? se + (int64_t)i * d : memory + (int64_t)node * d;
+            const float* oe = is_src ? other_emb_for_src : other_emb_for_dst;
+            const float* mo = oe ? oe + (int64_t)i * d : memory + (int64_t)other * d;
+#pragma unroll
+            for (int j = 0; j < MAXC; ++j) {
+                const int c = lane + 32 * j;
+                if (c < d) {
+                    a_self[j] += ms[c];
+                    a_other[j] += mo[c];
+                    a_te[j] += pfo_cosf(fmaf(delta, tw[c], tb[c]));
+                }
+            }
+            if (lane < F) a_e += edge_feat[(int64_t)eidx[i] * F + lane];
+            t_last = t32;
+            ++count;
+        }
+        const float n = (float)count;
+        float* out = pend_msg + (int64_t)node * rawp;
+#pragma unroll
+        for (int j = 0; j < MAXC; ++j) {
+            const int c = lane + 32 * j;
+            if (c < d) {
+                out[c] = a_self[j] / n;
+                out[d + c] = a_other[j] / n;
+                out[2 * d + F + c] = a_te[j] / n;
+            }
+        }
+        if (lane < F) out[2 * d + lane] = a_e / n;
+        if (lane == 0) {
+            pend_ts[node] = t_last;
+            pend_valid[node] = 1;
+            last_pos[node] = -1;
+        }
+    }
+}
+
+
 }  // namespace
 
 PFO_API int pfo_cell_forward(const int32_t* uniq, const int32_t* n_uniq, int64_t u_max, int d, int cell,
@@ -425,12 +502,29 @@ PFO_API int pfo_store_messages(const int32_t* src, const int32_t* dst, const int
                                int B, int d, int F, const float* memory, const float* last_update,
                                const float* edge_feat, const float* tw, const float* tb,
                                const float* other_emb_for_src, const float* other_emb_for_dst,
+                               const float* self_emb_for_src, const float* self_emb_for_dst,
                                float* pend_msg, int64_t rawp, float* pend_ts, uint8_t* pend_valid,
                                int32_t* last_pos, void* stream) {
     if (B <= 0) return 0;
     store_messages_kernel<<<pfo_grid(2 * (int64_t)B * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(
         src, dst, eidx, ts, B, d, F, memory, last_update, edge_feat, tw, tb, other_emb_for_src,
-        other_emb_for_dst, pend_msg, rawp, pend_ts, pend_valid, last_pos);
+        other_emb_for_dst, self_emb_for_src, self_emb_for_dst, pend_msg, rawp, pend_ts, pend_valid, last_pos);
+    PFO_LAUNCH_CHECK();
+}
+
+PFO_API int pfo_store_messages_mean(const int32_t* src, const int32_t* dst, const int32_t* eidx, const double* ts,
+                                    int B, int d, int F, const int32_t* sorted_node, const int32_t* order,
+                                    const float* memory, const float* last_update,
+                                    const float* edge_feat, const float* tw, const float* tb,
+                                    const float* other_emb_for_src, const float* other_emb_for_dst,
+                                    const float* self_emb_for_src, const float* self_emb_for_dst,
+                                    float* pend_msg, int64_t rawp, float* pend_ts, uint8_t* pend_valid,
+                                    int32_t* last_pos, void* stream) {
+    if (B <= 0) return 0;
+    if (d > 128 || F > 32) return (int)cudaErrorInvalidValue;
+    store_messages_mean_kernel<<<pfo_grid(2 * (int64_t)B * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        src, dst, eidx, ts, B, d, F, sorted_node, order, memory, last_update, edge_feat, tw, tb, other_emb_for_src,
+        other_emb_for_dst, self_emb_for_src, self_emb_for_dst, pend_msg, rawp, pend_ts, pend_valid, last_pos);
     PFO_LAUNCH_CHECK();
 }
 

@@ -33,6 +33,10 @@ class ModelConfig:
     embedding: str = "graph_attention"   # "graph_attention" | "time" | "identity"
     dyrep: bool = False
     dst_emb_in_msg: bool = False
+    src_emb_in_msg: bool = False
+    message_fn: str = "identity"         # "identity" | "mlp" (reference modules/message_function.py:13-33)
+    msg_dim: int = 100                   # output width of the MLP message function
+    aggregator: str = "last"             # "last" | "mean" (reference modules/message_aggregator.py:38-81)
     shift: tuple = (0.0, 1.0, 0.0, 1.0)  # mean/std time shift src, dst
     dropout: float = 0.0
     gemm_mode: str = "fp32"     # "fp32" (3xTF32 tcgen05, 1e-5) | "tf32" (tcgen05, 2e-2) | "bf16" | "simt" (FFMA)
@@ -60,6 +64,14 @@ class ModelConfig:
     @property
     def rawp(self):
         return (self.raw + 3) // 4 * 4
+
+    @property
+    def cell_in(self):          # input width of the memory updater
+        return self.raw if self.message_fn == "identity" else self.msg_dim
+
+    @property
+    def mlp_hidden(self):       # nn.Linear(raw, raw // 2) of the MLP message function
+        return self.raw // 2
 
     @property
     def cell(self):
@@ -218,6 +230,9 @@ class TGNEngine:
         if c.use_memory:
             pre = "memory_updater.memory_updater."
             names += [pre + "weight_ih", pre + "weight_hh", pre + "bias_ih", pre + "bias_hh"]
+            if c.message_fn == "mlp":
+                names += ["message_function.mlp.0.weight", "message_function.mlp.0.bias",
+                          "message_function.mlp.2.weight", "message_function.mlp.2.bias"]
         if c.embedding == "graph_attention":
             for l in range(c.n_layers):
                 a = f"embedding_module.attention_models.{l}."
@@ -243,6 +258,8 @@ class TGNEngine:
             pre = "memory_updater.memory_updater."
             flat += [params[pre + "weight_ih"].contiguous(), params[pre + "weight_hh"].contiguous(),
                      params[pre + "bias_ih"].contiguous(), params[pre + "bias_hh"].contiguous()]
+            if c.message_fn == "mlp":
+                flat += [params["message_function.mlp.%s" % k].contiguous() for k in ("0.weight", "0.bias", "2.weight", "2.bias")]
         if c.embedding == "graph_attention":
             flat += self._layer_params(params)
         elif c.embedding == "time":
@@ -327,7 +344,7 @@ class TGNEngine:
         batch = dict(src=src, dst=dst, ts=ts, eidx=eidx, q_nodes=q_nodes, q_ts=q_ts, n=int(n_neighbors),
                      B=B, train=bool(train), update_state=bool(update_state))
         if state_batch is not None:
-            if self.cfg.dst_emb_in_msg:
+            if self.cfg.dst_emb_in_msg or self.cfg.src_emb_in_msg:
                 raise NotImplementedError("messages that carry embeddings (dyrep) need the embedded batch as state batch")
             batch["state"] = dict(src=state_batch["src"], dst=state_batch["dst"], ts=state_batch["ts"],
                                   eidx=state_batch["eidx"], B=int(state_batch["src"].shape[0]))
@@ -369,9 +386,10 @@ class TGNEngine:
 
     # ------------------------------------------------------------------ overridable stages
     # (pfotgnrec_b200/dist.py replaces these three with their node-sharded, all-to-all versions)
-    def node_table(self, id_lists, cellW):
+    def node_table(self, id_lists, cellW, mlpW=None):
         """Unique touched nodes of the batch and their feature rows: Hnew = lazily updated memory
-        (GRU/RNN applied to the pending message), H0 = Hnew + node features, lu_u = last_update'."""
+        (GRU/RNN applied to the pending message, through the MLP message function when configured:
+        tgn.py:342-354 aggregate -> compute_message -> updater), H0 = Hnew + node features, lu_u = last_update'."""
         c, st, dev = self.cfg, self.state, self.device
         d = c.d
         uniq, u_max = self._unique_nodes(id_lists)
@@ -379,7 +397,7 @@ class TGNEngine:
         self.slot_map = st.slot_of_node
         G = c.gates * d
         H0 = torch.empty(u_max, d, device=dev)
-        Hnew = HG = XG = valid_u = lu_u = GI = GH = None
+        Hnew = HG = XG = valid_u = lu_u = GI = GH = M1 = X2 = None
         if c.use_memory:
             HG = torch.empty(u_max, d, device=dev)
             XG = torch.empty(u_max, c.rawp, device=dev)
@@ -389,18 +407,30 @@ class TGNEngine:
                       c.rawp, ptr(st.pend_valid), ptr(st.pend_ts), ptr(st.last_update),
                       ptr(HG), ptr(XG), ptr(valid_u), ptr(lu_u))
             W_ih, W_hh, b_ih, b_hh = cellW
+            X, ldx, kx = XG, c.rawp, c.raw
+            if c.message_fn == "mlp":          # Linear(raw, raw // 2) -> ReLU -> Linear(raw // 2, msg_dim)
+                W1, b1, W2, b2 = mlpW
+                hid, md = c.mlp_hidden, c.msg_dim
+                ld1, ld2 = (hid + 3) // 4 * 4, (md + 3) // 4 * 4
+                M1 = torch.empty(u_max, ld1, device=dev)
+                X2 = torch.empty(u_max, ld2, device=dev)
+                _linear(c, ptr(XG), c.rawp, None, ptr(W1), c.raw, 0, ptr(b1), ptr(M1), ld1, u_max, hid, c.raw,
+                        m_dev=ptr(n_uniq), act=1)
+                _linear(c, ptr(M1), ld1, None, ptr(W2), hid, 0, ptr(b2), ptr(X2), ld2, u_max, md, hid, m_dev=ptr(n_uniq))
+                X, ldx, kx = X2, ld2, md
             GI = torch.empty(u_max, G, device=dev)
             GH = torch.empty(u_max, G, device=dev)
-            _linear(c, ptr(XG), c.rawp, None, ptr(W_ih), c.raw, 0, ptr(b_ih), ptr(GI), G, u_max, G, c.raw, m_dev=ptr(n_uniq))
+            _linear(c, ptr(X), ldx, None, ptr(W_ih), kx, 0, ptr(b_ih), ptr(GI), G, u_max, G, kx, m_dev=ptr(n_uniq))
             _linear(c, ptr(HG), d, None, ptr(W_hh), d, 0, ptr(b_hh), ptr(GH), G, u_max, G, d, m_dev=ptr(n_uniq))
             Hnew = torch.empty(u_max, d, device=dev)
         _lib.call("pfo_cell_forward", ptr(uniq), ptr(n_uniq), u_max, d, c.cell, ptr(GI), ptr(GH), G, ptr(HG),
                   ptr(valid_u), ptr(self.node_feat), ptr(Hnew), ptr(H0))
         return dict(uniq=uniq, u_max=u_max, n_uniq=n_uniq, H0=H0, Hnew=Hnew, lu_u=lu_u, HG=HG, XG=XG,
-                    valid_u=valid_u, GI=GI, GH=GH)
+                    valid_u=valid_u, GI=GI, GH=GH, M1=M1, X2=X2)
 
-    def node_table_backward(self, tab, dH0, g_cell):
-        """dH0 (= dHnew) -> gradients of the cell weights (memory and messages are detached inputs)."""
+    def node_table_backward(self, tab, dH0, g_cell, mlpW=None, g_mlp=None, cellW=None):
+        """dH0 (= dHnew) -> gradients of the cell weights and, through the cell input, of the MLP message function
+        (memory and stored raw messages are detached inputs)."""
         c, dev = self.cfg, self.device
         d, u_max, n_uniq = c.d, tab["u_max"], tab["n_uniq"]
         G = c.gates * d
@@ -409,8 +439,24 @@ class TGNEngine:
         _lib.call("pfo_cell_backward", ptr(tab["uniq"]), ptr(n_uniq), u_max, d, c.cell, ptr(tab["GI"]), ptr(tab["GH"]),
                   G, ptr(tab["HG"]), ptr(tab["valid_u"]), ptr(dH0), ptr(dGI), ptr(dGH))
         gW_ih, gW_hh, gb_ih, gb_hh = g_cell
-        _wgrad(c, self.ws, ptr(dGI), G, ptr(tab["XG"]), c.rawp, None, u_max, G, c.raw, ptr(gW_ih), c.raw, ptr(gb_ih),
-               m_dev=ptr(n_uniq))
+        if c.message_fn == "mlp":
+            W1, b1, W2, b2 = mlpW
+            gW1, gb1, gW2, gb2 = g_mlp
+            hid, md = c.mlp_hidden, c.msg_dim
+            M1, X2 = tab["M1"], tab["X2"]
+            ld1, ld2 = M1.shape[1], X2.shape[1]
+            _wgrad(c, self.ws, ptr(dGI), G, ptr(X2), ld2, None, u_max, G, md, ptr(gW_ih), md, ptr(gb_ih), m_dev=ptr(n_uniq))
+            dX2 = torch.empty(u_max, ld2, device=dev)
+            _linear(c, ptr(dGI), G, None, ptr(cellW[0]), md, 1, None, ptr(dX2), ld2, u_max, md, G, m_dev=ptr(n_uniq))
+            _wgrad(c, self.ws, ptr(dX2), ld2, ptr(M1), ld1, None, u_max, md, hid, ptr(gW2), hid, ptr(gb2), m_dev=ptr(n_uniq))
+            dM1 = torch.empty(u_max, ld1, device=dev)
+            _linear(c, ptr(dX2), ld2, None, ptr(W2), hid, 1, None, ptr(dM1), ld1, u_max, hid, md, m_dev=ptr(n_uniq),
+                    relu_gate=ptr(M1), ld_gate=ld1)
+            _wgrad(c, self.ws, ptr(dM1), ld1, ptr(tab["XG"]), c.rawp, None, u_max, hid, c.raw, ptr(gW1), c.raw, ptr(gb1),
+                   m_dev=ptr(n_uniq))
+        else:
+            _wgrad(c, self.ws, ptr(dGI), G, ptr(tab["XG"]), c.rawp, None, u_max, G, c.raw, ptr(gW_ih), c.raw, ptr(gb_ih),
+                   m_dev=ptr(n_uniq))
         _wgrad(c, self.ws, ptr(dGH), G, ptr(tab["HG"]), d, None, u_max, G, d, ptr(gW_hh), d, ptr(gb_hh),
                m_dev=ptr(n_uniq))
 
@@ -422,13 +468,23 @@ class TGNEngine:
         src, dst = batch["src"], batch["dst"]
         _lib.call("pfo_persist_rank", ptr(src), ptr(dst), B, d, ptr(st.slot_of_node), ptr(tab["Hnew"]),
                   ptr(st.pend_valid), ptr(st.pend_ts), ptr(st.memory), ptr(st.last_update), ptr(st.last_pos))
-        o_src = o_dst = None
-        if c.dst_emb_in_msg:    # dyrep: the other endpoint's embedding rides in the message (tgn.py:364-365)
+        o_src = o_dst = s_src = s_dst = None
+        if c.dst_emb_in_msg:    # dyrep: the other endpoint's embedding rides in the message (tgn.py:362-365)
             o_src, o_dst = emb[B:2 * B], emb[:B]
-        _lib.call("pfo_store_messages", ptr(src), ptr(dst), ptr(batch["eidx"]), ptr(batch["ts"]), B, d, F,
-                  ptr(st.memory), ptr(st.last_update), ptr(self.edge_feat), ptr(tw), ptr(tb),
-                  ptr(o_src), ptr(o_dst), ptr(st.pend_msg), c.rawp, ptr(st.pend_ts), ptr(st.pend_valid),
-                  ptr(st.last_pos))
+        if c.src_emb_in_msg:    # the node's own embedding in place of its memory row (tgn.py:360-361)
+            s_src, s_dst = emb[:B], emb[B:2 * B]
+        common = (ptr(st.memory), ptr(st.last_update), ptr(self.edge_feat), ptr(tw), ptr(tb),
+                  ptr(o_src), ptr(o_dst), ptr(s_src), ptr(s_dst), ptr(st.pend_msg), c.rawp, ptr(st.pend_ts),
+                  ptr(st.pend_valid), ptr(st.last_pos))
+        if c.aggregator == "mean":
+            # (node, position) pairs of the batch grouped by node, positions ascending inside a node (append order)
+            nodes2 = torch.cat([src, dst])
+            sorted_node, order = torch.sort(nodes2, stable=True)
+            order = order.to(torch.int32)
+            _lib.call("pfo_store_messages_mean", ptr(src), ptr(dst), ptr(batch["eidx"]), ptr(batch["ts"]), B, d, F,
+                      ptr(sorted_node), ptr(order), *common)
+        else:
+            _lib.call("pfo_store_messages", ptr(src), ptr(dst), ptr(batch["eidx"]), ptr(batch["ts"]), B, d, F, *common)
 
     def _slots(self, ids):
         out = torch.empty(ids.shape, dtype=torch.int32, device=self.device)
@@ -522,6 +578,7 @@ class TGNStepFunction(torch.autograd.Function):
         it = iter(flat)
         tw, tb = next(it), next(it)
         cellW = [next(it) for _ in range(4)] if c.use_memory else None
+        mlpW = [next(it) for _ in range(4)] if c.use_memory and c.message_fn == "mlp" else None
         layerW, embW, rawW, fold_ws = [], None, None, None
         if c.embedding == "graph_attention":
             rawW = [[next(it) for _ in range(10)] for _ in range(c.n_layers)]
@@ -547,7 +604,7 @@ class TGNStepFunction(torch.autograd.Function):
             id_lists = id_lists + [sb["src"], sb["dst"]]    # their updated memory rows must be in the node table
 
         # 2. lazy memory update on the unique nodes (memory_updater.py:35-53, restricted)
-        tab = eng.node_table(id_lists, cellW)
+        tab = eng.node_table(id_lists, cellW, mlpW) if mlpW is not None else eng.node_table(id_lists, cellW)
         uniq, u_max, n_uniq = tab["uniq"], tab["u_max"], tab["n_uniq"]
         H0, Hnew, lu_u = tab["H0"], tab["Hnew"], tab["lu_u"]
 
@@ -579,7 +636,7 @@ class TGNStepFunction(torch.autograd.Function):
             _lib.call("pfo_gather_rows", ptr(Hnew), d, ptr(qslots), Q, d, ptr(out), d)
         if need_grad:
             ctx.eng, ctx.save = eng, save
-            ctx.pack = dict(flat=flat, cellW=cellW, layerW=layerW, rawW=rawW, fold_ws=fold_ws, embW=embW, tape=tape,
+            ctx.pack = dict(flat=flat, cellW=cellW, mlpW=mlpW, layerW=layerW, rawW=rawW, fold_ws=fold_ws, embW=embW, tape=tape,
                             tab=tab, u_max=u_max,
                             Hnew=Hnew, qslots=qslots, td=td, Q=Q)
         return out
@@ -597,6 +654,7 @@ class TGNStepFunction(torch.autograd.Function):
         it = iter(grads)
         g_tw, g_tb = next(it), next(it)
         g_cell = [next(it) for _ in range(4)] if c.use_memory else None
+        g_mlp = [next(it) for _ in range(4)] if c.use_memory and c.message_fn == "mlp" else None
         g_layers, g_raw, g_emb = [], [], None
         if c.embedding == "graph_attention":
             g_raw = [[next(it) for _ in range(10)] for _ in range(c.n_layers)]
@@ -644,7 +702,9 @@ class TGNStepFunction(torch.autograd.Function):
             eng.unfold_layer_grads(pk["rawW"], flat[1], pk["fold_ws"], g_layers, g_raw, [g[5] for g in g_layers])
             g_tw.add_(save["g_twtb"][:d])
             g_tb.add_(save["g_twtb"][d:])
-        if c.use_memory:
+        if c.use_memory and g_mlp is not None:
+            eng.node_table_backward(pk["tab"], dH0, g_cell, pk["mlpW"], g_mlp, pk["cellW"])
+        elif c.use_memory:
             eng.node_table_backward(pk["tab"], dH0, g_cell)
         if attention_grad:
             eng.join_side()

@@ -58,11 +58,10 @@ class TGN(torch.nn.Module):
         super(TGN, self).__init__()
         if use_memory and not memory_update_at_start:
             raise NotImplementedError("memory_update_at_start=False is never executed by main.py")
-        if use_memory and (aggregator_type != "last" or message_function != "identity"):
-            raise NotImplementedError("only the 'last' aggregator with the identity message function is on the "
-                                      "PfoTGNRec path (DESIGN.md, 'next' rows)")
-        if use_source_embedding_in_message:
-            raise NotImplementedError("use_source_embedding_in_message is always False in main.py")
+        if aggregator_type not in ("last", "mean"):
+            raise ValueError("Message aggregator {} not implemented".format(aggregator_type))
+        if message_function not in ("identity", "mlp"):
+            raise ValueError("Message function {} not implemented".format(message_function))
         if embedding_module_type == "graph_sum":
             raise NotImplementedError("graph_sum embedding is not used by main.py (DESIGN.md, 'next' rows)")
 
@@ -132,6 +131,9 @@ class TGN(torch.nn.Module):
                                 n_heads=n_heads, use_memory=use_memory, updater=memory_updater_type,
                                 embedding=embedding_module_type, dyrep=dyrep,
                                 dst_emb_in_msg=use_destination_embedding_in_message,
+                                src_emb_in_msg=use_source_embedding_in_message,
+                                message_fn=message_function if use_memory else "identity",
+                                msg_dim=int(message_dimension), aggregator=aggregator_type,
                                 shift=(float(mean_time_shift_src), float(std_time_shift_src),
                                        float(mean_time_shift_dst), float(std_time_shift_dst)),
                                 dropout=float(dropout), gemm_mode=gemm_mode)

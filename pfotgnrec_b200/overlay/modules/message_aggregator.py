@@ -1,5 +1,6 @@
 """Drop-in for reference modules/message_aggregator.py.  The `last` aggregator is the last-wins
-scatter of pfo_store_messages (dense pending table); the classes remain as the API surface."""
+scatter of pfo_store_messages, `mean` the in-order segment mean of pfo_store_messages_mean (dense pending
+table either way); the classes remain as the API surface over the dict-of-lists compat view."""
 import torch
 
 
@@ -26,7 +27,14 @@ class LastMessageAggregator(MessageAggregator):
 
 class MeanMessageAggregator(MessageAggregator):
     def aggregate(self, node_ids, messages):
-        raise NotImplementedError("mean aggregation is not on the PfoTGNRec path (main.py uses 'last')")
+        """Dict-of-lists view (compat): the dense table already holds the mean of every node's list."""
+        ids, msgs, tss = [], [], []
+        for node_id in sorted(set(int(x) for x in node_ids)):
+            if len(messages[node_id]) > 0:
+                ids.append(node_id)
+                msgs.append(torch.mean(torch.stack([m[0] for m in messages[node_id]]), dim=0))
+                tss.append(messages[node_id][-1][1])
+        return ids, (torch.stack(msgs) if ids else []), (torch.stack(tss) if ids else [])
 
 
 def get_message_aggregator(aggregator_type, device):

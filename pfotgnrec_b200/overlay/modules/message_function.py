@@ -1,4 +1,6 @@
-"""Drop-in for reference modules/message_function.py (identity is the only one main.py uses)."""
+"""Drop-in for reference modules/message_function.py: parameter containers with the reference's names and init
+order; the MLP (Linear -> ReLU -> Linear on the aggregated raw message, model/tgn.py:342-354) runs inside the lazy
+memory update of the step engine (pfo_linear_* / pfo_wgrad_*)."""
 from torch import nn
 
 
@@ -15,7 +17,7 @@ class MLPMessageFunction(MessageFunction):
             nn.Linear(raw_message_dimension // 2, message_dimension))
 
     def compute_message(self, raw_messages):
-        raise NotImplementedError("the MLP message function is not on the PfoTGNRec path")
+        raise NotImplementedError("the message MLP is evaluated inside TGN.compute_temporal_embeddings*")
 
 
 class IdentityMessageFunction(MessageFunction):

@@ -29,6 +29,9 @@ def oracle_from_golden(z, requires_grad=True):
                   n_heads=2, use_memory=bool(z["cfg_use_memory"]),
                   memory_updater=str(z["cfg_updater"]), embedding=str(z["cfg_embedding"]),
                   dyrep=bool(z["cfg_dyrep"]), use_destination_embedding_in_message=bool(z["cfg_dst_emb"]),
+                  use_source_embedding_in_message=bool(z["cfg_src_emb"]) if "cfg_src_emb" in z else False,
+                  message_function=str(z["cfg_msg_fn"]) if "cfg_msg_fn" in z else "identity",
+                  aggregator=str(z["cfg_aggregator"]) if "cfg_aggregator" in z else "last",
                   mean_time_shift_src=sh[0], std_time_shift_src=sh[1],
                   mean_time_shift_dst=sh[2], std_time_shift_dst=sh[3])
     return o, p

@@ -37,12 +37,14 @@ def build_tgn(tgn_mod, utils_mod, z, gemm_mode="fp32"):
                       device=torch.device("cuda"), n_layers=int(z["cfg_n_layers"]), n_heads=2, dropout=0.0,
                       use_memory=bool(z["cfg_use_memory"]), message_dimension=100, memory_dimension=int(z["cfg_d"]),
                       memory_update_at_start=True, embedding_module_type=str(z["cfg_embedding"]),
-                      message_function="identity", aggregator_type="last",
+                      message_function=str(z["cfg_msg_fn"]) if "cfg_msg_fn" in z else "identity",
+                       aggregator_type=str(z["cfg_aggregator"]) if "cfg_aggregator" in z else "last",
                       memory_updater_type=str(z["cfg_updater"]), n_neighbors=int(z["cfg_n_neighbors"]),
                       mean_time_shift_src=z["cfg_shift"][0], std_time_shift_src=z["cfg_shift"][1],
                       mean_time_shift_dst=z["cfg_shift"][2], std_time_shift_dst=z["cfg_shift"][3],
                       use_destination_embedding_in_message=bool(z["cfg_dst_emb"]),
-                      use_source_embedding_in_message=False, dyrep=bool(z["cfg_dyrep"]), gemm_mode=gemm_mode)
+                      use_source_embedding_in_message=bool(z["cfg_src_emb"]) if "cfg_src_emb" in z else False,
+                       dyrep=bool(z["cfg_dyrep"]), gemm_mode=gemm_mode)
     tgn = tgn.to(torch.device("cuda"))
     sd = tgn.state_dict()
     for k in z:
@@ -51,7 +53,7 @@ def build_tgn(tgn_mod, utils_mod, z, gemm_mode="fp32"):
     return tgn
 
 
-@pytest.mark.parametrize("tag", ["ours", "ours_nbg", "tgn", "jodie", "dyrep", "tgat2"])
+@pytest.mark.parametrize("tag", ["ours", "ours_nbg", "tgn", "jodie", "dyrep", "tgat2", "mlp_mean", "srcemb"])
 @pytest.mark.parametrize("mode", ["fp32", "simt"])
 def test_drop_in_tgn_matches_reference_golden(overlay, tag, mode):
     """1e-5 contract in both exact GEMM modes: "fp32" = 3xTF32 on the tcgen05 tensor cores (default),

@@ -32,15 +32,17 @@ def _build(tgn_mod, z, device="cpu"):
                        device=torch.device(device), n_layers=int(z["cfg_n_layers"]), n_heads=2, dropout=0.0,
                        use_memory=bool(z["cfg_use_memory"]), message_dimension=100, memory_dimension=int(z["cfg_d"]),
                        memory_update_at_start=True, embedding_module_type=str(z["cfg_embedding"]),
-                       message_function="identity", aggregator_type="last",
+                       message_function=str(z["cfg_msg_fn"]) if "cfg_msg_fn" in z else "identity",
+                       aggregator_type=str(z["cfg_aggregator"]) if "cfg_aggregator" in z else "last",
                        memory_updater_type=str(z["cfg_updater"]), n_neighbors=int(z["cfg_n_neighbors"]),
                        mean_time_shift_src=z["cfg_shift"][0], std_time_shift_src=z["cfg_shift"][1],
                        mean_time_shift_dst=z["cfg_shift"][2], std_time_shift_dst=z["cfg_shift"][3],
                        use_destination_embedding_in_message=bool(z["cfg_dst_emb"]),
-                       use_source_embedding_in_message=False, dyrep=bool(z["cfg_dyrep"]))
+                       use_source_embedding_in_message=bool(z["cfg_src_emb"]) if "cfg_src_emb" in z else False,
+                       dyrep=bool(z["cfg_dyrep"]))
 
 
-@pytest.mark.parametrize("tag", ["ours", "jodie", "dyrep", "tgat2"])
+@pytest.mark.parametrize("tag", ["ours", "jodie", "dyrep", "tgat2", "mlp_mean", "srcemb"])
 def test_initial_weights_and_keys_match_reference(overlay, tag):
     tgn_mod, _ = overlay
     z = load_golden(f"tgn_{tag}.npz")
