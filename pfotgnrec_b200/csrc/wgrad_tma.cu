@@ -105,11 +105,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         : "r"(taddr));
 }
 
+// one lane of a converged warp (see linear_tma.cu: the issue loops are walked by the whole warp so that their state
+// stays in uniform registers; only the TMA / MMA instruction is predicated)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 template <int PASSES>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmA, const WgTmaArgs p) {
     extern __shared__ uint8_t smem_raw[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler (role dispatch)
     const int stages = p.stages, nkb = p.nkb, b_boxes = p.b_boxes;
     const int n0 = blockIdx.y * TN;
     const int boxes = G_BOXES + b_boxes;                       // per stage: [G x4][A x nkb][ones]
@@ -170,26 +179,32 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0 && n_iters > 0) {
-            asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&tmG)) : "memory");
-            asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        if (n_iters > 0) {
+            if (lane == 0) {
+                asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&tmG)) : "memory");
+                asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+            }
+            __syncwarp();
             int stage = 0; uint32_t phase = 0;
             for (int it = 0; it < n_iters; ++it) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
-                mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(G_BOXES + nkb) * BOX_BYTES);
-                const int row = (int)(r_begin + (int64_t)it * R);
-                const uint32_t dst = smem_u32(sHi + (size_t)stage * stage_bytes);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(G_BOXES + nkb) * BOX_BYTES);
+                    const int row = (int)(r_begin + (int64_t)it * R);
+                    const uint32_t dst = smem_u32(sHi + (size_t)stage * stage_bytes);
 #pragma unroll
-                for (int b = 0; b < G_BOXES; ++b)
-                    tma_load_2d(dst + (uint32_t)b * BOX_BYTES, &tmG, n0 + b * 32, row, full_bar(stage));
-                for (int b = 0; b < nkb; ++b)
-                    tma_load_2d(dst + (uint32_t)(G_BOXES + b) * BOX_BYTES, &tmA, b * 32, row, full_bar(stage));
+                    for (int b = 0; b < G_BOXES; ++b)
+                        tma_load_2d(dst + (uint32_t)b * BOX_BYTES, &tmG, n0 + b * 32, row, full_bar(stage));
+                    for (int b = 0; b < nkb; ++b)
+                        tma_load_2d(dst + (uint32_t)(G_BOXES + b) * BOX_BYTES, &tmA, b * 32, row, full_bar(stage));
+                }
+                __syncwarp();
                 if (++stage == stages) { stage = 0; phase ^= 1u; }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0 && n_iters > 0) {
+        if (n_iters > 0) {
             // D = f32, A = B = tf32, both MN-major (bits 15, 16), N >> 3 at bit 17, M >> 4 at bit 24
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(p.NB >> 3) << 17) | ((uint32_t)(TN >> 4) << 24);
@@ -199,25 +214,28 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
                 tc_fence_after();
                 const uint32_t hi = smem_u32(sHi + (size_t)stage * stage_bytes);
                 const uint32_t lo = smem_u32(sLo + (size_t)stage * stage_bytes);
+                if (elect_one()) {
 #pragma unroll
-                for (int s = 0; s < R / 8; ++s) {
-                    const uint32_t koff = (uint32_t)s * 1024u;
-                    const uint64_t dg = desc_mn_sw128(hi + koff, BOX_BYTES);
-                    const uint64_t da = desc_mn_sw128(hi + (uint32_t)G_BOXES * BOX_BYTES + koff, BOX_BYTES);
-                    if (PASSES == 3) {
-                        const uint64_t dgl = desc_mn_sw128(lo + koff, BOX_BYTES);
-                        const uint64_t dal = desc_mn_sw128(lo + (uint32_t)G_BOXES * BOX_BYTES + koff, BOX_BYTES);
-                        tc_mma_tf32(tmem_base, dgl, da, idesc, (it | s) ? 1u : 0u);
-                        tc_mma_tf32(tmem_base, dg, dal, idesc, 1u);
-                        tc_mma_tf32(tmem_base, dg, da, idesc, 1u);
-                    } else {
-                        tc_mma_tf32(tmem_base, dg, da, idesc, (it | s) ? 1u : 0u);
+                    for (int s = 0; s < R / 8; ++s) {
+                        const uint32_t koff = (uint32_t)s * 1024u;
+                        const uint64_t dg = desc_mn_sw128(hi + koff, BOX_BYTES);
+                        const uint64_t da = desc_mn_sw128(hi + (uint32_t)G_BOXES * BOX_BYTES + koff, BOX_BYTES);
+                        if (PASSES == 3) {
+                            const uint64_t dgl = desc_mn_sw128(lo + koff, BOX_BYTES);
+                            const uint64_t dal = desc_mn_sw128(lo + (uint32_t)G_BOXES * BOX_BYTES + koff, BOX_BYTES);
+                            tc_mma_tf32(tmem_base, dgl, da, idesc, (it | s) ? 1u : 0u);
+                            tc_mma_tf32(tmem_base, dg, dal, idesc, 1u);
+                            tc_mma_tf32(tmem_base, dg, da, idesc, 1u);
+                        } else {
+                            tc_mma_tf32(tmem_base, dg, da, idesc, (it | s) ? 1u : 0u);
+                        }
                     }
+                    tc_commit(empty_bar(stage));
                 }
-                tc_commit(empty_bar(stage));
+                __syncwarp();
                 if (++stage == stages) { stage = 0; phase ^= 1u; }
             }
-            tc_commit(done_bar);
+            if (elect_one()) tc_commit(done_bar);
         }
         __syncwarp();
     } else {
@@ -232,6 +250,7 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
             if (PASSES == 3 || live < R) {
                 float4* hi = reinterpret_cast<float4*>(sHi + (size_t)stage * stage_bytes);
                 float4* lo = reinterpret_cast<float4*>(sLo + (size_t)stage * stage_bytes);
+#pragma unroll 4
                 for (int u = t; u < units; u += 32 * FIX_WARPS) {
                     const int row = (u % (BOX_BYTES / 16)) >> 3;
                     float4 v = hi[u];
