@@ -60,7 +60,14 @@ struct TmaLinArgs {
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-#define PFO_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[(slot)] = clock64(); } while (0)
+// the clock read carries a memory clobber: without it the compiler hoists the read above barriers (observed: the
+// "total" stamp after the teardown __syncthreads was taken before the epilogue had finished)
+__device__ __forceinline__ long long pfo_clock() {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory");
+    return t;
+}
+#define PFO_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[(slot)] = pfo_clock(); } while (0)
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
