@@ -278,6 +278,10 @@ def main():
                msg_fn="mlp", aggregator="mean", **common)
     _run_model(TGN, get_neighbor_finder, "srcemb", d=32, ts_mode="small", with_ppos=False, n_batches=3,
                src_emb=True, **{**common, "dst_emb": True})
+    _run_model(TGN, get_neighbor_finder, "gsum", d=32, ts_mode="small", with_ppos=False, n_batches=3,
+               **{**common, "embedding": "graph_sum"})
+    _run_model(TGN, get_neighbor_finder, "gsum2", d=32, ts_mode="small", with_ppos=False, n_batches=2,
+               **{**common, "embedding": "graph_sum", "use_memory": False, "n_layers": 2, "n_neighbors": 4})
     golden_mv_select(RandEdgeSampler)
     golden_eval_metrics()
 

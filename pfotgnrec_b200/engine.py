@@ -30,7 +30,7 @@ class ModelConfig:
     n_heads: int = 2
     use_memory: bool = True
     updater: str = "gru"        # "gru" | "rnn"
-    embedding: str = "graph_attention"   # "graph_attention" | "time" | "identity"
+    embedding: str = "graph_attention"   # "graph_attention" | "graph_sum" | "time" | "identity"
     dyrep: bool = False
     dst_emb_in_msg: bool = False
     src_emb_in_msg: bool = False
@@ -64,6 +64,14 @@ class ModelConfig:
     @property
     def rawp(self):
         return (self.raw + 3) // 4 * 4
+
+    @property
+    def graph(self):            # embeddings that walk the sampled temporal neighbourhood
+        return self.embedding in ("graph_attention", "graph_sum")
+
+    @property
+    def ekp1(self):             # single-head row of the neighbour kernels (graph_sum)
+        return self.ekp
 
     @property
     def cell_in(self):          # input width of the memory updater
@@ -214,6 +222,9 @@ class TGNEngine:
         self.device = node_feat.device
         self.n_nodes = node_feat.shape[0]
         self.ws = _Workspace(self.device)
+        # graph_sum sums over ALL n sampled slots, padded ones included (they carry node 0's features, the edge
+        # feature row 0 and te(t - 0), embedding_module.py:205-208): node 0 then needs a row in the node table
+        self.skip_zero = 0 if cfg.embedding == "graph_sum" else 1
         self.step_id = 0
         self.seed = 0
         # device-resident batch counter keying the dropout stream (bumped on the stream each batch, so a
@@ -241,6 +252,10 @@ class TGNEngine:
                           a + "multi_head_target.out_proj.weight", a + "multi_head_target.out_proj.bias",
                           a + "merger.fc1.weight", a + "merger.fc1.bias", a + "merger.fc2.weight",
                           a + "merger.fc2.bias"]
+        elif c.embedding == "graph_sum":
+            for l in range(c.n_layers):
+                names += [f"embedding_module.linear_1.{l}.weight", f"embedding_module.linear_1.{l}.bias",
+                          f"embedding_module.linear_2.{l}.weight", f"embedding_module.linear_2.{l}.bias"]
         elif c.embedding == "time":
             names += ["embedding_module.embedding_layer.weight", "embedding_module.embedding_layer.bias"]
         return names
@@ -262,6 +277,19 @@ class TGNEngine:
                 flat += [params["message_function.mlp.%s" % k].contiguous() for k in ("0.weight", "0.bias", "2.weight", "2.bias")]
         if c.embedding == "graph_attention":
             flat += self._layer_params(params)
+        elif c.embedding == "graph_sum":
+            # GraphSumEmbedding.aggregate (embedding_module.py:205-219) in the operand order of the neighbour kernel:
+            #   sum_j linear_1([h_j | te_j | e_j]) = n * (W1p . mean_j [h_j | e_j | te_j] + b1)   (columns permuted)
+            #   linear_2([sum | h_q | te(0)])     = W2a . [sum | h_q] + (b2 + W2[:, 2d:] cos(tb))   (te(0) = cos(b))
+            # built with torch ops on the parameters, so autograd carries the gradients back to them
+            F_ = c.n_edge_feat
+            for l in range(c.n_layers):
+                W1 = params[f"embedding_module.linear_1.{l}.weight"]
+                W2 = params[f"embedding_module.linear_2.{l}.weight"]
+                flat += [torch.cat([W1[:, :d], W1[:, 2 * d:2 * d + F_], W1[:, d:2 * d]], dim=1).contiguous(),
+                         params[f"embedding_module.linear_1.{l}.bias"].contiguous(),
+                         W2[:, :2 * d].contiguous(),
+                         params[f"embedding_module.linear_2.{l}.bias"] + W2[:, 2 * d:] @ torch.cos(tb)]
         elif c.embedding == "time":
             flat += [params["embedding_module.embedding_layer.weight"].reshape(d).contiguous(),
                      params["embedding_module.embedding_layer.bias"].contiguous()]
@@ -376,7 +404,7 @@ class TGNEngine:
         st = self.state
         total = 0
         for ids in id_lists:
-            _lib.call("pfo_mark_nodes", ptr(ids), ids.numel(), 1, ptr(st.bitmap))
+            _lib.call("pfo_mark_nodes", ptr(ids), ids.numel(), self.skip_zero, ptr(st.bitmap))
             total += ids.numel()
         u_max = min(total, self.n_nodes)
         uniq = torch.zeros(u_max, dtype=torch.int32, device=self.device)
@@ -488,7 +516,7 @@ class TGNEngine:
 
     def _slots(self, ids):
         out = torch.empty(ids.shape, dtype=torch.int32, device=self.device)
-        _lib.call("pfo_map_slots", ptr(ids), ids.numel(), 1, ptr(self.slot_map), ptr(out))
+        _lib.call("pfo_map_slots", ptr(ids), ids.numel(), self.skip_zero, ptr(self.slot_map), ptr(out))
         return out
 
     def _attention_forward(self, tree, W, H0, save):
@@ -567,6 +595,73 @@ class TGNEngine:
         _lib.call("pfo_scatter_add_rows", dhq_ptr, ldc, ptr(tp.qidx), M, d, ptr(tp.dTq), d)
 
 
+    # ------------------------------------------------------------------ graph_sum (embedding_module.py:183-219)
+    def _sum_forward(self, tree, W, H0, save):
+        """GraphSumEmbedding on the neighbour kernels: one head, zero query operand -> uniform softmax weights 1/n
+        over the n slots (all live: padded slots resolve to node 0's row), so XB = mean_j x_j and
+        relu(sum_j linear_1(x_j)) = relu(n * (W1p . XB + b1)) is the linear kernel's alpha = n.  Returns (OUT, tape)."""
+        c = self.cfg
+        d, ekp, F = c.d, c.ekp, c.n_edge_feat
+        dev = self.device
+        layer, M = tree["layer"], tree["M"]
+        n = tree["nbr"].shape[1]
+        W1p, b1, W2a, b2f = W[layer - 1]
+        tp = _LayerTape()
+        tp.layer, tp.M, tp.n = layer, M, n
+        tp.child_q = tp.child_n = None
+        if layer == 1:
+            tp.Tq, tp.qidx = H0, self._slots(tree["nodes"])
+            tp.T, tp.idx = H0, self._slots(tree["nbr"].reshape(-1)).view(M, n)
+        else:
+            out_q, tp.child_q = self._sum_forward(tree["child_q"], W, H0, save)
+            out_n, tp.child_n = self._sum_forward(tree["child_n"], W, H0, save)
+            tp.Tq, tp.qidx = out_q, torch.arange(M, dtype=torch.int32, device=dev)
+            tp.T, tp.idx = out_n, torch.arange(M * n, dtype=torch.int32, device=dev).view(M, n)
+        tp.eidx, tp.dt = tree["eidx"], tree["dt"]
+        tp.QK = torch.zeros(M, 1, ekp, device=dev)
+        tp.CAT = torch.empty(M, ekp, device=dev)     # XB = mean of [h | e | te] over the slots (+ psum, valid, one)
+        tp.P = torch.empty(M, 1, n, device=dev)
+        tp.invalid = torch.empty(M, dtype=torch.int32, device=dev)
+        tp.step = layer
+        _lib.call("pfo_attn_nbr_fwd", ptr(tp.QK), ptr(tp.T), d, ptr(tp.idx), ptr(tp.eidx), ptr(tp.dt),
+                  ptr(self.edge_feat), ptr(save["tw"]), ptr(save["tb"]), M, n, d, F, 1, ekp,
+                  0.0, self.seed, tp.step, None, ptr(tp.CAT), ekp, ptr(tp.P), ptr(tp.invalid))
+        tp.H1 = torch.empty(M, 2 * d, device=dev)   # [relu(sum_j linear_1(x_j)) | h_query]
+        _linear(c, ptr(tp.CAT), ekp, None, ptr(W1p), 2 * d + F, 0, ptr(b1), ptr(tp.H1), 2 * d, M, d, 2 * d + F,
+                alpha=float(n), act=1)
+        _lib.call("pfo_gather_rows", ptr(tp.Tq), d, ptr(tp.qidx), M, d, tp.H1.data_ptr() + d * F4, 2 * d)
+        out = torch.empty(M, d, device=dev)
+        tp.out_rows = M
+        _linear(c, ptr(tp.H1), 2 * d, None, ptr(W2a), 2 * d, 0, ptr(b2f), ptr(out), d, M, d, 2 * d)
+        return out, tp
+
+    def _sum_backward(self, tp, dOUT, W, dW, save):
+        c = self.cfg
+        d, ekp, F = c.d, c.ekp, c.n_edge_feat
+        dev = self.device
+        M, n = tp.M, tp.n
+        W1p, b1, W2a, b2f = W[tp.layer - 1]
+        gW1p, gb1, gW2a, gb2f = dW[tp.layer - 1]
+        ws = self.ws
+        _wgrad(c, ws, ptr(dOUT), d, ptr(tp.H1), 2 * d, None, M, d, 2 * d, ptr(gW2a), 2 * d, ptr(gb2f), accumulate=1)
+        # d/d(pre-activation of the relu) = n * dY gated by Y > 0; d/dh_query = dOUT . W2a[:, d:]
+        G1 = torch.empty(M, d, device=dev)
+        _linear(c, ptr(dOUT), d, None, ptr(W2a), 2 * d, 1, None, ptr(G1), d, M, d, d, alpha=float(n),
+                relu_gate=ptr(tp.H1), ld_gate=2 * d)
+        dhq = torch.empty(M, d, device=dev)
+        _linear(c, ptr(dOUT), d, None, W2a.data_ptr() + d * F4, 2 * d, 1, None, ptr(dhq), d, M, d, d)
+        _wgrad(c, ws, ptr(G1), d, ptr(tp.CAT), ekp, None, M, d, 2 * d + F, ptr(gW1p), 2 * d + F, ptr(gb1), accumulate=1)
+        dXB = torch.zeros(M, ekp, device=dev)
+        _linear(c, ptr(G1), d, None, ptr(W1p), 2 * d + F, 1, None, ptr(dXB), ekp, M, 2 * d + F, d)
+        dQK = torch.empty(M, 1, ekp, device=dev)     # scratch: the query operand is identically zero
+        nws = ws.get(_lib.query("pfo_attn_nbr_bwd_workspace_floats", d))
+        _lib.call("pfo_attn_nbr_bwd", ptr(tp.QK), ptr(dXB), ekp, ptr(tp.P), ptr(tp.invalid), ptr(tp.T), d, ptr(tp.idx),
+                  ptr(tp.eidx), ptr(tp.dt), ptr(self.edge_feat), ptr(save["tw"]), ptr(save["tb"]),
+                  M, n, d, F, 1, ekp, 0.0, self.seed, tp.step, None, ptr(dQK), ptr(tp.dT), d,
+                  ptr(save["g_twtb"]), 1, ptr(nws))
+        _lib.call("pfo_scatter_add_rows", ptr(dhq), d, ptr(tp.qidx), M, d, ptr(tp.dTq), d)
+
+
 class TGNStepFunction(torch.autograd.Function):
     """One batch of the TGN path as a single autograd node over the packed parameters."""
 
@@ -583,6 +678,8 @@ class TGNStepFunction(torch.autograd.Function):
         if c.embedding == "graph_attention":
             rawW = [[next(it) for _ in range(10)] for _ in range(c.n_layers)]
             layerW, fold_ws = eng.fold_layers(rawW, tb)             # side stream; joined before the attention
+        elif c.embedding == "graph_sum":
+            layerW = [[next(it) for _ in range(4)] for _ in range(c.n_layers)]
         elif c.embedding == "time":
             embW = [next(it), next(it)]
         q_nodes, q_ts, n, B = batch["q_nodes"], batch["q_ts"], batch["n"], batch["B"]
@@ -595,7 +692,7 @@ class TGNStepFunction(torch.autograd.Function):
         # 1. neighbour sampling tree + unique touched nodes
         tree = None
         id_lists = [q_nodes]
-        if c.embedding == "graph_attention":
+        if c.graph:
             tree = eng._sample_tree(q_nodes, q_ts, c.n_layers, n)
             id_lists = []
             eng._collect_level0(tree, id_lists)
@@ -615,6 +712,8 @@ class TGNStepFunction(torch.autograd.Function):
         if c.embedding == "graph_attention":
             eng.join_side()
             emb, tape = eng._attention_forward(tree, layerW, H0, save)
+        elif c.embedding == "graph_sum":
+            emb, tape = eng._sum_forward(tree, layerW, H0, save)
         elif c.embedding == "time":
             n_src = batch["src"].shape[0]
             emb = torch.empty(Q, d, device=dev)
@@ -664,6 +763,8 @@ class TGNStepFunction(torch.autograd.Function):
                 gq, gc, gw, gt = chunk.split(fsz + [d])
                 g_layers.append([gq.view_as(pk["layerW"][l][0]), gc, gw.view_as(pk["layerW"][l][2]),
                                  g_raw[l][8], g_raw[l][9], gt])
+        elif c.embedding == "graph_sum":
+            g_layers = [[next(it) for _ in range(4)] for _ in range(c.n_layers)]
         elif c.embedding == "time":
             g_emb = [next(it), next(it)]
         u_max = pk["u_max"]
@@ -683,6 +784,22 @@ class TGNStepFunction(torch.autograd.Function):
                       ptr(pk["embW"][0]), ptr(pk["embW"][1]), ptr(dOut), ptr(dH0), ptr(gwb), ptr(buf), need)
             g_emb[0].copy_(gwb[:d])
             g_emb[1].copy_(gwb[d:])
+        if c.embedding == "graph_sum" and not (c.use_memory and c.dyrep):
+            save["g_twtb"] = torch.zeros(2 * d, device=dev)
+            stack = [(pk["tape"], dOut)]
+            while stack:
+                tp, g = stack.pop()
+                if tp.layer == 1:
+                    tp.dTq = tp.dT = dH0
+                else:
+                    tp.dTq = torch.zeros(tp.child_q.out_rows, d, device=dev)
+                    tp.dT = torch.zeros(tp.child_n.out_rows, d, device=dev)
+                eng._sum_backward(tp, g, pk["layerW"], g_layers, save)
+                if tp.layer > 1:
+                    stack.append((tp.child_q, tp.dTq))
+                    stack.append((tp.child_n, tp.dT))
+            g_tw.add_(save["g_twtb"][:d])
+            g_tb.add_(save["g_twtb"][d:])
         if attention_grad:
             save["g_twtb"] = torch.zeros(2 * d, device=dev)
             # walk the tape from the outermost layer down; level-0 feature grads land in dH0

@@ -62,8 +62,6 @@ class TGN(torch.nn.Module):
             raise ValueError("Message aggregator {} not implemented".format(aggregator_type))
         if message_function not in ("identity", "mlp"):
             raise ValueError("Message function {} not implemented".format(message_function))
-        if embedding_module_type == "graph_sum":
-            raise NotImplementedError("graph_sum embedding is not used by main.py (DESIGN.md, 'next' rows)")
 
         self.n_layers = n_layers
         self.neighbor_finder = neighbor_finder

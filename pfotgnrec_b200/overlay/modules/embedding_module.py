@@ -63,8 +63,19 @@ class GraphEmbedding(EmbeddingModule):
 
 
 class GraphSumEmbedding(GraphEmbedding):
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError("graph_sum is not used by any model of main.py (API surface, DESIGN.md 'next')")
+    """Parameter container of reference embedding_module.py:183-219 (same attribute names and init order); the sum over
+    the sampled slots and both linear layers run in the step engine (TGNEngine._sum_forward)."""
+
+    def __init__(self, node_features, edge_features, memory, neighbor_finder, time_encoder, n_layers,
+                 n_node_features, n_edge_features, n_time_features, embedding_dimension, device,
+                 n_heads=2, dropout=0.1, use_memory=True):
+        super(GraphSumEmbedding, self).__init__(node_features, edge_features, memory, neighbor_finder, time_encoder,
+                                                n_layers, n_node_features, n_edge_features, n_time_features,
+                                                embedding_dimension, device, n_heads, dropout, use_memory)
+        self.linear_1 = torch.nn.ModuleList([torch.nn.Linear(embedding_dimension + n_time_features + n_edge_features,
+                                                             embedding_dimension) for _ in range(n_layers)])
+        self.linear_2 = torch.nn.ModuleList([torch.nn.Linear(embedding_dimension + n_node_features + n_time_features,
+                                                             embedding_dimension) for _ in range(n_layers)])
 
 
 class GraphAttentionEmbedding(GraphEmbedding):

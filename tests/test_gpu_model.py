@@ -53,7 +53,7 @@ def build_tgn(tgn_mod, utils_mod, z, gemm_mode="fp32"):
     return tgn
 
 
-@pytest.mark.parametrize("tag", ["ours", "ours_nbg", "tgn", "jodie", "dyrep", "tgat2", "mlp_mean", "srcemb"])
+@pytest.mark.parametrize("tag", ["ours", "ours_nbg", "tgn", "jodie", "dyrep", "tgat2", "mlp_mean", "srcemb", "gsum", "gsum2"])
 @pytest.mark.parametrize("mode", ["fp32", "simt"])
 def test_drop_in_tgn_matches_reference_golden(overlay, tag, mode):
     """1e-5 contract in both exact GEMM modes: "fp32" = 3xTF32 on the tcgen05 tensor cores (default),

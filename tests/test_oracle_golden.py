@@ -24,7 +24,7 @@ def test_neighbors_bit_exact(name, n):
     assert nb.dtype == np.int32 and ei.dtype == np.int32 and et.dtype == np.float32
 
 
-@pytest.mark.parametrize("tag", ["ours", "ours_nbg", "tgn", "jodie", "dyrep", "tgat2", "mlp_mean", "srcemb"])
+@pytest.mark.parametrize("tag", ["ours", "ours_nbg", "tgn", "jodie", "dyrep", "tgat2", "mlp_mean", "srcemb", "gsum", "gsum2"])
 def test_model_path_matches_reference(tag):
     z = load_golden(f"tgn_{tag}.npz")
     o, p = oracle_from_golden(z)

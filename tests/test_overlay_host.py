@@ -42,7 +42,7 @@ def _build(tgn_mod, z, device="cpu"):
                        dyrep=bool(z["cfg_dyrep"]))
 
 
-@pytest.mark.parametrize("tag", ["ours", "jodie", "dyrep", "tgat2", "mlp_mean", "srcemb"])
+@pytest.mark.parametrize("tag", ["ours", "jodie", "dyrep", "tgat2", "mlp_mean", "srcemb", "gsum", "gsum2"])
 def test_initial_weights_and_keys_match_reference(overlay, tag):
     tgn_mod, _ = overlay
     z = load_golden(f"tgn_{tag}.npz")
