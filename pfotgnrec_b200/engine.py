@@ -225,6 +225,7 @@ class TGNEngine:
         # graph_sum sums over ALL n sampled slots, padded ones included (they carry node 0's features, the edge
         # feature row 0 and te(t - 0), embedding_module.py:205-208): node 0 then needs a row in the node table
         self.skip_zero = 0 if cfg.embedding == "graph_sum" else 1
+        self._slot_cache = {}
         self.step_id = 0
         self.seed = 0
         # device-resident batch counter keying the dropout stream (bumped on the stream each batch, so a
@@ -515,8 +516,15 @@ class TGNEngine:
             _lib.call("pfo_store_messages", ptr(src), ptr(dst), ptr(batch["eidx"]), ptr(batch["ts"]), B, d, F, *common)
 
     def _slots(self, ids):
+        """Node ids -> rows of the batch's node table.  The query list is mapped twice per step (embedding rows and
+        the layer-1 query operand): the second request is served from the step's cache."""
+        key = (ids.data_ptr(), ids.numel())
+        hit = self._slot_cache.get(key)
+        if hit is not None and hit[0] is ids:
+            return hit[1]
         out = torch.empty(ids.shape, dtype=torch.int32, device=self.device)
         _lib.call("pfo_map_slots", ptr(ids), ids.numel(), self.skip_zero, ptr(self.slot_map), ptr(out))
+        self._slot_cache[key] = (ids, out)
         return out
 
     def _attention_forward(self, tree, W, H0, save):
@@ -708,6 +716,7 @@ class TGNStepFunction(torch.autograd.Function):
         # 3. embeddings
         tape = None
         td = None
+        eng._slot_cache = {}                            # slot_of_node was rewritten by this batch's compaction
         qslots = eng._slots(q_nodes)
         if c.embedding == "graph_attention":
             eng.join_side()
