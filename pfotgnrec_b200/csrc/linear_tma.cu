@@ -9,8 +9,9 @@
 //
 //   warp 0     TMA producer: one 128-row x 32-column fp32 box (16 KiB, SWIZZLE_128B) per K chunk
 //              into a ring of shared-memory stages (mbarrier full/empty handshake)
-//   warp 1     MMA issuer: one elected lane issues tcgen05.mma (M=128, N=NT, K=8 per instruction),
-//              accumulating in TMEM; tcgen05.commit releases the stage / publishes the accumulator
+//   warp 1     MMA issuer: the whole warp walks the (tile, chunk) loops, one elected lane issues tcgen05.mma
+//              (M=128, N=NT, K=8 per instruction), accumulating in TMEM; tcgen05.commit releases the stage /
+//              publishes the accumulator
 //   warps 2-9  epilogue: tcgen05.ld of their 32 TMEM lanes (lane = output row), bias / scale / relu / row-mask in
 //              registers, a swizzled staging tile per 16-column slab, then coalesced 16-byte stores (relu gate
 //              and accumulate applied there); two warps per lane quarter so the schedulers can hide latency
@@ -18,8 +19,10 @@
 //
 // passes = 1: plain TF32 (10-bit mantissa), the "fast" mode (2e-2 contract, in practice ~1e-3).
 // passes = 3: error-compensated 3xTF32 for the 1e-5 contract: a = a_hi + a_lo with a_hi =
-//   rna_tf32(a); D = A_hi.W_hi + A_lo.W_hi + A_hi.W_lo; the dropped terms are ~2^-22 relative.
-//   The splitter warps rewrite each landed stage in place (hi) and into a twin stage (lo).
+//   rna_tf32(a); D = A_lo.W_hi + A_hi.W_lo + A_hi.W_hi; the dropped terms are ~2^-22 relative.
+//   The splitter warps (one thread per tile row) rewrite each landed stage in place (hi) and put the residual
+//   into the stage's TMEM slot: the A_lo.W_hi MMA takes its A operand from tensor memory, so the ring needs no
+//   shared-memory twin.  TMEM columns: [2 accumulators x NT][stages x 32 A-lo columns] <= 512.
 // The weight slice W[n0:n0+NT, :K] is staged once per CTA (canonical no-swizzle K-major core
 // matrices, split hi/lo in 3-pass mode) and stays resident while the CTA walks its row tiles;
 // two TMEM accumulators let the epilogue of tile i overlap the MMAs of tile i+1.

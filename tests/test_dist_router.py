@@ -123,3 +123,42 @@ def test_replica_slice_rejects_ragged_batches():
     from pfotgnrec_b200.trainer import replica_slice
     with pytest.raises(ValueError):
         replica_slice(0, 130, 0, 4)
+
+
+def _metric_worker(rank, world, port, results):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import numpy as np
+    from pfotgnrec_b200.evalmetrics import EvalMetricBlock
+    from pfotgnrec_b200.trainer import allreduce_sum_, replica_slice
+    try:
+        # every rank holds the running sums of ITS slice of the users (replicated evaluation splits by user)
+        rng = np.random.default_rng(7)
+        per_event = rng.standard_normal((64, 18))
+        per_event[:, :6] = (per_event[:, :6] > 0)
+        ls, le = replica_slice(0, 64, rank, world)
+        mine = per_event[ls:le]
+        blk = EvalMetricBlock(np.zeros((1, 1, 29)), np.zeros((1, 1, 29)), 1, device="cpu")
+        blk.acc[:18] = torch.as_tensor(mine.sum(axis=0))
+        blk.acc[18:30] = torch.as_tensor((mine[:, 6:] > 0).sum(axis=0).astype(np.float64))
+        blk.acc[30] = mine.shape[0]
+        got = blk.summary("val", reduce=allreduce_sum_)
+        assert abs(got["val_recall_avg_3"] - per_event[:, 1].mean()) < 1e-12
+        assert abs(got["val_sharpe_avg_5_"] - per_event[:, 17].mean()) < 1e-12
+        assert abs(got["val_return_percent_1"] - (per_event[:, 6] > 0).mean()) < 1e-12
+        assert len(got) == 30
+        results[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_eval_metric_sums_all_reduce_gloo_world2():
+    """The 31 running sums of the evaluation metric block, held per rank for its slice of the users, reduce to the
+    whole-run dictionary with one all-reduce (reference evaluation.py:209-258 over all interactions)."""
+    world = 2
+    mgr = mp.Manager()
+    results = mgr.dict()
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_metric_worker, args=(world, port, results), nprocs=world, join=True)
+    assert dict(results) == {0: "ok", 1: "ok"}
