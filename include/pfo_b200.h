@@ -228,13 +228,15 @@ int pfo_eval_metrics(const int32_t* pos_rank, const int32_t* top_idx, int topk, 
 /* ---- K5: candidate sampling + mean-variance efficient selection --- utils/utils.py:65-114
  * (RandEdgeSampler) and main.py:197-304 (inline block).  Stocks are 0-based indices; logret is
  * float64 [n_days, n_stocks, n_returns].  sample != 0 draws cand[:,1:] from the Philox stream
- * (cand[:,0] = pos_stock); sample == 0 takes cand as input.  p_neg is [n_neg-th lowest .. lowest]. */
+ * (cand[:,0] = pos_stock - item_offset); sample == 0 takes cand as input.  p_neg is [n_neg-th lowest .. lowest].
+ * item_offset: pos_stock is read, and p_pos / p_neg are written, as stock index + item_offset (the item ids of the
+ * interaction stream, upper_u + 1 + stock); cand stays 0-based. */
 int pfo_mv_select(const int64_t* event_ids, const int32_t* day_idx, const int32_t* pos_stock,
                   const int64_t* port_ptr, const int32_t* port_items,
                   const int32_t* items_sorted, int n_items_universe,
                   const double* logret, int n_stocks, int n_returns,
                   int B, int K, double gamma, double lam, int n_pos, int n_neg, uint64_t seed, int sample,
-                  int32_t* cand, double* y_out, int32_t* p_pos, int32_t* p_neg, void* stream);
+                  int32_t* cand, double* y_out, int32_t* p_pos, int32_t* p_neg, int item_offset, void* stream);
 int pfo_sample_candidates(const int64_t* event_ids, const int64_t* port_ptr, const int32_t* port_items,
                           const int32_t* items_sorted, int n_items_universe, int B, int size,
                           uint64_t seed, int32_t* out, void* stream);

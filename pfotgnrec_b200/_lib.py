@@ -58,7 +58,7 @@ _SIGS = {
     "pfo_eval_score": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, P, P, P]),
     "pfo_eval_metrics": (c_int, [P, P, c_int, P, P, c_int, c_int, P, P, P, P, P, c_int, c_int, c_int, P, P, P]),
     "pfo_mv_select": (c_int, [P, P, P, P, P, P, c_int, P, c_int, c_int, c_int, c_int, c_double, c_double, c_int,
-                              c_int, c_uint64, c_int, P, P, P, P, P]),
+                              c_int, c_uint64, c_int, P, P, P, P, c_int, P]),
     "pfo_sample_candidates": (c_int, [P, P, P, P, c_int, c_int, c_int, c_uint64, P, P]),
 }
 

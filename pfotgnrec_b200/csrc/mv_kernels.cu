@@ -112,7 +112,7 @@ struct MvArgs {
     const int32_t* items; int M;
     const double* logret; int n_stocks; int T;
     int B; int K; double gamma; double lam; int n_pos; int n_neg; uint32_t k0, k1; int sample;
-    int32_t* cand; double* y_out; int32_t* p_pos; int32_t* p_neg;
+    int32_t* cand; double* y_out; int32_t* p_pos; int32_t* p_neg; int item_offset;
 };
 
 __global__ void __launch_bounds__(kWarps * 32)
@@ -137,7 +137,7 @@ mv_select_kernel(const MvArgs p) {
                                    : count_held_in_universe(held, nP, p.items, M, lane);
         const int n_av = M - nH;
         int my_cand = 0;
-        if (lane == 0) my_cand = p.pos_stock[b];
+        if (lane == 0) my_cand = p.pos_stock[b] - p.item_offset;
         if (!p.sample) {
             if (lane < C) my_cand = p.cand[b * C + lane];
         } else if (n_av < K) {
@@ -247,8 +247,8 @@ mv_select_kernel(const MvArgs p) {
         }
         if (lane < C) {
             const int desc = K - position;            // index in argsort(new_rank)[::-1]
-            if (desc < p.n_pos) p.p_pos[b * p.n_pos + desc] = my_cand;
-            if (desc >= C - p.n_neg) p.p_neg[b * p.n_neg + (desc - (C - p.n_neg))] = my_cand;
+            if (desc < p.n_pos) p.p_pos[b * p.n_pos + desc] = my_cand + p.item_offset;
+            if (desc >= C - p.n_neg) p.p_neg[b * p.n_neg + (desc - (C - p.n_neg))] = my_cand + p.item_offset;
         }
         __syncwarp();
     }
@@ -324,12 +324,12 @@ PFO_API int pfo_mv_select(const int64_t* event_ids, const int32_t* day_idx, cons
                           const int32_t* items_sorted, int n_items_universe,
                           const double* logret, int n_stocks, int n_returns,
                           int B, int K, double gamma, double lam, int n_pos, int n_neg, uint64_t seed, int sample,
-                          int32_t* cand, double* y_out, int32_t* p_pos, int32_t* p_neg, void* stream) {
+                          int32_t* cand, double* y_out, int32_t* p_pos, int32_t* p_neg, int item_offset, void* stream) {
     if (B <= 0) return 0;
     if (K < 1 || K > 31 || n_returns > 32 || n_returns < 2 || n_pos + n_neg > K + 1) return (int)cudaErrorInvalidValue;
     MvArgs a{event_ids, day_idx, pos_stock, port_ptr, port_items, items_sorted, n_items_universe,
              logret, n_stocks, n_returns, B, K, gamma, lam, n_pos, n_neg,
-             (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), sample, cand, y_out, p_pos, p_neg};
+             (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), sample, cand, y_out, p_pos, p_neg, item_offset};
     mv_select_kernel<<<pfo_grid((int64_t)B * 32, kWarps * 32, 8), kWarps * 32, 0, (cudaStream_t)stream>>>(a);
     PFO_LAUNCH_CHECK();
 }

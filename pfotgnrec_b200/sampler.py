@@ -66,7 +66,7 @@ class MVSelector:
         dev = self.device
         ev = _dev(event_ids, torch.int64, dev)
         di = _dev(day_idx, torch.int32, dev)
-        pos = (_dev(dst_items, torch.int32, dev) - (self.n_users + 1)).contiguous()
+        pos = _dev(dst_items, torch.int32, dev)          # item ids; the kernel subtracts / adds the item offset
         pp = _dev(port_ptr, torch.int64, dev)
         pi = _dev(port_items, torch.int32, dev)
         if pi.numel() == 0:
@@ -79,8 +79,8 @@ class MVSelector:
         p_neg = torch.empty(B * self.n_neg, dtype=torch.int32, device=dev)
         _lib.call("pfo_mv_select", ptr(ev), ptr(di), ptr(pos), ptr(pp), ptr(pi), ptr(self.universe),
                   self.universe.shape[0], ptr(self.logret), self.n_stocks, self.T, B, self.K, self.gamma, self.lam,
-                  self.n_pos, self.n_neg, self.seed, int(sample), ptr(cand_t), ptr(y), ptr(p_pos), ptr(p_neg))
-        off = self.n_users + 1
+                  self.n_pos, self.n_neg, self.seed, int(sample), ptr(cand_t), ptr(y), ptr(p_pos), ptr(p_neg),
+                  self.n_users + 1)
         if return_scores:
-            return p_pos + off, p_neg + off, cand_t, y
-        return p_pos + off, p_neg + off
+            return p_pos, p_neg, cand_t, y
+        return p_pos, p_neg

@@ -32,10 +32,13 @@ def load_overlay():
 
 
 class _BPR(torch.autograd.Function):
-    """-mean log sigmoid(mean_k(<u,p> - <u,n_k>)) with its gradient from one fused kernel (K6)."""
+    """-mean log sigmoid(mean_k(<u,p> - <u,n_k>)) with its gradient from one fused kernel (K6).  `grad_scale`
+    multiplies the gradients inside the kernel (the data-parallel trainer's 1 / world); with `unit_upstream` the
+    caller promises to call `.backward()` on the returned loss itself, so the three gradient tensors are handed to
+    autograd as they are instead of being multiplied by the upstream 1.0 (three elementwise launches per step)."""
 
     @staticmethod
-    def forward(ctx, eu, ep, en, ws):
+    def forward(ctx, eu, ep, en, ws, grad_scale=1.0, unit_upstream=False):
         B, d = eu.shape
         k = en.shape[0] // B
         eu, ep, en = eu.contiguous(), ep.contiguous(), en.contiguous()
@@ -44,14 +47,17 @@ class _BPR(torch.autograd.Function):
         du = torch.empty_like(eu) if need else None
         dp = torch.empty_like(ep) if need else None
         dn = torch.empty_like(en) if need else None
-        _lib.call("pfo_bpr", ptr(eu), ptr(ep), ptr(en), B, k, d, ptr(du), ptr(dp), ptr(dn), ptr(loss), 1.0, ptr(ws))
-        ctx.grads = (du, dp, dn)
+        _lib.call("pfo_bpr", ptr(eu), ptr(ep), ptr(en), B, k, d, ptr(du), ptr(dp), ptr(dn), ptr(loss), float(grad_scale),
+                  ptr(ws))
+        ctx.grads, ctx.unit_upstream = (du, dp, dn), bool(unit_upstream)
         return loss.squeeze(0)
 
     @staticmethod
     def backward(ctx, g):
         du, dp, dn = ctx.grads
-        return du * g, dp * g, dn * g, None
+        if ctx.unit_upstream:
+            return du, dp, dn, None, None, None
+        return du * g, dp * g, dn * g, None, None, None
 
 
 def bpr_loss(e_u, e_pos, e_neg, workspace=None):
@@ -313,8 +319,8 @@ class PfoTrainer:
             neg = self.neg_sampler.sample(b["ev"], b["port_ptr"], held, tc.p_neg_num, seed=tc.seed).reshape(-1)
             e_s, e_p, e_n = eng.compute_temporal_embeddings(params, b["src"], b["dst"], [neg], b["ts"], b["eidx"],
                                                             tc.n_neighbors, train=True, state_batch=sb)
-        loss = bpr_loss(e_s, e_p, e_n, self.bpr_ws)
-        (loss if self._loss_scale == 1.0 else loss * self._loss_scale).backward()
+        loss = _BPR.apply(e_s, e_p, e_n, self.bpr_ws, self._loss_scale, True)     # gradients pre-scaled in the kernel
+        loss.backward()
         return loss.detach()
 
     # hooks of the data-parallel subclass
