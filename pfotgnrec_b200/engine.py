@@ -356,7 +356,7 @@ class TGNEngine:
 
     # ------------------------------------------------------------------ public step
     def compute_temporal_embeddings(self, params, src, dst, extra_groups, ts, eidx, n_neighbors,
-                                    train=True, update_state=True, state_batch=None):
+                                    train=True, update_state=True, state_batch=None, packed=False):
         """src/dst int32[B], extra_groups list of int32[k*B] (interaction-major), ts float64[B],
         eidx int32[B] -- all device tensors.  Returns [emb_src, emb_dst, *emb_extra] ([.,d] fp32,
         differentiable w.r.t. `params` when grad mode is on) and advances memory / messages.
@@ -378,6 +378,8 @@ class TGNEngine:
             batch["state"] = dict(src=state_batch["src"], dst=state_batch["dst"], ts=state_batch["ts"],
                                   eidx=state_batch["eidx"], B=int(state_batch["src"].shape[0]))
         emb = TGNStepFunction.apply(self, batch, *flat)
+        if packed:          # one [Q, d] tensor, rows in group order: a loss over row blocks hands ONE gradient back
+            return emb      # (splitting costs autograd a zero fill and a concatenation of the pieces per step)
         return list(torch.split(emb, [g.shape[0] for g in groups]))
 
     # ------------------------------------------------------------------ forward internals
@@ -794,7 +796,7 @@ class TGNStepFunction(torch.autograd.Function):
             g_emb[0].copy_(gwb[:d])
             g_emb[1].copy_(gwb[d:])
         if c.embedding == "graph_sum" and not (c.use_memory and c.dyrep):
-            save["g_twtb"] = torch.zeros(2 * d, device=dev)
+            save["g_twtb"] = gbuf[:2 * d]               # [d/dw | d/db] = the first two entries of the flat buffer
             stack = [(pk["tape"], dOut)]
             while stack:
                 tp, g = stack.pop()
@@ -807,10 +809,8 @@ class TGNStepFunction(torch.autograd.Function):
                 if tp.layer > 1:
                     stack.append((tp.child_q, tp.dTq))
                     stack.append((tp.child_n, tp.dT))
-            g_tw.add_(save["g_twtb"][:d])
-            g_tb.add_(save["g_twtb"][d:])
         if attention_grad:
-            save["g_twtb"] = torch.zeros(2 * d, device=dev)
+            save["g_twtb"] = gbuf[:2 * d]               # the neighbour kernels accumulate into the zeroed flat buffer
             # walk the tape from the outermost layer down; level-0 feature grads land in dH0
             stack = [(pk["tape"], dOut)]
             while stack:
@@ -826,8 +826,6 @@ class TGNStepFunction(torch.autograd.Function):
                     stack.append((tp.child_n, tp.dT))
             # the fold's adjoint runs beside the memory-updater backward (it needs only the finished operand grads)
             eng.unfold_layer_grads(pk["rawW"], flat[1], pk["fold_ws"], g_layers, g_raw, [g[5] for g in g_layers])
-            g_tw.add_(save["g_twtb"][:d])
-            g_tb.add_(save["g_twtb"][d:])
         if c.use_memory and g_mlp is not None:
             eng.node_table_backward(pk["tab"], dH0, g_cell, pk["mlpW"], g_mlp, pk["cellW"])
         elif c.use_memory:

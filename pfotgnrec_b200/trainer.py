@@ -60,6 +60,35 @@ class _BPR(torch.autograd.Function):
         return du * g, dp * g, dn * g, None, None, None
 
 
+class _BPRPacked(torch.autograd.Function):
+    """The training step's BPR over the PACKED embedding tensor [Q, d] (row blocks [src | dst | (p_pos) | negatives]):
+    the fused kernel reads its three operands as row blocks and writes their gradients into the matching blocks of
+    one [Q, d] buffer, which is the gradient of the packed tensor -- no split / zero-fill / concatenation in autograd.
+    The caller calls `.backward()` on the returned loss itself (upstream gradient 1; `grad_scale` applied in the kernel)."""
+
+    @staticmethod
+    def forward(ctx, emb, B, pos_block, neg_block, k, ws, grad_scale):
+        d = emb.shape[1]
+        emb = emb.contiguous()
+        row = lambda t, blk: t.data_ptr() + blk * B * d * t.element_size()
+        loss = torch.empty(1, device=emb.device)
+        dEmb = None
+        if ctx.needs_input_grad[0]:
+            dEmb = torch.empty_like(emb)
+            for blk in range(neg_block):                 # blocks the loss does not read (dst in the PfoTGNRec step)
+                if blk not in (0, pos_block):
+                    dEmb[blk * B:(blk + 1) * B].zero_()
+        dptr = (lambda blk: row(dEmb, blk)) if dEmb is not None else (lambda blk: None)
+        _lib.call("pfo_bpr", row(emb, 0), row(emb, pos_block), row(emb, neg_block), B, k, d,
+                  dptr(0), dptr(pos_block), dptr(neg_block), ptr(loss), float(grad_scale), ptr(ws))
+        ctx.dEmb = dEmb
+        return loss.squeeze(0)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.dEmb, None, None, None, None, None, None
+
+
 def bpr_loss(e_u, e_pos, e_neg, workspace=None):
     """BPR loss of reference main.py:321-337 (e_neg is [B*k, d], interaction-major)."""
     if workspace is None:
@@ -312,14 +341,16 @@ class PfoTrainer:
         sb = b.get("state")                          # replicated data-parallel mode: the global batch advances the state
         if tc.model == "ours":
             p_pos, p_neg = self.mv.select(b["ev"], b["day"], b["dst"], b["port_ptr"], port_items)
-            e_s, _, e_p, e_n = eng.compute_temporal_embeddings(params, b["src"], b["dst"], [p_pos, p_neg], b["ts"],
-                                                               b["eidx"], tc.n_neighbors, train=True, state_batch=sb)
+            emb = eng.compute_temporal_embeddings(params, b["src"], b["dst"], [p_pos, p_neg], b["ts"], b["eidx"],
+                                                  tc.n_neighbors, train=True, state_batch=sb, packed=True)
+            pos_block, neg_block = 2, 3                  # rows [src | dst | p_pos | p_neg]
         else:
             held = port_items + (self.st.n_users + 1) if "port_items" in b else D.port_items_as_item_ids
             neg = self.neg_sampler.sample(b["ev"], b["port_ptr"], held, tc.p_neg_num, seed=tc.seed).reshape(-1)
-            e_s, e_p, e_n = eng.compute_temporal_embeddings(params, b["src"], b["dst"], [neg], b["ts"], b["eidx"],
-                                                            tc.n_neighbors, train=True, state_batch=sb)
-        loss = _BPR.apply(e_s, e_p, e_n, self.bpr_ws, self._loss_scale, True)     # gradients pre-scaled in the kernel
+            emb = eng.compute_temporal_embeddings(params, b["src"], b["dst"], [neg], b["ts"], b["eidx"],
+                                                  tc.n_neighbors, train=True, state_batch=sb, packed=True)
+            pos_block, neg_block = 1, 2                  # rows [src | dst | negatives]
+        loss = _BPRPacked.apply(emb, B, pos_block, neg_block, tc.p_neg_num, self.bpr_ws, self._loss_scale)
         loss.backward()
         return loss.detach()
 
