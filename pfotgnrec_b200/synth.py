@@ -169,3 +169,52 @@ def write_reference_format(stream: Stream, root: str, period: str = "30") -> str
         with open(os.path.join(d, f"time_feature_{name}_{period}.pkl"), "wb") as f:
             pickle.dump(tf, f)
     return d
+
+
+def read_reference_format(root: str, period: str = "30") -> Stream:
+    """Load `root/data/period_{p}/...` -- the files the reference's `get_data` / `main.py` / `evaluation.py` read
+    (utils/data.py:20-25, main.py:88-89, evaluation.py:41-43; formats in SURVEY 8f-2) -- into a `Stream`:
+    ml_transaction.json (records u, i, ts, label, idx, portfolio), ml_transaction.npy (edge features, row 0 = padding),
+    map_item_id.pkl (stock code -> 0-based index), time_feature_{past,future}_{p}.pkl (day 'YYYYMMDD' -> code -> prices).
+    Interactions are kept in file order (the reference never re-sorts them); the day of an interaction is
+    str(ts)[:8] like main.py:212 / evaluation.py:151; an empty portfolio is the reference's ['']."""
+    d = os.path.join(root, "data", f"period_{period}")
+    with open(os.path.join(d, "ml_transaction.json")) as f:
+        recs = json.load(f)
+    if isinstance(recs, dict):                                   # pandas' column-oriented layout
+        cols = {k: [v[i] for i in sorted(v, key=int)] for k, v in recs.items()}
+        recs = [dict(zip(cols, row)) for row in zip(*cols.values())]
+    E = len(recs)
+    src = np.fromiter((r["u"] for r in recs), dtype=np.int64, count=E)
+    dst = np.fromiter((r["i"] for r in recs), dtype=np.int64, count=E)
+    ts = np.fromiter((r["ts"] for r in recs), dtype=np.float64, count=E)
+    eidx = np.fromiter((r["idx"] for r in recs), dtype=np.int64, count=E)
+    efeat = np.load(os.path.join(d, "ml_transaction.npy")).astype(np.float64)
+    with open(os.path.join(d, "map_item_id.pkl"), "rb") as f:
+        map_item_id = pickle.load(f)
+    codes = [c for c, _ in sorted(map_item_id.items(), key=lambda kv: kv[1])]
+    n_users, n_items = int(src.max()), len(codes)
+    tables = {}
+    for name in ("future", "past"):
+        with open(os.path.join(d, f"time_feature_{name}_{period}.pkl"), "rb") as f:
+            tables[name] = pickle.load(f)
+    day_keys = sorted(set(tables["future"]) | set(tables["past"]))
+    day_of = {k: i for i, k in enumerate(day_keys)}
+    T1 = len(next(iter(next(iter(tables["future"].values())).values())))
+
+    def dense(tf):
+        a = np.full((len(day_keys), n_items, T1), np.nan)
+        for k, row in tf.items():
+            for code, prices in row.items():
+                j = map_item_id.get(code)
+                if j is not None:
+                    a[day_of[k], j] = prices
+        return a
+
+    day_idx = np.fromiter((day_of[str(t)[:8]] for t in ts), dtype=np.int32, count=E)
+    held = [[] if "" in r["portfolio"] else [map_item_id[c] for c in r["portfolio"]] for r in recs]
+    pptr = np.zeros(E + 1, dtype=np.int64)
+    np.cumsum([len(h) for h in held], out=pptr[1:])
+    pit = np.fromiter((x for h in held for x in h), dtype=np.int32, count=int(pptr[-1]))
+    return Stream(n_users, n_items, src, dst, ts, eidx, efeat, day_idx, pptr, pit, dense(tables["future"]),
+                  dense(tables["past"]), day_keys, codes)

@@ -457,6 +457,38 @@ class PfoTrainer:
             self.eval_step(a, b_, n_items=n_items)
         return self.eval_summary(EVAL)
 
+    def split_ranges(self):
+        """(train, validation, test) index ranges: the chronological 80/10/10 split of reference utils/data.py:27,48-50
+        (the stream is time-sorted, so the three masks are contiguous)."""
+        tr, va, _ = self.masks
+        n_tr, n_va = int(tr.sum()), int(va.sum())
+        return (0, n_tr), (n_tr, n_tr + n_va), (n_tr + n_va, self.st.n_events)
+
+    def fit(self, epochs=1, bs=None, max_batches=None, log=None):
+        """The epoch loop of reference main.py:144-443: re-initialise the memory, train over the training split in
+        batches of `bs` (the last one may be short), then evaluate the validation and the test split on the full
+        graph -- the memory carries over from training into validation into test, as in the reference.  Returns one
+        dictionary per epoch: the mean training loss plus the reference's 30 `valid_*` and 30 `test_*` keys."""
+        bs = int(bs or self.tc.bs)
+        (t0, t1), (v0, v1), (e0, e1) = self.split_ranges()
+        history = []
+        for epoch in range(int(epochs)):
+            if self.tgn.use_memory:
+                self.tgn.memory.__init_memory__()                    # main.py:152-153
+            losses = []
+            for bi in range(-(-(t1 - t0) // bs)):
+                if max_batches is not None and bi >= max_batches:    # main.py:162-164 (--test_run)
+                    break
+                s, e = t0 + bi * bs, min(t1, t0 + (bi + 1) * bs)
+                losses.append(self.train_step(s, e).clone())         # the graph's output buffer is reused next step
+            out = {"epoch": epoch, "loss": float(torch.stack(losses).mean().item()) if losses else float("nan")}
+            out.update(self.evaluate(v0, v1, bs=bs, EVAL="valid"))   # main.py:405-418
+            out.update(self.evaluate(e0, e1, bs=bs, EVAL="test"))    # main.py:427-440
+            history.append(out)
+            if log is not None:
+                log(out)
+        return history
+
     @staticmethod
     def recall_ndcg(pos_rank, ks=(1, 3, 5)):
         """Recall@k / NDCG@k with a single relevant item (reference evaluation.py:11-21,141-144)."""

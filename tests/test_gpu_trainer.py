@@ -199,3 +199,29 @@ def test_overlay_eval_recommendation_matches_trainer_loop(tmp_path, monkeypatch)
     for k in want:
         assert got[k] == want[k], (k, got[k], want[k])
     assert torch.equal(a.tgn.memory.memory.detach(), mem_want)
+
+
+def test_fit_epoch_loop_matches_manual_loop():
+    """PfoTrainer.fit (the epoch loop of reference main.py:144-443) == the same calls made by hand: memory re-initialised
+    per epoch, training batches over the training split (short last batch included), validation then test evaluation
+    on the full graph with the memory carried over.  lr = 0 keeps the weights fixed, so the two runs are bit-identical."""
+    from pfotgnrec_b200.trainer import PfoTrainer, TrainConfig
+    st = _stream(seed=8)
+    tc = TrainConfig(model="ours", bs=200, lr=0.0, cuda_graph=False)
+    a, b = PfoTrainer(st, tc, device="cuda:0"), PfoTrainer(st, tc, device="cuda:0")
+    hist = a.fit(epochs=2, bs=200)
+    assert len(hist) == 2 and all(len(h) == 62 for h in hist)
+    (t0, t1), (v0, v1), (e0, e1) = b.split_ranges()
+    assert (t0, e1) == (0, st.n_events) and t1 == v0 and v1 == e0 and (t1 - t0) % 200 != 0      # a short last batch
+    for epoch in range(2):
+        b.tgn.memory.__init_memory__()
+        losses = [float(b.train_step(s, min(t1, s + 200)).item()) for s in range(t0, t1, 200)]
+        want = {"epoch": epoch, "loss": float(np.mean(np.asarray(losses, dtype=np.float32)))}
+        want.update(b.evaluate(v0, v1, bs=200, EVAL="valid"))
+        want.update(b.evaluate(e0, e1, bs=200, EVAL="test"))
+        got = hist[epoch]
+        assert set(got) == set(want)
+        for k, v in want.items():
+            assert abs(got[k] - v) <= 1e-6 * max(1.0, abs(v)), (epoch, k, got[k], v)
+        assert 0.0 <= got["valid_recall_avg_5"] <= 1.0 and np.isfinite(got["loss"])
+    assert hist[0]["loss"] == hist[1]["loss"]            # same weights, memory reset: the epochs repeat exactly

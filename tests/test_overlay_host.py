@@ -111,3 +111,20 @@ def test_bench_reference_arm_json_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+
+
+def test_reference_on_disk_format_round_trip(tmp_path):
+    """synth.write_reference_format -> synth.read_reference_format reproduces the stream: ids, times, edge features,
+    day rows, portfolio CSR and both price tables (the files are the ones reference utils/data.py:20-25, main.py:88-89
+    and evaluation.py:41-43 load)."""
+    from pfotgnrec_b200.synth import make_stream, write_reference_format, read_reference_format
+    st = make_stream(n_users=120, n_items=25, n_events=900, n_days=9, seed=3, ts_mode="nbg")
+    write_reference_format(st, str(tmp_path), period="30")
+    rt = read_reference_format(str(tmp_path), period="30")
+    assert rt.n_users == st.sources.max() and rt.n_items == st.n_items and rt.codes == st.codes
+    for k in ("sources", "destinations", "timestamps", "edge_idxs", "edge_features", "port_ptr", "port_items",
+              "prices_future", "prices_past"):
+        assert np.array_equal(getattr(rt, k), getattr(st, k)), k
+    used = np.unique(st.day_idx)                  # day rows: same price rows for every interaction
+    assert [rt.day_keys[i] for i in rt.day_idx[:50]] == [st.day_keys[i] for i in st.day_idx[:50]]
+    assert np.array_equal(rt.prices_future[rt.day_idx], st.prices_future[st.day_idx]) and used.size > 0
