@@ -112,3 +112,16 @@ def test_eval_metric_block_matches_reference():
     assert set(got) == set(ref) and len(ref) == 30
     for k, v in ref.items():
         assert abs(got[k] - v) <= 1e-12 * max(1.0, abs(v)), (k, got[k], v)
+
+
+def test_philox4x32_10_known_answer_vectors():
+    """The shared random stream (oracle/philox.py == csrc/philox.cuh) is Philox4x32-10 of Random123: its three published
+    known-answer vectors (kat_vectors: zero, all-ones and the pi-digits counter / key)."""
+    from oracle.philox import philox4x32_10
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = philox4x32_10(np.array([ctr[0]], dtype=np.int64), ctr[1], ctr[2], ctr[3], key[0], key[1])
+        assert tuple(int(x[0]) for x in got) == want
