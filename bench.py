@@ -67,6 +67,25 @@ def make_data(a):
     return make_stream(n_users=a.users, n_items=a.items, n_events=a.events, n_days=a.days, seed=0, ts_mode="nbg")
 
 
+class StreamCursor:
+    """Start / end of consecutive batches inside [lo, hi) of the stream.  When the next batch would run past the end
+    the cursor wraps to `lo`: a long run on 8 GPUs (global batch 65 536) consumes more events than the 5 M-event
+    stream holds after the start offset, and the region is then replayed (same graph, same shapes, same work)."""
+
+    def __init__(self, lo, hi):
+        self.lo, self.hi, self.pos = int(lo), int(hi), int(lo)
+
+    def take(self, n):
+        n = int(n)
+        if n > self.hi - self.lo:
+            raise SystemExit(f"a batch of {n} events does not fit the stream region [{self.lo}, {self.hi})")
+        if self.pos + n > self.hi:
+            self.pos = self.lo
+        s = self.pos
+        self.pos += n
+        return s, s + n
+
+
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region: NVML in a polling thread (2 ms period --
     the timed region is tens of milliseconds, too short for `nvidia-smi -lms`), nvidia-smi as the fallback."""
@@ -138,12 +157,14 @@ def run_reference(a):
     per_event = (time.perf_counter() - t0) / 256
     budget = 150.0 / max(a.steps + a.warmup, 1)
     sample_bs = int(min(a.bs, max(256, budget / per_event)))
-    pos = s0 + a.bs
+    cur = StreamCursor(s0 + a.bs, st.n_events)
     for _ in range(a.warmup):
-        tr.train_step(pos, pos + sample_bs); pos += a.bs
+        pos = cur.take(a.bs)[0]
+        tr.train_step(pos, pos + sample_bs)
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        tr.train_step(pos, pos + sample_bs); pos += a.bs
+        pos = cur.take(a.bs)[0]
+        tr.train_step(pos, pos + sample_bs)
     dt = time.perf_counter() - t0
     v = a.steps * sample_bs / dt
     sample = f"{a.steps} steps x first {sample_bs} events of each {a.bs}-event batch (after {a.warmup} warm-up)"
@@ -316,12 +337,11 @@ def main():
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    pos = [s0]
+    cur = StreamCursor(s0, st.n_events)
 
     def step(_i=None):
-        s = pos[0]
-        pos[0] += bs * world if world > 1 else bs
-        return tr.train_step(s, s + bs) if world == 1 else tr.train_step(s, s + bs * world)
+        s, e = cur.take(bs * world)                  # the GLOBAL batch; each rank embeds its slice of it
+        return tr.train_step(s, e)
 
     for _ in range(a.warmup):
         step()
@@ -354,7 +374,9 @@ def main():
 
     # ---- end-to-end through the public API with HOST buffers (H2D of the batch + D2H of the loss per step)
     e2e = None
-    host = tr.make_host_batches(pos[0], a.steps + 1, bs) if hasattr(tr, "make_host_batches") else None
+    host = None
+    if hasattr(tr, "make_host_batches"):             # one cursor position per batch (the cursor may wrap in between)
+        host = [tr.make_host_batches(cur.take(bs * world)[0], 1, bs)[0] for _ in range(a.steps + 1)]
     if host is not None:
         tr.train_step_host(host[0])                  # warm the path
         barrier()
@@ -404,13 +426,12 @@ def main():
     # ---- the same step at the scale configuration's batch size: what the kernels reach once a launch carries enough
     # rows to leave the latency regime (extra information; `value` above stays the bs-8192 headline)
     large = None
-    if a.large_bs > 0 and world == 1 and not a.no_profile and a.large_bs != bs and pos[0] + 14 * a.large_bs < st.n_events:
+    if a.large_bs > 0 and world == 1 and not a.no_profile and a.large_bs != bs and 2 * a.large_bs < st.n_events - s0:
         BL = a.large_bs
 
         def lstep(_i=None):
-            s = pos[0]
-            pos[0] += BL
-            return tr.train_step(s, s + BL)
+            s, e = cur.take(BL)
+            return tr.train_step(s, e)
 
         for _ in range(4):                           # two eager steps, capture, one replay
             lstep()
@@ -443,14 +464,13 @@ def main():
     eval_users = None
     if a.eval_steps > 0 and hasattr(tr, "eval_step") and (world == 1 or a.parallelism == "replicated"):
         ebs = a.eval_bs * world                      # global evaluation batch
-        p = pos[0]
         for _ in range(3):                           # two eager steps, then the graph is captured
-            tr.eval_step(p, p + ebs); p += ebs
+            tr.eval_step(*cur.take(ebs))
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(a.eval_steps):
-            tr.eval_step(p, p + ebs); p += ebs
+            tr.eval_step(*cur.take(ebs))
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -468,10 +488,12 @@ def main():
         otr = OracleTrainer(st, a.workload, bs=bs, n_layers=a.layers, n_neighbors=a.neighbors)
         sb = 1024
         otr.train_step(s0, s0 + sb)
+        ccur = StreamCursor(s0 + bs, st.n_events)
         t0 = time.perf_counter()
         n_cpu = 0
         while time.perf_counter() - t0 < 15.0:
-            otr.train_step(s0 + (n_cpu + 1) * bs, s0 + (n_cpu + 1) * bs + sb)
+            cs = ccur.take(bs)[0]
+            otr.train_step(cs, cs + sb)
             n_cpu += 1
         dt = time.perf_counter() - t0
         cpu = {"value": n_cpu * sb / dt, "unit": "events/s", "cores": torch.get_num_threads(), "kind": "port",

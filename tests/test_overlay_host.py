@@ -128,3 +128,18 @@ def test_reference_on_disk_format_round_trip(tmp_path):
     used = np.unique(st.day_idx)                  # day rows: same price rows for every interaction
     assert [rt.day_keys[i] for i in rt.day_idx[:50]] == [st.day_keys[i] for i in st.day_idx[:50]]
     assert np.array_equal(rt.prices_future[rt.day_idx], st.prices_future[st.day_idx]) and used.size > 0
+
+
+def test_bench_stream_cursor_wraps_inside_the_region():
+    """bench.py's batch positions: consecutive, inside [lo, hi), wrapping to lo instead of running past the end (an
+    8-GPU run with 65 536-event global batches needs more events than the stream holds after the start offset)."""
+    sys.path.insert(0, ROOT)
+    from bench import StreamCursor
+    c = StreamCursor(2_000_000, 5_000_000)
+    seen = [c.take(65536) for _ in range(120)]
+    assert all(2_000_000 <= s and e <= 5_000_000 and e - s == 65536 for s, e in seen)
+    assert seen[0] == (2_000_000, 2_065_536) and seen[1][0] == seen[0][1]
+    wraps = [i for i in range(1, 120) if seen[i][0] != seen[i - 1][1]]
+    assert wraps == [45, 90] and all(seen[i][0] == 2_000_000 for i in wraps)       # (5M - 2M) // 65536 = 45 batches per lap
+    with pytest.raises(SystemExit):
+        StreamCursor(0, 100).take(101)
