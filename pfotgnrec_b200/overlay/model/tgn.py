@@ -8,14 +8,8 @@ import logging
 import numpy as np
 import torch
 
-from utils.utils import MergeLayer
-from modules.memory import Memory
-from modules.message_aggregator import get_message_aggregator
-from modules.message_function import get_message_function
-from modules.memory_updater import get_memory_updater
-from modules.embedding_module import get_embedding_module
-from model.time_encoding import TimeEncode
-
+from pfotgnrec_b200.containers import (Memory, TimeEncode, get_embedding_module, get_memory_updater,
+                                       get_message_aggregator, get_message_function)
 from pfotgnrec_b200.engine import TGNEngine, ModelConfig
 from pfotgnrec_b200.graph import NeighborFinder, TemporalCSR
 
@@ -55,76 +49,55 @@ class TGN(torch.nn.Module):
                  use_destination_embedding_in_message=False,
                  use_source_embedding_in_message=False,
                  dyrep=False, gemm_mode="fp32"):
-        super(TGN, self).__init__()
+        super().__init__()
         if use_memory and not memory_update_at_start:
             raise NotImplementedError("memory_update_at_start=False is never executed by main.py")
         if aggregator_type not in ("last", "mean"):
             raise ValueError("Message aggregator {} not implemented".format(aggregator_type))
         if message_function not in ("identity", "mlp"):
             raise ValueError("Message function {} not implemented".format(message_function))
-
-        self.n_layers = n_layers
-        self.neighbor_finder = neighbor_finder
-        self.device = device
-        self.logger = logging.getLogger(__name__)
-
+        # feature tables on the device; edge features z-normalised over ALL rows, the padding row included (tgn.py:38-41)
+        ef = edge_features.astype(np.float32)
+        ef = (ef - ef.mean(axis=0)) / ef.std(axis=0)
         self.node_raw_features = torch.from_numpy(node_features.astype(np.float32)).to(device)
-        # z-normalise edge features over all rows, padding row included (reference tgn.py:38-41)
-        edge_features = edge_features.astype(np.float32)
-        edge_features -= edge_features.mean(axis=0)
-        edge_features /= edge_features.std(axis=0)
-        self.edge_raw_features = torch.from_numpy(edge_features.astype(np.float32)).to(device)
-
-        self.n_node_features = self.node_raw_features.shape[1]
-        self.n_nodes = self.node_raw_features.shape[0]
+        self.edge_raw_features = torch.from_numpy(ef.astype(np.float32)).to(device)
+        self.n_nodes, self.n_node_features = self.node_raw_features.shape
         self.n_edge_features = self.edge_raw_features.shape[1]
-        self.embedding_dimension = self.n_node_features
-        self.n_neighbors = n_neighbors
-        self.embedding_module_type = embedding_module_type
-        self.use_destination_embedding_in_message = use_destination_embedding_in_message
-        self.use_source_embedding_in_message = use_source_embedding_in_message
-        self.dyrep = dyrep
-        self.use_memory = use_memory
-        self.time_encoder = TimeEncode(dimension=self.n_node_features)
+        # plain attributes the callers (and checkpoints of the reference) know by name
+        for name, value in dict(n_layers=n_layers, neighbor_finder=neighbor_finder, device=device,
+                                logger=logging.getLogger(__name__), embedding_dimension=self.n_node_features,
+                                n_neighbors=n_neighbors, embedding_module_type=embedding_module_type,
+                                use_destination_embedding_in_message=use_destination_embedding_in_message,
+                                use_source_embedding_in_message=use_source_embedding_in_message, dyrep=dyrep,
+                                use_memory=use_memory, mean_time_shift_src=mean_time_shift_src,
+                                std_time_shift_src=std_time_shift_src, mean_time_shift_dst=mean_time_shift_dst,
+                                std_time_shift_dst=std_time_shift_dst).items():
+            setattr(self, name, value)
+        # sub-modules in the reference's construction order: the generator draws decide the initial weights
+        d = self.n_node_features
+        self.time_encoder = TimeEncode(dimension=d)
         self.memory = None
-        self.mean_time_shift_src = mean_time_shift_src
-        self.std_time_shift_src = std_time_shift_src
-        self.mean_time_shift_dst = mean_time_shift_dst
-        self.std_time_shift_dst = std_time_shift_dst
-
-        if self.use_memory:
-            if memory_dimension != self.n_node_features:
+        if use_memory:
+            if memory_dimension != d:
                 raise ValueError("memory_dimension must equal the node feature dimension (memory + features)")
-            self.memory_dimension = memory_dimension
-            self.memory_update_at_start = memory_update_at_start
-            raw_message_dimension = 2 * self.memory_dimension + self.n_edge_features + self.time_encoder.dimension
-            message_dimension = message_dimension if message_function != "identity" else raw_message_dimension
-            self.memory = Memory(n_nodes=self.n_nodes, memory_dimension=self.memory_dimension,
-                                 input_dimension=message_dimension, message_dimension=message_dimension,
-                                 device=device, n_edge_features=self.n_edge_features)
+            self.memory_dimension, self.memory_update_at_start = memory_dimension, memory_update_at_start
+            raw_dim = 2 * memory_dimension + self.n_edge_features + self.time_encoder.dimension
+            message_dimension = raw_dim if message_function == "identity" else message_dimension
+            self.memory = Memory(n_nodes=self.n_nodes, memory_dimension=memory_dimension, input_dimension=message_dimension,
+                                 message_dimension=message_dimension, device=device,
+                                 n_edge_features=self.n_edge_features)
             self.message_aggregator = get_message_aggregator(aggregator_type=aggregator_type, device=device)
-            self.message_function = get_message_function(module_type=message_function,
-                                                          raw_message_dimension=raw_message_dimension,
+            self.message_function = get_message_function(module_type=message_function, raw_message_dimension=raw_dim,
                                                           message_dimension=message_dimension)
             self.memory_updater = get_memory_updater(module_type=memory_updater_type, memory=self.memory,
                                                      message_dimension=message_dimension,
-                                                     memory_dimension=self.memory_dimension, device=device)
-
-        self.embedding_module = get_embedding_module(module_type=embedding_module_type,
-                                                     node_features=self.node_raw_features,
-                                                     edge_features=self.edge_raw_features,
-                                                     memory=self.memory,
-                                                     neighbor_finder=self.neighbor_finder,
-                                                     time_encoder=self.time_encoder,
-                                                     n_layers=self.n_layers,
-                                                     n_node_features=self.n_node_features,
-                                                     n_edge_features=self.n_edge_features,
-                                                     n_time_features=self.n_node_features,
-                                                     embedding_dimension=self.embedding_dimension,
-                                                     device=self.device,
-                                                     n_heads=n_heads, dropout=dropout,
-                                                     use_memory=use_memory,
-                                                     n_neighbors=self.n_neighbors)
+                                                     memory_dimension=memory_dimension, device=device)
+        self.embedding_module = get_embedding_module(
+            module_type=embedding_module_type, node_features=self.node_raw_features,
+            edge_features=self.edge_raw_features, memory=self.memory, neighbor_finder=neighbor_finder,
+            time_encoder=self.time_encoder, n_layers=n_layers, n_node_features=d,
+            n_edge_features=self.n_edge_features, n_time_features=d, embedding_dimension=d, device=device,
+            n_heads=n_heads, dropout=dropout, use_memory=use_memory, n_neighbors=n_neighbors)
         self._cfg = ModelConfig(d=self.n_node_features, n_edge_feat=self.n_edge_features, n_layers=n_layers,
                                 n_heads=n_heads, use_memory=use_memory, updater=memory_updater_type,
                                 embedding=embedding_module_type, dyrep=dyrep,

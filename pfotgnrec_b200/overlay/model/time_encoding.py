@@ -1,17 +1,5 @@
-"""Drop-in for reference model/time_encoding.py: parameter container of cos(t*w+b).
-The encoding itself is fused into the message-store and attention kernels (fmaf + cosf)."""
-import numpy as np
-import torch
-
-
-class TimeEncode(torch.nn.Module):
-    def __init__(self, dimension):
-        super(TimeEncode, self).__init__()
-        self.dimension = dimension
-        self.w = torch.nn.Linear(1, dimension)      # drawn, then overwritten: keeps the RNG stream of the reference
-        self.w.weight = torch.nn.Parameter((torch.from_numpy(1 / 10 ** np.linspace(0, 9, dimension)))
-                                           .float().reshape(dimension, -1))
-        self.w.bias = torch.nn.Parameter(torch.zeros(dimension).float())
-
-    def forward(self, t):
-        raise NotImplementedError("TimeEncode is evaluated inside the fused CUDA kernels")
+"""Module path of reference model/time_encoding.py in the drop-in overlay: re-exports the parameter containers of
+pfotgnrec_b200/containers.py (the arithmetic runs in libpfo_b200.so behind TGN.compute_temporal_embeddings*)."""
+from pfotgnrec_b200.containers import (  # noqa: F401
+    TimeEncode,
+)

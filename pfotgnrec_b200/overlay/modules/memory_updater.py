@@ -1,44 +1,9 @@
-"""Drop-in for reference modules/memory_updater.py: parameter containers (torch GRUCell / RNNCell
-hold the weights, same init order); the update runs lazily on the touched nodes in the fused path."""
-from torch import nn
-import torch
-
-
-class MemoryUpdater(nn.Module):
-    def update_memory(self, unique_node_ids, unique_messages, timestamps):
-        pass
-
-
-class SequenceMemoryUpdater(MemoryUpdater):
-    def __init__(self, memory, message_dimension, memory_dimension, device):
-        super(SequenceMemoryUpdater, self).__init__()
-        self.memory = memory
-        self.layer_norm = torch.nn.LayerNorm(memory_dimension)   # present but never applied (reference :14)
-        self.message_dimension = message_dimension
-        self.device = device
-
-    def update_memory(self, unique_node_ids, unique_messages, timestamps):
-        raise NotImplementedError("memory is persisted inside TGN.compute_temporal_embeddings*")
-
-    def get_updated_memory(self, unique_node_ids, unique_messages, timestamps):
-        raise NotImplementedError("memory is updated lazily inside TGN.compute_temporal_embeddings*")
-
-
-class GRUMemoryUpdater(SequenceMemoryUpdater):
-    def __init__(self, memory, message_dimension, memory_dimension, device):
-        super(GRUMemoryUpdater, self).__init__(memory, message_dimension, memory_dimension, device)
-        self.memory_updater = nn.GRUCell(input_size=message_dimension, hidden_size=memory_dimension)
-
-
-class RNNMemoryUpdater(SequenceMemoryUpdater):
-    def __init__(self, memory, message_dimension, memory_dimension, device):
-        super(RNNMemoryUpdater, self).__init__(memory, message_dimension, memory_dimension, device)
-        self.memory_updater = nn.RNNCell(input_size=message_dimension, hidden_size=memory_dimension)
-
-
-def get_memory_updater(module_type, memory, message_dimension, memory_dimension, device):
-    if module_type == "gru":
-        return GRUMemoryUpdater(memory, message_dimension, memory_dimension, device)
-    elif module_type == "rnn":
-        return RNNMemoryUpdater(memory, message_dimension, memory_dimension, device)
-    raise ValueError("Memory updater {} not implemented".format(module_type))
+"""Module path of reference modules/memory_updater.py in the drop-in overlay: re-exports the parameter containers of
+pfotgnrec_b200/containers.py (the arithmetic runs in libpfo_b200.so behind TGN.compute_temporal_embeddings*)."""
+from pfotgnrec_b200.containers import (  # noqa: F401
+    MemoryUpdater,
+    SequenceMemoryUpdater,
+    GRUMemoryUpdater,
+    RNNMemoryUpdater,
+    get_memory_updater,
+)

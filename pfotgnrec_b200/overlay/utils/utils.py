@@ -10,54 +10,38 @@ import torch
 from pfotgnrec_b200 import _lib
 from pfotgnrec_b200.graph import NeighborFinder, TemporalCSR, get_neighbor_finder as _gnf
 from pfotgnrec_b200.sampler import CandidateSampler
-
-
-class MergeLayer(torch.nn.Module):
-    """Parameter container of fc2(relu(fc1([x1 | x2]))) (reference utils/utils.py:4-17).
-    The arithmetic runs inside the fused attention path (pfo_linear_*); same init order."""
-
-    def __init__(self, dim1, dim2, dim3, dim4):
-        super().__init__()
-        self.fc1 = torch.nn.Linear(dim1 + dim2, dim3)
-        self.fc2 = torch.nn.Linear(dim3, dim4)
-        self.act = torch.nn.ReLU()
-        torch.nn.init.xavier_normal_(self.fc1.weight)
-        torch.nn.init.xavier_normal_(self.fc2.weight)
-
-    def forward(self, x1, x2):
-        raise NotImplementedError("MergeLayer is evaluated inside TGN.compute_temporal_embeddings*")
+from pfotgnrec_b200.containers import MergeLayer  # noqa: F401  (reference utils/utils.py:4-17)
 
 
 class MLP(torch.nn.Module):
-    """Importable name only (reference utils/utils.py:19-35; never called by main.py)."""
+    """Importable name only (reference utils/utils.py:19-35 is imported by main.py:7 and never called)."""
 
     def __init__(self, dim, drop=0.3):
         super().__init__()
-        self.fc_1 = torch.nn.Linear(dim, 80)
-        self.fc_2 = torch.nn.Linear(80, 10)
-        self.fc_3 = torch.nn.Linear(10, 1)
-        self.act = torch.nn.ReLU()
-        self.dropout = torch.nn.Dropout(p=drop, inplace=False)
+        self.fc_1, self.fc_2, self.fc_3 = torch.nn.Linear(dim, 80), torch.nn.Linear(80, 10), torch.nn.Linear(10, 1)
+        self.act, self.dropout = torch.nn.ReLU(), torch.nn.Dropout(p=drop, inplace=False)
 
     def forward(self, x):
         raise NotImplementedError("MLP is not on the PfoTGNRec hot path")
 
 
 class EarlyStopMonitor(object):
-    """Reference utils/utils.py:38-62 (host-side bookkeeping)."""
+    """Patience counter with the interface of reference utils/utils.py:38-62 (imported by main.py:7, never called):
+    `early_stop_check(value)` is True once `max_round` consecutive values failed to improve on the best one by
+    more than `tolerance` (relative)."""
 
     def __init__(self, max_round=3, higher_better=True, tolerance=1e-10):
-        self.max_round, self.num_round = max_round, 0
-        self.epoch_count, self.best_epoch = 0, 0
-        self.last_best, self.higher_better, self.tolerance = None, higher_better, tolerance
+        self.max_round, self.higher_better, self.tolerance = max_round, higher_better, tolerance
+        self.num_round = self.epoch_count = self.best_epoch = 0
+        self.last_best = None
 
     def early_stop_check(self, curr_val):
-        if not self.higher_better:
-            curr_val *= -1
+        val = curr_val if self.higher_better else -curr_val
+        improved = self.last_best is not None and (val - self.last_best) / np.abs(self.last_best) > self.tolerance
         if self.last_best is None:
-            self.last_best = curr_val
-        elif (curr_val - self.last_best) / np.abs(self.last_best) > self.tolerance:
-            self.last_best, self.num_round, self.best_epoch = curr_val, 0, self.epoch_count
+            self.last_best = val
+        elif improved:
+            self.last_best, self.num_round, self.best_epoch = val, 0, self.epoch_count
         else:
             self.num_round += 1
         self.epoch_count += 1

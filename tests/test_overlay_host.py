@@ -143,3 +143,26 @@ def test_bench_stream_cursor_wraps_inside_the_region():
     assert wraps == [45, 90] and all(seen[i][0] == 2_000_000 for i in wraps)       # (5M - 2M) // 65536 = 45 batches per lap
     with pytest.raises(SystemExit):
         StreamCursor(0, 100).take(101)
+
+
+@pytest.mark.parametrize("tag", ["ours", "tgn", "jodie", "dyrep", "tgat2", "mlp_mean", "srcemb", "gsum", "gsum2"])
+def test_engine_binds_every_parameter_of_every_config(overlay, tag):
+    """Host-side plumbing between the drop-in TGN and the step engine, no kernel launched: the engine is built from
+    the overlay model's configuration and every parameter it packs for the kernels exists under the reference's name
+    (a renamed container attribute would only surface on the GPU otherwise)."""
+    tgn_mod, _ = overlay
+    z = load_golden(f"tgn_{tag}.npz")
+    tgn = _build(tgn_mod, z)
+    eng = tgn._get_engine()
+    params = tgn._params()
+    names = eng.param_names()
+    assert all(n in params for n in names), [n for n in names if n not in params]
+    flat = eng._pack(params)
+    assert len(flat) == len(names) and all(t.dtype == torch.float32 for t in flat)
+    assert eng.cfg.embedding == str(z["cfg_embedding"]) and eng.cfg.use_memory == bool(z["cfg_use_memory"])
+    if "cfg_msg_fn" in z:
+        assert eng.cfg.message_fn == (str(z["cfg_msg_fn"]) if eng.cfg.use_memory else "identity")
+        assert eng.cfg.aggregator == str(z["cfg_aggregator"])
+    trainable = {k for k, p in tgn.named_parameters() if p.requires_grad}
+    unused = {"memory_updater.layer_norm.weight", "memory_updater.layer_norm.bias"}       # never applied (reference too)
+    assert trainable - unused <= set(names) | {n.replace(".mlp.", ".layers.") for n in names}
