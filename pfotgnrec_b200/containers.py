@@ -295,20 +295,28 @@ class GraphEmbedding(EmbeddingModule):
 class GraphSumEmbedding(GraphEmbedding):
     """linear_1 over [h_nbr | te | e] summed over the slots, linear_2 over [sum | h_q | te(0)] (TGNEngine._sum_forward)."""
 
-    def __init__(self, *args, **kwargs):
-        super().__init__(*args, **kwargs)
-        d, dn, dt, de = (self.embedding_dimension, self.n_node_features, self.n_time_features, self.n_edge_features)
-        self.linear_1 = nn.ModuleList([nn.Linear(d + dt + de, d) for _ in range(self.n_layers)])
-        self.linear_2 = nn.ModuleList([nn.Linear(d + dn + dt, d) for _ in range(self.n_layers)])
+    def __init__(self, node_features, edge_features, memory, neighbor_finder, time_encoder, n_layers,
+                 n_node_features, n_edge_features, n_time_features, embedding_dimension, device,
+                 n_heads=2, dropout=0.1, use_memory=True):
+        super().__init__(node_features, edge_features, memory, neighbor_finder, time_encoder, n_layers,
+                         n_node_features, n_edge_features, n_time_features, embedding_dimension, device,
+                         n_heads, dropout, use_memory)
+        d = embedding_dimension
+        self.linear_1 = nn.ModuleList([nn.Linear(d + n_time_features + n_edge_features, d) for _ in range(n_layers)])
+        self.linear_2 = nn.ModuleList([nn.Linear(d + n_node_features + n_time_features, d) for _ in range(n_layers)])
 
 
 class GraphAttentionEmbedding(GraphEmbedding):
-    def __init__(self, *args, n_heads=2, dropout=0.1, **kwargs):
-        super().__init__(*args, n_heads=n_heads, dropout=dropout, **kwargs)
+    def __init__(self, node_features, edge_features, memory, neighbor_finder, time_encoder, n_layers,
+                 n_node_features, n_edge_features, n_time_features, embedding_dimension, device,
+                 n_heads=2, dropout=0.1, use_memory=True):
+        super().__init__(node_features, edge_features, memory, neighbor_finder, time_encoder, n_layers,
+                         n_node_features, n_edge_features, n_time_features, embedding_dimension, device,
+                         n_heads, dropout, use_memory)
         self.attention_models = nn.ModuleList([TemporalAttentionLayer(
-            n_node_features=self.n_node_features, n_neighbors_features=self.n_node_features,
-            n_edge_features=self.n_edge_features, time_dim=self.n_time_features, n_head=n_heads, dropout=dropout,
-            output_dimension=self.n_node_features) for _ in range(self.n_layers)])
+            n_node_features=n_node_features, n_neighbors_features=n_node_features, n_edge_features=n_edge_features,
+            time_dim=n_time_features, n_head=n_heads, dropout=dropout, output_dimension=n_node_features)
+            for _ in range(n_layers)])
 
 
 def get_embedding_module(module_type, node_features, edge_features, memory, neighbor_finder,
