@@ -51,6 +51,12 @@ def parse():
                          "under `large_batch`: at bs 8192 every kernel runs 10-40 us and is bound by launch / pipeline-fill "
                          "latency, not by HBM; 0 disables")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-kind", default="auto", choices=["auto", "port"],
+                    help="--impl reference: auto = the unmodified reference when its tree is staged, else the oracle port")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="--impl reference: seconds for the timed + warm-up steps")
+    ap.add_argument("--eval-budget", type=float, default=30.0, help="--impl reference: seconds for the evaluation sample")
+    ap.add_argument("--cpu-budget", type=float, default=30.0,
+                    help="seconds of reference steps for the GPU arm's cpu_baseline (run as a subprocess of --impl reference)")
     ap.add_argument("--no-profile", action="store_true")
     return ap.parse_args()
 
@@ -140,41 +146,124 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
 
 
+def _fit_line(t_small, n_small, t_big, n_big):
+    """Seconds per batch = c0 + c1 * events, from two probe steps."""
+    c1 = max((t_big - t_small) / (n_big - n_small), 1e-7)
+    return max(t_small - c1 * n_small, 0.0), c1
+
+
 def run_reference(a):
-    """The reference algorithm on the host cores: the oracle port (oracle/train_loop.py).  The reference
-    itself is pure Python and cannot travel to the GPU box (no /root/reference there); see DESIGN.md."""
+    """The reference arm: the UNMODIFIED reference (baseline/_ref, staged by baseline/stage_reference.py; its own TGN,
+    NeighborFinder, RandEdgeSampler and the text of main.py:167-394 as the step, evaluation.py:39-258 as the evaluation)
+    on the host cores, kind "reference".  Only when no reference tree is present does it fall back to the oracle port
+    (oracle/train_loop.py, kind "port").  Each step is a bounded sample -- the first `sample_bs` interactions of the
+    config's batch -- sized from two probe steps so that the run ends within `--ref-budget` seconds."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.train_loop import OracleTrainer
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    from stage_reference import ref_root
     torch.set_num_threads(os.cpu_count())
     st = make_data(a)
-    tr = OracleTrainer(st, a.workload, bs=a.bs, n_layers=a.layers, n_neighbors=a.neighbors)
+    root = ref_root()
+    kind = "reference" if root is not None and a.ref_kind != "port" else "port"
+    t_init = time.perf_counter()
+    if kind == "reference":
+        from ref_harness import ReferenceRunner
+        runner = ReferenceRunner(st, a.workload, bs=a.bs, n_layers=a.layers, n_neighbors=a.neighbors,
+                                 dropout=a.dropout, threads=os.cpu_count())
+        one = lambda pos, n: runner.train_step(pos // n * n, n)
+    else:
+        from oracle.train_loop import OracleTrainer
+        runner = OracleTrainer(st, a.workload, bs=a.bs, n_layers=a.layers, n_neighbors=a.neighbors)
+        one = lambda pos, n: runner.train_step(pos, pos + n)
+    t_init = time.perf_counter() - t_init
     s0 = int(st.n_events * 0.4)
-    # bounded sample: the step is the first `sample_bs` events of each batch, sized from a probe step
-    t0 = time.perf_counter()
-    tr.train_step(s0, s0 + 256)
-    per_event = (time.perf_counter() - t0) / 256
-    budget = 150.0 / max(a.steps + a.warmup, 1)
-    sample_bs = int(min(a.bs, max(256, budget / per_event)))
-    cur = StreamCursor(s0 + a.bs, st.n_events)
-    for _ in range(a.warmup):
+    # positions only move forward: the reference asserts that memory is never updated to a time in the past
+    # (modules/memory_updater.py:25); if the cursor ever wraps, the memory is re-initialised like at an epoch start
+    probes, p = [], s0
+    hi = int(st.n_events * 0.78)
+    n_a = int(max(8, min(256, (hi - s0) // 20)))     # two probe sizes; tiny test streams shrink them
+    n_b = 4 * n_a
+    for n in (n_a, n_b):
+        one(p, n)                                    # first touch at this size (allocations, lazy portfolios)
+        p += n
+        t0 = time.perf_counter()
+        one(p, n)
+        probes.append(time.perf_counter() - t0)
+        p += n
+    c0, c1 = _fit_line(probes[0], n_a, probes[1], n_b)
+    budget = float(a.ref_budget) / max(a.steps + a.warmup, 1)
+    sample_bs = int(min(a.bs, max(min(256, a.bs), (budget - c0) / c1)))
+    cur = StreamCursor(p, hi)
+    last = [p]
+
+    def step():
         pos = cur.take(a.bs)[0]
-        tr.train_step(pos, pos + sample_bs)
+        if pos < last[0] and hasattr(runner, "reset_memory"):
+            runner.reset_memory()
+        last[0] = pos
+        one(pos, sample_bs)
+
+    for _ in range(a.warmup):
+        step()
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        pos = cur.take(a.bs)[0]
-        tr.train_step(pos, pos + sample_bs)
+        step()
     dt = time.perf_counter() - t0
     v = a.steps * sample_bs / dt
-    sample = f"{a.steps} steps x first {sample_bs} events of each {a.bs}-event batch (after {a.warmup} warm-up)"
+    sample = (f"{a.steps} steps x first {sample_bs} interactions of each {a.bs}-interaction batch (after {a.warmup} warm-up "
+              f"steps); step = main.py:167-394 verbatim" if kind == "reference" else
+              f"{a.steps} steps x first {sample_bs} events of each {a.bs}-event batch (after {a.warmup} warm-up)")
+    ev = None
+    if a.eval_steps > 0 and kind == "reference":
+        # evaluation.py:39-258 on the full graph, all-stock ranking + metric block: a bounded number of users
+        e0 = int(st.n_events * 0.9)
+        ub = 16
+        _, users, t1 = runner.evaluate(e0, e0 + 2 * ub + 1, ub)          # probe (builds the full-graph finder first)
+        per_user = t1 / max(users, 1)
+        nb = int(max(2, min(64, float(a.eval_budget) / max(per_user * ub, 1e-6))))
+        _, users, t1 = runner.evaluate(e0 + 4 * ub, e0 + 4 * ub + nb * ub + 1, ub)
+        ev = {"metric": "eval_users_per_sec", "value": users / t1, "unit": "users/s", "n_items": a.items,
+              "cpu_baseline": {"value": users / t1, "unit": "users/s", "cores": torch.get_num_threads(), "kind": kind,
+                               "sample": f"{users} users in batches of {ub} through evaluation.py:39-258 "
+                                         f"(full-graph finder, ranking over all {a.items} stocks, metric block)"}}
     print(json.dumps({"impl": "reference", "metric": "train_events_per_sec", "value": v, "unit": "events/s",
                       "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                      "data": "synthetic", "config": {"workload": workload_name(a), "sample": sample},
+                      "data": "synthetic", "config": base_config(a, a.gpus),
                       "cpu_baseline": {"value": v, "unit": "events/s", "cores": torch.get_num_threads(),
-                                       "kind": "port", "sample": sample},
-                      "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                                       "kind": kind, "sample": sample,
+                                       "reference_tree": root, "init_s": t_init,
+                                       "threads_note": "the reference's Python loops are single-threaded; torch / BLAS ops "
+                                                       "use all cores"},
+                      "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "eval": ev}))
+
+
+def cpu_baseline_subprocess(a):
+    """cpu_baseline of the GPU arm: the reference arm above in its OWN process (the drop-in overlay and the reference
+    share module paths, so they cannot live in one interpreter), with a short budget.  Returns the parsed JSON line."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "6", "--warmup", "1",
+           "--ref-budget", str(a.cpu_budget), "--eval-budget", str(a.cpu_budget / 2), "--workload", a.workload,
+           "--bs", str(a.bs), "--layers", str(a.layers), "--neighbors", str(a.neighbors), "--users", str(a.users),
+           "--items", str(a.items), "--events", str(a.events), "--days", str(a.days), "--dropout", str(a.dropout),
+           "--eval-steps", str(a.eval_steps)]
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+        line = [l for l in p.stdout.strip().split("\n") if l.startswith("{")][-1]
+        return json.loads(line)
+    except Exception as exc:                         # the baseline is a reported figure: never fail the GPU line on it
+        return {"error": f"{type(exc).__name__}: {exc}"}
+
+
+def base_config(a, world):
+    """The part of `config` both arms share: what is computed, not how."""
+    return {"workload": workload_name(a), "global_batch": a.bs * max(int(world), 1), "dropout": a.dropout,
+            "eval": f"full ranking over all {a.items} stocks + metric block (Recall/NDCG, delta-return/delta-Sharpe @1,3,5)"}
 
 
 def algorithmic_work(name, args, n_uniq, extra):
@@ -461,7 +550,7 @@ def main():
                  "note": "same model, stream and timing rules at BASELINE config 4's batch size (graph replay, L2 flushed)"}
 
     # ---- eval users/sec (the second half of the metric): full ranking over all stocks, users split over the ranks
-    eval_users = None
+    eval_users, eval_roofline = None, None
     if a.eval_steps > 0 and hasattr(tr, "eval_step") and (world == 1 or a.parallelism == "replicated"):
         ebs = a.eval_bs * world                      # global evaluation batch
         for _ in range(3):                           # two eager steps, then the graph is captured
@@ -479,43 +568,52 @@ def main():
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
             ms = float(t.item())
         eval_users = a.eval_steps * ebs / (ms * 1e-3)
+        if world == 1 and not a.no_profile and rooflines is not None:
+            # per-kernel rooflines of the evaluation step (Q = users x (2 + N_ITEMS) queries), eager pass like the training one
+            graph_mode, tr.tc.cuda_graph = tr.tc.cuda_graph, False
+            try:
+                eagg = profile_kernels(lambda _i: tr.eval_step(*cur.take(ebs)), 2,
+                                       lambda: int(tr.tgn.memory.state.n_unique.item()) if tr.tgn.use_memory else 0, extra)
+            finally:
+                tr.tc.cuda_graph = graph_mode
+            etot = sum(v["ms"] for v in eagg.values())
+            for k, v in sorted(eagg.items(), key=lambda kv: -kv[1]["ms"]):
+                r = roofline_of(k, v, peaks, a.gemm, {})
+                if r is not None:
+                    r["share_of_step"] = v["ms"] / etot
+                    r["ms_per_step"] = v["ms"] / 2
+                    eval_roofline = r
+                    break
 
-    # ---- CPU baseline (oracle port) on the host cores, bounded sample, rank 0 only
-    cpu = None
+    # ---- CPU baseline: the unmodified reference on the host cores (its own process), bounded sample, rank 0 only
+    cpu, eval_cpu = None, None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        from oracle.train_loop import OracleTrainer
-        torch.set_num_threads(os.cpu_count())
-        otr = OracleTrainer(st, a.workload, bs=bs, n_layers=a.layers, n_neighbors=a.neighbors)
-        sb = 1024
-        otr.train_step(s0, s0 + sb)
-        ccur = StreamCursor(s0 + bs, st.n_events)
-        t0 = time.perf_counter()
-        n_cpu = 0
-        while time.perf_counter() - t0 < 15.0:
-            cs = ccur.take(bs)[0]
-            otr.train_step(cs, cs + sb)
-            n_cpu += 1
-        dt = time.perf_counter() - t0
-        cpu = {"value": n_cpu * sb / dt, "unit": "events/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"{n_cpu} steps x first {sb} events of a {bs}-event batch, ~15 s, after 1 warm-up step"}
+        ref = cpu_baseline_subprocess(a)
+        cpu = ref.get("cpu_baseline") or ref
+        eval_cpu = (ref.get("eval") or {}).get("cpu_baseline")
 
     if rank == 0:
+        ran_graph = bool(getattr(tr, "_graph_ok", lambda _b: False)(bs))
+        cfg = base_config(a, world)
+        cfg.update({"l2": "flushed between timed steps (256 MiB write)",
+                    "parallelism": "1 GPU" if world == 1 else (f"node-sharded x{world}" if a.parallelism == "sharded"
+                                                               else f"replicated state, data-parallel x{world}"),
+                    "timing": "sum of per-step CUDA-event durations, max over ranks",
+                    "gemm_mode": a.gemm, "cuda_graph": ran_graph})
+        ev_block = None
+        if eval_users is not None:
+            ev_block = {"metric": "eval_users_per_sec", "value": eval_users, "unit": "users/s", "n_items": a.items,
+                        "users_per_batch": a.eval_bs * world, "steps": a.eval_steps, "roofline": eval_roofline,
+                        "cpu_baseline": eval_cpu,
+                        "note": "full ranking over all stocks per user (evaluation.py:84-138) + metric block (:127-258), "
+                                "graph-replayed, CUDA events, max over ranks"}
         out = {"metric": "train_events_per_sec", "value": value, "unit": "events/s", "n_gpus": world,
                "steps": a.steps, "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if a.gemm == "fp32" else "bf16",
-               "data": "synthetic",
-               "config": {"workload": workload_name(a), "l2": "flushed between timed steps (256 MiB write)",
-                          "global_batch": events_per_step,
-                          "parallelism": "1 GPU" if world == 1 else (f"node-sharded x{world}" if a.parallelism == "sharded"
-                                                                     else f"replicated state, data-parallel x{world}"),
-                          "timing": "sum of per-step CUDA-event durations, max over ranks"},
+               "data": "synthetic", "config": cfg,
                "clocks": clk, "e2e": e2e, "gpu_launches": launches, "wall_s": wall,
-               "roofline": roofline, "cpu_baseline": cpu, "eval_users_per_sec": eval_users, "kernels": kernels,
-               "rooflines": rooflines, "large_batch": large}
-        out["config"].update({"dropout": a.dropout, "gemm_mode": a.gemm,
-                              "cuda_graph": bool(tc.cuda_graph and (world == 1 or a.parallelism == "replicated")),
-                              "eval": f"full ranking over all {a.items} stocks, {a.eval_bs} users per batch, metric block "
-                                      "(Recall/NDCG and delta-return/delta-Sharpe @1,3,5) on the device"})
+               "roofline": roofline, "cpu_baseline": cpu, "eval": ev_block, "eval_users_per_sec": eval_users,
+               "kernels": kernels, "rooflines": rooflines, "large_batch": large}
         print(json.dumps(out))
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -17,8 +17,14 @@ import types
 import numpy as np
 import torch
 
-REF = "/root/reference"
-OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "baseline"))
+from stage_reference import ref_root      # noqa: E402
+
+# /root/reference in the build container (the committed goldens come from there); the staged byte-for-byte copy
+# baseline/_ref on the GPU box (only `--device cuda`, the side-by-side run of tests/test_gpu_reference.py, uses it)
+REF = ref_root() or "/root/reference"
+OUT = os.path.join(ROOT, "tests", "golden")
 
 
 def _import_reference():
@@ -62,7 +68,7 @@ def golden_neighbors(get_neighbor_finder):
 
 def _run_model(TGN, get_neighbor_finder, tag, *, d, n_layers, n_neighbors, use_memory, updater,
                embedding, dyrep, dst_emb, ts_mode, with_ppos, B=24, n_batches=4, n_neg=3, seed=11,
-               msg_fn="identity", aggregator="last", src_emb=False):
+               msg_fn="identity", aggregator="last", src_emb=False, device="cpu", out_dir=None):
     from pfotgnrec_b200.synth import make_stream
     st = make_stream(n_users=40, n_items=12, n_events=B * n_batches + 40, n_days=10, seed=seed,
                      ts_mode=ts_mode, with_prices=False)
@@ -72,7 +78,7 @@ def _run_model(TGN, get_neighbor_finder, tag, *, d, n_layers, n_neighbors, use_m
     nf = get_neighbor_finder(_data(st), uniform=False, max_node_idx=st.n_nodes - 1)
     shift = (3.0, 7.0, 2.0, 5.0)
     tgn = TGN(neighbor_finder=nf, node_features=node_feat, edge_features=st.edge_features.copy(),
-              device=torch.device("cpu"), n_layers=n_layers, n_heads=2, dropout=0.0,
+              device=torch.device(device), n_layers=n_layers, n_heads=2, dropout=0.0,
               use_memory=use_memory, message_dimension=100, memory_dimension=d,
               memory_update_at_start=True, embedding_module_type=embedding,
               message_function=msg_fn, aggregator_type=aggregator, memory_updater_type=updater,
@@ -80,6 +86,7 @@ def _run_model(TGN, get_neighbor_finder, tag, *, d, n_layers, n_neighbors, use_m
               mean_time_shift_dst=shift[2], std_time_shift_dst=shift[3],
               use_destination_embedding_in_message=dst_emb, use_source_embedding_in_message=src_emb,
               dyrep=dyrep)
+    tgn = tgn.to(torch.device(device))              # main.py:124
     tgn.train()
     out = {"cfg_" + k: v for k, v in dict(d=d, n_layers=n_layers, n_neighbors=n_neighbors,
                                           use_memory=int(use_memory), B=B, n_batches=n_batches,
@@ -91,7 +98,7 @@ def _run_model(TGN, get_neighbor_finder, tag, *, d, n_layers, n_neighbors, use_m
     skip = ("memory.memory", "memory.last_update", "memory_updater.memory.", "embedding_module.memory.")
     for k, v in tgn.state_dict().items():
         if not any(k.startswith(s) or k == s for s in skip):
-            out["w_" + k] = v.detach().numpy().copy()
+            out["w_" + k] = v.detach().cpu().numpy().copy()
     out["node_feat"] = node_feat
     for k in ("sources", "destinations", "edge_idxs", "timestamps", "edge_features"):
         out["st_" + k] = getattr(st, k)
@@ -109,7 +116,7 @@ def _run_model(TGN, get_neighbor_finder, tag, *, d, n_layers, n_neighbors, use_m
             ppos = rng.integers(st.n_users + 1, st.n_nodes, size=B)
             e_s, e_d, e_p, e_n = tgn.compute_temporal_embeddings_p(src, dst, ppos, neg, ts, ei, n_neighbors)
             out[f"b{bi}_ppos"] = ppos
-            out[f"b{bi}_emb_ppos"] = e_p.detach().numpy().copy()
+            out[f"b{bi}_emb_ppos"] = e_p.detach().cpu().numpy().copy()
         else:
             e_s, e_d, e_n = tgn.compute_temporal_embeddings(src, dst, neg, ts, ei, n_neighbors)
             e_p = e_d
@@ -119,22 +126,22 @@ def _run_model(TGN, get_neighbor_finder, tag, *, d, n_layers, n_neighbors, use_m
         pos_scores = torch.sum(s_ * e_p.view(bs, 1, -1), dim=2)
         neg_scores = torch.matmul(s_, e_n.view(bs, n_neg, -1).transpose(1, 2)).squeeze()
         loss = -torch.mean(torch.log(torch.sigmoid(torch.mean(pos_scores - neg_scores, dim=1))))
-        if dyrep:
+        if dyrep or not loss.requires_grad:     # main.py:386-387; the identity embedding of batch 0 is plain zero memory
             loss.requires_grad_()
         loss.backward()
         if use_memory:
             tgn.memory.detach_memory()
         out[f"b{bi}_neg"] = neg
-        out[f"b{bi}_emb_src"] = e_s.detach().numpy().copy()
-        out[f"b{bi}_emb_dst"] = e_d.detach().numpy().copy()
-        out[f"b{bi}_emb_neg"] = e_n.detach().numpy().copy()
+        out[f"b{bi}_emb_src"] = e_s.detach().cpu().numpy().copy()
+        out[f"b{bi}_emb_dst"] = e_d.detach().cpu().numpy().copy()
+        out[f"b{bi}_emb_neg"] = e_n.detach().cpu().numpy().copy()
         out[f"b{bi}_loss"] = float(loss.item())
         for k, p in zip(names, params):
-            out[f"b{bi}_g_{k}"] = (p.grad.detach().numpy().copy() if p.grad is not None
+            out[f"b{bi}_g_{k}"] = (p.grad.detach().cpu().numpy().copy() if p.grad is not None
                                    else np.zeros(tuple(p.shape), dtype=np.float32))
         if use_memory:
-            out[f"b{bi}_memory"] = tgn.memory.memory.detach().numpy().copy()
-            out[f"b{bi}_last_update"] = tgn.memory.last_update.detach().numpy().copy()
+            out[f"b{bi}_memory"] = tgn.memory.memory.detach().cpu().numpy().copy()
+            out[f"b{bi}_last_update"] = tgn.memory.last_update.detach().cpu().numpy().copy()
             N = st.n_nodes
             raw = 3 * d + st.edge_features.shape[1]
             pv = np.zeros(N, dtype=bool)
@@ -144,10 +151,10 @@ def _run_model(TGN, get_neighbor_finder, tag, *, d, n_layers, n_neighbors, use_m
                 if len(lst) > 0:
                     pv[node] = True
                     pm[node] = (lst[-1][0] if aggregator == "last" else
-                                torch.mean(torch.stack([m[0] for m in lst]), dim=0)).detach().numpy()
+                                torch.mean(torch.stack([m[0] for m in lst]), dim=0)).detach().cpu().numpy()
                     pt[node] = float(lst[-1][1])
             out[f"b{bi}_pend_valid"], out[f"b{bi}_pend_msg"], out[f"b{bi}_pend_ts"] = pv, pm, pt
-    np.savez_compressed(os.path.join(OUT, f"tgn_{tag}.npz"), **out)
+    np.savez_compressed(os.path.join(out_dir or OUT, f"tgn_{tag}.npz"), **out)
     print(f"tgn_{tag}.npz", len(out))
 
 
@@ -250,6 +257,99 @@ def golden_eval_metrics():
     print("eval_metrics.npz", len(out), "batches", len(negs))
 
 
+def golden_sampler_support(RandEdgeSampler):
+    """The reference's RandEdgeSampler (utils/utils.py:65-114) on a synthetic batch: its OWN fields after construction
+    (`dst_unique`, `portfolio_list`) give the support of every interaction, available_i = setdiff1d(dst_unique,
+    portfolio_i) (:96), and its own `sample(size)` output shows the replace rule (:99-111): distinct ids iff
+    len(available_i) >= size.  The draws themselves come from numpy's MT19937 and are NOT the contract (the Philox
+    stream is); support, replace rule and uniformity are."""
+    from pfotgnrec_b200.synth import make_stream
+    st = make_stream(n_users=60, n_items=24, n_events=500, n_days=8, seed=41, ts_mode="nbg", with_prices=False)
+    map_item_id = {c: k for k, c in enumerate(st.codes)}
+    train_dst = st.destinations[:400]
+    # drop a few stocks from the training destinations so the universe is a strict subset of the items
+    train_dst = train_dst[~np.isin(train_dst - st.n_users - 1, [3, 7, 11])]
+    sl = slice(400, 464)
+    portfolios = np.array([[st.codes[k] for k in st.portfolio(e)] or [""] for e in range(sl.start, sl.stop)], dtype=object)
+    out = {"train_dst": train_dst, "e0": sl.start, "B": sl.stop - sl.start, "n_users": st.n_users}
+    for k in ("sources", "destinations", "port_ptr", "port_items", "edge_idxs"):
+        out["st_" + k] = getattr(st, k)
+    rs = RandEdgeSampler(st.sources[sl], train_dst, portfolios, st.n_users, map_item_id)
+    I = len(rs.dst_unique)
+    avail = np.zeros((out["B"], I), dtype=bool)
+    for i in range(out["B"]):
+        a = np.setdiff1d(rs.dst_unique, rs.portfolio_list[i])
+        avail[i] = np.isin(rs.dst_unique, a)
+    out["dst_unique"], out["available"] = rs.dst_unique, avail
+    np.random.seed(5)
+    for size in (3, 20, I - 2, I + 9):                   # without replacement ... with replacement (evaluation's case)
+        out[f"ref_sample_{size}"] = rs.sample(size)
+    out["sizes"] = np.array([3, 20, I - 2, I + 9])
+    rs2 = RandEdgeSampler(st.sources[sl], train_dst, portfolios, st.n_users, map_item_id, seed=2024)
+    out["ref_sample_seeded"] = rs2.sample(I)
+    np.savez_compressed(os.path.join(OUT, "sampler_support.npz"), **out)
+    print("sampler_support.npz", len(out))
+
+
+def golden_state_dict(TGN, get_neighbor_finder):
+    """A reference checkpoint: model A (seed 11) trains 2 batches with Adam, `A.state_dict()` is saved with ALL its
+    keys (parameters, the `time_encoder` registered under two names, the three aliases of the memory buffers:
+    memory.*, memory_updater.memory.*, embedding_module.memory.*); model B (seed 99) loads it (strict) and runs batch 3
+    -- the pending raw messages are not part of a state_dict, so B starts from the memory alone, as a reloaded reference
+    does.  The drop-in has to load the same dictionary and reproduce B's batch."""
+    from pfotgnrec_b200.synth import make_stream
+    d, B, n = 32, 24, 10
+    st = make_stream(n_users=40, n_items=12, n_events=B * 3 + 40, n_days=10, seed=13, ts_mode="small", with_prices=False)
+    rng = np.random.default_rng(14)
+    node_feat = rng.random((st.n_nodes, d))
+    nf = get_neighbor_finder(_data(st), uniform=False, max_node_idx=st.n_nodes - 1)
+
+    def make(seed):
+        torch.manual_seed(seed)
+        return TGN(neighbor_finder=nf, node_features=node_feat, edge_features=st.edge_features.copy(),
+                   device=torch.device("cpu"), n_layers=1, n_heads=2, dropout=0.0, use_memory=True,
+                   message_dimension=100, memory_dimension=d, memory_update_at_start=True,
+                   embedding_module_type="graph_attention", message_function="identity", aggregator_type="last",
+                   memory_updater_type="gru", n_neighbors=n, mean_time_shift_src=0.0, std_time_shift_src=1.0,
+                   mean_time_shift_dst=0.0, std_time_shift_dst=1.0, use_destination_embedding_in_message=False,
+                   use_source_embedding_in_message=False, dyrep=False)
+
+    def batch(tgn, bi, neg):
+        sl = slice(bi * B, (bi + 1) * B)
+        return tgn.compute_temporal_embeddings(st.sources[sl], st.destinations[sl], neg, st.timestamps[sl],
+                                               st.edge_idxs[sl], n)
+
+    A = make(11).train()
+    opt = torch.optim.Adam(A.parameters(), lr=1e-2)
+    negs = [rng.integers(st.n_users + 1, st.n_nodes, size=B * 3) for _ in range(3)]
+    for bi in range(2):
+        opt.zero_grad()
+        e_s, e_d, e_n = batch(A, bi, negs[bi])
+        s_ = e_s.view(B, 1, -1)
+        loss = -torch.mean(torch.log(torch.sigmoid(torch.mean(
+            torch.sum(s_ * e_d.view(B, 1, -1), dim=2) - torch.matmul(s_, e_n.view(B, 3, -1).transpose(1, 2)).squeeze(), dim=1))))
+        loss.backward()
+        opt.step()
+        A.memory.detach_memory()
+    sd = A.state_dict()
+    out = {"sd_" + k: v.detach().cpu().numpy().copy() for k, v in sd.items()}
+    out["sd_keys"] = np.array(list(sd.keys()))
+    Bm = make(99)
+    Bm.load_state_dict(sd, strict=True)
+    Bm.eval()
+    with torch.no_grad():
+        e_s, e_d, e_n = batch(Bm, 2, negs[2])
+    out.update(emb_src=e_s.numpy().copy(), emb_dst=e_d.numpy().copy(), emb_neg=e_n.numpy().copy(), neg=negs[2],
+               memory_after=Bm.memory.memory.detach().numpy().copy(),
+               last_update_after=Bm.memory.last_update.detach().numpy().copy(), node_feat=node_feat,
+               cfg_d=d, cfg_B=B, cfg_n=n)
+    for k in ("sources", "destinations", "edge_idxs", "timestamps", "edge_features"):
+        out["st_" + k] = getattr(st, k)
+    out["st_n_nodes"] = st.n_nodes
+    np.savez_compressed(os.path.join(OUT, "state_dict.npz"), **out)
+    print("state_dict.npz", len(out))
+
+
 class _StableNumpy:
     """numpy with argsort(kind='stable') -- documented deviation (ii)."""
 
@@ -259,34 +359,60 @@ class _StableNumpy:
         return getattr(np, name)
 
 
-def main():
-    os.makedirs(OUT, exist_ok=True)
-    TGN, get_neighbor_finder, RandEdgeSampler = _import_reference()
-    golden_neighbors(get_neighbor_finder)
+def model_cases():
+    """tag -> keyword arguments of `_run_model`: the six models main.py / BASELINE configs build and the API variants."""
     common = dict(n_layers=1, n_neighbors=10, use_memory=True, updater="gru",
                   embedding="graph_attention", dyrep=False, dst_emb=False)
-    _run_model(TGN, get_neighbor_finder, "ours", d=64, ts_mode="small", with_ppos=True, **common)
-    _run_model(TGN, get_neighbor_finder, "ours_nbg", d=32, ts_mode="nbg", with_ppos=True,
-               n_batches=2, **common)
-    _run_model(TGN, get_neighbor_finder, "tgn", d=32, ts_mode="small", with_ppos=False, **common)
-    _run_model(TGN, get_neighbor_finder, "jodie", d=32, ts_mode="small", with_ppos=False,
-               **{**common, "updater": "rnn", "embedding": "time"})
-    _run_model(TGN, get_neighbor_finder, "dyrep", d=32, ts_mode="small", with_ppos=False,
-               **{**common, "updater": "rnn", "dyrep": True, "dst_emb": True})
-    _run_model(TGN, get_neighbor_finder, "tgat2", d=32, ts_mode="small", with_ppos=False,
-               **{**common, "use_memory": False, "n_layers": 2, "n_neighbors": 5})
-    # API-surface variants no model of main.py builds: MLP message function + mean aggregator,
-    # and the node's own embedding in its message
-    _run_model(TGN, get_neighbor_finder, "mlp_mean", d=32, ts_mode="small", with_ppos=False, n_batches=3,
-               msg_fn="mlp", aggregator="mean", **common)
-    _run_model(TGN, get_neighbor_finder, "srcemb", d=32, ts_mode="small", with_ppos=False, n_batches=3,
-               src_emb=True, **{**common, "dst_emb": True})
-    _run_model(TGN, get_neighbor_finder, "gsum", d=32, ts_mode="small", with_ppos=False, n_batches=3,
-               **{**common, "embedding": "graph_sum"})
-    _run_model(TGN, get_neighbor_finder, "gsum2", d=32, ts_mode="small", with_ppos=False, n_batches=2,
-               **{**common, "embedding": "graph_sum", "use_memory": False, "n_layers": 2, "n_neighbors": 4})
-    golden_mv_select(RandEdgeSampler)
-    golden_eval_metrics()
+    return {
+        "ours": dict(d=64, ts_mode="small", with_ppos=True, **common),
+        "ours_nbg": dict(d=32, ts_mode="nbg", with_ppos=True, n_batches=2, **common),
+        "tgn": dict(d=32, ts_mode="small", with_ppos=False, **common),
+        "jodie": dict(d=32, ts_mode="small", with_ppos=False, **{**common, "updater": "rnn", "embedding": "time"}),
+        "dyrep": dict(d=32, ts_mode="small", with_ppos=False,
+                      **{**common, "updater": "rnn", "dyrep": True, "dst_emb": True}),
+        "tgat2": dict(d=32, ts_mode="small", with_ppos=False,
+                      **{**common, "use_memory": False, "n_layers": 2, "n_neighbors": 5}),
+        # BASELINE config 3 at its own shape: no memory, 2 layers x 20 neighbours (most-recent mode; the uniform mode
+        # draws from numpy's global MT19937 in the reference and is pinned through the Philox oracle instead)
+        "tgat2x20": dict(d=32, ts_mode="small", with_ppos=False, n_batches=2, B=16,
+                         **{**common, "use_memory": False, "n_layers": 2, "n_neighbors": 20}),
+        # API-surface variants no model of main.py builds (SURVEY 8f-4): MLP message function + mean aggregator,
+        # the node's own embedding in its message, graph_sum, and the identity embedding (memory rows as they are)
+        "mlp_mean": dict(d=32, ts_mode="small", with_ppos=False, n_batches=3, msg_fn="mlp", aggregator="mean", **common),
+        "srcemb": dict(d=32, ts_mode="small", with_ppos=False, n_batches=3, src_emb=True, **{**common, "dst_emb": True}),
+        "gsum": dict(d=32, ts_mode="small", with_ppos=False, n_batches=3, **{**common, "embedding": "graph_sum"}),
+        "gsum2": dict(d=32, ts_mode="small", with_ppos=False, n_batches=2,
+                      **{**common, "embedding": "graph_sum", "use_memory": False, "n_layers": 2, "n_neighbors": 4}),
+        "identity": dict(d=32, ts_mode="small", with_ppos=False, n_batches=3, **{**common, "embedding": "identity"}),
+    }
+
+
+def main(argv=None):
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--device", default="cpu", help="cuda: run the reference's own torch-CUDA path (side-by-side test)")
+    ap.add_argument("--out", default=None, help="output directory (default tests/golden; required with --device cuda)")
+    ap.add_argument("--only", default=None, help="one of the non-model goldens: sampler_support | state_dict")
+    ap.add_argument("--tags", default=None, help="comma-separated model cases (default: all, plus the non-model goldens)")
+    a = ap.parse_args(argv)
+    if a.device != "cpu" and a.out is None:
+        raise SystemExit("--device cuda writes side-by-side vectors: pass --out (the committed goldens are CPU runs)")
+    out_dir = a.out or OUT
+    os.makedirs(out_dir, exist_ok=True)
+    TGN, get_neighbor_finder, RandEdgeSampler = _import_reference()
+    cases = model_cases()
+    if a.only:
+        {"sampler_support": lambda: golden_sampler_support(RandEdgeSampler),
+         "state_dict": lambda: golden_state_dict(TGN, get_neighbor_finder)}[a.only]()
+        return
+    for tag in (a.tags.split(",") if a.tags else cases):
+        _run_model(TGN, get_neighbor_finder, tag, device=a.device, out_dir=out_dir, **cases[tag])
+    if a.tags is None and a.device == "cpu":
+        golden_neighbors(get_neighbor_finder)
+        golden_mv_select(RandEdgeSampler)
+        golden_eval_metrics()
+        golden_sampler_support(RandEdgeSampler)
+        golden_state_dict(TGN, get_neighbor_finder)
 
 
 if __name__ == "__main__":

@@ -106,6 +106,19 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def use_device(device):
+    """Make `device` the process's current CUDA device.  Every entry point launches on the current stream of the
+    CURRENT device (and cudaFuncSetAttribute / the SM count are per current device), so whoever binds this package to
+    cuda:N -- the trainer, the engine, the drop-in TGN, the command-line driver -- selects it first; kernels launched
+    for tensors of another device would otherwise run on device 0 against device-N pointers."""
+    dev = torch.device(device)
+    if dev.type == "cuda" and torch.cuda.is_available():
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        if torch.cuda.current_device() != idx:
+            torch.cuda.set_device(idx)
+    return dev
+
+
 def call(name, *args):
     """Invoke an entry point on the current torch stream and raise on a non-zero return."""
     global LAUNCHES

@@ -219,7 +219,7 @@ class TGNEngine:
         self.node_feat = node_feat.contiguous()
         self.edge_feat = edge_feat.contiguous()
         self.nf = neighbor_finder
-        self.device = node_feat.device
+        self.device = _lib.use_device(node_feat.device)
         self.n_nodes = node_feat.shape[0]
         self.ws = _Workspace(self.device)
         # graph_sum sums over ALL n sampled slots, padded ones included (they carry node 0's features, the edge

@@ -8,6 +8,7 @@ import logging
 import numpy as np
 import torch
 
+from pfotgnrec_b200 import _lib
 from pfotgnrec_b200.containers import (Memory, TimeEncode, get_embedding_module, get_memory_updater,
                                        get_message_aggregator, get_message_function)
 from pfotgnrec_b200.engine import TGNEngine, ModelConfig
@@ -50,6 +51,7 @@ class TGN(torch.nn.Module):
                  use_source_embedding_in_message=False,
                  dyrep=False, gemm_mode="fp32"):
         super().__init__()
+        _lib.use_device(device)      # main.py:103 hands cuda:{gpu}: the kernels launch on the current device's stream
         if use_memory and not memory_update_at_start:
             raise NotImplementedError("memory_update_at_start=False is never executed by main.py")
         if aggregator_type not in ("last", "mean"):

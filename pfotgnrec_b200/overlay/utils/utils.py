@@ -48,6 +48,27 @@ class EarlyStopMonitor(object):
         return self.num_round >= self.max_round
 
 
+_UNIVERSE_CACHE = {}
+
+
+def _universe_sampler(dst_list, device):
+    """unique(dst_list) on the device, cached across constructions.  main.py:193-194 / :344-347 / evaluation.py:84-88
+    build a new RandEdgeSampler for EVERY batch from the same `train_data.destinations` / `full_data.destinations`
+    array, and the reference pays an O(E log E) np.unique each time (utils/utils.py:73).  The cache key is the array's
+    identity (buffer address, length, dtype) guarded by a strided content fingerprint, so a different or modified array
+    is never served a stale universe."""
+    a = np.asarray(dst_list)
+    step = max(1, a.shape[0] // 64) if a.ndim == 1 and a.shape[0] else 1
+    key = (a.__array_interface__["data"][0], a.shape, str(a.dtype), str(device),
+           a[::step].tobytes() if a.ndim == 1 else a.tobytes())
+    hit = _UNIVERSE_CACHE.get(key)
+    if hit is None:
+        if len(_UNIVERSE_CACHE) > 8:
+            _UNIVERSE_CACHE.clear()
+        hit = _UNIVERSE_CACHE[key] = CandidateSampler(np.unique(a), device=device)
+    return hit
+
+
 class RandEdgeSampler(object):
     """Reference utils/utils.py:65-114.  `sample(size)` -> int64 [B, size] item ids drawn
     uniformly from unique(dst_list) minus each interaction's portfolio; without replacement
@@ -71,7 +92,7 @@ class RandEdgeSampler(object):
             else:
                 event_ids = np.arange(B, dtype=np.int64) + RandEdgeSampler._event_counter
                 RandEdgeSampler._event_counter += B
-        self._sampler = CandidateSampler(np.unique(dst_list), device=device)
+        self._sampler = _universe_sampler(dst_list, device)
         self._args = (np.asarray(event_ids, dtype=np.int64), ptr_, items)
 
     def sample(self, size):

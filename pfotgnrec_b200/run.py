@@ -40,6 +40,7 @@ def main(argv=None):
     from .synth import make_stream, read_reference_format, write_reference_format
     from .trainer import PfoTrainer, TrainConfig
     _lib.load()
+    _lib.use_device(torch.device("cuda", a.gpu))
     if a.synthetic is not None:
         u, i, e, d = a.synthetic
         write_reference_format(make_stream(n_users=u, n_items=i, n_events=e, n_days=d, seed=0, ts_mode="nbg"),

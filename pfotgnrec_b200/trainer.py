@@ -162,7 +162,12 @@ class PfoTrainer:
     """Builds the model on a synthetic stream and steps it (train or evaluate)."""
 
     def __init__(self, st: Stream, tc: TrainConfig, device="cuda", train_frac_mask=None):
-        self.st, self.tc, self.device = st, tc, torch.device(device)
+        self.st, self.tc, self.device = st, tc, _lib.use_device(device)
+        if tc.p_pos_num != 1:
+            # the fused BPR kernel (and the packed row blocks [src | dst | p_pos | p_neg]) address ONE p_pos row per
+            # interaction; main.py:327-331 would average over p_pos_num rows -- refuse instead of mis-addressing
+            raise NotImplementedError("p_pos_num != 1: the fused BPR path takes one MV-selected positive per interaction")
+        self.epoch = 0               # folded into the key of the candidate / negative streams (fresh draws per epoch)
         tgn_mod, _ = load_overlay()
         train_mask, val_mask, test_mask = st.split()
         if train_frac_mask is not None:
@@ -225,10 +230,19 @@ class PfoTrainer:
         return time_statistics(self.st.sources, self.st.destinations, self.st.timestamps)
 
     # ------------------------------------------------------------------ one training step
+    def _ev_offset(self):
+        """Offset of the Philox stream ids in the current epoch.  The reference draws fresh candidates every epoch
+        (np.random.choice from the unseeded global stream, main.py:194-195, utils/utils.py:103-111); here a draw is
+        keyed by (seed, stream id of the interaction, slot), so the epoch is folded into the id: id = edge idx +
+        epoch * (n_events + 1).  It rides in the batch's `ev` column -- a graph replay reads it from the static
+        buffer, nothing is baked into the captured kernels."""
+        return int(self.epoch) * (int(self.st.n_events) + 1)
+
     def _batch(self, s, e):
         D = self.dev_stream
-        return dict(src=D.src[s:e], dst=D.dst[s:e], ts=D.ts[s:e], eidx=D.eidx[s:e], ev=D.ev[s:e], day=D.day[s:e],
-                    port_ptr=D.port_ptr[s:e + 1])
+        off = self._ev_offset()
+        return dict(src=D.src[s:e], dst=D.dst[s:e], ts=D.ts[s:e], eidx=D.eidx[s:e],
+                    ev=D.ev[s:e] + off if off else D.ev[s:e], day=D.day[s:e], port_ptr=D.port_ptr[s:e + 1])
 
     def make_host_batches(self, start, count, bs):
         """Pinned host copies of `count` consecutive batches, as a caller holding numpy data passes them."""
@@ -239,7 +253,7 @@ class PfoTrainer:
             pp = st.port_ptr[s:e + 1]
             hb = dict(src=pin(st.sources[s:e].astype(np.int32)), dst=pin(st.destinations[s:e].astype(np.int32)),
                       ts=pin(st.timestamps[s:e]), eidx=pin(st.edge_idxs[s:e].astype(np.int32)),
-                      ev=pin(st.edge_idxs[s:e].astype(np.int64)), day=pin(st.day_idx[s:e].astype(np.int32)),
+                      ev=pin(st.edge_idxs[s:e].astype(np.int64) + self._ev_offset()), day=pin(st.day_idx[s:e].astype(np.int32)),
                       port_ptr=pin((pp - pp[0]).astype(np.int64)),
                       port_items=pin(np.r_[st.port_items[pp[0]:pp[-1]], 0].astype(np.int32)))
             hb["nbytes"] = sum(v.numel() * v.element_size() for v in hb.values())
@@ -283,7 +297,8 @@ class PfoTrainer:
         D, st = self.dev_stream, self.st
         x = sg.static
         x["src"].copy_(D.src[s:e]); x["dst"].copy_(D.dst[s:e]); x["ts"].copy_(D.ts[s:e])
-        x["eidx"].copy_(D.eidx[s:e]); x["ev"].copy_(D.ev[s:e]); x["day"].copy_(D.day[s:e])
+        x["eidx"].copy_(D.eidx[s:e]); x["day"].copy_(D.day[s:e])
+        torch.add(D.ev[s:e], self._ev_offset(), out=x["ev"])
         p0, p1 = int(st.port_ptr[s]), int(st.port_ptr[e])          # host copy of the CSR: no device sync
         torch.sub(D.port_ptr[s:e + 1], p0, out=x["port_ptr"])
         if p1 > p0:
@@ -433,20 +448,24 @@ class PfoTrainer:
         return pos_rank, top, cand, scores, None
 
     def reset_eval_metrics(self):
-        self.metrics.reset()
+        if self.metrics is not None:
+            self.metrics.reset()
 
     def eval_summary(self, EVAL="val"):
         """The dictionary reference eval_recommendation returns (evaluation.py:209-258), from the 31 running sums
         the evaluation steps since `reset_eval_metrics` left on the device (in the replicated multi-GPU mode the
         sums of the ranks' user slices are all-reduced first)."""
+        if self.metrics is None:         # no price tables on this stream: nothing to summarise
+            return {}
         return self.metrics.summary(EVAL, reduce=self._all_ranks_sum)
 
     def _all_ranks_sum(self, t):
         return t
 
-    def evaluate(self, s, e, bs=None, n_items=None, EVAL="val"):
+    def evaluate(self, s, e, bs=None, n_items=None, EVAL="val", max_batches=None):
         """The loop of reference eval_recommendation (evaluation.py:63-207) over interactions [s, e): batches of
-        `bs`, the last (short or exactly-ending) batch skipped like the reference does (:68-69)."""
+        `bs`, the last (short or exactly-ending) batch skipped like the reference does (:68-69); `max_batches` is the
+        reference's `is_test_run` stop (:72-74)."""
         bs = int(bs or self.tc.bs)
         self.reset_eval_metrics()
         n_batches = -(-(e - s) // bs)
@@ -454,6 +473,8 @@ class PfoTrainer:
             a, b_ = s + i * bs, min(e, s + (i + 1) * bs)
             if b_ == e:
                 continue
+            if max_batches is not None and i >= max_batches:
+                break
             self.eval_step(a, b_, n_items=n_items)
         return self.eval_summary(EVAL)
 
@@ -461,6 +482,10 @@ class PfoTrainer:
         """(train, validation, test) index ranges: the chronological 80/10/10 split of reference utils/data.py:27,48-50
         (the stream is time-sorted, so the three masks are contiguous)."""
         tr, va, _ = self.masks
+        if not np.all(np.diff(self.st.timestamps) >= 0):
+            # the index ranges below equal the reference's timestamp masks only on a chronological stream; on an
+            # unsorted file they would leak validation / test interactions into training
+            raise ValueError("the interaction stream is not sorted by timestamp: fit() walks contiguous index ranges")
         n_tr, n_va = int(tr.sum()), int(va.sum())
         return (0, n_tr), (n_tr, n_tr + n_va), (n_tr + n_va, self.st.n_events)
 
@@ -472,7 +497,9 @@ class PfoTrainer:
         bs = int(bs or self.tc.bs)
         (t0, t1), (v0, v1), (e0, e1) = self.split_ranges()
         history = []
+        self._check_fit(bs)
         for epoch in range(int(epochs)):
+            self.epoch = epoch
             if self.tgn.use_memory:
                 self.tgn.memory.__init_memory__()                    # main.py:152-153
             losses = []
@@ -482,12 +509,15 @@ class PfoTrainer:
                 s, e = t0 + bi * bs, min(t1, t0 + (bi + 1) * bs)
                 losses.append(self.train_step(s, e).clone())         # the graph's output buffer is reused next step
             out = {"epoch": epoch, "loss": float(torch.stack(losses).mean().item()) if losses else float("nan")}
-            out.update(self.evaluate(v0, v1, bs=bs, EVAL="valid"))   # main.py:405-418
-            out.update(self.evaluate(e0, e1, bs=bs, EVAL="test"))    # main.py:427-440
+            out.update(self.evaluate(v0, v1, bs=bs, EVAL="valid", max_batches=max_batches))   # main.py:405-418
+            out.update(self.evaluate(e0, e1, bs=bs, EVAL="test", max_batches=max_batches))    # main.py:427-440
             history.append(out)
             if log is not None:
                 log(out)
         return history
+
+    def _check_fit(self, bs):
+        pass
 
     @staticmethod
     def recall_ndcg(pos_rank, ks=(1, 3, 5)):
@@ -502,12 +532,14 @@ class PfoTrainer:
 
 
 def replica_slice(s, e, rank, world):
-    """This rank's share [ls, le) of the global batch [s, e): equal consecutive slices (the batch size must divide)."""
+    """This rank's share [ls, le) of the global batch [s, e): consecutive slices, the first (n mod world) ranks take
+    one interaction more (the short last batch of an epoch, main.py:180, rarely divides)."""
     n = e - s
-    if n % world != 0:
-        raise ValueError(f"global batch of {n} interactions does not split evenly over {world} ranks")
-    bs = n // world
-    return s + rank * bs, s + (rank + 1) * bs
+    if n < world:
+        raise ValueError(f"global batch of {n} interactions cannot be split over {world} ranks")
+    base, rem = divmod(n, world)
+    ls = s + rank * base + min(rank, rem)
+    return ls, ls + base + (1 if rank < rem else 0)
 
 
 def allreduce_sum_(flat, group=None):
@@ -549,6 +581,10 @@ class ReplicatedTrainer(PfoTrainer):
     def _zero_grads(self):
         self.gflat.zero_()
 
+    def _check_fit(self, bs):
+        if bs < self.world:
+            raise ValueError(f"fit: batch size {bs} is smaller than the number of ranks ({self.world})")
+
     def _all_ranks_sum(self, t):
         return allreduce_sum_(t, self.group) if self.world > 1 else t
 
@@ -574,6 +610,16 @@ class ReplicatedTrainer(PfoTrainer):
     def train_step(self, s, e, batch=None):
         """Global batch [s, e): this rank embeds its slice, every rank advances the state with all of it."""
         ls, le = replica_slice(s, e, self.rank, self.world)
+        if (e - s) % self.world != 0:
+            # ragged tail batch: the loss is the mean over the GLOBAL batch, so this rank's mean is weighted by its
+            # share; launched kernel by kernel (the captured graphs bake the even 1 / world weight)
+            b = self._batch(ls, le)
+            b["state"] = self._state_batch(s, e)
+            keep, self._loss_scale = self._loss_scale, (le - ls) / float(e - s)
+            try:
+                return self._step_body(b)
+            finally:
+                self._loss_scale = keep
         if self._graph_ok(le - ls) and e <= self.st.n_events:
             sg = self._step_graph(le - ls)
             self._fill_static(sg, ls, le)

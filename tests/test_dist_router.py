@@ -118,11 +118,19 @@ def test_replicated_dp_gradient_bucket_gloo_world2():
     assert dict(results) == {0: "ok", 1: "ok"}
 
 
-def test_replica_slice_rejects_ragged_batches():
+def test_replica_slice_covers_ragged_batches():
+    """The short last batch of an epoch (main.py:180) rarely divides by the world size: the slices stay consecutive,
+    cover the batch exactly once and differ by at most one interaction; fewer interactions than ranks is refused."""
     sys.path.insert(0, ROOT)
     from pfotgnrec_b200.trainer import replica_slice
+    for n, world in ((130, 4), (128, 4), (7, 2), (9, 8)):
+        cuts = [replica_slice(1000, 1000 + n, r, world) for r in range(world)]
+        assert cuts[0][0] == 1000 and cuts[-1][1] == 1000 + n
+        assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+        sizes = [b - a for a, b in cuts]
+        assert max(sizes) - min(sizes) <= 1 and min(sizes) >= 1
     with pytest.raises(ValueError):
-        replica_slice(0, 130, 0, 4)
+        replica_slice(0, 3, 0, 4)
 
 
 def _metric_worker(rank, world, port, results):

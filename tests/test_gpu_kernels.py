@@ -221,6 +221,21 @@ def test_candidate_sampler_vs_oracle(size):
         assert not (set(out[b].tolist()) & held)
 
 
+def test_candidate_sampler_support_and_replace_rule_vs_reference():
+    """K5's sampling kernel against the reference RandEdgeSampler's own support / replace rule / uniformity
+    (tests/golden/sampler_support.npz, utils/utils.py:73-113) -- the same checker the oracle passes on CPU."""
+    from test_oracle_golden import check_sampler_support
+    from pfotgnrec_b200.sampler import CandidateSampler
+    z = load_golden("sampler_support.npz")
+    cs = {}
+
+    def sample(ev, items, pptr, held, size, seed):
+        c = cs.setdefault(id(items), CandidateSampler(items))
+        return c.sample(ev, pptr, held, int(size), seed=int(seed)).cpu().numpy().astype(np.int64)
+
+    check_sampler_support(z, sample)
+
+
 # ------------------------------------------------------------------------------ K6 / eval
 def test_bpr_forward_backward():
     from oracle.tgn import bpr_loss

@@ -116,6 +116,65 @@ def test_dropout_stream_is_keyed_by_the_device_step_counter():
     assert abs(psum[live].mean() - 1.0) < 0.1
 
 
+def test_dropout_mask_placement_and_expectation():
+    """Placement and scaling of the attention dropout against nn.MultiheadAttention's (temporal_attention.py:28-32,
+    torch's multi_head_attention_forward: softmax -> dropout(p) on the WEIGHTS -> AV, no renormalisation):
+      * every dropped-path weight is either 0 or the undropped softmax weight / (1 - p), and a fraction ~p is dropped;
+      * the per-head weighted neighbour sum is linear in the weights, so its mean over many independent masks converges
+        to the undropped one (E[mask / (1 - p)] = 1) at the Monte-Carlo rate."""
+    from pfotgnrec_b200 import _lib
+    from pfotgnrec_b200._lib import ptr
+    g = torch.Generator(device="cuda").manual_seed(1)
+    Q, n, d, F, H, p = 192, 10, 64, 1, 2, 0.3
+    ekp = (2 * d + F + 3 + 3) // 4 * 4
+    T = torch.randn(300, d, device="cuda", generator=g)
+    QK = torch.randn(Q, H, ekp, device="cuda", generator=g) * 0.1
+    idx = torch.randint(0, 300, (Q, n), device="cuda", generator=g, dtype=torch.int32)
+    eidx = torch.randint(0, 50, (Q, n), device="cuda", generator=g, dtype=torch.int32)
+    dt = torch.rand(Q, n, device="cuda", generator=g) * 100
+    ef = torch.randn(50, F, device="cuda", generator=g)
+    tw, tb = torch.rand(d, device="cuda", generator=g), torch.rand(d, device="cuda", generator=g)
+
+    def run(p_drop, ctr, idx_=None):
+        XB = torch.empty(Q, H, ekp, device="cuda")
+        P = torch.empty(Q, H, n, device="cuda")
+        inv = torch.empty(Q, dtype=torch.int32, device="cuda")
+        c = torch.tensor([ctr], dtype=torch.int32, device="cuda")
+        ix = idx if idx_ is None else idx_
+        _lib.call("pfo_attn_nbr_fwd", ptr(QK), ptr(T), d, ptr(ix), ptr(eidx), ptr(dt), ptr(ef), ptr(tw), ptr(tb),
+                  Q, n, d, F, H, ekp, float(p_drop), 3, 1, ptr(c), ptr(XB), H * ekp, ptr(P), ptr(inv))
+        return XB, P
+
+    psum_col = 2 * d + F
+    # (a) one live neighbour per query: its softmax weight is 1, so after dropout the kept mass of a head is exactly
+    # 0 or 1 / (1 - p), and the head's neighbour sum is exactly 0 or x_j / (1 - p)
+    one = torch.full((Q, n), -1, dtype=torch.int32, device="cuda")
+    one[:, n - 1] = idx[:, n - 1]
+    XB1, _ = run(0.0, 0, one)
+    XBd, _ = run(p, 16, one)
+    mass = XBd[:, :, psum_col]
+    kept = mass != 0
+    assert torch.allclose(mass[kept], torch.full_like(mass[kept], 1.0 / (1.0 - p)), rtol=1e-6, atol=0)
+    assert mass[kept].unique().numel() == 1
+    assert 0.15 < float((~kept).float().mean()) < 0.45                                   # ~p of the 2Q (query, head) weights
+    assert torch.allclose(XBd[:, :, :d][kept], XB1[:, :, :d][kept] / (1.0 - p), rtol=1e-6, atol=1e-7)
+    assert float(XBd[:, :, :psum_col][~kept].abs().max()) == 0.0
+    # (b) the saved softmax weights do not depend on the mask; the dropped path is unbiased
+    XB0, P0 = run(0.0, 0)
+    assert torch.allclose(P0.sum(dim=2), torch.ones(Q, H, device="cuda"), atol=1e-5)
+    R = 400
+    acc = torch.zeros_like(XB0, dtype=torch.float64)
+    for r in range(R):
+        XB, P = run(p, 16 * (r + 1))
+        assert torch.equal(P, P0)
+        acc += XB.double()
+    mean = acc / R
+    assert abs(float(mean[:, :, psum_col].mean()) - 1.0) < 5e-3                           # E[sum_j p'_j] = 1
+    ref = XB0[:, :, :psum_col].double()
+    err = (mean[:, :, :psum_col] - ref).abs().mean() / ref.abs().mean()
+    assert err < 0.05, float(err)
+
+
 def test_eval_step_graph_replay_matches_eager_and_oracle():
     """Evaluation step (candidates, embeddings, scores, ranking): CUDA-graph replay == eager launches, and the
     first batch == the oracle's evaluation step (ranks bit-exact, scores to 1e-5)."""
@@ -225,3 +284,53 @@ def test_fit_epoch_loop_matches_manual_loop():
             assert abs(got[k] - v) <= 1e-6 * max(1.0, abs(v)), (epoch, k, got[k], v)
         assert 0.0 <= got["valid_recall_avg_5"] <= 1.0 and np.isfinite(got["loss"])
     assert hist[0]["loss"] == hist[1]["loss"]            # same weights, memory reset: the epochs repeat exactly
+
+
+def test_every_epoch_draws_fresh_candidates():
+    """The reference draws new candidates every epoch (np.random.choice from the unseeded global stream,
+    main.py:194-195): the Philox stream id of an interaction folds the epoch in, so epoch 1 differs from epoch 0 while
+    each epoch stays reproducible and independent of the batch split."""
+    from pfotgnrec_b200.synth import make_stream
+    from pfotgnrec_b200.trainer import PfoTrainer, TrainConfig
+    st = make_stream(n_users=300, n_items=60, n_events=3000, n_days=20, seed=1, ts_mode="small")
+    tr = PfoTrainer(st, TrainConfig(model="ours", bs=128), device="cuda")
+
+    def cands(epoch, s, e):
+        tr.epoch = epoch
+        b = tr._batch(s, e)
+        return tr.mv.select(b["ev"], b["day"], b["dst"], b["port_ptr"], tr.dev_stream.port_items,
+                            return_scores=True)[2].cpu().numpy()
+
+    c0, c1 = cands(0, 1000, 1128), cands(1, 1000, 1128)
+    assert np.array_equal(c0[:, 0], c1[:, 0])                       # column 0 is the true destination
+    assert (c0[:, 1:] != c1[:, 1:]).mean() > 0.5                    # fresh draws
+    assert np.array_equal(c1, cands(1, 1000, 1128))                 # reproducible
+    assert np.array_equal(c1[:64], cands(1, 1000, 1064))            # batch-split independent
+    # the static buffers of the captured graph carry the same offset
+    tr.epoch = 1
+    sg = tr._step_graph(128)
+    tr._fill_static(sg, 1000, 1128)
+    assert torch.equal(sg.static["ev"], tr._batch(1000, 1128)["ev"])
+    tr.epoch = 0
+    # baselines: the negatives of the BPR loss
+    tr2 = PfoTrainer(st, TrainConfig(model="tgn", bs=128), device="cuda")
+    def negs(epoch):
+        tr2.epoch = epoch
+        b = tr2._batch(1000, 1128)
+        return tr2.neg_sampler.sample(b["ev"], b["port_ptr"], tr2.dev_stream.port_items_as_item_ids, 3, seed=0).cpu().numpy()
+    assert (negs(0) != negs(1)).mean() > 0.5
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs a second GPU")
+def test_trainer_on_a_non_default_device():
+    """PfoTrainer(device='cuda:1') selects the device before any kernel is launched: same losses as on cuda:0."""
+    from pfotgnrec_b200.synth import make_stream
+    from pfotgnrec_b200.trainer import PfoTrainer, TrainConfig
+    st = make_stream(n_users=300, n_items=60, n_events=3000, n_days=20, seed=1, ts_mode="small")
+    losses = []
+    for dev in ("cuda:0", "cuda:1"):
+        tr = PfoTrainer(st, TrainConfig(model="ours", bs=128, cuda_graph=False), device=dev)
+        losses.append([float(tr.train_step(1000 + 128 * i, 1128 + 128 * i).item()) for i in range(3)])
+        assert tr.tgn.memory.memory.device == torch.device(dev)
+    torch.cuda.set_device(0)
+    assert np.allclose(losses[0], losses[1], rtol=1e-5)

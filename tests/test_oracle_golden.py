@@ -24,7 +24,8 @@ def test_neighbors_bit_exact(name, n):
     assert nb.dtype == np.int32 and ei.dtype == np.int32 and et.dtype == np.float32
 
 
-@pytest.mark.parametrize("tag", ["ours", "ours_nbg", "tgn", "jodie", "dyrep", "tgat2", "mlp_mean", "srcemb", "gsum", "gsum2"])
+@pytest.mark.parametrize("tag", ["ours", "ours_nbg", "tgn", "jodie", "dyrep", "tgat2", "tgat2x20", "mlp_mean", "srcemb", "gsum", "gsum2",
+                                 "identity"])
 def test_model_path_matches_reference(tag):
     z = load_golden(f"tgn_{tag}.npz")
     o, p = oracle_from_golden(z)
@@ -125,3 +126,49 @@ def test_philox4x32_10_known_answer_vectors():
     for ctr, key, want in kat:
         got = philox4x32_10(np.array([ctr[0]], dtype=np.int64), ctr[1], ctr[2], ctr[3], key[0], key[1])
         assert tuple(int(x[0]) for x in got) == want
+
+
+def _support_case(z):
+    e0, B, U = int(z["e0"]), int(z["B"]), int(z["n_users"])
+    ptr = z["st_port_ptr"][e0:e0 + B + 1]
+    held = z["st_port_items"][ptr[0]:ptr[-1]].astype(np.int64) + U + 1
+    return e0, B, ptr - ptr[0], held
+
+
+def check_sampler_support(z, sample_fn):
+    """Support, replace rule and uniformity of a candidate sampler against what the reference's RandEdgeSampler holds
+    after construction (utils/utils.py:73-81 -> `dst_unique`, `portfolio_list`) and does in `sample` (:93-113):
+    candidates come from setdiff1d(dst_unique, portfolio_i); they are distinct iff that set has >= size members (the
+    reference's own samples show the same pattern); every available item is equally likely."""
+    e0, B, pptr, held = _support_case(z)
+    dst_unique, avail = z["dst_unique"], z["available"]
+    assert np.array_equal(dst_unique, np.unique(z["train_dst"]))
+    ev = z["st_edge_idxs"][e0:e0 + B]
+    for size in z["sizes"].tolist():
+        ref = z[f"ref_sample_{size}"]
+        got = np.asarray(sample_fn(ev, dst_unique, pptr, held, size, 0))
+        assert got.shape == ref.shape
+        for i in range(B):
+            allowed = dst_unique[avail[i]]
+            assert np.isin(got[i], allowed).all(), (size, i)                   # support
+            assert np.isin(ref[i], allowed).all()
+            distinct = len(allowed) >= size                                    # replace rule (:99 vs :107)
+            assert (len(set(ref[i].tolist())) == size) == distinct
+            assert (len(set(got[i].tolist())) == size) == distinct, (size, i)
+    # uniformity over the available items: pooled chi-square of 64 interactions x 400 epochs x 3 draws
+    counts = np.zeros(len(dst_unique))
+    expect = np.zeros(len(dst_unique))
+    for rep in range(400):
+        got = np.asarray(sample_fn(ev + 1000 * rep, dst_unique, pptr, held, 3, 0))
+        counts += np.bincount(np.searchsorted(dst_unique, got.ravel()), minlength=len(dst_unique))
+        expect += (avail / avail.sum(axis=1, keepdims=True)).sum(axis=0) * 3
+    chi2 = float(((counts - expect) ** 2 / expect).sum())
+    dof = len(dst_unique) - 1
+    assert chi2 < dof + 6 * np.sqrt(2 * dof), (chi2, dof)                      # ~6 sigma of chi-square(dof)
+
+
+def test_candidate_sampler_support_and_replace_rule_vs_reference():
+    """oracle/sampling.py::sample_candidates against the reference RandEdgeSampler's own support / replace rule."""
+    z = load_golden("sampler_support.npz")
+    check_sampler_support(z, lambda ev, items, pptr, held, size, seed:
+                          sampling.sample_candidates(ev, items, pptr, held, size, seed))

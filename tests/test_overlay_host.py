@@ -94,23 +94,57 @@ def test_product_path_never_imports_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(dirpath, f)
 
 
-def test_bench_reference_arm_json_contract():
-    """`bench.py --impl reference` (the reference algorithm on the host cores, no GPU needed) prints ONE JSON line with
-    the contract keys the driver reads."""
+def _reference_arm(extra=()):
     import json
     import subprocess
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
                           "--warmup", "1", "--users", "300", "--items", "40", "--events", "3000", "--days", "20",
-                          "--bs", "64"], capture_output=True, text=True, timeout=600)
+                          "--bs", "64", "--ref-budget", "6", "--eval-budget", "2", *extra],
+                         capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
     assert len(lines) == 1
-    d = json.loads(lines[0])
+    return json.loads(lines[0])
+
+
+def _check_reference_line(d, kind):
     assert d["impl"] == "reference" and d["metric"] == "train_events_per_sec" and d["unit"] == "events/s"
     assert d["value"] > 0 and d["higher_is_better"] is True and d["steps"] == 2 and d["warmup"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["cpu_baseline"]["kind"] == kind and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"]
+    assert "workload" in d["config"] and d["config"]["global_batch"] == 64
+
+
+def test_bench_reference_arm_json_contract_port():
+    """`bench.py --impl reference --ref-kind port` (the oracle port on the host cores, the fallback when no reference
+    tree is staged) prints ONE JSON line with the contract keys the driver reads."""
+    _check_reference_line(_reference_arm(["--ref-kind", "port"]), "port")
+
+
+def test_bench_reference_arm_runs_the_unmodified_reference():
+    """With a reference tree present (/root/reference here, baseline/_ref on the GPU box) the arm drives the reference's
+    own modules and the text of main.py:167-394 (kind "reference"), training and evaluation."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    from stage_reference import ref_root
+    if ref_root() is None:
+        pytest.skip("no reference tree staged")
+    d = _reference_arm()
+    _check_reference_line(d, "reference")
+    ev = d["eval"]
+    assert ev["metric"] == "eval_users_per_sec" and ev["value"] > 0 and ev["cpu_baseline"]["kind"] == "reference"
+
+
+def test_staged_reference_is_byte_identical():
+    """baseline/_ref (git-ignored, shipped to the GPU box) is a byte-for-byte copy of the reference's python files."""
+    import hashlib
+    import json
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not (os.path.isdir("/root/reference") and os.path.exists(os.path.join(ref, "MANIFEST.json"))):
+        pytest.skip("needs both /root/reference and the staged copy")
+    for rel, sha in json.load(open(os.path.join(ref, "MANIFEST.json"))).items():
+        assert hashlib.sha256(open(os.path.join("/root/reference", rel), "rb").read()).hexdigest() == sha
+        assert hashlib.sha256(open(os.path.join(ref, rel), "rb").read()).hexdigest() == sha
 
 
 def test_reference_on_disk_format_round_trip(tmp_path):
@@ -166,3 +200,42 @@ def test_engine_binds_every_parameter_of_every_config(overlay, tag):
     trainable = {k for k, p in tgn.named_parameters() if p.requires_grad}
     unused = {"memory_updater.layer_norm.weight", "memory_updater.layer_norm.bias"}       # never applied (reference too)
     assert trainable - unused <= set(names) | {n.replace(".mlp.", ".layers.") for n in names}
+
+
+def _state_dict_case():
+    z = load_golden("state_dict.npz")
+    sd = {str(k): torch.tensor(z["sd_" + str(k)]) for k in z["sd_keys"]}
+    return z, sd
+
+
+def build_for_state_dict(tgn_mod, z, device, nf=None, seed=99):
+    d, n = int(z["cfg_d"]), int(z["cfg_n"])
+    torch.manual_seed(seed)
+    return tgn_mod.TGN(neighbor_finder=nf, node_features=z["node_feat"], edge_features=z["st_edge_features"].copy(),
+                       device=torch.device(device), n_layers=1, n_heads=2, dropout=0.0, use_memory=True,
+                       message_dimension=100, memory_dimension=d, memory_update_at_start=True,
+                       embedding_module_type="graph_attention", message_function="identity", aggregator_type="last",
+                       memory_updater_type="gru", n_neighbors=n, mean_time_shift_src=0.0, std_time_shift_src=1.0,
+                       mean_time_shift_dst=0.0, std_time_shift_dst=1.0, use_destination_embedding_in_message=False,
+                       use_source_embedding_in_message=False, dyrep=False)
+
+
+def test_overlay_loads_a_reference_checkpoint(overlay):
+    """A state_dict written by the UNMODIFIED reference after two Adam steps (tests/golden/state_dict.npz: every key,
+    including the three aliases of the memory buffers, the layer_norm the reference never applies and time_encoder under
+    two names) loads into the drop-in with strict=True; all tensors arrive, and the aliases still share one storage
+    with the engine's dense state."""
+    tgn_mod, _ = overlay
+    z, sd = _state_dict_case()
+    tgn = build_for_state_dict(tgn_mod, z, "cpu")
+    assert set(tgn.state_dict().keys()) == set(sd.keys())
+    res = tgn.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    got = tgn.state_dict()
+    for k, v in sd.items():
+        assert torch.equal(got[k], v), k
+    st = tgn.memory.state
+    assert st.memory.data_ptr() == tgn.memory.memory.data_ptr() == tgn.memory_updater.memory.memory.data_ptr() \
+        == tgn.embedding_module.memory.memory.data_ptr()
+    assert torch.equal(st.memory, sd["memory.memory"]) and torch.equal(st.last_update, sd["memory.last_update"])
+    assert float(sd["memory.memory"].abs().sum()) > 0
