@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define PFO_ABI_VERSION 1
+#define PFO_ABI_VERSION 2
 int pfo_abi_version(void);
 
 /* ---- K1: temporal neighbour sampling --- utils/utils.py:150-161 (find_before) and
@@ -27,10 +27,14 @@ int pfo_abi_version(void);
  * CSR adjacency sorted by (node, timestamp, stream order): rowptr[N+1], adj_nbr/adj_eidx/adj_ts[2E].
  * Outputs are [Q, n] row-major, right-aligned / left zero-padded; out_dt = fp32(t - fp32(edge time))
  * (modules/embedding_module.py:133-135).  uniform != 0 selects the uniform-with-replacement mode
- * (:193-204) driven by the shared Philox stream (counter = (query, call_id, slot, 3)). */
+ * (:193-204) driven by the shared Philox stream (counter = (query, call, slot, 3)) with
+ * call = call_id + *call_ctr (call_ctr may be NULL): the device part lets a captured CUDA graph draw a fresh
+ * stream on every replay.  lanes_per_query (most-recent mode): 1, 4, 8 or 32 lanes of a warp share one query's
+ * lower-bound search ((lanes+1)-ary, one dependent probe round per factor of lanes+1); 0 = chosen from n_queries. */
 int pfo_neighbor_sample(const int64_t* rowptr, const int32_t* adj_nbr, const int32_t* adj_eidx,
                         const double* adj_ts, const int32_t* q_nodes, const double* q_ts,
                         int64_t n_queries, int n_neighbors, int uniform, uint64_t seed, uint32_t call_id,
+                        const uint32_t* call_ctr, int lanes_per_query,
                         int32_t* out_nbr, int32_t* out_eidx, float* out_etime, float* out_dt, void* stream);
 
 /* ---- touched-node compaction (replaces the O(n_nodes) clone + Python loop of
@@ -153,6 +157,11 @@ int pfo_time_embedding_bwd(const int32_t* q_nodes, int64_t Q, int d, const int32
                            int64_t workspace_floats, void* stream);
 
 /* small row utilities (gather with idx < 0 -> zero row; scatter-add = its gradient) */
+/* ---- TimeEncode.forward alone --- model/time_encoding.py:17-25: out_cos[m, c] = cos(fmaf(t[m], w[c], b[c])) (fmaf ==
+ * nn.Linear(1, d) bit for bit), out_sin optional.  mode 0 = per-warp choice of the quadrant reduction as in the fused
+ * kernels, 1 = fp64 reduction (any |x| < 2^44), 2 = fp32 Cody-Waite reduction (|x| < 2^17). */
+int pfo_time_encode(const float* t, const float* w, const float* b, int64_t M, int d, int mode,
+                    float* out_cos, float* out_sin, void* stream);
 int pfo_reduce_partials(const float* partial, int rows, int cols, float* out, int accumulate, void* stream);
 int pfo_scatter_add_rows(const float* src, int64_t lds, const int32_t* idx, int64_t M, int d,
                          float* dst, int64_t ldd, void* stream);

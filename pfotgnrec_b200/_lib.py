@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libpfo_b200.so")
 P = c_void_p
 _SIGS = {
     "pfo_abi_version": (c_int, []),
-    "pfo_neighbor_sample": (c_int, [P, P, P, P, P, P, c_int64, c_int, c_int, c_uint64, c_uint32, P, P, P, P, P]),
+    "pfo_neighbor_sample": (c_int, [P, P, P, P, P, P, c_int64, c_int, c_int, c_uint64, c_uint32, P, c_int, P, P, P, P, P]),
     "pfo_mark_nodes": (c_int, [P, c_int64, c_int, P, P]),
     "pfo_compact_workspace_ints": (c_int64, [c_int64]),
     "pfo_compact_nodes": (c_int, [P, c_int64, P, P, P, P, P]),
@@ -43,6 +43,7 @@ _SIGS = {
     "pfo_time_embedding_fwd": (c_int, [P, P, c_int64, c_int64, c_int, P, P, P, c_float, c_float, c_float,
                                        c_float, P, P, P, P, P]),
     "pfo_time_embedding_bwd": (c_int, [P, c_int64, c_int, P, P, P, P, P, P, P, P, P, c_int64, P]),
+    "pfo_time_encode": (c_int, [P, P, P, c_int64, c_int, c_int, P, P, P]),
     "pfo_reduce_partials": (c_int, [P, c_int, c_int, P, c_int, P]),
     "pfo_scatter_add_rows": (c_int, [P, c_int64, P, c_int64, c_int, P, c_int64, P]),
     "pfo_gather_rows": (c_int, [P, c_int64, P, c_int64, c_int, P, c_int64, P]),
@@ -63,6 +64,7 @@ _SIGS = {
 }
 
 EXPORTS = tuple(_SIGS)
+ABI_VERSION = 2         # PFO_ABI_VERSION of include/pfo_b200.h this binding was written against
 _lib = None
 LAUNCHES = 0            # kernels launched through this binding (bench.py reports it)
 _LAUNCHES_PER_CALL = {"pfo_compact_nodes": 3, "pfo_fold_attention_fwd": 2, "pfo_fold_attention_bwd": 2,
@@ -89,7 +91,7 @@ def load():
     for name, (res, args) in _SIGS.items():
         fn = getattr(lib, name)      # AttributeError if the header and the library disagree
         fn.restype, fn.argtypes = res, args
-    if lib.pfo_abi_version() != 1:
+    if lib.pfo_abi_version() != ABI_VERSION:
         raise PfoError("libpfo_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -37,6 +37,19 @@ class TimeEncode(_Container):
         self.w.weight = nn.Parameter(freq.reshape(dimension, -1))
         self.w.bias = nn.Parameter(torch.zeros(dimension).float())
 
+    @torch.no_grad()
+    def forward(self, t):
+        """model/time_encoding.py:17-25 on its own (inference only; inside the TGN step the encoding is fused into the
+        message and attention kernels): t [batch, seq] -> cos(t * w + b) [batch, seq, dimension]."""
+        from . import _lib
+        t = t.contiguous().float()
+        out = torch.empty(tuple(t.shape) + (self.dimension,), device=t.device)
+        if t.device.type != "cuda":
+            raise _lib.PfoError("TimeEncode.forward runs in libpfo_b200.so on a CUDA device: there is no CPU fallback")
+        _lib.call("pfo_time_encode", _lib.ptr(t), _lib.ptr(self.w.weight.detach().reshape(-1).contiguous()),
+                  _lib.ptr(self.w.bias.detach().contiguous()), t.numel(), self.dimension, 0, _lib.ptr(out), None)
+        return out
+
 
 # ----------------------------------------------------------------------------- utils/utils.py:4-17
 class MergeLayer(_Container):

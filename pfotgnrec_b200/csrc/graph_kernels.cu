@@ -3,9 +3,14 @@
 //
 // Replaces reference utils/utils.py:150-220 (NeighborFinder.find_before /
 // get_temporal_neighbor) -- a Python loop over queries with np.searchsorted.
-// HBM-bound integer work: one lane owns one query for the binary search (32 searches
-// in flight per warp), then the warp emits its 32*n output slots cooperatively so that
-// the stores to the [Q, n] outputs are fully coalesced.
+// HBM / L2-latency-bound integer work.  A query is a chain of dependent loads: node id -> row bounds -> the
+// probes of the lower-bound search -> the gather of its n most recent entries.  The search is COOPERATIVE: LPQ lanes
+// of a warp share one query and probe LPQ split points of the current interval at once (a (LPQ+1)-ary search, one
+// ballot per round), so a stock row with 10^5 entries takes 4 dependent rounds with a whole warp per query, 6 with
+// 8 lanes, 17 with one lane (plain binary search).  More lanes per query shorten the chain but load more sectors,
+// so the launcher picks LPQ from the batch size: a whole warp per query while the queries do not fill the machine,
+// down to one lane per query (minimum traffic) once they do.  The warp then emits the n output slots of its queries
+// cooperatively so that the stores to the [Q, n] outputs are coalesced.
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -20,6 +25,37 @@ __device__ __forceinline__ int64_t lower_bound_ts(const double* __restrict__ ts,
     return lo;
 }
 
+// (LPQ+1)-ary lower bound shared by the LPQ consecutive lanes of a query group; every lane of the group returns the
+// same index.  `gmask` = the lanes of the calling group, `sub` = lane index inside it.  All 32 lanes of the warp call
+// this together (groups whose query is out of range pass lo == hi and fall through).
+template <int LPQ>
+__device__ __forceinline__ int64_t lower_bound_coop(const double* __restrict__ ts, int64_t lo, int64_t hi, double t,
+                                                    int sub, int gshift) {
+    if (LPQ == 1) return lower_bound_ts(ts, lo, hi, t);
+    const unsigned gmask = (LPQ == 32) ? 0xffffffffu : (((1u << LPQ) - 1u) << gshift);
+    // rounds are warp-uniform in count only per group, so the loop condition is voted over the whole warp
+    while (true) {
+        const int64_t s = hi - lo;
+        const bool wide = s > LPQ;
+        if (!__any_sync(0xffffffffu, wide)) break;
+        // split points p_j = lo + s (j + 1) / (LPQ + 1), j = 0 .. LPQ-1: strictly inside [lo, hi) and increasing when s > LPQ
+        const int64_t pj = lo + (s * (sub + 1)) / (LPQ + 1);
+        const bool pred = wide && (__ldg(ts + pj) < t);
+        const unsigned bal = __ballot_sync(0xffffffffu, pred) & gmask;
+        if (wide) {
+            const int c = __popc(bal);                      // predicates are monotone: the first c split points are < t
+            const int64_t nlo = c ? lo + (s * c) / (LPQ + 1) + 1 : lo;
+            const int64_t nhi = c < LPQ ? lo + (s * (c + 1)) / (LPQ + 1) : hi;
+            lo = nlo; hi = nhi;
+        }
+    }
+    // at most LPQ candidates left: one probe each
+    const bool pred = (lo + sub < hi) && (__ldg(ts + lo + sub) < t);
+    const unsigned bal = __ballot_sync(0xffffffffu, pred) & gmask;
+    return lo + __popc(bal);
+}
+
+template <int LPQ>
 __global__ void __launch_bounds__(256)
 neighbor_recent_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ adj_nbr,
                        const int32_t* __restrict__ adj_eidx, const double* __restrict__ adj_ts,
@@ -27,31 +63,32 @@ neighbor_recent_kernel(const int64_t* __restrict__ rowptr, const int32_t* __rest
                        int64_t Q, int n,
                        int32_t* __restrict__ out_nbr, int32_t* __restrict__ out_eidx,
                        float* __restrict__ out_etime, float* __restrict__ out_dt) {
+    constexpr int QPW = 32 / LPQ;                     // queries per warp-iteration
     const int lane = threadIdx.x & 31;
+    const int grp = lane / LPQ, sub = lane % LPQ;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t base = warp * 32; base < Q; base += nwarps * 32) {
-        const int64_t q = base + lane;
-        long long end = 0;
-        int cnt = 0;
+    for (int64_t base = warp * QPW; base < Q; base += nwarps * QPW) {
+        const int64_t q = base + grp;
+        int64_t lo = 0, hi = 0;
         double t = 0.0;
         if (q < Q) {
-            const int node = q_nodes[q];
-            t = q_ts[q];
-            const int64_t lo = rowptr[node], hi = rowptr[node + 1];
-            end = lower_bound_ts(adj_ts, lo, hi, t);
-            const int64_t c = end - lo;
-            cnt = c > n ? n : (int)c;          // only the most recent n are ever taken (utils.py:207-209)
+            const int node = __ldg(q_nodes + q);
+            t = __ldg(q_ts + q);
+            lo = __ldg(rowptr + node); hi = __ldg(rowptr + node + 1);
         }
-        const int nq = (Q - base) < 32 ? (int)(Q - base) : 32;
+        const long long end = lower_bound_coop<LPQ>(adj_ts, lo, hi, t, sub, grp * LPQ);
+        const int64_t c = end - lo;
+        const int cnt = c > n ? n : (int)c;           // only the most recent n are ever taken (utils.py:207-209)
+        const int nq = (Q - base) < QPW ? (int)(Q - base) : QPW;
         const int total = nq * n;
         for (int e0 = 0; e0 < total; e0 += 32) {
             const int e = e0 + lane;
             const bool live = e < total;
             const int ql = live ? e / n : 0;
-            const long long end_q = __shfl_sync(0xffffffffu, end, ql);
-            const int cnt_q = __shfl_sync(0xffffffffu, cnt, ql);
-            const double t_q = __shfl_sync(0xffffffffu, t, ql);
+            const long long end_q = __shfl_sync(0xffffffffu, end, ql * LPQ);
+            const int cnt_q = __shfl_sync(0xffffffffu, cnt, ql * LPQ);
+            const double t_q = __shfl_sync(0xffffffffu, t, ql * LPQ);
             if (live) {
                 const int j = e - ql * n;
                 const int jj = j - (n - cnt_q);      // right-aligned, left zero-padded (utils.py:216-218)
@@ -80,12 +117,15 @@ __global__ void __launch_bounds__(128)
 neighbor_uniform_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ adj_nbr,
                         const int32_t* __restrict__ adj_eidx, const double* __restrict__ adj_ts,
                         const int32_t* __restrict__ q_nodes, const double* __restrict__ q_ts,
-                        int64_t Q, int n, uint32_t k0, uint32_t k1, uint32_t call_id,
+                        int64_t Q, int n, uint32_t k0, uint32_t k1, uint32_t call_id_host,
+                        const uint32_t* __restrict__ call_ctr,
                         int32_t* __restrict__ out_nbr, int32_t* __restrict__ out_eidx,
                         float* __restrict__ out_etime, float* __restrict__ out_dt) {
     // uniform-with-replacement mode (utils.py:193-204); slot j of query q draws
     // pos = mulhi32(philox(q, call_id, j, PURPOSE_NBR).x, i) and the picks are ordered by
-    // (fp32 time, position): see oracle/graph.py for the contract.
+    // (fp32 time, position): see oracle/graph.py for the contract.  call_id = host part + device counter, so a
+    // captured CUDA graph of the step draws a fresh stream on every replay (the counter is bumped on the stream).
+    const uint32_t call_id = call_id_host + (call_ctr ? *call_ctr : 0u);
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < Q; q += (int64_t)gridDim.x * blockDim.x) {
         const int node = q_nodes[q];
         const double t = q_ts[q];
@@ -251,9 +291,19 @@ __global__ void map_slots_kernel(const int32_t* __restrict__ ids, int64_t count,
 
 }  // namespace
 
+template <int LPQ>
+static void launch_recent(const int64_t* rowptr, const int32_t* adj_nbr, const int32_t* adj_eidx, const double* adj_ts,
+                          const int32_t* q_nodes, const double* q_ts, int64_t Q, int n, int32_t* out_nbr,
+                          int32_t* out_eidx, float* out_etime, float* out_dt, cudaStream_t s) {
+    const int64_t threads = Q * LPQ;
+    neighbor_recent_kernel<LPQ><<<pfo_grid(threads, 256, 8), 256, 0, s>>>(
+        rowptr, adj_nbr, adj_eidx, adj_ts, q_nodes, q_ts, Q, n, out_nbr, out_eidx, out_etime, out_dt);
+}
+
 PFO_API int pfo_neighbor_sample(const int64_t* rowptr, const int32_t* adj_nbr, const int32_t* adj_eidx,
                                 const double* adj_ts, const int32_t* q_nodes, const double* q_ts,
                                 int64_t n_queries, int n_neighbors, int uniform, uint64_t seed, uint32_t call_id,
+                                const uint32_t* call_ctr, int lanes_per_query,
                                 int32_t* out_nbr, int32_t* out_eidx, float* out_etime, float* out_dt,
                                 void* stream) {
     if (n_queries <= 0) return 0;
@@ -263,11 +313,29 @@ PFO_API int pfo_neighbor_sample(const int64_t* rowptr, const int32_t* adj_nbr, c
         if (n_neighbors > PFO_MAX_UNIFORM_NBR) return (int)cudaErrorInvalidValue;
         neighbor_uniform_kernel<<<pfo_grid(n_queries, 128, 8), 128, 0, s>>>(
             rowptr, adj_nbr, adj_eidx, adj_ts, q_nodes, q_ts, n_queries, n_neighbors,
-            (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), call_id, out_nbr, out_eidx, out_etime, out_dt);
+            (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), call_id, call_ctr, out_nbr, out_eidx, out_etime,
+            out_dt);
     } else {
-        neighbor_recent_kernel<<<pfo_grid(n_queries, 256, 8), 256, 0, s>>>(
-            rowptr, adj_nbr, adj_eidx, adj_ts, q_nodes, q_ts, n_queries, n_neighbors,
-            out_nbr, out_eidx, out_etime, out_dt);
+        // lanes per query: as many as keep every warp of the launch resident at once (148 SMs x 64 warps), so the
+        // dependent-probe chain is as short as the batch allows; one lane per query (least traffic) for large batches
+        int lpq = lanes_per_query;
+        if (lpq <= 0) {
+            const int64_t resident = (int64_t)pfo_num_sms() * 64 * 32;      // threads
+            lpq = 32;
+            while (lpq > 1 && n_queries * lpq > resident) lpq >>= 1;
+            if (lpq == 16) lpq = 8;
+            if (lpq == 2) lpq = 1;
+        }
+#define PFO_K1(L) launch_recent<L>(rowptr, adj_nbr, adj_eidx, adj_ts, q_nodes, q_ts, n_queries, n_neighbors, \
+                                   out_nbr, out_eidx, out_etime, out_dt, s)
+        switch (lpq) {
+            case 32: PFO_K1(32); break;
+            case 8: PFO_K1(8); break;
+            case 4: PFO_K1(4); break;
+            case 1: PFO_K1(1); break;
+            default: return (int)cudaErrorInvalidValue;
+        }
+#undef PFO_K1
     }
     PFO_LAUNCH_CHECK();
 }

@@ -555,6 +555,40 @@ PFO_API int pfo_time_embedding_bwd(const int32_t* q_nodes, int64_t Q, int d, con
     PFO_LAUNCH_CHECK();
 }
 
+// TimeEncode.forward on its own (model/time_encoding.py:17-25): out[m, c] = cos(fmaf(t[m], w[c], b[c])), optionally the
+// sine too.  mode 0 = the per-warp choice the fused kernels make (pfo_math.cuh), 1 = fp64 reduction, 2 = fp32 Cody-Waite
+// reduction (only valid for |argument| < 2^17): the parity tests compare the two reductions through this entry point.
+static __global__ void time_encode_kernel(const float* __restrict__ t, const float* __restrict__ w,
+                                          const float* __restrict__ b, int64_t M, int d, int mode,
+                                          float* __restrict__ out_cos, float* __restrict__ out_sin) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t m = warp; m < M; m += nwarps) {
+        const float tm = t[m];
+        for (int c0 = 0; c0 < d; c0 += 32) {          // warp-uniform trip count; lanes past d idle on a zero argument
+            const int c = c0 + lane;
+            const float x = c < d ? fmaf(tm, w[c], b[c]) : 0.0f;
+            float sn, cs;
+            if (mode == 1) pfo_sincosf_f64(x, &sn, &cs);
+            else if (mode == 2) pfo_sincosf_f32(x, &sn, &cs);
+            else pfo_sincosf(x, &sn, &cs);
+            if (c < d) {
+                out_cos[m * d + c] = cs;
+                if (out_sin) out_sin[m * d + c] = sn;
+            }
+        }
+    }
+}
+
+PFO_API int pfo_time_encode(const float* t, const float* w, const float* b, int64_t M, int d, int mode,
+                            float* out_cos, float* out_sin, void* stream) {
+    if (M <= 0) return 0;
+    if (d <= 0 || mode < 0 || mode > 2) return (int)cudaErrorInvalidValue;
+    time_encode_kernel<<<pfo_grid(M * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(t, w, b, M, d, mode, out_cos, out_sin);
+    PFO_LAUNCH_CHECK();
+}
+
 PFO_API int pfo_reduce_partials(const float* partial, int rows, int cols, float* out, int accumulate, void* stream) {
     if (cols <= 0) return 0;
     reduce_partials_kernel<<<cols >= 32 ? (cols + 31) / 32 : cols, 256, 0, (cudaStream_t)stream>>>(partial, rows, cols, out, accumulate);

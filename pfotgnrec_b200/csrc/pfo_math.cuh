@@ -2,24 +2,20 @@
 //
 // TimeEncode arguments dt*w+b reach 1e13 rad on YYYYMMDDhhmmss timestamps (SURVEY.md hard part 1),
 // far beyond the 105615 rad where CUDA's cosf switches to a ~100-instruction, divergent,
-// local-memory slow path.  The fp32 argument is exact in fp64, so the quadrant reduction
-//     k = rint(x * 2/pi),   r = x - k*pi/2   (two fp64 fmas with a hi/lo split of pi/2)
-// is accurate to ~1e-16 for every |x| < 2^44, after which r in [-pi/4, pi/4] is rounded to fp32 and
-// fed to the classic single-precision minimax polynomials.  Absolute error <= ~1.5e-7 (about
-// 2 ulp of 1.0), the same class as cosf itself, at ~25 uniform instructions.
+// local-memory slow path.  Two quadrant reductions k = rint(x * 2/pi), r = x - k*pi/2 feed the same classic
+// single-precision minimax polynomials on [-pi/4, pi/4]:
+//   * fp64 (any |x| < 2^44): the fp32 argument is exact in fp64; two fp64 fmas with a hi/lo split of pi/2 give r to
+//     ~1e-16 before it is rounded to fp32.  Costs two conversions and four fp64 operations per argument.
+//   * fp32 Cody-Waite (|x| < 2^17): three fp32 fmas with a three-way split of pi/2.  r differs from the fp64 one by at
+//     most one rounding, the results by at most 1 ulp of 1.0 (tests/test_gpu_kernels.py::test_time_encode_cos_paths).
+// `pfo_cosf` / `pfo_sincosf` choose per WARP (one vote, no divergence): the fp32 path when every lane's argument is
+// small -- day-scale time deltas, the "small" streams -- else the fp64 path for the whole warp.
+// Absolute error <= ~1.5e-7 (about 2 ulp of 1.0), the same class as cosf itself.
 #pragma once
 
-__device__ __forceinline__ void pfo_sincosf(float x, float* s, float* c) {
-    const double xd = (double)x;
-    // k = rint(x * 2/pi) by the magic-number trick (|k| < 2^51): the biased sum holds k in its low mantissa bits, so
-    // the quadrant comes from a register move instead of an F2I.S64 and the rounding from a DADD instead of an FRND
-    // (conversions issue at a quarter of the fp64 FMA rate)
-    const double t = fma(xd, 0.63661977236758134308, 6755399441055744.0);   // 2/pi, 1.5 * 2^52
-    const int q = __double2loint(t) & 3;
-    const double kd = t - 6755399441055744.0;
-    double r = fma(-kd, 1.57079632679489655800e+00, xd);            // pi/2 (hi)
-    r = fma(-kd, 6.12323399573676603587e-17, r);                    // pi/2 (lo)
-    const float rf = (float)r;
+#define PFO_COS_FP32_LIMIT 131072.0f
+
+__device__ __forceinline__ void pfo_sincos_poly(float rf, int q, float* s, float* c) {
     const float r2 = rf * rf;
     const float sn = fmaf(rf * r2, fmaf(r2, fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f), -1.6666654611e-1f), rf);
     const float cs = fmaf(r2 * r2, fmaf(r2, fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f),
@@ -29,6 +25,39 @@ __device__ __forceinline__ void pfo_sincosf(float x, float* s, float* c) {
     *s = (q & 2) ? -s0 : s0;
     *c = ((q + 1) & 2) ? -c0 : c0;
 }
+
+__device__ __forceinline__ void pfo_sincosf_f64(float x, float* s, float* c) {
+    const double xd = (double)x;
+    // k = rint(x * 2/pi) by the magic-number trick (|k| < 2^51): the biased sum holds k in its low mantissa bits, so
+    // the quadrant comes from a register move instead of an F2I.S64 and the rounding from a DADD instead of an FRND
+    // (conversions issue at a quarter of the fp64 FMA rate)
+    const double t = fma(xd, 0.63661977236758134308, 6755399441055744.0);   // 2/pi, 1.5 * 2^52
+    const int q = __double2loint(t) & 3;
+    const double kd = t - 6755399441055744.0;
+    double r = fma(-kd, 1.57079632679489655800e+00, xd);            // pi/2 (hi)
+    r = fma(-kd, 6.12323399573676603587e-17, r);                    // pi/2 (lo)
+    pfo_sincos_poly((float)r, q, s, c);
+}
+
+__device__ __forceinline__ void pfo_sincosf_f32(float x, float* s, float* c) {
+    // valid for |x| < PFO_COS_FP32_LIMIT (k < 2^17, well inside the 2^22 range of the fp32 magic number)
+    const float t = fmaf(x, 0.63661977236758134308f, 12582912.0f);          // 2/pi, 1.5 * 2^23
+    const int q = __float_as_int(t) & 3;
+    const float kf = t - 12582912.0f;
+    float r = fmaf(-kf, 1.57079601e+00f, x);                                // pi/2 split three ways (Cody-Waite)
+    r = fmaf(-kf, 3.13916473e-07f, r);
+    r = fmaf(-kf, 5.39030253e-15f, r);
+    pfo_sincos_poly(r, q, s, c);
+}
+
+__device__ __forceinline__ void pfo_sincosf(float x, float* s, float* c) {
+    // the vote runs over the lanes that are converged here (every call site is warp-uniform control flow)
+    if (__all_sync(__activemask(), fabsf(x) < PFO_COS_FP32_LIMIT)) pfo_sincosf_f32(x, s, c);
+    else pfo_sincosf_f64(x, s, c);
+}
+
+__device__ __forceinline__ float pfo_cosf_f64(float x) { float s, c; pfo_sincosf_f64(x, &s, &c); return c; }
+__device__ __forceinline__ float pfo_cosf_f32(float x) { float s, c; pfo_sincosf_f32(x, &s, &c); return c; }
 
 __device__ __forceinline__ float pfo_cosf(float x) {
     float s, c;

@@ -703,7 +703,13 @@ class TGNStepFunction(torch.autograd.Function):
         tree = None
         id_lists = [q_nodes]
         if c.graph:
+            nf = eng.nf
+            calls0 = getattr(nf, "call_id", 0)
             tree = eng._sample_tree(q_nodes, q_ts, c.n_layers, n)
+            if getattr(nf, "call_ctr", None) is not None and torch.cuda.is_current_stream_capturing():
+                # uniform sampling inside a captured step: the host call ids are baked into the graph, the device
+                # counter advances by the step's number of K1 calls on every replay (fresh Philox streams)
+                nf.call_ctr.add_(nf.call_id - calls0)
             id_lists = []
             eng._collect_level0(tree, id_lists)
         sb = batch.get("state", batch)                  # interactions that advance the state (default: the embedded ones)

@@ -68,6 +68,10 @@ class NeighborFinder:
         self.uniform = bool(uniform)
         self.seed = int(seed)
         self.call_id = 0
+        # device part of the uniform mode's call counter: a captured CUDA graph bakes `call_id` in, so the step bumps
+        # this counter on the stream instead (engine.TGNStepFunction) and every replay draws a fresh Philox stream
+        self.call_ctr = torch.zeros(1, dtype=torch.int32, device=csr.device) if self.uniform else None
+        self.lanes_per_query = 0        # K1 search width: 0 = chosen by the kernel launcher from the query count
 
     # device API used by the engine -----------------------------------------------------
     def sample(self, q_nodes: torch.Tensor, q_ts: torch.Tensor, n_neighbors: int, out=None):
@@ -88,7 +92,7 @@ class NeighborFinder:
         c = self.csr
         _lib.call("pfo_neighbor_sample", _lib.ptr(c.rowptr), _lib.ptr(c.nbr), _lib.ptr(c.eidx), _lib.ptr(c.ts),
                   _lib.ptr(q_nodes), _lib.ptr(q_ts), Q, n, int(self.uniform), self.seed, self.call_id,
-                  _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(out[3]))
+                  _lib.ptr(self.call_ctr), int(self.lanes_per_query), _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(out[3]))
         self.call_id += 1
         return out
 

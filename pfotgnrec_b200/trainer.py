@@ -277,7 +277,7 @@ class PfoTrainer:
     # ---- CUDA-graph replay.  Every shape of the step is a function of the batch size alone (the unique-node
     # count lives on the device, kernels read it there), so one graph per batch size covers the stream.
     def _graph_ok(self, B):
-        return bool(self.tc.cuda_graph) and self.device.type == "cuda" and self.tc.model != "tgat"
+        return bool(self.tc.cuda_graph) and self.device.type == "cuda"
 
     def _step_graph(self, B):
         sg = self._graphs.get(B)

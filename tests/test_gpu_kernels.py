@@ -73,6 +73,85 @@ def test_neighbors_empty_and_delta():
     assert z[0].shape == (2, 1) and not z[0].any()
 
 
+@pytest.mark.parametrize("lpq", [1, 4, 8, 32, 0])
+def test_neighbors_cooperative_search_every_width(lpq):
+    """The (lanes+1)-ary cooperative lower-bound search of K1 at every lanes-per-query width (0 = the launcher's
+    choice): golden rows bit-exact, and a stream with heavy rows (a few stocks holding thousands of entries, ties in
+    the timestamps, queries before the first / after the last entry, ragged query counts) bit-exact against the
+    oracle's np.searchsorted (utils/utils.py:150-220)."""
+    from oracle.graph import AdjacencyOracle
+    from pfotgnrec_b200.graph import TemporalCSR, NeighborFinder
+    z = load_golden("neighbors.npz")
+    for name in ("small", "nbg"):
+        csr = TemporalCSR(z[f"{name}_sources"], z[f"{name}_destinations"], z[f"{name}_edge_idxs"],
+                          z[f"{name}_timestamps"], n_nodes=int(z[f"{name}_n_nodes"]), device=DEV)
+        nf = NeighborFinder(csr)
+        nf.lanes_per_query = lpq
+        for n in (10, 3, 1):
+            nb, ei, et = nf.get_temporal_neighbor(z[f"{name}_nodes"], z[f"{name}_ts"], n)
+            assert np.array_equal(nb, z[f"{name}_n{n}_nbr"]) and np.array_equal(ei, z[f"{name}_n{n}_eidx"])
+            assert np.array_equal(et, z[f"{name}_n{n}_etime"])
+    st = _stream(U=300, I=6, E=40000, mode="small", seed=17)        # 6 stocks x ~6 700 entries each, tied timestamps
+    adj = AdjacencyOracle(st.sources, st.destinations, st.edge_idxs, st.timestamps, n_nodes=st.n_nodes)
+    csr = TemporalCSR(st.sources, st.destinations, st.edge_idxs, st.timestamps, n_nodes=st.n_nodes, device=DEV)
+    nf = NeighborFinder(csr)
+    nf.lanes_per_query = lpq
+    rng = np.random.default_rng(lpq)
+    for Q in (1, 31, 33, 4099):
+        nodes = np.where(rng.random(Q) < 0.7, rng.integers(st.n_users + 1, st.n_nodes, size=Q),
+                         rng.integers(0, st.n_nodes, size=Q))
+        ts = st.timestamps[rng.integers(0, st.n_events, size=Q)] + rng.integers(-1, 2, size=Q)
+        ts[:1] = -3.0
+        ts[-1:] = st.timestamps[-1] + 10
+        for n in (10, 20, 1):
+            a = nf.get_temporal_neighbor(nodes, ts, n)
+            b = adj.get_temporal_neighbor(nodes, ts, n)
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y), (lpq, Q, n)
+
+
+def test_time_encode_cos_paths():
+    """TimeEncode (model/time_encoding.py:17-25) through pfo_time_encode: the fp32 Cody-Waite reduction agrees with the
+    fp64 reduction to <= 1 ulp of 1.0 on every argument below its 2^17 limit (cos and sin), both stay within 2e-7 of
+    the fp64 libm value, the per-warp choice equals one of the two bit for bit, and beyond the limit the choice is the
+    fp64 path (arguments ~1e10 rad on NBG-format time deltas)."""
+    from pfotgnrec_b200 import _lib
+    from pfotgnrec_b200._lib import ptr
+    d = 64
+    g = torch.Generator(device="cuda").manual_seed(0)
+    w = torch.tensor(1.0 / 10 ** np.linspace(0, 9, d), dtype=torch.float32, device=DEV)
+    b = torch.rand(d, device=DEV, generator=g)
+
+    def run(t, mode):
+        M = t.shape[0]
+        c, s_ = torch.empty(M, d, device=DEV), torch.empty(M, d, device=DEV)
+        _lib.call("pfo_time_encode", ptr(t), ptr(w), ptr(b), M, d, mode, ptr(c), ptr(s_))
+        return c, s_
+
+    ulp = float(np.spacing(np.float32(1.0)))
+    t_small = (torch.rand(20000, device=DEV, generator=g) * 2 - 1) * 131000.0
+    c64, s64 = run(t_small, 1)
+    c32, s32 = run(t_small, 2)
+    ca, sa = run(t_small, 0)
+    assert float((c32 - c64).abs().max()) <= 1.0 * ulp + 1e-12
+    assert float((s32 - s64).abs().max()) <= 1.0 * ulp + 1e-12
+    assert torch.equal(ca, c32) and torch.equal(sa, s32)              # every argument below the limit: the fp32 path
+    x = torch.addcmul(b.double(), t_small.double()[:, None], w.double())          # fmaf(t, w, b) exactly, rounded once below
+    x = x.float().double()
+    assert float((c64.double() - torch.cos(x)).abs().max()) < 2e-7
+    assert float((c32.double() - torch.cos(x)).abs().max()) < 2e-7
+    assert float((s32.double() - torch.sin(x)).abs().max()) < 2e-7
+    sign = torch.where(torch.rand(20000, device=DEV, generator=g) < 0.5, -1.0, 1.0)
+    t_big = sign * (1.0e9 + torch.rand(20000, device=DEV, generator=g) * 1.0e10)
+    cb, sb = run(t_big, 0)
+    c64b, s64b = run(t_big, 1)
+    # columns 0..31 share a warp instruction with column 0 (w = 1, |x| >= 1e9): the vote picks the fp64 path
+    assert torch.equal(cb[:, :32], c64b[:, :32]) and torch.equal(sb[:, :32], s64b[:, :32])
+    assert float((cb - c64b).abs().max()) <= 1.0 * ulp + 1e-12
+    xb = torch.addcmul(b.double(), t_big.double()[:, None], w.double()).float().double()
+    assert float((cb.double() - torch.cos(xb)).abs().max()) < 2e-7
+
+
 # ------------------------------------------------------------------------------ compaction
 def test_unique_node_compaction():
     from pfotgnrec_b200 import _lib

@@ -274,6 +274,7 @@ def test_fit_epoch_loop_matches_manual_loop():
     assert (t0, e1) == (0, st.n_events) and t1 == v0 and v1 == e0 and (t1 - t0) % 200 != 0      # a short last batch
     for epoch in range(2):
         b.tgn.memory.__init_memory__()
+        b.epoch = epoch                      # the candidate streams are keyed by the epoch (fresh draws, main.py:194-195)
         losses = [float(b.train_step(s, min(t1, s + 200)).item()) for s in range(t0, t1, 200)]
         want = {"epoch": epoch, "loss": float(np.mean(np.asarray(losses, dtype=np.float32)))}
         want.update(b.evaluate(v0, v1, bs=200, EVAL="valid"))

@@ -82,7 +82,7 @@ def test_c_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
-    assert lib.pfo_abi_version() == 1
+    assert lib.pfo_abi_version() == 2
 
 
 def test_product_path_never_imports_the_oracle():
