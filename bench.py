@@ -41,9 +41,9 @@ def parse():
                     help="fp32 = 3xTF32 on tcgen05 (1e-5 contract, default); tf32 / bf16 = 2e-2 contract; simt = FFMA")
     ap.add_argument("--dropout", type=float, default=0.1, help="attention dropout (reference main.py:29 default)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of one CUDA graph")
-    ap.add_argument("--parallelism", default="replicated", choices=["replicated", "sharded"],
-                    help="N > 1: replicated state + data-parallel interactions (default), or node-sharded state with "
-                         "all-to-all routing (pfotgnrec_b200/dist.py)")
+    ap.add_argument("--parallelism", default="sharded", choices=["replicated", "sharded"],
+                    help="N > 1: node-sharded state (owner = node mod N) with device-planned all-to-all routing "
+                         "(pfotgnrec_b200/dist.py, the default), or replicated state + data-parallel interactions")
     ap.add_argument("--eval-steps", type=int, default=8)
     ap.add_argument("--eval-bs", type=int, default=512, help="users per evaluation batch and GPU (reference --bs default)")
     ap.add_argument("--large-bs", type=int, default=65536,
@@ -407,6 +407,8 @@ def main():
     if world > 1 and a.parallelism == "sharded":
         from pfotgnrec_b200.dist import ShardedTrainer
         tr = ShardedTrainer(st, tc, dev, rank, world)
+        if a.no_graph:
+            tr.tc.cuda_graph = False
     elif world > 1:
         from pfotgnrec_b200.trainer import ReplicatedTrainer
         tr = ReplicatedTrainer(st, tc, dev, rank, world)
@@ -458,6 +460,8 @@ def main():
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         total_ms = float(t.item())
     clk = clocks.stop() if rank == 0 else None
+    if hasattr(tr, "ex"):
+        tr.ex.check_overflow()                       # a calibrated bucket that overflowed would have dropped rows
     events_per_step = bs * world
     value = a.steps * events_per_step / (total_ms * 1e-3)
 
@@ -551,7 +555,7 @@ def main():
 
     # ---- eval users/sec (the second half of the metric): full ranking over all stocks, users split over the ranks
     eval_users, eval_roofline = None, None
-    if a.eval_steps > 0 and hasattr(tr, "eval_step") and (world == 1 or a.parallelism == "replicated"):
+    if a.eval_steps > 0 and hasattr(tr, "eval_step"):
         ebs = a.eval_bs * world                      # global evaluation batch
         for _ in range(3):                           # two eager steps, then the graph is captured
             tr.eval_step(*cur.take(ebs))

@@ -30,11 +30,15 @@ int pfo_abi_version(void);
  * (:193-204) driven by the shared Philox stream (counter = (query, call, slot, 3)) with
  * call = call_id + *call_ctr (call_ctr may be NULL): the device part lets a captured CUDA graph draw a fresh
  * stream on every replay.  lanes_per_query (most-recent mode): 1, 4, 8 or 32 lanes of a warp share one query's
- * lower-bound search ((lanes+1)-ary, one dependent probe round per factor of lanes+1); 0 = chosen from n_queries. */
+ * lower-bound search ((lanes+1)-ary, one dependent probe round per factor of lanes+1); 0 = chosen from n_queries.
+ * Node-sharded use (queries routed to the rank that owns their CSR row): q_nodes[q] < 0 marks an empty routing slot
+ * (its outputs are zero rows); q_ids (may be NULL) = the id of each query in the un-sharded query list, which keys the
+ * uniform mode's stream so the draws do not depend on the number of ranks; ld_out (0 = n_neighbors) = row stride of
+ * the four outputs, so that they can be column blocks of one reply row; out_etime may be NULL. */
 int pfo_neighbor_sample(const int64_t* rowptr, const int32_t* adj_nbr, const int32_t* adj_eidx,
                         const double* adj_ts, const int32_t* q_nodes, const double* q_ts,
                         int64_t n_queries, int n_neighbors, int uniform, uint64_t seed, uint32_t call_id,
-                        const uint32_t* call_ctr, int lanes_per_query,
+                        const uint32_t* call_ctr, int lanes_per_query, const int32_t* q_ids, int64_t ld_out,
                         int32_t* out_nbr, int32_t* out_eidx, float* out_etime, float* out_dt, void* stream);
 
 /* ---- touched-node compaction (replaces the O(n_nodes) clone + Python loop of
@@ -145,6 +149,36 @@ int pfo_apply_messages(const int32_t* node, const int32_t* key, int64_t R, int d
                        const int32_t* slot_of_node, const float* Hnew, const float* rows, int64_t ldr,
                        const float* t32, float* memory, float* last_update, float* pend_msg, int64_t rawp,
                        float* pend_ts, uint8_t* pend_valid, int32_t* last_pos, void* stream);
+/* routed forms (device-side exchange plans): build writes each message into a row of `ldr` >= raw + 3 words followed by
+ * [owner-local node id = node / n_ranks | key = key_base + event (+ key_side on the destination side) | fp32 time];
+ * apply reads those three words from the received rows and skips empty slots (node id < 0). */
+int pfo_build_routed_messages(const int32_t* src_slot, const int32_t* dst_slot, const int32_t* src_node,
+                              const int32_t* dst_node, const int32_t* eidx, const double* ts, int B, int d, int F,
+                              const float* Hnew, const float* lu_u, const float* edge_feat, const float* tw,
+                              const float* tb, const float* other_emb_for_src, const float* other_emb_for_dst,
+                              int n_ranks, int key_base, int key_side, float* rows, int64_t ldr, void* stream);
+int pfo_apply_routed_messages(const float* rows, int64_t ldr, int64_t R, int d, int raw,
+                              const int32_t* slot_of_node, const float* Hnew, float* memory, float* last_update,
+                              float* pend_msg, int64_t rawp, float* pend_ts, uint8_t* pend_valid,
+                              int32_t* last_pos, void* stream);
+
+/* ---- device-side exchange plans of the node-sharded mode (no counterpart in the single-process reference; SURVEY.md
+ * section 8e).  plan: slot[i] = (ids[i] mod n_ranks) * cap + arrival order inside that bucket, -1 for dropped rows
+ * (ids[i] < 0, i >= *n_valid when n_valid != NULL, or bucket full -> *overflow |= 1); counts[g] = rows destined to
+ * rank g; local_id[i] = ids[i] / n_ranks (may be NULL).  scatter_rows / gather_words move rows of w 32-bit words into /
+ * out of their slots (gather fills rows whose slot is < 0 with `fill`).  pack / unpack_queries: the request rows of
+ * the neighbour exchange, [local node id | timestamp (2 words) | query id]. */
+int pfo_route_plan(const int32_t* ids, int64_t n_rows, const int32_t* n_valid, int n_ranks, int cap,
+                   int32_t* counts, int32_t* slot, int32_t* local_id, int32_t* overflow, void* stream);
+int pfo_scatter_rows(const void* src, int64_t lds, const int32_t* slot, int64_t M, int w, void* dst, int64_t ldd,
+                     void* stream);
+int pfo_gather_words(const void* src, int64_t lds, const int32_t* slot, int64_t M, int w, void* dst, int64_t ldd,
+                     uint32_t fill, void* stream);
+int pfo_pack_queries(const int32_t* local_id, const double* q_ts, const int32_t* q_ids, const int32_t* slot,
+                     int64_t n_queries, int32_t* out_rows, void* stream);
+int pfo_unpack_queries(const int32_t* in_rows, int64_t n_rows, int32_t* q_nodes, double* q_ts, int32_t* q_ids,
+                       void* stream);
+
 
 /* ---- jodie time-projection embedding --- modules/embedding_module.py:57-61, model/tgn.py:260-266 */
 int pfo_time_embedding_fwd(const int32_t* q_nodes, const double* q_ts, int64_t Q, int64_t n_src, int d,
@@ -158,8 +192,8 @@ int pfo_time_embedding_bwd(const int32_t* q_nodes, int64_t Q, int d, const int32
 
 /* small row utilities (gather with idx < 0 -> zero row; scatter-add = its gradient) */
 /* ---- TimeEncode.forward alone --- model/time_encoding.py:17-25: out_cos[m, c] = cos(fmaf(t[m], w[c], b[c])) (fmaf ==
- * nn.Linear(1, d) bit for bit), out_sin optional.  mode 0 = per-warp choice of the quadrant reduction as in the fused
- * kernels, 1 = fp64 reduction (any |x| < 2^44), 2 = fp32 Cody-Waite reduction (|x| < 2^17). */
+ * nn.Linear(1, d) bit for bit), out_sin optional.  mode 0 / 1 = the fp64 quadrant reduction the fused kernels use
+ * (any |x| < 2^44), 2 = fp32 Cody-Waite reduction (|x| < 2^17; kept for the comparison test). */
 int pfo_time_encode(const float* t, const float* w, const float* b, int64_t M, int d, int mode,
                     float* out_cos, float* out_sin, void* stream);
 int pfo_reduce_partials(const float* partial, int rows, int cols, float* out, int accumulate, void* stream);

@@ -16,7 +16,8 @@ LIB_PATH = os.path.join(_HERE, "libpfo_b200.so")
 P = c_void_p
 _SIGS = {
     "pfo_abi_version": (c_int, []),
-    "pfo_neighbor_sample": (c_int, [P, P, P, P, P, P, c_int64, c_int, c_int, c_uint64, c_uint32, P, c_int, P, P, P, P, P]),
+    "pfo_neighbor_sample": (c_int, [P, P, P, P, P, P, c_int64, c_int, c_int, c_uint64, c_uint32, P, c_int, P, c_int64,
+                                    P, P, P, P, P]),
     "pfo_mark_nodes": (c_int, [P, c_int64, c_int, P, P]),
     "pfo_compact_workspace_ints": (c_int64, [c_int64]),
     "pfo_compact_nodes": (c_int, [P, c_int64, P, P, P, P, P]),
@@ -40,6 +41,14 @@ _SIGS = {
                                         P, P, P, P]),
     "pfo_build_messages": (c_int, [P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_int64, P, P]),
     "pfo_apply_messages": (c_int, [P, P, c_int64, c_int, c_int, P, P, P, c_int64, P, P, P, P, c_int64, P, P, P, P]),
+    "pfo_build_routed_messages": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P, P, c_int, c_int,
+                                          c_int, P, c_int64, P]),
+    "pfo_apply_routed_messages": (c_int, [P, c_int64, c_int64, c_int, c_int, P, P, P, P, P, c_int64, P, P, P, P]),
+    "pfo_route_plan": (c_int, [P, c_int64, P, c_int, c_int, P, P, P, P, P]),
+    "pfo_scatter_rows": (c_int, [P, c_int64, P, c_int64, c_int, P, c_int64, P]),
+    "pfo_gather_words": (c_int, [P, c_int64, P, c_int64, c_int, P, c_int64, c_uint32, P]),
+    "pfo_pack_queries": (c_int, [P, P, P, P, c_int64, P, P]),
+    "pfo_unpack_queries": (c_int, [P, c_int64, P, P, P, P]),
     "pfo_time_embedding_fwd": (c_int, [P, P, c_int64, c_int64, c_int, P, P, P, c_float, c_float, c_float,
                                        c_float, P, P, P, P, P]),
     "pfo_time_embedding_bwd": (c_int, [P, c_int64, c_int, P, P, P, P, P, P, P, P, P, c_int64, P]),
@@ -70,7 +79,7 @@ LAUNCHES = 0            # kernels launched through this binding (bench.py report
 _LAUNCHES_PER_CALL = {"pfo_compact_nodes": 3, "pfo_fold_attention_fwd": 2, "pfo_fold_attention_bwd": 2,
                       "pfo_fold_attention_workspace_doubles": 0, "pfo_wgrad_f32": 2, "pfo_wgrad_tf32": 2,
                       "pfo_wgrad_tf32_workspace_floats": 0, "pfo_time_embedding_bwd": 2,
-                      "pfo_attn_nbr_bwd": 2, "pfo_bpr": 2, "pfo_eval_metrics": 2, "pfo_apply_messages": 2, "pfo_abi_version": 0,
+                      "pfo_attn_nbr_bwd": 2, "pfo_bpr": 2, "pfo_eval_metrics": 2, "pfo_apply_messages": 2, "pfo_apply_routed_messages": 2, "pfo_abi_version": 0,
                       "pfo_compact_workspace_ints": 0, "pfo_wgrad_workspace_floats": 0,
                       "pfo_attn_nbr_bwd_workspace_floats": 0}
 

@@ -16,6 +16,7 @@ SOURCES = {
     "linear_tma.cu": [],
     "wgrad_tma.cu": [],
     "memory_kernels.cu": [],
+    "route_kernels.cu": [],
     "attention_kernels.cu": [],
     "fold_kernels.cu": [],
     "mv_kernels.cu": ["-fmad=false"],

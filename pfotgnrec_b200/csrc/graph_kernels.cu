@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256)
 neighbor_recent_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ adj_nbr,
                        const int32_t* __restrict__ adj_eidx, const double* __restrict__ adj_ts,
                        const int32_t* __restrict__ q_nodes, const double* __restrict__ q_ts,
-                       int64_t Q, int n,
+                       int64_t Q, int n, int64_t ld,
                        int32_t* __restrict__ out_nbr, int32_t* __restrict__ out_eidx,
                        float* __restrict__ out_etime, float* __restrict__ out_dt) {
     constexpr int QPW = 32 / LPQ;                     // queries per warp-iteration
@@ -75,7 +75,7 @@ neighbor_recent_kernel(const int64_t* __restrict__ rowptr, const int32_t* __rest
         if (q < Q) {
             const int node = __ldg(q_nodes + q);
             t = __ldg(q_ts + q);
-            lo = __ldg(rowptr + node); hi = __ldg(rowptr + node + 1);
+            if (node >= 0) { lo = __ldg(rowptr + node); hi = __ldg(rowptr + node + 1); }   // node < 0: an empty routing slot
         }
         const long long end = lower_bound_coop<LPQ>(adj_ts, lo, hi, t, sub, grp * LPQ);
         const int64_t c = end - lo;
@@ -100,10 +100,10 @@ neighbor_recent_kernel(const int64_t* __restrict__ rowptr, const int32_t* __rest
                     ei = __ldg(adj_eidx + idx);
                     tt = (float)__ldg(adj_ts + idx);   // fp32 edge time (utils.py:179-180)
                 }
-                const int64_t o = base * n + e;
+                const int64_t o = (base + ql) * ld + j;
                 out_nbr[o] = nb;
                 out_eidx[o] = ei;
-                out_etime[o] = tt;
+                if (out_etime) out_etime[o] = tt;
                 // fp64 subtraction of the fp32-rounded edge time, then fp32 (embedding_module.py:133-135)
                 out_dt[o] = (float)(t_q - (double)tt);
             }
@@ -118,7 +118,7 @@ neighbor_uniform_kernel(const int64_t* __restrict__ rowptr, const int32_t* __res
                         const int32_t* __restrict__ adj_eidx, const double* __restrict__ adj_ts,
                         const int32_t* __restrict__ q_nodes, const double* __restrict__ q_ts,
                         int64_t Q, int n, uint32_t k0, uint32_t k1, uint32_t call_id_host,
-                        const uint32_t* __restrict__ call_ctr,
+                        const uint32_t* __restrict__ call_ctr, const int32_t* __restrict__ q_ids, int64_t ld,
                         int32_t* __restrict__ out_nbr, int32_t* __restrict__ out_eidx,
                         float* __restrict__ out_etime, float* __restrict__ out_dt) {
     // uniform-with-replacement mode (utils.py:193-204); slot j of query q draws
@@ -129,19 +129,23 @@ neighbor_uniform_kernel(const int64_t* __restrict__ rowptr, const int32_t* __res
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < Q; q += (int64_t)gridDim.x * blockDim.x) {
         const int node = q_nodes[q];
         const double t = q_ts[q];
-        const int64_t lo = rowptr[node], hi = rowptr[node + 1];
+        int64_t lo = 0, hi = 0;
+        if (node >= 0) { lo = rowptr[node]; hi = rowptr[node + 1]; }        // node < 0: an empty routing slot
         const uint32_t cnt = (uint32_t)(lower_bound_ts(adj_ts, lo, hi, t) - lo);
         uint32_t pos[PFO_MAX_UNIFORM_NBR];
         float tt[PFO_MAX_UNIFORM_NBR];
-        const int64_t o = q * n;
+        const int64_t o = q * ld;
+        // the stream is keyed by the query's id: its position in this launch, or -- when the queries were routed here
+        // from other ranks -- the position it has in the un-sharded query list (q_ids)
+        const uint32_t qid = q_ids ? (uint32_t)q_ids[q] : (uint32_t)q;
         if (cnt == 0) {
             for (int j = 0; j < n; ++j) {
-                out_nbr[o + j] = 0; out_eidx[o + j] = 0; out_etime[o + j] = 0.0f; out_dt[o + j] = (float)t;
+                out_nbr[o + j] = 0; out_eidx[o + j] = 0; if (out_etime) out_etime[o + j] = 0.0f; out_dt[o + j] = (float)t;
             }
             continue;
         }
         for (int j = 0; j < n; ++j) {
-            const uint32_t p = mulhi32(philox4x32_10((uint32_t)q, call_id, (uint32_t)j, PFO_PURPOSE_NBR, k0, k1).x, cnt);
+            const uint32_t p = mulhi32(philox4x32_10(qid, call_id, (uint32_t)j, PFO_PURPOSE_NBR, k0, k1).x, cnt);
             const float tj = (float)__ldg(adj_ts + lo + p);
             int k = j;                                   // insertion sort by (time, position)
             while (k > 0 && (tt[k - 1] > tj || (tt[k - 1] == tj && pos[k - 1] > p))) {
@@ -152,7 +156,7 @@ neighbor_uniform_kernel(const int64_t* __restrict__ rowptr, const int32_t* __res
         for (int j = 0; j < n; ++j) {
             out_nbr[o + j] = __ldg(adj_nbr + lo + pos[j]);
             out_eidx[o + j] = __ldg(adj_eidx + lo + pos[j]);
-            out_etime[o + j] = tt[j];
+            if (out_etime) out_etime[o + j] = tt[j];
             out_dt[o + j] = (float)(t - (double)tt[j]);
         }
     }
@@ -293,28 +297,30 @@ __global__ void map_slots_kernel(const int32_t* __restrict__ ids, int64_t count,
 
 template <int LPQ>
 static void launch_recent(const int64_t* rowptr, const int32_t* adj_nbr, const int32_t* adj_eidx, const double* adj_ts,
-                          const int32_t* q_nodes, const double* q_ts, int64_t Q, int n, int32_t* out_nbr,
+                          const int32_t* q_nodes, const double* q_ts, int64_t Q, int n, int64_t ld, int32_t* out_nbr,
                           int32_t* out_eidx, float* out_etime, float* out_dt, cudaStream_t s) {
     const int64_t threads = Q * LPQ;
     neighbor_recent_kernel<LPQ><<<pfo_grid(threads, 256, 8), 256, 0, s>>>(
-        rowptr, adj_nbr, adj_eidx, adj_ts, q_nodes, q_ts, Q, n, out_nbr, out_eidx, out_etime, out_dt);
+        rowptr, adj_nbr, adj_eidx, adj_ts, q_nodes, q_ts, Q, n, ld, out_nbr, out_eidx, out_etime, out_dt);
 }
 
 PFO_API int pfo_neighbor_sample(const int64_t* rowptr, const int32_t* adj_nbr, const int32_t* adj_eidx,
                                 const double* adj_ts, const int32_t* q_nodes, const double* q_ts,
                                 int64_t n_queries, int n_neighbors, int uniform, uint64_t seed, uint32_t call_id,
-                                const uint32_t* call_ctr, int lanes_per_query,
+                                const uint32_t* call_ctr, int lanes_per_query, const int32_t* q_ids, int64_t ld_out,
                                 int32_t* out_nbr, int32_t* out_eidx, float* out_etime, float* out_dt,
                                 void* stream) {
     if (n_queries <= 0) return 0;
     if (n_neighbors <= 0) return (int)cudaErrorInvalidValue;
+    const int64_t ld = ld_out > 0 ? ld_out : n_neighbors;
+    if (ld < n_neighbors) return (int)cudaErrorInvalidValue;
     cudaStream_t s = (cudaStream_t)stream;
     if (uniform) {
         if (n_neighbors > PFO_MAX_UNIFORM_NBR) return (int)cudaErrorInvalidValue;
         neighbor_uniform_kernel<<<pfo_grid(n_queries, 128, 8), 128, 0, s>>>(
             rowptr, adj_nbr, adj_eidx, adj_ts, q_nodes, q_ts, n_queries, n_neighbors,
-            (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), call_id, call_ctr, out_nbr, out_eidx, out_etime,
-            out_dt);
+            (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), call_id, call_ctr, q_ids, ld, out_nbr, out_eidx,
+            out_etime, out_dt);
     } else {
         // lanes per query: as many as keep every warp of the launch resident at once (148 SMs x 64 warps), so the
         // dependent-probe chain is as short as the batch allows; one lane per query (least traffic) for large batches
@@ -326,7 +332,7 @@ PFO_API int pfo_neighbor_sample(const int64_t* rowptr, const int32_t* adj_nbr, c
             if (lpq == 16) lpq = 8;
             if (lpq == 2) lpq = 1;
         }
-#define PFO_K1(L) launch_recent<L>(rowptr, adj_nbr, adj_eidx, adj_ts, q_nodes, q_ts, n_queries, n_neighbors, \
+#define PFO_K1(L) launch_recent<L>(rowptr, adj_nbr, adj_eidx, adj_ts, q_nodes, q_ts, n_queries, n_neighbors, ld, \
                                    out_nbr, out_eidx, out_etime, out_dt, s)
         switch (lpq) {
             case 32: PFO_K1(32); break;

@@ -315,7 +315,9 @@ build_messages_kernel(const int32_t* __restrict__ src_slot, const int32_t* __res
                       const float* __restrict__ Hnew, const float* __restrict__ lu_u,
                       const float* __restrict__ edge_feat, const float* __restrict__ tw, const float* __restrict__ tb,
                       const float* __restrict__ other_emb_for_src, const float* __restrict__ other_emb_for_dst,
-                      float* __restrict__ rows, int64_t ldr, float* __restrict__ t32_out) {
+                      float* __restrict__ rows, int64_t ldr, float* __restrict__ t32_out,
+                      const int32_t* __restrict__ src_node, const int32_t* __restrict__ dst_node, int n_ranks,
+                      int key_base, int key_side) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -337,13 +339,25 @@ build_messages_kernel(const int32_t* __restrict__ src_slot, const int32_t* __res
             out[2 * d + F + c] = pfo_cosf(fmaf(delta, tw[c], tb[c]));
         }
         for (int c = lane; c < F; c += 32) out[2 * d + c] = ef[c];
-        if (lane == 0) t32_out[idx] = t32;
+        if (lane == 0) {
+            if (t32_out) t32_out[idx] = t32;
+            if (src_node) {
+                // routed row: [message (raw) | owner-local node id | global batch position | fp32 time] -- the three
+                // words the owner's last-wins pass reads (key = side * B_global + rank * B + event)
+                const int raw = 3 * d + F;
+                const int node = is_src ? src_node[i] : dst_node[i];
+                int* meta = reinterpret_cast<int*>(out + raw);
+                meta[0] = node / n_ranks;
+                meta[1] = key_base + i + (is_src ? 0 : key_side);
+                meta[2] = __float_as_int(t32);
+            }
+        }
     }
 }
 
 // apply (owner side), pass 1: last-wins key + persist of the positives that had a pending message
 __global__ void __launch_bounds__(256)
-apply_rank_kernel(const int32_t* __restrict__ node, const int32_t* __restrict__ key, int64_t R, int d,
+apply_rank_kernel(const int32_t* __restrict__ node, const int32_t* __restrict__ key, int64_t meta_stride, int64_t R, int d,
                   const int32_t* __restrict__ slot_of_node, const float* __restrict__ Hnew,
                   const uint8_t* __restrict__ pend_valid, const float* __restrict__ pend_ts,
                   float* __restrict__ memory, float* __restrict__ last_update, int32_t* __restrict__ last_pos) {
@@ -351,8 +365,9 @@ apply_rank_kernel(const int32_t* __restrict__ node, const int32_t* __restrict__ 
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = warp; r < R; r += nwarps) {
-        const int v = node[r];
-        if (lane == 0) atomicMax(last_pos + v, key[r]);
+        const int v = node[r * meta_stride];
+        if (v < 0) continue;                              // empty routing slot
+        if (lane == 0) atomicMax(last_pos + v, key[r * meta_stride]);
         if (pend_valid[v]) {
             const float* h = Hnew + (int64_t)slot_of_node[v] * d;
             float* m = memory + (int64_t)v * d;
@@ -364,7 +379,7 @@ apply_rank_kernel(const int32_t* __restrict__ node, const int32_t* __restrict__ 
 
 // pass 2: the row with the largest global position per node becomes the pending message
 __global__ void __launch_bounds__(256)
-apply_store_kernel(const int32_t* __restrict__ node, const int32_t* __restrict__ key, int64_t R, int raw,
+apply_store_kernel(const int32_t* __restrict__ node, const int32_t* __restrict__ key, int64_t meta_stride, int64_t R, int raw,
                    const float* __restrict__ rows, int64_t ldr, const float* __restrict__ t32,
                    float* __restrict__ pend_msg, int64_t rawp, float* __restrict__ pend_ts,
                    uint8_t* __restrict__ pend_valid, int32_t* __restrict__ last_pos) {
@@ -372,14 +387,14 @@ apply_store_kernel(const int32_t* __restrict__ node, const int32_t* __restrict__
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = warp; r < R; r += nwarps) {
-        const int v = node[r];
-        if (last_pos[v] != key[r]) continue;
+        const int v = node[r * meta_stride];
+        if (v < 0 || last_pos[v] != key[r * meta_stride]) continue;
         __syncwarp();
         const float* in = rows + r * ldr;
         float* out = pend_msg + (int64_t)v * rawp;
         for (int c = lane; c < raw; c += 32) out[c] = in[c];
         __syncwarp();
-        if (lane == 0) { pend_ts[v] = t32[r]; pend_valid[v] = 1; last_pos[v] = -1; }
+        if (lane == 0) { pend_ts[v] = t32[r * meta_stride]; pend_valid[v] = 1; last_pos[v] = -1; }
     }
 }
 
@@ -556,8 +571,8 @@ PFO_API int pfo_time_embedding_bwd(const int32_t* q_nodes, int64_t Q, int d, con
 }
 
 // TimeEncode.forward on its own (model/time_encoding.py:17-25): out[m, c] = cos(fmaf(t[m], w[c], b[c])), optionally the
-// sine too.  mode 0 = the per-warp choice the fused kernels make (pfo_math.cuh), 1 = fp64 reduction, 2 = fp32 Cody-Waite
-// reduction (only valid for |argument| < 2^17): the parity tests compare the two reductions through this entry point.
+// sine too.  mode 0 / 1 = the fp64 quadrant reduction of the fused kernels (pfo_math.cuh), 2 = fp32 Cody-Waite reduction
+// (only valid for |argument| < 2^17): the parity tests compare the two reductions through this entry point.
 static __global__ void time_encode_kernel(const float* __restrict__ t, const float* __restrict__ w,
                                           const float* __restrict__ b, int64_t M, int d, int mode,
                                           float* __restrict__ out_cos, float* __restrict__ out_sin) {
@@ -616,7 +631,39 @@ PFO_API int pfo_build_messages(const int32_t* src_slot, const int32_t* dst_slot,
     if (B <= 0) return 0;
     build_messages_kernel<<<pfo_grid(2 * (int64_t)B * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(
         src_slot, dst_slot, eidx, ts, B, d, F, Hnew, lu_u, edge_feat, tw, tb, other_emb_for_src, other_emb_for_dst,
-        rows, ldr, t32_out);
+        rows, ldr, t32_out, nullptr, nullptr, 1, 0, 0);
+    PFO_LAUNCH_CHECK();
+}
+
+PFO_API int pfo_build_routed_messages(const int32_t* src_slot, const int32_t* dst_slot, const int32_t* src_node,
+                                      const int32_t* dst_node, const int32_t* eidx, const double* ts, int B, int d,
+                                      int F, const float* Hnew, const float* lu_u, const float* edge_feat,
+                                      const float* tw, const float* tb, const float* other_emb_for_src,
+                                      const float* other_emb_for_dst, int n_ranks, int key_base, int key_side,
+                                      float* rows, int64_t ldr, void* stream) {
+    if (B <= 0) return 0;
+    if (ldr < 3 * d + F + 3 || n_ranks <= 0) return (int)cudaErrorInvalidValue;
+    build_messages_kernel<<<pfo_grid(2 * (int64_t)B * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        src_slot, dst_slot, eidx, ts, B, d, F, Hnew, lu_u, edge_feat, tw, tb, other_emb_for_src, other_emb_for_dst,
+        rows, ldr, nullptr, src_node, dst_node, n_ranks, key_base, key_side);
+    PFO_LAUNCH_CHECK();
+}
+
+PFO_API int pfo_apply_routed_messages(const float* rows, int64_t ldr, int64_t R, int d, int raw,
+                                      const int32_t* slot_of_node, const float* Hnew, float* memory,
+                                      float* last_update, float* pend_msg, int64_t rawp, float* pend_ts,
+                                      uint8_t* pend_valid, int32_t* last_pos, void* stream) {
+    if (R <= 0) return 0;
+    if (ldr < raw + 3) return (int)cudaErrorInvalidValue;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int grid = pfo_grid(R * 32, 256, 8);
+    const int32_t* node = reinterpret_cast<const int32_t*>(rows) + raw;      // meta words behind the message
+    const int32_t* key = node + 1;
+    const float* t32 = rows + raw + 2;
+    apply_rank_kernel<<<grid, 256, 0, s>>>(node, key, ldr, R, d, slot_of_node, Hnew, pend_valid, pend_ts, memory,
+                                           last_update, last_pos);
+    apply_store_kernel<<<grid, 256, 0, s>>>(node, key, ldr, R, raw, rows, ldr, t32, pend_msg, rawp, pend_ts, pend_valid,
+                                            last_pos);
     PFO_LAUNCH_CHECK();
 }
 
@@ -627,9 +674,9 @@ PFO_API int pfo_apply_messages(const int32_t* node, const int32_t* key, int64_t 
     if (R <= 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     const int grid = pfo_grid(R * 32, 256, 8);
-    apply_rank_kernel<<<grid, 256, 0, s>>>(node, key, R, d, slot_of_node, Hnew, pend_valid, pend_ts, memory,
+    apply_rank_kernel<<<grid, 256, 0, s>>>(node, key, 1, R, d, slot_of_node, Hnew, pend_valid, pend_ts, memory,
                                            last_update, last_pos);
-    apply_store_kernel<<<grid, 256, 0, s>>>(node, key, R, raw, rows, ldr, t32, pend_msg, rawp, pend_ts, pend_valid,
+    apply_store_kernel<<<grid, 256, 0, s>>>(node, key, 1, R, raw, rows, ldr, t32, pend_msg, rawp, pend_ts, pend_valid,
                                             last_pos);
     PFO_LAUNCH_CHECK();
 }

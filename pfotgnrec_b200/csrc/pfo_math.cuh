@@ -2,14 +2,18 @@
 //
 // TimeEncode arguments dt*w+b reach 1e13 rad on YYYYMMDDhhmmss timestamps (SURVEY.md hard part 1),
 // far beyond the 105615 rad where CUDA's cosf switches to a ~100-instruction, divergent,
-// local-memory slow path.  Two quadrant reductions k = rint(x * 2/pi), r = x - k*pi/2 feed the same classic
-// single-precision minimax polynomials on [-pi/4, pi/4]:
-//   * fp64 (any |x| < 2^44): the fp32 argument is exact in fp64; two fp64 fmas with a hi/lo split of pi/2 give r to
-//     ~1e-16 before it is rounded to fp32.  Costs two conversions and four fp64 operations per argument.
-//   * fp32 Cody-Waite (|x| < 2^17): three fp32 fmas with a three-way split of pi/2.  r differs from the fp64 one by at
-//     most one rounding, the results by at most 1 ulp of 1.0 (tests/test_gpu_kernels.py::test_time_encode_cos_paths).
-// `pfo_cosf` / `pfo_sincosf` choose per WARP (one vote, no divergence): the fp32 path when every lane's argument is
-// small -- day-scale time deltas, the "small" streams -- else the fp64 path for the whole warp.
+// local-memory slow path (measured: 133 Gcos/s against 1 100 on such arguments, tools/cos_probe.cu).  Two quadrant
+// reductions k = rint(x * 2/pi), r = x - k*pi/2 feed the same classic single-precision minimax polynomials on
+// [-pi/4, pi/4]:
+//   * fp64 (any |x| < 2^44) -- THE PRODUCT PATH: the fp32 argument is exact in fp64; two fp64 fmas with a hi/lo split
+//     of pi/2 give r to ~1e-16 before it is rounded to fp32.  Two conversions and four fp64 operations per argument.
+//   * fp32 Cody-Waite (|x| < 2^17): three fp32 fmas with a three-way split of pi/2; within 1 ulp of 1.0 of the fp64
+//     path (tests/test_gpu_kernels.py::test_time_encode_cos_paths).
+// Measured on B200 (profiles/r2_cos_probe.txt): 1 088 Gcos/s for the fp64 reduction, 1 341 for the fp32 one -- fp64
+// FMAs issue at half the fp32 rate here, so the fp64 part is ~20 % of a cosine, not its bulk -- and choosing between
+// the two per warp (vote + branch) ran SLOWER than the fp64 path alone (1 049 Gcos/s with every argument small, 835 on
+// mixed warps; attention fwd / bwd 133 -> 149 us / 180 -> 204 us).  The kernels therefore always take the fp64
+// reduction; the fp32 one stays as `mode 2` of pfo_time_encode for the comparison test.
 // Absolute error <= ~1.5e-7 (about 2 ulp of 1.0), the same class as cosf itself.
 #pragma once
 
@@ -50,11 +54,7 @@ __device__ __forceinline__ void pfo_sincosf_f32(float x, float* s, float* c) {
     pfo_sincos_poly(r, q, s, c);
 }
 
-__device__ __forceinline__ void pfo_sincosf(float x, float* s, float* c) {
-    // the vote runs over the lanes that are converged here (every call site is warp-uniform control flow)
-    if (__all_sync(__activemask(), fabsf(x) < PFO_COS_FP32_LIMIT)) pfo_sincosf_f32(x, s, c);
-    else pfo_sincosf_f64(x, s, c);
-}
+__device__ __forceinline__ void pfo_sincosf(float x, float* s, float* c) { pfo_sincosf_f64(x, s, c); }
 
 __device__ __forceinline__ float pfo_cosf_f64(float x) { float s, c; pfo_sincosf_f64(x, &s, &c); return c; }
 __device__ __forceinline__ float pfo_cosf_f32(float x) { float s, c; pfo_sincosf_f32(x, &s, &c); return c; }

@@ -1,24 +1,30 @@
-"""Node-sharded multi-GPU path: one process per GPU, NCCL all-to-all.
+"""Node-sharded multi-GPU path: one process per GPU, state partitioned by node id.
 
-The reference is single-process; this module ADDS the sharding the north_star asks for:
+The reference is single-process (main.py:103); this module ADDS the sharding the north_star asks for:
 
-* owner(x) = x mod G.  Each rank owns, for its nodes only: memory, last_update, the pending
-  message table and the CSR adjacency rows (stored under the local index x // G).  Node and
-  edge features, the price table and the weights are replicated (static / tiny).
-* The global batch is split by event index (rank r takes the r-th slice); per step the ranks
-  exchange, with `all_to_all_single`:
-    R1  (node, t) queries -> owners, K1 on the local CSR rows, neighbour lists back;
-    R2  unique touched node ids -> owners, lazy GRU/RNN there (de-duplicated over all
-        requesters), updated-memory rows + last_update' back;
-    R3  (training) d(loss)/d(row) back to the owners, cell backward there;
-    R4  message rows built where the events live -> owners, persist + last-wins there, the
-        winner chosen by GLOBAL batch position so the result does not depend on G;
-  followed by one all-reduce of the ~133 k parameter gradients.
-* Every quantity is identical to the 1-GPU path on the same global batch up to fp32 summation
-  order (tools/check_sharded.py asserts it on 2 GPUs).
+* owner(x) = x mod G.  Each rank owns, for its nodes only: memory, last_update, the pending-message table and the
+  CSR adjacency rows (stored under the local index x // G).  Node and edge features, the price table and the weights
+  are replicated (static / small).
+* The global batch is split by interaction index (rank r takes the r-th slice); per step the ranks exchange
+    R1  (node, t) queries -> owners, K1 on the local CSR rows, neighbour lists back in the same slots;
+    R2  unique touched node ids -> owners, lazy GRU/RNN there (de-duplicated over all requesters), updated-memory
+        rows + last_update' back in the same slots;
+    R3  (training) d(loss)/d(row) back to the owners along R2's slots, cell backward there;
+    R4  message rows built where the interactions live -> owners, persist + last-wins there, the winner chosen by
+        GLOBAL batch position so the result does not depend on G;
+  followed by one all-reduce of the ~133 k parameter gradients (flat bucket, parameter .grad are views into it).
+* Every exchange plan lives on the DEVICE (csrc/route_kernels.cu): a row's place in the send buffer is
+  slot = dest * cap + arrival order (warp-aggregated atomics), every (source, destination) pair owns `cap` rows, the
+  buffers go through one equal-split all-to-all with static sizes, empty slots carry id -1 and are skipped by the
+  consumer kernels, replies come back in the same slots.  No split size ever crosses the host, so the whole step --
+  six all-to-alls, the all-reduce and Adam included -- is captured in ONE CUDA graph per batch size like the
+  single-GPU step.  Capacities start at a size that cannot overflow, are calibrated from the bucket counts of the two
+  eager warm-up steps (max over ranks, x margin) and frozen at capture; an overflow flag on the device guards them.
+* Every quantity is identical to the 1-GPU path on the same global batch up to fp32 summation order
+  (tests/test_gpu_sharded.py on 2 GPUs: loss, gradients, memory, last_update, pending flags).
 
-`Router` is pure torch + torch.distributed, so its bucket logic is covered by world_size-2
-gloo tests on CPU (tests/test_dist_router.py).
+`Exchange` also runs on CPU tensors with the gloo backend (plans by torch ops instead of the CUDA kernels), which is
+how the slot / reply logic is covered by world_size-2 tests without a GPU (tests/test_dist_router.py).
 """
 from __future__ import annotations
 
@@ -28,96 +34,234 @@ import torch.distributed as dist
 
 from . import _lib
 from ._lib import ptr
-from .engine import TGNEngine, TGNState, ModelConfig, _linear, _wgrad
+from .engine import TGNEngine, TGNState, ModelConfig, _linear
 from .graph import TemporalCSR, NeighborFinder
+from .trainer import PfoTrainer, allreduce_sum_, replica_slice
+
+F4 = 4
 
 
 class Plan:
-    __slots__ = ("order", "send", "recv", "n_in", "n_out")
+    __slots__ = ("slot", "local", "cap", "rows", "counts")
 
 
-class Router:
-    """Variable-size bucket exchange: rows of x go to rank dest[i]; `backward` returns replies
-    to the original row order."""
+class Exchange:
+    """Fixed-capacity bucket exchange with device-side plans (see the module docstring)."""
 
-    def __init__(self, group=None):
+    def __init__(self, device, group=None, margin=1.3, quantum=256):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self.device = torch.device(device)
+        self.margin, self.quantum = float(margin), int(quantum)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.frozen = {}            # key -> capacity fixed for the captured graphs
+        self.observed = {}          # key -> largest bucket count seen in eager steps (max over ranks)
+        self._pending = []          # (key, counts tensor) of the current eager step
 
-    def plan(self, dest: torch.Tensor) -> Plan:
+    # ---- capacities
+    def safe_cap(self, rows):
+        """A capacity that cannot overflow by construction at G <= 2 and is generous beyond: 2 * rows / G."""
+        G = self.world
+        return int(rows) if G <= 2 else int(-(-2 * int(rows) // G))
+
+    def cap_for(self, key, rows):
+        cap = self.frozen.get(key)
+        return cap if cap is not None else max(self.safe_cap(rows), 1)
+
+    def collect(self):
+        """End of an eager step: one host read of the bucket counts, max over ranks (a collective: every rank calls it
+        after every eager step).  Never called during graph capture or replay."""
+        if not self._pending:
+            return
+        keys = [k for k, _ in self._pending]
+        mx = torch.stack([c.max() for _, c in self._pending]).to(torch.int64)
+        if self.world > 1:
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
+        for k, v in zip(keys, mx.tolist()):
+            self.observed[k] = max(self.observed.get(k, 0), int(v))
+        self._pending = []
+
+    def freeze(self):
+        """Fix the capacity of every exchange observed so far (called right before a graph capture)."""
+        for k, v in self.observed.items():
+            if k not in self.frozen:
+                q = self.quantum
+                self.frozen[k] = max(q, int(-(-int(v * self.margin + 1) // q) * q))
+
+    def check_overflow(self):
+        """Host read of the overflow flag (one sync): raised when a frozen capacity turned out too small."""
+        flag = self.overflow.clone()
+        if self.world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+        if int(flag.item()) != 0:
+            raise RuntimeError("node-sharded exchange overflowed a calibrated bucket capacity: rows were dropped; "
+                               "re-run with a larger `exchange_margin`")
+
+    # ---- plan + movement
+    def plan(self, key, ids, rows, n_valid=None):
+        """ids int32[rows] (global node ids; < 0 = no row).  Returns the plan: slot / owner-local id per row."""
+        G = self.world
         p = Plan()
-        dest = dest.long()
-        p.order = torch.sort(dest, stable=True).indices
-        send = torch.bincount(dest, minlength=self.world)
-        recv = torch.empty_like(send)
-        dist.all_to_all_single(recv, send, group=self.group)
-        p.send, p.recv = send.tolist(), recv.tolist()          # host sync: split sizes live on the host
-        p.n_in, p.n_out = int(dest.shape[0]), int(sum(p.recv))
+        p.rows, p.cap = int(rows), self.cap_for(key, rows)
+        dev = ids.device
+        p.counts = torch.empty(G, dtype=torch.int32, device=dev)
+        p.slot = torch.empty(rows, dtype=torch.int32, device=dev)
+        p.local = torch.empty(rows, dtype=torch.int32, device=dev)
+        if dev.type == "cuda":
+            _lib.call("pfo_route_plan", ptr(ids), rows, ptr(n_valid), G, p.cap, ptr(p.counts), ptr(p.slot), ptr(p.local),
+                      ptr(self.overflow))
+        else:                       # host logic of the gloo tests: the same plan by torch ops (stable arrival order)
+            idl = ids.long()
+            ok = idl >= 0
+            if n_valid is not None:
+                ok &= torch.arange(rows) < int(n_valid.item())
+            dest = torch.where(ok, idl % G, torch.full_like(idl, G))
+            onehot = torch.nn.functional.one_hot(dest, G + 1)[:, :G]
+            pos = (torch.cumsum(onehot, 0) - onehot).gather(1, dest.clamp(max=G - 1).view(-1, 1)).view(-1)
+            p.counts.copy_(onehot.sum(0).to(torch.int32))
+            fits = ok & (pos < p.cap)
+            if bool((ok & ~fits).any()):
+                self.overflow.fill_(1)
+            p.slot.copy_(torch.where(fits, dest * p.cap + pos, torch.full_like(pos, -1)).to(torch.int32))
+            p.local.copy_(torch.where(ok, idl // G, torch.full_like(idl, -1)).to(torch.int32))
+        if key not in self.frozen and not (dev.type == "cuda" and torch.cuda.is_current_stream_capturing()):
+            self._pending.append((key, p.counts))
         return p
 
-    def forward(self, p: Plan, x: torch.Tensor) -> torch.Tensor:
-        xs = x.index_select(0, p.order).contiguous()
-        out = torch.empty((p.n_out,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
-        dist.all_to_all_single(out, xs, output_split_sizes=p.recv, input_split_sizes=p.send, group=self.group)
+    def buffer(self, plan, width, dtype=torch.int32, fill=None):
+        buf = torch.empty(self.world * plan.cap, width, dtype=dtype, device=plan.slot.device)
+        if fill is not None:
+            buf.fill_(fill)
+        return buf
+
+    def scatter(self, plan, rows, buf):
+        """buf[slot[i], :w] = rows[i, :w] (32-bit words of any type; rows may be a column block of a wider tensor)."""
+        w = rows.shape[1] if rows.dim() > 1 else 1
+        if rows.device.type == "cuda":
+            _lib.call("pfo_scatter_rows", ptr(rows), rows.stride(0) if rows.dim() > 1 else 1, ptr(plan.slot), plan.rows, w,
+                      ptr(buf), buf.stride(0))
+        else:
+            ok = plan.slot >= 0
+            buf.view(buf.shape[0], -1)[plan.slot[ok].long(), :w] = rows.view(plan.rows, -1)[ok]
+        return buf
+
+    def gather(self, plan, buf, col0, w, out, fill=0):
+        """out[i, :w] = buf[slot[i], col0:col0+w], `fill` (a 32-bit pattern) where the row was dropped."""
+        if buf.device.type == "cuda":
+            _lib.call("pfo_gather_words", buf.data_ptr() + col0 * F4, buf.stride(0), ptr(plan.slot), plan.rows, w,
+                      ptr(out), out.stride(0) if out.dim() > 1 else 1, int(fill) & 0xffffffff)
+        else:
+            ok = plan.slot >= 0
+            o = out.view(plan.rows, -1)
+            o.fill_(0)
+            o[ok] = buf[plan.slot[ok].long(), col0:col0 + w]
         return out
 
-    def backward(self, p: Plan, y: torch.Tensor) -> torch.Tensor:
-        ys = torch.empty((p.n_in,) + tuple(y.shape[1:]), dtype=y.dtype, device=y.device)
-        dist.all_to_all_single(ys, y.contiguous(), output_split_sizes=p.send, input_split_sizes=p.recv,
-                               group=self.group)
-        out = torch.empty_like(ys)
-        out.index_copy_(0, p.order, ys)
+    def all_to_all(self, buf):
+        out = torch.empty_like(buf)
+        if self.world > 1:
+            dist.all_to_all_single(out, buf, group=self.group)
+        else:
+            out.copy_(buf)
         return out
 
 
 def local_csr(st_sources, st_destinations, st_edge_idxs, st_timestamps, n_nodes, rank, world, device):
-    """CSR rows of the nodes owned by `rank`, indexed by x // world; neighbour ids stay global."""
+    """CSR rows of the nodes owned by `rank`, indexed by x // world; neighbour ids stay global.  Built on the device
+    when `device` is CUDA: the 2E (node, neighbour, edge, time) entries are filtered to the owned nodes first, then
+    ordered by one stable sort by time and one stable sort by local node (= the per-node stable sort of
+    utils/utils.py:139), so a rank only ever sorts its own share."""
+    dev = torch.device(device)
+    n_local = (n_nodes + world - 1) // world
+    csr = TemporalCSR.__new__(TemporalCSR)
+    csr.n_nodes, csr.n_events, csr.device = n_local, int(len(st_sources)), dev
+    if dev.type == "cuda":
+        src = torch.as_tensor(np.asarray(st_sources, dtype=np.int64), device=dev)
+        dst = torch.as_tensor(np.asarray(st_destinations, dtype=np.int64), device=dev)
+        eid = torch.as_tensor(np.asarray(st_edge_idxs, dtype=np.int64), device=dev)
+        ts = torch.as_tensor(np.asarray(st_timestamps, dtype=np.float64), device=dev)
+        return _local_csr_device(csr, src, dst, eid, ts, n_local, rank, world)
     src = np.asarray(st_sources, dtype=np.int64)
     dst = np.asarray(st_destinations, dtype=np.int64)
-    E = src.shape[0]
     node = np.stack([src, dst], axis=1).ravel()
     other = np.stack([dst, src], axis=1).ravel()
     eid = np.repeat(np.asarray(st_edge_idxs, dtype=np.int64), 2)
     ts = np.repeat(np.asarray(st_timestamps, dtype=np.float64), 2)
     mine = np.nonzero(node % world == rank)[0]
-    n_local = (n_nodes + world - 1) // world
     ln = node[mine] // world
     order = np.lexsort((np.arange(mine.shape[0]), ts[mine], ln))
-    csr = TemporalCSR.__new__(TemporalCSR)
-    csr.n_nodes, csr.n_events, csr.device = n_local, E, torch.device(device)
     rowptr = np.zeros(n_local + 1, dtype=np.int64)
     np.cumsum(np.bincount(ln, minlength=n_local), out=rowptr[1:])
-    csr.rowptr = torch.as_tensor(rowptr, device=device)
-    csr.nbr = torch.as_tensor(other[mine][order].astype(np.int32), device=device)
-    csr.eidx = torch.as_tensor(eid[mine][order].astype(np.int32), device=device)
-    csr.ts = torch.as_tensor(ts[mine][order], device=device)
+    csr.rowptr = torch.as_tensor(rowptr, device=dev)
+    csr.nbr = torch.as_tensor(other[mine][order].astype(np.int32), device=dev)
+    csr.eidx = torch.as_tensor(eid[mine][order].astype(np.int32), device=dev)
+    csr.ts = torch.as_tensor(ts[mine][order], device=dev)
     return csr
 
 
-class ShardedNeighborFinder:
-    """K1 over the owners' CSR rows: exchange R1."""
+def _local_csr_device(csr, src, dst, eid, ts, n_local, rank, world):
+    """Device build of `local_csr` from device columns (also the path of the GPU-resident generator)."""
+    parts = []
+    for node, other in ((src, dst), (dst, src)):            # each interaction is appended to both endpoints
+        mine = torch.nonzero(node % world == rank).view(-1)
+        parts.append((mine, torch.div(node[mine], world, rounding_mode="floor"), other[mine]))
+    # stream order of the 2E entries is (event, side): restore it after concatenating the two sides
+    pos = torch.cat([parts[0][0] * 2, parts[1][0] * 2 + 1])
+    o0 = torch.sort(pos).indices
+    ev = torch.cat([parts[0][0], parts[1][0]])[o0]
+    ln = torch.cat([parts[0][1], parts[1][1]])[o0]
+    other = torch.cat([parts[0][2], parts[1][2]])[o0]
+    t = ts[ev]
+    o1 = torch.sort(t, stable=True).indices
+    o2 = torch.sort(ln[o1], stable=True).indices
+    order = o1[o2]
+    csr.nbr = other[order].to(torch.int32).contiguous()
+    csr.eidx = eid[ev][order].to(torch.int32).contiguous()
+    csr.ts = t[order].contiguous()
+    counts = torch.bincount(ln, minlength=n_local)
+    csr.rowptr = torch.zeros(n_local + 1, dtype=torch.int64, device=src.device)
+    torch.cumsum(counts, 0, out=csr.rowptr[1:])
+    return csr
 
-    def __init__(self, local_nf: NeighborFinder, router: Router):
-        if local_nf.uniform:
-            raise NotImplementedError("uniform neighbour sampling is single-GPU only in this round")
-        self.local, self.router, self.uniform = local_nf, router, False
 
-    def sample(self, q_nodes, q_ts, n_neighbors, out=None):
-        G, R = self.router.world, q_nodes.shape[0]
+class ShardedNeighborFinder(NeighborFinder):
+    """K1 over the owners' CSR rows: exchange R1.  `sample` has the interface of `NeighborFinder.sample`; the queries
+    travel to the rank that owns their row as [local node id | t | query id], K1 runs there over every slot of the
+    receive buffer (empty slots answer with zero rows) writing [nbr | eidx | dt] straight into the reply row, and the
+    requester picks its answers out of the same slots."""
+
+    def __init__(self, local_csr_, exchange: Exchange, uniform=False, seed=0, tag="nf"):
+        super().__init__(local_csr_, uniform=uniform, seed=seed)
+        self.ex, self.tag = exchange, tag
+
+    def sample(self, q_nodes, q_ts, n_neighbors, out=None, q_ids=None, ld_out=0):
+        ex, Q = self.ex, q_nodes.shape[0]
         n = max(int(n_neighbors), 1)
-        plan = self.router.plan(q_nodes % G)
-        req = torch.empty(R, 3, dtype=torch.int32, device=q_nodes.device)
-        req[:, 0] = torch.div(q_nodes, G, rounding_mode="floor")
-        req[:, 1:3] = q_ts.contiguous().view(torch.int32).view(R, 2)
-        got = self.router.forward(plan, req)
-        ql = got[:, 0].contiguous()
-        qt = got[:, 1:3].contiguous().view(torch.float64).view(-1)
-        nbr, eidx, _et, dt = self.local.sample(ql, qt, n)
-        reply = torch.cat([nbr, eidx, dt.view(torch.int32)], dim=1)
-        back = self.router.backward(plan, reply)
-        return (back[:, :n].contiguous(), back[:, n:2 * n].contiguous(), None,
-                back[:, 2 * n:].contiguous().view(torch.float32))
+        dev = q_nodes.device
+        if n_neighbors <= 0:
+            return super().sample(q_nodes, q_ts, n_neighbors)
+        plan = ex.plan((self.tag, "R1", Q), q_nodes, Q)
+        req = ex.buffer(plan, 4, fill=-1)
+        _lib.call("pfo_pack_queries", ptr(plan.local), ptr(q_ts), ptr(q_ids), ptr(plan.slot), Q, ptr(req))
+        got = ex.all_to_all(req)
+        R = got.shape[0]
+        qn = torch.empty(R, dtype=torch.int32, device=dev)
+        qt = torch.empty(R, dtype=torch.float64, device=dev)
+        qi = torch.empty(R, dtype=torch.int32, device=dev)
+        _lib.call("pfo_unpack_queries", ptr(got), R, ptr(qn), ptr(qt), ptr(qi))
+        reply = torch.empty(R, 3 * n, dtype=torch.int32, device=dev)
+        rf = reply.view(torch.float32)
+        NeighborFinder.sample(self, qn, qt, n, out=(reply[:, :n], reply[:, n:2 * n], None, rf[:, 2 * n:]),
+                              q_ids=qi if self.uniform else None, ld_out=3 * n)
+        back = ex.all_to_all(reply)
+        nbr = torch.empty(Q, n, dtype=torch.int32, device=dev)
+        eidx = torch.empty(Q, n, dtype=torch.int32, device=dev)
+        dt = torch.empty(Q, n, dtype=torch.float32, device=dev)
+        ex.gather(plan, back, 0, n, nbr)
+        ex.gather(plan, back, n, n, eidx)
+        ex.gather(plan, back, 2 * n, n, dt)
+        return nbr, eidx, None, dt
 
 
 class _Scratch:
@@ -134,43 +278,44 @@ class _Scratch:
 class ShardedEngine(TGNEngine):
     """TGNEngine whose node table, its backward and the message store go through the owners."""
 
-    def __init__(self, cfg: ModelConfig, node_feat, edge_feat, local_nf, router: Router, n_nodes_global):
+    def __init__(self, cfg: ModelConfig, state: TGNState, node_feat, edge_feat, nf, exchange: Exchange,
+                 n_nodes_global):
         if cfg.message_fn != "identity" or cfg.aggregator != "last" or cfg.src_emb_in_msg:
             raise NotImplementedError("the node-sharded engine covers the models main.py builds: identity message "
                                       "function, `last` aggregator, memory rows in the messages")
-        self.router, self.G, self.rank = router, router.world, router.rank
-        self.n_global = n_nodes_global
-        n_local = (n_nodes_global + self.G - 1) // self.G
-        state = TGNState(n_local, cfg, node_feat.device)
-        super().__init__(cfg, state, node_feat, edge_feat, ShardedNeighborFinder(local_nf, router))
-        self.req = _Scratch(n_nodes_global, node_feat.device)
+        self.ex, self.G, self.rank = exchange, exchange.world, exchange.rank
+        self.n_global = int(n_nodes_global)
+        super().__init__(cfg, state, node_feat, edge_feat, nf)
+        self.req = _Scratch(self.n_global, node_feat.device)
+        self.tag = "train"
 
-    # requester-side unique ids over the global id space (exact count: one host sync)
-    def _unique_global(self, id_lists):
-        r = self.req
-        total = 0
-        for ids in id_lists:
-            _lib.call("pfo_mark_nodes", ptr(ids), ids.numel(), 1, ptr(r.bitmap))
-            total += ids.numel()
-        cap = min(total, self.n_global)
-        uniq = torch.zeros(cap, dtype=torch.int32, device=self.device)
-        _lib.call("pfo_compact_nodes", ptr(r.bitmap), self.n_global, ptr(r.compact_ws), ptr(uniq),
-                  ptr(r.slot_of_node), ptr(r.n_unique))
-        U = int(r.n_unique.item())
-        return uniq[:U].contiguous(), U
+    def _query_ids(self, groups, B):
+        """Position of each query in the query list of the un-sharded step on the global batch: group g holds
+        k_g * B_global rows interaction-major and this rank's slice starts at interaction key_base of the batch."""
+        if not getattr(self.nf, "uniform", False):
+            return None
+        dev, out, off = self.device, [], 0
+        base, Bg = getattr(self, "key_base", self.rank * B), getattr(self, "key_side", B * self.G)
+        for g in groups:
+            k = g.shape[0] // B
+            out.append(off + base * k + torch.arange(g.shape[0], dtype=torch.int32, device=dev))
+            off += Bg * k
+        return torch.cat(out)
 
-    def node_table(self, id_lists, cellW):
-        c, st, dev, G = self.cfg, self.state, self.device, self.G
+    def node_table(self, id_lists, cellW, mlpW=None):
+        c, st, dev, G, ex = self.cfg, self.state, self.device, self.G, self.ex
         d = c.d
-        uniq, U = self._unique_global(id_lists)
+        uniq, u_max = self._unique_nodes(id_lists, scratch=self.req, n_nodes=self.n_global)
+        n_uniq = self.req.n_unique.clone()
         self.slot_map = self.req.slot_of_node
-        n_uniq = torch.tensor([U], dtype=torch.int32, device=dev)
         nf_rows = self.node_feat.index_select(0, uniq.long())
         if not c.use_memory:
-            return dict(uniq=uniq, u_max=U, n_uniq=n_uniq, H0=nf_rows, Hnew=None, lu_u=None)
-        # R2: ids -> owners
-        plan = self.router.plan(uniq % G)
-        got = self.router.forward(plan, torch.div(uniq, G, rounding_mode="floor").view(-1, 1))[:, 0].contiguous()
+            return dict(uniq=uniq, u_max=u_max, n_uniq=n_uniq, H0=nf_rows, Hnew=None, lu_u=None)
+        # R2: unique ids -> owners
+        plan = ex.plan((self.tag, "R2", u_max), uniq, u_max, n_valid=n_uniq)
+        req = ex.buffer(plan, 1, fill=-1)
+        ex.scatter(plan, plan.local.view(-1, 1), req)
+        got = ex.all_to_all(req).view(-1)
         R = got.shape[0]
         _lib.call("pfo_mark_nodes", ptr(got), R, 0, ptr(st.bitmap))
         u_own = min(max(R, 1), st.n_nodes)
@@ -192,145 +337,203 @@ class ShardedEngine(TGNEngine):
         _linear(c, ptr(XG), c.rawp, None, ptr(W_ih), c.raw, 0, ptr(b_ih), ptr(GI), Gd, u_own, Gd, c.raw, m_dev=ptr(n_own))
         _linear(c, ptr(HG), d, None, ptr(W_hh), d, 0, ptr(b_hh), ptr(GH), Gd, u_own, Gd, d, m_dev=ptr(n_own))
         Hnew_own = torch.zeros(u_own, d, device=dev)
-        scratch = torch.empty(u_own, d, device=dev)         # H0 is formed on the requester
+        scratch = torch.empty(u_own, d, device=dev)         # H0 = Hnew + node features is formed on the requester
         _lib.call("pfo_cell_forward", ptr(uo), ptr(n_own), u_own, d, c.cell, ptr(GI), ptr(GH), Gd, ptr(HG),
                   ptr(valid_u), ptr(self.node_feat), ptr(Hnew_own), ptr(scratch))
         slots_own = torch.empty(R, dtype=torch.int32, device=dev)
         _lib.call("pfo_map_slots", ptr(got), R, 0, ptr(st.slot_of_node), ptr(slots_own))
-        reply = torch.empty(R, d + 1, device=dev)
+        reply = torch.empty(R, d + 1, device=dev)           # [updated memory row | last_update'] per received id
         _lib.call("pfo_gather_rows", ptr(Hnew_own), d, ptr(slots_own), R, d, ptr(reply), d + 1)
-        reply[:, d] = lu_own.index_select(0, slots_own.long())
-        back = self.router.backward(plan, reply)
-        Hnew = back[:, :d].contiguous()
-        lu_u = back[:, d].contiguous()
+        _lib.call("pfo_gather_rows", ptr(lu_own), 1, ptr(slots_own), R, 1, reply.data_ptr() + d * F4, d + 1)
+        back = ex.all_to_all(reply)
+        Hnew = torch.empty(u_max, d, device=dev)
+        lu_u = torch.empty(u_max, device=dev)
+        ex.gather(plan, back, 0, d, Hnew)
+        ex.gather(plan, back, d, 1, lu_u)
         own = dict(uniq=uo, u_max=u_own, n_uniq=n_own, HG=HG, XG=XG, valid_u=valid_u, GI=GI, GH=GH,
-                   Hnew=Hnew_own, slots=slots_own, R=R)
-        return dict(uniq=uniq, u_max=U, n_uniq=n_uniq, H0=Hnew + nf_rows, Hnew=Hnew, lu_u=lu_u, plan=plan, own=own)
+                   Hnew=Hnew_own, slots=slots_own, R=R, M1=None, X2=None)
+        return dict(uniq=uniq, u_max=u_max, n_uniq=n_uniq, H0=Hnew + nf_rows, Hnew=Hnew, lu_u=lu_u, plan=plan, own=own)
 
-    def node_table_backward(self, tab, dH0, g_cell):
-        # R3: gradient rows -> owners, summed over requesters, then the cell backward of the base class
-        own = tab["own"]
-        got = self.router.forward(tab["plan"], dH0)
-        d = self.cfg.d
+    def node_table_backward(self, tab, dH0, g_cell, mlpW=None, g_mlp=None, cellW=None):
+        # R3: gradient rows -> owners along R2's slots, summed over requesters, then the cell backward of the base class
+        own, ex, d = tab["own"], self.ex, self.cfg.d
+        send = ex.buffer(tab["plan"], d, dtype=torch.float32)
+        ex.scatter(tab["plan"], dH0, send)
+        got = ex.all_to_all(send)
         dH_own = torch.zeros(own["u_max"], d, device=self.device)
         _lib.call("pfo_scatter_add_rows", ptr(got), d, ptr(own["slots"]), own["R"], d, ptr(dH_own), d)
         TGNEngine.node_table_backward(self, own, dH_own, g_cell)
 
     def persist_and_store(self, tab, batch, emb, tw, tb):
         # R4: rows built here, applied at the owners with last-wins by global batch position
-        c, st, dev, G = self.cfg, self.state, self.device, self.G
+        c, st, dev, G, ex = self.cfg, self.state, self.device, self.G, self.ex
         d, F, B = c.d, c.n_edge_feat, batch["B"]
         src, dst = batch["src"], batch["dst"]
         s_slot, d_slot = self._slots(src), self._slots(dst)
-        rows = torch.empty(2 * B, c.raw, device=dev)
-        t32 = torch.empty(2 * B, device=dev)
+        ldr = (c.raw + 3 + 3) // 4 * 4                       # message | owner-local node | global position | fp32 time
+        rows = torch.empty(2 * B, ldr, device=dev)
         o_src = o_dst = None
         if c.dst_emb_in_msg:
             o_src, o_dst = emb[B:2 * B].contiguous(), emb[:B].contiguous()
-        _lib.call("pfo_build_messages", ptr(s_slot), ptr(d_slot), ptr(batch["eidx"]), ptr(batch["ts"]), B, d, F,
-                  ptr(tab["Hnew"]), ptr(tab["lu_u"]), ptr(self.edge_feat), ptr(tw), ptr(tb), ptr(o_src), ptr(o_dst),
-                  ptr(rows), c.raw, ptr(t32))
+        key_base = int(getattr(self, "key_base", self.rank * B))
+        key_side = int(getattr(self, "key_side", B * G))
+        _lib.call("pfo_build_routed_messages", ptr(s_slot), ptr(d_slot), ptr(src), ptr(dst), ptr(batch["eidx"]),
+                  ptr(batch["ts"]), B, d, F, ptr(tab["Hnew"]), ptr(tab["lu_u"]), ptr(self.edge_feat), ptr(tw), ptr(tb),
+                  ptr(o_src), ptr(o_dst), G, key_base, key_side, ptr(rows), ldr)
         nodes = torch.cat([src, dst])
-        Bg = B * G
-        ar = torch.arange(B, dtype=torch.int32, device=dev) + self.rank * B
-        key = torch.cat([ar, ar + Bg])
-        meta = torch.stack([torch.div(nodes, G, rounding_mode="floor"), key, t32.view(torch.int32)], dim=1)
-        plan = self.router.plan(nodes % G)
-        got_meta = self.router.forward(plan, meta)
-        got_rows = self.router.forward(plan, rows)
-        R = got_meta.shape[0]
+        plan = ex.plan((self.tag, "R4", 2 * B), nodes, 2 * B)
+        send = ex.buffer(plan, ldr, dtype=torch.float32)
+        send.view(torch.int32)[:, c.raw].fill_(-1)           # empty slots: node id -1 (only this column is read first)
+        ex.scatter(plan, rows, send)
+        got = ex.all_to_all(send)
         own = tab["own"]
-        node_l = got_meta[:, 0].contiguous()
-        key_r = got_meta[:, 1].contiguous()
-        t_r = got_meta[:, 2].contiguous().view(torch.float32)
-        _lib.call("pfo_apply_messages", ptr(node_l), ptr(key_r), R, d, c.raw, ptr(st.slot_of_node), ptr(own["Hnew"]),
-                  ptr(got_rows), c.raw, ptr(t_r), ptr(st.memory), ptr(st.last_update), ptr(st.pend_msg), c.rawp,
-                  ptr(st.pend_ts), ptr(st.pend_valid), ptr(st.last_pos))
+        _lib.call("pfo_apply_routed_messages", ptr(got), ldr, got.shape[0], d, c.raw, ptr(st.slot_of_node),
+                  ptr(own["Hnew"]), ptr(st.memory), ptr(st.last_update), ptr(st.pend_msg), c.rawp, ptr(st.pend_ts),
+                  ptr(st.pend_valid), ptr(st.last_pos))
 
 
-class ShardedTrainer:
-    """PfoTrainer over G ranks: global batch [s, s + bs*G), rank r trains on its r-th slice."""
+class ShardedTrainer(PfoTrainer):
+    """PfoTrainer over G ranks with node-sharded state: global batch [s, e), rank r trains / evaluates its r-th slice."""
 
-    def __init__(self, st, tc, device, rank, world):
-        from .trainer import PfoTrainer, StreamOnDevice, load_overlay
-        from .sampler import MVSelector, CandidateSampler
-        from .synth import log_returns
-        self.st, self.tc, self.device, self.rank, self.world = st, tc, torch.device(device), rank, world
-        self.router = Router()
-        tgn_mod, _ = load_overlay()
-        train_mask = st.split()[0]
-        tr = np.nonzero(train_mask)[0]
-        csr = local_csr(st.sources[tr], st.destinations[tr], st.edge_idxs[tr], st.timestamps[tr], st.n_nodes,
-                        rank, world, device)
-        node_feat = np.random.RandomState(0).rand(st.n_nodes, tc.d)
-        kw = dict(memory_updater_type="gru", embedding_module_type="graph_attention", use_memory=True)
-        if tc.model == "jodie":
-            kw.update(memory_updater_type="rnn", embedding_module_type="time")
-        elif tc.model == "tgat":
-            kw.update(use_memory=False)
-        ms, ss, md, sd = PfoTrainer._time_statistics(self)
-        torch.manual_seed(tc.seed)                        # identical initial weights on every rank
-        self.tgn = tgn_mod.TGN(neighbor_finder=None, node_features=node_feat, edge_features=st.edge_features.copy(),
-                               device=self.device, n_layers=tc.n_layers, n_heads=tc.n_heads, dropout=tc.dropout,
-                               message_dimension=100, memory_dimension=tc.d, message_function="identity",
-                               aggregator_type="last", n_neighbors=tc.n_neighbors, mean_time_shift_src=ms,
-                               std_time_shift_src=ss, mean_time_shift_dst=md, std_time_shift_dst=sd,
-                               gemm_mode=tc.gemm_mode, **kw).to(self.device)
-        self.engine = ShardedEngine(self.tgn._cfg, self.tgn.node_raw_features, self.tgn.edge_raw_features,
-                                    NeighborFinder(csr), self.router, st.n_nodes)
-        self.opt = torch.optim.Adam(self.tgn.parameters(), lr=tc.lr, fused=True)
-        self.dev_stream = StreamOnDevice(st, device)
-        universe_items = np.unique(st.destinations[tr])
-        self.mv = None
-        if tc.model == "ours":
-            self.mv = MVSelector(log_returns(st.prices_future), universe_items - st.n_users - 1, st.n_users,
-                                 gamma=tc.gamma, lam=tc.lambda_mv, n_candidates=tc.num_negatives,
-                                 n_pos=tc.p_pos_num, n_neg=tc.p_neg_num, seed=tc.seed, device=device)
-        self.neg_sampler = CandidateSampler(universe_items, device=device)
-        self.bpr_ws = torch.empty(1024, device=self.device)
+    def __init__(self, st, tc, device, rank, world, group=None, exchange_margin=1.3, nccl_in_graph=True):
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self.ex = Exchange(device, group=group, margin=exchange_margin)
+        if tc.model == "dyrep":
+            raise NotImplementedError("dyrep messages carry embeddings: routed, but not verified in this mode")
+        super().__init__(st, tc, device)
+        self._loss_scale = 1.0 / self.world
+        self.nccl_in_graph = bool(nccl_in_graph)
+        self._graph_tail_eager = not self.nccl_in_graph
+        # NCCL's watchdog thread touches the CUDA API while this thread captures: keep the capture check thread-local
+        self._capture_kw = {"capture_error_mode": "thread_local"}
+        self.engine.seed = tc.seed + 7919 * self.rank         # decorrelate the dropout streams of the ranks
         self.params = [p for p in self.tgn.parameters() if p.requires_grad]
+        sizes = [p.numel() for p in self.params]
+        self.gflat = torch.zeros(sum(sizes), device=self.device)          # gradient bucket; p.grad are views into it
+        for p, g in zip(self.params, self.gflat.split(sizes)):
+            p.grad = g.view_as(p)
 
-    def train_step(self, s, e):
-        from .trainer import bpr_loss
-        tc, D, G = self.tc, self.dev_stream, self.world
-        bs = (e - s) // G
-        ls, le = s + self.rank * bs, s + (self.rank + 1) * bs
-        b = dict(src=D.src[ls:le], dst=D.dst[ls:le], ts=D.ts[ls:le], eidx=D.eidx[ls:le], ev=D.ev[ls:le],
-                 day=D.day[ls:le], port_ptr=D.port_ptr[ls:le + 1])
-        self.tgn.train()
-        self.opt.zero_grad(set_to_none=True)
-        params = self.tgn._params()
-        if tc.model == "ours":
-            p_pos, p_neg = self.mv.select(b["ev"], b["day"], b["dst"], b["port_ptr"], D.port_items)
-            e_s, _, e_p, e_n = self.engine.compute_temporal_embeddings(params, b["src"], b["dst"], [p_pos, p_neg],
-                                                                       b["ts"], b["eidx"], tc.n_neighbors, train=True)
-        else:
-            neg = self.neg_sampler.sample(b["ev"], b["port_ptr"], D.port_items_as_item_ids, tc.p_neg_num,
-                                          seed=tc.seed).reshape(-1)
-            e_s, e_p, e_n = self.engine.compute_temporal_embeddings(params, b["src"], b["dst"], [neg], b["ts"],
-                                                                    b["eidx"], tc.n_neighbors, train=True)
-        loss = bpr_loss(e_s, e_p, e_n, self.bpr_ws)
-        loss.backward()
-        # one all-reduce of the parameter gradients (loss is the mean over the GLOBAL batch)
-        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
-        flat = torch.cat([g.reshape(-1) for g in grads])
-        dist.all_reduce(flat)
-        flat.div_(G)
-        off = 0
-        for p, g in zip(self.params, grads):
-            n = g.numel()
-            p.grad = flat[off:off + n].view_as(p)
-            off += n
-        self.opt.step()
-        return loss.detach()
+    # ---- construction hooks
+    def _build_finders(self, tr):
+        st, tc, dev = self.st, self.tc, self.device
+        uniform = tc.model == "tgat"
+        csr_tr = local_csr(st.sources[tr], st.destinations[tr], st.edge_idxs[tr], st.timestamps[tr], st.n_nodes,
+                           self.rank, self.world, dev)
+        csr_full = local_csr(st.sources, st.destinations, st.edge_idxs, st.timestamps, st.n_nodes,
+                             self.rank, self.world, dev)
+        self.csr_train, self.csr_full = csr_tr, csr_full
+        self.nf_train = ShardedNeighborFinder(csr_tr, self.ex, uniform=uniform, seed=tc.seed, tag="nf_train")
+        self.nf_full = ShardedNeighborFinder(csr_full, self.ex, uniform=uniform, seed=tc.seed, tag="nf_full")
+
+    def _tgn_extra(self):
+        return {"memory_nodes": (self.st.n_nodes + self.world - 1) // self.world}
+
+    def _bind_engine(self):
+        tgn = self.tgn
+        state = tgn.memory.state if tgn.use_memory else None
+        self.engine = ShardedEngine(tgn._cfg, state, tgn.node_raw_features, tgn.edge_raw_features, self.nf_train,
+                                    self.ex, self.st.n_nodes)
+        tgn._engine = self.engine
+
+    # ---- gradient bucket (same scheme as the replicated trainer)
+    def _zero_grads(self):
+        self.gflat.zero_()
+
+    def _reduce_grads(self):
+        if self.world > 1:
+            allreduce_sum_(self.gflat, self.group)
+
+    def _all_ranks_sum(self, t):
+        return allreduce_sum_(t, self.group) if self.world > 1 else t
+
+    def _check_fit(self, bs):
+        if bs < self.world:
+            raise ValueError(f"fit: batch size {bs} is smaller than the number of ranks ({self.world})")
+
+    # ---- steps
+    def _slice(self, s, e):
+        ls, le = replica_slice(s, e, self.rank, self.world)
+        self.engine.key_base, self.engine.key_side = ls - s, e - s
+        return ls, le
+
+    def _run_graphed(self, sg):
+        if sg.graph is None and sg.eager_steps >= 2:
+            self.ex.freeze()                                  # capacities fixed from the eager steps' bucket counts
+        eager = sg.graph is None and sg.eager_steps < 2
+        out = super()._run_graphed(sg)
+        if eager:
+            self.ex.collect()
+        return out
+
+    def train_step(self, s, e, batch=None):
+        ls, le = self._slice(s, e)
+        self.engine.tag = "train"
+        if (e - s) % self.world != 0 or not (self._graph_ok(le - ls) and e <= self.st.n_events):
+            # ragged tail batch (or graphs off): launched kernel by kernel, this rank's mean weighted by its share
+            keep, self._loss_scale = self._loss_scale, (le - ls) / float(e - s)
+            try:
+                out = self._step_body(self._batch(ls, le))
+            finally:
+                self._loss_scale = keep
+            self.ex.collect()
+            return out
+        sg = self._step_graph(le - ls)
+        self._fill_static(sg, ls, le)
+        return self._run_graphed(sg)
+
+    def eval_step(self, s, e, n_items=None, batch=None, state_batch=None):
+        """Global evaluation batch [s, e): this rank scores its slice of the users (returns its slice of the results)."""
+        ls, le = self._slice(s, e)
+        self.engine.tag = "eval"
+        N = int(n_items) if n_items is not None else int(self.eval_sampler.items.shape[0])
+        sg = self._graphs.get(le - ls)
+        eg = sg.evals.get((N, False)) if sg is not None else None
+        replay = eg is not None and eg.graph is not None
+        capture = eg is not None and eg.graph is None and eg.eager_steps >= 2 and self._graph_ok(le - ls)
+        if capture:
+            self.ex.freeze()
+        out = super().eval_step(ls, le, n_items=n_items, ev_base=ls - s)
+        if not replay and not capture:
+            self.ex.collect()                                 # an eager step ran: record its bucket counts
+        return out
+
+    def make_host_batches(self, start, count, bs):
+        """Pinned host copies of this rank's slices of `count` consecutive GLOBAL batches of bs * world interactions."""
+        out = []
+        for i in range(count):
+            s = start + i * bs * self.world
+            ls, _ = replica_slice(s, s + bs * self.world, self.rank, self.world)
+            hb = super().make_host_batches(ls, 1, bs)[0]
+            hb["_global"] = (s, s + bs * self.world)
+            out.append(hb)
+        return out
+
+    def train_step_host(self, hb):
+        s, e = hb.pop("_global")
+        self._slice(s, e)
+        self.engine.tag = "train"
+        try:
+            B = hb["src"].shape[0]
+            sg = self._step_graph(B)
+            for k, v in hb.items():
+                if k == "nbytes":
+                    continue
+                dstb = sg.static[k]
+                (dstb[:v.shape[0]] if k == "port_items" else dstb).copy_(v, non_blocking=True)
+            return self._run_graphed(sg)
+        finally:
+            hb["_global"] = (s, e)
 
     def gather_memory(self):
-        """Global [N, d] memory / last_update / pend_valid assembled on every rank (tests)."""
+        """Global [N, .] memory / last_update / pend_valid assembled on every rank (tests)."""
         st, G = self.engine.state, self.world
         outs = []
         for t in (st.memory, st.last_update, st.pend_valid.to(torch.float32)):
             parts = [torch.empty_like(t) for _ in range(G)]
-            dist.all_gather(parts, t.contiguous())
+            if G > 1:
+                dist.all_gather(parts, t.contiguous(), group=self.group)
+            else:
+                parts = [t]
             full = torch.stack(parts, dim=1).reshape((-1,) + tuple(t.shape[1:]))[:self.st.n_nodes]
             outs.append(full)
         return outs

@@ -371,7 +371,7 @@ class TGNEngine:
         q_ts = torch.cat([ts if g.shape[0] == B else ts.repeat_interleave(g.shape[0] // B) for g in groups])
         flat = self._pack(params)
         batch = dict(src=src, dst=dst, ts=ts, eidx=eidx, q_nodes=q_nodes, q_ts=q_ts, n=int(n_neighbors),
-                     B=B, train=bool(train), update_state=bool(update_state))
+                     B=B, train=bool(train), update_state=bool(update_state), q_ids=self._query_ids(groups, B))
         if state_batch is not None:
             if self.cfg.dst_emb_in_msg or self.cfg.src_emb_in_msg:
                 raise NotImplementedError("messages that carry embeddings (dyrep) need the embedded batch as state batch")
@@ -383,16 +383,29 @@ class TGNEngine:
         return list(torch.split(emb, [g.shape[0] for g in groups]))
 
     # ------------------------------------------------------------------ forward internals
-    def _sample_tree(self, nodes, ts, layer, n):
+    def _query_ids(self, groups, B):
+        """Ids of the queries in the un-sharded query list (only the node-sharded engine needs them: they key the
+        uniform neighbour stream, so that the draws do not depend on the number of ranks)."""
+        return None
+
+    def _sample_tree(self, nodes, ts, layer, n, q_ids=None):
         """Neighbour sampling in the call order of the reference recursion
         (modules/embedding_module.py:115-145): inner queries, own call, inner neighbours."""
         if layer == 0:
             return None
         M = nodes.shape[0]
-        child_q = self._sample_tree(nodes, ts, layer - 1, n)
-        nbr, eidx, _etime, dt = self.nf.sample(nodes, ts, n)
+        child_q = self._sample_tree(nodes, ts, layer - 1, n, q_ids)
+        if q_ids is not None:
+            nbr, eidx, _etime, dt = self.nf.sample(nodes, ts, n, q_ids=q_ids)
+        else:
+            nbr, eidx, _etime, dt = self.nf.sample(nodes, ts, n)
         n_eff = nbr.shape[1]
-        child_n = self._sample_tree(nbr.reshape(-1), ts.repeat_interleave(n_eff), layer - 1, n) if layer > 1 else None
+        child_n = None
+        if layer > 1:
+            # a neighbour's id = its position in the flattened [M, n] list of the un-sharded call
+            ids_n = None if q_ids is None else (q_ids.view(-1, 1) * n_eff
+                                                + torch.arange(n_eff, dtype=torch.int32, device=nodes.device)).reshape(-1)
+            child_n = self._sample_tree(nbr.reshape(-1), ts.repeat_interleave(n_eff), layer - 1, n, ids_n)
         return dict(layer=layer, M=M, nodes=nodes, nbr=nbr, eidx=eidx, dt=dt, child_q=child_q, child_n=child_n)
 
     def _collect_level0(self, tree, out):
@@ -403,15 +416,19 @@ class TGNEngine:
             self._collect_level0(tree["child_q"], out)
             self._collect_level0(tree["child_n"], out)
 
-    def _unique_nodes(self, id_lists):
-        st = self.state
+    def _unique_nodes(self, id_lists, scratch=None, n_nodes=None, skip_zero=None):
+        """Ascending unique ids of `id_lists` (bitmap marks -> scan -> compact).  `scratch` holds the bitmap, the
+        slot-of-node map, the scan workspace and the device-side count (default: the state's own, over its nodes)."""
+        st = self.state if scratch is None else scratch
+        n_nodes = self.n_nodes if n_nodes is None else n_nodes
+        skip = self.skip_zero if skip_zero is None else skip_zero
         total = 0
         for ids in id_lists:
-            _lib.call("pfo_mark_nodes", ptr(ids), ids.numel(), self.skip_zero, ptr(st.bitmap))
+            _lib.call("pfo_mark_nodes", ptr(ids), ids.numel(), skip, ptr(st.bitmap))
             total += ids.numel()
-        u_max = min(total, self.n_nodes)
+        u_max = min(total, n_nodes)
         uniq = torch.zeros(u_max, dtype=torch.int32, device=self.device)
-        _lib.call("pfo_compact_nodes", ptr(st.bitmap), self.n_nodes, ptr(st.compact_ws), ptr(uniq),
+        _lib.call("pfo_compact_nodes", ptr(st.bitmap), n_nodes, ptr(st.compact_ws), ptr(uniq),
                   ptr(st.slot_of_node), ptr(st.n_unique))
         return uniq, u_max
 
@@ -705,7 +722,7 @@ class TGNStepFunction(torch.autograd.Function):
         if c.graph:
             nf = eng.nf
             calls0 = getattr(nf, "call_id", 0)
-            tree = eng._sample_tree(q_nodes, q_ts, c.n_layers, n)
+            tree = eng._sample_tree(q_nodes, q_ts, c.n_layers, n, batch.get("q_ids"))
             if getattr(nf, "call_ctr", None) is not None and torch.cuda.is_current_stream_capturing():
                 # uniform sampling inside a captured step: the host call ids are baked into the graph, the device
                 # counter advances by the step's number of K1 calls on every replay (fresh Philox streams)

@@ -74,8 +74,10 @@ class NeighborFinder:
         self.lanes_per_query = 0        # K1 search width: 0 = chosen by the kernel launcher from the query count
 
     # device API used by the engine -----------------------------------------------------
-    def sample(self, q_nodes: torch.Tensor, q_ts: torch.Tensor, n_neighbors: int, out=None):
-        """q_nodes int32[Q], q_ts float64[Q] on the device -> (nbr i32, eidx i32, etime f32, dt f32) [Q, n]."""
+    def sample(self, q_nodes: torch.Tensor, q_ts: torch.Tensor, n_neighbors: int, out=None, q_ids=None, ld_out=0):
+        """q_nodes int32[Q], q_ts float64[Q] on the device -> (nbr i32, eidx i32, etime f32, dt f32) [Q, n].
+        q_ids / ld_out / out[2] = None: the node-sharded caller's query ids, reply-row stride and skipped edge times
+        (see include/pfo_b200.h)."""
         Q = q_nodes.shape[0]
         n = max(int(n_neighbors), 1)
         dev = q_nodes.device
@@ -92,7 +94,7 @@ class NeighborFinder:
         c = self.csr
         _lib.call("pfo_neighbor_sample", _lib.ptr(c.rowptr), _lib.ptr(c.nbr), _lib.ptr(c.eidx), _lib.ptr(c.ts),
                   _lib.ptr(q_nodes), _lib.ptr(q_ts), Q, n, int(self.uniform), self.seed, self.call_id,
-                  _lib.ptr(self.call_ctr), int(self.lanes_per_query), _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(out[3]))
+                  _lib.ptr(self.call_ctr), int(self.lanes_per_query), _lib.ptr(q_ids), int(ld_out), _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(out[3]))
         self.call_id += 1
         return out
 

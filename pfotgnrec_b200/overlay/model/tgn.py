@@ -49,7 +49,7 @@ class TGN(torch.nn.Module):
                  memory_updater_type="gru",
                  use_destination_embedding_in_message=False,
                  use_source_embedding_in_message=False,
-                 dyrep=False, gemm_mode="fp32"):
+                 dyrep=False, gemm_mode="fp32", memory_nodes=None):
         super().__init__()
         _lib.use_device(device)      # main.py:103 hands cuda:{gpu}: the kernels launch on the current device's stream
         if use_memory and not memory_update_at_start:
@@ -85,7 +85,9 @@ class TGN(torch.nn.Module):
             self.memory_dimension, self.memory_update_at_start = memory_dimension, memory_update_at_start
             raw_dim = 2 * memory_dimension + self.n_edge_features + self.time_encoder.dimension
             message_dimension = raw_dim if message_function == "identity" else message_dimension
-            self.memory = Memory(n_nodes=self.n_nodes, memory_dimension=memory_dimension, input_dimension=message_dimension,
+            # memory_nodes (extension, node-sharded mode): this rank holds the memory rows of the nodes it owns only
+            self.memory = Memory(n_nodes=int(memory_nodes) if memory_nodes is not None else self.n_nodes,
+                                 memory_dimension=memory_dimension, input_dimension=message_dimension,
                                  message_dimension=message_dimension, device=device,
                                  n_edge_features=self.n_edge_features)
             self.message_aggregator = get_message_aggregator(aggregator_type=aggregator_type, device=device)

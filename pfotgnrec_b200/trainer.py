@@ -175,13 +175,7 @@ class PfoTrainer:
         self.masks = (train_mask, val_mask, test_mask)
         self.n_train = int(train_mask.sum())
         tr = np.nonzero(train_mask)[0]
-        self.csr_train = TemporalCSR(st.sources[tr], st.destinations[tr], st.edge_idxs[tr], st.timestamps[tr],
-                                     n_nodes=st.n_nodes, device=device)
-        self.csr_full = TemporalCSR(st.sources, st.destinations, st.edge_idxs, st.timestamps,
-                                    n_nodes=st.n_nodes, device=device)
-        uniform = tc.model == "tgat"
-        self.nf_train = NeighborFinder(self.csr_train, uniform=uniform, seed=tc.seed)
-        self.nf_full = NeighborFinder(self.csr_full, uniform=uniform, seed=tc.seed)
+        self._build_finders(tr)
         rs = np.random.RandomState(0)                     # main.py:9,87: node features ~ U(0,1)
         node_feat = rs.rand(st.n_nodes, tc.d)
         kw = dict(memory_updater_type="gru", embedding_module_type="graph_attention", use_memory=True,
@@ -201,7 +195,8 @@ class PfoTrainer:
                                aggregator_type="last", n_neighbors=tc.n_neighbors,
                                mean_time_shift_src=ms, std_time_shift_src=ss, mean_time_shift_dst=md,
                                std_time_shift_dst=sd, use_source_embedding_in_message=False,
-                               gemm_mode=tc.gemm_mode, **kw).to(self.device)
+                               gemm_mode=tc.gemm_mode, **self._tgn_extra(), **kw).to(self.device)
+        self._bind_engine()
         self.opt = torch.optim.Adam(self.tgn.parameters(), lr=tc.lr, fused=True, capturable=True)
         self._graphs = {}            # batch size -> _StepGraph
         self.dev_stream = StreamOnDevice(st, device)
@@ -225,6 +220,24 @@ class PfoTrainer:
     @property
     def eval_acc(self):
         return self.metrics.acc
+
+    # ---- hooks of the node-sharded subclass (pfotgnrec_b200/dist.py)
+    def _build_finders(self, tr):
+        """Train-split and full adjacency (main.py:95-96) as device CSRs + the K1 finders on top."""
+        st, tc = self.st, self.tc
+        self.csr_train = TemporalCSR(st.sources[tr], st.destinations[tr], st.edge_idxs[tr], st.timestamps[tr],
+                                     n_nodes=st.n_nodes, device=self.device)
+        self.csr_full = TemporalCSR(st.sources, st.destinations, st.edge_idxs, st.timestamps,
+                                    n_nodes=st.n_nodes, device=self.device)
+        uniform = tc.model == "tgat"
+        self.nf_train = NeighborFinder(self.csr_train, uniform=uniform, seed=tc.seed)
+        self.nf_full = NeighborFinder(self.csr_full, uniform=uniform, seed=tc.seed)
+
+    def _tgn_extra(self):
+        return {}
+
+    def _bind_engine(self):
+        pass
 
     def _time_statistics(self):
         return time_statistics(self.st.sources, self.st.destinations, self.st.timestamps)
@@ -315,7 +328,7 @@ class PfoTrainer:
             self._zero_grads()
             g = torch.cuda.CUDAGraph()
             launches0 = _lib.LAUNCHES
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, **self._capture_kw):
                 sg.loss = self._fwd_bwd(sg.static) if self._graph_tail_eager else self._step_body(sg.static)
             sg.launches = _lib.LAUNCHES - launches0
             sg.graph = g
@@ -372,6 +385,7 @@ class PfoTrainer:
     # hooks of the data-parallel subclass
     _loss_scale = 1.0
     _graph_tail_eager = False
+    _capture_kw = {}             # multi-rank trainers capture NCCL collectives: capture_error_mode="thread_local"
 
     def _zero_grads(self):
         self.opt.zero_grad(set_to_none=True)
@@ -381,7 +395,7 @@ class PfoTrainer:
 
     # ------------------------------------------------------------------ one evaluation step
     @torch.no_grad()
-    def eval_step(self, s, e, n_items=None, batch=None, state_batch=None):
+    def eval_step(self, s, e, n_items=None, batch=None, state_batch=None, ev_base=None):
         """Interactions [s, e): N_ITEMS candidates per interaction (seed 2024), embeddings, scores, rank of
         the true item and top-5 (reference evaluation.py:84-115,134-138), then the metric block (:127-207) into
         `per_event` float64[B,18] and the running sums `self.eval_acc`.  Advances memory like the
@@ -391,6 +405,10 @@ class PfoTrainer:
         if batch is None and self._graph_ok(e - s) and e - s > 0 and e <= self.st.n_events:
             sg = self._step_graph(e - s)
             self._fill_static(sg, s, e)
+            if ev_base is not None:      # multi-GPU: position of this rank's slice inside the global evaluation batch
+                if "ev_base" not in sg.static:
+                    sg.static["ev_base"] = torch.zeros(1, dtype=torch.int64, device=self.device)
+                sg.static["ev_base"].fill_(int(ev_base))
             if state_batch is not None:
                 self._ensure_state_buffers(sg, state_batch["src"].shape[0])
                 for k, v in state_batch.items():
@@ -403,7 +421,7 @@ class PfoTrainer:
                 torch.cuda.synchronize(self.device)
                 g = torch.cuda.CUDAGraph()
                 launches0 = _lib.LAUNCHES
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, **self._capture_kw):
                     eg.loss = self._eval_body(sg.static, N, state_batch is not None)
                 eg.launches = _lib.LAUNCHES - launches0
                 eg.graph = g
@@ -413,6 +431,8 @@ class PfoTrainer:
         b = dict(batch) if batch is not None else self._batch(s, e)
         if state_batch is not None:
             b["state"] = state_batch
+        if ev_base is not None:
+            b["ev_base"] = int(ev_base)
         return self._eval_body(b, N, state_batch is not None)
 
     def _ensure_state_buffers(self, sg, Bg):
@@ -428,8 +448,10 @@ class PfoTrainer:
         eng = tgn._get_engine()
         eng.nf = self.nf_full
         B = b["src"].shape[0]
-        # evaluation recreates RandomState(2024) per batch: the stream is keyed by position in the batch
+        # evaluation recreates RandomState(2024) per batch: the stream is keyed by position in the (global) batch
         ev = torch.arange(B, dtype=torch.int64, device=self.device)
+        if "ev_base" in b:
+            ev = ev + b["ev_base"]
         held = b["port_items"] + (self.st.n_users + 1) if "port_items" in b else D.port_items_as_item_ids
         cand = self.eval_sampler.sample(ev, b["port_ptr"], held, N, seed=2024)
         e_s, e_d, e_c = eng.compute_temporal_embeddings(tgn._params(), b["src"], b["dst"], [cand.reshape(-1)], b["ts"],
@@ -601,7 +623,7 @@ class ReplicatedTrainer(PfoTrainer):
         """Global evaluation batch [s, e): this rank scores its slice of the users against all candidates, every
         rank advances the state with the whole batch (returns this rank's slice of the results)."""
         ls, le = replica_slice(s, e, self.rank, self.world)
-        return super().eval_step(ls, le, n_items=n_items, state_batch=self._state_batch(s, e))
+        return super().eval_step(ls, le, n_items=n_items, state_batch=self._state_batch(s, e), ev_base=ls - s)
 
     def _state_batch(self, s, e):
         D = self.dev_stream

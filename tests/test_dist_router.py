@@ -14,39 +14,72 @@ def _worker(rank, world, port, results):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from pfotgnrec_b200.dist import Router
+    from pfotgnrec_b200.dist import Exchange
     try:
-        r = Router()
+        ex = Exchange("cpu")
         g = torch.Generator().manual_seed(100 + rank)
         # a sharded table: node x lives on rank x % world at row x // world; value = f(x)
         N, d = 1000, 5
         n_local = (N + world - 1) // world
         local_ids = torch.arange(n_local) * world + rank
         table = (local_ids.float().unsqueeze(1) * 10 + torch.arange(d).float())
-        for R in (0, 1, 257):
-            ids = torch.randint(0, N, (R,), generator=g)
-            plan = r.plan(ids % world)
-            got = r.forward(plan, (ids // world).view(-1, 1))[:, 0]
-            assert got.numel() == sum(plan.recv)
-            reply = table[got] if got.numel() else table[:0]
-            back = r.backward(plan, reply)
+        for step, R in enumerate((1, 257, 64, 257)):
+            ids = torch.randint(0, N, (R,), generator=g).to(torch.int32)
+            ids[::7] = -1                                        # rows that are not sent
+            n_valid = torch.tensor([R - 3], dtype=torch.int32)   # device-side count: the tail is ignored too
+            live = (ids >= 0) & (torch.arange(R) < R - 3)
+            plan = ex.plan(("t", R), ids, R, n_valid=n_valid)
+            assert plan.cap == ex.cap_for(("t", R), R)
+            assert torch.equal(plan.slot >= 0, live)
+            assert torch.equal(plan.local[live].long(), ids[live].long() // world)
+            # request: owner-local ids into their slots, empty slots stay -1
+            req = ex.buffer(plan, 1, fill=-1)
+            ex.scatter(plan, plan.local.view(-1, 1), req)
+            got = ex.all_to_all(req).view(-1)
+            assert int((got >= 0).sum()) <= got.numel()
+            # reply in the same slots: rows of the owner's table
+            reply = torch.zeros(got.numel(), d)
+            ok = got >= 0
+            reply[ok] = table[got[ok].long()]
+            back = ex.all_to_all(reply)
+            out = torch.empty(R, d)
+            ex.gather(plan, back, 0, d, out)
             expect = ids.float().unsqueeze(1) * 10 + torch.arange(d).float()
-            assert torch.equal(back, expect), (rank, R)
-            # gradient direction: rows sent to the owners and summed there
-            grads = torch.ones(R, d)
-            recv = r.forward(plan, grads)
-            acc = torch.zeros(n_local, d).index_add_(0, got, recv)
+            assert torch.equal(out[live], expect[live]), (rank, R)
+            assert float(out[~live].abs().sum()) == 0.0
+            # gradient direction: rows travel to the owners along the same slots and are summed there
+            send = ex.buffer(plan, d, dtype=torch.float32)
+            ex.scatter(plan, torch.ones(R, d), send)
+            recv = ex.all_to_all(send)
+            acc = torch.zeros(n_local, d).index_add_(0, got[ok].long(), recv[ok])
             total = acc.sum()
             dist.all_reduce(total)
-            cnt = torch.tensor([float(R)])
+            cnt = torch.tensor([float(live.sum())])
             dist.all_reduce(cnt)
             assert float(total) == float(cnt) * d
+            ex.collect()                                         # eager step: bucket counts -> max over ranks
+            if step == 1:
+                ex.freeze()                                      # R = 257 is calibrated from here on
+        key = ("t", 257)
+        assert key in ex.frozen and ex.frozen[key] % ex.quantum == 0 and ex.frozen[key] >= ex.observed[key]
+        ex.check_overflow()
+        # a frozen capacity that is too small drops rows and raises the flag on every rank
+        ex.frozen[("tiny", 64)] = 2
+        plan = ex.plan(("tiny", 64), torch.arange(64, dtype=torch.int32) * world, 64)      # all rows to rank 0
+        assert int((plan.slot >= 0).sum()) == 2
+        try:
+            ex.check_overflow()
+            raise AssertionError("overflow not reported")
+        except RuntimeError:
+            pass
         results[rank] = "ok"
     finally:
         dist.destroy_process_group()
 
 
-def test_router_round_trip_gloo_world2():
+def test_exchange_round_trip_gloo_world2():
+    """Fixed-capacity bucket exchange of the node-sharded path (pfotgnrec_b200/dist.py::Exchange): slots, request /
+    reply in the same slots, gradient direction, capacity calibration and the overflow flag, on 2 gloo ranks."""
     world = 2
     mgr = mp.Manager()
     results = mgr.dict()

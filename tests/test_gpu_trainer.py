@@ -284,7 +284,8 @@ def test_fit_epoch_loop_matches_manual_loop():
         for k, v in want.items():
             assert abs(got[k] - v) <= 1e-6 * max(1.0, abs(v)), (epoch, k, got[k], v)
         assert 0.0 <= got["valid_recall_avg_5"] <= 1.0 and np.isfinite(got["loss"])
-    assert hist[0]["loss"] == hist[1]["loss"]            # same weights, memory reset: the epochs repeat exactly
+    # same weights, memory reset -- but every epoch draws fresh MV candidates, like the reference (main.py:194-195)
+    assert hist[0]["loss"] != hist[1]["loss"] and abs(hist[0]["loss"] - hist[1]["loss"]) < 0.1
 
 
 def test_every_epoch_draws_fresh_candidates():
