@@ -44,6 +44,12 @@ def parse():
     ap.add_argument("--parallelism", default="sharded", choices=["replicated", "sharded"],
                     help="N > 1: node-sharded state (owner = node mod N) with device-planned all-to-all routing "
                          "(pfotgnrec_b200/dist.py, the default), or replicated state + data-parallel interactions")
+    ap.add_argument("--procedural", action="store_true",
+                    help="GPU-resident procedural stream (pfotgnrec_b200/synth_device.py) instead of the host-built one: the "
+                         "only way to the scale configuration; runs the node-sharded trainer at any N (N = 1 included)")
+    ap.add_argument("--config4", action="store_true",
+                    help="BASELINE config 4: --procedural with 10^7 users x 5 000 stocks x 10^9 interactions, global batch "
+                         "65 536 (= --bs 8192 on 8 GPUs)")
     ap.add_argument("--eval-steps", type=int, default=8)
     ap.add_argument("--eval-bs", type=int, default=512, help="users per evaluation batch and GPU (reference --bs default)")
     ap.add_argument("--large-bs", type=int, default=65536,
@@ -58,10 +64,18 @@ def parse():
     ap.add_argument("--cpu-budget", type=float, default=30.0,
                     help="seconds of reference steps for the GPU arm's cpu_baseline (run as a subprocess of --impl reference)")
     ap.add_argument("--no-profile", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.config4:
+        a.procedural, a.users, a.items, a.events = True, 10_000_000, 5_000, 1_000_000_000
+    return a
 
 
 def workload_name(a):
+    if a.procedural:
+        return (f"{'PfoTGNRec' if a.workload == 'ours' else a.workload} train step "
+                f"(d=64, {a.layers} layer{'s' if a.layers > 1 else ''}, {a.neighbors} neighbours, 2 heads"
+                f"{', MV sampling K=20' if a.workload == 'ours' else ''}), "
+                f"GPU-resident procedural {a.users}-user x {a.items}-stock x {a.events}-event stream, bs={a.bs} per GPU")
     return (f"{'PfoTGNRec' if a.workload == 'ours' else a.workload} train step "
             f"(d=64, {a.layers} layer{'s' if a.layers > 1 else ''}, {a.neighbors} neighbours, 2 heads"
             f"{', MV sampling K=20' if a.workload == 'ours' else ''}), "
@@ -401,10 +415,18 @@ def main():
     from pfotgnrec_b200 import _lib
     from pfotgnrec_b200.trainer import PfoTrainer, TrainConfig
     _lib.load()
-    st = make_data(a)
+    if a.procedural:
+        from pfotgnrec_b200.synth_device import DeviceStream
+        if world == 1:                               # the sharded trainer's exchange needs a process group, even of one
+            import torch.distributed as dist
+            dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{29700 + os.getpid() % 200}", rank=0,
+                                    world_size=1, device_id=dev)
+        st = DeviceStream(a.users, a.items, a.events, n_days=a.days, seed=0, device=dev)
+    else:
+        st = make_data(a)
     tc = TrainConfig(model=a.workload, bs=a.bs, gemm_mode=a.gemm, dropout=a.dropout, cuda_graph=not a.no_graph,
                      n_layers=a.layers, n_neighbors=a.neighbors)
-    if world > 1 and a.parallelism == "sharded":
+    if a.procedural or (world > 1 and a.parallelism == "sharded"):
         from pfotgnrec_b200.dist import ShardedTrainer
         tr = ShardedTrainer(st, tc, dev, rank, world)
         if a.no_graph:
@@ -429,6 +451,9 @@ def main():
         torch.cuda.synchronize()
 
     cur = StreamCursor(s0, st.n_events)
+    if a.procedural:                                 # evaluate the batches' columns ahead of the timed loops
+        pre = StreamCursor(s0, st.n_events)
+        tr.prefetch([pre.take(bs * world) for _ in range(a.warmup + 2 * a.steps + 8)])
 
     def step(_i=None):
         s, e = cur.take(bs * world)                  # the GLOBAL batch; each rank embeds its slice of it
@@ -489,7 +514,7 @@ def main():
 
     # ---- per-kernel pass (eager launches, CUDA events per C-ABI call) for the rooflines
     roofline, kernels, rooflines = None, None, None
-    if not a.no_profile and world == 1:
+    if not a.no_profile and world == 1 and not a.procedural:
         ncu = {}
         try:
             ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
@@ -591,7 +616,7 @@ def main():
 
     # ---- CPU baseline: the unmodified reference on the host cores (its own process), bounded sample, rank 0 only
     cpu, eval_cpu = None, None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+    if rank == 0 and world == 1 and not a.no_cpu_baseline and not a.procedural:
         ref = cpu_baseline_subprocess(a)
         cpu = ref.get("cpu_baseline") or ref
         eval_cpu = (ref.get("eval") or {}).get("cpu_baseline")
@@ -600,8 +625,10 @@ def main():
         ran_graph = bool(getattr(tr, "_graph_ok", lambda _b: False)(bs))
         cfg = base_config(a, world)
         cfg.update({"l2": "flushed between timed steps (256 MiB write)",
-                    "parallelism": "1 GPU" if world == 1 else (f"node-sharded x{world}" if a.parallelism == "sharded"
-                                                               else f"replicated state, data-parallel x{world}"),
+                    "parallelism": ("1 GPU" if world == 1 and not a.procedural else
+                                    (f"node-sharded x{world} (owner = node mod {world}, device-planned all-to-all)"
+                                     if a.parallelism == "sharded" or a.procedural
+                                     else f"replicated state, data-parallel x{world}")),
                     "timing": "sum of per-step CUDA-event durations, max over ranks",
                     "gemm_mode": a.gemm, "cuda_graph": ran_graph})
         ev_block = None

@@ -140,6 +140,40 @@ def call(name, *args):
         raise PfoError(f"{name} failed with cudaError {rc}")
 
 
+class _NoRange:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_RANGE = _NoRange()
+NVTX = os.environ.get("PFO_NVTX", "0") not in ("", "0")
+
+
+class nvtx_range:
+    """`with nvtx_range("stage"):` -- an NVTX range around a stage of the step (sampling, node table, attention, BPR,
+    backward, optimiser, ...) when PFO_NVTX=1, so that ncu / nsys group the launches by stage; a no-op object otherwise
+    (the ranges are host-side markers: they are not captured into CUDA graphs, profile with --no-graph)."""
+
+    def __new__(cls, name):
+        if not NVTX:
+            return _NO_RANGE
+        return object.__new__(cls)
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        torch.cuda.nvtx.range_pop()
+        return False
+
+
 def query(name, *args):
     """Host-only helper entry points (workspace sizes)."""
     return getattr(load(), name)(*args)

@@ -101,6 +101,7 @@ __device__ __forceinline__ float multi_reduce(float (&v)[NV], int lane) {
 template <int DPL, int NH>
 __global__ void __launch_bounds__(128)
 attn_nbr_fwd_kernel(const NbrArgs p) {
+    pfo_pdl_prologue();
     extern __shared__ float smem[];
     constexpr int d = 32 * DPL;
     constexpr int SW = 2 * d + 32;                      // stash row: [h | cos | e(32)]
@@ -258,6 +259,7 @@ attn_nbr_fwd_kernel(const NbrArgs p) {
 template <int DPL, int NH>
 __global__ void __launch_bounds__(128)
 attn_nbr_bwd_kernel(const NbrArgs p) {
+    pfo_pdl_prologue();
     extern __shared__ float smem[];
     constexpr int d = 32 * DPL;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -459,6 +461,7 @@ __global__ void __launch_bounds__(256)
 bpr_kernel(const float* __restrict__ eu, const float* __restrict__ ep, const float* __restrict__ en,
            int B, int k, int d, float* __restrict__ du, float* __restrict__ dp, float* __restrict__ dn,
            float* __restrict__ loss_partial, float grad_scale) {
+    pfo_pdl_prologue();
     __shared__ float wl[8];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -509,6 +512,7 @@ __global__ void __launch_bounds__(256)
 eval_score_kernel(const float* __restrict__ es, const float* __restrict__ ed, const float* __restrict__ ec,
                   int n_cand, int d, int topk, float* __restrict__ scores, int32_t* __restrict__ pos_rank,
                   int32_t* __restrict__ top_idx) {
+    pfo_pdl_prologue();
     extern __shared__ float sh[];            // [1 + n_cand] scores, then reduction scratch
     const int b = blockIdx.x;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -571,7 +575,7 @@ int launch_fwd(const NbrArgs& a, cudaStream_t s) {
     int per_sm = (int)((200 * 1024) / (smem + 1024));
     if (per_sm > 5) per_sm = 5;
     if (per_sm < 1) per_sm = 1;
-    attn_nbr_fwd_kernel<DPL, NH><<<pfo_grid(a.Q * 32, 128, 2 * per_sm), 128, smem, s>>>(a);
+    pfo_launch(attn_nbr_fwd_kernel<DPL, NH>, pfo_grid(a.Q * 32, 128, 2 * per_sm), 128, smem, s, a);
     PFO_LAUNCH_CHECK();
 }
 
@@ -582,7 +586,7 @@ int launch_bwd(const NbrArgs& a, int grid, size_t smem, cudaStream_t s) {
         cudaFuncSetAttribute(attn_nbr_bwd_kernel<DPL, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    attn_nbr_bwd_kernel<DPL, NH><<<grid, 128, smem, s>>>(a);
+    pfo_launch(attn_nbr_bwd_kernel<DPL, NH>, grid, 128, smem, s, a);
     PFO_LAUNCH_CHECK();
 }
 
@@ -678,7 +682,7 @@ PFO_API int pfo_bpr(const float* eu, const float* ep, const float* en, int B, in
     cudaStream_t s = (cudaStream_t)stream;
     int grid = pfo_grid((int64_t)B * 32, 256, 8);   // one warp per interaction when they fit (latency-bound, tiny)
     if (grid > 1024) grid = 1024;
-    bpr_kernel<<<grid, 256, 0, s>>>(eu, ep, en, B, k, d, du, dp, dn, workspace, grad_scale);
+    pfo_launch(bpr_kernel, grid, 256, 0, s, eu, ep, en, B, k, d, du, dp, dn, workspace, grad_scale);
     // loss = sum over blocks of per-block means/B contributions: reduce rows=grid, cols=1
     return pfo_reduce_partials(workspace, grid, 1, loss, 0, stream);
 }
@@ -692,6 +696,6 @@ PFO_API int pfo_eval_score(const float* es, const float* ed, const float* ec, in
         cudaFuncSetAttribute(eval_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    eval_score_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(es, ed, ec, n_cand, d, topk, scores, pos_rank, top_idx);
+    pfo_launch(eval_score_kernel, B, 256, smem, (cudaStream_t)stream, es, ed, ec, n_cand, d, topk, scores, pos_rank, top_idx);
     PFO_LAUNCH_CHECK();
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "../../include/pfo_b200.h"
 
 #define PFO_API extern "C" __attribute__((visibility("default")))
@@ -26,6 +27,46 @@ static inline int pfo_grid(int64_t work, int block, int ctas_per_sm) {
     int64_t cap = (int64_t)pfo_num_sms() * ctas_per_sm;
     if (need < 1) need = 1;
     return (int)(need < cap ? need : cap);
+}
+
+// ---- programmatic dependent launch.  A step is ~60 kernels of 5-200 us chained through one stream (one CUDA graph):
+// with plain launches every kernel boundary costs the full drain -> schedule -> ramp-up gap.  Every kernel of this
+// library is therefore launched with the programmatic-stream-serialization attribute and begins with
+//     griddepcontrol.wait;               (returns once the preceding grid has completed and its writes are visible)
+//     griddepcontrol.launch_dependents;  (lets the NEXT grid's CTAs be scheduled while this one still runs)
+// so the next kernel's launch latency and CTA ramp-up overlap this kernel's execution, while no kernel reads or
+// writes global memory before its predecessor is complete (the wait comes first, so the relaxation is never
+// transitive: when grid C starts, grid B has passed its own wait, i.e. grid A is complete).  Kernels of other
+// libraries in between (torch, NCCL) neither wait nor trigger and keep plain stream order.  PFO_PDL=0 in the
+// environment turns the attribute off (the two instructions are then no-ops).
+__device__ __forceinline__ void pfo_pdl_prologue() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+static inline bool pfo_pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("PFO_PDL");
+        on = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return on != 0;
+}
+
+template <typename... KArgs, typename... Args>
+static inline void pfo_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pfo_pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);     // errors surface through PFO_LAUNCH_CHECK
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -56,6 +56,7 @@ eval_metrics_kernel(const int32_t* __restrict__ pos_rank, const int32_t* __restr
                     const int32_t* __restrict__ port_items, const double* __restrict__ lr_past,
                     const double* __restrict__ lr_future, int n_stocks, int T, int B,
                     double* __restrict__ per_event) {
+    pfo_pdl_prologue();
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -112,6 +113,7 @@ eval_metrics_kernel(const int32_t* __restrict__ pos_rank, const int32_t* __restr
 // acc[30] += B; one CTA, fixed summation order (deterministic)
 __global__ void __launch_bounds__(1024)
 eval_metrics_reduce_kernel(const double* __restrict__ per_event, int B, double* __restrict__ acc) {
+    pfo_pdl_prologue();
     __shared__ double sh_sum[32][kCols];
     __shared__ double sh_pos[32][kCols];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -147,9 +149,9 @@ PFO_API int pfo_eval_metrics(const int32_t* pos_rank, const int32_t* top_idx, in
     if (n_returns < 1 || n_returns > 32 || topk < 5 || n_cand + 1 < 5) return (int)cudaErrorInvalidValue;
     cudaStream_t s = (cudaStream_t)stream;
     const int grid = pfo_grid((int64_t)B * 32, 128, 16);
-    eval_metrics_kernel<<<grid, 128, 0, s>>>(pos_rank, top_idx, topk, pos_item, cand, n_cand, item_offset, day_idx,
+    pfo_launch(eval_metrics_kernel, grid, 128, 0, s, pos_rank, top_idx, topk, pos_item, cand, n_cand, item_offset, day_idx,
                                              port_ptr, port_items, logret_past, logret_future, n_stocks, n_returns, B,
                                              per_event);
-    if (acc != nullptr) eval_metrics_reduce_kernel<<<1, 1024, 0, s>>>(per_event, B, acc);
+    if (acc != nullptr) pfo_launch(eval_metrics_reduce_kernel, 1, 1024, 0, s, per_event, B, acc);
     PFO_LAUNCH_CHECK();
 }

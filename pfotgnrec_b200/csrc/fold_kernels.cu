@@ -91,6 +91,7 @@ __host__ __device__ __forceinline__ int tiles(int x) { return (x + TS - 1) / TS;
 
 // ---- forward stage 1: T_h = Wo_h [Wv_h | bv_h] | Wqk_h = s Wk_h^T Wq_h[:, :d] | te0, cq, padding rows of Wqk
 __global__ void __launch_bounds__(256) fold_fwd1_kernel(const FoldArgs p) {
+    pfo_pdl_prologue();
     const int d = p.d, E = p.E, Ek = p.Ek, H = p.H, hd = p.hd, ekp = p.ekp, R = Ek + 1;
     __shared__ double As[TS][TS + 1], Bs[TS][TS + 1];   // A tile [m][k], B tile [k][n]
     int job = blockIdx.x;
@@ -131,6 +132,7 @@ static int fold_fwd1_jobs(int d, int F, int H) { const int E = 2 * d, Ek = E + F
 
 // ---- forward stage 2: Wc1T head rows = (W1a T_h)^T | cqk, `valid` / `one` / padding rows, W1b^T rows
 __global__ void __launch_bounds__(256) fold_fwd2_kernel(const FoldArgs p) {
+    pfo_pdl_prologue();
     const int d = p.d, E = p.E, Ek = p.Ek, H = p.H, hd = p.hd, ekp = p.ekp, R = Ek + 1;
     __shared__ double As[TS][TS + 1], Bs[TS][TS + 1];   // A tile [m][k], B tile [k][n]
     int job = blockIdx.x;
@@ -186,6 +188,7 @@ static int fold_fwd2_jobs(int d, int F, int H) { const int Ek = 2 * d + F; retur
 // ---- backward stage 1 (needs T and cq of the forward):
 //   gW1a | gT_h = (W1a^T gB_h)^T (layout [h][r][e]) | gWq[:, :d] | gWk | gbo, gcq, gW1b, gb1
 __global__ void __launch_bounds__(256) fold_bwd1_kernel(const FoldArgs p) {
+    pfo_pdl_prologue();
     const int d = p.d, E = p.E, Ek = p.Ek, H = p.H, hd = p.hd, ekp = p.ekp, R = Ek + 1;
     const float* gc1 = p.gWc1T + (size_t)R * d;                   // head 0, `valid` row
     __shared__ double As[TS][TS + 1], Bs[TS][TS + 1];   // A tile [m][k], B tile [k][n]
@@ -257,6 +260,7 @@ static int fold_bwd1_jobs(int d, int F, int H) {
 
 // ---- backward stage 2 (needs gT and gcq): gWo | gWv, gbv | gb_in (q, k parts), gWq[:, d:], gtb
 __global__ void __launch_bounds__(256) fold_bwd2_kernel(const FoldArgs p) {
+    pfo_pdl_prologue();
     const int d = p.d, E = p.E, Ek = p.Ek, H = p.H, hd = p.hd, R = Ek + 1;
     __shared__ double As[TS][TS + 1], Bs[TS][TS + 1];   // A tile [m][k], B tile [k][n]
     int job = blockIdx.x;
@@ -333,8 +337,8 @@ PFO_API int pfo_fold_attention_fwd(const float* Wq, const float* Wk, const float
     if (fill(a, Wq, Wk, Wv, b_in, Wo, bo, W1, b1, tb, d, F, H, ekp, workspace)) return (int)cudaErrorInvalidValue;
     a.Wqk = Wqk; a.cqk = cqk; a.Wc1T = Wc1T;
     cudaStream_t s = (cudaStream_t)stream;
-    fold_fwd1_kernel<<<fold_fwd1_jobs(d, F, H), 256, 0, s>>>(a);
-    fold_fwd2_kernel<<<fold_fwd2_jobs(d, F, H), 256, 0, s>>>(a);
+    pfo_launch(fold_fwd1_kernel, fold_fwd1_jobs(d, F, H), 256, 0, s, a);
+    pfo_launch(fold_fwd2_kernel, fold_fwd2_jobs(d, F, H), 256, 0, s, a);
     PFO_LAUNCH_CHECK();
 }
 
@@ -349,7 +353,7 @@ PFO_API int pfo_fold_attention_bwd(const float* Wq, const float* Wk, const float
     a.gWqk = gWqk; a.gcqk = gcqk; a.gWc1T = gWc1T;
     a.gWq = gWq; a.gWk = gWk; a.gWv = gWv; a.gb_in = gb_in; a.gWo = gWo; a.gbo = gbo; a.gW1 = gW1; a.gb1 = gb1; a.gtb = gtb;
     cudaStream_t s = (cudaStream_t)stream;
-    fold_bwd1_kernel<<<fold_bwd1_jobs(d, F, H), 256, 0, s>>>(a);
-    fold_bwd2_kernel<<<fold_bwd2_jobs(d, F, H), 256, 0, s>>>(a);
+    pfo_launch(fold_bwd1_kernel, fold_bwd1_jobs(d, F, H), 256, 0, s, a);
+    pfo_launch(fold_bwd2_kernel, fold_bwd2_jobs(d, F, H), 256, 0, s, a);
     PFO_LAUNCH_CHECK();
 }

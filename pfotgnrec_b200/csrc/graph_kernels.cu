@@ -63,6 +63,7 @@ neighbor_recent_kernel(const int64_t* __restrict__ rowptr, const int32_t* __rest
                        int64_t Q, int n, int64_t ld,
                        int32_t* __restrict__ out_nbr, int32_t* __restrict__ out_eidx,
                        float* __restrict__ out_etime, float* __restrict__ out_dt) {
+    pfo_pdl_prologue();
     constexpr int QPW = 32 / LPQ;                     // queries per warp-iteration
     const int lane = threadIdx.x & 31;
     const int grp = lane / LPQ, sub = lane % LPQ;
@@ -121,6 +122,7 @@ neighbor_uniform_kernel(const int64_t* __restrict__ rowptr, const int32_t* __res
                         const uint32_t* __restrict__ call_ctr, const int32_t* __restrict__ q_ids, int64_t ld,
                         int32_t* __restrict__ out_nbr, int32_t* __restrict__ out_eidx,
                         float* __restrict__ out_etime, float* __restrict__ out_dt) {
+    pfo_pdl_prologue();
     // uniform-with-replacement mode (utils.py:193-204); slot j of query q draws
     // pos = mulhi32(philox(q, call_id, j, PURPOSE_NBR).x, i) and the picks are ordered by
     // (fp32 time, position): see oracle/graph.py for the contract.  call_id = host part + device counter, so a
@@ -174,6 +176,7 @@ constexpr int kMarkThreads = 1024;
 // words inside a warp with __match_any_sync, which the compiler expands into a ~200-instruction loop per warp.
 __global__ void __launch_bounds__(kMarkThreads)
 mark_nodes_kernel(const int32_t* __restrict__ ids, int64_t count, int skip_zero, uint32_t* __restrict__ bitmap) {
+    pfo_pdl_prologue();
     __shared__ int tag[kMarkSlots];
     __shared__ uint32_t bits[kMarkSlots];
     for (int i = threadIdx.x; i < kMarkSlots; i += kMarkThreads) { tag[i] = -1; bits[i] = 0u; }
@@ -227,6 +230,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
 
 __global__ void __launch_bounds__(kCompactBlock)
 compact_count_kernel(const uint32_t* __restrict__ bitmap, int64_t n_words, int32_t* __restrict__ block_sums) {
+    pfo_pdl_prologue();
     const int64_t w0 = (int64_t)blockIdx.x * kWordsPerBlock + (int64_t)threadIdx.x * kWordsPerThread;
     int c = 0;
 #pragma unroll
@@ -239,6 +243,7 @@ compact_count_kernel(const uint32_t* __restrict__ bitmap, int64_t n_words, int32
 
 __global__ void __launch_bounds__(kCompactBlock)
 compact_scan_kernel(int32_t* __restrict__ block_sums, int n_blocks, int32_t* __restrict__ n_unique) {
+    pfo_pdl_prologue();
     // single CTA: exclusive scan of the per-block counts, in place
     __shared__ int carry;
     if (threadIdx.x == 0) carry = 0;
@@ -260,6 +265,7 @@ compact_scan_kernel(int32_t* __restrict__ block_sums, int n_blocks, int32_t* __r
 __global__ void __launch_bounds__(kCompactBlock)
 compact_emit_kernel(uint32_t* __restrict__ bitmap, int64_t n_words, const int32_t* __restrict__ block_offs,
                     int32_t* __restrict__ uniq_ids, int32_t* __restrict__ slot_of_node) {
+    pfo_pdl_prologue();
     const int64_t w0 = (int64_t)blockIdx.x * kWordsPerBlock + (int64_t)threadIdx.x * kWordsPerThread;
     uint32_t words[kWordsPerThread];
     int c = 0;
@@ -287,6 +293,7 @@ compact_emit_kernel(uint32_t* __restrict__ bitmap, int64_t n_words, const int32_
 
 __global__ void map_slots_kernel(const int32_t* __restrict__ ids, int64_t count, int skip_zero,
                                  const int32_t* __restrict__ slot_of_node, int32_t* __restrict__ out) {
+    pfo_pdl_prologue();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
         const int v = ids[i];
         out[i] = (v > 0 || (v == 0 && !skip_zero)) ? slot_of_node[v] : -1;
@@ -300,7 +307,7 @@ static void launch_recent(const int64_t* rowptr, const int32_t* adj_nbr, const i
                           const int32_t* q_nodes, const double* q_ts, int64_t Q, int n, int64_t ld, int32_t* out_nbr,
                           int32_t* out_eidx, float* out_etime, float* out_dt, cudaStream_t s) {
     const int64_t threads = Q * LPQ;
-    neighbor_recent_kernel<LPQ><<<pfo_grid(threads, 256, 8), 256, 0, s>>>(
+    pfo_launch(neighbor_recent_kernel<LPQ>, pfo_grid(threads, 256, 8), 256, 0, s, 
         rowptr, adj_nbr, adj_eidx, adj_ts, q_nodes, q_ts, Q, n, ld, out_nbr, out_eidx, out_etime, out_dt);
 }
 
@@ -317,7 +324,7 @@ PFO_API int pfo_neighbor_sample(const int64_t* rowptr, const int32_t* adj_nbr, c
     cudaStream_t s = (cudaStream_t)stream;
     if (uniform) {
         if (n_neighbors > PFO_MAX_UNIFORM_NBR) return (int)cudaErrorInvalidValue;
-        neighbor_uniform_kernel<<<pfo_grid(n_queries, 128, 8), 128, 0, s>>>(
+        pfo_launch(neighbor_uniform_kernel, pfo_grid(n_queries, 128, 8), 128, 0, s, 
             rowptr, adj_nbr, adj_eidx, adj_ts, q_nodes, q_ts, n_queries, n_neighbors,
             (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), call_id, call_ctr, q_ids, ld, out_nbr, out_eidx,
             out_etime, out_dt);
@@ -352,7 +359,7 @@ PFO_API int pfo_mark_nodes(const int32_t* ids, int64_t count, int skip_zero, uin
     if (count <= 0) return 0;
     int64_t grid = (count + 2 * kMarkThreads - 1) / (2 * kMarkThreads);      // >= 2 ids per thread, at most one CTA per SM
     if (grid > pfo_num_sms()) grid = pfo_num_sms();
-    mark_nodes_kernel<<<(int)grid, kMarkThreads, 0, (cudaStream_t)stream>>>(ids, count, skip_zero, bitmap);
+    pfo_launch(mark_nodes_kernel, (int)grid, kMarkThreads, 0, (cudaStream_t)stream, ids, count, skip_zero, bitmap);
     PFO_LAUNCH_CHECK();
 }
 
@@ -366,15 +373,15 @@ PFO_API int pfo_compact_nodes(uint32_t* bitmap, int64_t n_nodes, int32_t* worksp
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t n_words = (n_nodes + 31) / 32;
     const int n_blocks = (int)((n_words + kWordsPerBlock - 1) / kWordsPerBlock);
-    compact_count_kernel<<<n_blocks, kCompactBlock, 0, s>>>(bitmap, n_words, workspace);
-    compact_scan_kernel<<<1, kCompactBlock, 0, s>>>(workspace, n_blocks, n_unique);
-    compact_emit_kernel<<<n_blocks, kCompactBlock, 0, s>>>(bitmap, n_words, workspace, uniq_ids, slot_of_node);
+    pfo_launch(compact_count_kernel, n_blocks, kCompactBlock, 0, s, bitmap, n_words, workspace);
+    pfo_launch(compact_scan_kernel, 1, kCompactBlock, 0, s, workspace, n_blocks, n_unique);
+    pfo_launch(compact_emit_kernel, n_blocks, kCompactBlock, 0, s, bitmap, n_words, workspace, uniq_ids, slot_of_node);
     PFO_LAUNCH_CHECK();
 }
 
 PFO_API int pfo_map_slots(const int32_t* ids, int64_t count, int skip_zero, const int32_t* slot_of_node,
                           int32_t* out, void* stream) {
     if (count <= 0) return 0;
-    map_slots_kernel<<<pfo_grid(count, 256, 8), 256, 0, (cudaStream_t)stream>>>(ids, count, skip_zero, slot_of_node, out);
+    pfo_launch(map_slots_kernel, pfo_grid(count, 256, 8), 256, 0, (cudaStream_t)stream, ids, count, skip_zero, slot_of_node, out);
     PFO_LAUNCH_CHECK();
 }

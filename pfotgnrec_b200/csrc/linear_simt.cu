@@ -32,6 +32,7 @@ struct LinearArgs {
 template <int TN>
 __global__ void __launch_bounds__(256)
 linear_kernel(const LinearArgs p) {
+    pfo_pdl_prologue();
     constexpr int BN = 16 * TN;
     constexpr int LDW_S = BN + 4;
     __shared__ __align__(16) float As[2][BK][LDA_S];
@@ -165,6 +166,7 @@ struct WgradArgs {
 
 __global__ void __launch_bounds__(256)
 wgrad_kernel(const WgradArgs p) {
+    pfo_pdl_prologue();
     __shared__ __align__(16) float Gs[WR][LDG_S];
     __shared__ __align__(16) float As[WR][LDG_S];
     int64_t M = p.M;
@@ -232,6 +234,7 @@ wgrad_kernel(const WgradArgs p) {
 
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int S, int N, int K, int Kaug,
                                     float* __restrict__ dW, int64_t lddw, float* __restrict__ db, int accumulate) {
+    pfo_pdl_prologue();
     const int total = N * Kaug;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         float s = 0.0f;
@@ -249,7 +252,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int S, in
 template <int TN>
 int launch_linear(const LinearArgs& a, cudaStream_t s) {
     dim3 grid((unsigned)((a.M + BM - 1) / BM), (unsigned)((a.N + 16 * TN - 1) / (16 * TN)));
-    linear_kernel<TN><<<grid, 256, 0, s>>>(a);
+    pfo_launch(linear_kernel<TN>, grid, 256, 0, s, a);
     PFO_LAUNCH_CHECK();
 }
 
@@ -304,9 +307,9 @@ int pfo_wgrad_f32_impl(const float* G, int64_t ldg, const float* A, int64_t lda,
     if (S > cap) S = cap;
     if (S < 1) S = 1;
     WgradArgs a{G, ldg, A, lda, a_idx, workspace, M, m_dev, N, K, Kaug, (int)S};
-    wgrad_kernel<<<dim3(tiles, (unsigned)S), 256, 0, s>>>(a);
+    pfo_launch(wgrad_kernel, dim3(tiles, (unsigned)S), 256, 0, s, a);
     const int total = N * Kaug;
-    wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(workspace, (int)S, N, K, Kaug, dW, lddw, db, accumulate);
+    pfo_launch(wgrad_reduce_kernel, (total + 255) / 256, 256, 0, s, workspace, (int)S, N, K, Kaug, dW, lddw, db, accumulate);
     PFO_LAUNCH_CHECK();
 }
 

@@ -63,6 +63,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 __global__ void __launch_bounds__(THREADS, 1)
 linear_tc_kernel(const TcArgs p) {
+    pfo_pdl_prologue();
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
@@ -237,6 +238,6 @@ PFO_API int pfo_linear_bf16(const float* A, int64_t lda, const int32_t* a_idx, c
     if (per_sm > 4) per_sm = 4;
     int64_t grid = (int64_t)pfo_num_sms() * per_sm;
     if (grid > tiles) grid = tiles;
-    linear_tc_kernel<<<(unsigned)grid, THREADS, smem, (cudaStream_t)stream>>>(a);
+    pfo_launch(linear_tc_kernel, (unsigned)grid, THREADS, smem, (cudaStream_t)stream, a);
     PFO_LAUNCH_CHECK();
 }

@@ -168,6 +168,7 @@ struct Producer {
 template <int PASSES>
 __global__ void __launch_bounds__(PASSES == 3 ? THREADS_3 : THREADS_1, 1)
 linear_tma_kernel(const __grid_constant__ CUtensorMap tmA, const TmaLinArgs p) {
+    pfo_pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler (role dispatch)
@@ -524,7 +525,7 @@ int launch_tma(const CUtensorMap& map, const TmaLinArgs& a, dim3 grid, size_t sm
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    linear_tma_kernel<PASSES><<<grid, PASSES == 3 ? THREADS_3 : THREADS_1, smem, s>>>(map, a);
+    pfo_launch(linear_tma_kernel<PASSES>, grid, PASSES == 3 ? THREADS_3 : THREADS_1, smem, s, map, a);
     PFO_LAUNCH_CHECK();
 }
 

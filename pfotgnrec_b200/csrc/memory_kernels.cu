@@ -22,6 +22,7 @@ cell_forward_kernel(const int32_t* __restrict__ uniq, const int32_t* __restrict_
                     int cell, const float* __restrict__ GI, const float* __restrict__ GH, int64_t ldg,
                     const float* __restrict__ HG, const uint8_t* __restrict__ valid_u,
                     const float* __restrict__ node_feat, float* __restrict__ Hnew, float* __restrict__ H0) {
+    pfo_pdl_prologue();
     int64_t U = *n_uniq; if (U > u_max) U = u_max;
     const int64_t total = U * d;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -56,6 +57,7 @@ cell_backward_kernel(const int32_t* __restrict__ uniq, const int32_t* __restrict
                      int cell, const float* __restrict__ GI, const float* __restrict__ GH, int64_t ldg,
                      const float* __restrict__ HG, const uint8_t* __restrict__ valid_u,
                      const float* __restrict__ dH, float* __restrict__ dGI, float* __restrict__ dGH) {
+    pfo_pdl_prologue();
     int64_t U = *n_uniq; if (U > u_max) U = u_max;
     const int64_t total = U * d;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -102,6 +104,7 @@ gather_state_kernel(const int32_t* __restrict__ uniq, const int32_t* __restrict_
                     const uint8_t* __restrict__ pend_valid, const float* __restrict__ pend_ts,
                     const float* __restrict__ last_update,
                     float* __restrict__ HG, float* __restrict__ XG, uint8_t* __restrict__ valid_u, float* __restrict__ lu_u) {
+    pfo_pdl_prologue();
     int64_t U = *n_uniq; if (U > u_max) U = u_max;
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -132,6 +135,7 @@ persist_rank_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__
                     const int32_t* __restrict__ slot_of_node, const float* __restrict__ Hnew,
                     const uint8_t* __restrict__ pend_valid, const float* __restrict__ pend_ts,
                     float* __restrict__ memory, float* __restrict__ last_update, int32_t* __restrict__ last_pos) {
+    pfo_pdl_prologue();
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -160,6 +164,7 @@ store_messages_kernel(const int32_t* __restrict__ src, const int32_t* __restrict
                       const float* __restrict__ self_emb_for_src, const float* __restrict__ self_emb_for_dst,
                       float* __restrict__ pend_msg, int64_t rawp, float* __restrict__ pend_ts,
                       uint8_t* __restrict__ pend_valid, int32_t* __restrict__ last_pos) {
+    pfo_pdl_prologue();
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -202,6 +207,7 @@ time_embedding_fwd_kernel(const int32_t* __restrict__ q_nodes, const double* __r
                           float mean_src, float std_src, float mean_dst, float std_dst,
                           const float* __restrict__ W, const float* __restrict__ b,
                           float* __restrict__ td_out, float* __restrict__ emb) {
+    pfo_pdl_prologue();
     const int64_t total = Q * d;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t q = i / d;
@@ -223,6 +229,7 @@ time_embedding_bwd_kernel(const int32_t* __restrict__ q_nodes, int64_t Q, int d,
                           const int32_t* __restrict__ slot_of_node, const float* __restrict__ Hnew,
                           const float* __restrict__ td, const float* __restrict__ W, const float* __restrict__ b,
                           const float* __restrict__ dEmb, float* __restrict__ dHnew, float* __restrict__ partial) {
+    pfo_pdl_prologue();
     extern __shared__ float sm[];          // [2][d]
     for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) sm[c] = 0.0f;
     __syncthreads();
@@ -247,6 +254,7 @@ time_embedding_bwd_kernel(const int32_t* __restrict__ q_nodes, int64_t Q, int d,
 // e.g. the BPR loss partials) put the rows across the lanes instead.
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const float* __restrict__ partial, int rows, int cols, float* __restrict__ out, int accumulate) {
+    pfo_pdl_prologue();
     __shared__ float sm[8][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (cols >= 32) {
@@ -283,6 +291,7 @@ reduce_partials_kernel(const float* __restrict__ partial, int rows, int cols, fl
 __global__ void __launch_bounds__(256)
 scatter_add_rows_kernel(const float* __restrict__ src, int64_t lds, const int32_t* __restrict__ idx, int64_t M, int d,
                         float* __restrict__ dst, int64_t ldd) {
+    pfo_pdl_prologue();
     const int64_t total = M * d;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t m = i / d;
@@ -296,6 +305,7 @@ scatter_add_rows_kernel(const float* __restrict__ src, int64_t lds, const int32_
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const float* __restrict__ src, int64_t lds, const int32_t* __restrict__ idx, int64_t M, int d,
                    float* __restrict__ dst, int64_t ldd) {
+    pfo_pdl_prologue();
     const int64_t total = M * d;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t m = i / d;
@@ -318,6 +328,7 @@ build_messages_kernel(const int32_t* __restrict__ src_slot, const int32_t* __res
                       float* __restrict__ rows, int64_t ldr, float* __restrict__ t32_out,
                       const int32_t* __restrict__ src_node, const int32_t* __restrict__ dst_node, int n_ranks,
                       int key_base, int key_side) {
+    pfo_pdl_prologue();
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -361,6 +372,7 @@ apply_rank_kernel(const int32_t* __restrict__ node, const int32_t* __restrict__ 
                   const int32_t* __restrict__ slot_of_node, const float* __restrict__ Hnew,
                   const uint8_t* __restrict__ pend_valid, const float* __restrict__ pend_ts,
                   float* __restrict__ memory, float* __restrict__ last_update, int32_t* __restrict__ last_pos) {
+    pfo_pdl_prologue();
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -383,6 +395,7 @@ apply_store_kernel(const int32_t* __restrict__ node, const int32_t* __restrict__
                    const float* __restrict__ rows, int64_t ldr, const float* __restrict__ t32,
                    float* __restrict__ pend_msg, int64_t rawp, float* __restrict__ pend_ts,
                    uint8_t* __restrict__ pend_valid, int32_t* __restrict__ last_pos) {
+    pfo_pdl_prologue();
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -414,6 +427,7 @@ store_messages_mean_kernel(const int32_t* __restrict__ src, const int32_t* __res
                            const float* __restrict__ self_emb_for_src, const float* __restrict__ self_emb_for_dst,
                            float* __restrict__ pend_msg, int64_t rawp, float* __restrict__ pend_ts,
                            uint8_t* __restrict__ pend_valid, int32_t* __restrict__ last_pos) {
+    pfo_pdl_prologue();
     constexpr int MAXC = 4;                                    // d <= 128: columns per lane and segment
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -480,7 +494,7 @@ PFO_API int pfo_cell_forward(const int32_t* uniq, const int32_t* n_uniq, int64_t
                              const uint8_t* valid_u, const float* node_feat, float* Hnew, float* H0,
                              void* stream) {
     if (u_max <= 0) return 0;
-    cell_forward_kernel<<<pfo_grid(u_max * d, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+    pfo_launch(cell_forward_kernel, pfo_grid(u_max * d, 256, 8), 256, 0, (cudaStream_t)stream, 
         uniq, n_uniq, u_max, d, cell, GI, GH, ldg, HG, valid_u, node_feat, Hnew, H0);
     PFO_LAUNCH_CHECK();
 }
@@ -489,7 +503,7 @@ PFO_API int pfo_cell_backward(const int32_t* uniq, const int32_t* n_uniq, int64_
                               const float* GI, const float* GH, int64_t ldg, const float* HG,
                               const uint8_t* valid_u, const float* dH, float* dGI, float* dGH, void* stream) {
     if (u_max <= 0) return 0;
-    cell_backward_kernel<<<pfo_grid(u_max * d, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+    pfo_launch(cell_backward_kernel, pfo_grid(u_max * d, 256, 8), 256, 0, (cudaStream_t)stream, 
         uniq, n_uniq, u_max, d, cell, GI, GH, ldg, HG, valid_u, dH, dGI, dGH);
     PFO_LAUNCH_CHECK();
 }
@@ -499,7 +513,7 @@ PFO_API int pfo_gather_state(const int32_t* uniq, const int32_t* n_uniq, int64_t
                              const float* pend_ts, const float* last_update,
                              float* HG, float* XG, uint8_t* valid_u, float* lu_u, void* stream) {
     if (u_max <= 0) return 0;
-    gather_state_kernel<<<pfo_grid(u_max * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+    pfo_launch(gather_state_kernel, pfo_grid(u_max * 32, 256, 8), 256, 0, (cudaStream_t)stream, 
         uniq, n_uniq, u_max, d, raw, memory, pend_msg, rawp, pend_valid, pend_ts, last_update, HG, XG, valid_u, lu_u);
     PFO_LAUNCH_CHECK();
 }
@@ -508,7 +522,7 @@ PFO_API int pfo_persist_rank(const int32_t* src, const int32_t* dst, int B, int 
                              const float* Hnew, const uint8_t* pend_valid, const float* pend_ts,
                              float* memory, float* last_update, int32_t* last_pos, void* stream) {
     if (B <= 0) return 0;
-    persist_rank_kernel<<<pfo_grid(2 * (int64_t)B * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+    pfo_launch(persist_rank_kernel, pfo_grid(2 * (int64_t)B * 32, 256, 8), 256, 0, (cudaStream_t)stream, 
         src, dst, B, d, slot_of_node, Hnew, pend_valid, pend_ts, memory, last_update, last_pos);
     PFO_LAUNCH_CHECK();
 }
@@ -521,7 +535,7 @@ PFO_API int pfo_store_messages(const int32_t* src, const int32_t* dst, const int
                                float* pend_msg, int64_t rawp, float* pend_ts, uint8_t* pend_valid,
                                int32_t* last_pos, void* stream) {
     if (B <= 0) return 0;
-    store_messages_kernel<<<pfo_grid(2 * (int64_t)B * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+    pfo_launch(store_messages_kernel, pfo_grid(2 * (int64_t)B * 32, 256, 8), 256, 0, (cudaStream_t)stream, 
         src, dst, eidx, ts, B, d, F, memory, last_update, edge_feat, tw, tb, other_emb_for_src,
         other_emb_for_dst, self_emb_for_src, self_emb_for_dst, pend_msg, rawp, pend_ts, pend_valid, last_pos);
     PFO_LAUNCH_CHECK();
@@ -537,7 +551,7 @@ PFO_API int pfo_store_messages_mean(const int32_t* src, const int32_t* dst, cons
                                     int32_t* last_pos, void* stream) {
     if (B <= 0) return 0;
     if (d > 128 || F > 32) return (int)cudaErrorInvalidValue;
-    store_messages_mean_kernel<<<pfo_grid(2 * (int64_t)B * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+    pfo_launch(store_messages_mean_kernel, pfo_grid(2 * (int64_t)B * 32, 256, 8), 256, 0, (cudaStream_t)stream, 
         src, dst, eidx, ts, B, d, F, sorted_node, order, memory, last_update, edge_feat, tw, tb, other_emb_for_src,
         other_emb_for_dst, self_emb_for_src, self_emb_for_dst, pend_msg, rawp, pend_ts, pend_valid, last_pos);
     PFO_LAUNCH_CHECK();
@@ -548,7 +562,7 @@ PFO_API int pfo_time_embedding_fwd(const int32_t* q_nodes, const double* q_ts, i
                                    float mean_src, float std_src, float mean_dst, float std_dst,
                                    const float* W, const float* b, float* td_out, float* emb, void* stream) {
     if (Q <= 0) return 0;
-    time_embedding_fwd_kernel<<<pfo_grid(Q * d, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+    pfo_launch(time_embedding_fwd_kernel, pfo_grid(Q * d, 256, 8), 256, 0, (cudaStream_t)stream, 
         q_nodes, q_ts, Q, n_src, d, slot_of_node, Hnew, lu_u,
         mean_src, std_src, mean_dst, std_dst, W, b, td_out, emb);
     PFO_LAUNCH_CHECK();
@@ -563,10 +577,10 @@ PFO_API int pfo_time_embedding_bwd(const int32_t* q_nodes, int64_t Q, int d, con
     int grid = pfo_grid(Q * d, 256, 2);
     if ((int64_t)grid * 2 * d > workspace_floats) grid = (int)(workspace_floats / (2 * d));
     if (grid < 1) return (int)cudaErrorInvalidValue;
-    time_embedding_bwd_kernel<<<grid, 256, 2 * d * sizeof(float), s>>>(q_nodes, Q, d, slot_of_node, Hnew, td, W, b,
+    pfo_launch(time_embedding_bwd_kernel, grid, 256, 2 * d * sizeof(float), s, q_nodes, Q, d, slot_of_node, Hnew, td, W, b,
                                                                       dEmb, dHnew, workspace);
     // partial rows are [dW(d) | db(d)]; dWdb receives the same layout
-    reduce_partials_kernel<<<(2 * d + 31) / 32, 256, 0, s>>>(workspace, grid, 2 * d, dWdb, 0);
+    pfo_launch(reduce_partials_kernel, (2 * d + 31) / 32, 256, 0, s, workspace, grid, 2 * d, dWdb, 0);
     PFO_LAUNCH_CHECK();
 }
 
@@ -576,6 +590,7 @@ PFO_API int pfo_time_embedding_bwd(const int32_t* q_nodes, int64_t Q, int d, con
 static __global__ void time_encode_kernel(const float* __restrict__ t, const float* __restrict__ w,
                                           const float* __restrict__ b, int64_t M, int d, int mode,
                                           float* __restrict__ out_cos, float* __restrict__ out_sin) {
+    pfo_pdl_prologue();
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -600,27 +615,27 @@ PFO_API int pfo_time_encode(const float* t, const float* w, const float* b, int6
                             float* out_cos, float* out_sin, void* stream) {
     if (M <= 0) return 0;
     if (d <= 0 || mode < 0 || mode > 2) return (int)cudaErrorInvalidValue;
-    time_encode_kernel<<<pfo_grid(M * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(t, w, b, M, d, mode, out_cos, out_sin);
+    pfo_launch(time_encode_kernel, pfo_grid(M * 32, 256, 8), 256, 0, (cudaStream_t)stream, t, w, b, M, d, mode, out_cos, out_sin);
     PFO_LAUNCH_CHECK();
 }
 
 PFO_API int pfo_reduce_partials(const float* partial, int rows, int cols, float* out, int accumulate, void* stream) {
     if (cols <= 0) return 0;
-    reduce_partials_kernel<<<cols >= 32 ? (cols + 31) / 32 : cols, 256, 0, (cudaStream_t)stream>>>(partial, rows, cols, out, accumulate);
+    pfo_launch(reduce_partials_kernel, cols >= 32 ? (cols + 31) / 32 : cols, 256, 0, (cudaStream_t)stream, partial, rows, cols, out, accumulate);
     PFO_LAUNCH_CHECK();
 }
 
 PFO_API int pfo_scatter_add_rows(const float* src, int64_t lds, const int32_t* idx, int64_t M, int d,
                                  float* dst, int64_t ldd, void* stream) {
     if (M <= 0) return 0;
-    scatter_add_rows_kernel<<<pfo_grid(M * d, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, lds, idx, M, d, dst, ldd);
+    pfo_launch(scatter_add_rows_kernel, pfo_grid(M * d, 256, 8), 256, 0, (cudaStream_t)stream, src, lds, idx, M, d, dst, ldd);
     PFO_LAUNCH_CHECK();
 }
 
 PFO_API int pfo_gather_rows(const float* src, int64_t lds, const int32_t* idx, int64_t M, int d,
                             float* dst, int64_t ldd, void* stream) {
     if (M <= 0) return 0;
-    gather_rows_kernel<<<pfo_grid(M * d, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, lds, idx, M, d, dst, ldd);
+    pfo_launch(gather_rows_kernel, pfo_grid(M * d, 256, 8), 256, 0, (cudaStream_t)stream, src, lds, idx, M, d, dst, ldd);
     PFO_LAUNCH_CHECK();
 }
 
@@ -629,7 +644,7 @@ PFO_API int pfo_build_messages(const int32_t* src_slot, const int32_t* dst_slot,
                                const float* tw, const float* tb, const float* other_emb_for_src,
                                const float* other_emb_for_dst, float* rows, int64_t ldr, float* t32_out, void* stream) {
     if (B <= 0) return 0;
-    build_messages_kernel<<<pfo_grid(2 * (int64_t)B * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+    pfo_launch(build_messages_kernel, pfo_grid(2 * (int64_t)B * 32, 256, 8), 256, 0, (cudaStream_t)stream, 
         src_slot, dst_slot, eidx, ts, B, d, F, Hnew, lu_u, edge_feat, tw, tb, other_emb_for_src, other_emb_for_dst,
         rows, ldr, t32_out, nullptr, nullptr, 1, 0, 0);
     PFO_LAUNCH_CHECK();
@@ -643,7 +658,7 @@ PFO_API int pfo_build_routed_messages(const int32_t* src_slot, const int32_t* ds
                                       float* rows, int64_t ldr, void* stream) {
     if (B <= 0) return 0;
     if (ldr < 3 * d + F + 3 || n_ranks <= 0) return (int)cudaErrorInvalidValue;
-    build_messages_kernel<<<pfo_grid(2 * (int64_t)B * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+    pfo_launch(build_messages_kernel, pfo_grid(2 * (int64_t)B * 32, 256, 8), 256, 0, (cudaStream_t)stream, 
         src_slot, dst_slot, eidx, ts, B, d, F, Hnew, lu_u, edge_feat, tw, tb, other_emb_for_src, other_emb_for_dst,
         rows, ldr, nullptr, src_node, dst_node, n_ranks, key_base, key_side);
     PFO_LAUNCH_CHECK();
@@ -660,9 +675,9 @@ PFO_API int pfo_apply_routed_messages(const float* rows, int64_t ldr, int64_t R,
     const int32_t* node = reinterpret_cast<const int32_t*>(rows) + raw;      // meta words behind the message
     const int32_t* key = node + 1;
     const float* t32 = rows + raw + 2;
-    apply_rank_kernel<<<grid, 256, 0, s>>>(node, key, ldr, R, d, slot_of_node, Hnew, pend_valid, pend_ts, memory,
+    pfo_launch(apply_rank_kernel, grid, 256, 0, s, node, key, ldr, R, d, slot_of_node, Hnew, pend_valid, pend_ts, memory,
                                            last_update, last_pos);
-    apply_store_kernel<<<grid, 256, 0, s>>>(node, key, ldr, R, raw, rows, ldr, t32, pend_msg, rawp, pend_ts, pend_valid,
+    pfo_launch(apply_store_kernel, grid, 256, 0, s, node, key, ldr, R, raw, rows, ldr, t32, pend_msg, rawp, pend_ts, pend_valid,
                                             last_pos);
     PFO_LAUNCH_CHECK();
 }
@@ -674,9 +689,9 @@ PFO_API int pfo_apply_messages(const int32_t* node, const int32_t* key, int64_t 
     if (R <= 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     const int grid = pfo_grid(R * 32, 256, 8);
-    apply_rank_kernel<<<grid, 256, 0, s>>>(node, key, 1, R, d, slot_of_node, Hnew, pend_valid, pend_ts, memory,
+    pfo_launch(apply_rank_kernel, grid, 256, 0, s, node, key, 1, R, d, slot_of_node, Hnew, pend_valid, pend_ts, memory,
                                            last_update, last_pos);
-    apply_store_kernel<<<grid, 256, 0, s>>>(node, key, 1, R, raw, rows, ldr, t32, pend_msg, rawp, pend_ts, pend_valid,
+    pfo_launch(apply_store_kernel, grid, 256, 0, s, node, key, 1, R, raw, rows, ldr, t32, pend_msg, rawp, pend_ts, pend_valid,
                                             last_pos);
     PFO_LAUNCH_CHECK();
 }

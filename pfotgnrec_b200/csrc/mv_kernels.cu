@@ -117,6 +117,7 @@ struct MvArgs {
 
 __global__ void __launch_bounds__(kWarps * 32)
 mv_select_kernel(const MvArgs p) {
+    pfo_pdl_prologue();
     __shared__ unsigned long long keys[kWarps][kCap];
     __shared__ int counts[kWarps];
     __shared__ int hs[kWarps][32];
@@ -260,6 +261,7 @@ __global__ void __launch_bounds__(256)
 sample_candidates_kernel(const int64_t* __restrict__ event_ids, const int64_t* __restrict__ port_ptr,
                          const int32_t* __restrict__ port_items, const int32_t* __restrict__ items, int M,
                          int size, uint32_t k0, uint32_t k1, int pow2, int32_t* __restrict__ out) {
+    pfo_pdl_prologue();
     extern __shared__ unsigned long long sk[];      // [pow2]
     __shared__ int n_held_s;
     __shared__ int hs[32];
@@ -330,7 +332,7 @@ PFO_API int pfo_mv_select(const int64_t* event_ids, const int32_t* day_idx, cons
     MvArgs a{event_ids, day_idx, pos_stock, port_ptr, port_items, items_sorted, n_items_universe,
              logret, n_stocks, n_returns, B, K, gamma, lam, n_pos, n_neg,
              (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), sample, cand, y_out, p_pos, p_neg, item_offset};
-    mv_select_kernel<<<pfo_grid((int64_t)B * 32, kWarps * 32, 8), kWarps * 32, 0, (cudaStream_t)stream>>>(a);
+    pfo_launch(mv_select_kernel, pfo_grid((int64_t)B * 32, kWarps * 32, 8), kWarps * 32, 0, (cudaStream_t)stream, a);
     PFO_LAUNCH_CHECK();
 }
 
@@ -347,7 +349,7 @@ PFO_API int pfo_sample_candidates(const int64_t* event_ids, const int64_t* port_
         cudaFuncSetAttribute(sample_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         attr_set = true;
     }
-    sample_candidates_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(
+    pfo_launch(sample_candidates_kernel, B, 256, smem, (cudaStream_t)stream, 
         event_ids, port_ptr, port_items, items_sorted, n_items_universe, size,
         (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), pow2, out);
     PFO_LAUNCH_CHECK();

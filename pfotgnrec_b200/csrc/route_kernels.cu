@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(256)
 route_plan_kernel(const int32_t* __restrict__ ids, int64_t R, const int32_t* __restrict__ n_valid, int G, int cap,
                   int32_t* __restrict__ counts, int32_t* __restrict__ slot, int32_t* __restrict__ local_id,
                   int32_t* __restrict__ overflow) {
+    pfo_pdl_prologue();
     const int lane = threadIdx.x & 31;
     const int64_t limit = n_valid ? (int64_t)*n_valid : R;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -56,6 +57,7 @@ route_plan_kernel(const int32_t* __restrict__ ids, int64_t R, const int32_t* __r
 __global__ void __launch_bounds__(256)
 scatter_rows_kernel(const uint32_t* __restrict__ src, int64_t lds, const int32_t* __restrict__ slot, int64_t M, int w,
                     uint32_t* __restrict__ dst, int64_t ldd) {
+    pfo_pdl_prologue();
     const int64_t total = M * w;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t m = i / w;
@@ -69,6 +71,7 @@ scatter_rows_kernel(const uint32_t* __restrict__ src, int64_t lds, const int32_t
 __global__ void __launch_bounds__(256)
 gather_words_kernel(const uint32_t* __restrict__ src, int64_t lds, const int32_t* __restrict__ slot, int64_t M, int w,
                     uint32_t* __restrict__ dst, int64_t ldd, uint32_t fill) {
+    pfo_pdl_prologue();
     const int64_t total = M * w;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t m = i / w;
@@ -83,6 +86,7 @@ __global__ void __launch_bounds__(256)
 pack_queries_kernel(const int32_t* __restrict__ local_id, const double* __restrict__ q_ts,
                     const int32_t* __restrict__ q_ids, const int32_t* __restrict__ slot, int64_t Q,
                     int32_t* __restrict__ out) {
+    pfo_pdl_prologue();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < Q; i += (int64_t)gridDim.x * blockDim.x) {
         const int s = slot[i];
         if (s < 0) continue;
@@ -100,6 +104,7 @@ pack_queries_kernel(const int32_t* __restrict__ local_id, const double* __restri
 __global__ void __launch_bounds__(256)
 unpack_queries_kernel(const int32_t* __restrict__ in, int64_t R, int32_t* __restrict__ q_nodes,
                       double* __restrict__ q_ts, int32_t* __restrict__ q_ids) {
+    pfo_pdl_prologue();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < R; i += (int64_t)gridDim.x * blockDim.x) {
         const int4 row = reinterpret_cast<const int4*>(in)[i];
         q_nodes[i] = row.x;
@@ -118,7 +123,7 @@ PFO_API int pfo_route_plan(const int32_t* ids, int64_t n_rows, const int32_t* n_
     cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int32_t) * n_ranks, s);
     if (e != cudaSuccess) return (int)e;
     if (n_rows <= 0) return 0;
-    route_plan_kernel<<<pfo_grid(n_rows, 256, 4), 256, 0, s>>>(ids, n_rows, n_valid, n_ranks, cap, counts, slot,
+    pfo_launch(route_plan_kernel, pfo_grid(n_rows, 256, 4), 256, 0, s, ids, n_rows, n_valid, n_ranks, cap, counts, slot,
                                                               local_id, overflow);
     PFO_LAUNCH_CHECK();
 }
@@ -126,7 +131,7 @@ PFO_API int pfo_route_plan(const int32_t* ids, int64_t n_rows, const int32_t* n_
 PFO_API int pfo_scatter_rows(const void* src, int64_t lds, const int32_t* slot, int64_t M, int w, void* dst,
                              int64_t ldd, void* stream) {
     if (M <= 0 || w <= 0) return 0;
-    scatter_rows_kernel<<<pfo_grid(M * w, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+    pfo_launch(scatter_rows_kernel, pfo_grid(M * w, 256, 8), 256, 0, (cudaStream_t)stream, 
         (const uint32_t*)src, lds, slot, M, w, (uint32_t*)dst, ldd);
     PFO_LAUNCH_CHECK();
 }
@@ -134,7 +139,7 @@ PFO_API int pfo_scatter_rows(const void* src, int64_t lds, const int32_t* slot, 
 PFO_API int pfo_gather_words(const void* src, int64_t lds, const int32_t* slot, int64_t M, int w, void* dst,
                              int64_t ldd, uint32_t fill, void* stream) {
     if (M <= 0 || w <= 0) return 0;
-    gather_words_kernel<<<pfo_grid(M * w, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+    pfo_launch(gather_words_kernel, pfo_grid(M * w, 256, 8), 256, 0, (cudaStream_t)stream, 
         (const uint32_t*)src, lds, slot, M, w, (uint32_t*)dst, ldd, fill);
     PFO_LAUNCH_CHECK();
 }
@@ -142,7 +147,7 @@ PFO_API int pfo_gather_words(const void* src, int64_t lds, const int32_t* slot, 
 PFO_API int pfo_pack_queries(const int32_t* local_id, const double* q_ts, const int32_t* q_ids, const int32_t* slot,
                              int64_t n_queries, int32_t* out_rows, void* stream) {
     if (n_queries <= 0) return 0;
-    pack_queries_kernel<<<pfo_grid(n_queries, 256, 8), 256, 0, (cudaStream_t)stream>>>(local_id, q_ts, q_ids, slot,
+    pfo_launch(pack_queries_kernel, pfo_grid(n_queries, 256, 8), 256, 0, (cudaStream_t)stream, local_id, q_ts, q_ids, slot,
                                                                                      n_queries, out_rows);
     PFO_LAUNCH_CHECK();
 }
@@ -150,6 +155,6 @@ PFO_API int pfo_pack_queries(const int32_t* local_id, const double* q_ts, const 
 PFO_API int pfo_unpack_queries(const int32_t* in_rows, int64_t n_rows, int32_t* q_nodes, double* q_ts, int32_t* q_ids,
                                void* stream) {
     if (n_rows <= 0) return 0;
-    unpack_queries_kernel<<<pfo_grid(n_rows, 256, 8), 256, 0, (cudaStream_t)stream>>>(in_rows, n_rows, q_nodes, q_ts, q_ids);
+    pfo_launch(unpack_queries_kernel, pfo_grid(n_rows, 256, 8), 256, 0, (cudaStream_t)stream, in_rows, n_rows, q_nodes, q_ts, q_ids);
     PFO_LAUNCH_CHECK();
 }

@@ -116,6 +116,7 @@ __device__ __forceinline__ bool elect_one() {
 template <int PASSES>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmA, const WgTmaArgs p) {
+    pfo_pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler (role dispatch)
@@ -336,6 +337,7 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
 __global__ void __launch_bounds__(256)
 wgrad_tma_reduce_kernel(const float* __restrict__ partial, int S, int N, int K, int Kaug,
                         float* __restrict__ dW, int64_t lddw, float* __restrict__ db, int accumulate) {
+    pfo_pdl_prologue();
     __shared__ float sm[8][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int total = N * Kaug;
@@ -376,7 +378,7 @@ int launch_wg(const CUtensorMap& mg, const CUtensorMap& ma, const WgTmaArgs& a, 
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    wgrad_tma_kernel<PASSES><<<grid, WG_THREADS, smem, s>>>(mg, ma, a);
+    pfo_launch(wgrad_tma_kernel<PASSES>, grid, WG_THREADS, smem, s, mg, ma, a);
     return (int)cudaGetLastError();
 }
 
@@ -424,6 +426,6 @@ PFO_API int pfo_wgrad_tf32(const float* G, int64_t ldg, const float* A, int64_t 
     int rc = passes == 3 ? launch_wg<3>(mg, ma, a, grid, smem, s) : launch_wg<1>(mg, ma, a, grid, smem, s);
     if (rc) return rc;
     const int total = N * a.Kaug;
-    wgrad_tma_reduce_kernel<<<(total + 31) / 32, 256, 0, s>>>(workspace, a.S, N, K, a.Kaug, dW, lddw, db, accumulate);
+    pfo_launch(wgrad_tma_reduce_kernel, (total + 31) / 32, 256, 0, s, workspace, a.S, N, K, a.Kaug, dW, lddw, db, accumulate);
     PFO_LAUNCH_CHECK();
 }

@@ -37,6 +37,7 @@ from ._lib import ptr
 from .engine import TGNEngine, TGNState, ModelConfig, _linear
 from .graph import TemporalCSR, NeighborFinder
 from .trainer import PfoTrainer, allreduce_sum_, replica_slice
+from .synth_device import DeviceStream
 
 F4 = 4
 
@@ -201,28 +202,60 @@ def local_csr(st_sources, st_destinations, st_edge_idxs, st_timestamps, n_nodes,
 
 
 def _local_csr_device(csr, src, dst, eid, ts, n_local, rank, world):
-    """Device build of `local_csr` from device columns (also the path of the GPU-resident generator)."""
-    parts = []
-    for node, other in ((src, dst), (dst, src)):            # each interaction is appended to both endpoints
-        mine = torch.nonzero(node % world == rank).view(-1)
-        parts.append((mine, torch.div(node[mine], world, rounding_mode="floor"), other[mine]))
-    # stream order of the 2E entries is (event, side): restore it after concatenating the two sides
-    pos = torch.cat([parts[0][0] * 2, parts[1][0] * 2 + 1])
-    o0 = torch.sort(pos).indices
-    ev = torch.cat([parts[0][0], parts[1][0]])[o0]
-    ln = torch.cat([parts[0][1], parts[1][1]])[o0]
-    other = torch.cat([parts[0][2], parts[1][2]])[o0]
-    t = ts[ev]
+    """Device build of `local_csr` from device columns."""
+    return build_local_csr(csr, [(0, src, dst)], lambda ev: ts[ev], lambda ev: eid[ev], n_local, rank, world)
+
+
+def build_local_csr(csr, chunks, ts_of, eidx_of, n_local, rank, world):
+    """CSR rows of the owned nodes from an iterator of (first interaction index, sources, destinations) device chunks --
+    a 10^9-interaction stream never sits in memory at once: each chunk is filtered to the entries whose node this rank
+    owns (each interaction is appended to both endpoints, utils/utils.py:122-123), only those are kept, and timestamps
+    / edge idxs are looked up for the survivors (`ts_of`, `eidx_of`: functions of the interaction index).  Order inside
+    a row = (timestamp, stream order) through two stable device sorts (torch.sort on CUDA is a radix sort)."""
+    ev_l, ln_l, other_l, side_l = [], [], [], []
+    dev = None
+    for i0, src, dst in chunks:
+        dev = src.device
+        src, dst = src.long(), dst.long()
+        for side, (node, other) in enumerate(((src, dst), (dst, src))):
+            mine = torch.nonzero(node % world == rank).view(-1)
+            ev_l.append(mine + i0)
+            ln_l.append(torch.div(node[mine], world, rounding_mode="floor").to(torch.int32))
+            other_l.append(other[mine].to(torch.int32))
+            side_l.append(torch.full_like(mine, side, dtype=torch.int8))
+    ev, ln, other, side = torch.cat(ev_l), torch.cat(ln_l), torch.cat(other_l), torch.cat(side_l)
+    del ev_l, ln_l, other_l, side_l
+    # stream order of the 2E entries is (interaction, side): restore it, then sort by time, then by node (both stable)
+    o0 = torch.sort(ev * 2 + side.long()).indices
+    ev, ln, other = ev[o0], ln[o0], other[o0]
+    del o0, side
+    t = ts_of(ev)
     o1 = torch.sort(t, stable=True).indices
     o2 = torch.sort(ln[o1], stable=True).indices
     order = o1[o2]
-    csr.nbr = other[order].to(torch.int32).contiguous()
-    csr.eidx = eid[ev][order].to(torch.int32).contiguous()
+    del o1, o2
+    csr.nbr = other[order].contiguous()
+    csr.eidx = eidx_of(ev[order]).to(torch.int32).contiguous()
     csr.ts = t[order].contiguous()
-    counts = torch.bincount(ln, minlength=n_local)
-    csr.rowptr = torch.zeros(n_local + 1, dtype=torch.int64, device=src.device)
+    counts = torch.bincount(ln.long(), minlength=n_local)
+    csr.rowptr = torch.zeros(n_local + 1, dtype=torch.int64, device=dev)
     torch.cumsum(counts, 0, out=csr.rowptr[1:])
     return csr
+
+
+def local_csr_from_device_stream(ds, n_events, rank, world, chunk=1 << 26):
+    """`local_csr` of the first `n_events` interactions of a procedural `synth_device.DeviceStream`."""
+    n_local = (ds.n_nodes + world - 1) // world
+    csr = TemporalCSR.__new__(TemporalCSR)
+    csr.n_nodes, csr.n_events, csr.device = n_local, int(n_events), ds.device
+
+    def chunks():
+        for i0 in range(0, n_events, chunk):
+            i = torch.arange(i0, min(n_events, i0 + chunk), dtype=torch.int64, device=ds.device)
+            src, dst = ds.src_dst(i)
+            yield i0, src, dst
+
+    return build_local_csr(csr, chunks(), ds.timestamps, lambda ev: ev + 1, n_local, rank, world)
 
 
 class ShardedNeighborFinder(NeighborFinder):
@@ -414,9 +447,96 @@ class ShardedTrainer(PfoTrainer):
             p.grad = g.view_as(p)
 
     # ---- construction hooks
+    @property
+    def procedural(self):
+        return isinstance(self.st, DeviceStream)
+
+    def _prepare_stream(self, train_frac_mask=None):
+        """Host streams go through the base class.  A procedural `DeviceStream` (scale configuration, 10^9 interactions)
+        never materialises on the host: the split point comes from a bisection on its monotone timestamps, the feature
+        tables are drawn on the device, and batches are evaluated from the interaction index on demand."""
+        if not self.procedural:
+            return super()._prepare_stream(train_frac_mask)
+        st, tc, dev = self.st, self.tc, self.device
+        if tc.model == "jodie":
+            raise NotImplementedError("the time embedding needs per-node inter-event statistics of the whole stream "
+                                      "(utils/data.py:75-99): not computed for procedural streams")
+        self.n_train, self.masks = st.n_train(0.8), None
+        self._n_val_end = st.n_train(0.9)
+        self.dev_stream = None
+        self._col_cache = {}
+        g = torch.Generator(device=dev).manual_seed(0)
+        node_feat = torch.rand(st.n_nodes, tc.d, device=dev, generator=g)          # main.py:87: U(0, 1)
+        edge_feat = torch.zeros(st.n_events + 1, 1, device=dev)
+        present = torch.zeros(st.n_items, dtype=torch.bool, device=dev)
+        present_tr = torch.zeros(st.n_items, dtype=torch.bool, device=dev)
+        chunk = 1 << 26
+        for i0 in range(0, st.n_events, chunk):
+            i = torch.arange(i0, min(st.n_events, i0 + chunk), dtype=torch.int64, device=dev)
+            edge_feat[i0 + 1:i0 + 1 + i.numel(), 0] = st.edge_feature(i)
+            item = st.src_dst(i)[1].long() - st.n_users - 1
+            present[item] = True
+            n_in = max(0, min(self.n_train - i0, i.numel()))
+            if n_in > 0:
+                present_tr[item[:n_in]] = True
+        off = st.n_users + 1
+        return dict(train_index=None, node_feat=node_feat, edge_feat=edge_feat, time_statistics=(0.0, 1.0, 0.0, 1.0),
+                    universe_train=torch.nonzero(present_tr).view(-1).cpu().numpy() + off,
+                    universe_all=torch.nonzero(present).view(-1).cpu().numpy() + off)
+
+    def _columns(self, s, e):
+        """Device columns of interactions [s, e) of a procedural stream (small cache: a batch is usually asked for twice,
+        by the static-buffer fill and by the host-batch builder)."""
+        key = (int(s), int(e))
+        c = self._col_cache.get(key)
+        if c is None:
+            if len(self._col_cache) >= 256:
+                self._col_cache.pop(next(iter(self._col_cache)))
+            c = self._col_cache[key] = self.st.columns(s, e)
+        return c
+
+    def prefetch(self, spans):
+        """Evaluate the columns of the given (s, e) GLOBAL batches ahead of time (this rank's slices), so that a timed
+        loop only copies them into the static buffers."""
+        if self.procedural:
+            for s, e in spans:
+                self._columns(*replica_slice(s, e, self.rank, self.world))
+
+    def _batch(self, s, e):
+        if not self.procedural:
+            return super()._batch(s, e)
+        c, off = self._columns(s, e), self._ev_offset()
+        b = dict(c)
+        if off:
+            b["ev"] = c["ev"] + off
+        return b
+
+    def _port_capacity(self, B):
+        return self.st.max_port * B + 1 if self.procedural else super()._port_capacity(B)
+
+    def _fill_static(self, sg, s, e):
+        if not self.procedural:
+            return super()._fill_static(sg, s, e)
+        c, x = self._columns(s, e), sg.static
+        for k in ("src", "dst", "ts", "eidx", "day", "port_ptr", "port_items"):
+            x[k].copy_(c[k])
+        torch.add(c["ev"], self._ev_offset(), out=x["ev"])
+
+    def split_ranges(self):
+        if not self.procedural:
+            return super().split_ranges()
+        return (0, self.n_train), (self.n_train, self._n_val_end), (self._n_val_end, self.st.n_events)
+
     def _build_finders(self, tr):
         st, tc, dev = self.st, self.tc, self.device
         uniform = tc.model == "tgat"
+        if self.procedural:
+            csr_tr = local_csr_from_device_stream(st, self.n_train, self.rank, self.world)
+            csr_full = local_csr_from_device_stream(st, st.n_events, self.rank, self.world)
+            self.csr_train, self.csr_full = csr_tr, csr_full
+            self.nf_train = ShardedNeighborFinder(csr_tr, self.ex, uniform=uniform, seed=tc.seed, tag="nf_train")
+            self.nf_full = ShardedNeighborFinder(csr_full, self.ex, uniform=uniform, seed=tc.seed, tag="nf_full")
+            return
         csr_tr = local_csr(st.sources[tr], st.destinations[tr], st.edge_idxs[tr], st.timestamps[tr], st.n_nodes,
                            self.rank, self.world, dev)
         csr_full = local_csr(st.sources, st.destinations, st.edge_idxs, st.timestamps, st.n_nodes,
@@ -502,8 +622,13 @@ class ShardedTrainer(PfoTrainer):
         out = []
         for i in range(count):
             s = start + i * bs * self.world
-            ls, _ = replica_slice(s, s + bs * self.world, self.rank, self.world)
-            hb = super().make_host_batches(ls, 1, bs)[0]
+            ls, le = replica_slice(s, s + bs * self.world, self.rank, self.world)
+            if self.procedural:
+                c, off = self._columns(ls, le), self._ev_offset()
+                hb = {k: (v + off if k == "ev" else v).cpu().pin_memory() for k, v in c.items()}
+                hb["nbytes"] = sum(v.numel() * v.element_size() for v in hb.values())
+            else:
+                hb = super().make_host_batches(ls, 1, bs)[0]
             hb["_global"] = (s, s + bs * self.world)
             out.append(hb)
         return out

@@ -722,7 +722,8 @@ class TGNStepFunction(torch.autograd.Function):
         if c.graph:
             nf = eng.nf
             calls0 = getattr(nf, "call_id", 0)
-            tree = eng._sample_tree(q_nodes, q_ts, c.n_layers, n, batch.get("q_ids"))
+            with _lib.nvtx_range("K1 neighbour sampling"):
+                tree = eng._sample_tree(q_nodes, q_ts, c.n_layers, n, batch.get("q_ids"))
             if getattr(nf, "call_ctr", None) is not None and torch.cuda.is_current_stream_capturing():
                 # uniform sampling inside a captured step: the host call ids are baked into the graph, the device
                 # counter advances by the step's number of K1 calls on every replay (fresh Philox streams)
@@ -734,7 +735,8 @@ class TGNStepFunction(torch.autograd.Function):
             id_lists = id_lists + [sb["src"], sb["dst"]]    # their updated memory rows must be in the node table
 
         # 2. lazy memory update on the unique nodes (memory_updater.py:35-53, restricted)
-        tab = eng.node_table(id_lists, cellW, mlpW) if mlpW is not None else eng.node_table(id_lists, cellW)
+        with _lib.nvtx_range("K3 node table (compaction + lazy memory update)"):
+            tab = eng.node_table(id_lists, cellW, mlpW) if mlpW is not None else eng.node_table(id_lists, cellW)
         uniq, u_max, n_uniq = tab["uniq"], tab["u_max"], tab["n_uniq"]
         H0, Hnew, lu_u = tab["H0"], tab["Hnew"], tab["lu_u"]
 
@@ -745,7 +747,8 @@ class TGNStepFunction(torch.autograd.Function):
         qslots = eng._slots(q_nodes)
         if c.embedding == "graph_attention":
             eng.join_side()
-            emb, tape = eng._attention_forward(tree, layerW, H0, save)
+            with _lib.nvtx_range("K4 temporal attention forward"):
+                emb, tape = eng._attention_forward(tree, layerW, H0, save)
         elif c.embedding == "graph_sum":
             emb, tape = eng._sum_forward(tree, layerW, H0, save)
         elif c.embedding == "time":
@@ -762,7 +765,8 @@ class TGNStepFunction(torch.autograd.Function):
 
         # 4. persist positives, then build + store the new raw messages (tgn.py:185-206)
         if c.use_memory and batch["update_state"]:
-            eng.persist_and_store(tab, sb, emb, tw, tb)
+            with _lib.nvtx_range("K2 persist + message store"):
+                eng.persist_and_store(tab, sb, emb, tw, tb)
         out = emb
         if c.use_memory and c.dyrep:    # dyrep returns the updated memory rows (tgn.py:211-215, :322-325)
             out = torch.empty(Q, d, device=dev)
@@ -843,16 +847,18 @@ class TGNStepFunction(torch.autograd.Function):
                 else:
                     tp.dTq = torch.zeros(tp.child_q.out_rows, d, device=dev)
                     tp.dT = torch.zeros(tp.child_n.out_rows, d, device=dev)
-                eng._attention_backward(tp, g, pk["layerW"], g_layers, save)
+                with _lib.nvtx_range("K4 temporal attention backward"):
+                    eng._attention_backward(tp, g, pk["layerW"], g_layers, save)
                 if tp.layer > 1:
                     stack.append((tp.child_q, tp.dTq))
                     stack.append((tp.child_n, tp.dT))
             # the fold's adjoint runs beside the memory-updater backward (it needs only the finished operand grads)
             eng.unfold_layer_grads(pk["rawW"], flat[1], pk["fold_ws"], g_layers, g_raw, [g[5] for g in g_layers])
-        if c.use_memory and g_mlp is not None:
-            eng.node_table_backward(pk["tab"], dH0, g_cell, pk["mlpW"], g_mlp, pk["cellW"])
-        elif c.use_memory:
-            eng.node_table_backward(pk["tab"], dH0, g_cell)
+        with _lib.nvtx_range("K3 memory updater backward"):
+            if c.use_memory and g_mlp is not None:
+                eng.node_table_backward(pk["tab"], dH0, g_cell, pk["mlpW"], g_mlp, pk["cellW"])
+            elif c.use_memory:
+                eng.node_table_backward(pk["tab"], dH0, g_cell)
         if attention_grad:
             eng.join_side()
             for g in g_layers:

@@ -59,10 +59,16 @@ class TGN(torch.nn.Module):
         if message_function not in ("identity", "mlp"):
             raise ValueError("Message function {} not implemented".format(message_function))
         # feature tables on the device; edge features z-normalised over ALL rows, the padding row included (tgn.py:38-41)
-        ef = edge_features.astype(np.float32)
-        ef = (ef - ef.mean(axis=0)) / ef.std(axis=0)
-        self.node_raw_features = torch.from_numpy(node_features.astype(np.float32)).to(device)
-        self.edge_raw_features = torch.from_numpy(ef.astype(np.float32)).to(device)
+        if isinstance(edge_features, torch.Tensor):      # extension: tables already on the device (scale configuration)
+            ef = edge_features.to(device=device, dtype=torch.float32)
+            var, mean = torch.var_mean(ef, dim=0, unbiased=False)
+            self.edge_raw_features = ((ef - mean) / var.sqrt()).contiguous()
+            self.node_raw_features = node_features.to(device=device, dtype=torch.float32).contiguous()
+        else:
+            ef = edge_features.astype(np.float32)
+            ef = (ef - ef.mean(axis=0)) / ef.std(axis=0)
+            self.node_raw_features = torch.from_numpy(node_features.astype(np.float32)).to(device)
+            self.edge_raw_features = torch.from_numpy(ef.astype(np.float32)).to(device)
         self.n_nodes, self.n_node_features = self.node_raw_features.shape
         self.n_edge_features = self.edge_raw_features.shape[1]
         # plain attributes the callers (and checkpoints of the reference) know by name

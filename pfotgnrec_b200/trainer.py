@@ -169,15 +169,8 @@ class PfoTrainer:
             raise NotImplementedError("p_pos_num != 1: the fused BPR path takes one MV-selected positive per interaction")
         self.epoch = 0               # folded into the key of the candidate / negative streams (fresh draws per epoch)
         tgn_mod, _ = load_overlay()
-        train_mask, val_mask, test_mask = st.split()
-        if train_frac_mask is not None:
-            train_mask = train_frac_mask
-        self.masks = (train_mask, val_mask, test_mask)
-        self.n_train = int(train_mask.sum())
-        tr = np.nonzero(train_mask)[0]
-        self._build_finders(tr)
-        rs = np.random.RandomState(0)                     # main.py:9,87: node features ~ U(0,1)
-        node_feat = rs.rand(st.n_nodes, tc.d)
+        info = self._prepare_stream(train_frac_mask)         # split, device columns, feature tables, item universes
+        self._build_finders(info["train_index"])
         kw = dict(memory_updater_type="gru", embedding_module_type="graph_attention", use_memory=True,
                   dyrep=False, use_destination_embedding_in_message=False)
         if tc.model == "jodie":
@@ -186,10 +179,10 @@ class PfoTrainer:
             kw.update(memory_updater_type="rnn", dyrep=True, use_destination_embedding_in_message=True)
         elif tc.model == "tgat":
             kw.update(use_memory=False)
-        ms, ss, md, sd = self._time_statistics()
+        ms, ss, md, sd = info["time_statistics"]
         torch.manual_seed(tc.seed)
-        self.tgn = tgn_mod.TGN(neighbor_finder=self.nf_train, node_features=node_feat,
-                               edge_features=st.edge_features.copy(), device=self.device, n_layers=tc.n_layers,
+        self.tgn = tgn_mod.TGN(neighbor_finder=self.nf_train, node_features=info["node_feat"],
+                               edge_features=info["edge_feat"], device=self.device, n_layers=tc.n_layers,
                                n_heads=tc.n_heads, dropout=tc.dropout, message_dimension=100,
                                memory_dimension=tc.d, memory_update_at_start=True, message_function="identity",
                                aggregator_type="last", n_neighbors=tc.n_neighbors,
@@ -199,8 +192,7 @@ class PfoTrainer:
         self._bind_engine()
         self.opt = torch.optim.Adam(self.tgn.parameters(), lr=tc.lr, fused=True, capturable=True)
         self._graphs = {}            # batch size -> _StepGraph
-        self.dev_stream = StreamOnDevice(st, device)
-        universe_items = np.unique(st.destinations[tr])
+        universe_items = info["universe_train"]
         self.universe_items = universe_items
         self.mv = None
         if tc.model == "ours":
@@ -208,7 +200,7 @@ class PfoTrainer:
                                  gamma=tc.gamma, lam=tc.lambda_mv, n_candidates=tc.num_negatives,
                                  n_pos=tc.p_pos_num, n_neg=tc.p_neg_num, seed=tc.seed, device=device)
         self.neg_sampler = CandidateSampler(universe_items, device=device)
-        self.eval_sampler = CandidateSampler(np.unique(st.destinations), device=device)
+        self.eval_sampler = CandidateSampler(info["universe_all"], device=device)
         self.bpr_ws = torch.empty(1024, device=self.device)
         # evaluation metric block (reference evaluation.py:127-258): in-sample (past) / out-of-sample (future)
         # daily log-returns and the running sums of the per-interaction metrics live on the device
@@ -216,6 +208,22 @@ class PfoTrainer:
         if st.prices_past.shape[0] == len(st.day_keys) and st.prices_past.shape[1] == st.n_items:
             self.metrics = EvalMetricBlock(log_returns(st.prices_past), log_returns(st.prices_future),
                                            st.n_users + 1, device=self.device)
+
+    def _prepare_stream(self, train_frac_mask=None):
+        """Everything the constructor derives from the interaction stream (host `synth.Stream`): the chronological
+        split (utils/data.py:27,48-50), the columns resident on the device, node features ~ U(0,1) (main.py:9,87), the
+        edge features, the time statistics (utils/data.py:75-99) and the item universes of the two samplers."""
+        st, tc = self.st, self.tc
+        train_mask, val_mask, test_mask = st.split()
+        if train_frac_mask is not None:
+            train_mask = train_frac_mask
+        self.masks = (train_mask, val_mask, test_mask)
+        self.n_train = int(train_mask.sum())
+        tr = np.nonzero(train_mask)[0]
+        self.dev_stream = StreamOnDevice(st, self.device)
+        return dict(train_index=tr, node_feat=np.random.RandomState(0).rand(st.n_nodes, tc.d),
+                    edge_feat=st.edge_features.copy(), time_statistics=self._time_statistics(),
+                    universe_train=np.unique(st.destinations[tr]), universe_all=np.unique(st.destinations))
 
     @property
     def eval_acc(self):
@@ -296,7 +304,7 @@ class PfoTrainer:
         sg = self._graphs.get(B)
         if sg is None:
             st, dev = self.st, self.device
-            cap = int(np.max(np.diff(st.port_ptr))) * B + 1 if st.port_ptr.size > 1 else 1
+            cap = self._port_capacity(B)
             i32, i64 = torch.int32, torch.int64
             static = dict(src=torch.zeros(B, dtype=i32, device=dev), dst=torch.zeros(B, dtype=i32, device=dev),
                           ts=torch.zeros(B, dtype=torch.float64, device=dev), eidx=torch.zeros(B, dtype=i32, device=dev),
@@ -305,6 +313,11 @@ class PfoTrainer:
                           port_items=torch.zeros(cap, dtype=i32, device=dev))
             sg = self._graphs[B] = _StepGraph(static)
         return sg
+
+    def _port_capacity(self, B):
+        """Entries of the static portfolio buffer of a B-interaction batch (largest portfolio x B, + 1 spare)."""
+        pp = self.st.port_ptr
+        return int(np.max(np.diff(pp))) * B + 1 if pp.size > 1 else 1
 
     def _fill_static(self, sg, s, e):
         D, st = self.dev_stream, self.st
@@ -354,8 +367,9 @@ class PfoTrainer:
         return loss
 
     def _finish(self):
-        self._reduce_grads()
-        self.opt.step()
+        with _lib.nvtx_range("gradient exchange + Adam"):
+            self._reduce_grads()
+            self.opt.step()
 
     def _fwd_bwd(self, b):
         tc, D = self.tc, self.dev_stream
@@ -365,10 +379,11 @@ class PfoTrainer:
         self._zero_grads()
         params = tgn._params()
         B = b["src"].shape[0]
-        port_items = b.get("port_items", D.port_items)
+        port_items = b["port_items"] if "port_items" in b else D.port_items
         sb = b.get("state")                          # replicated data-parallel mode: the global batch advances the state
         if tc.model == "ours":
-            p_pos, p_neg = self.mv.select(b["ev"], b["day"], b["dst"], b["port_ptr"], port_items)
+            with _lib.nvtx_range("K5 candidate sampling + MV selection"):
+                p_pos, p_neg = self.mv.select(b["ev"], b["day"], b["dst"], b["port_ptr"], port_items)
             emb = eng.compute_temporal_embeddings(params, b["src"], b["dst"], [p_pos, p_neg], b["ts"], b["eidx"],
                                                   tc.n_neighbors, train=True, state_batch=sb, packed=True)
             pos_block, neg_block = 2, 3                  # rows [src | dst | p_pos | p_neg]
@@ -378,8 +393,10 @@ class PfoTrainer:
             emb = eng.compute_temporal_embeddings(params, b["src"], b["dst"], [neg], b["ts"], b["eidx"],
                                                   tc.n_neighbors, train=True, state_batch=sb, packed=True)
             pos_block, neg_block = 1, 2                  # rows [src | dst | negatives]
-        loss = _BPRPacked.apply(emb, B, pos_block, neg_block, tc.p_neg_num, self.bpr_ws, self._loss_scale)
-        loss.backward()
+        with _lib.nvtx_range("K6 BPR forward + backward"):
+            loss = _BPRPacked.apply(emb, B, pos_block, neg_block, tc.p_neg_num, self.bpr_ws, self._loss_scale)
+        with _lib.nvtx_range("backward"):
+            loss.backward()
         return loss.detach()
 
     # hooks of the data-parallel subclass
@@ -459,7 +476,7 @@ class PfoTrainer:
                                                         state_batch=b["state"] if with_state else None)
         if self.metrics is not None and N >= 4:
             pos_rank, top, scores, per_event = self.metrics.step(e_s, e_d, e_c, b["dst"], cand, b["day"], b["port_ptr"],
-                                                                 b.get("port_items", D.port_items))
+                                                                 b["port_items"] if "port_items" in b else D.port_items)
             return pos_rank, top, cand, scores, per_event
         d = e_s.shape[1]
         scores = torch.empty(B, 1 + N, device=self.device)

@@ -203,3 +203,31 @@ def test_eval_metric_sums_all_reduce_gloo_world2():
     port = 31500 + os.getpid() % 2000
     mp.spawn(_metric_worker, args=(world, port, results), nprocs=world, join=True)
     assert dict(results) == {0: "ok", 1: "ok"}
+
+
+def test_chunked_device_csr_build_matches_the_host_build():
+    """build_local_csr (the chunked torch build used on the GPU, also for the 10^9-interaction procedural stream) ==
+    the numpy build of the owned rows == the rows of the global stable (node, time, stream order) sort."""
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    from pfotgnrec_b200.dist import local_csr, local_csr_from_device_stream, _local_csr_device
+    from pfotgnrec_b200.graph import TemporalCSR
+    from pfotgnrec_b200.synth_device import DeviceStream
+    ds = DeviceStream(n_users=700, n_items=40, n_events=6000, n_days=12, seed=3, device="cpu")
+    st = ds.materialise()
+    n_tr = ds.n_train()
+    for world in (2, 3):
+        for rank in range(world):
+            ref = local_csr(st.sources[:n_tr], st.destinations[:n_tr], st.edge_idxs[:n_tr], st.timestamps[:n_tr],
+                            st.n_nodes, rank, world, "cpu")
+            got = local_csr_from_device_stream(ds, n_tr, rank, world, chunk=1000)      # 5 chunks
+            n_local = (st.n_nodes + world - 1) // world
+            blank = TemporalCSR.__new__(TemporalCSR)
+            blank.n_nodes, blank.n_events, blank.device = n_local, n_tr, torch.device("cpu")
+            t = lambda a, dt: torch.as_tensor(np.asarray(a[:n_tr], dtype=dt))
+            one = _local_csr_device(blank, t(st.sources, np.int64), t(st.destinations, np.int64),
+                                    t(st.edge_idxs, np.int64), t(st.timestamps, np.float64), n_local, rank, world)
+            for c in (got, one):
+                for k in ("rowptr", "nbr", "eidx", "ts"):
+                    assert torch.equal(getattr(c, k).long() if k != "ts" else getattr(c, k),
+                                       getattr(ref, k).long() if k != "ts" else getattr(ref, k)), (world, rank, k)
