@@ -646,8 +646,13 @@ def main():
                "roofline": roofline, "cpu_baseline": cpu, "eval": ev_block, "eval_users_per_sec": eval_users,
                "kernels": kernels, "rooflines": rooflines, "large_batch": large}
         print(json.dumps(out))
-    if world > 1:
-        torch.distributed.destroy_process_group()
+    if world > 1 or a.procedural:
+        # the captured graphs of the sharded mode hold NCCL kernels; tearing the communicator down under them can block
+        # for minutes -- everything is printed, so synchronise, meet the other ranks and leave without the teardown
+        sys.stdout.flush()
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        os._exit(0)
 
 
 if __name__ == "__main__":

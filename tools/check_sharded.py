@@ -12,7 +12,13 @@ from pfotgnrec_b200.trainer import PfoTrainer, TrainConfig
 from pfotgnrec_b200.dist import ShardedTrainer
 
 
+def trainable(tr):
+    return [(k, p) for k, p in tr.tgn.named_parameters() if p.requires_grad]
+
+
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("PFO_HANG_DUMP_S", "100")), exit=True)   # where a hang sits
     rank, world, lr_ = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(lr_)
     dev = torch.device("cuda", lr_)
@@ -25,7 +31,7 @@ def main():
     kw = dict(model=model, lr=0.0, n_layers=layers, n_neighbors=nbrs, cuda_graph=graph)   # lr 0: weights stay equal
     sh = ShardedTrainer(st, TrainConfig(bs=bs, **kw), dev, rank, world)
     single = PfoTrainer(st, TrainConfig(bs=bs * world, **kw), device=dev)
-    for (k, a), (_, b) in zip(sh.tgn.named_parameters(), single.tgn.named_parameters()):
+    for (k, a), (_, b) in zip(trainable(sh), trainable(single)):
         assert torch.equal(a, b), k
     s0, worst = 12000, 0.0
     spans = [(s0 + i * bs * world, s0 + (i + 1) * bs * world) for i in range(6)]
@@ -38,7 +44,9 @@ def main():
         l_sh = float(l_sh.item())
         l_1 = float(single.train_step(s, e).item())
         assert abs(l_sh - l_1) < 1e-5 * max(1.0, abs(l_1)), (i, l_sh, l_1)
-        for (k, a), (_, b) in zip(sh.tgn.named_parameters(), single.tgn.named_parameters()):
+        if rank == 0:
+            print(f"step {i}: loss {l_sh:.6f} == {l_1:.6f}", flush=True)
+        for (k, a), (_, b) in zip(trainable(sh), trainable(single)):
             ga = a.grad if a.grad is not None else torch.zeros_like(a)
             gb = b.grad if b.grad is not None else torch.zeros_like(b)
             scale = max(float(gb.abs().max()), 1e-3)
@@ -88,7 +96,12 @@ def main():
               f"steps, loss {l_sh:.6f} vs {l_1:.6f}, worst grad rel.err {worst:.2e}, memory rel.err {merr:.2e}, "
               f"eval score rel.err {everr:.2e}; {t['sharded']:.3f} ms/step sharded vs {t['single']:.3f} ms single "
               f"(global batch {bs * world}); frozen capacities {caps}", flush=True)
-    dist.destroy_process_group()
+    faulthandler.cancel_dump_traceback_later()
+    sys.stdout.flush()
+    # captured graphs hold NCCL kernels: release them before the communicator goes away, and do not wait on teardown
+    torch.cuda.synchronize()
+    dist.barrier()
+    os._exit(0)
 
 
 if __name__ == "__main__":
