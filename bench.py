@@ -544,7 +544,8 @@ def main():
     # ---- the same step at the scale configuration's batch size: what the kernels reach once a launch carries enough
     # rows to leave the latency regime (extra information; `value` above stays the bs-8192 headline)
     large = None
-    if a.large_bs > 0 and world == 1 and not a.no_profile and a.large_bs != bs and 2 * a.large_bs < st.n_events - s0:
+    if (a.large_bs > 0 and world == 1 and rooflines is not None and a.large_bs != bs
+            and 2 * a.large_bs < st.n_events - s0):
         BL = a.large_bs
 
         def lstep(_i=None):

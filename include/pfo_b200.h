@@ -178,6 +178,15 @@ int pfo_pack_queries(const int32_t* local_id, const double* q_ts, const int32_t*
                      int64_t n_queries, int32_t* out_rows, void* stream);
 int pfo_unpack_queries(const int32_t* in_rows, int64_t n_rows, int32_t* q_nodes, double* q_ts, int32_t* q_ids,
                        void* stream);
+/* fused unpacking of the two request / reply exchanges: unroute_neighbors = reply rows [nbr | eidx | dt] (3n words) at
+ * slot[q] -> three dense [Q, n] arrays; route_reply_rows (owner) = [updated memory row | last_update'] per received id;
+ * unroute_rows (requester) = rows of the unique-node table from their slots plus H0 = memory' + node_feat[uniq]. */
+int pfo_unroute_neighbors(const int32_t* back, const int32_t* slot, int64_t n_queries, int n, int32_t* nbr,
+                          int32_t* eidx, float* dt, void* stream);
+int pfo_route_reply_rows(const float* Hnew_own, const float* lu_own, const int32_t* slots_own, int64_t n_rows, int d,
+                         float* reply, void* stream);
+int pfo_unroute_rows(const float* back, const int32_t* slot, const int32_t* uniq, const float* node_feat,
+                     int64_t n_rows, int d, float* Hnew, float* lu_u, float* H0, void* stream);
 
 
 /* ---- jodie time-projection embedding --- modules/embedding_module.py:57-61, model/tgn.py:260-266 */

@@ -114,7 +114,90 @@ unpack_queries_kernel(const int32_t* __restrict__ in, int64_t R, int32_t* __rest
     }
 }
 
+// requester side of R1: the reply rows [nbr (n) | eidx (n) | dt (n)] come back in the slots the queries left in; one pass
+// puts them into the three dense [Q, n] arrays of the un-sharded finder (dropped rows: zeros)
+__global__ void __launch_bounds__(256)
+unroute_neighbors_kernel(const int32_t* __restrict__ back, const int32_t* __restrict__ slot, int64_t Q, int n,
+                         int32_t* __restrict__ nbr, int32_t* __restrict__ eidx, float* __restrict__ dt) {
+    pfo_pdl_prologue();
+    const int64_t total = Q * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = i / n;
+        const int j = (int)(i - q * n);
+        const int s = slot[q];
+        int a = 0, b = 0, c = 0;
+        if (s >= 0) {
+            const int32_t* row = back + (int64_t)s * 3 * n;
+            a = row[j]; b = row[n + j]; c = row[2 * n + j];
+        }
+        nbr[i] = a; eidx[i] = b; dt[i] = __int_as_float(c);
+    }
+}
+
+// owner side of R2: reply row = [updated memory row (d) | last_update'] of the node each received id names (holes: zeros)
+__global__ void __launch_bounds__(256)
+route_reply_rows_kernel(const float* __restrict__ Hnew_own, const float* __restrict__ lu_own,
+                        const int32_t* __restrict__ slots_own, int64_t R, int d, float* __restrict__ reply) {
+    pfo_pdl_prologue();
+    const int w = d + 1;
+    const int64_t total = R * w;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / w;
+        const int c = (int)(i - r * w);
+        const int s = slots_own[r];
+        float v = 0.0f;
+        if (s >= 0) v = c < d ? Hnew_own[(int64_t)s * d + c] : lu_own[s];
+        reply[i] = v;
+    }
+}
+
+// requester side of R2: rows of the unique-node table from the reply slots, and H0 = memory' + node features
+__global__ void __launch_bounds__(256)
+unroute_rows_kernel(const float* __restrict__ back, const int32_t* __restrict__ slot, const int32_t* __restrict__ uniq,
+                    const float* __restrict__ node_feat, int64_t U, int d, float* __restrict__ Hnew,
+                    float* __restrict__ lu_u, float* __restrict__ H0) {
+    pfo_pdl_prologue();
+    const int w = d + 1;
+    const int64_t total = U * w;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t u = i / w;
+        const int c = (int)(i - u * w);
+        const int s = slot[u];
+        const float v = s >= 0 ? back[(int64_t)s * w + c] : 0.0f;
+        if (c < d) {
+            Hnew[u * d + c] = v;
+            H0[u * d + c] = v + node_feat[(int64_t)uniq[u] * d + c];
+        } else {
+            lu_u[u] = v;
+        }
+    }
+}
+
 }  // namespace
+
+PFO_API int pfo_unroute_neighbors(const int32_t* back, const int32_t* slot, int64_t n_queries, int n, int32_t* nbr,
+                                  int32_t* eidx, float* dt, void* stream) {
+    if (n_queries <= 0) return 0;
+    pfo_launch(unroute_neighbors_kernel, pfo_grid(n_queries * n, 256, 8), 256, 0, (cudaStream_t)stream, back, slot,
+               n_queries, n, nbr, eidx, dt);
+    PFO_LAUNCH_CHECK();
+}
+
+PFO_API int pfo_route_reply_rows(const float* Hnew_own, const float* lu_own, const int32_t* slots_own, int64_t n_rows,
+                                 int d, float* reply, void* stream) {
+    if (n_rows <= 0) return 0;
+    pfo_launch(route_reply_rows_kernel, pfo_grid(n_rows * (d + 1), 256, 8), 256, 0, (cudaStream_t)stream, Hnew_own,
+               lu_own, slots_own, n_rows, d, reply);
+    PFO_LAUNCH_CHECK();
+}
+
+PFO_API int pfo_unroute_rows(const float* back, const int32_t* slot, const int32_t* uniq, const float* node_feat,
+                             int64_t n_rows, int d, float* Hnew, float* lu_u, float* H0, void* stream) {
+    if (n_rows <= 0) return 0;
+    pfo_launch(unroute_rows_kernel, pfo_grid(n_rows * (d + 1), 256, 8), 256, 0, (cudaStream_t)stream, back, slot, uniq,
+               node_feat, n_rows, d, Hnew, lu_u, H0);
+    PFO_LAUNCH_CHECK();
+}
 
 PFO_API int pfo_route_plan(const int32_t* ids, int64_t n_rows, const int32_t* n_valid, int n_ranks, int cap,
                            int32_t* counts, int32_t* slot, int32_t* local_id, int32_t* overflow, void* stream) {

@@ -291,9 +291,7 @@ class ShardedNeighborFinder(NeighborFinder):
         nbr = torch.empty(Q, n, dtype=torch.int32, device=dev)
         eidx = torch.empty(Q, n, dtype=torch.int32, device=dev)
         dt = torch.empty(Q, n, dtype=torch.float32, device=dev)
-        ex.gather(plan, back, 0, n, nbr)
-        ex.gather(plan, back, n, n, eidx)
-        ex.gather(plan, back, 2 * n, n, dt)
+        _lib.call("pfo_unroute_neighbors", ptr(back), ptr(plan.slot), Q, n, ptr(nbr), ptr(eidx), ptr(dt))
         return nbr, eidx, None, dt
 
 
@@ -321,6 +319,8 @@ class ShardedEngine(TGNEngine):
         super().__init__(cfg, state, node_feat, edge_feat, nf)
         self.req = _Scratch(self.n_global, node_feat.device)
         self.tag = "train"
+        self.overlap_store = True       # R4 beside the backward pass (side stream)
+        self._side_pending = False
 
     def _query_ids(self, groups, B):
         """Position of each query in the query list of the un-sharded step on the global batch: group g holds
@@ -341,9 +341,9 @@ class ShardedEngine(TGNEngine):
         uniq, u_max = self._unique_nodes(id_lists, scratch=self.req, n_nodes=self.n_global)
         n_uniq = self.req.n_unique.clone()
         self.slot_map = self.req.slot_of_node
-        nf_rows = self.node_feat.index_select(0, uniq.long())
         if not c.use_memory:
-            return dict(uniq=uniq, u_max=u_max, n_uniq=n_uniq, H0=nf_rows, Hnew=None, lu_u=None)
+            return dict(uniq=uniq, u_max=u_max, n_uniq=n_uniq, H0=self.node_feat.index_select(0, uniq.long()),
+                        Hnew=None, lu_u=None)
         # R2: unique ids -> owners
         plan = ex.plan((self.tag, "R2", u_max), uniq, u_max, n_valid=n_uniq)
         req = ex.buffer(plan, 1, fill=-1)
@@ -376,20 +376,23 @@ class ShardedEngine(TGNEngine):
         slots_own = torch.empty(R, dtype=torch.int32, device=dev)
         _lib.call("pfo_map_slots", ptr(got), R, 0, ptr(st.slot_of_node), ptr(slots_own))
         reply = torch.empty(R, d + 1, device=dev)           # [updated memory row | last_update'] per received id
-        _lib.call("pfo_gather_rows", ptr(Hnew_own), d, ptr(slots_own), R, d, ptr(reply), d + 1)
-        _lib.call("pfo_gather_rows", ptr(lu_own), 1, ptr(slots_own), R, 1, reply.data_ptr() + d * F4, d + 1)
+        _lib.call("pfo_route_reply_rows", ptr(Hnew_own), ptr(lu_own), ptr(slots_own), R, d, ptr(reply))
         back = ex.all_to_all(reply)
         Hnew = torch.empty(u_max, d, device=dev)
         lu_u = torch.empty(u_max, device=dev)
-        ex.gather(plan, back, 0, d, Hnew)
-        ex.gather(plan, back, d, 1, lu_u)
+        H0 = torch.empty(u_max, d, device=dev)              # rows of the table + node features, in one pass
+        _lib.call("pfo_unroute_rows", ptr(back), ptr(plan.slot), ptr(uniq), ptr(self.node_feat), u_max, d, ptr(Hnew),
+                  ptr(lu_u), ptr(H0))
         own = dict(uniq=uo, u_max=u_own, n_uniq=n_own, HG=HG, XG=XG, valid_u=valid_u, GI=GI, GH=GH,
                    Hnew=Hnew_own, slots=slots_own, R=R, M1=None, X2=None)
-        return dict(uniq=uniq, u_max=u_max, n_uniq=n_uniq, H0=Hnew + nf_rows, Hnew=Hnew, lu_u=lu_u, plan=plan, own=own)
+        return dict(uniq=uniq, u_max=u_max, n_uniq=n_uniq, H0=H0, Hnew=Hnew, lu_u=lu_u, plan=plan, own=own)
 
     def node_table_backward(self, tab, dH0, g_cell, mlpW=None, g_mlp=None, cellW=None):
         # R3: gradient rows -> owners along R2's slots, summed over requesters, then the cell backward of the base class
         own, ex, d = tab["own"], self.ex, self.cfg.d
+        if self._side_pending:          # the message exchange of the forward pass: its collective was issued first
+            self.join_side()
+            self._side_pending = False
         send = ex.buffer(tab["plan"], d, dtype=torch.float32)
         ex.scatter(tab["plan"], dH0, send)
         got = ex.all_to_all(send)
@@ -398,11 +401,23 @@ class ShardedEngine(TGNEngine):
         TGNEngine.node_table_backward(self, own, dH_own, g_cell)
 
     def persist_and_store(self, tab, batch, emb, tw, tb):
-        # R4: rows built here, applied at the owners with last-wins by global batch position
+        """R4: message rows built here, applied at the owners with last-wins by global batch position.  In a training
+        step nothing downstream of the forward pass reads the state this writes, so the whole exchange runs on the
+        engine's side stream, beside the BPR loss and the backward pass, and is joined at the end of the backward."""
+        if self.overlap_store and batch["train"] and torch.is_grad_enabled():
+            cur = torch.cuda.current_stream(self.device)
+            s_slot, d_slot = self._slots(batch["src"]), self._slots(batch["dst"])      # cached maps, main stream
+            self.side.wait_stream(cur)
+            with torch.cuda.stream(self.side):
+                self._persist_and_store(tab, batch, emb, tw, tb, s_slot, d_slot)
+            self._side_pending = True
+        else:
+            self._persist_and_store(tab, batch, emb, tw, tb, self._slots(batch["src"]), self._slots(batch["dst"]))
+
+    def _persist_and_store(self, tab, batch, emb, tw, tb, s_slot, d_slot):
         c, st, dev, G, ex = self.cfg, self.state, self.device, self.G, self.ex
         d, F, B = c.d, c.n_edge_feat, batch["B"]
         src, dst = batch["src"], batch["dst"]
-        s_slot, d_slot = self._slots(src), self._slots(dst)
         ldr = (c.raw + 3 + 3) // 4 * 4                       # message | owner-local node | global position | fp32 time
         rows = torch.empty(2 * B, ldr, device=dev)
         o_src = o_dst = None
