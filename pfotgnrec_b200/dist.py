@@ -49,26 +49,36 @@ class Plan:
 class Exchange:
     """Fixed-capacity bucket exchange with device-side plans (see the module docstring)."""
 
-    def __init__(self, device, group=None, margin=1.3, quantum=256):
+    def __init__(self, device, group=None, margin=1.4, quantum=256):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.device = torch.device(device)
         self.margin, self.quantum = float(margin), int(quantum)
         self.overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.batch = (1, 1)         # (this rank's interactions, the largest slice of any rank) of the current batch
         self.frozen = {}            # key -> capacity fixed for the captured graphs
         self.observed = {}          # key -> largest bucket count seen in eager steps (max over ranks)
         self._pending = []          # (key, counts tensor) of the current eager step
 
     # ---- capacities
     def safe_cap(self, rows):
-        """A capacity that cannot overflow by construction at G <= 2 and is generous beyond: 2 * rows / G."""
+        """A capacity that cannot overflow by construction at G <= 2 and is generous beyond: 3 * rows / G (the eager
+        calibration steps run with it; hot stocks skew the buckets by well under 2x at Zipf(0.8))."""
         G = self.world
-        return int(rows) if G <= 2 else int(-(-2 * int(rows) // G))
+        return int(rows) if G <= 2 else min(int(rows), int(-(-3 * int(rows) // G)))
 
     def cap_for(self, key, rows):
         cap = self.frozen.get(key)
         return cap if cap is not None else max(self.safe_cap(rows), 1)
+
+    def common_rows(self, rows):
+        """The row count the RANK WITH THE LARGEST SLICE has for this exchange.  Buffer shapes must agree on every rank
+        (equal-split all-to-all), but the short last batch of an epoch gives the ranks slices that differ by one
+        interaction: every exchange carries a whole number of rows per interaction, so it is scaled to the largest
+        slice -- a pure function of the global batch, identical everywhere."""
+        b_loc, b_max = self.batch
+        return int(rows) if b_loc == b_max else -(-int(rows) // b_loc) * b_max
 
     def collect(self):
         """End of an eager step: one host read of the bucket counts, max over ranks (a collective: every rank calls it
@@ -100,11 +110,14 @@ class Exchange:
                                "re-run with a larger `exchange_margin`")
 
     # ---- plan + movement
-    def plan(self, key, ids, rows, n_valid=None):
-        """ids int32[rows] (global node ids; < 0 = no row).  Returns the plan: slot / owner-local id per row."""
+    def plan(self, tag, ids, rows, n_valid=None, cap_rows=None):
+        """ids int32[rows] (global node ids; < 0 = no row).  Returns the plan: slot / owner-local id per row.  The
+        capacity (and the calibration key) depend on `cap_rows`, the rank-independent size of this exchange."""
         G = self.world
         p = Plan()
-        p.rows, p.cap = int(rows), self.cap_for(key, rows)
+        cap_rows = self.common_rows(rows) if cap_rows is None else int(cap_rows)
+        key = tuple(tag) + (cap_rows,)
+        p.rows, p.cap = int(rows), self.cap_for(key, cap_rows)
         dev = ids.device
         p.counts = torch.empty(G, dtype=torch.int32, device=dev)
         p.slot = torch.empty(rows, dtype=torch.int32, device=dev)
@@ -274,7 +287,7 @@ class ShardedNeighborFinder(NeighborFinder):
         dev = q_nodes.device
         if n_neighbors <= 0:
             return super().sample(q_nodes, q_ts, n_neighbors)
-        plan = ex.plan((self.tag, "R1", Q), q_nodes, Q)
+        plan = ex.plan((self.tag, "R1"), q_nodes, Q)
         req = ex.buffer(plan, 4, fill=-1)
         _lib.call("pfo_pack_queries", ptr(plan.local), ptr(q_ts), ptr(q_ids), ptr(plan.slot), Q, ptr(req))
         got = ex.all_to_all(req)
@@ -345,7 +358,8 @@ class ShardedEngine(TGNEngine):
             return dict(uniq=uniq, u_max=u_max, n_uniq=n_uniq, H0=self.node_feat.index_select(0, uniq.long()),
                         Hnew=None, lu_u=None)
         # R2: unique ids -> owners
-        plan = ex.plan((self.tag, "R2", u_max), uniq, u_max, n_valid=n_uniq)
+        total = sum(int(ids.numel()) for ids in id_lists)
+        plan = ex.plan((self.tag, "R2"), uniq, u_max, n_valid=n_uniq, cap_rows=min(ex.common_rows(total), self.n_global))
         req = ex.buffer(plan, 1, fill=-1)
         ex.scatter(plan, plan.local.view(-1, 1), req)
         got = ex.all_to_all(req).view(-1)
@@ -429,7 +443,7 @@ class ShardedEngine(TGNEngine):
                   ptr(batch["ts"]), B, d, F, ptr(tab["Hnew"]), ptr(tab["lu_u"]), ptr(self.edge_feat), ptr(tw), ptr(tb),
                   ptr(o_src), ptr(o_dst), G, key_base, key_side, ptr(rows), ldr)
         nodes = torch.cat([src, dst])
-        plan = ex.plan((self.tag, "R4", 2 * B), nodes, 2 * B)
+        plan = ex.plan((self.tag, "R4"), nodes, 2 * B)
         send = ex.buffer(plan, ldr, dtype=torch.float32)
         send.view(torch.int32)[:, c.raw].fill_(-1)           # empty slots: node id -1 (only this column is read first)
         ex.scatter(plan, rows, send)
@@ -443,7 +457,7 @@ class ShardedEngine(TGNEngine):
 class ShardedTrainer(PfoTrainer):
     """PfoTrainer over G ranks with node-sharded state: global batch [s, e), rank r trains / evaluates its r-th slice."""
 
-    def __init__(self, st, tc, device, rank, world, group=None, exchange_margin=1.3, nccl_in_graph=True):
+    def __init__(self, st, tc, device, rank, world, group=None, exchange_margin=1.4, nccl_in_graph=True):
         self.rank, self.world, self.group = int(rank), int(world), group
         self.ex = Exchange(device, group=group, margin=exchange_margin)
         if tc.model == "dyrep":
@@ -589,6 +603,7 @@ class ShardedTrainer(PfoTrainer):
     def _slice(self, s, e):
         ls, le = replica_slice(s, e, self.rank, self.world)
         self.engine.key_base, self.engine.key_side = ls - s, e - s
+        self.ex.batch = (le - ls, -(-(e - s) // self.world))
         return ls, le
 
     def _run_graphed(self, sg):

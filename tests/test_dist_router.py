@@ -28,7 +28,7 @@ def _worker(rank, world, port, results):
             ids[::7] = -1                                        # rows that are not sent
             n_valid = torch.tensor([R - 3], dtype=torch.int32)   # device-side count: the tail is ignored too
             live = (ids >= 0) & (torch.arange(R) < R - 3)
-            plan = ex.plan(("t", R), ids, R, n_valid=n_valid)
+            plan = ex.plan(("t",), ids, R, n_valid=n_valid)
             assert plan.cap == ex.cap_for(("t", R), R)
             assert torch.equal(plan.slot >= 0, live)
             assert torch.equal(plan.local[live].long(), ids[live].long() // world)
@@ -65,13 +65,27 @@ def _worker(rank, world, port, results):
         ex.check_overflow()
         # a frozen capacity that is too small drops rows and raises the flag on every rank
         ex.frozen[("tiny", 64)] = 2
-        plan = ex.plan(("tiny", 64), torch.arange(64, dtype=torch.int32) * world, 64)      # all rows to rank 0
+        plan = ex.plan(("tiny",), torch.arange(64, dtype=torch.int32) * world, 64)         # all rows to rank 0
         assert int((plan.slot >= 0).sum()) == 2
         try:
             ex.check_overflow()
             raise AssertionError("overflow not reported")
         except RuntimeError:
             pass
+        # ragged slices (the short last batch of an epoch): this rank has 5 or 4 interactions x 6 rows, the buffers are
+        # sized for the largest slice on every rank, so the equal-split all-to-all still lines up
+        b_loc = 5 - rank
+        ex.batch = (b_loc, 5)
+        ids = (torch.arange(6 * b_loc, dtype=torch.int32) * 3 + rank) % N
+        plan = ex.plan(("ragged",), ids, 6 * b_loc)
+        assert plan.cap == ex.cap_for(("ragged", 30), 30)
+        req = ex.buffer(plan, 1, fill=-1)
+        ex.scatter(plan, plan.local.view(-1, 1), req)
+        got = ex.all_to_all(req).view(-1)
+        n_got = torch.tensor([float((got >= 0).sum())])
+        dist.all_reduce(n_got)
+        assert float(n_got) == 6 * 5 + 6 * 4
+        ex.collect()
         results[rank] = "ok"
     finally:
         dist.destroy_process_group()
