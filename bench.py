@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--parallelism", default="sharded", choices=["replicated", "sharded"],
                     help="N > 1: node-sharded state (owner = node mod N) with device-planned all-to-all routing "
                          "(pfotgnrec_b200/dist.py, the default), or replicated state + data-parallel interactions")
+    ap.add_argument("--sharded-1gpu", action="store_true",
+                    help="N = 1: run the node-sharded trainer on one rank (every exchange degenerates to a copy): isolates "
+                         "the cost of the routing kernels from the cost of the collectives")
     ap.add_argument("--procedural", action="store_true",
                     help="GPU-resident procedural stream (pfotgnrec_b200/synth_device.py) instead of the host-built one: the "
                          "only way to the scale configuration; runs the node-sharded trainer at any N (N = 1 included)")
@@ -415,18 +418,19 @@ def main():
     from pfotgnrec_b200 import _lib
     from pfotgnrec_b200.trainer import PfoTrainer, TrainConfig
     _lib.load()
+    one_rank = world == 1 and (a.procedural or a.sharded_1gpu)
+    if one_rank:                                     # the sharded trainer's exchange needs a process group, even of one
+        import torch.distributed as dist
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{29700 + os.getpid() % 200}", rank=0,
+                                world_size=1, device_id=dev)
     if a.procedural:
         from pfotgnrec_b200.synth_device import DeviceStream
-        if world == 1:                               # the sharded trainer's exchange needs a process group, even of one
-            import torch.distributed as dist
-            dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{29700 + os.getpid() % 200}", rank=0,
-                                    world_size=1, device_id=dev)
         st = DeviceStream(a.users, a.items, a.events, n_days=a.days, seed=0, device=dev)
     else:
         st = make_data(a)
     tc = TrainConfig(model=a.workload, bs=a.bs, gemm_mode=a.gemm, dropout=a.dropout, cuda_graph=not a.no_graph,
                      n_layers=a.layers, n_neighbors=a.neighbors)
-    if a.procedural or (world > 1 and a.parallelism == "sharded"):
+    if one_rank or (world > 1 and a.parallelism == "sharded"):
         from pfotgnrec_b200.dist import ShardedTrainer
         tr = ShardedTrainer(st, tc, dev, rank, world)
         if a.no_graph:
@@ -626,9 +630,9 @@ def main():
         ran_graph = bool(getattr(tr, "_graph_ok", lambda _b: False)(bs))
         cfg = base_config(a, world)
         cfg.update({"l2": "flushed between timed steps (256 MiB write)",
-                    "parallelism": ("1 GPU" if world == 1 and not a.procedural else
+                    "parallelism": ("1 GPU" if world == 1 and not one_rank else
                                     (f"node-sharded x{world} (owner = node mod {world}, device-planned all-to-all)"
-                                     if a.parallelism == "sharded" or a.procedural
+                                     if a.parallelism == "sharded" or one_rank
                                      else f"replicated state, data-parallel x{world}")),
                     "timing": "sum of per-step CUDA-event durations, max over ranks",
                     "gemm_mode": a.gemm, "cuda_graph": ran_graph})
@@ -647,7 +651,7 @@ def main():
                "roofline": roofline, "cpu_baseline": cpu, "eval": ev_block, "eval_users_per_sec": eval_users,
                "kernels": kernels, "rooflines": rooflines, "large_batch": large}
         print(json.dumps(out))
-    if world > 1 or a.procedural:
+    if world > 1 or one_rank:
         # the captured graphs of the sharded mode hold NCCL kernels; tearing the communicator down under them can block
         # for minutes -- everything is printed, so synchronise, meet the other ranks and leave without the teardown
         sys.stdout.flush()
