@@ -60,6 +60,9 @@ def parse():
                          "under `large_batch`: at bs 8192 every kernel runs 10-40 us and is bound by launch / pipeline-fill "
                          "latency, not by HBM; 0 disables")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu-step", action="store_true",
+                    help="for ncu --profile-from-start off: after the warm-up, bracket ONE eager (kernel by kernel) training "
+                         "step with cudaProfilerStart/Stop and exit; numbers printed under a profiler are not bench values")
     ap.add_argument("--ref-kind", default="auto", choices=["auto", "port"],
                     help="--impl reference: auto = the unmodified reference when its tree is staged, else the oracle port")
     ap.add_argument("--ref-budget", type=float, default=150.0, help="--impl reference: seconds for the timed + warm-up steps")
@@ -403,6 +406,9 @@ def main():
     a = parse()
     if a.impl == "reference":
         return run_reference(a)
+    if os.environ.get("PFO_HANG_DUMP_S"):            # debugging aid for multi-rank runs: where every thread sits, then exit
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["PFO_HANG_DUMP_S"]), exit=True)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -466,6 +472,16 @@ def main():
     for _ in range(a.warmup):
         step()
     barrier()
+    if a.ncu_step:
+        tr.tc.cuda_graph = False
+        step()                                       # one un-profiled eager step (lazy allocations of the eager path)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"ncu_step": True, "note": "one eager training step was bracketed for the profiler"}))
+        return
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()

@@ -166,12 +166,13 @@ int pfo_apply_routed_messages(const float* rows, int64_t ldr, int64_t R, int d, 
  * section 8e).  plan: slot[i] = (ids[i] mod n_ranks) * cap + arrival order inside that bucket, -1 for dropped rows
  * (ids[i] < 0, i >= *n_valid when n_valid != NULL, or bucket full -> *overflow |= 1); counts[g] = rows destined to
  * rank g; local_id[i] = ids[i] / n_ranks (may be NULL).  scatter_rows / gather_words move rows of w 32-bit words into /
- * out of their slots (gather fills rows whose slot is < 0 with `fill`).  pack / unpack_queries: the request rows of
+ * out of their slots (gather fills rows whose slot is < 0 with `fill`); n_valid (device, may be NULL) bounds the rows
+ * walked when the table is sized for the worst case.  pack / unpack_queries: the request rows of
  * the neighbour exchange, [local node id | timestamp (2 words) | query id]. */
 int pfo_route_plan(const int32_t* ids, int64_t n_rows, const int32_t* n_valid, int n_ranks, int cap,
                    int32_t* counts, int32_t* slot, int32_t* local_id, int32_t* overflow, void* stream);
-int pfo_scatter_rows(const void* src, int64_t lds, const int32_t* slot, int64_t M, int w, void* dst, int64_t ldd,
-                     void* stream);
+int pfo_scatter_rows(const void* src, int64_t lds, const int32_t* slot, int64_t M, const int32_t* n_valid, int w,
+                     void* dst, int64_t ldd, void* stream);
 int pfo_gather_words(const void* src, int64_t lds, const int32_t* slot, int64_t M, int w, void* dst, int64_t ldd,
                      uint32_t fill, void* stream);
 int pfo_pack_queries(const int32_t* local_id, const double* q_ts, const int32_t* q_ids, const int32_t* slot,
@@ -185,8 +186,8 @@ int pfo_unroute_neighbors(const int32_t* back, const int32_t* slot, int64_t n_qu
                           int32_t* eidx, float* dt, void* stream);
 int pfo_route_reply_rows(const float* Hnew_own, const float* lu_own, const int32_t* slots_own, int64_t n_rows, int d,
                          float* reply, void* stream);
-int pfo_unroute_rows(const float* back, const int32_t* slot, const int32_t* uniq, const float* node_feat,
-                     int64_t n_rows, int d, float* Hnew, float* lu_u, float* H0, void* stream);
+int pfo_unroute_rows(const float* back, const int32_t* slot, const int32_t* uniq, const int32_t* n_valid,
+                     const float* node_feat, int64_t n_rows, int d, float* Hnew, float* lu_u, float* H0, void* stream);
 
 
 /* ---- jodie time-projection embedding --- modules/embedding_module.py:57-61, model/tgn.py:260-266 */

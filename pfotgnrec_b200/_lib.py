@@ -45,13 +45,13 @@ _SIGS = {
                                           c_int, P, c_int64, P]),
     "pfo_apply_routed_messages": (c_int, [P, c_int64, c_int64, c_int, c_int, P, P, P, P, P, c_int64, P, P, P, P]),
     "pfo_route_plan": (c_int, [P, c_int64, P, c_int, c_int, P, P, P, P, P]),
-    "pfo_scatter_rows": (c_int, [P, c_int64, P, c_int64, c_int, P, c_int64, P]),
+    "pfo_scatter_rows": (c_int, [P, c_int64, P, c_int64, P, c_int, P, c_int64, P]),
     "pfo_gather_words": (c_int, [P, c_int64, P, c_int64, c_int, P, c_int64, c_uint32, P]),
     "pfo_pack_queries": (c_int, [P, P, P, P, c_int64, P, P]),
     "pfo_unpack_queries": (c_int, [P, c_int64, P, P, P, P]),
     "pfo_unroute_neighbors": (c_int, [P, P, c_int64, c_int, P, P, P, P]),
     "pfo_route_reply_rows": (c_int, [P, P, P, c_int64, c_int, P, P]),
-    "pfo_unroute_rows": (c_int, [P, P, P, P, c_int64, c_int, P, P, P, P]),
+    "pfo_unroute_rows": (c_int, [P, P, P, P, P, c_int64, c_int, P, P, P, P]),
     "pfo_time_embedding_fwd": (c_int, [P, P, c_int64, c_int64, c_int, P, P, P, c_float, c_float, c_float,
                                        c_float, P, P, P, P, P]),
     "pfo_time_embedding_bwd": (c_int, [P, c_int64, c_int, P, P, P, P, P, P, P, P, P, c_int64, P]),

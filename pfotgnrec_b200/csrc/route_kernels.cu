@@ -55,9 +55,10 @@ route_plan_kernel(const int32_t* __restrict__ ids, int64_t R, const int32_t* __r
 
 // dst[slot[m], 0:w] = src[m, 0:w] for slot[m] >= 0 (32-bit words, any payload type)
 __global__ void __launch_bounds__(256)
-scatter_rows_kernel(const uint32_t* __restrict__ src, int64_t lds, const int32_t* __restrict__ slot, int64_t M, int w,
-                    uint32_t* __restrict__ dst, int64_t ldd) {
+scatter_rows_kernel(const uint32_t* __restrict__ src, int64_t lds, const int32_t* __restrict__ slot, int64_t M,
+                    const int32_t* __restrict__ n_valid, int w, uint32_t* __restrict__ dst, int64_t ldd) {
     pfo_pdl_prologue();
+    if (n_valid && *n_valid < M) M = *n_valid;      // the tables are sized for the worst case: walk the live rows only
     const int64_t total = M * w;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t m = i / w;
@@ -154,9 +155,10 @@ route_reply_rows_kernel(const float* __restrict__ Hnew_own, const float* __restr
 // requester side of R2: rows of the unique-node table from the reply slots, and H0 = memory' + node features
 __global__ void __launch_bounds__(256)
 unroute_rows_kernel(const float* __restrict__ back, const int32_t* __restrict__ slot, const int32_t* __restrict__ uniq,
-                    const float* __restrict__ node_feat, int64_t U, int d, float* __restrict__ Hnew,
-                    float* __restrict__ lu_u, float* __restrict__ H0) {
+                    const int32_t* __restrict__ n_valid, const float* __restrict__ node_feat, int64_t U, int d,
+                    float* __restrict__ Hnew, float* __restrict__ lu_u, float* __restrict__ H0) {
     pfo_pdl_prologue();
+    if (n_valid && *n_valid < U) U = *n_valid;      // rows past the unique count are never read downstream
     const int w = d + 1;
     const int64_t total = U * w;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -191,11 +193,12 @@ PFO_API int pfo_route_reply_rows(const float* Hnew_own, const float* lu_own, con
     PFO_LAUNCH_CHECK();
 }
 
-PFO_API int pfo_unroute_rows(const float* back, const int32_t* slot, const int32_t* uniq, const float* node_feat,
-                             int64_t n_rows, int d, float* Hnew, float* lu_u, float* H0, void* stream) {
+PFO_API int pfo_unroute_rows(const float* back, const int32_t* slot, const int32_t* uniq, const int32_t* n_valid,
+                             const float* node_feat, int64_t n_rows, int d, float* Hnew, float* lu_u, float* H0,
+                             void* stream) {
     if (n_rows <= 0) return 0;
     pfo_launch(unroute_rows_kernel, pfo_grid(n_rows * (d + 1), 256, 8), 256, 0, (cudaStream_t)stream, back, slot, uniq,
-               node_feat, n_rows, d, Hnew, lu_u, H0);
+               n_valid, node_feat, n_rows, d, Hnew, lu_u, H0);
     PFO_LAUNCH_CHECK();
 }
 
@@ -211,11 +214,11 @@ PFO_API int pfo_route_plan(const int32_t* ids, int64_t n_rows, const int32_t* n_
     PFO_LAUNCH_CHECK();
 }
 
-PFO_API int pfo_scatter_rows(const void* src, int64_t lds, const int32_t* slot, int64_t M, int w, void* dst,
-                             int64_t ldd, void* stream) {
+PFO_API int pfo_scatter_rows(const void* src, int64_t lds, const int32_t* slot, int64_t M, const int32_t* n_valid,
+                             int w, void* dst, int64_t ldd, void* stream) {
     if (M <= 0 || w <= 0) return 0;
     pfo_launch(scatter_rows_kernel, pfo_grid(M * w, 256, 8), 256, 0, (cudaStream_t)stream, 
-        (const uint32_t*)src, lds, slot, M, w, (uint32_t*)dst, ldd);
+        (const uint32_t*)src, lds, slot, M, n_valid, w, (uint32_t*)dst, ldd);
     PFO_LAUNCH_CHECK();
 }
 

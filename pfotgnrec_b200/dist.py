@@ -149,12 +149,13 @@ class Exchange:
             buf.fill_(fill)
         return buf
 
-    def scatter(self, plan, rows, buf):
-        """buf[slot[i], :w] = rows[i, :w] (32-bit words of any type; rows may be a column block of a wider tensor)."""
+    def scatter(self, plan, rows, buf, n_valid=None):
+        """buf[slot[i], :w] = rows[i, :w] (32-bit words of any type; rows may be a column block of a wider tensor);
+        n_valid (device int32, optional): only the first *n_valid rows are walked."""
         w = rows.shape[1] if rows.dim() > 1 else 1
         if rows.device.type == "cuda":
-            _lib.call("pfo_scatter_rows", ptr(rows), rows.stride(0) if rows.dim() > 1 else 1, ptr(plan.slot), plan.rows, w,
-                      ptr(buf), buf.stride(0))
+            _lib.call("pfo_scatter_rows", ptr(rows), rows.stride(0) if rows.dim() > 1 else 1, ptr(plan.slot), plan.rows,
+                      ptr(n_valid), w, ptr(buf), buf.stride(0))
         else:
             ok = plan.slot >= 0
             buf.view(buf.shape[0], -1)[plan.slot[ok].long(), :w] = rows.view(plan.rows, -1)[ok]
@@ -361,7 +362,7 @@ class ShardedEngine(TGNEngine):
         total = sum(int(ids.numel()) for ids in id_lists)
         plan = ex.plan((self.tag, "R2"), uniq, u_max, n_valid=n_uniq, cap_rows=min(ex.common_rows(total), self.n_global))
         req = ex.buffer(plan, 1, fill=-1)
-        ex.scatter(plan, plan.local.view(-1, 1), req)
+        ex.scatter(plan, plan.local.view(-1, 1), req, n_valid=n_uniq)
         got = ex.all_to_all(req).view(-1)
         R = got.shape[0]
         _lib.call("pfo_mark_nodes", ptr(got), R, 0, ptr(st.bitmap))
@@ -395,11 +396,11 @@ class ShardedEngine(TGNEngine):
         Hnew = torch.empty(u_max, d, device=dev)
         lu_u = torch.empty(u_max, device=dev)
         H0 = torch.empty(u_max, d, device=dev)              # rows of the table + node features, in one pass
-        _lib.call("pfo_unroute_rows", ptr(back), ptr(plan.slot), ptr(uniq), ptr(self.node_feat), u_max, d, ptr(Hnew),
-                  ptr(lu_u), ptr(H0))
+        _lib.call("pfo_unroute_rows", ptr(back), ptr(plan.slot), ptr(uniq), ptr(n_uniq), ptr(self.node_feat), u_max, d,
+                  ptr(Hnew), ptr(lu_u), ptr(H0))
         own = dict(uniq=uo, u_max=u_own, n_uniq=n_own, HG=HG, XG=XG, valid_u=valid_u, GI=GI, GH=GH,
                    Hnew=Hnew_own, slots=slots_own, R=R, M1=None, X2=None)
-        return dict(uniq=uniq, u_max=u_max, n_uniq=n_uniq, H0=H0, Hnew=Hnew, lu_u=lu_u, plan=plan, own=own)
+        return dict(uniq=uniq, u_max=u_max, n_uniq=n_uniq, H0=H0, Hnew=Hnew, lu_u=lu_u, plan=plan, own=own, n_req=n_uniq)
 
     def node_table_backward(self, tab, dH0, g_cell, mlpW=None, g_mlp=None, cellW=None):
         # R3: gradient rows -> owners along R2's slots, summed over requesters, then the cell backward of the base class
@@ -408,7 +409,7 @@ class ShardedEngine(TGNEngine):
             self.join_side()
             self._side_pending = False
         send = ex.buffer(tab["plan"], d, dtype=torch.float32)
-        ex.scatter(tab["plan"], dH0, send)
+        ex.scatter(tab["plan"], dH0, send, n_valid=tab["n_req"])
         got = ex.all_to_all(send)
         dH_own = torch.zeros(own["u_max"], d, device=self.device)
         _lib.call("pfo_scatter_add_rows", ptr(got), d, ptr(own["slots"]), own["R"], d, ptr(dH_own), d)
