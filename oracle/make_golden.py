@@ -257,6 +257,37 @@ def golden_eval_metrics():
     print("eval_metrics.npz", len(out), "batches", len(negs))
 
 
+def golden_uniform_neighbors(get_neighbor_finder):
+    """The reference's NeighborFinder in UNIFORM mode (utils/utils.py:193-204): per query the support its own
+    `find_before` returns (everything strictly before the cut time) and one draw of `get_temporal_neighbor` (numpy's
+    global MT19937: the values are not the contract, their structure is -- n picks WITH replacement out of the support,
+    re-sorted by fp32 time, all-zero rows when the support is empty)."""
+    from pfotgnrec_b200.synth import make_stream
+    st = make_stream(n_users=60, n_items=12, n_events=700, n_days=15, seed=51, ts_mode="small", with_prices=False)
+    nf = get_neighbor_finder(_data(st), uniform=True, max_node_idx=st.n_nodes - 1)
+    rng = np.random.default_rng(52)
+    Q, n = 200, 8
+    nodes = rng.integers(0, st.n_nodes, size=Q)
+    ts = st.timestamps[rng.integers(0, st.n_events, size=Q)] + rng.integers(-1, 2, size=Q)
+    ts[:3] = [-1.0, st.timestamps[-1] + 5, st.timestamps[0]]
+    smax = max(len(nf.find_before(int(v), float(t))[0]) for v, t in zip(nodes, ts))
+    sup_e = np.zeros((Q, smax), dtype=np.int64)
+    sup_n = np.zeros((Q, smax), dtype=np.int64)
+    sup_len = np.zeros(Q, dtype=np.int64)
+    for q, (v, t) in enumerate(zip(nodes, ts)):
+        nb, ei, _ = nf.find_before(int(v), float(t))
+        sup_len[q] = len(nb)
+        sup_n[q, :len(nb)], sup_e[q, :len(ei)] = nb, ei
+    np.random.seed(7)
+    nb, ei, et = nf.get_temporal_neighbor(nodes, ts, n_neighbors=n)
+    out = dict(nodes=nodes, ts=ts, n=n, sup_len=sup_len, sup_nbr=sup_n, sup_eidx=sup_e, ref_nbr=nb, ref_eidx=ei, ref_etime=et,
+               n_nodes=st.n_nodes)
+    for k in ("sources", "destinations", "edge_idxs", "timestamps"):
+        out["st_" + k] = getattr(st, k)
+    np.savez_compressed(os.path.join(OUT, "neighbors_uniform.npz"), **out)
+    print("neighbors_uniform.npz", len(out))
+
+
 def golden_sampler_support(RandEdgeSampler):
     """The reference's RandEdgeSampler (utils/utils.py:65-114) on a synthetic batch: its OWN fields after construction
     (`dst_unique`, `portfolio_list`) give the support of every interaction, available_i = setdiff1d(dst_unique,
@@ -392,7 +423,7 @@ def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--device", default="cpu", help="cuda: run the reference's own torch-CUDA path (side-by-side test)")
     ap.add_argument("--out", default=None, help="output directory (default tests/golden; required with --device cuda)")
-    ap.add_argument("--only", default=None, help="one of the non-model goldens: sampler_support | state_dict")
+    ap.add_argument("--only", default=None, help="one of the non-model goldens: sampler_support | state_dict | uniform_neighbors")
     ap.add_argument("--tags", default=None, help="comma-separated model cases (default: all, plus the non-model goldens)")
     a = ap.parse_args(argv)
     if a.device != "cpu" and a.out is None:
@@ -402,7 +433,8 @@ def main(argv=None):
     TGN, get_neighbor_finder, RandEdgeSampler = _import_reference()
     cases = model_cases()
     if a.only:
-        {"sampler_support": lambda: golden_sampler_support(RandEdgeSampler),
+        {"uniform_neighbors": lambda: golden_uniform_neighbors(get_neighbor_finder),
+         "sampler_support": lambda: golden_sampler_support(RandEdgeSampler),
          "state_dict": lambda: golden_state_dict(TGN, get_neighbor_finder)}[a.only]()
         return
     for tag in (a.tags.split(",") if a.tags else cases):
@@ -413,6 +445,7 @@ def main(argv=None):
         golden_eval_metrics()
         golden_sampler_support(RandEdgeSampler)
         golden_state_dict(TGN, get_neighbor_finder)
+        golden_uniform_neighbors(get_neighbor_finder)
 
 
 if __name__ == "__main__":

@@ -116,12 +116,16 @@ class Memory(nn.Module):
         return out
 
     def store_raw_messages(self, nodes, node_id_to_messages):
+        """modules/memory.py:35-37 on the dense table: the LAST message appended for a node is the one the `last`
+        aggregator would pick, so it becomes the node's pending row (one stacked copy, no per-row kernel launches)."""
         st = self._state
-        for node in nodes:
-            for msg, ts in node_id_to_messages[node]:
-                st.pend_msg[node, :st.cfg.raw] = msg
-                st.pend_ts[node] = ts
-                st.pend_valid[node] = 1
+        keep = [(int(node), node_id_to_messages[node][-1]) for node in nodes if len(node_id_to_messages[node]) > 0]
+        if not keep:
+            return
+        idx = torch.as_tensor([k for k, _ in keep], dtype=torch.long, device=st.pend_msg.device)
+        st.pend_msg[idx, :st.cfg.raw] = torch.stack([m[0] for _, m in keep]).to(st.pend_msg)
+        st.pend_ts[idx] = torch.stack([torch.as_tensor(m[1]).reshape(()) for _, m in keep]).to(st.pend_ts)
+        st.pend_valid[idx] = 1
 
     def get_memory(self, node_idxs):
         return self.memory[node_idxs, :]

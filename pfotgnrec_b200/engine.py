@@ -213,8 +213,12 @@ class TGNEngine:
 
     def __init__(self, cfg: ModelConfig, state: Optional[TGNState], node_feat: torch.Tensor,
                  edge_feat: torch.Tensor, neighbor_finder):
-        assert cfg.d % 32 == 0 and cfg.d <= 128, "kernels are specialised for d in {32,64,96,128}"
-        assert cfg.E % cfg.n_heads == 0
+        # the limits the kernels are specialised for, named here: past this point a violation would only surface as
+        # cudaErrorInvalidValue from an entry point
+        if cfg.d % 32 != 0 or not 32 <= cfg.d <= 128:
+            raise ValueError(f"memory / feature dimension d={cfg.d}: the kernels are specialised for d in {{32, 64, 96, 128}}")
+        if cfg.embedding == "graph_attention" and (cfg.n_heads < 1 or cfg.n_heads > 4 or cfg.E % cfg.n_heads != 0):
+            raise ValueError(f"n_heads={cfg.n_heads}: the attention kernels take 1..4 heads that divide 2 * d = {cfg.E}")
         self.cfg, self.state = cfg, state
         self.node_feat = node_feat.contiguous()
         self.edge_feat = edge_feat.contiguous()
@@ -367,6 +371,8 @@ class TGNEngine:
         without exchanging rows."""
         groups = [src, dst] + list(extra_groups)
         B = src.shape[0]
+        if self.cfg.graph and int(n_neighbors) > 32:
+            raise ValueError(f"n_neighbors={n_neighbors}: the neighbour kernels hold one sampled slot per lane (at most 32)")
         q_nodes = torch.cat(groups)
         q_ts = torch.cat([ts if g.shape[0] == B else ts.repeat_interleave(g.shape[0] // B) for g in groups])
         flat = self._pack(params)

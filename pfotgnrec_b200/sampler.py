@@ -59,6 +59,10 @@ class MVSelector:
         self.n_users = int(n_users)
         self.gamma, self.lam = float(gamma), float(lam)
         self.K, self.n_pos, self.n_neg, self.seed = int(n_candidates), int(n_pos), int(n_neg), int(seed)
+        if not 1 <= self.K <= 31:
+            raise ValueError(f"num_negatives={self.K}: the MV kernel ranks the true item + candidates in one warp (K <= 31)")
+        if self.n_pos + self.n_neg > self.K + 1:
+            raise ValueError("p_pos_num + p_neg_num exceeds the number of ranked items (num_negatives + 1)")
 
     def select(self, event_ids, day_idx, dst_items, port_ptr, port_items, cand=None, return_scores=False):
         """dst_items: item ids (U+1..U+I) of the true destinations; portfolio CSR over 0-based stocks.

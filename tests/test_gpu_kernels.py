@@ -110,6 +110,23 @@ def test_neighbors_cooperative_search_every_width(lpq):
                 assert np.array_equal(x, y), (lpq, Q, n)
 
 
+def test_uniform_neighbors_structure_vs_reference():
+    """K1's uniform mode against the supports / structure of the reference's own uniform NeighborFinder
+    (tests/golden/neighbors_uniform.npz, utils/utils.py:193-204) -- the checker the oracle passes on CPU."""
+    from test_oracle_golden import check_uniform_neighbors
+    from pfotgnrec_b200.graph import TemporalCSR, NeighborFinder
+    z = load_golden("neighbors_uniform.npz")
+    csr = TemporalCSR(z["st_sources"], z["st_destinations"], z["st_edge_idxs"], z["st_timestamps"],
+                      n_nodes=int(z["n_nodes"]), device=DEV)
+    nf = NeighborFinder(csr, uniform=True, seed=3)
+
+    def sample(nodes, ts, n, call):
+        nf.call_id = call
+        return nf.get_temporal_neighbor(nodes, ts, n)
+
+    check_uniform_neighbors(z, sample)
+
+
 def test_time_encode_cos_paths():
     """TimeEncode (model/time_encoding.py:17-25) through pfo_time_encode: the fp64 quadrant reduction the kernels use
     stays within 2e-7 of the fp64 libm value from day-scale arguments up to ~1e10 rad (NBG-format time deltas); the fp32

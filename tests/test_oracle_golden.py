@@ -172,3 +172,40 @@ def test_candidate_sampler_support_and_replace_rule_vs_reference():
     z = load_golden("sampler_support.npz")
     check_sampler_support(z, lambda ev, items, pptr, held, size, seed:
                           sampling.sample_candidates(ev, items, pptr, held, size, seed))
+
+
+def check_uniform_neighbors(z, sample_fn):
+    """Structure of a uniform-mode neighbour sampler against the reference's (utils/utils.py:193-204), on the supports
+    the reference's own `find_before` returned: every pick is an (neighbour, edge) pair of the support, n picks with
+    replacement (so a support smaller than n repeats), ascending fp32 times, all-zero rows for an empty support -- the
+    reference's own draw has the same structure; uniformity over the support is checked in the aggregate."""
+    n, Q = int(z["n"]), z["nodes"].shape[0]
+    ts_of_edge = np.zeros(int(z["st_edge_idxs"].max()) + 1, dtype=np.float32)
+    ts_of_edge[z["st_edge_idxs"]] = z["st_timestamps"].astype(np.float32)
+    hist, expect = np.zeros(8), np.zeros(8)
+    for call in range(30):
+        nb, ei, et = sample_fn(z["nodes"], z["ts"], n, call)
+        for q in range(Q):
+            L = int(z["sup_len"][q])
+            if L == 0:
+                assert not nb[q].any() and not ei[q].any() and not et[q].any()
+                continue
+            pairs = set(zip(z["sup_nbr"][q, :L].tolist(), z["sup_eidx"][q, :L].tolist()))
+            assert all((a, b) in pairs for a, b in zip(nb[q].tolist(), ei[q].tolist())), (call, q)
+            assert np.all(np.diff(et[q]) >= 0) and np.array_equal(et[q], ts_of_edge[ei[q]])
+            if call == 0:
+                rp = set(zip(z["ref_nbr"][q].tolist(), z["ref_eidx"][q].tolist()))
+                assert rp <= pairs and np.all(np.diff(z["ref_etime"][q]) >= 0)
+            if L >= 8:           # position of each pick inside the support, folded to 8 bins
+                order = {e: k for k, e in enumerate(z["sup_eidx"][q, :L].tolist())}
+                for e in ei[q].tolist():
+                    hist[order[e] * 8 // L] += 1
+                expect += np.bincount(np.arange(L) * 8 // L, minlength=8) * (n / L)
+    assert hist.sum() > 5000 and np.abs(hist - expect).max() < 5 * np.sqrt(expect.max()), (hist, expect)
+
+
+def test_uniform_neighbors_structure_vs_reference():
+    z = load_golden("neighbors_uniform.npz")
+    adj = AdjacencyOracle(z["st_sources"], z["st_destinations"], z["st_edge_idxs"], z["st_timestamps"],
+                          n_nodes=int(z["n_nodes"]), uniform=True)
+    check_uniform_neighbors(z, lambda nodes, ts, n, call: adj.get_temporal_neighbor(nodes, ts, n, call_id=call, seed=3))
