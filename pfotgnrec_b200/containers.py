@@ -25,6 +25,26 @@ class _Container(nn.Module):
         raise NotImplementedError(f"{type(self).__name__} is {_FUSED}")
 
 
+class _Exact:
+    gemm_mode = "simt"          # standalone sub-module calls use the fp32 FFMA kernel
+
+
+@torch.no_grad()
+def _dense(x, linear, relu=False):
+    """y = act(x W^T + b) through pfo_linear_f32 (inference only: the trained path is the fused step)."""
+    from . import _lib
+    from .engine import _linear
+    if x.device.type != "cuda":
+        raise _lib.PfoError("sub-module forwards run in libpfo_b200.so on a CUDA device: there is no CPU fallback")
+    x = x.contiguous().float()
+    M, K = x.shape
+    W, b = linear.weight.detach().contiguous(), linear.bias.detach().contiguous()
+    N = W.shape[0]
+    y = torch.empty(M, N, device=x.device)
+    _linear(_Exact, _lib.ptr(x), K, None, _lib.ptr(W), K, 0, _lib.ptr(b), _lib.ptr(y), N, M, N, K, act=1 if relu else 0)
+    return y
+
+
 # ----------------------------------------------------------------------------- model/time_encoding.py:5-25
 class TimeEncode(_Container):
     """cos(t * w + b), w_k = 10^(-9k/(d-1)), b = 0, both learnable."""
@@ -60,6 +80,10 @@ class MergeLayer(_Container):
         self.fc1, self.fc2, self.act = nn.Linear(dim1 + dim2, dim3), nn.Linear(dim3, dim4), nn.ReLU()
         for lin in (self.fc1, self.fc2):
             nn.init.xavier_normal_(lin.weight)
+
+    def forward(self, x1, x2):
+        """utils/utils.py:14-17 on its own (inference only): fc2(relu(fc1([x1 | x2])))."""
+        return _dense(_dense(torch.cat([x1, x2], dim=1), self.fc1, relu=True), self.fc2)
 
 
 # ----------------------------------------------------------------------------- model/temporal_attention.py:7-32
@@ -173,7 +197,9 @@ class MLPMessageFunction(MessageFunction):
                                                nn.Linear(half, message_dimension))
 
     def compute_message(self, raw_messages):
-        raise NotImplementedError(f"the message MLP is {_FUSED}")
+        """modules/message_function.py:23-26 on its own (inference only; the trained path runs it inside the lazy
+        memory update)."""
+        return _dense(_dense(raw_messages, self.mlp[0], relu=True), self.mlp[2])
 
 
 def get_message_function(module_type, raw_message_dimension, message_dimension):

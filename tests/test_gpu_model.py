@@ -263,3 +263,21 @@ def test_backup_restore_memory_round_trip(overlay):
     # the state after restore + batch 2 equals the reference's golden after batch 2 (eval mode == dropout 0 here)
     assert rel_err(tgn.memory.memory.cpu().numpy(), z["b2_memory"]) < TOL
     assert np.array_equal(tgn.memory.state.pend_valid.cpu().numpy().astype(bool), z["b2_pend_valid"])
+
+
+def test_standalone_sub_module_forwards():
+    """Reference-derived scripts may call a sub-module directly: MergeLayer (utils/utils.py:14-17), the MLP message
+    function (modules/message_function.py:23-26) and TimeEncode (model/time_encoding.py:17-25) evaluate on their own
+    through the library, against the same arithmetic in fp64 torch."""
+    from pfotgnrec_b200.containers import MergeLayer, MLPMessageFunction
+    torch.manual_seed(0)
+    ml = MergeLayer(128, 64, 64, 64).cuda()
+    x1, x2 = torch.randn(300, 128, device="cuda"), torch.randn(300, 64, device="cuda")
+    ref = torch.relu(torch.cat([x1, x2], 1).double() @ ml.fc1.weight.double().T + ml.fc1.bias.double())
+    ref = ref @ ml.fc2.weight.double().T + ml.fc2.bias.double()
+    assert rel_err(ml(x1, x2).cpu().numpy(), ref.cpu().numpy()) < TOL
+    mf = MLPMessageFunction(193, 100).cuda()
+    raw = torch.randn(257, 193, device="cuda")
+    ref = torch.relu(raw.double() @ mf.mlp[0].weight.double().T + mf.mlp[0].bias.double())
+    ref = ref @ mf.mlp[2].weight.double().T + mf.mlp[2].bias.double()
+    assert rel_err(mf.compute_message(raw).cpu().numpy(), ref.cpu().numpy()) < TOL
