@@ -652,6 +652,9 @@ def main():
                                      else f"replicated state, data-parallel x{world}")),
                     "timing": "sum of per-step CUDA-event durations, max over ranks",
                     "gemm_mode": a.gemm, "cuda_graph": ran_graph})
+        if hasattr(tr, "ex"):
+            cfg["exchange_transport"] = ("peer-memory stores + flag barrier (CUDA IPC arenas over NVLink)"
+                                         if tr.ex.transport == "peer" else "NCCL all_to_all_single")
         ev_block = None
         if eval_users is not None:
             ev_block = {"metric": "eval_users_per_sec", "value": eval_users, "unit": "users/s", "n_items": a.items,

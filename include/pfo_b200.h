@@ -294,6 +294,24 @@ int pfo_sample_candidates(const int64_t* event_ids, const int64_t* port_ptr, con
                           const int32_t* items_sorted, int n_items_universe, int B, int size,
                           uint64_t seed, int32_t* out, void* stream);
 
+/* ---- peer-memory transport of the node-sharded exchanges (no counterpart in the reference; csrc/peer_kernels.cu).
+ * alloc: cudaMalloc'ed, zeroed arena + its 64-byte CUDA IPC handle; open / close: map / unmap a peer's arena; the first
+ * pfo_peer_header_bytes() of every arena hold the barrier flags and epochs.  push: block g (block_words 32-bit words) of
+ * the local send buffer -> arena of rank g at recv_off_bytes + rank * block_words * 4 (`bases`: HOST array of the
+ * n_ranks arena addresses in this process).  barrier `id`: signal every peer, wait for every peer (error_word |= 2 after
+ * timeout_s instead of hanging). */
+int pfo_peer_alloc(int64_t bytes, void** ptr, unsigned char* handle64);
+int pfo_peer_open(const unsigned char* handle64, void** ptr);
+int pfo_peer_close(void* ptr);
+int pfo_peer_free(void* ptr);
+int pfo_peer_max_ranks(void);
+int pfo_peer_max_barriers(void);
+int64_t pfo_peer_header_bytes(void);
+int pfo_peer_push(const void* send, const uint64_t* bases, int64_t recv_off_bytes, int n_ranks, int rank,
+                  int64_t block_words, void* stream);
+int pfo_peer_barrier(const uint64_t* bases, int n_ranks, int rank, int id, uint32_t* error_word, double timeout_s,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

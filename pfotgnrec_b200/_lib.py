@@ -52,6 +52,15 @@ _SIGS = {
     "pfo_unroute_neighbors": (c_int, [P, P, c_int64, c_int, P, P, P, P]),
     "pfo_route_reply_rows": (c_int, [P, P, P, c_int64, c_int, P, P]),
     "pfo_unroute_rows": (c_int, [P, P, P, P, P, c_int64, c_int, P, P, P, P]),
+    "pfo_peer_alloc": (c_int, [c_int64, P, P]),
+    "pfo_peer_open": (c_int, [P, P]),
+    "pfo_peer_close": (c_int, [P]),
+    "pfo_peer_free": (c_int, [P]),
+    "pfo_peer_max_ranks": (c_int, []),
+    "pfo_peer_max_barriers": (c_int, []),
+    "pfo_peer_header_bytes": (c_int64, []),
+    "pfo_peer_push": (c_int, [P, P, c_int64, c_int, c_int, c_int64, P]),
+    "pfo_peer_barrier": (c_int, [P, c_int, c_int, c_int, P, c_double, P]),
     "pfo_time_embedding_fwd": (c_int, [P, P, c_int64, c_int64, c_int, P, P, P, c_float, c_float, c_float,
                                        c_float, P, P, P, P, P]),
     "pfo_time_embedding_bwd": (c_int, [P, c_int64, c_int, P, P, P, P, P, P, P, P, P, c_int64, P]),
@@ -82,7 +91,8 @@ LAUNCHES = 0            # kernels launched through this binding (bench.py report
 _LAUNCHES_PER_CALL = {"pfo_compact_nodes": 3, "pfo_fold_attention_fwd": 2, "pfo_fold_attention_bwd": 2,
                       "pfo_fold_attention_workspace_doubles": 0, "pfo_wgrad_f32": 2, "pfo_wgrad_tf32": 2,
                       "pfo_wgrad_tf32_workspace_floats": 0, "pfo_time_embedding_bwd": 2,
-                      "pfo_attn_nbr_bwd": 2, "pfo_bpr": 2, "pfo_eval_metrics": 2, "pfo_apply_messages": 2, "pfo_apply_routed_messages": 2, "pfo_abi_version": 0,
+                      "pfo_attn_nbr_bwd": 2, "pfo_bpr": 2, "pfo_eval_metrics": 2, "pfo_apply_messages": 2, "pfo_apply_routed_messages": 2, "pfo_abi_version": 0, "pfo_peer_alloc": 0, "pfo_peer_open": 0, "pfo_peer_close": 0, "pfo_peer_free": 0,
+                      "pfo_peer_max_ranks": 0, "pfo_peer_max_barriers": 0, "pfo_peer_header_bytes": 0,
                       "pfo_compact_workspace_ints": 0, "pfo_wgrad_workspace_floats": 0,
                       "pfo_attn_nbr_bwd_workspace_floats": 0}
 

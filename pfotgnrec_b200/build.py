@@ -17,6 +17,7 @@ SOURCES = {
     "wgrad_tma.cu": [],
     "memory_kernels.cu": [],
     "route_kernels.cu": [],
+    "peer_kernels.cu": [],
     "attention_kernels.cu": [],
     "fold_kernels.cu": [],
     "mv_kernels.cu": ["-fmad=false"],

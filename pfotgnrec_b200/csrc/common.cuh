@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 #include "../../include/pfo_b200.h"
 
 #define PFO_API extern "C" __attribute__((visibility("default")))

@@ -43,13 +43,89 @@ F4 = 4
 
 
 class Plan:
-    __slots__ = ("slot", "local", "cap", "rows", "counts")
+    __slots__ = ("slot", "local", "cap", "rows", "counts", "calibrated")
+
+
+class _RawCuda:
+    """A raw device allocation as an object torch.as_tensor can wrap without copying (__cuda_array_interface__)."""
+
+    def __init__(self, address, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(address), False),
+                                         "version": 2}
+
+
+class PeerArena:
+    """One cudaMalloc'ed arena per rank, mapped into every other rank of the node through CUDA IPC
+    (csrc/peer_kernels.cu).  Receive buffers are bump-allocated from it: the ranks run the same sequence of exchanges
+    with the same (calibrated) shapes, so a buffer has the same offset in every arena and a peer can store straight
+    into it.  `begin_step` rewinds the allocator and places the step-start barrier."""
+
+    def __init__(self, device, group, nbytes):
+        import ctypes
+        self.device, self.group = torch.device(device), group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > int(_lib.query("pfo_peer_max_ranks")):
+            raise _lib.PfoError("peer transport: too many ranks for one node's arena table")
+        self.nbytes = int(nbytes)
+        lib = _lib.load()
+        ptr_, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+        rc = lib.pfo_peer_alloc(self.nbytes, ctypes.byref(ptr_), handle)
+        if rc != 0:
+            raise _lib.PfoError(f"pfo_peer_alloc failed with cudaError {rc}")
+        self.local = int(ptr_.value)
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, bytes(handle), group=group)
+        bases = []
+        for g in range(self.world):
+            if g == self.rank:
+                bases.append(self.local)
+                continue
+            p, h = ctypes.c_void_p(), (ctypes.c_ubyte * 64).from_buffer_copy(handles[g])
+            rc = lib.pfo_peer_open(h, ctypes.byref(p))
+            if rc != 0:
+                raise _lib.PfoError(f"pfo_peer_open(rank {g}) failed with cudaError {rc}")
+            bases.append(int(p.value))
+        self.bases = (ctypes.c_uint64 * self.world)(*bases)
+        self.bytes_view = torch.as_tensor(_RawCuda(self.local, self.nbytes), device=self.device)
+        self.header = (int(_lib.query("pfo_peer_header_bytes")) + 255) // 256 * 256
+        self.max_barriers = int(_lib.query("pfo_peer_max_barriers"))
+        self.error = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.offset, self.next_id = self.header, 1
+        self.timeout_s = 20.0
+
+    def begin_step(self):
+        """Rewind the allocator; barrier 0 keeps a fast rank out of buffers a slow rank still reads from the last step."""
+        self.offset, self.next_id = self.header, 1
+        _lib.call("pfo_peer_barrier", self.bases, self.world, self.rank, 0, ptr(self.error), self.timeout_s)
+
+    def room(self, nbytes):
+        return self.offset + (int(nbytes) + 255) // 256 * 256 <= self.nbytes and self.next_id < self.max_barriers
+
+    def alloc(self, shape, dtype):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nbytes = n * torch.empty(0, dtype=dtype).element_size()
+        off = self.offset
+        self.offset += (nbytes + 255) // 256 * 256
+        return off, self.bytes_view[off:off + nbytes].view(dtype).view(*shape)
+
+    def all_to_all(self, buf):
+        """Equal-split all-to-all of `buf` ([G * rows, w] of 32-bit elements): push + barrier."""
+        G = self.world
+        off, out = self.alloc(tuple(buf.shape), buf.dtype)
+        block_words = buf.numel() // G
+        _lib.call("pfo_peer_push", ptr(buf), self.bases, off, G, self.rank, block_words)
+        _lib.call("pfo_peer_barrier", self.bases, G, self.rank, self.next_id, ptr(self.error), self.timeout_s)
+        self.next_id += 1
+        return out
 
 
 class Exchange:
     """Fixed-capacity bucket exchange with device-side plans (see the module docstring)."""
 
-    def __init__(self, device, group=None, margin=1.4, quantum=256):
+    def __init__(self, device, group=None, margin=1.4, quantum=256, transport="peer", arena_bytes=2 << 30):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -60,6 +136,23 @@ class Exchange:
         self.frozen = {}            # key -> capacity fixed for the captured graphs
         self.observed = {}          # key -> largest bucket count seen in eager steps (max over ranks)
         self._pending = []          # (key, counts tensor) of the current eager step
+        # transport of the all-to-alls: "peer" = direct stores into the other GPUs' arenas + flag barrier for every
+        # exchange whose capacity is calibrated (the captured steps); NCCL all_to_all_single otherwise / as fallback
+        self.arena = None
+        self.transport = "nccl"
+        if transport == "peer" and self.device.type == "cuda":
+            ok = torch.ones(1, dtype=torch.int32, device=self.device)
+            try:
+                self.arena = PeerArena(self.device, group, arena_bytes)
+            except Exception as exc:                         # no IPC / no peer access on this box: NCCL carries everything
+                ok.zero_()
+                self._peer_error = str(exc)
+            if self.world > 1:
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 1:
+                self.transport = "peer"
+            else:
+                self.arena = None
 
     # ---- capacities
     def safe_cap(self, rows):
@@ -100,12 +193,22 @@ class Exchange:
                 q = self.quantum
                 self.frozen[k] = max(q, int(-(-int(v * self.margin + 1) // q) * q))
 
+    def begin_step(self):
+        """Start of a (train or evaluation) step, inside the captured region."""
+        if self.arena is not None:
+            self.arena.begin_step()
+
     def check_overflow(self):
         """Host read of the overflow flag (one sync): raised when a frozen capacity turned out too small."""
         flag = self.overflow.clone()
+        if self.arena is not None:
+            flag |= self.arena.error
         if self.world > 1:
             dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
-        if int(flag.item()) != 0:
+        v = int(flag.item())
+        if v & 2:
+            raise RuntimeError("peer-memory barrier timed out: a rank did not reach an exchange (results are invalid)")
+        if v & 1:
             raise RuntimeError("node-sharded exchange overflowed a calibrated bucket capacity: rows were dropped; "
                                "re-run with a larger `exchange_margin`")
 
@@ -118,6 +221,7 @@ class Exchange:
         cap_rows = self.common_rows(rows) if cap_rows is None else int(cap_rows)
         key = tuple(tag) + (cap_rows,)
         p.rows, p.cap = int(rows), self.cap_for(key, cap_rows)
+        p.calibrated = key in self.frozen
         dev = ids.device
         p.counts = torch.empty(G, dtype=torch.int32, device=dev)
         p.slot = torch.empty(rows, dtype=torch.int32, device=dev)
@@ -173,7 +277,12 @@ class Exchange:
             o[ok] = buf[plan.slot[ok].long(), col0:col0 + w]
         return out
 
-    def all_to_all(self, buf):
+    def all_to_all(self, buf, plan=None):
+        """Equal-split all-to-all of a slot buffer.  Calibrated exchanges (fixed, tight capacities: every captured step)
+        go through the peer arena when it has room; the oversized buffers of the calibration steps go through NCCL."""
+        if (self.arena is not None and plan is not None and plan.calibrated and buf.is_contiguous()
+                and buf.element_size() == 4 and self.arena.room(buf.numel() * 4)):
+            return self.arena.all_to_all(buf)
         out = torch.empty_like(buf)
         if self.world > 1:
             dist.all_to_all_single(out, buf, group=self.group)
@@ -291,7 +400,7 @@ class ShardedNeighborFinder(NeighborFinder):
         plan = ex.plan((self.tag, "R1"), q_nodes, Q)
         req = ex.buffer(plan, 4, fill=-1)
         _lib.call("pfo_pack_queries", ptr(plan.local), ptr(q_ts), ptr(q_ids), ptr(plan.slot), Q, ptr(req))
-        got = ex.all_to_all(req)
+        got = ex.all_to_all(req, plan)
         R = got.shape[0]
         qn = torch.empty(R, dtype=torch.int32, device=dev)
         qt = torch.empty(R, dtype=torch.float64, device=dev)
@@ -301,7 +410,7 @@ class ShardedNeighborFinder(NeighborFinder):
         rf = reply.view(torch.float32)
         NeighborFinder.sample(self, qn, qt, n, out=(reply[:, :n], reply[:, n:2 * n], None, rf[:, 2 * n:]),
                               q_ids=qi if self.uniform else None, ld_out=3 * n)
-        back = ex.all_to_all(reply)
+        back = ex.all_to_all(reply, plan)
         nbr = torch.empty(Q, n, dtype=torch.int32, device=dev)
         eidx = torch.empty(Q, n, dtype=torch.int32, device=dev)
         dt = torch.empty(Q, n, dtype=torch.float32, device=dev)
@@ -363,7 +472,7 @@ class ShardedEngine(TGNEngine):
         plan = ex.plan((self.tag, "R2"), uniq, u_max, n_valid=n_uniq, cap_rows=min(ex.common_rows(total), self.n_global))
         req = ex.buffer(plan, 1, fill=-1)
         ex.scatter(plan, plan.local.view(-1, 1), req, n_valid=n_uniq)
-        got = ex.all_to_all(req).view(-1)
+        got = ex.all_to_all(req, plan).view(-1)
         R = got.shape[0]
         _lib.call("pfo_mark_nodes", ptr(got), R, 0, ptr(st.bitmap))
         u_own = min(max(R, 1), st.n_nodes)
@@ -392,7 +501,7 @@ class ShardedEngine(TGNEngine):
         _lib.call("pfo_map_slots", ptr(got), R, 0, ptr(st.slot_of_node), ptr(slots_own))
         reply = torch.empty(R, d + 1, device=dev)           # [updated memory row | last_update'] per received id
         _lib.call("pfo_route_reply_rows", ptr(Hnew_own), ptr(lu_own), ptr(slots_own), R, d, ptr(reply))
-        back = ex.all_to_all(reply)
+        back = ex.all_to_all(reply, plan)
         Hnew = torch.empty(u_max, d, device=dev)
         lu_u = torch.empty(u_max, device=dev)
         H0 = torch.empty(u_max, d, device=dev)              # rows of the table + node features, in one pass
@@ -410,7 +519,7 @@ class ShardedEngine(TGNEngine):
             self._side_pending = False
         send = ex.buffer(tab["plan"], d, dtype=torch.float32)
         ex.scatter(tab["plan"], dH0, send, n_valid=tab["n_req"])
-        got = ex.all_to_all(send)
+        got = ex.all_to_all(send, tab["plan"])
         dH_own = torch.zeros(own["u_max"], d, device=self.device)
         _lib.call("pfo_scatter_add_rows", ptr(got), d, ptr(own["slots"]), own["R"], d, ptr(dH_own), d)
         TGNEngine.node_table_backward(self, own, dH_own, g_cell)
@@ -448,7 +557,7 @@ class ShardedEngine(TGNEngine):
         send = ex.buffer(plan, ldr, dtype=torch.float32)
         send.view(torch.int32)[:, c.raw].fill_(-1)           # empty slots: node id -1 (only this column is read first)
         ex.scatter(plan, rows, send)
-        got = ex.all_to_all(send)
+        got = ex.all_to_all(send, plan)
         own = tab["own"]
         _lib.call("pfo_apply_routed_messages", ptr(got), ldr, got.shape[0], d, c.raw, ptr(st.slot_of_node),
                   ptr(own["Hnew"]), ptr(st.memory), ptr(st.last_update), ptr(st.pend_msg), c.rawp, ptr(st.pend_ts),
@@ -458,9 +567,12 @@ class ShardedEngine(TGNEngine):
 class ShardedTrainer(PfoTrainer):
     """PfoTrainer over G ranks with node-sharded state: global batch [s, e), rank r trains / evaluates its r-th slice."""
 
-    def __init__(self, st, tc, device, rank, world, group=None, exchange_margin=1.4, nccl_in_graph=True):
+    def __init__(self, st, tc, device, rank, world, group=None, exchange_margin=1.4, nccl_in_graph=True, transport=None):
+        import os
         self.rank, self.world, self.group = int(rank), int(world), group
-        self.ex = Exchange(device, group=group, margin=exchange_margin)
+        _lib.use_device(device)
+        self.ex = Exchange(device, group=group, margin=exchange_margin,
+                           transport=transport or os.environ.get("PFO_TRANSPORT", "peer"))
         if tc.model == "dyrep":
             raise NotImplementedError("dyrep messages carry embeddings: routed, but not verified in this mode")
         super().__init__(st, tc, device)
@@ -601,6 +713,14 @@ class ShardedTrainer(PfoTrainer):
             raise ValueError(f"fit: batch size {bs} is smaller than the number of ranks ({self.world})")
 
     # ---- steps
+    def _fwd_bwd(self, b):
+        self.ex.begin_step()                                  # inside the captured region: step-start barrier of the arena
+        return super()._fwd_bwd(b)
+
+    def _eval_body(self, b, N, with_state):
+        self.ex.begin_step()
+        return super()._eval_body(b, N, with_state)
+
     def _slice(self, s, e):
         ls, le = replica_slice(s, e, self.rank, self.world)
         self.engine.key_base, self.engine.key_side = ls - s, e - s

@@ -92,6 +92,7 @@ def main():
         t[name] = (time.perf_counter() - t0) / 20 * 1e3
     if rank == 0:
         caps = {str(k): v for k, v in sh.ex.frozen.items()}
+        print(f"transport {sh.ex.transport}; ", end="")
         print(f"sharded x{world} == single GPU ({model}, graph={graph}): {len(spans)} train steps (last ragged) + 4 eval "
               f"steps, loss {l_sh:.6f} vs {l_1:.6f}, worst grad rel.err {worst:.2e}, memory rel.err {merr:.2e}, "
               f"eval score rel.err {everr:.2e}; {t['sharded']:.3f} ms/step sharded vs {t['single']:.3f} ms single "

@@ -28,6 +28,10 @@ from pfotgnrec_b200.dist import ShardedTrainer
 sh = ShardedTrainer(st, TrainConfig(model="ours", bs=96, dropout=0.1, cuda_graph=False), "cuda:0", 0, 1)
 out["sharded_1rank"] = [float(sh.train_step(1500 + 96 * i, 1596 + 96 * i).item()) for i in range(2)]
 sh.eval_step(3000, 3032)
+sh.ex.freeze()          # calibrated capacities: the next steps go through the peer-memory transport (push + barrier)
+out["sharded_1rank_peer"] = [float(sh.train_step(1700 + 96 * i, 1796 + 96 * i).item()) for i in range(2)]
+sh.eval_step(3032, 3064)
+out["transport"] = sh.ex.transport
 torch.cuda.synchronize()
 sh.ex.check_overflow()
 print("sanitize_step:", out, flush=True)
