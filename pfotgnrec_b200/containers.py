@@ -38,11 +38,15 @@ def _dense(x, linear, relu=False):
         raise _lib.PfoError("sub-module forwards run in libpfo_b200.so on a CUDA device: there is no CPU fallback")
     x = x.contiguous().float()
     M, K = x.shape
+    lda = (K + 3) // 4 * 4                   # operand rows are read as 16-byte vectors: pad the row stride like the engine does
+    if lda != K:
+        x = torch.nn.functional.pad(x, (0, lda - K))
     W, b = linear.weight.detach().contiguous(), linear.bias.detach().contiguous()
     N = W.shape[0]
-    y = torch.empty(M, N, device=x.device)
-    _linear(_Exact, _lib.ptr(x), K, None, _lib.ptr(W), K, 0, _lib.ptr(b), _lib.ptr(y), N, M, N, K, act=1 if relu else 0)
-    return y
+    ldc = (N + 3) // 4 * 4
+    y = torch.empty(M, ldc, device=x.device)
+    _linear(_Exact, _lib.ptr(x), lda, None, _lib.ptr(W), K, 0, _lib.ptr(b), _lib.ptr(y), ldc, M, N, K, act=1 if relu else 0)
+    return y[:, :N] if ldc != N else y
 
 
 # ----------------------------------------------------------------------------- model/time_encoding.py:5-25
