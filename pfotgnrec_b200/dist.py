@@ -528,15 +528,17 @@ class ShardedEngine(TGNEngine):
         """R4: message rows built here, applied at the owners with last-wins by global batch position.  In a training
         step nothing downstream of the forward pass reads the state this writes, so the whole exchange runs on the
         engine's side stream, beside the BPR loss and the backward pass, and is joined at the end of the backward."""
+        B = batch["B"]
+        qs = self.qslots_last                               # the query list starts with [src | dst]: their table rows
         if self.overlap_store and batch["train"] and torch.is_grad_enabled():
             cur = torch.cuda.current_stream(self.device)
-            s_slot, d_slot = self._slots(batch["src"]), self._slots(batch["dst"])      # cached maps, main stream
+            s_slot, d_slot = qs[:B], qs[B:2 * B]
             self.side.wait_stream(cur)
             with torch.cuda.stream(self.side):
                 self._persist_and_store(tab, batch, emb, tw, tb, s_slot, d_slot)
             self._side_pending = True
         else:
-            self._persist_and_store(tab, batch, emb, tw, tb, self._slots(batch["src"]), self._slots(batch["dst"]))
+            self._persist_and_store(tab, batch, emb, tw, tb, qs[:B], qs[B:2 * B])
 
     def _persist_and_store(self, tab, batch, emb, tw, tb, s_slot, d_slot):
         c, st, dev, G, ex = self.cfg, self.state, self.device, self.G, self.ex
