@@ -95,20 +95,30 @@ int pfo_linear_bf16(const float* A, int64_t lda, const int32_t* a_idx, const flo
 
 /* ---- memory updater gates on the unique touched nodes --- modules/memory_updater.py:35-53
  * (get_updated_memory) restricted to nodes that are read.  cell: 0 GRU, 1 RNN, 2 no memory.
- * gather_state snapshots the rows of the unique nodes (HG memory, XG pending message, valid_u,
- * lu_u = last_update') before persist / store overwrite them.  GI/GH are the input / hidden
- * pre-activations ([U,3d] or [U,d]).  Hnew = updated memory rows, H0 = Hnew + node_feat rows
- * (modules/embedding_module.py:93-98). */
+ * gather_state snapshots the rows of the unique nodes (HG memory, XG pending message with row stride ldx >= rawp,
+ * valid_u, lu_u = last_update') before persist / store overwrite them; Hcat (optional, row stride ldh) receives a
+ * second copy of the memory row -- the tail of the operand row [cell input | memory] of the merged contraction.
+ * merged == 0: GI / GH are the input / hidden pre-activations ([U,3d] or [U,d], two GEMMs).  merged != 0: GI is G4 =
+ * [r | z | n_i | n_h] ([U,4d], GRU; r and z already summed) or the single pre-activation ([U,d], RNN) of ONE GEMM over
+ * [cell input | memory] with the block weight pfo_pack_cell builds from weight_ih / weight_hh / bias_ih / bias_hh
+ * (kx = input width, kxp = its padded width in the operand row); dGI is then [U,4d] / [U,d], GH / dGH are unused, and
+ * pfo_unpack_cell_grads adds the block weight's gradient back into the four tensors.  Hnew = updated memory rows,
+ * H0 = Hnew + node_feat rows (modules/embedding_module.py:93-98). */
 int pfo_gather_state(const int32_t* uniq, const int32_t* n_uniq, int64_t u_max, int d, int raw,
                      const float* memory, const float* pend_msg, int64_t rawp, const uint8_t* pend_valid,
                      const float* pend_ts, const float* last_update,
-                     float* HG, float* XG, uint8_t* valid_u, float* lu_u, void* stream);
-int pfo_cell_forward(const int32_t* uniq, const int32_t* n_uniq, int64_t u_max, int d, int cell,
+                     float* HG, float* XG, int64_t ldx, float* Hcat, int64_t ldh, uint8_t* valid_u, float* lu_u,
+                     void* stream);
+int pfo_cell_forward(const int32_t* uniq, const int32_t* n_uniq, int64_t u_max, int d, int cell, int merged,
                      const float* GI, const float* GH, int64_t ldg, const float* HG,
                      const uint8_t* valid_u, const float* node_feat, float* Hnew, float* H0, void* stream);
-int pfo_cell_backward(const int32_t* uniq, const int32_t* n_uniq, int64_t u_max, int d, int cell,
+int pfo_cell_backward(const int32_t* uniq, const int32_t* n_uniq, int64_t u_max, int d, int cell, int merged,
                       const float* GI, const float* GH, int64_t ldg, const float* HG,
                       const uint8_t* valid_u, const float* dH, float* dGI, float* dGH, void* stream);
+int pfo_pack_cell(const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh, int d, int kx, int kxp,
+                  int cell, float* Wc, float* bc, void* stream);
+int pfo_unpack_cell_grads(const float* gWc, const float* gbc, int d, int kx, int kxp, int cell, float* gW_ih,
+                          float* gW_hh, float* gb_ih, float* gb_hh, void* stream);
 
 /* ---- persist + message store --- model/tgn.py:185-206 (update_memory for positives, clear,
  * get_raw_messages x2, store_raw_messages), model/tgn.py:357-378, modules/memory.py:35-37,

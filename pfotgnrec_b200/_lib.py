@@ -32,9 +32,11 @@ _SIGS = {
     "pfo_wgrad_tf32": (c_int, [P, c_int64, P, c_int64, P, c_int64, P, c_int, c_int, P, c_int64, P, c_int, P, c_int, P]),
     "pfo_wgrad_workspace_floats": (c_int64, [c_int64, c_int, c_int, c_int]),
     "pfo_wgrad_f32": (c_int, [P, c_int64, P, c_int64, P, c_int64, P, c_int, c_int, P, c_int64, P, c_int, P, P]),
-    "pfo_gather_state": (c_int, [P, P, c_int64, c_int, c_int, P, P, c_int64, P, P, P, P, P, P, P, P]),
-    "pfo_cell_forward": (c_int, [P, P, c_int64, c_int, c_int, P, P, c_int64, P, P, P, P, P, P]),
-    "pfo_cell_backward": (c_int, [P, P, c_int64, c_int, c_int, P, P, c_int64, P, P, P, P, P, P]),
+    "pfo_gather_state": (c_int, [P, P, c_int64, c_int, c_int, P, P, c_int64, P, P, P, P, P, c_int64, P, c_int64, P, P, P]),
+    "pfo_cell_forward": (c_int, [P, P, c_int64, c_int, c_int, c_int, P, P, c_int64, P, P, P, P, P, P]),
+    "pfo_cell_backward": (c_int, [P, P, c_int64, c_int, c_int, c_int, P, P, c_int64, P, P, P, P, P, P]),
+    "pfo_pack_cell": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P, P, P]),
+    "pfo_unpack_cell_grads": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, P, P, P]),
     "pfo_persist_rank": (c_int, [P, P, c_int, c_int, P, P, P, P, P, P, P, P]),
     "pfo_store_messages": (c_int, [P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, c_int64, P, P, P, P]),
     "pfo_store_messages_mean": (c_int, [P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, P, c_int64,

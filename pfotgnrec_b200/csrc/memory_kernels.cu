@@ -19,7 +19,7 @@ namespace {
 //       2 = no memory (H0 = node features only).
 __global__ void __launch_bounds__(256)
 cell_forward_kernel(const int32_t* __restrict__ uniq, const int32_t* __restrict__ n_uniq, int64_t u_max, int d,
-                    int cell, const float* __restrict__ GI, const float* __restrict__ GH, int64_t ldg,
+                    int cell, int merged, const float* __restrict__ GI, const float* __restrict__ GH, int64_t ldg,
                     const float* __restrict__ HG, const uint8_t* __restrict__ valid_u,
                     const float* __restrict__ node_feat, float* __restrict__ Hnew, float* __restrict__ H0) {
     pfo_pdl_prologue();
@@ -35,15 +35,28 @@ cell_forward_kernel(const int32_t* __restrict__ uniq, const int32_t* __restrict_
         float hn = h;
         if (valid_u[u]) {
             const float* gi = GI + u * ldg;
-            const float* gh = GH + u * ldg;
-            if (cell == 0) {
-                // torch GRUCell: r,z = sigmoid(i + h); n = tanh(i_n + r * h_n); h' = n + z * (h - n)
-                const float r = sigmoidf_(gi[c] + gh[c]);
-                const float z = sigmoidf_(gi[d + c] + gh[d + c]);
-                const float n = tanhf(gi[2 * d + c] + r * gh[2 * d + c]);
-                hn = n + z * (h - n);
+            if (merged) {
+                // one contraction over [message | memory]: G4 = [r | z | n_i | n_h] with the r, z sums already formed
+                // (GRU, 4d wide) or the single pre-activation (RNN, d wide)
+                if (cell == 0) {
+                    const float r = sigmoidf_(gi[c]);
+                    const float z = sigmoidf_(gi[d + c]);
+                    const float n = tanhf(gi[2 * d + c] + r * gi[3 * d + c]);
+                    hn = n + z * (h - n);
+                } else {
+                    hn = tanhf(gi[c]);
+                }
             } else {
-                hn = tanhf(gi[c] + gh[c]);
+                const float* gh = GH + u * ldg;
+                if (cell == 0) {
+                    // torch GRUCell: r,z = sigmoid(i + h); n = tanh(i_n + r * h_n); h' = n + z * (h - n)
+                    const float r = sigmoidf_(gi[c] + gh[c]);
+                    const float z = sigmoidf_(gi[d + c] + gh[d + c]);
+                    const float n = tanhf(gi[2 * d + c] + r * gh[2 * d + c]);
+                    hn = n + z * (h - n);
+                } else {
+                    hn = tanhf(gi[c] + gh[c]);
+                }
             }
         }
         Hnew[i] = hn;
@@ -54,7 +67,7 @@ cell_forward_kernel(const int32_t* __restrict__ uniq, const int32_t* __restrict_
 // backward of the cell w.r.t. its pre-activations (memory and messages are detached inputs)
 __global__ void __launch_bounds__(256)
 cell_backward_kernel(const int32_t* __restrict__ uniq, const int32_t* __restrict__ n_uniq, int64_t u_max, int d,
-                     int cell, const float* __restrict__ GI, const float* __restrict__ GH, int64_t ldg,
+                     int cell, int merged, const float* __restrict__ GI, const float* __restrict__ GH, int64_t ldg,
                      const float* __restrict__ HG, const uint8_t* __restrict__ valid_u,
                      const float* __restrict__ dH, float* __restrict__ dGI, float* __restrict__ dGH) {
     pfo_pdl_prologue();
@@ -64,9 +77,36 @@ cell_backward_kernel(const int32_t* __restrict__ uniq, const int32_t* __restrict
         const int64_t u = i / d;
         const int c = (int)(i - u * d);
         float* dgi = dGI + u * ldg;
-        float* dgh = dGH + u * ldg;
         const bool live = valid_u[u] != 0;
         const float g = dH[i];
+        if (merged) {
+            if (cell == 0) {
+                float dr = 0.f, dz = 0.f, dn = 0.f, dhn = 0.f;
+                if (live) {
+                    const float* gi = GI + u * ldg;
+                    const float h = HG[i];
+                    const float r = sigmoidf_(gi[c]);
+                    const float z = sigmoidf_(gi[d + c]);
+                    const float hn_ = gi[3 * d + c];
+                    const float n = tanhf(gi[2 * d + c] + r * hn_);
+                    const float dn_ = g * (1.0f - z);
+                    dn = dn_ * (1.0f - n * n);
+                    dz = g * (h - n) * z * (1.0f - z);
+                    dr = dn * hn_ * r * (1.0f - r);
+                    dhn = dn * r;
+                }
+                dgi[c] = dr; dgi[d + c] = dz; dgi[2 * d + c] = dn; dgi[3 * d + c] = dhn;
+            } else {
+                float dp = 0.f;
+                if (live) {
+                    const float y = tanhf(GI[u * ldg + c]);
+                    dp = g * (1.0f - y * y);
+                }
+                dgi[c] = dp;
+            }
+            continue;
+        }
+        float* dgh = dGH + u * ldg;
         if (cell == 0) {
             float dr = 0.f, dz = 0.f, dn = 0.f, dhn = 0.f;
             if (live) {
@@ -103,7 +143,8 @@ gather_state_kernel(const int32_t* __restrict__ uniq, const int32_t* __restrict_
                     const float* __restrict__ memory, const float* __restrict__ pend_msg, int64_t rawp,
                     const uint8_t* __restrict__ pend_valid, const float* __restrict__ pend_ts,
                     const float* __restrict__ last_update,
-                    float* __restrict__ HG, float* __restrict__ XG, uint8_t* __restrict__ valid_u, float* __restrict__ lu_u) {
+                    float* __restrict__ HG, float* __restrict__ XG, int64_t ldx, float* __restrict__ Hcat, int64_t ldh,
+                    uint8_t* __restrict__ valid_u, float* __restrict__ lu_u) {
     pfo_pdl_prologue();
     int64_t U = *n_uniq; if (U > u_max) U = u_max;
     const int lane = threadIdx.x & 31;
@@ -113,11 +154,15 @@ gather_state_kernel(const int32_t* __restrict__ uniq, const int32_t* __restrict_
         const int node = uniq[u];
         const bool v = pend_valid[node] != 0;
         const float* m = memory + (int64_t)node * d;
-        for (int c = lane; c < d; c += 32) HG[u * d + c] = m[c];
+        for (int c = lane; c < d; c += 32) {
+            const float mc = m[c];
+            HG[u * d + c] = mc;
+            if (Hcat) Hcat[u * ldh + c] = mc;     // second copy behind the cell input: operand row [input | memory]
+        }
         if (XG) {
             const float* x = pend_msg + (int64_t)node * rawp;
-            // XG rows keep the 16-byte-aligned stride of the table (rawp) so that TMA can stream them
-            for (int c = lane; c < rawp; c += 32) XG[u * rawp + c] = (v && c < raw) ? x[c] : 0.0f;
+            // XG rows keep a 16-byte-aligned stride (ldx >= rawp) so that TMA can stream them
+            for (int c = lane; c < rawp; c += 32) XG[u * ldx + c] = (v && c < raw) ? x[c] : 0.0f;
         }
         if (lane == 0) {
             valid_u[u] = v ? 1 : 0;
@@ -489,32 +534,114 @@ store_messages_mean_kernel(const int32_t* __restrict__ src, const int32_t* __res
 
 }  // namespace
 
-PFO_API int pfo_cell_forward(const int32_t* uniq, const int32_t* n_uniq, int64_t u_max, int d, int cell,
+PFO_API int pfo_cell_forward(const int32_t* uniq, const int32_t* n_uniq, int64_t u_max, int d, int cell, int merged,
                              const float* GI, const float* GH, int64_t ldg, const float* HG,
                              const uint8_t* valid_u, const float* node_feat, float* Hnew, float* H0,
                              void* stream) {
     if (u_max <= 0) return 0;
     pfo_launch(cell_forward_kernel, pfo_grid(u_max * d, 256, 8), 256, 0, (cudaStream_t)stream, 
-        uniq, n_uniq, u_max, d, cell, GI, GH, ldg, HG, valid_u, node_feat, Hnew, H0);
+        uniq, n_uniq, u_max, d, cell, merged, GI, GH, ldg, HG, valid_u, node_feat, Hnew, H0);
     PFO_LAUNCH_CHECK();
 }
 
-PFO_API int pfo_cell_backward(const int32_t* uniq, const int32_t* n_uniq, int64_t u_max, int d, int cell,
+PFO_API int pfo_cell_backward(const int32_t* uniq, const int32_t* n_uniq, int64_t u_max, int d, int cell, int merged,
                               const float* GI, const float* GH, int64_t ldg, const float* HG,
                               const uint8_t* valid_u, const float* dH, float* dGI, float* dGH, void* stream) {
     if (u_max <= 0) return 0;
     pfo_launch(cell_backward_kernel, pfo_grid(u_max * d, 256, 8), 256, 0, (cudaStream_t)stream, 
-        uniq, n_uniq, u_max, d, cell, GI, GH, ldg, HG, valid_u, dH, dGI, dGH);
+        uniq, n_uniq, u_max, d, cell, merged, GI, GH, ldg, HG, valid_u, dH, dGI, dGH);
     PFO_LAUNCH_CHECK();
 }
 
 PFO_API int pfo_gather_state(const int32_t* uniq, const int32_t* n_uniq, int64_t u_max, int d, int raw,
                              const float* memory, const float* pend_msg, int64_t rawp, const uint8_t* pend_valid,
                              const float* pend_ts, const float* last_update,
-                             float* HG, float* XG, uint8_t* valid_u, float* lu_u, void* stream) {
+                             float* HG, float* XG, int64_t ldx, float* Hcat, int64_t ldh, uint8_t* valid_u, float* lu_u,
+                             void* stream) {
     if (u_max <= 0) return 0;
+    if (XG != nullptr && ldx < rawp) return (int)cudaErrorInvalidValue;
     pfo_launch(gather_state_kernel, pfo_grid(u_max * 32, 256, 8), 256, 0, (cudaStream_t)stream, 
-        uniq, n_uniq, u_max, d, raw, memory, pend_msg, rawp, pend_valid, pend_ts, last_update, HG, XG, valid_u, lu_u);
+        uniq, n_uniq, u_max, d, raw, memory, pend_msg, rawp, pend_valid, pend_ts, last_update, HG, XG, ldx, Hcat, ldh,
+        valid_u, lu_u);
+    PFO_LAUNCH_CHECK();
+}
+
+// ---- one contraction for the memory updater.  torch's GRUCell / RNNCell (modules/memory_updater.py:60,68) apply
+// W_ih [g*d, kx] to the message and W_hh [g*d, d] to the memory in two GEMMs; over the concatenated operand
+// [message (kxp columns, zero padded) | memory (d)] they are ONE GEMM with the block weight
+//   GRU  rows [r | z] = [W_i{r,z} | W_h{r,z}] (the sums r, z need),  n_i = [W_in | 0],  n_h = [0 | W_hn]   -> 4d x (kxp + d)
+//   RNN  rows         = [W_ih | W_hh]                                                                    ->  d x (kxp + d)
+// which reads the operand once and saves a launch each way.  pack builds the block weight / bias from the reference's
+// four tensors, unpack is its adjoint (accumulating into their gradients).
+static __global__ void __launch_bounds__(256)
+pack_cell_kernel(const float* __restrict__ W_ih, const float* __restrict__ W_hh, const float* __restrict__ b_ih,
+                 const float* __restrict__ b_hh, int d, int kx, int kxp, int cell, float* __restrict__ Wc,
+                 float* __restrict__ bc) {
+    pfo_pdl_prologue();
+    const int K = kxp + d, rows = cell == 0 ? 4 * d : d;
+    const int64_t total = (int64_t)rows * K;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total + rows; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i >= total) {                                   // bias
+            const int r = (int)(i - total);
+            float v;
+            if (cell != 0 || r < 2 * d) v = b_ih[r] + b_hh[r];
+            else if (r < 3 * d) v = b_ih[r];
+            else v = b_hh[r - d];
+            bc[r] = v;
+            continue;
+        }
+        const int r = (int)(i / K), k = (int)(i - (int64_t)r * K);
+        float v = 0.0f;
+        const bool msg = k < kxp;
+        if (cell != 0 || r < 2 * d) v = msg ? (k < kx ? W_ih[(int64_t)r * kx + k] : 0.0f) : W_hh[(int64_t)r * d + (k - kxp)];
+        else if (r < 3 * d) v = msg && k < kx ? W_ih[(int64_t)r * kx + k] : 0.0f;
+        else v = msg ? 0.0f : W_hh[(int64_t)(r - d) * d + (k - kxp)];
+        Wc[i] = v;
+    }
+}
+
+static __global__ void __launch_bounds__(256)
+unpack_cell_grads_kernel(const float* __restrict__ gWc, const float* __restrict__ gbc, int d, int kx, int kxp, int cell,
+                         float* __restrict__ gW_ih, float* __restrict__ gW_hh, float* __restrict__ gb_ih,
+                         float* __restrict__ gb_hh) {
+    pfo_pdl_prologue();
+    const int K = kxp + d, g = cell == 0 ? 3 : 1;
+    const int64_t n_ih = (int64_t)g * d * kx, n_hh = (int64_t)g * d * d;
+    const int64_t total = n_ih + n_hh + 2 * (int64_t)g * d;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < n_ih) {                                     // W_ih[r, k]: block row r of the message columns
+            const int r = (int)(i / kx), k = (int)(i - (int64_t)r * kx);
+            gW_ih[i] += gWc[(int64_t)r * K + k];
+        } else if (i < n_ih + n_hh) {                       // W_hh[r, k]: the n rows live one block further down
+            const int64_t j = i - n_ih;
+            const int r = (int)(j / d), k = (int)(j - (int64_t)r * d);
+            const int rc = (cell == 0 && r >= 2 * d) ? r + d : r;
+            gW_hh[j] += gWc[(int64_t)rc * K + kxp + k];
+        } else {
+            const int64_t j = i - n_ih - n_hh;
+            const bool hh = j >= (int64_t)g * d;
+            const int r = (int)(hh ? j - (int64_t)g * d : j);
+            const int rc = (cell == 0 && r >= 2 * d && hh) ? r + d : r;
+            (hh ? gb_hh : gb_ih)[r] += gbc[rc];
+        }
+    }
+}
+
+PFO_API int pfo_pack_cell(const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh, int d, int kx,
+                          int kxp, int cell, float* Wc, float* bc, void* stream) {
+    if (d <= 0 || kx <= 0 || kxp < kx || (cell != 0 && cell != 1)) return (int)cudaErrorInvalidValue;
+    const int64_t total = (int64_t)(cell == 0 ? 4 * d : d) * (kxp + d + 1);
+    pfo_launch(pack_cell_kernel, pfo_grid(total, 256, 2), 256, 0, (cudaStream_t)stream, W_ih, W_hh, b_ih, b_hh, d, kx,
+               kxp, cell, Wc, bc);
+    PFO_LAUNCH_CHECK();
+}
+
+PFO_API int pfo_unpack_cell_grads(const float* gWc, const float* gbc, int d, int kx, int kxp, int cell, float* gW_ih,
+                                  float* gW_hh, float* gb_ih, float* gb_hh, void* stream) {
+    if (d <= 0 || kx <= 0 || kxp < kx || (cell != 0 && cell != 1)) return (int)cudaErrorInvalidValue;
+    const int64_t total = (int64_t)(cell == 0 ? 3 : 1) * d * (kx + d + 2);
+    pfo_launch(unpack_cell_grads_kernel, pfo_grid(total, 256, 2), 256, 0, (cudaStream_t)stream, gWc, gbc, d, kx, kxp,
+               cell, gW_ih, gW_hh, gb_ih, gb_hh);
     PFO_LAUNCH_CHECK();
 }
 

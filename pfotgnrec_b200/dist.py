@@ -480,23 +480,10 @@ class ShardedEngine(TGNEngine):
         _lib.call("pfo_compact_nodes", ptr(st.bitmap), st.n_nodes, ptr(st.compact_ws), ptr(uo),
                   ptr(st.slot_of_node), ptr(st.n_unique))
         n_own = st.n_unique.clone()
-        Gd = c.gates * d
-        HG = torch.empty(u_own, d, device=dev)
-        XG = torch.empty(u_own, c.rawp, device=dev)
-        valid_u = torch.empty(u_own, dtype=torch.uint8, device=dev)
-        lu_own = torch.zeros(u_own, device=dev)
-        _lib.call("pfo_gather_state", ptr(uo), ptr(n_own), u_own, d, c.raw, ptr(st.memory), ptr(st.pend_msg),
-                  c.rawp, ptr(st.pend_valid), ptr(st.pend_ts), ptr(st.last_update),
-                  ptr(HG), ptr(XG), ptr(valid_u), ptr(lu_own))
-        W_ih, W_hh, b_ih, b_hh = cellW
-        GI = torch.empty(u_own, Gd, device=dev)
-        GH = torch.empty(u_own, Gd, device=dev)
-        _linear(c, ptr(XG), c.rawp, None, ptr(W_ih), c.raw, 0, ptr(b_ih), ptr(GI), Gd, u_own, Gd, c.raw, m_dev=ptr(n_own))
-        _linear(c, ptr(HG), d, None, ptr(W_hh), d, 0, ptr(b_hh), ptr(GH), Gd, u_own, Gd, d, m_dev=ptr(n_own))
-        Hnew_own = torch.zeros(u_own, d, device=dev)
-        scratch = torch.empty(u_own, d, device=dev)         # H0 = Hnew + node features is formed on the requester
-        _lib.call("pfo_cell_forward", ptr(uo), ptr(n_own), u_own, d, c.cell, ptr(GI), ptr(GH), Gd, ptr(HG),
-                  ptr(valid_u), ptr(self.node_feat), ptr(Hnew_own), ptr(scratch))
+        # the memory updater on the owned rows (H0 = memory' + node features is formed on the requester: the owner's
+        # ids are local indices, its H0 output is scratch)
+        own = self._cell_table(uo, n_own, u_own, cellW)
+        Hnew_own, lu_own = own["Hnew"], own["lu_u"]
         slots_own = torch.empty(R, dtype=torch.int32, device=dev)
         _lib.call("pfo_map_slots", ptr(got), R, 0, ptr(st.slot_of_node), ptr(slots_own))
         reply = torch.empty(R, d + 1, device=dev)           # [updated memory row | last_update'] per received id
@@ -507,8 +494,7 @@ class ShardedEngine(TGNEngine):
         H0 = torch.empty(u_max, d, device=dev)              # rows of the table + node features, in one pass
         _lib.call("pfo_unroute_rows", ptr(back), ptr(plan.slot), ptr(uniq), ptr(n_uniq), ptr(self.node_feat), u_max, d,
                   ptr(Hnew), ptr(lu_u), ptr(H0))
-        own = dict(uniq=uo, u_max=u_own, n_uniq=n_own, HG=HG, XG=XG, valid_u=valid_u, GI=GI, GH=GH,
-                   Hnew=Hnew_own, slots=slots_own, R=R, M1=None, X2=None)
+        own.update(slots=slots_own, R=R)
         return dict(uniq=uniq, u_max=u_max, n_uniq=n_uniq, H0=H0, Hnew=Hnew, lu_u=lu_u, plan=plan, own=own, n_req=n_uniq)
 
     def node_table_backward(self, tab, dH0, g_cell, mlpW=None, g_mlp=None, cellW=None):

@@ -40,6 +40,7 @@ class ModelConfig:
     shift: tuple = (0.0, 1.0, 0.0, 1.0)  # mean/std time shift src, dst
     dropout: float = 0.0
     gemm_mode: str = "fp32"     # "fp32" (3xTF32 tcgen05, 1e-5) | "tf32" (tcgen05, 2e-2) | "bf16" | "simt" (FFMA)
+    cell_gemm: str = "merged"   # memory updater: "merged" = one contraction over [message | memory]; "split" = two
 
     @property
     def E(self):                # attention embed dim = d + time dim
@@ -444,43 +445,77 @@ class TGNEngine:
         """Unique touched nodes of the batch and their feature rows: Hnew = lazily updated memory
         (GRU/RNN applied to the pending message, through the MLP message function when configured:
         tgn.py:342-354 aggregate -> compute_message -> updater), H0 = Hnew + node features, lu_u = last_update'."""
+        uniq, u_max = self._unique_nodes(id_lists)
+        n_uniq = self.state.n_unique.clone()
+        self.slot_map = self.state.slot_of_node
+        return self._cell_table(uniq, n_uniq, u_max, cellW, mlpW)
+
+    def _cell_table(self, uniq, n_uniq, u_max, cellW, mlpW=None):
+        """The memory updater on the rows `uniq` of this engine's state (modules/memory_updater.py:35-53).
+        cfg.cell_gemm == "merged": ONE contraction over the operand row [cell input | memory] with the block weight of
+        pfo_pack_cell (the operand is read once, one GEMM launch instead of two each way); "split": torch's two GEMMs."""
         c, st, dev = self.cfg, self.state, self.device
         d = c.d
-        uniq, u_max = self._unique_nodes(id_lists)
-        n_uniq = st.n_unique.clone()
-        self.slot_map = st.slot_of_node
         G = c.gates * d
         H0 = torch.empty(u_max, d, device=dev)
-        Hnew = HG = XG = valid_u = lu_u = GI = GH = M1 = X2 = None
-        if c.use_memory:
-            HG = torch.empty(u_max, d, device=dev)
-            XG = torch.empty(u_max, c.rawp, device=dev)
-            valid_u = torch.empty(u_max, dtype=torch.uint8, device=dev)
-            lu_u = torch.empty(u_max, device=dev)
-            _lib.call("pfo_gather_state", ptr(uniq), ptr(n_uniq), u_max, d, c.raw, ptr(st.memory), ptr(st.pend_msg),
-                      c.rawp, ptr(st.pend_valid), ptr(st.pend_ts), ptr(st.last_update),
-                      ptr(HG), ptr(XG), ptr(valid_u), ptr(lu_u))
-            W_ih, W_hh, b_ih, b_hh = cellW
-            X, ldx, kx = XG, c.rawp, c.raw
-            if c.message_fn == "mlp":          # Linear(raw, raw // 2) -> ReLU -> Linear(raw // 2, msg_dim)
-                W1, b1, W2, b2 = mlpW
-                hid, md = c.mlp_hidden, c.msg_dim
-                ld1, ld2 = (hid + 3) // 4 * 4, (md + 3) // 4 * 4
-                M1 = torch.empty(u_max, ld1, device=dev)
-                X2 = torch.empty(u_max, ld2, device=dev)
-                _linear(c, ptr(XG), c.rawp, None, ptr(W1), c.raw, 0, ptr(b1), ptr(M1), ld1, u_max, hid, c.raw,
-                        m_dev=ptr(n_uniq), act=1)
-                _linear(c, ptr(M1), ld1, None, ptr(W2), hid, 0, ptr(b2), ptr(X2), ld2, u_max, md, hid, m_dev=ptr(n_uniq))
-                X, ldx, kx = X2, ld2, md
+        tab = dict(uniq=uniq, u_max=u_max, n_uniq=n_uniq, H0=H0, Hnew=None, lu_u=None, HG=None, XG=None, valid_u=None,
+                   GI=None, GH=None, M1=None, X2=None, XH=None, Wc=None, merged=False)
+        if not c.use_memory:
+            _lib.call("pfo_cell_forward", ptr(uniq), ptr(n_uniq), u_max, d, c.cell, 0, None, None, G, None, None,
+                      ptr(self.node_feat), None, ptr(H0))
+            return tab
+        merged = c.cell_gemm == "merged"
+        mlp = c.message_fn == "mlp"
+        HG = torch.empty(u_max, d, device=dev)
+        valid_u = torch.empty(u_max, dtype=torch.uint8, device=dev)
+        lu_u = torch.empty(u_max, device=dev)
+        hid, md = c.mlp_hidden, c.msg_dim
+        ld1, ld2 = (hid + 3) // 4 * 4, (md + 3) // 4 * 4
+        kx, kxp = (md, ld2) if mlp else (c.raw, c.rawp)     # width of the cell input and of its slot in the operand row
+        ldx = kxp + d
+        XH = None
+        if merged:                                          # operand rows [cell input (kxp) | memory (d)]
+            XH = (torch.zeros if mlp else torch.empty)(u_max, ldx, device=dev)
+        XG = torch.empty(u_max, c.rawp, device=dev) if (mlp or not merged) else XH
+        _lib.call("pfo_gather_state", ptr(uniq), ptr(n_uniq), u_max, d, c.raw, ptr(st.memory), ptr(st.pend_msg),
+                  c.rawp, ptr(st.pend_valid), ptr(st.pend_ts), ptr(st.last_update),
+                  ptr(HG), ptr(XG), c.rawp if XG is not XH else ldx,
+                  (XH.data_ptr() + kxp * F4) if merged else None, ldx, ptr(valid_u), ptr(lu_u))
+        W_ih, W_hh, b_ih, b_hh = cellW
+        X, ldxin = XG, c.rawp
+        M1 = X2 = None
+        if mlp:          # Linear(raw, raw // 2) -> ReLU -> Linear(raw // 2, msg_dim)
+            W1, b1, W2, b2 = mlpW
+            M1 = torch.empty(u_max, ld1, device=dev)
+            _linear(c, ptr(XG), c.rawp, None, ptr(W1), c.raw, 0, ptr(b1), ptr(M1), ld1, u_max, hid, c.raw,
+                    m_dev=ptr(n_uniq), act=1)
+            if merged:
+                X2, ldxin = XH, ldx                         # the message lands in its slot of the operand row
+            else:
+                X2, ldxin = torch.empty(u_max, ld2, device=dev), ld2
+            _linear(c, ptr(M1), ld1, None, ptr(W2), hid, 0, ptr(b2), ptr(X2), ldxin, u_max, md, hid, m_dev=ptr(n_uniq))
+            X = X2
+        Hnew = torch.empty(u_max, d, device=dev)
+        GI = GH = Wc = None
+        if merged:
+            Gm = 4 * d if c.cell == CELL_GRU else d
+            Wc = torch.empty(Gm, ldx, device=dev)
+            bc = torch.empty(Gm, device=dev)
+            _lib.call("pfo_pack_cell", ptr(W_ih), ptr(W_hh), ptr(b_ih), ptr(b_hh), d, kx, kxp, c.cell, ptr(Wc), ptr(bc))
+            GI = torch.empty(u_max, Gm, device=dev)
+            _linear(c, ptr(XH), ldx, None, ptr(Wc), ldx, 0, ptr(bc), ptr(GI), Gm, u_max, Gm, ldx, m_dev=ptr(n_uniq))
+            _lib.call("pfo_cell_forward", ptr(uniq), ptr(n_uniq), u_max, d, c.cell, 1, ptr(GI), None, Gm, ptr(HG),
+                      ptr(valid_u), ptr(self.node_feat), ptr(Hnew), ptr(H0))
+        else:
             GI = torch.empty(u_max, G, device=dev)
             GH = torch.empty(u_max, G, device=dev)
-            _linear(c, ptr(X), ldx, None, ptr(W_ih), kx, 0, ptr(b_ih), ptr(GI), G, u_max, G, kx, m_dev=ptr(n_uniq))
+            _linear(c, ptr(X), ldxin, None, ptr(W_ih), kx, 0, ptr(b_ih), ptr(GI), G, u_max, G, kx, m_dev=ptr(n_uniq))
             _linear(c, ptr(HG), d, None, ptr(W_hh), d, 0, ptr(b_hh), ptr(GH), G, u_max, G, d, m_dev=ptr(n_uniq))
-            Hnew = torch.empty(u_max, d, device=dev)
-        _lib.call("pfo_cell_forward", ptr(uniq), ptr(n_uniq), u_max, d, c.cell, ptr(GI), ptr(GH), G, ptr(HG),
-                  ptr(valid_u), ptr(self.node_feat), ptr(Hnew), ptr(H0))
-        return dict(uniq=uniq, u_max=u_max, n_uniq=n_uniq, H0=H0, Hnew=Hnew, lu_u=lu_u, HG=HG, XG=XG,
-                    valid_u=valid_u, GI=GI, GH=GH, M1=M1, X2=X2)
+            _lib.call("pfo_cell_forward", ptr(uniq), ptr(n_uniq), u_max, d, c.cell, 0, ptr(GI), ptr(GH), G, ptr(HG),
+                      ptr(valid_u), ptr(self.node_feat), ptr(Hnew), ptr(H0))
+        tab.update(Hnew=Hnew, lu_u=lu_u, HG=HG, XG=XG, valid_u=valid_u, GI=GI, GH=GH, M1=M1, X2=X2, XH=XH, Wc=Wc,
+                   merged=merged, kx=kx, kxp=kxp, ldx=ldx, ldxin=ldxin)
+        return tab
 
     def node_table_backward(self, tab, dH0, g_cell, mlpW=None, g_mlp=None, cellW=None):
         """dH0 (= dHnew) -> gradients of the cell weights and, through the cell input, of the MLP message function
@@ -488,31 +523,45 @@ class TGNEngine:
         c, dev = self.cfg, self.device
         d, u_max, n_uniq = c.d, tab["u_max"], tab["n_uniq"]
         G = c.gates * d
-        dGI = torch.empty(u_max, G, device=dev)
-        dGH = torch.empty(u_max, G, device=dev)
-        _lib.call("pfo_cell_backward", ptr(tab["uniq"]), ptr(n_uniq), u_max, d, c.cell, ptr(tab["GI"]), ptr(tab["GH"]),
-                  G, ptr(tab["HG"]), ptr(tab["valid_u"]), ptr(dH0), ptr(dGI), ptr(dGH))
         gW_ih, gW_hh, gb_ih, gb_hh = g_cell
-        if c.message_fn == "mlp":
+        mlp = c.message_fn == "mlp"
+        hid, md = c.mlp_hidden, c.msg_dim
+        if tab["merged"]:
+            kx, kxp, ldx = tab["kx"], tab["kxp"], tab["ldx"]
+            Gm = 4 * d if c.cell == CELL_GRU else d
+            dG = torch.empty(u_max, Gm, device=dev)
+            _lib.call("pfo_cell_backward", ptr(tab["uniq"]), ptr(n_uniq), u_max, d, c.cell, 1, ptr(tab["GI"]), None, Gm,
+                      ptr(tab["HG"]), ptr(tab["valid_u"]), ptr(dH0), ptr(dG), None)
+            gWc = torch.empty(Gm, ldx, device=dev)
+            gbc = torch.empty(Gm, device=dev)
+            _wgrad(c, self.ws, ptr(dG), Gm, ptr(tab["XH"]), ldx, None, u_max, Gm, ldx, ptr(gWc), ldx, ptr(gbc),
+                   m_dev=ptr(n_uniq))
+            _lib.call("pfo_unpack_cell_grads", ptr(gWc), ptr(gbc), d, kx, kxp, c.cell, ptr(gW_ih), ptr(gW_hh),
+                      ptr(gb_ih), ptr(gb_hh))
+            dGI, W_in, ldw_in, Gin = dG, tab["Wc"], ldx, Gm   # d(cell input) = dG . Wc[:, :kx]
+        else:
+            dGI = torch.empty(u_max, G, device=dev)
+            dGH = torch.empty(u_max, G, device=dev)
+            _lib.call("pfo_cell_backward", ptr(tab["uniq"]), ptr(n_uniq), u_max, d, c.cell, 0, ptr(tab["GI"]),
+                      ptr(tab["GH"]), G, ptr(tab["HG"]), ptr(tab["valid_u"]), ptr(dH0), ptr(dGI), ptr(dGH))
+            X, ldxin, kx = (tab["X2"], tab["ldxin"], md) if mlp else (tab["XG"], c.rawp, c.raw)
+            _wgrad(c, self.ws, ptr(dGI), G, ptr(X), ldxin, None, u_max, G, kx, ptr(gW_ih), kx, ptr(gb_ih), m_dev=ptr(n_uniq))
+            _wgrad(c, self.ws, ptr(dGH), G, ptr(tab["HG"]), d, None, u_max, G, d, ptr(gW_hh), d, ptr(gb_hh),
+                   m_dev=ptr(n_uniq))
+            W_in, ldw_in, Gin = (cellW[0] if cellW is not None else None), md, G
+        if mlp:
             W1, b1, W2, b2 = mlpW
             gW1, gb1, gW2, gb2 = g_mlp
-            hid, md = c.mlp_hidden, c.msg_dim
-            M1, X2 = tab["M1"], tab["X2"]
-            ld1, ld2 = M1.shape[1], X2.shape[1]
-            _wgrad(c, self.ws, ptr(dGI), G, ptr(X2), ld2, None, u_max, G, md, ptr(gW_ih), md, ptr(gb_ih), m_dev=ptr(n_uniq))
+            M1 = tab["M1"]
+            ld1, ld2 = M1.shape[1], (md + 3) // 4 * 4
             dX2 = torch.empty(u_max, ld2, device=dev)
-            _linear(c, ptr(dGI), G, None, ptr(cellW[0]), md, 1, None, ptr(dX2), ld2, u_max, md, G, m_dev=ptr(n_uniq))
+            _linear(c, ptr(dGI), Gin, None, ptr(W_in), ldw_in, 1, None, ptr(dX2), ld2, u_max, md, Gin, m_dev=ptr(n_uniq))
             _wgrad(c, self.ws, ptr(dX2), ld2, ptr(M1), ld1, None, u_max, md, hid, ptr(gW2), hid, ptr(gb2), m_dev=ptr(n_uniq))
             dM1 = torch.empty(u_max, ld1, device=dev)
             _linear(c, ptr(dX2), ld2, None, ptr(W2), hid, 1, None, ptr(dM1), ld1, u_max, hid, md, m_dev=ptr(n_uniq),
                     relu_gate=ptr(M1), ld_gate=ld1)
             _wgrad(c, self.ws, ptr(dM1), ld1, ptr(tab["XG"]), c.rawp, None, u_max, hid, c.raw, ptr(gW1), c.raw, ptr(gb1),
                    m_dev=ptr(n_uniq))
-        else:
-            _wgrad(c, self.ws, ptr(dGI), G, ptr(tab["XG"]), c.rawp, None, u_max, G, c.raw, ptr(gW_ih), c.raw, ptr(gb_ih),
-                   m_dev=ptr(n_uniq))
-        _wgrad(c, self.ws, ptr(dGH), G, ptr(tab["HG"]), d, None, u_max, G, d, ptr(gW_hh), d, ptr(gb_hh),
-               m_dev=ptr(n_uniq))
 
     def persist_and_store(self, tab, batch, emb, tw, tb):
         """Persist the positives' memory from the lazy result, then build and store the new raw
