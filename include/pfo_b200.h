@@ -211,6 +211,12 @@ int pfo_time_embedding_bwd(const int32_t* q_nodes, int64_t Q, int d, const int32
                            int64_t workspace_floats, void* stream);
 
 /* small row utilities (gather with idx < 0 -> zero row; scatter-add = its gradient) */
+/* ---- optimiser step --- main.py:123,389 (torch.optim.Adam(lr), defaults otherwise) over ONE flat parameter / gradient /
+ * moment buffer (the trainer lays the parameters out in the engine's operand order and the step's backward writes its
+ * gradients straight into the flat gradient buffer).  *step = t >= 1, kept on the device. */
+int pfo_adam_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                  float beta1, float beta2, float eps, const int32_t* step, void* stream);
+
 /* ---- TimeEncode.forward alone --- model/time_encoding.py:17-25: out_cos[m, c] = cos(fmaf(t[m], w[c], b[c])) (fmaf ==
  * nn.Linear(1, d) bit for bit), out_sin optional.  mode 0 / 1 = the fp64 quadrant reduction the fused kernels use
  * (any |x| < 2^44), 2 = fp32 Cody-Waite reduction (|x| < 2^17; kept for the comparison test). */

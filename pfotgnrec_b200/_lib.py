@@ -67,6 +67,7 @@ _SIGS = {
                                        c_float, P, P, P, P, P]),
     "pfo_time_embedding_bwd": (c_int, [P, c_int64, c_int, P, P, P, P, P, P, P, P, P, c_int64, P]),
     "pfo_time_encode": (c_int, [P, P, P, c_int64, c_int, c_int, P, P, P]),
+    "pfo_adam_flat": (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, P, P]),
     "pfo_reduce_partials": (c_int, [P, c_int, c_int, P, c_int, P]),
     "pfo_scatter_add_rows": (c_int, [P, c_int64, P, c_int64, c_int, P, c_int64, P]),
     "pfo_gather_rows": (c_int, [P, c_int64, P, c_int64, c_int, P, c_int64, P]),

@@ -571,10 +571,12 @@ class ShardedTrainer(PfoTrainer):
         self._capture_kw = {"capture_error_mode": "thread_local"}
         self.engine.seed = tc.seed + 7919 * self.rank         # decorrelate the dropout streams of the ranks
         self.params = [p for p in self.tgn.parameters() if p.requires_grad]
-        sizes = [p.numel() for p in self.params]
-        self.gflat = torch.zeros(sum(sizes), device=self.device)          # gradient bucket; p.grad are views into it
-        for p, g in zip(self.params, self.gflat.split(sizes)):
-            p.grad = g.view_as(p)
+        self._own_bucket = self.gflat is None                 # else: the flat gradient buffer of the base class (engine sink)
+        if self._own_bucket:
+            sizes = [p.numel() for p in self.params]
+            self.gflat = torch.zeros(sum(sizes), device=self.device)
+            for p, g in zip(self.params, self.gflat.split(sizes)):
+                p.grad = g.view_as(p)
 
     # ---- construction hooks
     @property
@@ -687,7 +689,8 @@ class ShardedTrainer(PfoTrainer):
 
     # ---- gradient bucket (same scheme as the replicated trainer)
     def _zero_grads(self):
-        self.gflat.zero_()
+        if self._own_bucket:
+            self.gflat.zero_()
 
     def _reduce_grads(self):
         if self.world > 1:

@@ -231,6 +231,9 @@ class TGNEngine:
         # feature row 0 and te(t - 0), embedding_module.py:205-208): node 0 then needs a row in the node table
         self.skip_zero = 0 if cfg.embedding == "graph_sum" else 1
         self._slot_cache = {}
+        # optional flat gradient buffer in the order of `param_names()` (set by the trainers): the step's backward then
+        # writes every parameter gradient straight into it and hands autograd nothing to accumulate
+        self.grad_sink = None
         self.step_id = 0
         self.seed = 0
         # device-resident batch counter keying the dropout stream (bumped on the stream each batch, so a
@@ -265,6 +268,11 @@ class TGNEngine:
         elif c.embedding == "time":
             names += ["embedding_module.embedding_layer.weight", "embedding_module.embedding_layer.bias"]
         return names
+
+    def flat_layout_ok(self):
+        """True when every operand of the step is one reference parameter as it is (`_pack` adds no arithmetic), i.e.
+        the flat buffers of the trainer can follow `param_names()`.  graph_sum derives its operands with torch ops."""
+        return self.cfg.embedding != "graph_sum"
 
     def _pack(self, params):
         """Derived, kernel-friendly tensors built with torch autograd ops on the reference-named
@@ -842,7 +850,11 @@ class TGNStepFunction(torch.autograd.Function):
         dOut = dOut.contiguous()
         flat = pk["flat"]
         sizes = [t.numel() for t in flat]              # one zero-fill for all operand gradients
-        gbuf = torch.zeros(sum(sizes), device=dev)
+        sink = eng.grad_sink
+        if sink is not None and sink.numel() == sum(sizes):
+            gbuf = sink.zero_()
+        else:
+            sink, gbuf = None, torch.zeros(sum(sizes), device=dev)
         grads = [g.view_as(t) for g, t in zip(gbuf.split(sizes), flat)]
         it = iter(grads)
         g_tw, g_tb = next(it), next(it)
@@ -919,4 +931,6 @@ class TGNStepFunction(torch.autograd.Function):
             eng.join_side()
             for g in g_layers:
                 g_tb.add_(g[5])
+        if sink is not None:                            # gradients are in place: nothing for autograd to route
+            return (None, None) + (None,) * len(flat)
         return (None, None) + tuple(grads)

@@ -31,6 +31,28 @@ def load_overlay():
     return importlib.import_module("model.tgn"), importlib.import_module("utils.utils")
 
 
+class FlatAdam:
+    """torch.optim.Adam(lr) (main.py:123; betas 0.9 / 0.999, eps 1e-8, no weight decay) over one flat parameter buffer:
+    a single `pfo_adam_flat` launch per step, step count on the device (graph replays keep counting)."""
+
+    def __init__(self, flat_params, flat_grads, lr, betas=(0.9, 0.999), eps=1e-8):
+        self.p, self.g = flat_params, flat_grads
+        self.m, self.v = torch.zeros_like(flat_params), torch.zeros_like(flat_params)
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.t = torch.zeros(1, dtype=torch.int32, device=flat_params.device)
+
+    def step(self):
+        self.t.add_(1)
+        _lib.call("pfo_adam_flat", ptr(self.p), ptr(self.g), ptr(self.m), ptr(self.v), self.p.numel(), self.lr,
+                  self.betas[0], self.betas[1], self.eps, ptr(self.t))
+
+    def zero_grad(self, set_to_none=False):
+        self.g.zero_()
+
+    def state_dict(self):
+        return {"exp_avg": self.m, "exp_avg_sq": self.v, "step": self.t, "lr": self.lr, "betas": self.betas, "eps": self.eps}
+
+
 class _BPR(torch.autograd.Function):
     """-mean log sigmoid(mean_k(<u,p> - <u,n_k>)) with its gradient from one fused kernel (K6).  `grad_scale`
     multiplies the gradients inside the kernel (the data-parallel trainer's 1 / world); with `unit_upstream` the
@@ -190,7 +212,7 @@ class PfoTrainer:
                                std_time_shift_dst=sd, use_source_embedding_in_message=False,
                                gemm_mode=tc.gemm_mode, **self._tgn_extra(), **kw).to(self.device)
         self._bind_engine()
-        self.opt = torch.optim.Adam(self.tgn.parameters(), lr=tc.lr, fused=True, capturable=True)
+        self._setup_optimizer()
         self._graphs = {}            # batch size -> _StepGraph
         universe_items = info["universe_train"]
         self.universe_items = universe_items
@@ -208,6 +230,32 @@ class PfoTrainer:
         if st.prices_past.shape[0] == len(st.day_keys) and st.prices_past.shape[1] == st.n_items:
             self.metrics = EvalMetricBlock(log_returns(st.prices_past), log_returns(st.prices_future),
                                            st.n_users + 1, device=self.device)
+
+    def _setup_optimizer(self):
+        """Adam (main.py:123).  When every operand of the step is a reference parameter as it is, the parameters are
+        re-homed into ONE flat buffer in the engine's operand order, the step's backward writes their gradients
+        straight into the flat gradient buffer `gflat` (engine.grad_sink; `.grad` of each parameter is a view of it, and
+        it is the bucket the multi-GPU trainers all-reduce), and the optimiser step is one launch (`pfo_adam_flat`).
+        Otherwise (graph_sum derives its operands with torch ops) torch's fused Adam runs on the separate tensors."""
+        tc, eng = self.tc, self.tgn._get_engine()
+        self.gflat, self.flat_params = None, None
+        if not eng.flat_layout_ok():
+            self.opt = torch.optim.Adam(self.tgn.parameters(), lr=tc.lr, fused=True, capturable=True)
+            return
+        named = dict(self.tgn.named_parameters(remove_duplicate=False))
+        plist = [named[k] for k in eng.param_names()]
+        sizes = [p.numel() for p in plist]
+        if any(n % 4 for n in sizes):                     # slices must stay 16-byte aligned for the GEMM operand loads
+            self.opt = torch.optim.Adam(self.tgn.parameters(), lr=tc.lr, fused=True, capturable=True)
+            return
+        flat = torch.cat([p.detach().reshape(-1) for p in plist]).contiguous()
+        self.gflat = torch.zeros_like(flat)
+        for p, w, g in zip(plist, flat.split(sizes), self.gflat.split(sizes)):
+            p.data = w.view_as(p)                         # same values, now a slice of the flat buffer
+            p.grad = g.view_as(p)
+        self.flat_params = flat
+        eng.grad_sink = self.gflat
+        self.opt = FlatAdam(flat, self.gflat, lr=tc.lr)
 
     def _prepare_stream(self, train_frac_mask=None):
         """Everything the constructor derives from the interaction stream (host `synth.Stream`): the chronological
@@ -405,7 +453,8 @@ class PfoTrainer:
     _capture_kw = {}             # multi-rank trainers capture NCCL collectives: capture_error_mode="thread_local"
 
     def _zero_grads(self):
-        self.opt.zero_grad(set_to_none=True)
+        if self.gflat is None:
+            self.opt.zero_grad(set_to_none=True)          # flat layout: the backward zero-fills its gradient buffer itself
 
     def _reduce_grads(self):
         pass
@@ -612,13 +661,16 @@ class ReplicatedTrainer(PfoTrainer):
         self._graph_tail_eager = not self.nccl_in_graph
         self.tgn._get_engine().seed = tc.seed + 7919 * self.rank        # decorrelate the dropout streams of the replicas
         self.params = [p for p in self.tgn.parameters() if p.requires_grad]
-        sizes = [p.numel() for p in self.params]
-        self.gflat = torch.zeros(sum(sizes), device=self.device)         # gradient bucket; p.grad are views into it
-        for p, g in zip(self.params, self.gflat.split(sizes)):
-            p.grad = g.view_as(p)
+        self._own_bucket = self.gflat is None
+        if self._own_bucket:         # operands derived by torch ops (graph_sum): autograd accumulates into views of a bucket
+            sizes = [p.numel() for p in self.params]
+            self.gflat = torch.zeros(sum(sizes), device=self.device)
+            for p, g in zip(self.params, self.gflat.split(sizes)):
+                p.grad = g.view_as(p)
 
     def _zero_grads(self):
-        self.gflat.zero_()
+        if self._own_bucket:
+            self.gflat.zero_()
 
     def _check_fit(self, bs):
         if bs < self.world:
