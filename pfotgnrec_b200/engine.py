@@ -40,7 +40,12 @@ class ModelConfig:
     shift: tuple = (0.0, 1.0, 0.0, 1.0)  # mean/std time shift src, dst
     dropout: float = 0.0
     gemm_mode: str = "fp32"     # "fp32" (3xTF32 tcgen05, 1e-5) | "tf32" (tcgen05, 2e-2) | "bf16" | "simt" (FFMA)
-    cell_gemm: str = "merged"   # memory updater: "merged" = one contraction over [message | memory]; "split" = two
+    # memory updater GEMMs: "split" = torch's two (W_ih . message, W_hh . memory); "merged" = ONE contraction over the
+    # operand row [message | memory] with a block weight.  Measured at bs 8192 (profiles/r2_bench_merged_cell.json): the
+    # merged forward GEMM saves 15 us, but the merged weight gradient [4d x (raw + d)] costs 118 us against 74 us for the
+    # two separate ones (the wgrad kernel's slab decomposition degrades at N = 256), and the bf16 kernel does not take
+    # the shape -- so "split" stays the default and "merged" is an opt-in covered by its own parity test.
+    cell_gemm: str = "split"
 
     @property
     def E(self):                # attention embed dim = d + time dim

@@ -281,3 +281,23 @@ def test_standalone_sub_module_forwards():
     ref = torch.relu(raw.double() @ mf.mlp[0].weight.double().T + mf.mlp[0].bias.double())
     ref = ref @ mf.mlp[2].weight.double().T + mf.mlp[2].bias.double()
     assert rel_err(mf.compute_message(raw).cpu().numpy(), ref.detach().cpu().numpy()) < TOL
+
+
+@pytest.mark.parametrize("tag", ["ours", "jodie", "mlp_mean"])
+def test_merged_cell_gemm_matches_reference_golden(overlay, tag):
+    """ModelConfig.cell_gemm = "merged" (one contraction over [message | memory] with the block weight of pfo_pack_cell,
+    gradients unpacked by pfo_unpack_cell_grads; opt-in, see engine.ModelConfig) under the same 1e-5 / 5e-5 contract:
+    GRU, RNN and the MLP message function in front of the cell."""
+    tgn_mod, utils_mod = overlay
+    z = load_golden(f"tgn_{tag}.npz")
+    orig = tgn_mod.TGN._get_engine
+
+    def merged_engine(self):
+        self._cfg.cell_gemm = "merged"
+        return orig(self)
+
+    tgn_mod.TGN._get_engine = merged_engine
+    try:
+        check_against_vectors(tgn_mod, utils_mod, z, "fp32", tag + "/merged")
+    finally:
+        tgn_mod.TGN._get_engine = orig
