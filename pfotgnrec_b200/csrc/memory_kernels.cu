@@ -305,8 +305,18 @@ reduce_partials_kernel(const float* __restrict__ partial, int rows, int cols, fl
     if (cols >= 32) {
         const int c = blockIdx.x * 32 + lane;
         float s = 0.0f;
-        if (c < cols)
-            for (int r = w; r < rows; r += 8) s += partial[(int64_t)r * cols + c];
+        if (c < cols) {      // four independent chains per warp (fixed association: deterministic)
+            float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+            int r = w;
+            for (; r + 24 < rows; r += 32) {
+                s0 += partial[(int64_t)r * cols + c];
+                s1 += partial[(int64_t)(r + 8) * cols + c];
+                s2 += partial[(int64_t)(r + 16) * cols + c];
+                s3 += partial[(int64_t)(r + 24) * cols + c];
+            }
+            for (; r < rows; r += 8) s0 += partial[(int64_t)r * cols + c];
+            s = (s0 + s1) + (s2 + s3);
+        }
         sm[w][lane] = s;
         __syncthreads();
         if (w == 0 && c < cols) {

@@ -343,8 +343,20 @@ wgrad_tma_reduce_kernel(const float* __restrict__ partial, int S, int N, int K, 
     const int total = N * Kaug;
     const int i = blockIdx.x * 32 + lane;
     float s = 0.0f;
-    if (i < total)
-        for (int y = w; y < S; y += 8) s += partial[(int64_t)y * total + i];
+    if (i < total) {
+        // four independent chains per warp (fixed association, still deterministic): the loads of a single running sum
+        // would queue behind each other's latency
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+        int y = w;
+        for (; y + 24 < S; y += 32) {
+            s0 += partial[(int64_t)y * total + i];
+            s1 += partial[(int64_t)(y + 8) * total + i];
+            s2 += partial[(int64_t)(y + 16) * total + i];
+            s3 += partial[(int64_t)(y + 24) * total + i];
+        }
+        for (; y < S; y += 8) s0 += partial[(int64_t)y * total + i];
+        s = (s0 + s1) + (s2 + s3);
+    }
     sm[w][lane] = s;
     __syncthreads();
     if (w == 0 && i < total) {
