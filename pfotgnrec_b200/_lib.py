@@ -91,7 +91,7 @@ EXPORTS = tuple(_SIGS)
 ABI_VERSION = 2         # PFO_ABI_VERSION of include/pfo_b200.h this binding was written against
 _lib = None
 LAUNCHES = 0            # kernels launched through this binding (bench.py reports it)
-_LAUNCHES_PER_CALL = {"pfo_compact_nodes": 3, "pfo_fold_attention_fwd": 2, "pfo_fold_attention_bwd": 2,
+_LAUNCHES_PER_CALL = {"pfo_compact_nodes": 1, "pfo_fold_attention_fwd": 2, "pfo_fold_attention_bwd": 2,
                       "pfo_fold_attention_workspace_doubles": 0, "pfo_wgrad_f32": 2, "pfo_wgrad_tf32": 2,
                       "pfo_wgrad_tf32_workspace_floats": 0, "pfo_time_embedding_bwd": 2,
                       "pfo_attn_nbr_bwd": 2, "pfo_bpr": 2, "pfo_eval_metrics": 2, "pfo_apply_messages": 2, "pfo_apply_routed_messages": 2, "pfo_abi_version": 0, "pfo_peer_alloc": 0, "pfo_peer_open": 0, "pfo_peer_close": 0, "pfo_peer_free": 0,
@@ -151,7 +151,10 @@ def call(name, *args):
     global LAUNCHES
     lib = load()
     rc = getattr(lib, name)(*args, stream())
-    LAUNCHES += _LAUNCHES_PER_CALL.get(name, 1)
+    if name == "pfo_compact_nodes":          # one CTA for small id spaces (<= 8192 bitmap words), three kernels beyond
+        LAUNCHES += 1 if (int(args[1]) + 31) // 32 <= 8192 else 3
+    else:
+        LAUNCHES += _LAUNCHES_PER_CALL.get(name, 1)
     if rc != 0:
         raise PfoError(f"{name} failed with cudaError {rc}")
 

@@ -291,6 +291,62 @@ compact_emit_kernel(uint32_t* __restrict__ bitmap, int64_t n_words, const int32_
     }
 }
 
+// Small id spaces (<= kSmallWords bitmap words, i.e. <= 262 144 nodes: the bench stream, an owner's share of a sharded
+// one): count, scan and emit in ONE CTA instead of three launches -- at this size each of the three is pure launch latency.
+constexpr int kSmallThreads = 1024;
+constexpr int kSmallPerThread = 8;
+constexpr int kSmallWords = kSmallThreads * kSmallPerThread;
+
+__global__ void __launch_bounds__(kSmallThreads)
+compact_small_kernel(uint32_t* __restrict__ bitmap, int64_t n_words, int32_t* __restrict__ uniq_ids,
+                     int32_t* __restrict__ slot_of_node, int32_t* __restrict__ n_unique) {
+    pfo_pdl_prologue();
+    __shared__ int warp_tot[kSmallThreads / 32];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int per = (int)((n_words + kSmallThreads - 1) / kSmallThreads);       // consecutive words per thread (<= 8)
+    const int64_t w0 = (int64_t)t * per;
+    uint32_t words[kSmallPerThread];
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < kSmallPerThread; ++k) {
+        words[k] = (k < per && w0 + k < n_words) ? bitmap[w0 + k] : 0u;
+        c += __popc(words[k]);
+    }
+    int inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) warp_tot[w] = inc;
+    __syncthreads();
+    if (w == 0) {                                        // scan of the 32 warp totals
+        int v = warp_tot[lane], iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, iv, o);
+            if (lane >= o) iv += y;
+        }
+        warp_tot[lane] = iv - v;                         // exclusive offset of warp `lane`
+        if (lane == 31) *n_unique = iv;
+    }
+    __syncthreads();
+    int pos = warp_tot[w] + inc - c;
+#pragma unroll
+    for (int k = 0; k < kSmallPerThread; ++k) {
+        uint32_t x = words[k];
+        if (x) bitmap[w0 + k] = 0u;                      // leave the bitmap clean for the next batch
+        while (x) {
+            const int b = __ffs(x) - 1;
+            x &= x - 1;
+            const int node = (int)((w0 + k) * 32 + b);
+            uniq_ids[pos] = node;                        // ascending node id -> deterministic order
+            slot_of_node[node] = pos;
+            ++pos;
+        }
+    }
+}
+
 __global__ void map_slots_kernel(const int32_t* __restrict__ ids, int64_t count, int skip_zero,
                                  const int32_t* __restrict__ slot_of_node, int32_t* __restrict__ out) {
     pfo_pdl_prologue();
@@ -372,6 +428,10 @@ PFO_API int pfo_compact_nodes(uint32_t* bitmap, int64_t n_nodes, int32_t* worksp
                               int32_t* slot_of_node, int32_t* n_unique, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t n_words = (n_nodes + 31) / 32;
+    if (n_words <= kSmallWords) {
+        pfo_launch(compact_small_kernel, 1, kSmallThreads, 0, s, bitmap, n_words, uniq_ids, slot_of_node, n_unique);
+        PFO_LAUNCH_CHECK();
+    }
     const int n_blocks = (int)((n_words + kWordsPerBlock - 1) / kWordsPerBlock);
     pfo_launch(compact_count_kernel, n_blocks, kCompactBlock, 0, s, bitmap, n_words, workspace);
     pfo_launch(compact_scan_kernel, 1, kCompactBlock, 0, s, workspace, n_blocks, n_unique);

@@ -15,13 +15,22 @@ The reference is single-process (main.py:103); this module ADDS the sharding the
   followed by one all-reduce of the ~133 k parameter gradients (flat bucket, parameter .grad are views into it).
 * Every exchange plan lives on the DEVICE (csrc/route_kernels.cu): a row's place in the send buffer is
   slot = dest * cap + arrival order (warp-aggregated atomics), every (source, destination) pair owns `cap` rows, the
-  buffers go through one equal-split all-to-all with static sizes, empty slots carry id -1 and are skipped by the
-  consumer kernels, replies come back in the same slots.  No split size ever crosses the host, so the whole step --
-  six all-to-alls, the all-reduce and Adam included -- is captured in ONE CUDA graph per batch size like the
-  single-GPU step.  Capacities start at a size that cannot overflow, are calibrated from the bucket counts of the two
-  eager warm-up steps (max over ranks, x margin) and frozen at capture; an overflow flag on the device guards them.
+  buffers have static shapes, empty slots carry id -1 and are skipped by the consumer kernels, replies come back in the
+  same slots.  No split size ever crosses the host, so the whole step -- six exchanges, the all-reduce and Adam included
+  -- is captured in ONE CUDA graph per batch size like the single-GPU step.  Capacities start at a size that cannot
+  overflow, are calibrated from the bucket counts of the two eager warm-up steps (max over ranks, x margin) and frozen at
+  capture; an overflow flag on the device guards them.
+* Transport (csrc/peer_kernels.cu): a calibrated exchange is a PUSH of each destination's block straight into that
+  rank's receive buffer -- a cudaMalloc'ed arena every rank maps through CUDA IPC, same offset everywhere -- followed by
+  a flag barrier over the same peer mappings (release / acquire at system scope, epochs in device memory, timeout
+  instead of a hang).  Two small launches instead of one NCCL all-to-all (1.185 -> 1.111 ms per step on 2 GPUs,
+  1.244 -> 1.180 ms on 8).  The oversized calibration steps, and a box without peer access, use all_to_all_single.
+* R4 runs on the engine's side stream beside the BPR loss and the attention backward (nothing it writes is read there).
 * Every quantity is identical to the 1-GPU path on the same global batch up to fp32 summation order
-  (tests/test_gpu_sharded.py on 2 GPUs: loss, gradients, memory, last_update, pending flags).
+  (tools/check_sharded.py under torchrun, tests/test_gpu_sharded.py: loss, gradients, memory, last_update, pending
+  flags, evaluation candidates and scores, on 2 GPUs; the same machinery on one rank runs in the 1-GPU test tier).
+* A procedural `synth_device.DeviceStream` (BASELINE config 4: 10^9 interactions) is consumed without ever existing on
+  the host: columns per batch from the interaction index, CSR rows of the owned nodes from 64 M-interaction chunks.
 
 `Exchange` also runs on CPU tensors with the gloo backend (plans by torch ops instead of the CUDA kernels), which is
 how the slot / reply logic is covered by world_size-2 tests without a GPU (tests/test_dist_router.py).
@@ -540,7 +549,7 @@ class ShardedEngine(TGNEngine):
         _lib.call("pfo_build_routed_messages", ptr(s_slot), ptr(d_slot), ptr(src), ptr(dst), ptr(batch["eidx"]),
                   ptr(batch["ts"]), B, d, F, ptr(tab["Hnew"]), ptr(tab["lu_u"]), ptr(self.edge_feat), ptr(tw), ptr(tb),
                   ptr(o_src), ptr(o_dst), G, key_base, key_side, ptr(rows), ldr)
-        nodes = torch.cat([src, dst])
+        nodes = self.q_nodes_last[:2 * B]                    # the query list starts with [src | dst]
         plan = ex.plan((self.tag, "R4"), nodes, 2 * B)
         send = ex.buffer(plan, ldr, dtype=torch.float32)
         send.view(torch.int32)[:, c.raw].fill_(-1)           # empty slots: node id -1 (only this column is read first)

@@ -814,6 +814,7 @@ class TGNStepFunction(torch.autograd.Function):
         eng._slot_cache = {}                            # slot_of_node was rewritten by this batch's compaction
         qslots = eng._slots(q_nodes)
         eng.qslots_last = qslots                        # rows [src | dst | ...] of the batch in the node table
+        eng.q_nodes_last = q_nodes
         if c.embedding == "graph_attention":
             eng.join_side()
             with _lib.nvtx_range("K4 temporal attention forward"):
