@@ -151,8 +151,8 @@ def call(name, *args):
     global LAUNCHES
     lib = load()
     rc = getattr(lib, name)(*args, stream())
-    if name == "pfo_compact_nodes":          # one CTA for small id spaces (<= 8192 bitmap words), three kernels beyond
-        LAUNCHES += 1 if (int(args[1]) + 31) // 32 <= 8192 else 3
+    if name == "pfo_compact_nodes":          # one CTA for small id spaces (<= 1024 bitmap words), three kernels beyond
+        LAUNCHES += 1 if (int(args[1]) + 31) // 32 <= 1024 else 3
     else:
         LAUNCHES += _LAUNCHES_PER_CALL.get(name, 1)
     if rc != 0:

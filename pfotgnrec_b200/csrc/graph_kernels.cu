@@ -291,10 +291,12 @@ compact_emit_kernel(uint32_t* __restrict__ bitmap, int64_t n_words, const int32_
     }
 }
 
-// Small id spaces (<= kSmallWords bitmap words, i.e. <= 262 144 nodes: the bench stream, an owner's share of a sharded
-// one): count, scan and emit in ONE CTA instead of three launches -- at this size each of the three is pure launch latency.
+// Small id spaces (<= kSmallWords bitmap words = 32 768 nodes: an owner's share of a sharded stream, the test streams):
+// count, scan and emit in ONE CTA instead of three launches.  Measured: beyond that the single SM's scattered stores of
+// the emit phase cost more than the two launches saved (bench stream, 101 001 nodes: 0.872 -> 0.885 ms per step with a
+// 262 144-node limit), so larger spaces keep the three-kernel path.
 constexpr int kSmallThreads = 1024;
-constexpr int kSmallPerThread = 8;
+constexpr int kSmallPerThread = 1;
 constexpr int kSmallWords = kSmallThreads * kSmallPerThread;
 
 __global__ void __launch_bounds__(kSmallThreads)

@@ -175,7 +175,7 @@ def test_time_encode_cos_paths():
 def test_unique_node_compaction():
     from pfotgnrec_b200 import _lib
     from pfotgnrec_b200._lib import ptr
-    for N in (1000, 100003, 262144, 400003):          # one-CTA path up to 262 144 nodes, three-kernel path beyond
+    for N in (1000, 32768, 32769, 100003, 400003):    # one-CTA path up to 32 768 nodes, three-kernel path beyond
         rng = np.random.default_rng(N)
         ids = rng.integers(0, N, size=5000).astype(np.int32)
         ids[:10] = 0
