@@ -301,6 +301,9 @@ def algorithmic_work(name, args, n_uniq, extra):
     if name == "pfo_attn_nbr_fwd":
         Q, n, d, F, H, ekp = args[9:15]
         return "byte", Q * (2 * H * ekp * 4 + n * (4 * d + 4 * F + 12) + H * n * 4)
+    if name == "pfo_attn_nbr_fwd_rows":              # query operand shared per node: its rows are a cache-resident table,
+        Q, n, d, F, H, ekp = args[10:16]             # so only the row index counts as per-query traffic
+        return "byte", Q * (H * ekp * 4 + 4 + n * (4 * d + 4 * F + 12) + H * n * 4)
     if name == "pfo_attn_nbr_bwd":
         Q, n, d, F, H, ekp = args[13:19]
         return "byte", Q * (3 * H * ekp * 4 + n * (2 * 4 * d + 4 * F + 12) + H * n * 4)
@@ -518,19 +521,23 @@ def main():
     if host is not None:
         tr.train_step_host(host[0])                  # warm the path
         barrier()
-        t0 = time.perf_counter()
+        dt = 0.0
         for hb in host[1:]:
-            flush.fill_(1)                           # same L2 flush as the device-timed loop (inside e2e's clock)
-            l = tr.train_step_host(hb)
-            _ = float(l.item())                      # device -> host read of the step's result
+            flush.fill_(1)                           # same L2 flush as the device-timed loop, outside the step's clock
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()                 # host clock around the call a user makes: H2D of the batch ->
+            l = tr.train_step_host(hb)               # step -> D2H of the loss (the read synchronises the device)
+            _ = float(l.item())
+            dt += time.perf_counter() - t0
         barrier()
-        dt = time.perf_counter() - t0
         if world > 1:
             t = torch.tensor([dt], device=dev, dtype=torch.float64)
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": a.steps * events_per_step / dt, "unit": "events/s",
-               "h2d_bytes_per_step": int(host[1]["nbytes"]) * world, "d2h_bytes_per_step": 4 * world}
+               "h2d_bytes_per_step": int(host[1]["nbytes"]) * world, "d2h_bytes_per_step": 4 * world,
+               "timing": "sum of per-step host wall-clock durations (pinned host batch -> one H2D copy -> step -> loss "
+                         "read back), L2 flushed between steps outside the clock, max over ranks"}
 
     # ---- per-kernel pass (eager launches, CUDA events per C-ABI call) for the rooflines
     roofline, kernels, rooflines = None, None, None

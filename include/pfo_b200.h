@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define PFO_ABI_VERSION 2
+#define PFO_ABI_VERSION 3
 int pfo_abi_version(void);
 
 /* ---- K1: temporal neighbour sampling --- utils/utils.py:150-161 (find_before) and
@@ -236,7 +236,16 @@ int pfo_gather_rows(const float* src, int64_t lds, const int32_t* idx, int64_t M
  * XB / dXB rows are ldxb / lddxb floats apart.  T is the feature table the
  * neighbour rows are gathered from (idx < 0 = padded neighbour); P [Q,H,n] = softmax weights.
  * Dropout on the attention weights (p_drop > 0) draws from the shared Philox stream keyed by
- * (query, head * n + slot, step + *step_dev); step_dev (optional) is a device-resident batch counter. */
+ * (query, slot, step + *step_dev) -- one Philox4x32 block per (query, slot), word h = head h; step_dev (optional)
+ * is a device-resident batch counter.
+ * pfo_attn_nbr_fwd_rows: the same kernel with the query operand shared between queries -- query q reads row
+ * qk_row[q] of QK (NULL = row q).  qk_h depends on the query NODE only (the query's own time encoding is te(0),
+ * model/temporal_attention.py:48-50), so when a batch asks about few distinct nodes at many times -- full-ranking
+ * evaluation, evaluation.py:84-115: every user against all stocks -- the caller computes one row per node. */
+int pfo_attn_nbr_fwd_rows(const float* QK, const int32_t* qk_row, const float* T, int64_t ldt, const int32_t* idx,
+                          const int32_t* eidx, const float* dt, const float* efeat, const float* tw, const float* tb,
+                          int64_t Q, int n, int d, int F, int H, int ekp, float p_drop, uint64_t seed, uint32_t step,
+                          const uint32_t* step_dev, float* XB, int64_t ldxb, float* P, int32_t* invalid, void* stream);
 int pfo_attn_nbr_fwd(const float* QK, const float* T, int64_t ldt, const int32_t* idx, const int32_t* eidx,
                      const float* dt, const float* efeat, const float* tw, const float* tb,
                      int64_t Q, int n, int d, int F, int H, int ekp, float p_drop, uint64_t seed, uint32_t step,

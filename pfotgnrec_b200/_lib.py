@@ -73,6 +73,8 @@ _SIGS = {
     "pfo_gather_rows": (c_int, [P, c_int64, P, c_int64, c_int, P, c_int64, P]),
     "pfo_attn_nbr_fwd": (c_int, [P, P, c_int64, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int,
                                  c_float, c_uint64, c_uint32, P, P, c_int64, P, P, P]),
+    "pfo_attn_nbr_fwd_rows": (c_int, [P, P, P, c_int64, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int,
+                                      c_float, c_uint64, c_uint32, P, P, c_int64, P, P, P]),
     "pfo_attn_nbr_bwd_workspace_floats": (c_int64, [c_int]),
     "pfo_attn_nbr_bwd": (c_int, [P, P, c_int64, P, P, P, c_int64, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int,
                                  c_float, c_uint64, c_uint32, P, P, P, c_int64, P, c_int, P, P]),
@@ -88,7 +90,7 @@ _SIGS = {
 }
 
 EXPORTS = tuple(_SIGS)
-ABI_VERSION = 2         # PFO_ABI_VERSION of include/pfo_b200.h this binding was written against
+ABI_VERSION = 3         # PFO_ABI_VERSION of include/pfo_b200.h this binding was written against
 _lib = None
 LAUNCHES = 0            # kernels launched through this binding (bench.py reports it)
 _LAUNCHES_PER_CALL = {"pfo_compact_nodes": 1, "pfo_fold_attention_fwd": 2, "pfo_fold_attention_bwd": 2,

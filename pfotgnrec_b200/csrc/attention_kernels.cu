@@ -24,9 +24,10 @@
 namespace {
 
 constexpr int kMaxHeads = 4;      // instantiated head counts: 1, 2, 4
+constexpr int64_t kMaxRowFloats = (int64_t)1 << 28;   // row strides are kept as 32-bit byte counts in the kernels
 
 struct NbrArgs {
-    const float* QK; const float* T; int64_t ldt;
+    const float* QK; const int32_t* qk_row; const float* T; int64_t ldt;
     const int32_t* idx; const int32_t* eidx; const float* dt;
     const float* efeat; const float* tw; const float* tb;
     int64_t Q; int n; int d; int F; int H; int ekp;
@@ -36,16 +37,37 @@ struct NbrArgs {
     const float* dXB; int64_t lddxb; float* dQK; float* dT; int64_t lddt; float* partial;
 };
 
-// the dropout stream is keyed by (query, head * n + slot, step): `step` = p.step + *p.step_dev, the device
-// part being a per-batch counter the host bumps on the stream (so a captured CUDA graph replays fresh masks)
-__device__ __forceinline__ float keep_scale(const NbrArgs& p, uint32_t step, int64_t q, int h, int j) {
-    if (p.p_drop <= 0.0f) return 1.0f;
-    const uint32_t r = philox4x32_10((uint32_t)q, (uint32_t)(h * p.n + j), step, PFO_PURPOSE_DROPOUT, p.k0, p.k1).x;
-    const float u = (float)(r >> 8) * (1.0f / 16777216.0f);
-    return u < p.p_drop ? 0.0f : 1.0f / (1.0f - p.p_drop);
+// the dropout stream is keyed by (query, slot, step): ONE Philox4x32 block per (query, slot), word h of the block is
+// head h's draw (kMaxHeads = 4 words).  `step` = p.step + *p.step_dev, the device part being a per-batch counter the
+// host bumps on the stream (so a captured CUDA graph replays fresh masks)
+template <int NH>
+__device__ __forceinline__ void keep_scales(const NbrArgs& p, uint32_t step, int64_t q, int j, float (&keep)[NH]) {
+    static_assert(NH <= 4, "one Philox block carries four heads");
+#pragma unroll
+    for (int h = 0; h < NH; ++h) keep[h] = 1.0f;
+    if (p.p_drop <= 0.0f) return;
+    const Philox4 r = philox4x32_10((uint32_t)q, (uint32_t)j, step, PFO_PURPOSE_DROPOUT, p.k0, p.k1);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    const float inv = 1.0f / (1.0f - p.p_drop);
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+        const float u = (float)(w[h] >> 8) * (1.0f / 16777216.0f);
+        keep[h] = u < p.p_drop ? 0.0f : inv;
+    }
 }
 
 // DPL consecutive floats of a row owned by one lane (rows are 16-byte aligned, checked by the entry points)
+// same, through the read-only path of a gathered row whose address came out of pfo_row_ptr (an address built in PTX
+// carries no state space: a plain dereference would compile to a generic LD instead of LDG)
+template <int DPL>
+__device__ __forceinline__ void ldg_cols(const char* p, float (&v)[DPL]) {
+    if constexpr (DPL == 2) { const float2 t = __ldg(reinterpret_cast<const float2*>(p)); v[0] = t.x; v[1] = t.y; }
+    else if constexpr (DPL == 4) { const float4 t = __ldg(reinterpret_cast<const float4*>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else {
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) v[i] = __ldg(reinterpret_cast<const float*>(p) + i);
+    }
+}
 template <int DPL>
 __device__ __forceinline__ void ld_cols(const float* __restrict__ p, float (&v)[DPL]) {
     if constexpr (DPL == 2) { const float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y; }
@@ -112,6 +134,13 @@ attn_nbr_fwd_kernel(const NbrArgs p) {
     const int F = p.F, n = p.n, ekp = p.ekp;
     float* stash = smem + (size_t)wib * n * SW;
     const int c0 = lane * DPL;
+    // gather addresses as byte base + index * byte stride with a 32-bit stride (checked by the entry point): one
+    // IMAD.WIDE per gathered row instead of a 64 x 32-bit multiply-add chain (the SASS showed 4 + 10 integer
+    // instructions per neighbour for the two gathers)
+    const char* Tb = reinterpret_cast<const char*>(p.T) + (size_t)c0 * sizeof(float);
+    const int ldtb = (int)(p.ldt * (int64_t)sizeof(float));
+    const char* efb = reinterpret_cast<const char*>(p.efeat) + (size_t)lane * sizeof(float);
+    const int Fb = p.F * (int)sizeof(float);
     const uint32_t step = p.step + (p.step_dev ? *p.step_dev : 0u);
     float tw[DPL], tb[DPL];
 #pragma unroll
@@ -129,9 +158,11 @@ attn_nbr_fwd_kernel(const NbrArgs p) {
                 dt_n = __ldg(p.dt + q * n + lane);
                 ei_n = __ldg(p.eidx + q * n + lane);
             }
+            // queries may share rows of the query operand (pfo_attn_nbr_fwd_rows: one row per distinct query NODE)
+            const int64_t qr = p.qk_row ? (int64_t)__ldg(p.qk_row + q) : q;
 #pragma unroll
             for (int h = 0; h < NH; ++h) {
-                const float* qk = p.QK + (q * NH + h) * ekp;
+                const float* qk = p.QK + (qr * NH + h) * ekp;
                 ld_cols<DPL>(qk + c0, qa_n[h]);
 #pragma unroll
                 for (int i = 0; i < DPL; ++i) qg_n[h][i] = qk[d + F + c0 + i];
@@ -170,8 +201,8 @@ attn_nbr_fwd_kernel(const NbrArgs p) {
 #pragma unroll
                 for (int i = 0; i < DPL; ++i) xh[u][i] = 0.0f;
                 if (id[u] >= 0) {
-                    ld_cols<DPL>(p.T + (int64_t)id[u] * p.ldt + c0, xh[u]);
-                    if (lane < F) xe[u] = __ldg(p.efeat + (int64_t)ei * F + lane);
+                    ldg_cols<DPL>(pfo_row_ptr(Tb, id[u], ldtb), xh[u]);
+                    if (lane < F) xe[u] = __ldg(reinterpret_cast<const float*>(pfo_row_ptr(efb, ei, Fb)));
                 }
             }
             float part[NV];
@@ -206,7 +237,8 @@ attn_nbr_fwd_kernel(const NbrArgs p) {
         }
         __syncwarp();
         // ---- phase B: softmax over the slots (lane = slot), then the dropout factor of torch's attention dropout
-        float w[NH], psum[NH];
+        float w[NH], psum[NH], keep[NH];
+        keep_scales<NH>(p, step, q, lane, keep);
 #pragma unroll
         for (int h = 0; h < NH; ++h) {
             const float m = warp_max(live_l ? sj[h] : -INFINITY);
@@ -214,7 +246,7 @@ attn_nbr_fwd_kernel(const NbrArgs p) {
             const float l = warp_sum(e);
             const float pw = any ? e / l : 0.0f;
             if (lane < n) p.P[(q * NH + h) * n + lane] = pw;
-            w[h] = live_l ? pw * keep_scale(p, step, q, h, lane) : 0.0f;
+            w[h] = live_l ? pw * keep[h] : 0.0f;
             psum[h] = warp_sum(w[h]);
         }
         // ---- phase C
@@ -270,6 +302,13 @@ attn_nbr_bwd_kernel(const NbrArgs p) {
     float* stash = smem + (size_t)wib * n * sw;
     float* red = smem + (size_t)wpb * n * sw;           // [wpb][2][d] for the block reduction
     const int c0 = lane * DPL;
+    // byte bases + 32-bit byte strides of the gathers and of the gradient scatter (see the forward kernel)
+    const char* Tb = reinterpret_cast<const char*>(p.T) + (size_t)c0 * sizeof(float);
+    const int ldtb = (int)(p.ldt * (int64_t)sizeof(float));
+    const char* efb = reinterpret_cast<const char*>(p.efeat) + (size_t)lane * sizeof(float);
+    const int Fb = p.F * (int)sizeof(float);
+    char* dTb = reinterpret_cast<char*>(p.dT) + (size_t)c0 * sizeof(float);
+    const int lddtb = (int)(p.lddt * (int64_t)sizeof(float));
     const uint32_t step = p.step + (p.step_dev ? *p.step_dev : 0u);
     float tw[DPL], tb[DPL], dwl[DPL], dbl[DPL];
 #pragma unroll
@@ -326,12 +365,9 @@ attn_nbr_bwd_kernel(const NbrArgs p) {
             de[h] = 0.f;
         }
         load_header(q + nwarps);
+        keep_scales<NH>(p, step, q, lane, dpj);         // dpj holds the factor until pass A overwrites it with dp_hj
 #pragma unroll
-        for (int h = 0; h < NH; ++h) {
-            const float keep = (id_l >= 0) ? keep_scale(p, step, q, h, lane) : 1.0f;
-            pk[h] = pj[h] * keep;                       // softmax weight after dropout (what multiplied x_j forward)
-            dpj[h] = keep;                              // holds the factor until pass A overwrites it with dp_hj
-        }
+        for (int h = 0; h < NH; ++h) pk[h] = pj[h] * dpj[h];   // softmax weight after dropout (what multiplied x_j forward)
         if (!dead) {
             // pass A: rebuild x_j (kUnroll gathers in flight), stash it, dp_hj = keep_hj * (dXB_h . [x_j | 1])
             for (int j0 = 0; j0 < n; j0 += kUnroll) {
@@ -348,8 +384,8 @@ attn_nbr_bwd_kernel(const NbrArgs p) {
 #pragma unroll
                     for (int i = 0; i < DPL; ++i) xh[u][i] = 0.0f;
                     if (id[u] >= 0) {
-                        ld_cols<DPL>(p.T + (int64_t)id[u] * p.ldt + c0, xh[u]);
-                        if (lane < F) xe[u] = __ldg(p.efeat + (int64_t)ei * F + lane);
+                        ldg_cols<DPL>(pfo_row_ptr(Tb, id[u], ldtb), xh[u]);
+                        if (lane < F) xe[u] = __ldg(reinterpret_cast<const float*>(pfo_row_ptr(efb, ei, Fb)));
                     }
                 }
                 float part[kUnroll * NH];
@@ -418,7 +454,7 @@ attn_nbr_bwd_kernel(const NbrArgs p) {
                         gxt[i] += pw * gg[h][i] + ds * qg[h][i];
                     }
                 }
-                float* drow = p.dT + (int64_t)id * p.lddt + c0;
+                float* drow = reinterpret_cast<float*>(const_cast<char*>(pfo_row_ptr(dTb, id, lddtb)));
                 if constexpr (DPL == 4) red_add_f32x4(drow, gxh[0], gxh[1], gxh[2], gxh[3]);
                 else if constexpr (DPL == 2) red_add_f32x2(drow, gxh[0], gxh[1]);
                 else {
@@ -619,17 +655,27 @@ PFO_API int pfo_attn_nbr_fwd(const float* QK, const float* T, int64_t ldt, const
                              int64_t Q, int n, int d, int F, int H, int ekp,
                              float p_drop, uint64_t seed, uint32_t step, const uint32_t* step_dev,
                              float* XB, int64_t ldxb, float* P, int32_t* invalid, void* stream) {
+    return pfo_attn_nbr_fwd_rows(QK, nullptr, T, ldt, idx, eidx, dt, efeat, tw, tb, Q, n, d, F, H, ekp, p_drop, seed, step,
+                                 step_dev, XB, ldxb, P, invalid, stream);
+}
+
+PFO_API int pfo_attn_nbr_fwd_rows(const float* QK, const int32_t* qk_row, const float* T, int64_t ldt, const int32_t* idx,
+                                  const int32_t* eidx, const float* dt, const float* efeat, const float* tw, const float* tb,
+                                  int64_t Q, int n, int d, int F, int H, int ekp,
+                                  float p_drop, uint64_t seed, uint32_t step, const uint32_t* step_dev,
+                                  float* XB, int64_t ldxb, float* P, int32_t* invalid, void* stream) {
     if (Q <= 0) return 0;
     if (d % 32 != 0 || d > 128 || F > 32 || H > kMaxHeads || n > 32 || n < 1 || ekp < 2 * d + F + 3 ||
         ldxb < (int64_t)H * ekp)
         return (int)cudaErrorInvalidValue;
     NbrArgs a{};
-    a.QK = QK; a.T = T; a.ldt = ldt; a.idx = idx; a.eidx = eidx; a.dt = dt; a.efeat = efeat; a.tw = tw; a.tb = tb;
+    a.QK = QK; a.qk_row = qk_row; a.T = T; a.ldt = ldt; a.idx = idx; a.eidx = eidx; a.dt = dt; a.efeat = efeat; a.tw = tw; a.tb = tb;
     a.Q = Q; a.n = n; a.d = d; a.F = F; a.H = H; a.ekp = ekp; a.p_drop = p_drop;
     a.k0 = (uint32_t)(seed & 0xffffffffu); a.k1 = (uint32_t)(seed >> 32); a.step = step; a.step_dev = step_dev;
     a.XB = XB; a.ldxb = ldxb; a.P = P; a.invalid = invalid;
     cudaStream_t s = (cudaStream_t)stream;
-    if (ldt % 4 != 0 || ldxb % 4 != 0 || ekp % 4 != 0 || !aligned16(T) || !aligned16(QK) || !aligned16(XB))
+    if (ldt % 4 != 0 || ldxb % 4 != 0 || ekp % 4 != 0 || !aligned16(T) || !aligned16(QK) || !aligned16(XB) ||
+        ldt > kMaxRowFloats)
         return (int)cudaErrorInvalidValue;             // rows are read / written with 8- and 16-byte accesses
     switch (d / 32) {
         case 1: return dispatch_fwd<1>(a, s);
@@ -663,7 +709,7 @@ PFO_API int pfo_attn_nbr_bwd(const float* QK, const float* dXB, int64_t lddxb, c
     const int max_grid = 2 * 148 * 4;
     if (grid > max_grid) grid = max_grid;
     if (ldt % 4 != 0 || lddxb % 4 != 0 || lddt % 4 != 0 || ekp % 4 != 0 || !aligned16(T) || !aligned16(QK) ||
-        !aligned16(dXB) || !aligned16(dQK) || !aligned16(dT))
+        !aligned16(dXB) || !aligned16(dQK) || !aligned16(dT) || ldt > kMaxRowFloats || lddt > kMaxRowFloats)
         return (int)cudaErrorInvalidValue;
     int rc;
     switch (d / 32) {

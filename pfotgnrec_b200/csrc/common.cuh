@@ -96,4 +96,13 @@ __device__ __forceinline__ void red_add_f32x2(float* addr, float a, float b) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" :: "l"(addr), "f"(a), "f"(b) : "memory");
 }
 
+// base + idx * stride_bytes as ONE IMAD.WIDE (signed 32 x 32 + 64).  Written as PTX because the compiler, given
+// `base + (int64_t)idx * stride`, re-derives the base from its parts and widens the stride (6 integer instructions per
+// gathered row in the neighbour kernels' SASS instead of 1).
+__device__ __forceinline__ const char* pfo_row_ptr(const char* base, int idx, int stride_bytes) {
+    unsigned long long a;
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(a) : "r"(idx), "r"(stride_bytes), "l"((unsigned long long)base));
+    return reinterpret_cast<const char*>(a);
+}
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }

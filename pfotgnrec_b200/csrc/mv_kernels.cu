@@ -15,6 +15,7 @@ namespace {
 
 constexpr int kCap = 256;          // threshold-select buffer per warp
 constexpr int kWarps = 4;
+constexpr int kStage = 8;          // candidate rows of the return table in flight per warp while staging
 
 __device__ __forceinline__ int find_pos(const int32_t* __restrict__ items, int M, int v) {
     int lo = 0, hi = M;
@@ -122,10 +123,12 @@ mv_select_kernel(const MvArgs p) {
     __shared__ int counts[kWarps];
     __shared__ int hs[kWarps][32];
     __shared__ double Ssum[kWarps][32];
+    extern __shared__ double rows_all[];                // [kWarps][C][T | 1] candidate rows of the return table
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t warp = (int64_t)blockIdx.x * kWarps + wib;
     const int64_t nwarps = (int64_t)gridDim.x * kWarps;
     const int K = p.K, C = K + 1, M = p.M, T = p.T;
+    const int TS = T | 1;                               // odd row stride (doubles): lane-per-row walks stay conflict-free
     for (int64_t b = warp; b < p.B; b += nwarps) {
         const int64_t g = p.event_ids[b];
         const uint32_t g_lo = (uint32_t)(g & 0xffffffffll), g_hi = (uint32_t)((g >> 32) & 0xffffffffll);
@@ -201,6 +204,22 @@ mv_select_kernel(const MvArgs p) {
 
         // ---- y_mv (main.py:243-271), closed form, left-to-right fp64 sums ----
         const double* lr = p.logret + (int64_t)p.day_idx[b] * p.n_stocks * T;
+        // the C candidate rows of the day's return table, staged in shared memory with coalesced loads (lane = return
+        // column, kStage rows in flight): lane c then walks ITS row from shared memory in the same left-to-right order
+        // (bit-identical sums).  Walking the rows straight from global memory cost one 8-byte sector per lane and
+        // step -- 4 passes x T dependent round trips to L1 / L2 per interaction.
+        double* rows = rows_all + (size_t)wib * C * TS;
+        for (int c0 = 0; c0 < C; c0 += kStage) {
+            double v[kStage];
+#pragma unroll
+            for (int u = 0; u < kStage; ++u) {
+                const int cu = __shfl_sync(0xffffffffu, my_cand, (c0 + u) & 31);
+                v[u] = (c0 + u < C && lane < T) ? __ldg(lr + (int64_t)cu * T + lane) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < kStage; ++u)
+                if (c0 + u < C && lane < T) rows[(c0 + u) * TS + lane] = v[u];
+        }
         if (lane < T) {
             double s = 0.0;
             for (int k = 0; k < nP; ++k) s = s + lr[(int64_t)held[k] * T + lane];
@@ -209,7 +228,7 @@ mv_select_kernel(const MvArgs p) {
         __syncwarp();
         double y = 0.0;
         if (lane < C) {
-            const double* r = lr + (int64_t)my_cand * T;
+            const double* r = rows + lane * TS;
             double acc = 0.0;
             for (int t = 0; t < T; ++t) acc = acc + r[t];
             const double mu = acc / (double)T;
@@ -332,7 +351,12 @@ PFO_API int pfo_mv_select(const int64_t* event_ids, const int32_t* day_idx, cons
     MvArgs a{event_ids, day_idx, pos_stock, port_ptr, port_items, items_sorted, n_items_universe,
              logret, n_stocks, n_returns, B, K, gamma, lam, n_pos, n_neg,
              (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), sample, cand, y_out, p_pos, p_neg, item_offset};
-    pfo_launch(mv_select_kernel, pfo_grid((int64_t)B * 32, kWarps * 32, 8), kWarps * 32, 0, (cudaStream_t)stream, a);
+    // candidate rows in shared memory: kWarps x (K + 1) rows of (T | 1) doubles (<= 34 KB, inside the default 48 KB
+    // with the 10 KB of static tables); the grid is capped at the CTAs that are resident at once
+    const size_t smem = (size_t)kWarps * (K + 1) * (n_returns | 1) * sizeof(double);
+    int per_sm = (int)((200 * 1024) / (smem + 10 * 1024 + 1024));
+    if (per_sm > 8) per_sm = 8;
+    pfo_launch(mv_select_kernel, pfo_grid((int64_t)B * 32, kWarps * 32, per_sm), kWarps * 32, smem, (cudaStream_t)stream, a);
     PFO_LAUNCH_CHECK();
 }
 

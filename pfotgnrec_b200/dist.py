@@ -776,8 +776,7 @@ class ShardedTrainer(PfoTrainer):
             ls, le = replica_slice(s, s + bs * self.world, self.rank, self.world)
             if self.procedural:
                 c, off = self._columns(ls, le), self._ev_offset()
-                hb = {k: (v + off if k == "ev" else v).cpu().pin_memory() for k, v in c.items()}
-                hb["nbytes"] = sum(v.numel() * v.element_size() for v in hb.values())
+                hb = self._pack_host_batch({k: (v + off if k == "ev" else v).cpu() for k, v in c.items()})
             else:
                 hb = super().make_host_batches(ls, 1, bs)[0]
             hb["_global"] = (s, s + bs * self.world)
@@ -791,11 +790,7 @@ class ShardedTrainer(PfoTrainer):
         try:
             B = hb["src"].shape[0]
             sg = self._step_graph(B)
-            for k, v in hb.items():
-                if k == "nbytes":
-                    continue
-                dstb = sg.static[k]
-                (dstb[:v.shape[0]] if k == "port_items" else dstb).copy_(v, non_blocking=True)
+            self._copy_host_batch(sg, hb)
             return self._run_graphed(sg)
         finally:
             hb["_global"] = (s, e)

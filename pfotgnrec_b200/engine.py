@@ -640,15 +640,30 @@ class TGNEngine:
         tp.CAT = torch.empty(M, ldc, device=dev)
         hq_ptr = tp.CAT.data_ptr() + hq * F4
         _lib.call("pfo_gather_rows", ptr(tp.Tq), d, ptr(tp.qidx), M, d, hq_ptr, ldc)
-        tp.QK = torch.empty(M, H, ekp, device=dev)  # qk_h = Wk_h^T q_h for both heads: one contraction over h_query
-        _linear(c, hq_ptr, ldc, None, ptr(Wqk), d, 0, ptr(cqk), ptr(tp.QK), hq, M, hq, d)
         tp.P = torch.empty(M, H, n, device=dev)
         tp.invalid = torch.empty(M, dtype=torch.int32, device=dev)
         tp.step = layer
         p_drop = c.dropout if save["train"] else 0.0
-        _lib.call("pfo_attn_nbr_fwd", ptr(tp.QK), ptr(tp.T), d, ptr(tp.idx), ptr(tp.eidx), ptr(tp.dt),
-                  ptr(self.edge_feat), ptr(save["tw"]), ptr(save["tb"]), M, n, d, F, H, ekp,
-                  float(p_drop), self.seed, tp.step, ptr(self.step_ctr), ptr(tp.CAT), ldc, ptr(tp.P), ptr(tp.invalid))
+        U = H0.shape[0]
+        if layer == 1 and not save.get("grad", True) and 2 * (U + 1) <= M:
+            # qk_h depends on the query NODE only (the query's time encoding is te(0)): when the queries outnumber the
+            # rows of the node table -- full-ranking evaluation asks about every stock once per user -- the
+            # contraction runs once per table row and the neighbour kernel reads row slot(query node); row U = the
+            # operand of a query without a table row (h_q = 0: the bias alone).  Inference only: the backward keeps
+            # per-query rows.
+            tp.QK = torch.empty(U + 1, H, ekp, device=dev)
+            _linear(c, ptr(H0), d, None, ptr(Wqk), d, 0, ptr(cqk), ptr(tp.QK), hq, U, hq, d, m_dev=ptr(save["n_uniq"]))
+            tp.QK[U].copy_(cqk.view(H, ekp))
+            qk_row = torch.where(tp.qidx < 0, torch.full_like(tp.qidx, U), tp.qidx)
+            _lib.call("pfo_attn_nbr_fwd_rows", ptr(tp.QK), ptr(qk_row), ptr(tp.T), d, ptr(tp.idx), ptr(tp.eidx),
+                      ptr(tp.dt), ptr(self.edge_feat), ptr(save["tw"]), ptr(save["tb"]), M, n, d, F, H, ekp,
+                      float(p_drop), self.seed, tp.step, ptr(self.step_ctr), ptr(tp.CAT), ldc, ptr(tp.P), ptr(tp.invalid))
+        else:
+            tp.QK = torch.empty(M, H, ekp, device=dev)  # qk_h = Wk_h^T q_h for both heads: one contraction over h_query
+            _linear(c, hq_ptr, ldc, None, ptr(Wqk), d, 0, ptr(cqk), ptr(tp.QK), hq, M, hq, d)
+            _lib.call("pfo_attn_nbr_fwd", ptr(tp.QK), ptr(tp.T), d, ptr(tp.idx), ptr(tp.eidx), ptr(tp.dt),
+                      ptr(self.edge_feat), ptr(save["tw"]), ptr(save["tb"]), M, n, d, F, H, ekp,
+                      float(p_drop), self.seed, tp.step, ptr(self.step_ctr), ptr(tp.CAT), ldc, ptr(tp.P), ptr(tp.invalid))
         tp.H1 = torch.empty(M, d, device=dev)       # relu(fc1([out_proj(attn) | h_query])), biases folded into Wc1T
         _linear(c, ptr(tp.CAT), ldc, None, ptr(Wc1T), d, 1, None, ptr(tp.H1), d, M, d, ldc, act=1)
         # the output is NOT kept on the tape: it is the autograd output, and holding it from the
@@ -779,7 +794,7 @@ class TGNStepFunction(torch.autograd.Function):
             embW = [next(it), next(it)]
         q_nodes, q_ts, n, B = batch["q_nodes"], batch["q_ts"], batch["n"], batch["B"]
         Q = q_nodes.shape[0]
-        save = dict(train=batch["train"], tw=tw, tb=tb)
+        save = dict(train=batch["train"], tw=tw, tb=tb, grad=need_grad)
         eng.step_id += 1
         if c.dropout > 0.0 and batch["train"]:
             eng.step_ctr.add_(16)
@@ -806,6 +821,7 @@ class TGNStepFunction(torch.autograd.Function):
         with _lib.nvtx_range("K3 node table (compaction + lazy memory update)"):
             tab = eng.node_table(id_lists, cellW, mlpW) if mlpW is not None else eng.node_table(id_lists, cellW)
         uniq, u_max, n_uniq = tab["uniq"], tab["u_max"], tab["n_uniq"]
+        save["n_uniq"] = n_uniq
         H0, Hnew, lu_u = tab["H0"], tab["Hnew"], tab["lu_u"]
 
         # 3. embeddings

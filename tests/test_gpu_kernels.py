@@ -628,3 +628,92 @@ def test_fold_attention_forward_and_adjoint(d, F, H):
     names = ["Wq", "Wk", "Wv", "b_in", "Wo", "bo", "W1", "b1", "tb"]
     for nm, a, b in zip(names, w, w64):
         assert rel_err(a.grad.cpu().numpy(), b.grad.cpu().numpy()) < 1e-6, nm
+
+
+# ------------------------------------------------------------------------------ K4 neighbour kernels
+def _nbr_restatement(QK, T, idx, eidx, dt, ef, tw, tb, d, F, H, ekp):
+    """fp64 torch restatement of the neighbour-level kernel (csrc/attention_kernels.cu header): per query and head,
+    x_j = [T[idx_j] | ef[eidx_j] | cos(dt_j w + b)], masked softmax of qk_h . x_j over the live slots,
+    XB_h = [sum_j p_j x_j (as h | e | te) | sum_j p_j | valid | one | 0..]."""
+    Q, n = idx.shape
+    live = idx >= 0
+    h = T[idx.clamp(min=0).long()]                                    # [Q, n, d]
+    e = ef[eidx.long()]                                               # [Q, n, F]
+    te = torch.cos(dt.unsqueeze(-1) * tw + tb)                         # [Q, n, d]
+    x = torch.cat([h, e, te], dim=-1) * live.unsqueeze(-1)             # [Q, n, 2d + F]
+    s = torch.einsum("qhk,qnk->qhn", QK[:, :, :2 * d + F], x)
+    s = s.masked_fill(~live.unsqueeze(1), float("-inf"))
+    any_live = live.any(dim=1)
+    p = torch.softmax(s, dim=-1)
+    p = torch.where(any_live.view(Q, 1, 1), p, torch.zeros_like(p))
+    xb = torch.einsum("qhn,qnk->qhk", p, x)
+    tail = torch.zeros(Q, H, ekp - (2 * d + F), dtype=xb.dtype, device=xb.device)
+    tail[:, :, 0] = p.sum(-1)
+    tail[:, :, 1] = any_live.to(xb.dtype).view(Q, 1)
+    tail[:, :, 2] = 1.0
+    return torch.cat([xb, tail], dim=-1), p
+
+
+@pytest.mark.parametrize("d,F,H,n", [(64, 1, 2, 10), (32, 3, 2, 7), (64, 1, 4, 20), (128, 2, 1, 5)])
+def test_attn_nbr_forward_backward_vs_torch(d, F, H, n):
+    """pfo_attn_nbr_fwd / _bwd against an fp64 torch restatement and its autograd (1e-5 of max-norm), the shared-row
+    entry point pfo_attn_nbr_fwd_rows bit-identical to per-query rows, strided feature tables and a strided XB."""
+    from pfotgnrec_b200 import _lib
+    from pfotgnrec_b200._lib import ptr
+    g = torch.Generator(device="cuda").manual_seed(d + F + H + n)
+    Q, R, NE = 1037, 400, 77
+    ekp = (2 * d + F + 3 + 3) // 4 * 4
+    ldt, ldxb = d + 4, H * ekp + d                                    # table rows and XB rows with a stride
+    Tfull = torch.randn(R, ldt, device=DEV, generator=g)
+    T = Tfull[:, :d]
+    QK = torch.randn(Q, H, ekp, device=DEV, generator=g) * 0.3
+    idx = torch.randint(-1, R, (Q, n), device=DEV, generator=g, dtype=torch.int32)
+    idx[5] = -1                                                       # a query without neighbours
+    idx[6, : n - 1] = -1
+    eidx = torch.randint(0, NE, (Q, n), device=DEV, generator=g, dtype=torch.int32)
+    dt = torch.rand(Q, n, device=DEV, generator=g) * 10               # small arguments: fp32 fmaf(dt, w, b) ~ the fp64 one
+    ef = torch.randn(NE, F, device=DEV, generator=g)
+    tw, tb = torch.rand(d, device=DEV, generator=g), torch.rand(d, device=DEV, generator=g)
+
+    def fwd(qk, rows=None):
+        XB = torch.full((Q, ldxb), 7.0, device=DEV)
+        P = torch.empty(Q, H, n, device=DEV)
+        inv = torch.empty(Q, dtype=torch.int32, device=DEV)
+        if rows is None:
+            _lib.call("pfo_attn_nbr_fwd", ptr(qk), ptr(Tfull), ldt, ptr(idx), ptr(eidx), ptr(dt), ptr(ef), ptr(tw), ptr(tb),
+                      Q, n, d, F, H, ekp, 0.0, 0, 0, None, ptr(XB), ldxb, ptr(P), ptr(inv))
+        else:
+            _lib.call("pfo_attn_nbr_fwd_rows", ptr(qk), ptr(rows), ptr(Tfull), ldt, ptr(idx), ptr(eidx), ptr(dt), ptr(ef),
+                      ptr(tw), ptr(tb), Q, n, d, F, H, ekp, 0.0, 0, 0, None, ptr(XB), ldxb, ptr(P), ptr(inv))
+        return XB, P, inv
+
+    XB, P, inv = fwd(QK)
+    leaf = [t.double().detach().requires_grad_(True) for t in (QK, T, tw, tb)]
+    ref, pref = _nbr_restatement(leaf[0], leaf[1], idx, eidx, dt.double(), ef.double(), leaf[2], leaf[3], d, F, H, ekp)
+    got = XB[:, :H * ekp].view(Q, H, ekp)
+    assert rel_err(got.cpu().numpy(), ref.detach().cpu().numpy()) < 1e-5
+    assert rel_err(P.cpu().numpy(), pref.detach().cpu().numpy()) < 1e-5
+    assert torch.equal(inv.bool(), ~(idx >= 0).any(dim=1))
+    assert float((XB[:, H * ekp:] - 7.0).abs().max()) == 0.0            # the h_query slot of the row is not touched
+    # shared rows: 50 distinct query operands, query q reads row q % 50
+    tab = QK[:50].contiguous()
+    rows = (torch.arange(Q, device=DEV) % 50).to(torch.int32)
+    XBr, Pr, _ = fwd(tab, rows)
+    XBe, Pe, _ = fwd(tab[rows.long()].contiguous())
+    assert torch.equal(XBr, XBe) and torch.equal(Pr, Pe)
+    # backward against autograd of the restatement
+    G = torch.randn(Q, ldxb, device=DEV, generator=g)
+    (ref * G[:, :H * ekp].view(Q, H, ekp).double()).sum().backward()
+    dQK = torch.empty(Q, H, ekp, device=DEV)
+    dT = torch.zeros(R, ldt, device=DEV)
+    gwb = torch.zeros(2 * d, device=DEV)
+    ws = torch.empty(int(_lib.query("pfo_attn_nbr_bwd_workspace_floats", d)), device=DEV)
+    _lib.call("pfo_attn_nbr_bwd", ptr(QK), ptr(G), ldxb, ptr(P), ptr(inv), ptr(Tfull), ldt, ptr(idx), ptr(eidx), ptr(dt),
+              ptr(ef), ptr(tw), ptr(tb), Q, n, d, F, H, ekp, 0.0, 0, 0, None, ptr(dQK), ptr(dT), ldt, ptr(gwb), 0, ptr(ws))
+    k = 2 * d + F
+    assert rel_err(dQK[:, :, :k].cpu().numpy(), leaf[0].grad[:, :, :k].cpu().numpy()) < 1e-5
+    assert float(dQK[:, :, k:].abs().max()) == 0.0
+    assert rel_err(dT[:, :d].cpu().numpy(), leaf[1].grad.cpu().numpy()) < 1e-5
+    assert float(dT[:, d:].abs().max()) == 0.0
+    assert rel_err(gwb[:d].cpu().numpy(), leaf[2].grad.cpu().numpy()) < 2e-5
+    assert rel_err(gwb[d:].cpu().numpy(), leaf[3].grad.cpu().numpy()) < 2e-5

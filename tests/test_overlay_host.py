@@ -82,7 +82,7 @@ def test_c_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
-    assert lib.pfo_abi_version() == 2
+    assert lib.pfo_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_product_path_never_imports_the_oracle():
@@ -239,3 +239,32 @@ def test_overlay_loads_a_reference_checkpoint(overlay):
         == tgn.embedding_module.memory.memory.data_ptr()
     assert torch.equal(st.memory, sd["memory.memory"]) and torch.equal(st.last_update, sd["memory.last_update"])
     assert float(sd["memory.memory"].abs().sum()) > 0
+
+
+def test_packed_batch_layout_round_trip():
+    """The one-buffer batch layout of the trainer (host staging buffer == static device buffers): fields are 16-byte
+    aligned, disjoint, in the same place for any portfolio length, and the views round-trip their columns."""
+    import torch
+    from pfotgnrec_b200.trainer import PfoTrainer
+    B = 37
+    lay_a, n_a = PfoTrainer._pack_layout(B, 5)
+    lay_b, n_b = PfoTrainer._pack_layout(B, 5 * B + 1)
+    assert n_a <= n_b and n_a % 16 == 0
+    spans = []
+    for k, (off, n, dt) in lay_a.items():
+        assert off % 16 == 0 and lay_b[k][0] == off          # offsets depend on B only: a short host buffer is a prefix
+        spans.append((off, off + n * torch.empty((), dtype=dt).element_size()))
+    spans.sort()
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:])) and spans[-1][1] <= n_a
+    assert max(lay_a, key=lambda k: lay_a[k][0]) == "port_items"
+    buf = torch.zeros(n_a, dtype=torch.uint8)
+    v = PfoTrainer._packed_views(buf, B, 5)
+    assert v["src"].dtype == torch.int32 and v["ts"].dtype == torch.float64 and v["port_ptr"].shape[0] == B + 1
+    v["ts"].copy_(torch.arange(B, dtype=torch.float64) * 1e9 + 0.5)
+    v["ev"].copy_(torch.arange(B, dtype=torch.int64) + (1 << 40))
+    v["port_items"].copy_(torch.arange(5, dtype=torch.int32))
+    big = torch.zeros(n_b, dtype=torch.uint8)
+    big[:n_a].copy_(buf)                                      # what train_step_host does with the device buffer
+    w = PfoTrainer._packed_views(big, B, 5 * B + 1)
+    assert torch.equal(w["ts"], v["ts"]) and torch.equal(w["ev"], v["ev"]) and torch.equal(w["port_items"][:5], v["port_items"])
+    assert int(w["src"].abs().sum()) == 0
