@@ -46,7 +46,11 @@ struct WgTmaArgs {
     int NB;                    // MMA N = accumulator columns
     int stages;
     int tmem_cols;
+    int fused;                 // reduce the slabs inside this launch (grid barrier) instead of a second kernel
+    float* dW; int64_t lddw; float* db; int accumulate;
 };
+
+__device__ unsigned g_wgrad_sync[2];   // arrivals / departures of the fused reduction's grid barrier (self-resetting)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -330,6 +334,57 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
                      :: "r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
     }
+    if (!p.fused) return;
+    // ---- fused slab reduction (replaces the second launch).  Grid barrier: the grid is at most one CTA per SM and a
+    // CTA holds an SM's shared memory alone, so once the grids ahead in the stream have drained every CTA of this one
+    // is resident (a dependent grid launched programmatically cannot start before all of these CTAs have -- they
+    // trigger it in their first instruction -- and it cannot take their place, it waits for this grid to complete).
+    // Then every CTA sums its share of the N x Kaug outputs over the S slabs in slab order (deterministic).  The two
+    // counters reset themselves: the last CTA to leave zeroes them for the next launch.  One instance at a time per
+    // device: launches are serialised on the caller's stream.
+    const unsigned n_ctas = gridDim.x * gridDim.y;
+    if (tid == 0) {
+        __threadfence();                                           // this CTA's partial is visible device-wide
+        atomicAdd(&g_wgrad_sync[0], 1u);
+        unsigned seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(&g_wgrad_sync[0]) : "memory");
+            if (seen < n_ctas) __nanosleep(32);
+        } while (seen < n_ctas);
+    }
+    __syncthreads();
+    {
+        const int total = p.N * p.Kaug;
+        const int cta = (int)(blockIdx.y * gridDim.x + blockIdx.x);
+        const int stride = (int)n_ctas * WG_THREADS;
+        for (int i = cta * WG_THREADS + tid; i < total; i += stride) {
+            const float* src = p.partial + i;
+            float s0 = 0.0f;
+            int y = 0;
+            for (; y + 4 <= p.S; y += 4) {                         // four loads in flight, one running sum (slab order)
+                const float a0 = __ldcg(src + (int64_t)y * total), a1 = __ldcg(src + (int64_t)(y + 1) * total);
+                const float a2 = __ldcg(src + (int64_t)(y + 2) * total), a3 = __ldcg(src + (int64_t)(y + 3) * total);
+                s0 = (((s0 + a0) + a1) + a2) + a3;
+            }
+            for (; y < p.S; ++y) s0 += __ldcg(src + (int64_t)y * total);
+            const int n = i / p.Kaug, k = i - n * p.Kaug;
+            if (k < p.K) {
+                float* d = p.dW + (int64_t)n * p.lddw + k;
+                *d = p.accumulate ? *d + s0 : s0;
+            } else if (p.db) {
+                p.db[n] = p.accumulate ? p.db[n] + s0 : s0;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned left = atomicAdd(&g_wgrad_sync[1], 1u);
+        if (left == n_ctas - 1) {                                  // everyone is past the spin: safe to reset
+            g_wgrad_sync[1] = 0u;
+            __threadfence();
+            g_wgrad_sync[0] = 0u;
+        }
+    }
 }
 
 // dW (+)= sum over the slabs, in a fixed order (deterministic).  A CTA owns 32 consecutive outputs; its 8 warps
@@ -380,6 +435,16 @@ int slabs_for(int64_t M, int n_ntiles) {
     if (S > cap) S = cap;
     if (S < 1) S = 1;
     return (int)S;
+}
+
+// PFO_WGRAD_FUSED=0 keeps the slab reduction as its own launch (the form of the earlier rounds)
+bool wgrad_fused_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("PFO_WGRAD_FUSED");
+        on = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return on != 0;
 }
 
 template <int PASSES>
@@ -435,8 +500,10 @@ PFO_API int pfo_wgrad_tf32(const float* G, int64_t ldg, const float* A, int64_t 
     const size_t smem = (size_t)stages * stage_bytes + fixed;
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid((unsigned)a.S, (unsigned)n_ntiles);
+    a.fused = wgrad_fused_enabled() && (int)(grid.x * grid.y) <= pfo_num_sms() ? 1 : 0;
+    a.dW = dW; a.lddw = lddw; a.db = db; a.accumulate = accumulate;
     int rc = passes == 3 ? launch_wg<3>(mg, ma, a, grid, smem, s) : launch_wg<1>(mg, ma, a, grid, smem, s);
-    if (rc) return rc;
+    if (rc || a.fused) return rc;
     const int total = N * a.Kaug;
     pfo_launch(wgrad_tma_reduce_kernel, (total + 31) / 32, 256, 0, s, workspace, a.S, N, K, a.Kaug, dW, lddw, db, accumulate);
     PFO_LAUNCH_CHECK();

@@ -37,6 +37,8 @@ how the slot / reply logic is covered by world_size-2 tests without a GPU (tests
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -451,7 +453,7 @@ class ShardedEngine(TGNEngine):
         super().__init__(cfg, state, node_feat, edge_feat, nf)
         self.req = _Scratch(self.n_global, node_feat.device)
         self.tag = "train"
-        self.overlap_store = True       # R4 beside the backward pass (side stream)
+        self.overlap_store = os.environ.get("PFO_SHARDED_OVERLAP", "1") != "0"     # R4 beside the backward pass (side stream)
         self._side_pending = False
 
     def _query_ids(self, groups, B):
@@ -509,9 +511,7 @@ class ShardedEngine(TGNEngine):
     def node_table_backward(self, tab, dH0, g_cell, mlpW=None, g_mlp=None, cellW=None):
         # R3: gradient rows -> owners along R2's slots, summed over requesters, then the cell backward of the base class
         own, ex, d = tab["own"], self.ex, self.cfg.d
-        if self._side_pending:          # the message exchange of the forward pass: its collective was issued first
-            self.join_side()
-            self._side_pending = False
+        self.join_store()               # the message exchange of the forward pass: its collective was issued first
         send = ex.buffer(tab["plan"], d, dtype=torch.float32)
         ex.scatter(tab["plan"], dH0, send, n_valid=tab["n_req"])
         got = ex.all_to_all(send, tab["plan"])
@@ -525,15 +525,10 @@ class ShardedEngine(TGNEngine):
         engine's side stream, beside the BPR loss and the backward pass, and is joined at the end of the backward."""
         B = batch["B"]
         qs = self.qslots_last                               # the query list starts with [src | dst]: their table rows
-        if self.overlap_store and batch["train"] and torch.is_grad_enabled():
-            cur = torch.cuda.current_stream(self.device)
-            s_slot, d_slot = qs[:B], qs[B:2 * B]
-            self.side.wait_stream(cur)
-            with torch.cuda.stream(self.side):
-                self._persist_and_store(tab, batch, emb, tw, tb, s_slot, d_slot)
-            self._side_pending = True
-        else:
-            self._persist_and_store(tab, batch, emb, tw, tb, qs[:B], qs[B:2 * B])
+        self._persist_and_store(tab, batch, emb, tw, tb, qs[:B], qs[B:2 * B])   # stream chosen by TGNEngine.store_state
+
+    def _store_overlaps(self):
+        return True                                         # R4's buffers belong to the stream that allocates them
 
     def _persist_and_store(self, tab, batch, emb, tw, tb, s_slot, d_slot):
         c, st, dev, G, ex = self.cfg, self.state, self.device, self.G, self.ex

@@ -245,6 +245,12 @@ class TGNEngine:
         # captured CUDA graph of the step draws fresh masks on every replay)
         self.step_ctr = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.side = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        # training steps of the trainers (a backward pass always follows the forward pass): persist + message store run
+        # on the side stream beside the loss and the attention backward -- nothing there reads the state they write --
+        # and are joined before the memory-updater backward.  Off by default: a caller of the drop-in TGN may read the
+        # memory between its forward and backward calls on the main stream.
+        self.overlap_store = False
+        self._side_pending = False
         if state is None:        # memory-less models still need the compaction scratch
             self.state = TGNState(self.n_nodes, ModelConfig(d=cfg.d, n_edge_feat=cfg.n_edge_feat), self.device)
 
@@ -391,7 +397,8 @@ class TGNEngine:
         q_ts = torch.cat([ts if g.shape[0] == B else ts.repeat_interleave(g.shape[0] // B) for g in groups])
         flat = self._pack(params)
         batch = dict(src=src, dst=dst, ts=ts, eidx=eidx, q_nodes=q_nodes, q_ts=q_ts, n=int(n_neighbors),
-                     B=B, train=bool(train), update_state=bool(update_state), q_ids=self._query_ids(groups, B))
+                     B=B, train=bool(train), update_state=bool(update_state), q_ids=self._query_ids(groups, B),
+                     grad=torch.is_grad_enabled())      # inside Function.forward grad mode is always off: ask here
         if state_batch is not None:
             if self.cfg.dst_emb_in_msg or self.cfg.src_emb_in_msg:
                 raise NotImplementedError("messages that carry embeddings (dyrep) need the embedded batch as state batch")
@@ -575,6 +582,25 @@ class TGNEngine:
                     relu_gate=ptr(M1), ld_gate=ld1)
             _wgrad(c, self.ws, ptr(dM1), ld1, ptr(tab["XG"]), c.rawp, None, u_max, hid, c.raw, ptr(gW1), c.raw, ptr(gb1),
                    m_dev=ptr(n_uniq))
+
+    def _store_overlaps(self):
+        """The state update can leave the main stream when it allocates nothing (the `mean` aggregator sorts)."""
+        return self.cfg.aggregator == "last"
+
+    def store_state(self, tab, batch, emb, tw, tb, overlap):
+        """`persist_and_store`, on the side stream when `overlap` (see `overlap_store`)."""
+        if overlap and self.overlap_store and self.side is not None and self._store_overlaps():
+            self.side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.side):
+                self.persist_and_store(tab, batch, emb, tw, tb)
+            self._side_pending = True
+        else:
+            self.persist_and_store(tab, batch, emb, tw, tb)
+
+    def join_store(self):
+        if self._side_pending:
+            self.join_side()
+            self._side_pending = False
 
     def persist_and_store(self, tab, batch, emb, tw, tb):
         """Persist the positives' memory from the lazy result, then build and store the new raw
@@ -779,7 +805,7 @@ class TGNStepFunction(torch.autograd.Function):
     def forward(ctx, eng: TGNEngine, batch, *flat):
         c, st, dev = eng.cfg, eng.state, eng.device
         d, F = c.d, c.n_edge_feat
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = any(ctx.needs_input_grad) and batch.get("grad", True)
         it = iter(flat)
         tw, tb = next(it), next(it)
         cellW = [next(it) for _ in range(4)] if c.use_memory else None
@@ -792,6 +818,7 @@ class TGNStepFunction(torch.autograd.Function):
             layerW = [[next(it) for _ in range(4)] for _ in range(c.n_layers)]
         elif c.embedding == "time":
             embW = [next(it), next(it)]
+        eng.join_store()                                # a forward pass whose backward never ran left its store pending
         q_nodes, q_ts, n, B = batch["q_nodes"], batch["q_ts"], batch["n"], batch["B"]
         Q = q_nodes.shape[0]
         save = dict(train=batch["train"], tw=tw, tb=tb, grad=need_grad)
@@ -852,7 +879,7 @@ class TGNStepFunction(torch.autograd.Function):
         # 4. persist positives, then build + store the new raw messages (tgn.py:185-206)
         if c.use_memory and batch["update_state"]:
             with _lib.nvtx_range("K2 persist + message store"):
-                eng.persist_and_store(tab, sb, emb, tw, tb)
+                eng.store_state(tab, sb, emb, tw, tb, overlap=need_grad and batch["train"])
         out = emb
         if c.use_memory and c.dyrep:    # dyrep returns the updated memory rows (tgn.py:211-215, :322-325)
             out = torch.empty(Q, d, device=dev)
@@ -953,6 +980,7 @@ class TGNStepFunction(torch.autograd.Function):
             eng.join_side()
             for g in g_layers:
                 g_tb.add_(g[5])
+        eng.join_store()                                # the forward pass's state update (side stream) ends here at the latest
         if sink is not None:                            # gradients are in place: nothing for autograd to route
             return (None, None) + (None,) * len(flat)
         return (None, None) + tuple(grads)
