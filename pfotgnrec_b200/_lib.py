@@ -102,7 +102,7 @@ _LAUNCHES_PER_CALL = {"pfo_compact_nodes": 1, "pfo_fold_attention_fwd": 2, "pfo_
                       "pfo_attn_nbr_bwd_workspace_floats": 0}
 
 
-_WGRAD_FUSED = os.environ.get("PFO_WGRAD_FUSED", "1")[:1] != "0"
+_WGRAD_FUSED = os.environ.get("PFO_WGRAD_FUSED", "0")[:1] == "1"
 
 
 class PfoError(RuntimeError):
@@ -158,7 +158,7 @@ def call(name, *args):
     rc = getattr(lib, name)(*args, stream())
     if name == "pfo_compact_nodes":          # one CTA for small id spaces (<= 1024 bitmap words), three kernels beyond
         LAUNCHES += 1 if (int(args[1]) + 31) // 32 <= 1024 else 3
-    elif name == "pfo_wgrad_tf32":           # the slab reduction rides in the same launch unless PFO_WGRAD_FUSED=0
+    elif name == "pfo_wgrad_tf32":           # the slab reduction is a second launch unless PFO_WGRAD_FUSED=1
         LAUNCHES += 1 if _WGRAD_FUSED else 2
     else:
         LAUNCHES += _LAUNCHES_PER_CALL.get(name, 1)

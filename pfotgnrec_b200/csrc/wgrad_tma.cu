@@ -437,12 +437,16 @@ int slabs_for(int64_t M, int n_ntiles) {
     return (int)S;
 }
 
-// PFO_WGRAD_FUSED=0 keeps the slab reduction as its own launch (the form of the earlier rounds)
+// PFO_WGRAD_FUSED=1 reduces the slabs inside the contraction launch.  Measured SLOWER than the second launch at the
+// bench shapes (step 0.872 ms against 0.845 ms, 220 us against 190 us in the five weight gradients of a step,
+// profiles/r2_bench_wgrad_fused.json): every CTA idles at the barrier until the slowest slab is done and the reduction
+// then runs on 148 CTAs x 320 threads instead of up to 1 164 CTAs.  Parity-green (the GPU suite ran with it), kept as
+// an opt-in.
 bool wgrad_fused_enabled() {
     static int on = -1;
     if (on < 0) {
         const char* e = getenv("PFO_WGRAD_FUSED");
-        on = (e != nullptr && e[0] == '0') ? 0 : 1;
+        on = (e != nullptr && e[0] == '1') ? 1 : 0;
     }
     return on != 0;
 }

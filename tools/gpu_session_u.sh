@@ -1,0 +1,20 @@
+#!/bin/bash
+# round-2 session U (2 GPUs): sharded == single GPU with R4 on the side stream, 2-GPU lines with / without the overlap
+mkdir -p gpurun_out
+run() { timeout $1 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $2 "${@:3}"; }
+export PFO_HANG_DUMP_S=140
+for m in ours tgat; do
+  run 170 $((29610 + RANDOM % 80)) tools/check_sharded.py $m > gpurun_out/u_check_$m.log 2>&1; echo "rc=$?" >> gpurun_out/u_check_$m.log
+  grep -a "single GPU\|Error\|rc=\|File \"/tmp/code" gpurun_out/u_check_$m.log | tail -6
+done
+for ov in 1 0; do
+  PFO_SHARDED_OVERLAP=$ov run 180 $((29700 + RANDOM % 80)) bench.py --gpus 2 --steps 30 --warmup 5 --no-cpu-baseline --large-bs 0 --eval-steps 4 > gpurun_out/u_bench_2gpu_ov$ov.json 2> gpurun_out/u_bench_2gpu_ov$ov.err
+  tail -c 200 gpurun_out/u_bench_2gpu_ov$ov.err
+  python - $ov <<'PY'
+import json, sys
+try:
+    b=json.loads(open('gpurun_out/u_bench_2gpu_ov%s.json' % sys.argv[1]).read().strip().split('\n')[-1])
+    print('x2 overlap', sys.argv[1], b['value'], b['ms_per_step'], b['e2e']['value'], b['eval_users_per_sec'], b['config'].get('exchange_transport'))
+except Exception as e: print('no line', e)
+PY
+done
