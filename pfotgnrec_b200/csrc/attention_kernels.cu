@@ -608,20 +608,24 @@ int launch_fwd(const NbrArgs& a, cudaStream_t s) {
         attr_set = true;
     }
     const size_t smem = (size_t)4 * a.n * (2 * a.d + 32) * sizeof(float);      // 4 warps x n stash rows
-    int per_sm = (int)((200 * 1024) / (smem + 1024));
-    if (per_sm > 5) per_sm = 5;
-    if (per_sm < 1) per_sm = 1;
-    pfo_launch(attn_nbr_fwd_kernel<DPL, NH>, pfo_grid(a.Q * 32, 128, 2 * per_sm), 128, smem, s, a);
+    static const int env_waves = [] { const char* e = getenv("PFO_ATTN_FWD_CTAS"); return e ? atoi(e) : 0; }();
+    // one resident wave (registers allow 6 CTAs per SM at d = 64, 2 heads); PFO_ATTN_FWD_CTAS overrides the CTAs per SM
+    const int per_sm = env_waves > 0 ? env_waves : pfo_resident(attn_nbr_fwd_kernel<DPL, NH>, 128, smem);
+    pfo_launch(attn_nbr_fwd_kernel<DPL, NH>, pfo_grid(a.Q * 32, 128, per_sm), 128, smem, s, a);
     PFO_LAUNCH_CHECK();
 }
 
 template <int DPL, int NH>
-int launch_bwd(const NbrArgs& a, int grid, size_t smem, cudaStream_t s) {
+int launch_bwd(const NbrArgs& a, int& grid, size_t smem, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(attn_nbr_bwd_kernel<DPL, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
+    static const int env_ctas = [] { const char* e = getenv("PFO_ATTN_BWD_CTAS"); return e ? atoi(e) : 0; }();
+    const int per_sm = env_ctas > 0 ? env_ctas : pfo_resident(attn_nbr_bwd_kernel<DPL, NH>, 128, smem);
+    const int cap = pfo_num_sms() * per_sm;          // one resident wave; `grid` is the caller's bound (workspace rows)
+    if (grid > cap) grid = cap;
     pfo_launch(attn_nbr_bwd_kernel<DPL, NH>, grid, 128, smem, s, a);
     PFO_LAUNCH_CHECK();
 }
@@ -637,7 +641,7 @@ int dispatch_fwd(const NbrArgs& a, cudaStream_t s) {
     }
 }
 template <int DPL>
-int dispatch_bwd(const NbrArgs& a, int grid, size_t smem, cudaStream_t s) {
+int dispatch_bwd(const NbrArgs& a, int& grid, size_t smem, cudaStream_t s) {
     switch (a.H) {
         case 1: return launch_bwd<DPL, 1>(a, grid, smem, s);
         case 2: return launch_bwd<DPL, 2>(a, grid, smem, s);
@@ -705,8 +709,8 @@ PFO_API int pfo_attn_nbr_bwd(const float* QK, const float* dXB, int64_t lddxb, c
     cudaStream_t s = (cudaStream_t)stream;
     const int wpb = 4;
     const size_t smem = ((size_t)wpb * n * (3 * d + 32) + (size_t)wpb * 2 * d) * sizeof(float);
-    int grid = pfo_grid(Q * 32, 128, 4);
-    const int max_grid = 2 * 148 * 4;
+    int grid = pfo_grid(Q * 32, 128, 8);             // upper bound: the launcher caps it at one resident wave
+    const int max_grid = 2 * 148 * 4;                // rows of the partial workspace
     if (grid > max_grid) grid = max_grid;
     if (ldt % 4 != 0 || lddxb % 4 != 0 || lddt % 4 != 0 || ekp % 4 != 0 || !aligned16(T) || !aligned16(QK) ||
         !aligned16(dXB) || !aligned16(dQK) || !aligned16(dT) || ldt > kMaxRowFloats || lddt > kMaxRowFloats)
@@ -726,7 +730,7 @@ PFO_API int pfo_bpr(const float* eu, const float* ep, const float* en, int B, in
                     float* du, float* dp, float* dn, float* loss, float grad_scale, float* workspace, void* stream) {
     if (B <= 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    int grid = pfo_grid((int64_t)B * 32, 256, 8);   // one warp per interaction when they fit (latency-bound, tiny)
+    int grid = pfo_grid((int64_t)B * 32, 256, pfo_resident(bpr_kernel, 256, 0));   // one warp per interaction when they fit
     if (grid > 1024) grid = 1024;
     pfo_launch(bpr_kernel, grid, 256, 0, s, eu, ep, en, B, k, d, du, dp, dn, workspace, grad_scale);
     // loss = sum over blocks of per-block means/B contributions: reduce rows=grid, cols=1

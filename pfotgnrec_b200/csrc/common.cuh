@@ -30,6 +30,24 @@ static inline int pfo_grid(int64_t work, int block, int ctas_per_sm) {
     return (int)(need < cap ? need : cap);
 }
 
+// CTAs of `kernel` resident per SM at this block size and dynamic shared-memory size (occupancy API; a few cached
+// entries).  A grid-stride kernel whose grid is a guessed multiple of the SM count runs a short second wave when fewer
+// CTAs fit than guessed (10 CTAs per SM asked, 6 resident: the last 4 run at two thirds of the occupancy); sizing the
+// grid to exactly one resident wave keeps every SM at full occupancy until the end.
+template <typename... KArgs>
+static inline int pfo_resident(void (*kernel)(KArgs...), int block, size_t smem) {
+    struct Entry { const void* k; int block; size_t smem; int occ; };
+    static Entry cache[16];
+    static int used = 0;
+    const void* kp = reinterpret_cast<const void*>(kernel);
+    for (int i = 0; i < used; ++i)
+        if (cache[i].k == kp && cache[i].block == block && cache[i].smem == smem) return cache[i].occ;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem) != cudaSuccess || occ < 1) occ = 1;
+    if (used < 16) cache[used++] = Entry{kp, block, smem, occ};
+    return occ;
+}
+
 // ---- programmatic dependent launch.  A step is ~60 kernels of 5-200 us chained through one stream (one CUDA graph):
 // with plain launches every kernel boundary costs the full drain -> schedule -> ramp-up gap.  Every kernel of this
 // library is therefore launched with the programmatic-stream-serialization attribute and begins with

@@ -530,7 +530,7 @@ int launch_tma(const CUtensorMap& map, const TmaLinArgs& a, dim3 grid, size_t sm
 }
 
 long long* g_linear_trace = nullptr;
-int g_linear_min_stages = 2;
+int g_linear_min_stages = 5;      // swept 2..5 at the bench shapes after the MMA-issue fix: 0.841 -> 0.831 ms/step
 int g_linear_dbg = 0;
 
 }  // namespace
@@ -592,7 +592,8 @@ PFO_API int pfo_linear_tf32(const float* A, int64_t lda, const int32_t* a_idx, c
     // covered (Little: ~100 KB in flight per SM), so N is cut into more column tiles -- whose CTAs re-read the row
     // tile from L2 -- until `want` stages fit beside the resident weight slice; 3-pass mode also needs
     // 2 * NT + 32 * stages <= 512 TMEM columns.
-    const int want = g_linear_min_stages;
+    static const int env_want = [] { const char* e = getenv("PFO_LINEAR_MIN_STAGES"); return e ? atoi(e) : 0; }();
+    const int want = env_want > 0 ? env_want : g_linear_min_stages;
     int n_ntiles = (N + 255) / 256;
     int NT, stages;
     for (;;) {

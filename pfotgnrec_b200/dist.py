@@ -453,7 +453,10 @@ class ShardedEngine(TGNEngine):
         super().__init__(cfg, state, node_feat, edge_feat, nf)
         self.req = _Scratch(self.n_global, node_feat.device)
         self.tag = "train"
-        self.overlap_store = os.environ.get("PFO_SHARDED_OVERLAP", "1") != "0"     # R4 beside the backward pass (side stream)
+        # R4 beside the loss and the attention backward (side stream): parity-green on 2 GPUs, but measured SLOWER there
+        # (1.066 against 1.038 ms/step, profiles/r2_bench_2gpu_sharded_r4_overlap.json: the exchange and the backward
+        # kernels compete for the same SMs and the join sits on the critical path), so it is an opt-in
+        self.overlap_store = os.environ.get("PFO_SHARDED_OVERLAP", "0") == "1"
         self._side_pending = False
 
     def _query_ids(self, groups, B):

@@ -212,7 +212,7 @@ class PfoTrainer:
                                std_time_shift_dst=sd, use_source_embedding_in_message=False,
                                gemm_mode=tc.gemm_mode, **self._tgn_extra(), **kw).to(self.device)
         self._bind_engine()
-        if os.environ.get("PFO_STORE_OVERLAP", "1") != "0" and type(self.tgn._get_engine()).__name__ == "TGNEngine":
+        if os.environ.get("PFO_STORE_OVERLAP", "1") != "0" and type(self) is PfoTrainer:
             # every training step of this loop runs its backward right after the forward: the state update of the
             # forward pass may leave the main stream (engine.TGNEngine.store_state)
             self.tgn._get_engine().overlap_store = True
