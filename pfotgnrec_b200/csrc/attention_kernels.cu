@@ -609,8 +609,10 @@ int launch_fwd(const NbrArgs& a, cudaStream_t s) {
     }
     const size_t smem = (size_t)4 * a.n * (2 * a.d + 32) * sizeof(float);      // 4 warps x n stash rows
     static const int env_waves = [] { const char* e = getenv("PFO_ATTN_FWD_CTAS"); return e ? atoi(e) : 0; }();
-    // one resident wave (registers allow 6 CTAs per SM at d = 64, 2 heads); PFO_ATTN_FWD_CTAS overrides the CTAs per SM
-    const int per_sm = env_waves > 0 ? env_waves : pfo_resident(attn_nbr_fwd_kernel<DPL, NH>, 128, smem);
+    // two resident waves (the occupancy API says 6 CTAs per SM at d = 64, 2 heads).  Measured at bs 8192, CTAs per SM
+    // -> step: 5 -> 0.863 ms, 6 -> 0.838, 10 -> 0.837, 12 -> 0.831 (finer slices of the query list even out the tail);
+    // PFO_ATTN_FWD_CTAS overrides the CTAs per SM
+    const int per_sm = env_waves > 0 ? env_waves : 2 * pfo_resident(attn_nbr_fwd_kernel<DPL, NH>, 128, smem);
     pfo_launch(attn_nbr_fwd_kernel<DPL, NH>, pfo_grid(a.Q * 32, 128, per_sm), 128, smem, s, a);
     PFO_LAUNCH_CHECK();
 }
@@ -730,7 +732,8 @@ PFO_API int pfo_bpr(const float* eu, const float* ep, const float* en, int B, in
                     float* du, float* dp, float* dn, float* loss, float grad_scale, float* workspace, void* stream) {
     if (B <= 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    int grid = pfo_grid((int64_t)B * 32, 256, pfo_resident(bpr_kernel, 256, 0));   // one warp per interaction when they fit
+    int grid = pfo_grid((int64_t)B * 32, 256, 8);   // one warp per interaction when they fit (latency-bound, tiny; one
+                                                    // resident wave -- 5 CTAs per SM -- measured slower: 27 against 21 us)
     if (grid > 1024) grid = 1024;
     pfo_launch(bpr_kernel, grid, 256, 0, s, eu, ep, en, B, k, d, du, dp, dn, workspace, grad_scale);
     // loss = sum over blocks of per-block means/B contributions: reduce rows=grid, cols=1
