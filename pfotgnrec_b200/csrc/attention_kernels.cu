@@ -609,10 +609,10 @@ int launch_fwd(const NbrArgs& a, cudaStream_t s) {
     }
     const size_t smem = (size_t)4 * a.n * (2 * a.d + 32) * sizeof(float);      // 4 warps x n stash rows
     static const int env_waves = [] { const char* e = getenv("PFO_ATTN_FWD_CTAS"); return e ? atoi(e) : 0; }();
-    // two resident waves (the occupancy API says 6 CTAs per SM at d = 64, 2 heads).  Measured at bs 8192, CTAs per SM
-    // -> step: 5 -> 0.863 ms, 6 -> 0.838, 10 -> 0.837, 12 -> 0.831 (finer slices of the query list even out the tail);
-    // PFO_ATTN_FWD_CTAS overrides the CTAs per SM
-    const int per_sm = env_waves > 0 ? env_waves : 2 * pfo_resident(attn_nbr_fwd_kernel<DPL, NH>, 128, smem);
+    // three resident waves (the occupancy API says 6 CTAs per SM at d = 64, 2 heads).  Measured at bs 8192, CTAs per
+    // SM -> step: 5 -> 0.863 ms, 6 -> 0.838, 10 -> 0.837, 12 -> 0.831 / 0.829, 18 -> 0.822 (finer slices of the query
+    // list even out the tail; profiles/r2_knob_sweeps.txt); PFO_ATTN_FWD_CTAS overrides the CTAs per SM
+    const int per_sm = env_waves > 0 ? env_waves : 3 * pfo_resident(attn_nbr_fwd_kernel<DPL, NH>, 128, smem);
     pfo_launch(attn_nbr_fwd_kernel<DPL, NH>, pfo_grid(a.Q * 32, 128, per_sm), 128, smem, s, a);
     PFO_LAUNCH_CHECK();
 }

@@ -32,7 +32,7 @@ def main(path, out):
         a = agg.setdefault(ep, {"launches": 0, "bytes": 0.0, "us": 0.0})
         a["launches"] += 1; a["bytes"] += b; a["us"] += t
     res = {k: {"dram_bytes_per_launch": v["bytes"] / v["launches"], "ncu_us_per_launch": v["us"] / v["launches"],
-               "launches_profiled": v["launches"], "source": "profiles/r2_ncu_full_summary.txt (ncu --set full --clock-control none, one eager training step after warm-up, bs 8192, final round-2 kernels)"} for k, v in agg.items()}
+               "launches_profiled": v["launches"], "source": "profiles/r2f_ncu_full_summary.txt (ncu --set full --clock-control none over the kernels of the C-ABI entry points, one eager training step after warm-up, bs 8192, final round-2 kernels)"} for k, v in agg.items()}
     json.dump(res, open(out, "w"), indent=1, sort_keys=True)
     for k, v in sorted(res.items()):
         print(f"{k:24s} {v['dram_bytes_per_launch'] / 1e6:9.2f} MB/launch {v['ncu_us_per_launch']:8.1f} us x{v['launches_profiled']}")
