@@ -219,7 +219,8 @@ int pfo_adam_flat(float* params, const float* grads, float* exp_avg, float* exp_
 
 /* ---- TimeEncode.forward alone --- model/time_encoding.py:17-25: out_cos[m, c] = cos(fmaf(t[m], w[c], b[c])) (fmaf ==
  * nn.Linear(1, d) bit for bit), out_sin optional.  mode 0 / 1 = the fp64 quadrant reduction the fused kernels use
- * (any |x| < 2^44), 2 = fp32 Cody-Waite reduction (|x| < 2^17; kept for the comparison test). */
+ * (any |x| < 2^44), 2 = fp32 Cody-Waite reduction (|x| < 2^17; kept for the comparison test), 3 = the cosine-only
+ * half-turn reduction + one even polynomial of the neighbour forward kernel (any |x| < 2^44; out_sin as in mode 0). */
 int pfo_time_encode(const float* t, const float* w, const float* b, int64_t M, int d, int mode,
                     float* out_cos, float* out_sin, void* stream);
 int pfo_reduce_partials(const float* partial, int rows, int cols, float* out, int accumulate, void* stream);

@@ -214,7 +214,7 @@ attn_nbr_fwd_kernel(const NbrArgs p) {
                 float xt[DPL];
 #pragma unroll
                 for (int i = 0; i < DPL; ++i)
-                    xt[i] = pfo_cosf(fmaf(dtj[u], tw[i], tb[i]));   // full-range, never __cosf (SURVEY hard part 1)
+                    xt[i] = pfo_cosf_half(fmaf(dtj[u], tw[i], tb[i]));   // full-range, never __cosf (SURVEY hard part 1)
                 float* st = stash + (j0 + u) * SW;
                 st_cols<DPL>(st + c0, xh[u]);
                 st_cols<DPL>(st + d + c0, xt);

@@ -381,6 +381,24 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tmA, const TmaLinArgs p) {
             const float brs = p.bias_row_scale ? p.bias_row_scale[mc * p.ld_brs] : 1.0f;
             for (int c0 = half * 16; c0 < NT; c0 += 32) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_stride + (uint32_t)c0;
+                const int nb = n0 + c0 + ch * 4;
+                const bool full4 = p.vec_ok && nb + 3 < p.N;
+                // the relu gate and the accumulate operand of the slab's four row groups are loaded up front: inside
+                // the store loop each load sat right in front of its store, four dependent DRAM round trips per
+                // slab (the gated dgrad launch took 26 us against 14 us for the ungated one of the same shape)
+                float4 g4[4], o4[4];
+                if (full4 && (p.relu_gate || p.accumulate)) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int64_t m = m0 + i * 8 + r_sub;
+                        g4[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+                        o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (m < M) {
+                            if (p.relu_gate) g4[i] = *reinterpret_cast<const float4*>(p.relu_gate + m * p.ld_gate + nb);
+                            if (p.accumulate) o4[i] = *reinterpret_cast<const float4*>(p.C + m * p.ldc + nb);
+                        }
+                    }
+                }
                 uint32_t r[16];
                 tmem_ld16(taddr, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -399,9 +417,7 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tmA, const TmaLinArgs p) {
                     *reinterpret_cast<float4*>(dst + (((uint32_t)j ^ sw) << 4)) = v;
                 }
                 __syncwarp();
-                const int nb = n0 + c0 + ch * 4;
                 if (nb < p.N) {
-                    const bool full4 = p.vec_ok && nb + 3 < p.N;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int row = i * 8 + r_sub;
@@ -412,16 +428,12 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tmA, const TmaLinArgs p) {
                         float* cp = p.C + m * p.ldc + nb;
                         if (full4) {
                             if (p.relu_gate) {
-                                const float4 g = *reinterpret_cast<const float4*>(p.relu_gate + m * p.ld_gate + nb);
-                                if (g.x <= 0.f) v[0] = 0.f;
-                                if (g.y <= 0.f) v[1] = 0.f;
-                                if (g.z <= 0.f) v[2] = 0.f;
-                                if (g.w <= 0.f) v[3] = 0.f;
+                                if (g4[i].x <= 0.f) v[0] = 0.f;
+                                if (g4[i].y <= 0.f) v[1] = 0.f;
+                                if (g4[i].z <= 0.f) v[2] = 0.f;
+                                if (g4[i].w <= 0.f) v[3] = 0.f;
                             }
-                            if (p.accumulate) {
-                                const float4 o = *reinterpret_cast<const float4*>(cp);
-                                v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
-                            }
+                            if (p.accumulate) { v[0] += o4[i].x; v[1] += o4[i].y; v[2] += o4[i].z; v[3] += o4[i].w; }
                             *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
                         } else {
 #pragma unroll

@@ -723,7 +723,8 @@ PFO_API int pfo_time_embedding_bwd(const int32_t* q_nodes, int64_t Q, int d, con
 
 // TimeEncode.forward on its own (model/time_encoding.py:17-25): out[m, c] = cos(fmaf(t[m], w[c], b[c])), optionally the
 // sine too.  mode 0 / 1 = the fp64 quadrant reduction of the fused kernels (pfo_math.cuh), 2 = fp32 Cody-Waite reduction
-// (only valid for |argument| < 2^17): the parity tests compare the two reductions through this entry point.
+// (only valid for |argument| < 2^17), 3 = the cosine-only half-turn form of the neighbour forward kernel (sine as in
+// mode 0): the parity tests compare the reductions through this entry point.
 static __global__ void time_encode_kernel(const float* __restrict__ t, const float* __restrict__ w,
                                           const float* __restrict__ b, int64_t M, int d, int mode,
                                           float* __restrict__ out_cos, float* __restrict__ out_sin) {
@@ -740,6 +741,7 @@ static __global__ void time_encode_kernel(const float* __restrict__ t, const flo
             if (mode == 1) pfo_sincosf_f64(x, &sn, &cs);
             else if (mode == 2) pfo_sincosf_f32(x, &sn, &cs);
             else pfo_sincosf(x, &sn, &cs);
+            if (mode == 3) cs = pfo_cosf_half(x);      // the cosine-only form of the neighbour forward kernel
             if (c < d) {
                 out_cos[m * d + c] = cs;
                 if (out_sin) out_sin[m * d + c] = sn;
@@ -751,7 +753,7 @@ static __global__ void time_encode_kernel(const float* __restrict__ t, const flo
 PFO_API int pfo_time_encode(const float* t, const float* w, const float* b, int64_t M, int d, int mode,
                             float* out_cos, float* out_sin, void* stream) {
     if (M <= 0) return 0;
-    if (d <= 0 || mode < 0 || mode > 2) return (int)cudaErrorInvalidValue;
+    if (d <= 0 || mode < 0 || mode > 3) return (int)cudaErrorInvalidValue;
     pfo_launch(time_encode_kernel, pfo_grid(M * 32, 256, 8), 256, 0, (cudaStream_t)stream, t, w, b, M, d, mode, out_cos, out_sin);
     PFO_LAUNCH_CHECK();
 }

@@ -54,6 +54,28 @@ __device__ __forceinline__ void pfo_sincosf_f32(float x, float* s, float* c) {
     pfo_sincos_poly(r, q, s, c);
 }
 
+// Cosine alone (the neighbour forward kernel needs no sine): half-turn reduction k = rint(x / pi), r = x - k pi in
+// [-pi/2, pi/2] with the same fp64 magic-number rounding and hi / lo split, then ONE even polynomial of degree 10 in r
+// (interpolated at the Chebyshev nodes of r^2; 2.2e-10 from cos on the interval, 1.1e-7 with its fp32 Horner rounding --
+// the class of the quadrant form, tests/test_gpu_kernels.py::test_time_encode_cos_paths) and the sign of (-1)^k as an
+// XOR.  14 instructions against ~24 for the sine / cosine pair + quadrant selects.
+__device__ __forceinline__ float pfo_cosf_half(float x) {
+    const double xd = (double)x;
+    const double t = fma(xd, 0.31830988618379067154, 6755399441055744.0);    // 1/pi, 1.5 * 2^52
+    const unsigned sign = ((unsigned)__double2loint(t)) << 31;
+    const double kd = t - 6755399441055744.0;
+    double r = fma(-kd, 3.14159265358979311600e+00, xd);                      // pi (hi)
+    r = fma(-kd, 1.22464679914735317723e-16, r);                              // pi (lo)
+    const float rf = (float)r;
+    const float u = rf * rf;
+    float c = fmaf(u, -2.604992346277868e-07f, 2.476006920915097e-05f);
+    c = fmaf(u, c, -0.0013888359535485506f);
+    c = fmaf(u, c, 0.04166663438081741f);
+    c = fmaf(u, c, -0.5f);
+    c = fmaf(u, c, 1.0f);
+    return __uint_as_float(__float_as_uint(c) ^ sign);
+}
+
 __device__ __forceinline__ void pfo_sincosf(float x, float* s, float* c) { pfo_sincosf_f64(x, s, c); }
 
 __device__ __forceinline__ float pfo_cosf_f64(float x) { float s, c; pfo_sincosf_f64(x, &s, &c); return c; }

@@ -157,12 +157,16 @@ def test_time_encode_cos_paths():
     assert float((c64.double() - torch.cos(x)).abs().max()) < 2e-7
     assert float((s64.double() - torch.sin(x)).abs().max()) < 2e-7
     assert float((c32.double() - torch.cos(x)).abs().max()) < 2e-7
+    ch, sh = run(t_small, 3)                              # cosine-only half-turn form (neighbour forward kernel)
+    assert float((ch.double() - torch.cos(x)).abs().max()) < 2e-7 and torch.equal(sh, s64)
+    assert float((ch - c64).abs().max()) <= 3.0 * ulp
     sign = torch.where(torch.rand(20000, device=DEV, generator=g) < 0.5, -1.0, 1.0)
     t_big = sign * (1.0e9 + torch.rand(20000, device=DEV, generator=g) * 1.0e10)
     cb, sb = run(t_big, 0)
     xb = torch.addcmul(b.double(), t_big.double()[:, None], w.double()).float().double()
     assert float((cb.double() - torch.cos(xb)).abs().max()) < 2e-7
     assert float((sb.double() - torch.sin(xb)).abs().max()) < 2e-7
+    assert float((run(t_big, 3)[0].double() - torch.cos(xb)).abs().max()) < 2e-7
     # the standalone module forward (containers.TimeEncode) goes through the same entry point
     from pfotgnrec_b200.containers import TimeEncode
     te = TimeEncode(d).to(DEV)
