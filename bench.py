@@ -524,9 +524,7 @@ def main():
         dt = 0.0
         for hb in host[1:]:
             flush.fill_(1)                           # same L2 flush as the device-timed loop, outside the step's clock
-            if world > 1:
-                torch.distributed.barrier()          # every rank enters the step together (the step's exchanges would
-            torch.cuda.synchronize()                 # otherwise charge a rank for its peers' flush)
+            torch.cuda.synchronize()
             t0 = time.perf_counter()                 # host clock around the call a user makes: H2D of the batch ->
             l = tr.train_step_host(hb)               # step -> D2H of the loss (the read synchronises the device)
             _ = float(l.item())
