@@ -354,8 +354,12 @@ PFO_API int pfo_mv_select(const int64_t* event_ids, const int32_t* day_idx, cons
     // candidate rows in shared memory: kWarps x (K + 1) rows of (T | 1) doubles (<= 34 KB, inside the default 48 KB
     // with the 10 KB of static tables); the grid is capped at the CTAs that are resident at once
     const size_t smem = (size_t)kWarps * (K + 1) * (n_returns | 1) * sizeof(double);
-    int per_sm = (int)((200 * 1024) / (smem + 10 * 1024 + 1024));
-    if (per_sm > 8) per_sm = 8;
+    // exactly the CTAs that are resident (occupancy API: 7 per SM at K = 20, T = 29).  A guessed 6 left 3 552 warps for
+    // 8 192 interactions -- three rounds for a third of the warps -- where 7 x 148 x 4 = 4 144 warps need two (the
+    // final capture shows the staging took the long-scoreboard stalls from 7.9 to 1.9 cycles per issue, but the
+    // launch time did not move: profiles/r2f_stall_reasons.txt)
+    int per_sm = pfo_resident(mv_select_kernel, kWarps * 32, smem);
+    if (const char* e = getenv("PFO_MV_CTAS")) { const int v = atoi(e); if (v > 0) per_sm = v; }    // tools/k5_time.py
     pfo_launch(mv_select_kernel, pfo_grid((int64_t)B * 32, kWarps * 32, per_sm), kWarps * 32, smem, (cudaStream_t)stream, a);
     PFO_LAUNCH_CHECK();
 }
